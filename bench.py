@@ -1,0 +1,401 @@
+#!/usr/bin/env python
+"""bench.py -- pages/s of the EAST decode + LANMS + box filters + crop/resize/pad hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the hot path over one batch of synthetic pages PER GPU (pages are independent, so
+ranks never exchange data: weak scaling, no collective on the data path; torch.distributed is used only
+for the barrier and the max-over-ranks of the timings).
+
+Workload (BASELINE.json configs[2]): 64 synthetic 2048x2048 pages per GPU, ~2000 word quads per page
+(score map 512x512, geometry 8x512x512, page image 2048x2048x3 u8), TRBA 32x128 crop batch output.
+
+One JSON line on rank 0:
+  value    pages/s, inputs resident in HBM, device-timed (CUDA events on the launch stream), max over ranks
+  e2e      pages/s through the C-ABI call with HOST buffers (pinned): H2D of maps+pages, the path, D2H of the
+           boxes / counts / crop list, every step (the crop batch stays on the device for the recogniser, as
+           the reference leaves it on `self.device`, recognizers/_trba/__init__.py:288)
+  roofline the stage that dominates the step time, algorithmic bytes / its CUDA-event time
+  stages   every stage: ms per step, algorithmic bytes, GB/s, fraction of the measured HBM peak
+  cpu_baseline  the C oracle (a port of the reference's algorithm) on a bounded sample, 1 host thread
+--impl reference: the CPU implementation (oracle port; the reference itself is numpy/numba/cv2 Python that
+needs packages absent from this image) on all host threads, page-parallel, bounded sample per step.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "manuscript-ocr_b200")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np  # noqa: E402
+
+import synthdata  # noqa: E402
+
+METRIC = "pages/sec (EAST decode+NMS+crop)"
+OUT_H, OUT_W = 32, 128
+FALLBACK_HBM_GBS = 6650.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pages", type=int, default=64, help="pages per GPU per step")
+    ap.add_argument("--page-size", type=int, default=2048)
+    ap.add_argument("--words", type=int, default=2000)
+    ap.add_argument("--cpu-pages", type=int, default=8, help="pages in the bounded cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return (f"{a.pages}x{a.page_size}x{a.page_size} synthetic pages per GPU, ~{a.words} quads/page, "
+            f"TRBA {OUT_H}x{OUT_W} crop batch (BASELINE configs[2])")
+
+
+def measured_peak():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ---- CPU side: the oracle chain for one page (test infrastructure used as the reported baseline) ------------------
+def cpu_page(score, geo, img, page):
+    from oracle import cpu
+
+    quads = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    nms = cpu.locality_aware_nms(quads, 0.2)
+    boxes = cpu.east_postprocess(nms, (page, page), target_size=page)
+    rects, valid = cpu.word_rects(boxes, page, page, 5)
+    n = 0
+    for r in rects[valid]:
+        cpu.crop_resize_pad(img, r, OUT_H, OUT_W)
+        n += 1
+    return len(boxes), n
+
+
+def cpu_baseline(a, n_pages, threads):
+    """pages/s of the oracle on `n_pages` pages of the workload, `threads` host threads (page-parallel;
+    the C oracle is called through ctypes, which releases the GIL)."""
+    from concurrent.futures import ThreadPoolExecutor
+
+    from oracle import cpu
+
+    cpu.lib()
+    data = [(synthdata.make_maps(10_000 + i, a.page_size, a.words)[:2], synthdata.make_page_image(10_000 + i, a.page_size))
+            for i in range(n_pages)]
+
+    def one(i):
+        (s, g), img = data[i]
+        return cpu_page(s, g, img, a.page_size)
+
+    t0 = time.perf_counter()
+    if threads <= 1:
+        res = [one(i) for i in range(n_pages)]
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            res = list(ex.map(one, range(n_pages)))
+    dt = time.perf_counter() - t0
+    return n_pages / dt, sum(r[0] for r in res), dt
+
+
+def run_reference(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    threads = max(1, cores)
+    per_step = max(2, min(a.pages, threads))
+    for _ in range(max(0, min(a.warmup, 1))):
+        cpu_baseline(a, min(2, per_step), threads)
+    times, boxes = [], 0
+    for _ in range(a.steps):
+        pps, nb, dt = cpu_baseline(a, per_step, threads)
+        times.append(dt)
+        boxes += nb
+    total = sum(times)
+    value = per_step * a.steps / total
+    sample = (f"{per_step} pages per step of the same synthetic workload, C oracle port page-parallel over "
+              f"{threads} host threads")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "pages/s", "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64 (NMS) / f32 (boxes) / u8 (crops)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample": sample},
+        "boxes_per_sec": boxes / total,
+        "cpu_baseline": {"value": value, "unit": "pages/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---- clocks ----------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self, t0, t1):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.2:
+                continue
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- the B200 arm ------------------------------------------------------------------------------------------------------
+def run_b200(a):
+    import torch
+
+    import manuscript_b200 as mb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t[0])
+
+    P, S = a.pages, a.page_size
+    seeds = [rank * P + i for i in range(P)]  # this rank's shard of the corpus: pages [rank*P, (rank+1)*P)
+    score_np, geo_np, imgs_np = synthdata.make_batch(seeds, S, a.words)
+    M = S // 4
+    pin = dict(pin_memory=True)
+    h_score = torch.empty((P, M, M), dtype=torch.float32, **pin)
+    h_geo = torch.empty((P, 8, M, M), dtype=torch.float32, **pin)
+    h_pages = torch.empty((P, S, S, 3), dtype=torch.uint8, **pin)
+    h_score.copy_(torch.from_numpy(score_np))
+    h_geo.copy_(torch.from_numpy(geo_np))
+    h_pages.copy_(torch.from_numpy(imgs_np))
+    d_score, d_geo, d_pages = h_score.to(dev), h_geo.to(dev), h_pages.to(dev)
+
+    params = mb.EastParams.default(target_size=S)
+    cap_boxes = 4096
+    crops_cap = P * (a.words + a.words // 4 + 64)
+    runner = mb.PageBatch(device=local, params=params, cap_boxes=cap_boxes, crops_cap=crops_cap, out_hw=(OUT_H, OUT_W))
+    ctx = runner.ctx
+
+    # warm-up (also sizes the scratch arenas)
+    for _ in range(max(a.warmup, 3)):
+        res = runner.run(d_score, d_geo, d_pages)
+    torch.cuda.synchronize()
+    flags = int(res.flags.max().item())
+    assert flags == 0, f"device flags {flags}"
+
+    # per-page work counts for the algorithmic-byte model (outside the timed region)
+    counts = res.box_counts.cpu().numpy().astype(np.int64)
+    n_crops = int(res.n_crops.item())
+    crops = res.crops[:n_crops].cpu().numpy().astype(np.int64)
+    src_px = int(((crops[:, 3] - crops[:, 1]) * (crops[:, 4] - crops[:, 2])).sum())
+    cand = torch.empty((P, (M // 2) * (M // 2), 9), dtype=torch.float32, device=dev)
+    ccnt = torch.zeros((P,), dtype=torch.int32, device=dev)
+    cflg = torch.zeros((P,), dtype=torch.int32, device=dev)
+    mb._cabi.check(ctx.lib.ms_decode_quads(ctx.handle, d_score.data_ptr(), d_geo.data_ptr(), P, M, M, 0.6, 4.0, 2,
+                                           cand.data_ptr(), cand.shape[1], ccnt.data_ptr(), cflg.data_ptr(),
+                                           torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    n_cand = int(ccnt.sum().item())
+    # NMS output count == boxes before the filters; the filters only drop boxes, so use the NMS count from lanms
+    nms_out = torch.empty_like(cand)
+    ncnt = torch.zeros((P,), dtype=torch.int32, device=dev)
+    mb._cabi.check(ctx.lib.ms_lanms(ctx.handle, cand.data_ptr(), ccnt.data_ptr(), P, cand.shape[1], 0.2,
+                                    nms_out.data_ptr(), ncnt.data_ptr(), cflg.data_ptr(),
+                                    torch.cuda.current_stream().cuda_stream))
+    torch.cuda.synchronize()
+    n_nms = int(ncnt.sum().item())
+    del cand, nms_out
+    n_boxes = int(counts.sum())
+
+    alg = {  # bytes per step on this GPU
+        "decode": 4 * M * M * P + 72 * n_cand,
+        "lanms": 36 * n_cand + 36 * n_nms,
+        "east_boxes": 36 * n_nms + 36 * n_boxes,
+        "word_rects": 36 * n_boxes + 20 * n_crops,
+        "crop": 3 * src_px + 3 * OUT_H * OUT_W * 4 * n_crops,
+    }
+
+    # ---- timed region 1: inputs resident in HBM, device-timed ------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    ctx.stage_timing(True)
+    launches0 = ctx.launches
+    stream = torch.cuda.current_stream()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.perf_counter()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        runner.run(d_score, d_geo, d_pages)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    t_wall1 = time.perf_counter()
+    ms_total = max_over_ranks(ev0.elapsed_time(ev1))
+    launches = ctx.launches - launches0
+    nb, stage_ms = ctx.stage_times()
+    ctx.stage_timing(False)
+    assert nb == a.steps, (nb, a.steps)
+
+    # ---- timed region 2: end to end through the host-buffer C-ABI call -------------------------------------------
+    e2e = None
+    if not a.no_e2e:
+        for _ in range(2):
+            runner.run_host(h_score, h_geo, h_pages)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(a.steps):
+            rh = runner.run_host(h_score, h_geo, h_pages)
+        torch.cuda.synchronize()
+        t_e2e = max_over_ranks(time.perf_counter() - t0)
+        barrier()
+        nch = int(rh.n_crops[0])
+        assert nch == n_crops and int(rh.box_counts.sum()) == n_boxes
+        h2d = h_score.numel() * 4 + h_geo.numel() * 4 + h_pages.numel()
+        d2h = P * cap_boxes * 36 + P * 8 + 4 + nch * 20
+        e2e = {"value": world * P * a.steps / t_e2e, "unit": "pages/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / a.steps,
+               "note": "ms_page_batch_host with pinned host buffers; crop batch left on the device for the recogniser"}
+    if rank == 0:
+        sampler.stop()
+
+    total_boxes = sum_over_ranks(float(n_boxes))
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = measured_peak()
+    ms_step = ms_total / a.steps
+    stages = {}
+    for k, v in stage_ms.items():
+        ms = v / a.steps
+        gbs = alg[k] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+        stages[k] = {"ms_per_step": ms, "share": v / max(sum(stage_ms.values()), 1e-12), "alg_bytes": int(alg[k]),
+                     "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
+    dom = max(stage_ms, key=lambda k: stage_ms[k])
+    roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
+                "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "alg_bytes_per_launch": int(alg[dom]), "ms_per_launch": stages[dom]["ms_per_step"]}
+    whole = sum(alg.values()) / (ms_step * 1e-3) / 1e9
+    line = {
+        "metric": METRIC, "value": world * P * a.steps / (ms_total * 1e-3), "unit": "pages/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64 (NMS) / f32 (boxes) / u8 (crops)", "data": "synthetic",
+        "config": {"workload": workload_name(a), "pages_per_gpu": P, "page": S, "map": M, "words_per_page": a.words,
+                   "candidates_per_page": n_cand / P, "boxes_per_page": n_boxes / P, "crops_per_page": n_crops / P,
+                   "l2": "inputs (maps + pages) of one step exceed L2 (no flush needed)",
+                   "parallelism": f"pages sharded over {world} GPU(s), no collective"},
+        "boxes_per_sec": total_boxes * a.steps / (ms_total * 1e-3),
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "whole_step": {"alg_bytes": int(sum(alg.values())), "gbs": whole, "frac_of_hbm_peak": whole / peak},
+        "stages": stages,
+        "clocks": sampler.summary(t_wall0, t_wall1),
+    }
+    if e2e is not None:
+        line["e2e"] = e2e
+    if world == 1 and not a.no_cpu_baseline:
+        pps, _, dt = cpu_baseline(a, a.cpu_pages, 1)
+        line["cpu_baseline"] = {"value": pps, "unit": "pages/s", "cores": 1, "kind": "port",
+                                "sample": f"{a.cpu_pages} pages of the same workload through the C oracle "
+                                          f"(oracle/oracle.c), 1 thread, {dt:.1f} s"}
+    print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_b200(a)
+
+
+if __name__ == "__main__":
+    main()

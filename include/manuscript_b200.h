@@ -1,0 +1,188 @@
+/*
+ * manuscript_b200.h -- C ABI of the B200-native (sm_100a) EAST post-processing -> TRBA batch path.
+ *
+ * Drop-in boundary for the detector->recognizer hot path of olegiy/manuscript-ocr v0.1.8.
+ * Each entry point names the reference interface it replaces (paths relative to the reference
+ * root).  The reference has no FFI of its own (it is pure Python): these are the
+ * functions its numpy-level seam would bind -- see INTEGRATION.md for the ctypes stubs.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; `stream` is a cudaStream_t passed as void* (NULL = default).
+ *   - *_host entry points take HOST buffers, copy in/out themselves and synchronise before return.
+ *   - device entry points take DEVICE pointers, are stream-ordered and never synchronise; data-
+ *     dependent sizes stay on the device (counts arrays), so a whole page batch runs without a
+ *     host round trip.  Per-page outputs are "page-strided": page p owns rows
+ *     [p*cap_per_page, p*cap_per_page + counts[p]).
+ *   - return value: MS_OK or a negative MS_ERR_*; ms_last_error() gives a message.  No exceptions
+ *     cross the boundary.  There is NO CPU fallback: without a CUDA device every call fails.
+ *   - quads are rows of 9 float32: x0,y0,x1,y1,x2,y2,x3,y3,score (the reference's (N,9) layout).
+ *   - tie rule: where the reference uses numpy's unstable argsort (lanms.py:138,167; infer.py:199)
+ *     ties are broken by original index (numpy kind="stable"), see DESIGN.md.
+ */
+#ifndef MANUSCRIPT_B200_H
+#define MANUSCRIPT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define MS_API __attribute__((visibility("default")))
+#else
+#define MS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_OK 0
+#define MS_ERR_INVALID (-1)  /* bad argument                                                  */
+#define MS_ERR_CUDA (-2)     /* CUDA runtime error (message in ms_last_error)                  */
+#define MS_ERR_CAPACITY (-3) /* an output or internal capacity was exceeded                    */
+#define MS_ERR_INDEX (-4)    /* quantised pixel outside the map: reference raises IndexError   */
+#define MS_ERR_NO_DEVICE (-5)
+
+/* per-page status bits written by the device entry points into `flags` (int32 per page) */
+#define MS_FLAG_CAND_OVERFLOW 1 /* more candidates than cap_per_page            */
+#define MS_FLAG_INDEX_ERROR 2   /* utils.py:370 would raise IndexError          */
+#define MS_FLAG_EDGE_OVERFLOW 4 /* NMS suppression-edge buffer exceeded         */
+
+typedef struct ms_ctx ms_ctx;
+
+/* EAST constructor parameters that shape the path (infer.py:28-43). */
+typedef struct ms_east_params {
+    float score_thresh;          /* 0.6  */
+    double scale;                /* 1/score_geo_scale = 4.0 */
+    int quantization;            /* 2    */
+    double iou_threshold;        /* 0.2  */
+    double expand_ratio_w;       /* 0.9  */
+    double expand_ratio_h;       /* 0.9  */
+    int target_size;             /* 1280 */
+    int axis_aligned_output;     /* 1    */
+    int remove_area_anomalies;   /* 1    */
+    double anomaly_sigma_threshold; /* 5.0 */
+    int anomaly_min_box_count;   /* 30   */
+} ms_east_params;
+
+MS_API const char *ms_version(void);
+MS_API const char *ms_last_error(void);
+MS_API void ms_east_params_default(ms_east_params *p);
+
+/* context = device + scratch arena (grown on demand, reused across calls) */
+MS_API int ms_create(int device, ms_ctx **out);
+MS_API void ms_destroy(ms_ctx *ctx);
+MS_API int ms_device_count(void);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+MS_API int64_t ms_launch_count(const ms_ctx *ctx);
+
+/* Per-stage device timing of ms_page_batch (CUDA events recorded on the launch stream between the
+ * stages; used by bench.py for the live roofline numbers).  Stages: 0 decode, 1 lanms, 2 expand+filters,
+ * 3 word rects, 4 crop/resize/pad.  ms_stage_times waits for the recorded batches, writes the SUM of
+ * each stage's milliseconds over the batches recorded since the last read into ms[0..MS_N_STAGES) and
+ * returns the number of batches (<= 256 are retained), or a negative error. */
+#define MS_N_STAGES 5
+MS_API int ms_stage_timing(ms_ctx *ctx, int enable);
+MS_API int ms_stage_times(ms_ctx *ctx, double *ms);
+
+/* ---------------------------------------------------------------------------------------------
+ * HOST-buffer entry points: one page, the reference's function-level seam.
+ * ------------------------------------------------------------------------------------------- */
+
+/* replaces decode_quads_from_maps, detectors/_east/utils.py:328 (called infer.py:319).
+ * score (map_h,map_w) f32; geo (8,map_h,map_w) f32 planar (the memory behind infer.py:321's
+ * transposed view).  Writes up to `cap` rows, *n_out = N (rows in (y,x) order). */
+MS_API int ms_decode_quads_host(ms_ctx *ctx, const float *score, const float *geo, int map_h, int map_w,
+                         float score_thresh, double scale, int quantization, float *quads_out,
+                         int64_t cap, int64_t *n_out);
+
+/* replaces locality_aware_nms, detectors/_east/lanms.py:156 (called infer.py:332).
+ * boxes (n,9) f32 -> out (<=n,9) f32 in descending-score order. */
+MS_API int ms_lanms_host(ms_ctx *ctx, const float *boxes, int64_t n, double iou_threshold, float *out,
+                  int64_t *m_out);
+
+/* replaces standard_nms, detectors/_east/lanms.py:133.  polys (n,4,2) f64, scores (n) f64 ->
+ * keep_idx (<=n) int64 indices in kept order. */
+MS_API int ms_standard_nms_host(ms_ctx *ctx, const double *polys, const double *scores, int64_t n,
+                         double iou_threshold, int64_t *keep_idx, int64_t *k_out);
+
+/* replaces polygon_iou / should_merge, lanms.py:80-96, evaluated on the device for n pairs:
+ * subj,clip (n,4,2) f64 -> iou (n) f64. */
+MS_API int ms_polygon_iou_host(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double *iou);
+
+/* replaces expand_boxes, detectors/_east/utils.py:384 (called infer.py:340). */
+MS_API int ms_expand_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, double expand_w, double expand_h,
+                         float *out);
+
+/* replaces EAST._scale_boxes_to_original/_remove_fully_contained_boxes/_remove_area_anomalies/
+ * _convert_to_axis_aligned, infer.py:134-233, applied after expand_boxes exactly as
+ * infer.py:340-356 does.  quads (n,9) post-NMS -> out (<=n,9). */
+MS_API int ms_east_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, const ms_east_params *p, int orig_h,
+                       int orig_w, float *out, int64_t *m_out);
+
+/* replaces the crop loop of Pipeline.predict + Pipeline._extract_word_image, _pipeline.py:125-137,
+ * 204-221: polys (n,8) f32 -> rects (n,4) int32 [x1,y1,x2,y2) and valid (n) u8. */
+MS_API int ms_word_rects_host(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w,
+                       int min_text_size, int32_t *rects, uint8_t *valid);
+
+/* replaces ResizeAndPadA.apply + get_val_transform + the torch.stack of TRBA.predict,
+ * recognizers/_trba/data/transforms.py:85-120,185-193 and recognizers/_trba/__init__.py:264-288,
+ * 382-390: page (img_h,img_w,3) u8 + rects (n,4) -> batch (n,3,out_h,out_w) f32 normalised
+ * (and/or the uint8 canvases (n,out_h,out_w,3); either output may be NULL). */
+MS_API int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const int32_t *rects,
+                            int64_t n, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8);
+
+/* ---------------------------------------------------------------------------------------------
+ * DEVICE entry points: a batch of pages, stream-ordered, no host synchronisation.
+ * ------------------------------------------------------------------------------------------- */
+
+/* utils.py:328 for n_pages maps.  score (n_pages,map_h,map_w), geo (n_pages,8,map_h,map_w).
+ * quads_out (n_pages*cap_per_page,9); counts (n_pages) int32; flags (n_pages) int32 (OR-ed). */
+MS_API int ms_decode_quads(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int map_h, int map_w,
+                    float score_thresh, double scale, int quantization, float *quads_out,
+                    int cap_per_page, int32_t *counts, int32_t *flags, void *stream);
+
+/* lanms.py:156 for n_pages candidate lists (page-strided in, page-strided out). */
+MS_API int ms_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+             double iou_threshold, float *quads_out, int32_t *counts_out, int32_t *flags, void *stream);
+
+/* utils.py:384 + infer.py:134-233 for n_pages NMS outputs.  orig_hw (n_pages,2) int32 on the
+ * device, or NULL for (target_size,target_size). */
+MS_API int ms_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                  const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
+                  void *stream);
+
+/* _pipeline.py:125-137,204-221 for n_pages box lists: compacts the valid crops of all pages, in
+ * (page, box) order, into crops_out rows of 5 int32 [page,x1,y1,x2,y2]; *n_crops (device int32). */
+MS_API int ms_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                  const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
+                  int64_t crops_cap, int32_t *n_crops, void *stream);
+
+/* transforms.py:85-120,185-193 for a crop list over a batch of equally sized pages
+ * pages (n_pages,img_h,img_w,3) u8.  crops (<=crops_cap,5) int32 and n_crops on the device.
+ * batch_f32 (crops_cap,3,out_h,out_w) and/or canvas_u8 (crops_cap,out_h,out_w,3). */
+MS_API int ms_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w,
+                       const int32_t *crops, const int32_t *n_crops, int64_t crops_cap, int out_h,
+                       int out_w, float *batch_f32, uint8_t *canvas_u8, void *stream);
+
+/* decode -> LANMS -> expand/filters -> word rects -> crop batch in one call (device buffers).
+ * boxes_out (n_pages*cap_boxes,9), box_counts (n_pages); crops_out/n_crops/batch as above. */
+MS_API int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
+                  int map_h, int map_w, int img_h, int img_w, const ms_east_params *p, int min_text_size,
+                  int out_h, int out_w, int cap_boxes, float *boxes_out, int32_t *box_counts,
+                  int32_t *crops_out, int64_t crops_cap, int32_t *n_crops, float *batch_f32,
+                  uint8_t *canvas_u8, int32_t *flags, void *stream);
+
+/* Same path with HOST buffers (pinned or pageable): H2D of maps + pages, the batch, D2H of boxes,
+ * counts, crop list and (optionally, if batch_f32_host != NULL) the crop batch.  When
+ * batch_dev_out != NULL the crop batch stays on the device and its pointer is returned there
+ * (as the reference leaves it on `self.device`, recognizers/_trba/__init__.py:288). */
+MS_API int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages,
+                       int n_pages, int map_h, int map_w, int img_h, int img_w, const ms_east_params *p,
+                       int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
+                       int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
+                       float *batch_f32_host, float **batch_dev_out, int32_t *flags);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MANUSCRIPT_B200_H */

@@ -1,0 +1,813 @@
+// C-ABI layer of libmanuscript_b200.so: context, scratch arenas, the host-buffer entry points (one
+// page, the reference's function-level seam) and the device-buffer entry points (page batches,
+// stream-ordered).  Declarations and the reference interface each entry replaces: include/manuscript_b200.h.
+//
+// There is no CPU path in this library: every entry point launches the sm_100a kernels of
+// decode.cu / sort.cu / lanms.cu / boxes.cu / crop.cu or fails.
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <new>
+
+#include "ms_internal.cuh"
+
+// ---- errors ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+
+void ms_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+int ms_check_cuda(cudaError_t e, const char *what)
+{
+    if (e == cudaSuccess) return MS_OK;
+    ms_set_error("CUDA error in %s: %s", what, cudaGetErrorString(e));
+    return MS_ERR_CUDA;
+}
+
+extern "C" const char *ms_last_error(void) { return g_err; }
+extern "C" const char *ms_version(void) { return "manuscript_b200 0.1 (sm_100a)"; }
+
+extern "C" void ms_east_params_default(ms_east_params *p)
+{
+    // EAST.__init__ defaults, infer.py:28-43
+    if (!p) return;
+    p->score_thresh = 0.6f;
+    p->scale = 1.0 / 0.25;
+    p->quantization = 2;
+    p->iou_threshold = 0.2;
+    p->expand_ratio_w = 0.9;
+    p->expand_ratio_h = 0.9;
+    p->target_size = 1280;
+    p->axis_aligned_output = 1;
+    p->remove_area_anomalies = 1;
+    p->anomaly_sigma_threshold = 5.0;
+    p->anomaly_min_box_count = 30;
+}
+
+extern "C" int ms_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+// ---- context --------------------------------------------------------------------------------------------
+extern "C" int ms_create(int device, ms_ctx **out)
+{
+    if (!out) {
+        ms_set_error("ms_create: out is NULL");
+        return MS_ERR_INVALID;
+    }
+    *out = nullptr;
+    int n = ms_device_count();
+    if (n <= 0) {
+        ms_set_error("ms_create: no CUDA device (this library has no CPU path)");
+        return MS_ERR_NO_DEVICE;
+    }
+    if (device < 0 || device >= n) {
+        ms_set_error("ms_create: device %d out of range [0,%d)", device, n);
+        return MS_ERR_INVALID;
+    }
+    MS_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    MS_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        ms_set_error("ms_create: device %d is sm_%d%d; this library is built for sm_100a only", device, prop.major,
+                     prop.minor);
+        return MS_ERR_NO_DEVICE;
+    }
+    ms_ctx *c = new (std::nothrow) ms_ctx();
+    if (!c) {
+        ms_set_error("ms_create: out of host memory");
+        return MS_ERR_INVALID;
+    }
+    memset(c, 0, sizeof(*c));
+    c->device = device;
+    c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : MS_NUM_SMS_B200;
+    int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc == MS_OK) {
+        c->pinned_bytes = 1 << 20;
+        rc = ms_check_cuda(cudaMallocHost((void **)&c->pinned, c->pinned_bytes), "cudaMallocHost");
+    }
+    if (rc != MS_OK) {
+        ms_destroy(c);
+        return rc;
+    }
+    *out = c;
+    return MS_OK;
+}
+
+extern "C" void ms_destroy(ms_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->own_stream) {
+        cudaStreamSynchronize(ctx->own_stream);
+        cudaStreamDestroy(ctx->own_stream);
+    }
+    if (ctx->timing_ev) {
+        for (int i = 0; i < MS_TIMING_RING * (MS_N_STAGES + 1); i++) cudaEventDestroy(ctx->timing_ev[i]);
+        free(ctx->timing_ev);
+    }
+    if (ctx->arena) cudaFree(ctx->arena);
+    if (ctx->stage) cudaFree(ctx->stage);
+    if (ctx->pinned) cudaFreeHost(ctx->pinned);
+    delete ctx;
+}
+
+extern "C" int64_t ms_launch_count(const ms_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ms_stage_timing(ms_ctx *ctx, int enable)
+{
+    if (!ctx) return MS_ERR_INVALID;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    if (enable && !ctx->timing_ev) {
+        const int n = MS_TIMING_RING * (MS_N_STAGES + 1);
+        ctx->timing_ev = (cudaEvent_t *)calloc(n, sizeof(cudaEvent_t));
+        if (!ctx->timing_ev) return MS_ERR_INVALID;
+        for (int i = 0; i < n; i++) MS_CUDA(cudaEventCreate(&ctx->timing_ev[i]));
+    }
+    ctx->timing = enable ? 1 : 0;
+    ctx->timing_n = 0;
+    return MS_OK;
+}
+
+extern "C" int ms_stage_times(ms_ctx *ctx, double *ms)
+{
+    if (!ctx || !ms) return MS_ERR_INVALID;
+    MS_CUDA(cudaSetDevice(ctx->device));
+    for (int s = 0; s < MS_N_STAGES; s++) ms[s] = 0.0;
+    const int n = ctx->timing_n;
+    for (int b = 0; b < n; b++) {
+        cudaEvent_t *ev = ctx->timing_ev + (size_t)b * (MS_N_STAGES + 1);
+        MS_CUDA(cudaEventSynchronize(ev[MS_N_STAGES]));
+        for (int s = 0; s < MS_N_STAGES; s++) {
+            float t = 0.f;
+            MS_CUDA(cudaEventElapsedTime(&t, ev[s], ev[s + 1]));
+            ms[s] += (double)t;
+        }
+    }
+    ctx->timing_n = 0;
+    return n;
+}
+
+// records the boundary event `idx` of the current batch when stage timing is on
+static int timing_mark(ms_ctx *ctx, int idx, cudaStream_t st)
+{
+    if (!ctx->timing || !ctx->timing_ev || ctx->timing_n >= MS_TIMING_RING) return MS_OK;
+    MS_CUDA(cudaEventRecord(ctx->timing_ev[(size_t)ctx->timing_n * (MS_N_STAGES + 1) + idx], st));
+    if (idx == MS_N_STAGES) ctx->timing_n++;
+    return MS_OK;
+}
+
+static int grow(ms_ctx *ctx, char **buf, size_t *have, size_t want, const char *what)
+{
+    if (want <= *have) return MS_OK;
+    // growing frees memory that queued work may still use: drain the device first
+    MS_CUDA(cudaDeviceSynchronize());
+    if (*buf) MS_CUDA(cudaFree(*buf));
+    *buf = nullptr;
+    *have = 0;
+    size_t sz = want + want / 4 + (1 << 20);
+    cudaError_t e = cudaMalloc((void **)buf, sz);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        sz = want;
+        e = cudaMalloc((void **)buf, sz);
+    }
+    if (e != cudaSuccess) {
+        ms_set_error("%s: cudaMalloc(%zu) failed: %s", what, sz, cudaGetErrorString(e));
+        return MS_ERR_CUDA;
+    }
+    *have = sz;
+    (void)ctx;
+    return MS_OK;
+}
+
+int ms_arena_reserve(ms_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->arena, &ctx->arena_bytes, bytes, "arena"); }
+int ms_stage_reserve(ms_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->stage, &ctx->stage_bytes, bytes, "stage"); }
+
+static inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
+
+#define MS_CTX(ctx)                                          \
+    do {                                                     \
+        if (!(ctx)) {                                        \
+            ms_set_error("%s: ctx is NULL", __func__);       \
+            return MS_ERR_INVALID;                           \
+        }                                                    \
+        MS_CUDA(cudaSetDevice((ctx)->device));               \
+    } while (0)
+
+#define MS_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != MS_OK) return _r;  \
+    } while (0)
+
+static int flags_to_rc(int32_t f, const char *where)
+{
+    if (f & MS_FLAG_INDEX_ERROR) {
+        ms_set_error("%s: quantised pixel index outside the map (the reference raises IndexError, utils.py:370); "
+                     "map sides must be multiples of the quantisation step",
+                     where);
+        return MS_ERR_INDEX;
+    }
+    if (f & MS_FLAG_CAND_OVERFLOW) {
+        ms_set_error("%s: more candidates than the output capacity", where);
+        return MS_ERR_CAPACITY;
+    }
+    if (f & MS_FLAG_EDGE_OVERFLOW) {
+        ms_set_error("%s: NMS suppression-edge buffer exceeded", where);
+        return MS_ERR_CAPACITY;
+    }
+    return MS_OK;
+}
+
+// =========================================================================================================
+// device entry points
+// =========================================================================================================
+extern "C" int ms_decode_quads(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int map_h, int map_w,
+                               float score_thresh, double scale, int quantization, float *quads_out, int cap_per_page,
+                               int32_t *counts, int32_t *flags, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!score || !geo || !quads_out || !counts || !flags) {
+        ms_set_error("ms_decode_quads: NULL pointer");
+        return MS_ERR_INVALID;
+    }
+    if (quantization < 1) quantization = 1;  // utils.py:347 only quantises when > 1
+    MS_TRY(ms_arena_reserve(ctx, msk_decode_scratch(n_pages, map_h, map_w, quantization)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_decode(ctx, score, geo, n_pages, map_h, map_w, score_thresh, scale, quantization, quads_out,
+                      cap_per_page, counts, flags, bump, (cudaStream_t)stream);
+}
+
+extern "C" int ms_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                        double iou_threshold, float *quads_out, int32_t *counts_out, int32_t *flags, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!quads || !counts || !quads_out || !counts_out || !flags || cap_per_page <= 0) {
+        ms_set_error("ms_lanms: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    MS_TRY(ms_arena_reserve(ctx, msk_lanms_scratch(n_pages, cap_per_page)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_lanms(ctx, quads, counts, n_pages, cap_per_page, iou_threshold, quads_out, counts_out, flags, bump,
+                     (cudaStream_t)stream);
+}
+
+extern "C" int ms_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                             const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
+                             void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!quads || !counts || !quads_out || !counts_out || !p || cap_per_page <= 0) {
+        ms_set_error("ms_east_boxes: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    MS_TRY(ms_arena_reserve(ctx, msk_east_boxes_scratch(n_pages, cap_per_page)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_east_boxes(ctx, quads, counts, n_pages, cap_per_page, p, orig_hw, quads_out, counts_out, bump,
+                          (cudaStream_t)stream);
+}
+
+static size_t word_rects_scratch_full(int n_pages, int cap_per_page)
+{
+    return msk_word_rects_scratch(n_pages) + al256((size_t)n_pages * cap_per_page * 4 * sizeof(int32_t)) + 1024;
+}
+
+extern "C" int ms_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                             const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
+                             int64_t crops_cap, int32_t *n_crops, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!quads || !counts || !crops_out || !n_crops || cap_per_page <= 0 || crops_cap < 0) {
+        ms_set_error("ms_word_rects: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    MS_TRY(ms_arena_reserve(ctx, word_rects_scratch_full(n_pages, cap_per_page)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_word_rects(ctx, quads, counts, n_pages, cap_per_page, img_hw, img_h, img_w, min_text_size, crops_out,
+                          crops_cap, n_crops, bump, (cudaStream_t)stream);
+}
+
+extern "C" int ms_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w,
+                                  const int32_t *crops, const int32_t *n_crops, int64_t crops_cap, int out_h, int out_w,
+                                  float *batch_f32, uint8_t *canvas_u8, void *stream)
+{
+    MS_CTX(ctx);
+    if (!pages || !crops || !n_crops) {
+        ms_set_error("ms_crop_resize_pad: NULL pointer");
+        return MS_ERR_INVALID;
+    }
+    return msk_crop(ctx, pages, n_pages, img_h, img_w, crops, n_crops, crops_cap, out_h, out_w, batch_f32, canvas_u8,
+                    (cudaStream_t)stream);
+}
+
+// candidate capacity per page that can never overflow: one row per quantisation cell (utils.py:347-356)
+static int cand_cap(int map_h, int map_w, int q)
+{
+    if (q < 1) q = 1;
+    long long c = (long long)((map_h + q - 1) / q) * ((map_w + q - 1) / q);
+    return (int)(c > 0x7fffffffLL ? 0x7fffffff : c);
+}
+
+static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c)
+{
+    size_t fixed = 2 * al256((size_t)n_pages * cap_c * 9 * sizeof(float)) + 2 * al256((size_t)n_pages * sizeof(int32_t));
+    size_t stage = msk_decode_scratch(n_pages, map_h, map_w, q);
+    size_t s2 = msk_lanms_scratch(n_pages, cap_c);
+    if (s2 > stage) stage = s2;
+    s2 = msk_east_boxes_scratch(n_pages, cap_c);
+    if (s2 > stage) stage = s2;
+    s2 = word_rects_scratch_full(n_pages, cap_c);
+    if (s2 > stage) stage = s2;
+    return fixed + stage + 4096;
+}
+
+__global__ void ms_copy_boxes_kernel(const float *__restrict__ src, const int32_t *__restrict__ counts, int n_pages,
+                                     int cap_src, int cap_dst, float *__restrict__ dst, int32_t *__restrict__ counts_dst,
+                                     int32_t *__restrict__ flags)
+{
+    // page-strided (cap_src) -> page-strided (cap_dst); rows beyond cap_dst are dropped and flagged
+    const int page = blockIdx.y;
+    int k = counts[page];
+    if (k > cap_dst) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags + page, MS_FLAG_CAND_OVERFLOW);
+        k = cap_dst;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) counts_dst[page] = k;
+    const float *s = src + (size_t)page * cap_src * 9;
+    float *d = dst + (size_t)page * cap_dst * 9;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k * 9; i += gridDim.x * blockDim.x) d[i] = s[i];
+}
+
+extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
+                             int map_h, int map_w, int img_h, int img_w, const ms_east_params *p, int min_text_size,
+                             int out_h, int out_w, int cap_boxes, float *boxes_out, int32_t *box_counts,
+                             int32_t *crops_out, int64_t crops_cap, int32_t *n_crops, float *batch_f32,
+                             uint8_t *canvas_u8, int32_t *flags, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!score || !geo || !p || !boxes_out || !box_counts || !flags || cap_boxes <= 0) {
+        ms_set_error("ms_page_batch: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    const bool want_crops = pages != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int q = p->quantization < 1 ? 1 : p->quantization;
+    const int cap_c = cand_cap(map_h, map_w, q);
+    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates, later the filtered boxes
+    float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
+    int32_t *ca = bump.take<int32_t>(n_pages);
+    int32_t *cb = bump.take<int32_t>(n_pages);
+    if (!cb) {
+        ms_set_error("ms_page_batch: arena too small");
+        return MS_ERR_CAPACITY;
+    }
+    MS_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_pages * sizeof(int32_t), st));
+    MS_TRY(timing_mark(ctx, 0, st));
+    MS_TRY(msk_decode(ctx, score, geo, n_pages, map_h, map_w, p->score_thresh, p->scale, q, qa, cap_c, ca, flags, bump,
+                      st));
+    MS_TRY(timing_mark(ctx, 1, st));
+    MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
+    // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
+    ms_east_params pp = *p;
+    MS_TRY(timing_mark(ctx, 2, st));
+    MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, &pp, nullptr, qa, ca, bump, st));
+    {
+        dim3 grid(8, n_pages);
+        ms_copy_boxes_kernel<<<grid, 256, 0, st>>>(qa, ca, n_pages, cap_c, cap_boxes, boxes_out, box_counts, flags);
+        MS_LAUNCH_CHECK(ctx);
+    }
+    MS_TRY(timing_mark(ctx, 3, st));
+    if (want_crops) {
+        MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, nullptr, img_h, img_w, min_text_size,
+                              crops_out, crops_cap, n_crops, bump, st));
+        MS_TRY(timing_mark(ctx, 4, st));
+        if (batch_f32 || canvas_u8)
+            MS_TRY(msk_crop(ctx, pages, n_pages, img_h, img_w, crops_out, n_crops, crops_cap, out_h, out_w, batch_f32,
+                            canvas_u8, st));
+    } else {
+        MS_TRY(timing_mark(ctx, 4, st));
+    }
+    MS_TRY(timing_mark(ctx, MS_N_STAGES, st));
+    return MS_OK;
+}
+
+// =========================================================================================================
+// host entry points (one page; copy in, run, copy out, synchronise)
+// =========================================================================================================
+extern "C" int ms_decode_quads_host(ms_ctx *ctx, const float *score, const float *geo, int map_h, int map_w,
+                                    float score_thresh, double scale, int quantization, float *quads_out, int64_t cap,
+                                    int64_t *n_out)
+{
+    MS_CTX(ctx);
+    if (!score || !geo || !n_out || map_h <= 0 || map_w <= 0 || cap < 0 || (cap > 0 && !quads_out)) {
+        ms_set_error("ms_decode_quads_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    *n_out = 0;
+    if (quantization < 1) quantization = 1;
+    const size_t plane = (size_t)map_h * map_w;
+    int capd = cand_cap(map_h, map_w, quantization);
+    if (cap < capd) capd = (int)cap;
+    if (capd < 1) capd = 1;
+    size_t need = al256(plane * 4) + al256(plane * 32) + al256((size_t)capd * 36) + 1024;
+    MS_TRY(ms_stage_reserve(ctx, need));
+    MS_TRY(ms_arena_reserve(ctx, msk_decode_scratch(1, map_h, map_w, quantization)));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_score = sb.take<float>(plane);
+    float *d_geo = sb.take<float>(plane * 8);
+    float *d_out = sb.take<float>((size_t)capd * 9);
+    int32_t *d_cnt = sb.take<int32_t>(2);
+    if (!d_cnt) {
+        ms_set_error("ms_decode_quads_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_score, score, plane * 4, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_geo, geo, plane * 32, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int32_t), st));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_decode(ctx, d_score, d_geo, 1, map_h, map_w, score_thresh, scale, quantization, d_out, capd, d_cnt,
+                      d_cnt + 1, bump, st));
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    MS_CUDA(cudaMemcpyAsync(h, d_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    MS_TRY(flags_to_rc(h[1], "decode_quads"));
+    const int n = h[0];
+    if (n > 0) {
+        MS_CUDA(cudaMemcpyAsync(quads_out, d_out, (size_t)n * 36, cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+    }
+    *n_out = n;
+    return MS_OK;
+}
+
+extern "C" int ms_lanms_host(ms_ctx *ctx, const float *boxes, int64_t n, double iou_threshold, float *out,
+                             int64_t *m_out)
+{
+    MS_CTX(ctx);
+    if (!m_out || n < 0 || (n > 0 && (!boxes || !out))) {
+        ms_set_error("ms_lanms_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    *m_out = 0;
+    if (n == 0) return MS_OK;  // lanms.py:163-164
+    if (n >= (int64_t)1 << 30) {
+        ms_set_error("ms_lanms_host: n too large");
+        return MS_ERR_INVALID;
+    }
+    const int cap = (int)n;
+    MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 36) + 1024));
+    MS_TRY(ms_arena_reserve(ctx, msk_lanms_scratch(1, cap)));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_in = sb.take<float>((size_t)n * 9);
+    float *d_out = sb.take<float>((size_t)n * 9);
+    int32_t *d_cnt = sb.take<int32_t>(3);
+    if (!d_cnt) {
+        ms_set_error("ms_lanms_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    h[0] = cap;
+    h[1] = 0;
+    h[2] = 0;
+    MS_CUDA(cudaMemcpyAsync(d_cnt, h, 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_in, boxes, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_lanms(ctx, d_in, d_cnt, 1, cap, iou_threshold, d_out, d_cnt + 1, d_cnt + 2, bump, st));
+    MS_CUDA(cudaMemcpyAsync(h + 4, d_cnt, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    MS_TRY(flags_to_rc(h[6], "locality_aware_nms"));
+    const int m = h[5];
+    if (m > 0) {
+        MS_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * 36, cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+    }
+    *m_out = m;
+    return MS_OK;
+}
+
+extern "C" int ms_standard_nms_host(ms_ctx *ctx, const double *polys, const double *scores, int64_t n,
+                                    double iou_threshold, int64_t *keep_idx, int64_t *k_out)
+{
+    MS_CTX(ctx);
+    if (!k_out || n < 0 || (n > 0 && (!polys || !scores || !keep_idx))) {
+        ms_set_error("ms_standard_nms_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    *k_out = 0;
+    if (n == 0) return MS_OK;
+    if (n >= (int64_t)1 << 27) {
+        ms_set_error("ms_standard_nms_host: n too large");
+        return MS_ERR_INVALID;
+    }
+    MS_TRY(ms_stage_reserve(ctx, al256((size_t)n * 64) + al256((size_t)n * 8) + al256((size_t)n * 4) + 1024));
+    MS_TRY(ms_arena_reserve(ctx, msk_standard_nms_scratch((int)n)));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    double *d_p = sb.take<double>((size_t)n * 8);
+    double *d_s = sb.take<double>((size_t)n);
+    int32_t *d_keep = sb.take<int32_t>((size_t)n);
+    int32_t *d_cnt = sb.take<int32_t>(2);
+    if (!d_cnt) {
+        ms_set_error("ms_standard_nms_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_p, polys, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_s, scores, (size_t)n * 8, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int32_t), st));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_standard_nms(ctx, d_p, d_s, (int)n, iou_threshold, d_keep, d_cnt, d_cnt + 1, bump, st));
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    MS_CUDA(cudaMemcpyAsync(h, d_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    MS_TRY(flags_to_rc(h[1], "standard_nms"));
+    const int k = h[0];
+    if (k > 0) {
+        // int32 on the device -> int64 for the caller, staged through a temporary host copy
+        int32_t *tmp = (int32_t *)malloc((size_t)k * sizeof(int32_t));
+        if (!tmp) {
+            ms_set_error("ms_standard_nms_host: out of host memory");
+            return MS_ERR_INVALID;
+        }
+        cudaError_t e = cudaMemcpyAsync(tmp, d_keep, (size_t)k * 4, cudaMemcpyDeviceToHost, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) {
+            free(tmp);
+            return ms_check_cuda(e, "standard_nms read-back");
+        }
+        for (int i = 0; i < k; i++) keep_idx[i] = tmp[i];
+        free(tmp);
+    }
+    *k_out = k;
+    return MS_OK;
+}
+
+extern "C" int ms_polygon_iou_host(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double *iou)
+{
+    MS_CTX(ctx);
+    if (n < 0 || (n > 0 && (!subj || !clip || !iou))) {
+        ms_set_error("ms_polygon_iou_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 64) + al256((size_t)n * 8) + 1024));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    double *d_a = sb.take<double>((size_t)n * 8);
+    double *d_b = sb.take<double>((size_t)n * 8);
+    double *d_o = sb.take<double>((size_t)n);
+    if (!d_o) {
+        ms_set_error("ms_polygon_iou_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_a, subj, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_b, clip, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    MS_TRY(msk_polygon_iou(ctx, d_a, d_b, n, d_o, st));
+    MS_CUDA(cudaMemcpyAsync(iou, d_o, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+extern "C" int ms_expand_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, double expand_w, double expand_h,
+                                    float *out)
+{
+    MS_CTX(ctx);
+    if (n < 0 || (n > 0 && (!quads || !out))) {
+        ms_set_error("ms_expand_boxes_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 36) + 1024));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_in = sb.take<float>((size_t)n * 9);
+    float *d_out = sb.take<float>((size_t)n * 9);
+    if (!d_out) {
+        ms_set_error("ms_expand_boxes_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_in, quads, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    MS_TRY(msk_expand(ctx, d_in, n, expand_w, expand_h, d_out, st));
+    MS_CUDA(cudaMemcpyAsync(out, d_out, (size_t)n * 36, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+extern "C" int ms_east_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, const ms_east_params *p, int orig_h,
+                                  int orig_w, float *out, int64_t *m_out)
+{
+    MS_CTX(ctx);
+    if (!m_out || !p || n < 0 || (n > 0 && (!quads || !out))) {
+        ms_set_error("ms_east_boxes_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    *m_out = 0;
+    if (n == 0) return MS_OK;
+    if (n >= (int64_t)1 << 30) {
+        ms_set_error("ms_east_boxes_host: n too large");
+        return MS_ERR_INVALID;
+    }
+    const int cap = (int)n;
+    MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 36) + 1024));
+    MS_TRY(ms_arena_reserve(ctx, msk_east_boxes_scratch(1, cap)));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_in = sb.take<float>((size_t)n * 9);
+    float *d_out = sb.take<float>((size_t)n * 9);
+    int32_t *d_i = sb.take<int32_t>(4);
+    if (!d_i) {
+        ms_set_error("ms_east_boxes_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    h[0] = cap;
+    h[1] = 0;
+    h[2] = orig_h;
+    h[3] = orig_w;
+    MS_CUDA(cudaMemcpyAsync(d_i, h, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_in, quads, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_east_boxes(ctx, d_in, d_i, 1, cap, p, d_i + 2, d_out, d_i + 1, bump, st));
+    MS_CUDA(cudaMemcpyAsync(h + 8, d_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    const int m = h[8];
+    if (m > 0) {
+        MS_CUDA(cudaMemcpyAsync(out, d_out, (size_t)m * 36, cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+    }
+    *m_out = m;
+    return MS_OK;
+}
+
+extern "C" int ms_word_rects_host(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w, int min_text_size,
+                                  int32_t *rects, uint8_t *valid)
+{
+    MS_CTX(ctx);
+    if (n < 0 || (n > 0 && (!polys8 || !rects || !valid))) {
+        ms_set_error("ms_word_rects_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    MS_TRY(ms_stage_reserve(ctx, al256((size_t)n * 32) + al256((size_t)n * 16) + al256((size_t)n) + 1024));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_p = sb.take<float>((size_t)n * 8);
+    int32_t *d_r = sb.take<int32_t>((size_t)n * 4);
+    uint8_t *d_v = sb.take<uint8_t>((size_t)n);
+    if (!d_v) {
+        ms_set_error("ms_word_rects_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_p, polys8, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    MS_TRY(msk_word_rects_flat(ctx, d_p, n, img_h, img_w, min_text_size, d_r, d_v, st));
+    MS_CUDA(cudaMemcpyAsync(rects, d_r, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(valid, d_v, (size_t)n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+__global__ void ms_rects_to_crops_kernel(const int32_t *__restrict__ rects, int64_t n, int32_t *__restrict__ crops,
+                                         int32_t *__restrict__ n_crops)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        crops[i * 5] = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) crops[i * 5 + 1 + k] = rects[i * 4 + k];
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) *n_crops = (int32_t)n;
+}
+
+extern "C" int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const int32_t *rects,
+                                       int64_t n, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8)
+{
+    MS_CTX(ctx);
+    if (n < 0 || img_h <= 0 || img_w <= 0 || out_h <= 0 || out_w <= 0 || (n > 0 && (!page || !rects)) ||
+        (!batch_f32 && !canvas_u8)) {
+        ms_set_error("ms_crop_resize_pad_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    if (n >= (int64_t)1 << 30) {
+        ms_set_error("ms_crop_resize_pad_host: n too large");
+        return MS_ERR_INVALID;
+    }
+    const size_t page_bytes = (size_t)img_h * img_w * 3;
+    const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float), one_u = (size_t)3 * out_h * out_w;
+    size_t need = al256(page_bytes) + al256((size_t)n * 16) + al256((size_t)n * 20) + 1024;
+    if (batch_f32) need += al256((size_t)n * one_f);
+    if (canvas_u8) need += al256((size_t)n * one_u);
+    MS_TRY(ms_stage_reserve(ctx, need));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    uint8_t *d_page = sb.take<uint8_t>(page_bytes);
+    int32_t *d_rects = sb.take<int32_t>((size_t)n * 4);
+    int32_t *d_crops = sb.take<int32_t>((size_t)n * 5);
+    int32_t *d_n = sb.take<int32_t>(1);
+    float *d_f = batch_f32 ? sb.take<float>((size_t)n * 3 * out_h * out_w) : nullptr;
+    uint8_t *d_u = canvas_u8 ? sb.take<uint8_t>((size_t)n * one_u) : nullptr;
+    if (!d_n || (batch_f32 && !d_f) || (canvas_u8 && !d_u)) {
+        ms_set_error("ms_crop_resize_pad_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_page, page, page_bytes, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_rects, rects, (size_t)n * 16, cudaMemcpyHostToDevice, st));
+    {
+        int grid = (int)((n + 255) / 256);
+        if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
+        ms_rects_to_crops_kernel<<<grid, 256, 0, st>>>(d_rects, n, d_crops, d_n);
+        MS_LAUNCH_CHECK(ctx);
+    }
+    MS_TRY(msk_crop(ctx, d_page, 1, img_h, img_w, d_crops, d_n, n, out_h, out_w, d_f, d_u, st));
+    if (batch_f32) MS_CUDA(cudaMemcpyAsync(batch_f32, d_f, (size_t)n * one_f, cudaMemcpyDeviceToHost, st));
+    if (canvas_u8) MS_CUDA(cudaMemcpyAsync(canvas_u8, d_u, (size_t)n * one_u, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
+                                  int map_h, int map_w, int img_h, int img_w, const ms_east_params *p,
+                                  int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
+                                  int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
+                                  float *batch_f32_host, float **batch_dev_out, int32_t *flags)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!score || !geo || !p || !boxes_out || !box_counts || !flags || cap_boxes <= 0 || map_h <= 0 || map_w <= 0) {
+        ms_set_error("ms_page_batch_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    const bool want_crops = pages != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
+    const bool want_batch = want_crops && (batch_f32_host || batch_dev_out);
+    const size_t plane = (size_t)map_h * map_w;
+    const size_t page_bytes = (size_t)img_h * img_w * 3;
+    const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float);
+    size_t need = al256(n_pages * plane * 4) + al256(n_pages * plane * 32) + al256((size_t)n_pages * cap_boxes * 36) +
+                  2 * al256((size_t)n_pages * 4) + 4096;
+    if (want_crops) need += al256(n_pages * page_bytes) + al256((size_t)crops_cap * 20) + 256;
+    if (want_batch) need += al256((size_t)crops_cap * one_f);
+    MS_TRY(ms_stage_reserve(ctx, need));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_score = sb.take<float>(n_pages * plane);
+    float *d_geo = sb.take<float>(n_pages * plane * 8);
+    float *d_boxes = sb.take<float>((size_t)n_pages * cap_boxes * 9);
+    int32_t *d_cnt = sb.take<int32_t>(n_pages);
+    int32_t *d_flags = sb.take<int32_t>(n_pages);
+    uint8_t *d_pages = want_crops ? sb.take<uint8_t>(n_pages * page_bytes) : nullptr;
+    int32_t *d_crops = want_crops ? sb.take<int32_t>((size_t)crops_cap * 5) : nullptr;
+    int32_t *d_nc = want_crops ? sb.take<int32_t>(1) : nullptr;
+    float *d_batch = want_batch ? sb.take<float>((size_t)crops_cap * 3 * out_h * out_w) : nullptr;
+    if (!d_flags || (want_crops && !d_nc) || (want_batch && !d_batch)) {
+        ms_set_error("ms_page_batch_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_score, score, n_pages * plane * 4, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_geo, geo, n_pages * plane * 32, cudaMemcpyHostToDevice, st));
+    if (want_crops) {
+        MS_CUDA(cudaMemcpyAsync(d_pages, pages, n_pages * page_bytes, cudaMemcpyHostToDevice, st));
+        MS_CUDA(cudaMemsetAsync(d_nc, 0, sizeof(int32_t), st));
+    }
+    MS_TRY(ms_page_batch(ctx, d_score, d_geo, d_pages, n_pages, map_h, map_w, img_h, img_w, p, min_text_size, out_h,
+                         out_w, cap_boxes, d_boxes, d_cnt, d_crops, crops_cap, d_nc, d_batch, nullptr, d_flags, st));
+    MS_CUDA(cudaMemcpyAsync(box_counts, d_cnt, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(flags, d_flags, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(boxes_out, d_boxes, (size_t)n_pages * cap_boxes * 36, cudaMemcpyDeviceToHost, st));
+    if (want_crops) MS_CUDA(cudaMemcpyAsync(n_crops, d_nc, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    int32_t all = 0;
+    for (int i = 0; i < n_pages; i++) all |= flags[i];
+    MS_TRY(flags_to_rc(all, "page_batch"));
+    if (want_crops) {
+        int64_t nc = *n_crops;
+        if (nc > crops_cap) nc = crops_cap;
+        if (nc > 0) {
+            MS_CUDA(cudaMemcpyAsync(crops_out, d_crops, (size_t)nc * 20, cudaMemcpyDeviceToHost, st));
+            if (batch_f32_host)
+                MS_CUDA(cudaMemcpyAsync(batch_f32_host, d_batch, (size_t)nc * one_f, cudaMemcpyDeviceToHost, st));
+            MS_CUDA(cudaStreamSynchronize(st));
+        }
+    }
+    if (batch_dev_out) *batch_dev_out = d_batch;
+    return MS_OK;
+}

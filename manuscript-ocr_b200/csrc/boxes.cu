@@ -1,0 +1,614 @@
+// Box post-processing between NMS and the crop batch, float32, bit-exact with the reference's numpy.
+// Replaces expand_boxes (reference detectors/_east/utils.py:384-422), the EAST box filters
+// (detectors/_east/infer.py:134-233: _scale_boxes_to_original, _remove_fully_contained_boxes,
+// _remove_area_anomalies, _convert_to_axis_aligned) and the crop-rectangle logic of
+// Pipeline.predict / _extract_word_image (_pipeline.py:125-137, 204-221).
+//
+// These stages touch K ~ 10^3 boxes per page (36 B each): they are latency bound, not HBM bound.
+// One CTA per page; every reduction follows numpy's summation order so thresholds compare equal.
+#include "ms_internal.cuh"
+
+namespace {
+
+// ---- utils.py:384-422 expand_boxes, one quad ---------------------------------------------------------
+__device__ __forceinline__ void expand_quad(const float *p, float sx, float sy, float *o)
+{
+    const float eps = (float)1e-6;
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        t[i] = p[2 * i] * p[2 * j + 1] - p[2 * j] * p[2 * i + 1];
+    }
+    float area = ((t[0] + t[1]) + t[2]) + t[3];  // np.sum over the 4-long axis: left to right
+    float sign = area > 0 ? 1.0f : (area < 0 ? -1.0f : 1.0f);
+    if (area != area) sign = area;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int ip = (i + 3) & 3, in = (i + 1) & 3;
+        float e1x = p[2 * i] - p[2 * ip], e1y = p[2 * i + 1] - p[2 * ip + 1];
+        float e2x = p[2 * in] - p[2 * i], e2y = p[2 * in + 1] - p[2 * i + 1];
+        float l1 = sqrtf(e1x * e1x + e1y * e1y);
+        float l2 = sqrtf(e2x * e2x + e2y * e2y);
+        float n1x = sign * e1y / (l1 + eps), n1y = sign * (-e1x) / (l1 + eps);
+        float n2x = sign * e2y / (l2 + eps), n2y = sign * (-e2x) / (l2 + eps);
+        float ax = n1x + n2x, ay = n1y + n2y;
+        float nn = sqrtf(ax * ax + ay * ay);
+        if (nn > 0) {
+            ax = ax / nn;
+            ay = ay / nn;
+        } else {
+            ax = 0.0f;
+            ay = 0.0f;
+        }
+        float off = l1 < l2 ? l1 : l2;
+        if (l1 != l1 || l2 != l2) off = NAN;
+        o[2 * i] = p[2 * i] + (sx * off) * ax;
+        o[2 * i + 1] = p[2 * i + 1] + (sy * off) * ay;
+    }
+    o[8] = p[8];
+}
+
+__global__ void expand_kernel(const float *__restrict__ quads, int64_t n, double ew, double eh, float *__restrict__ out)
+{
+    const bool ident = (ew == 0 && eh == 0);  // utils.py:388 returns the input unchanged
+    const float sx = (float)(1.0 + ew) - 1.0f, sy = (float)(1.0 + eh) - 1.0f;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float p[9], o[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) p[k] = quads[i * 9 + k];
+        if (ident) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) o[k] = p[k];
+        } else {
+            expand_quad(p, sx, sy, o);
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) out[i * 9 + k] = o[k];
+    }
+}
+
+// infer.py:174-183
+__device__ __forceinline__ float quad_area_f32(const float *p)
+{
+    float t[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        int j = (i + 1) & 3;
+        t[i] = p[2 * i] * p[2 * j + 1] - p[2 * i + 1] * p[2 * j];
+    }
+    float s = ((t[0] + t[1]) + t[2]) + t[3];
+    return 0.5f * fabsf(s);
+}
+
+// cv2.pointPolygonTest(contour f32 (4 pts), pt, measureDist=False), called from infer.py:185-192
+__device__ __forceinline__ int point_in_quad(const float *cnt, float px, float py)
+{
+    int counter = 0;
+    float vx = cnt[6], vy = cnt[7];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        float v0x = vx, v0y = vy;
+        vx = cnt[2 * i];
+        vy = cnt[2 * i + 1];
+        if ((v0y <= py && vy <= py) || (v0y > py && vy > py) || (v0x < px && vx < px)) {
+            if (py == vy && (px == vx || (py == v0y && ((v0x <= px && px <= vx) || (vx <= px && px <= v0x))))) return 0;
+            continue;
+        }
+        double dist = (double)(py - v0y) * (double)(vx - v0x) - (double)(px - v0x) * (double)(vy - v0y);
+        if (dist == 0) return 0;
+        if (vy < v0y) dist = -dist;
+        counter += dist > 0;
+    }
+    return (counter & 1) ? 1 : -1;
+}
+
+__device__ __forceinline__ bool quad_inside(const float *inner, const float *outer)
+{
+#pragma unroll
+    for (int v = 0; v < 4; v++)
+        if (point_in_quad(outer, inner[2 * v], inner[2 * v + 1]) < 0) return false;
+    return true;
+}
+
+// numpy pairwise summation of a contiguous f32 vector (np.add.reduce; oracle.c np_pairwise_f32)
+__device__ float np_pairwise_f32(const float *a, int n)
+{
+    if (n < 8) {
+        float r = -0.0f;
+        for (int i = 0; i < n; i++) r += a[i];
+        return r;
+    } else if (n <= 128) {
+        float r[8];
+        for (int k = 0; k < 8; k++) r[k] = a[k];
+        int i;
+        for (i = 8; i < n - (n % 8); i += 8)
+            for (int k = 0; k < 8; k++) r[k] += a[i + k];
+        float res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+        for (; i < n; i++) res += a[i];
+        return res;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        return np_pairwise_f32(a, n2) + np_pairwise_f32(a + n2, n - n2);
+    }
+}
+
+__device__ __forceinline__ bool area_before(float aa, int ia, float ab, int ib)
+{
+    // position in np.argsort(areas, kind="stable"): ascending, NaN last, ties by index
+    bool an = aa != aa, bn = ab != ab;
+    if (an || bn) {
+        if (an != bn) return bn;
+        return ia < ib;
+    }
+    if (aa < ab) return true;
+    if (aa > ab) return false;
+    return ia < ib;
+}
+
+struct EastScratch {
+    float *work;      // (P*cap, 9) expanded + scaled quads
+    float *area;      // P*cap
+    int32_t *order;   // P*cap: box index at each area rank
+    int32_t *rank;    // P*cap
+    uint8_t *removed; // P*cap
+    uint8_t *needseq; // P*cap
+    float *karea;     // P*cap compacted areas / deviations
+    float *kdev;
+    int32_t *kidx;    // P*cap compacted indices
+};
+
+__device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    __syncthreads();
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = lane < nw ? s_warp[lane] : 0;
+        int winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += t;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+
+// One CTA per page: expand -> scale -> contained removal -> anomaly removal -> axis align.
+__global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict__ quads,
+                                                         const int32_t *__restrict__ counts, int cap,
+                                                         ms_east_params P, const int32_t *__restrict__ orig_hw,
+                                                         EastScratch S, float *__restrict__ out,
+                                                         int32_t *__restrict__ counts_out)
+{
+    const int page = blockIdx.x;
+    const int K = counts[page];
+    const size_t pb = (size_t)page * cap;
+    float *work = S.work + pb * 9;
+    float *area = S.area + pb;
+    int32_t *order = S.order + pb, *rank = S.rank + pb, *kidx = S.kidx + pb;
+    uint8_t *removed = S.removed + pb, *needseq = S.needseq + pb;
+    float *karea = S.karea + pb, *kdev = S.kdev + pb;
+    __shared__ int s_warp[33];
+    __shared__ int s_flag;
+    __shared__ float s_thr;
+    __shared__ int s_apply;
+
+    // 1) expand (utils.py:384) + scale to the original image (infer.py:134-147)
+    const bool ident = (P.expand_ratio_w == 0 && P.expand_ratio_h == 0);
+    const float ex = (float)(1.0 + P.expand_ratio_w) - 1.0f, ey = (float)(1.0 + P.expand_ratio_h) - 1.0f;
+    int oh = P.target_size, ow = P.target_size;
+    if (orig_hw) {
+        oh = orig_hw[2 * page];
+        ow = orig_hw[2 * page + 1];
+    }
+    const float sx = (float)((double)ow / (double)P.target_size);
+    const float sy = (float)((double)oh / (double)P.target_size);
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        float p[9], o[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) p[k] = quads[(pb + i) * 9 + k];
+        if (ident) {
+#pragma unroll
+            for (int k = 0; k < 9; k++) o[k] = p[k];
+        } else {
+            expand_quad(p, ex, ey, o);
+        }
+#pragma unroll
+        for (int v = 0; v < 4; v++) {
+            o[2 * v] = o[2 * v] * sx;
+            o[2 * v + 1] = o[2 * v + 1] * sy;
+        }
+#pragma unroll
+        for (int k = 0; k < 9; k++) work[(size_t)i * 9 + k] = o[k];
+        area[i] = quad_area_f32(o);
+        removed[i] = 0;
+        needseq[i] = 0;
+    }
+    __syncthreads();
+
+    // 2) infer.py:194-214 contained-box removal, ascending-area scan with the stable tie rule
+    if (K > 1) {
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            float ai = area[i];
+            int r = 0;
+            for (int j = 0; j < K; j++) r += (j != i && area_before(area[j], j, ai, i)) ? 1 : 0;
+            rank[i] = r;
+            order[r] = i;
+        }
+        __syncthreads();
+        const float eps = (float)1e-6;
+        for (int i = threadIdx.x; i < K; i += blockDim.x) {
+            float qi[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) qi[k] = work[(size_t)i * 9 + k];
+            const float ai = area[i];
+            const int ri = rank[i];
+            bool later_hit = false, earlier_hit = false;
+            for (int j = 0; j < K && !later_hit; j++) {
+                if (j == i) continue;
+                if (area[j] + eps < ai) continue;  // infer.py:208
+                float qj[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
+                if (!quad_inside(qi, qj)) continue;
+                if (rank[j] > ri)
+                    later_hit = true;  // j is still unprocessed (kept) when i is visited
+                else
+                    earlier_hit = true;  // j's own fate decides
+            }
+            removed[i] = later_hit ? 1 : 0;
+            needseq[i] = (!later_hit && earlier_hit) ? 1 : 0;
+        }
+        __syncthreads();
+        // the rare boxes whose only containers precede them in the scan (near-equal areas, duplicates):
+        // resolved in rank order, each one cooperatively
+        for (int r = 0; r < K; r++) {
+            const int i = order[r];
+            if (!needseq[i]) continue;  // uniform: same value read by every thread
+            if (threadIdx.x == 0) s_flag = 0;
+            __syncthreads();
+            float qi[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) qi[k] = work[(size_t)i * 9 + k];
+            const float ai = area[i];
+            bool hit = false;
+            for (int j = threadIdx.x; j < K && !hit; j += blockDim.x) {
+                if (j == i || rank[j] > r || removed[j]) continue;
+                if (area[j] + eps < ai) continue;
+                float qj[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
+                hit = quad_inside(qi, qj);
+            }
+            if (hit) s_flag = 1;
+            __syncthreads();
+            if (threadIdx.x == 0) removed[i] = s_flag ? 1 : 0;
+            __syncthreads();
+        }
+    }
+
+    // compaction 1 (original order)
+    int K1 = 0;
+    for (int base = 0; base < K; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int k = (i < K && !removed[i]) ? 1 : 0;
+        int total;
+        int pos = block_excl_scan(k, s_warp, total);
+        if (k) {
+            kidx[K1 + pos] = i;
+            karea[K1 + pos] = area[i];
+        }
+        K1 += total;
+    }
+    __syncthreads();
+
+    // 3) infer.py:216-233 area anomalies: numpy f32 mean / std (pairwise sums), threshold in f32
+    if (threadIdx.x == 0) s_apply = 0;
+    __syncthreads();
+    if (P.remove_area_anomalies && K1 > 0 && K1 > P.anomaly_min_box_count) {
+        __shared__ float s_mean;
+        if (threadIdx.x == 0) s_mean = np_pairwise_f32(karea, K1) / (float)K1;
+        __syncthreads();
+        const float mean32 = s_mean;
+        for (int i = threadIdx.x; i < K1; i += blockDim.x) {
+            float d = karea[i] - mean32;
+            kdev[i] = d * d;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float var32 = np_pairwise_f32(kdev, K1) / (float)K1;
+            float std32 = sqrtf(var32);
+            double stdv = (double)std32;
+            if (stdv != 0.0) {
+                double thr = (double)mean32 + P.anomaly_sigma_threshold * stdv;
+                s_thr = (float)thr;
+                s_apply = 1;
+            }
+        }
+        __syncthreads();
+        if (s_apply) {
+            // `if not np.any(keep): return quads`
+            if (threadIdx.x == 0) s_flag = 0;
+            __syncthreads();
+            bool any = false;
+            for (int i = threadIdx.x; i < K1; i += blockDim.x) any = any || (karea[i] <= s_thr);
+            if (any) s_flag = 1;
+            __syncthreads();
+            if (threadIdx.x == 0 && !s_flag) s_apply = 0;
+            __syncthreads();
+        }
+    }
+    const bool apply = s_apply != 0;
+    const float athr = s_thr;
+
+    // compaction 2 + 4) infer.py:149-172 axis alignment, write
+    int K2 = 0;
+    for (int base = 0; base < K1; base += blockDim.x) {
+        int t = base + threadIdx.x;
+        int k = (t < K1 && (!apply || karea[t] <= athr)) ? 1 : 0;
+        int total;
+        int pos = block_excl_scan(k, s_warp, total);
+        if (k) {
+            const float *q = work + (size_t)kidx[t] * 9;
+            float *o = out + (pb + K2 + pos) * 9;
+            if (P.axis_aligned_output) {
+                float x0 = q[0], x1 = q[0], y0 = q[1], y1 = q[1];
+#pragma unroll
+                for (int v = 1; v < 4; v++) {
+                    x0 = q[2 * v] < x0 ? q[2 * v] : x0;
+                    x1 = q[2 * v] > x1 ? q[2 * v] : x1;
+                    y0 = q[2 * v + 1] < y0 ? q[2 * v + 1] : y0;
+                    y1 = q[2 * v + 1] > y1 ? q[2 * v + 1] : y1;
+                }
+                o[0] = x0; o[1] = y0; o[2] = x1; o[3] = y0;
+                o[4] = x1; o[5] = y1; o[6] = x0; o[7] = y1;
+            } else {
+#pragma unroll
+                for (int k2 = 0; k2 < 8; k2++) o[k2] = q[k2];
+            }
+            o[8] = q[8];
+        }
+        K2 += total;
+    }
+    if (threadIdx.x == 0) counts_out[page] = K2;
+}
+
+// ---- _pipeline.py:125-137, 204-221 ---------------------------------------------------------------------
+__device__ __forceinline__ int py_slice(int start, int stop, int dim, int &s_out)
+{
+    if (start < 0) {
+        start += dim;
+        if (start < 0) start = 0;
+    } else if (start > dim)
+        start = dim;
+    if (stop < 0) {
+        stop += dim;
+        if (stop < 0) stop = 0;
+    } else if (stop > dim)
+        stop = dim;
+    s_out = start;
+    return stop > start ? stop - start : 0;
+}
+
+__device__ __forceinline__ int f2i_trunc(float v)
+{
+    // np.array(list of python floats, dtype=int32): C cast; out-of-range / NaN is undefined there --
+    // x86 yields INT_MIN, reproduced here
+    if (!(v > -2147483904.0f && v < 2147483648.0f)) return INT_MIN;
+    return (int)v;
+}
+
+__device__ __forceinline__ bool word_rect(const float *q, int img_h, int img_w, int min_text, int *rect)
+{
+    int xmin, xmax, ymin, ymax;
+    xmin = xmax = f2i_trunc(q[0]);
+    ymin = ymax = f2i_trunc(q[1]);
+#pragma unroll
+    for (int v = 1; v < 4; v++) {
+        int x = f2i_trunc(q[2 * v]), y = f2i_trunc(q[2 * v + 1]);
+        xmin = min(xmin, x);
+        xmax = max(xmax, x);
+        ymin = min(ymin, y);
+        ymax = max(ymax, y);
+    }
+    rect[0] = rect[1] = rect[2] = rect[3] = 0;
+    // numpy int32 subtraction wraps; widths here are far from overflow on every supported input
+    if (!((long long)xmax - xmin >= min_text && (long long)ymax - ymin >= min_text)) return false;
+    int x1 = max(0, xmin), y1 = max(0, ymin);
+    int x2 = min(img_w, xmax), y2 = min(img_h, ymax);
+    int sx, sy;
+    int w = py_slice(x1, x2, img_w, sx);
+    int h = py_slice(y1, y2, img_h, sy);
+    if (w <= 0 || h <= 0) return false;
+    rect[0] = sx;
+    rect[1] = sy;
+    rect[2] = sx + w;
+    rect[3] = sy + h;
+    return true;
+}
+
+__global__ void word_rects_flat_kernel(const float *__restrict__ polys8, int64_t n, int img_h, int img_w, int min_text,
+                                       int32_t *__restrict__ rects, uint8_t *__restrict__ valid)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        float q[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) q[k] = polys8[i * 8 + k];
+        int r[4];
+        bool ok = word_rect(q, img_h, img_w, min_text, r);
+#pragma unroll
+        for (int k = 0; k < 4; k++) rects[i * 4 + k] = r[k];
+        valid[i] = ok ? 1 : 0;
+    }
+}
+
+// one CTA per page: ordered compaction of valid crops into a page-strided temp list
+__global__ void __launch_bounds__(256) word_rects_page_kernel(const float *__restrict__ quads,
+                                                              const int32_t *__restrict__ counts, int cap,
+                                                              const int32_t *__restrict__ img_hw, int img_h, int img_w,
+                                                              int min_text, int32_t *__restrict__ tmp,
+                                                              int32_t *__restrict__ page_n)
+{
+    const int page = blockIdx.x;
+    const int K = counts[page];
+    const size_t pb = (size_t)page * cap;
+    if (img_hw) {
+        img_h = img_hw[2 * page];
+        img_w = img_hw[2 * page + 1];
+    }
+    __shared__ int s_warp[33];
+    int run = 0;
+    for (int base = 0; base < K; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int r[4] = {0, 0, 0, 0};
+        int ok = 0;
+        if (i < K) {
+            float q[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) q[k] = quads[(pb + i) * 9 + k];
+            ok = word_rect(q, img_h, img_w, min_text, r) ? 1 : 0;
+        }
+        int total;
+        int pos = block_excl_scan(ok, s_warp, total);
+        if (ok) {
+            int32_t *d = tmp + (pb + run + pos) * 4;
+            d[0] = r[0]; d[1] = r[1]; d[2] = r[2]; d[3] = r[3];
+        }
+        run += total;
+    }
+    if (threadIdx.x == 0) page_n[page] = run;
+}
+
+__global__ void word_rects_offsets_kernel(const int32_t *__restrict__ page_n, int n_pages, int32_t *page_off,
+                                          int64_t crops_cap, int32_t *n_crops)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        long long run = 0;
+        for (int p = 0; p < n_pages; p++) {
+            page_off[p] = (int32_t)run;
+            run += page_n[p];
+        }
+        page_off[n_pages] = (int32_t)run;
+        *n_crops = (int32_t)(run > crops_cap ? crops_cap : run);
+    }
+}
+
+__global__ void word_rects_pack_kernel(const int32_t *__restrict__ tmp, const int32_t *__restrict__ page_n,
+                                       const int32_t *__restrict__ page_off, int n_pages, int cap, int64_t crops_cap,
+                                       int32_t *__restrict__ crops)
+{
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int p = (int)(g / cap), i = (int)(g % cap);
+    if (p >= n_pages || i >= page_n[p]) return;
+    int64_t dst = (int64_t)page_off[p] + i;
+    if (dst >= crops_cap) return;
+    const int32_t *s = tmp + ((size_t)p * cap + i) * 4;
+    int32_t *d = crops + dst * 5;
+    d[0] = p; d[1] = s[0]; d[2] = s[1]; d[3] = s[2]; d[4] = s[3];
+}
+
+void carve_east(ms_bump &bump, EastScratch &S, size_t n)
+{
+    S.work = bump.take<float>(n * 9);
+    S.area = bump.take<float>(n);
+    S.order = bump.take<int32_t>(n);
+    S.rank = bump.take<int32_t>(n);
+    S.removed = bump.take<uint8_t>(n);
+    S.needseq = bump.take<uint8_t>(n);
+    S.karea = bump.take<float>(n);
+    S.kdev = bump.take<float>(n);
+    S.kidx = bump.take<int32_t>(n);
+}
+
+}  // namespace
+
+int msk_expand(ms_ctx *ctx, const float *quads, int64_t n, double ew, double eh, float *out, cudaStream_t st)
+{
+    if (n <= 0) return MS_OK;
+    int grid = (int)((n + 127) / 128);
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    expand_kernel<<<grid, 128, 0, st>>>(quads, n, ew, eh, out);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+size_t msk_east_boxes_scratch(int n_pages, int cap_per_page)
+{
+    ms_bump probe{nullptr, 0, 0};
+    EastScratch S;
+    carve_east(probe, S, (size_t)n_pages * cap_per_page);
+    return probe.off + 4096;
+}
+
+int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
+                   ms_bump bump, cudaStream_t st)
+{
+    if (n_pages <= 0) return MS_OK;
+    if (!p || p->target_size <= 0) {
+        ms_set_error("east_boxes: bad params");
+        return MS_ERR_INVALID;
+    }
+    EastScratch S;
+    carve_east(bump, S, (size_t)n_pages * cap_per_page);
+    if (!S.kidx) {
+        ms_set_error("east_boxes: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    // device recursion in np_pairwise_f32: depth <= log2(cap/128) + 1 frames of a few dozen bytes
+    east_boxes_kernel<<<n_pages, 512, 0, st>>>(quads, counts, cap_per_page, *p, orig_hw, S, quads_out, counts_out);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+size_t msk_word_rects_scratch(int n_pages) { return (size_t)(2 * n_pages + 2) * sizeof(int32_t) + 1024; }
+
+// NOTE: the page-strided temp list (n_pages*cap*4 int32) is taken from the bump as well.
+int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                   const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
+                   int64_t crops_cap, int32_t *n_crops, ms_bump bump, cudaStream_t st)
+{
+    if (n_pages <= 0) return MS_OK;
+    int32_t *page_n = bump.take<int32_t>(n_pages);
+    int32_t *page_off = bump.take<int32_t>(n_pages + 1);
+    int32_t *tmp = bump.take<int32_t>((size_t)n_pages * cap_per_page * 4);
+    if (!tmp) {
+        ms_set_error("word_rects: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    word_rects_page_kernel<<<n_pages, 256, 0, st>>>(quads, counts, cap_per_page, img_hw, img_h, img_w, min_text_size,
+                                                    tmp, page_n);
+    MS_LAUNCH_CHECK(ctx);
+    word_rects_offsets_kernel<<<1, 32, 0, st>>>(page_n, n_pages, page_off, crops_cap, n_crops);
+    MS_LAUNCH_CHECK(ctx);
+    size_t threads = (size_t)n_pages * cap_per_page;
+    word_rects_pack_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(tmp, page_n, page_off, n_pages, cap_per_page,
+                                                                         crops_cap, crops_out);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+int msk_word_rects_flat(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w, int min_text_size,
+                        int32_t *rects, uint8_t *valid, cudaStream_t st)
+{
+    if (n <= 0) return MS_OK;
+    int grid = (int)((n + 127) / 128);
+    if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
+    word_rects_flat_kernel<<<grid, 128, 0, st>>>(polys8, n, img_h, img_w, min_text_size, rects, valid);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}

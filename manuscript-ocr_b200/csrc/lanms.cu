@@ -1,0 +1,726 @@
+// Locality-aware merge + polygon-IoU NMS on the device, float64, bit-exact with the reference.
+// Replaces locality_aware_nms / standard_nms / polygon_iou (reference detectors/_east/lanms.py).
+//
+// What the reference computes (lanms.py:156-207), per page:
+//   1. stable sort of the (N,9) candidates by x0 = boxes[:,0]                       (lanms.py:166)
+//   2. a SEQUENTIAL scan: box i merges into the last cluster iff IoU(box_i, last_poly) > thr,
+//      weighted vertex average after normalize_polygon, score = max         (lanms.py:174-192)
+//   3. greedy NMS over the clusters in descending score, subject = kept box   (lanms.py:133-153)
+//   4. rows = kept clusters in that order, cast to f32                          (lanms.py:204-207)
+//
+// How it is parallelised without changing a single decision:
+//   (2) A non-merge resets the scan state to the box itself, so the state after any cluster start is
+//       known without history.  hot[i] = IoU(box_i, box_{i-1}) > thr is computed for every i in
+//       parallel; every hot position speculatively runs the sequential merge from start(box_{i-1})
+//       until the first non-merge (lanms_runs_kernel); a per-page pass then walks the hot positions
+//       in order and accepts a run only if its predecessor really is a cluster start (i.e. is not
+//       covered by an earlier accepted run).  Accepted runs + untouched singletons are exactly the
+//       reference's clusters, in creation order.  Worst case (one giant cluster) degrades to the
+//       sequential cost on the device, never to a wrong answer.
+//   (3) suppression edges hi->lo (IoU(hi,lo) > thr, hi earlier in stable score order) are found by
+//       a sweep over clusters in their x0 order with an inflated-bounding-box prefilter, then the
+//       greedy recurrence keep[i] = !any(keep[j], j->i) is resolved in rounds (a node is decided as
+//       soon as all its predecessors are).  Identical to the sequential loop because the IoU
+//       predicate is a pure function of the ordered pair.
+//       The bbox prefilter is exact only for convex, positively oriented clip quads (for those the
+//       Sutherland-Hodgman result is empty when the boxes are apart); any other quad ("irregular":
+//       concave, self-intersecting, clockwise, degenerate, non-finite) is paired with every box of
+//       its page, and thr < 0 (where IoU==0 pairs merge too) disables the prefilter altogether.
+//
+// Roofline: this stage is NOT HBM bound (36 B/box in, 36 B/kept out); it is bounded by fp64 ALU
+// latency of the clip and by the serial dependencies above.
+#include "ms_internal.cuh"
+
+namespace {
+
+constexpr int kEdgeFactor = 16;  // suppression-edge capacity per candidate (overflow -> flag)
+
+struct LanmsBuffers {
+    int32_t *page_off;   // n_pages+1 exclusive offsets of candidate counts (packed space)
+    int32_t *n_total;    // == page_off[n_pages]
+    uint64_t *keys, *keys_tmp;
+    uint32_t *vals, *vals_tmp;
+    double *sq;          // sorted candidate polys, 8 doubles each
+    float *ss;           // sorted candidate scores (f32 exact)
+    int32_t *pos_page;   // page of each packed position
+    uint8_t *mflag;      // 0 anchor / 1 merged / 2 accepted run head
+    uint8_t *hot;
+    int32_t *hot_list;
+    int32_t *hot_count;
+    int32_t *run_end;
+    double *run_poly;
+    double *run_score;
+    // clusters, stored at page_off[p] + c
+    double *cl_poly;
+    double *cl_score;
+    float *cl_key;
+    float4 *cl_bbox;
+    uint8_t *cl_irr;
+    int32_t *cl_orig;    // priority tie-break index (creation order)
+    int32_t *cl_count;   // per page
+    float *page_slack;   // per page: max(key - minx) over regular clusters
+    uint64_t *edges;
+    int32_t *edge_count; // per page
+    uint8_t *state;      // 0 undecided / 1 kept / 2 suppressed
+    uint8_t *blocked;
+    int32_t *kept_list;
+};
+
+// ---- helpers ------------------------------------------------------------------------------------
+__device__ __forceinline__ bool prio_before(double sa, int ia, double sb, int ib)
+{
+    // position in np.argsort(-scores, kind="stable"): larger score first, NaN last, ties by index
+    bool an = sa != sa, bn = sb != sb;
+    if (an || bn) {
+        if (an != bn) return bn;
+        return ia < ib;
+    }
+    if (sa > sb) return true;
+    if (sa < sb) return false;
+    return ia < ib;
+}
+
+__device__ __forceinline__ void load_quad(const double *__restrict__ src, double *dst)
+{
+    const double2 *s2 = reinterpret_cast<const double2 *>(src);
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        double2 t = s2[k];
+        dst[2 * k] = t.x;
+        dst[2 * k + 1] = t.y;
+    }
+}
+
+// convex + positively oriented + finite, with a relative margin; also returns the inflated bbox
+__device__ __forceinline__ bool quad_regular_bbox(const double *p, float4 &bb)
+{
+    double minx = p[0], maxx = p[0], miny = p[1], maxy = p[1];
+    bool finite = true;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        double x = p[2 * v], y = p[2 * v + 1];
+        finite = finite && (fabs(x) < 1e30) && (fabs(y) < 1e30);  // false for NaN/Inf too
+        minx = fmin(minx, x);
+        maxx = fmax(maxx, x);
+        miny = fmin(miny, y);
+        maxy = fmax(maxy, y);
+    }
+    bool convex = true;
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        int a = v, b = (v + 1) & 3, c = (v + 2) & 3;
+        double e1x = p[2 * b] - p[2 * a], e1y = p[2 * b + 1] - p[2 * a + 1];
+        double e2x = p[2 * c] - p[2 * b], e2y = p[2 * c + 1] - p[2 * b + 1];
+        double cr = e1x * e2y - e1y * e2x;
+        double l1 = e1x * e1x + e1y * e1y, l2 = e2x * e2x + e2y * e2y;
+        // sin(angle) > 1e-3 and both edges longer than 1e-3 px
+        convex = convex && (cr > 0) && (cr * cr > 1e-6 * l1 * l2) && (l1 > 1e-6) && (l2 > 1e-6);
+    }
+    if (!(finite && convex)) {
+        bb = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
+        return false;
+    }
+    double ext = fmax(fmax(fabs(minx), fabs(maxx)), fmax(fabs(miny), fabs(maxy)));
+    double m = 1e-3 + 1e-6 * ext;
+    bb.x = __double2float_rd(minx - m);
+    bb.y = __double2float_rd(miny - m);
+    bb.z = __double2float_ru(maxx + m);
+    bb.w = __double2float_ru(maxy + m);
+    return true;
+}
+
+// ---- 0. page offsets ---------------------------------------------------------------------------------
+__global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_pages, int32_t *page_off,
+                                     int32_t *n_total, int32_t *hot_count, int32_t *edge_count)
+{
+    // one thread: n_pages is small (<= a few thousand)
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        int run = 0;
+        for (int p = 0; p < n_pages; p++) {
+            page_off[p] = run;
+            run += counts[p];
+            edge_count[p] = 0;
+        }
+        page_off[n_pages] = run;
+        *n_total = run;
+        *hot_count = 0;
+    }
+}
+
+// ---- 1. sort keys (page | orderable x0), values = strided source row ---------------------------------
+__global__ void lanms_keys_kernel(const float *__restrict__ quads, const int32_t *__restrict__ counts,
+                                  const int32_t *__restrict__ page_off, int n_pages, int cap,
+                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+{
+    size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    int p = (int)(g / cap), i = (int)(g % cap);
+    if (p >= n_pages || i >= counts[p]) return;
+    size_t row = (size_t)p * cap + i;
+    int dst = page_off[p] + i;
+    keys[dst] = ((uint64_t)p << 32) | ms_orderable_f32(quads[row * 9]);
+    vals[dst] = (uint32_t)row;
+}
+
+// ---- 2. gather into sorted order (f64) + hot bits -----------------------------------------------------
+__global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__restrict__ quads,
+                                                               const uint64_t *__restrict__ keys,
+                                                               const uint32_t *__restrict__ vals,
+                                                               const int32_t *__restrict__ page_off,
+                                                               const int32_t *__restrict__ n_total, double thr,
+                                                               LanmsBuffers B)
+{
+    const int n = *n_total;
+    double buf[4 * MS_MAXV];
+    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
+        int page = (int)(keys[s] >> 32);
+        const float *row = quads + (size_t)vals[s] * 9;
+        double me[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) me[k] = (double)row[k];
+        double2 *dst = reinterpret_cast<double2 *>(B.sq + (size_t)s * 8);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = make_double2(me[2 * k], me[2 * k + 1]);
+        B.ss[s] = row[8];
+        B.pos_page[s] = page;
+        B.mflag[s] = 0;
+        bool is_hot = false;
+        if (s > page_off[page]) {
+            const float *prow = quads + (size_t)vals[s - 1] * 9;
+            double pv[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) pv[k] = (double)prow[k];
+            is_hot = ms_quad_iou(me, pv, buf) > thr;  // lanms.py:180 subject = new box, clip = last
+        }
+        B.hot[s] = is_hot ? 1 : 0;
+        if (is_hot) {
+            int slot = atomicAdd(B.hot_count, 1);
+            B.hot_list[slot] = s;
+        }
+    }
+}
+
+// ---- 3. speculative runs from every hot position ---------------------------------------------------------
+__global__ void __launch_bounds__(128) lanms_runs_kernel(const int32_t *__restrict__ page_off, double thr,
+                                                         LanmsBuffers B)
+{
+    const int nh = *B.hot_count;
+    double buf[4 * MS_MAXV];
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nh; j += gridDim.x * blockDim.x) {
+        const int h = B.hot_list[j];
+        const int page_end = page_off[B.pos_page[h] + 1];
+        double L[8], nb[8], al[8];
+        load_quad(B.sq + (size_t)(h - 1) * 8, L);
+        double wsum = (double)B.ss[h - 1];
+        double score = wsum;
+        int i = h;
+        load_quad(B.sq + (size_t)i * 8, nb);
+        while (true) {
+            // merge box i into the running cluster (lanms.py:181-188)
+            double sc = (double)B.ss[i];
+            ms_align_vertices(L, nb, al);
+            double tw = wsum + sc;
+#pragma unroll
+            for (int k = 0; k < 8; k++) L[k] = (L[k] * wsum + al[k] * sc) / tw;
+            wsum = tw;
+            score = (sc > score) ? sc : score;  // python max(old, new)
+            i++;
+            if (i >= page_end) break;
+            load_quad(B.sq + (size_t)i * 8, nb);
+            if (!(ms_quad_iou(nb, L, buf) > thr)) break;
+        }
+        B.run_end[h] = i;
+        double2 *dst = reinterpret_cast<double2 *>(B.run_poly + (size_t)h * 8);
+#pragma unroll
+        for (int k = 0; k < 4; k++) dst[k] = make_double2(L[2 * k], L[2 * k + 1]);
+        B.run_score[h] = score;
+    }
+}
+
+// ---- 4. accept runs in order, build clusters (one CTA per page) --------------------------------------------
+constexpr int kResolveThreads = 1024;
+
+__device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = v;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, inc, off);
+        if (lane >= off) inc += t;
+    }
+    __syncthreads();  // protect s_warp reuse
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+        int winc = w;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, winc, off);
+            if (lane >= off) winc += t;
+        }
+        s_warp[lane] = winc - w;
+        if (lane == 31) s_warp[32] = winc;
+    }
+    __syncthreads();
+    total = s_warp[32];
+    return s_warp[warp] + inc - v;
+}
+
+__global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const int32_t *__restrict__ page_off,
+                                                                         int all_irregular, LanmsBuffers B)
+{
+    const int page = blockIdx.x;
+    const int p0 = page_off[page], p1 = page_off[page + 1];
+    __shared__ int s_warp[33];
+    __shared__ int s_h[kResolveThreads], s_e[kResolveThreads];
+    __shared__ int s_vh[kResolveThreads], s_ve[kResolveThreads];
+    __shared__ int s_nvalid, s_klast;
+    __shared__ float s_slack[32];
+    if (threadIdx.x == 0) s_klast = p0 - 1;
+    __syncthreads();
+
+    // phase A: walk hot positions in order, accept a run iff its head lies beyond the last accepted run
+    for (int base = p0; base < p1; base += kResolveThreads) {
+        int s = base + threadIdx.x;
+        int flag = (s < p1 && B.hot[s]) ? 1 : 0;
+        int total;
+        int pos = block_excl_scan_1024(flag, s_warp, total);
+        if (flag) {
+            s_h[pos] = s;
+            s_e[pos] = B.run_end[s];
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int klast = s_klast, nv = 0;
+            for (int j = 0; j < total; j++) {
+                int h = s_h[j];
+                if (h > klast) {
+                    klast = s_e[j];
+                    s_vh[nv] = h;
+                    s_ve[nv] = klast;
+                    nv++;
+                }
+            }
+            s_klast = klast;
+            s_nvalid = nv;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < s_nvalid; j += kResolveThreads) {
+            int h = s_vh[j], e = s_ve[j];
+            B.mflag[h] = 2;
+            for (int i = h + 1; i < e; i++) B.mflag[i] = 1;
+        }
+        __syncthreads();
+    }
+    __threadfence_block();
+    __syncthreads();
+
+    // phase B: anchors (mflag == 0) in order are the clusters
+    int run_base = 0;
+    float slack = 0.0f;
+    for (int base = p0; base < p1; base += kResolveThreads) {
+        int s = base + threadIdx.x;
+        int anchor = (s < p1 && B.mflag[s] == 0) ? 1 : 0;
+        int total;
+        int pos = block_excl_scan_1024(anchor, s_warp, total);
+        if (anchor) {
+            int c = run_base + pos;
+            size_t slot = (size_t)p0 + c;
+            bool has_run = (s + 1 < p1) && (B.mflag[s + 1] == 2);
+            double poly[8];
+            double score;
+            if (has_run) {
+                load_quad(B.run_poly + (size_t)(s + 1) * 8, poly);
+                score = B.run_score[s + 1];
+            } else {
+                load_quad(B.sq + (size_t)s * 8, poly);
+                score = (double)B.ss[s];
+            }
+            double2 *dst = reinterpret_cast<double2 *>(B.cl_poly + slot * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) dst[k] = make_double2(poly[2 * k], poly[2 * k + 1]);
+            B.cl_score[slot] = score;
+            float key = (float)B.sq[(size_t)s * 8];  // anchor x0: the (sorted) sweep key
+            B.cl_key[slot] = key;
+            float4 bb;
+            bool reg = quad_regular_bbox(poly, bb) && !all_irregular;
+            if (!reg) bb = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
+            B.cl_bbox[slot] = bb;
+            B.cl_irr[slot] = reg ? 0 : 1;
+            B.cl_orig[slot] = c;
+            B.state[slot] = 0;
+            if (reg) slack = fmaxf(slack, key - bb.x);
+        }
+        run_base += total;
+    }
+    // page slack = max over regular clusters of (key - minx); keys are sorted, so every box that can
+    // overlap box a starts no later than maxx_a + slack in key order
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) slack = fmaxf(slack, __shfl_xor_sync(0xffffffffu, slack, off));
+    if ((threadIdx.x & 31) == 0) s_slack[threadIdx.x >> 5] = slack;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = 0.0f;
+        for (int w = 0; w < kResolveThreads / 32; w++) m = fmaxf(m, s_slack[w]);
+        B.page_slack[page] = m;
+        B.cl_count[page] = run_base;
+    }
+}
+
+// ---- 5. suppression edges: sweep in key order, bbox prefilter, fp64 clip -------------------------------------
+constexpr int kPairThreads = 128;
+constexpr int kPairWarps = kPairThreads / 32;
+constexpr int kQueue = 96;  // per-warp pending pairs (flush at >= 32)
+
+__device__ __forceinline__ void eval_pair(int a, int b, int p0, int page, double thr, const LanmsBuffers &B,
+                                          int edge_cap, int32_t *flags, double *buf)
+{
+    // a, b: local cluster indices of `page`
+    size_t sa = (size_t)p0 + a, sb = (size_t)p0 + b;
+    double qa[8], qb[8];
+    load_quad(B.cl_poly + sa * 8, qa);
+    load_quad(B.cl_poly + sb * 8, qb);
+    bool a_first = prio_before(B.cl_score[sa], B.cl_orig[sa], B.cl_score[sb], B.cl_orig[sb]);
+    // lanms.py:149 should_merge(polys[idx] (kept, earlier), polys[idx_j] (later))
+    double iou = a_first ? ms_quad_iou(qa, qb, buf) : ms_quad_iou(qb, qa, buf);
+    if (iou > thr) {
+        int hi = a_first ? a : b, lo = a_first ? b : a;
+        int e = atomicAdd(B.edge_count + page, 1);
+        if (e < edge_cap)
+            B.edges[(size_t)p0 * kEdgeFactor + e] = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
+        else
+            atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
+    }
+}
+
+__global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t *__restrict__ page_off,
+                                                                   const int32_t *__restrict__ n_total, double thr,
+                                                                   LanmsBuffers B, int32_t *flags)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int n = *n_total;
+    __shared__ int2 s_q[kPairWarps][kQueue];
+    __shared__ int s_qpage[kPairWarps][kQueue];
+    int2 *q = s_q[warp];
+    int *qpage = s_qpage[warp];
+    int qn = 0;  // warp-uniform
+    double buf[4 * MS_MAXV];
+    const int wid = blockIdx.x * kPairWarps + warp, nw = gridDim.x * kPairWarps;
+
+    for (int slot = wid; slot < n; slot += nw) {
+        const int page = B.pos_page[slot];
+        const int p0 = page_off[page];
+        const int a = slot - p0;
+        const int C = B.cl_count[page];
+        if (a >= C) continue;
+        const bool a_irr = B.cl_irr[slot] != 0;
+        const float4 ba = B.cl_bbox[slot];
+        const float limit = ba.z + B.page_slack[page];
+        // regular a: forward sweep; irregular a: every other box of the page (pairs of two irregular
+        // boxes are produced once, by the one with the smaller index)
+        int b0 = a_irr ? 0 : a + 1;
+        for (int bb = b0; bb < C; bb += 32) {
+            int b = bb + lane;
+            bool live = b < C && b != a;
+            bool hit = false;
+            bool beyond = false;
+            if (live) {
+                size_t sb = (size_t)p0 + b;
+                bool b_irr = B.cl_irr[sb] != 0;
+                if (a_irr) {
+                    hit = !(b_irr && b < a);
+                } else {
+                    beyond = B.cl_key[sb] > limit;
+                    if (!b_irr && !beyond) {
+                        float4 o = B.cl_bbox[sb];
+                        hit = !(o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y);
+                    }
+                }
+            }
+            uint32_t m = __ballot_sync(0xffffffffu, hit);
+            if (hit) {
+                int pos = qn + __popc(m & ((1u << lane) - 1u));
+                q[pos] = make_int2(a, b);
+                qpage[pos] = page;
+            }
+            qn += __popc(m);
+            __syncwarp();
+            while (qn >= 32) {
+                int idx = qn - 32 + lane;
+                int2 pr = q[idx];
+                int pg = qpage[idx];
+                __syncwarp();
+                eval_pair(pr.x, pr.y, page_off[pg], pg, thr, B,
+                          (page_off[pg + 1] - page_off[pg]) * kEdgeFactor, flags, buf);
+                qn -= 32;
+                __syncwarp();
+            }
+            // keys ascend: once every live lane is beyond the limit, nothing further can overlap
+            if (!a_irr && __all_sync(0xffffffffu, !live || beyond) && __any_sync(0xffffffffu, live && beyond)) break;
+        }
+    }
+    if (lane < qn) {
+        int2 pr = q[lane];
+        int pg = qpage[lane];
+        eval_pair(pr.x, pr.y, page_off[pg], pg, thr, B, (page_off[pg + 1] - page_off[pg]) * kEdgeFactor, flags,
+                  buf);
+    }
+}
+
+// ---- 6. greedy recurrence in rounds (one CTA per page) ----------------------------------------------------------
+__global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
+{
+    const int page = blockIdx.x;
+    const int p0 = page_off[page];
+    const int C = B.cl_count[page];
+    int E = B.edge_count[page];
+    const int ecap = (page_off[page + 1] - p0) * kEdgeFactor;
+    if (E > ecap) E = ecap;
+    const uint64_t *edges = B.edges + (size_t)p0 * kEdgeFactor;
+    uint8_t *state = B.state + p0;
+    uint8_t *blocked = B.blocked + p0;
+    __shared__ int s_undecided;
+    while (true) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) blocked[c] = 0;
+        if (threadIdx.x == 0) s_undecided = 0;
+        __syncthreads();
+        for (int e = threadIdx.x; e < E; e += blockDim.x) {
+            uint64_t ed = edges[e];
+            int hi = (int)(ed >> 32), lo = (int)(ed & 0xffffffffu);
+            if (state[lo] == 0) {
+                uint8_t sh = state[hi];
+                if (sh == 1)
+                    state[lo] = 2;
+                else if (sh == 0)
+                    blocked[lo] = 1;
+            }
+        }
+        __syncthreads();
+        int und = 0;
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            if (state[c] == 0) {
+                if (!blocked[c])
+                    state[c] = 1;
+                else
+                    und = 1;
+            }
+        }
+        if (und) s_undecided = 1;
+        __syncthreads();
+        if (!s_undecided) break;
+        __syncthreads();
+    }
+}
+
+// ---- 7. kept clusters -> rows in stable descending-score order (one CTA per page) -------------------------------
+__global__ void __launch_bounds__(1024) lanms_emit_kernel(const int32_t *__restrict__ page_off, int cap,
+                                                          LanmsBuffers B, float *__restrict__ out,
+                                                          int32_t *__restrict__ counts_out,
+                                                          int32_t *__restrict__ keep_idx_out)
+{
+    const int page = blockIdx.x;
+    const int p0 = page_off[page];
+    const int C = B.cl_count[page];
+    __shared__ int s_warp[33];
+    int32_t *kept = B.kept_list + p0;
+    int run_base = 0;
+    for (int base = 0; base < C; base += 1024) {
+        int c = base + threadIdx.x;
+        int k = (c < C && B.state[p0 + c] == 1) ? 1 : 0;
+        int total;
+        int pos = block_excl_scan_1024(k, s_warp, total);
+        if (k) kept[run_base + pos] = c;
+        run_base += total;
+    }
+    __syncthreads();
+    const int K = run_base;
+    if (threadIdx.x == 0) counts_out[page] = K;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        int c = kept[i];
+        double sc = B.cl_score[p0 + c];
+        int oc = B.cl_orig[p0 + c];
+        int rank = 0;
+        for (int j = 0; j < K; j++) {
+            int c2 = kept[j];
+            if (c2 != c && prio_before(B.cl_score[p0 + c2], B.cl_orig[p0 + c2], sc, oc)) rank++;
+        }
+        if (out) {
+            float *row = out + ((size_t)page * cap + rank) * 9;
+            const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
+#pragma unroll
+            for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
+            row[8] = (float)sc;
+        }
+        if (keep_idx_out) keep_idx_out[(size_t)page * cap + rank] = oc;
+    }
+}
+
+// ---- standalone helpers ---------------------------------------------------------------------------------------------
+__global__ void iou_pairs_kernel(const double *__restrict__ subj, const double *__restrict__ clip, int64_t n,
+                                 double *__restrict__ iou)
+{
+    double buf[4 * MS_MAXV];
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a[8], b[8];
+        load_quad(subj + i * 8, a);
+        load_quad(clip + i * 8, b);
+        iou[i] = ms_quad_iou(a, b, buf);
+    }
+}
+
+// clusters given directly (standard_nms): every box is treated as irregular => exact all-pairs mode
+__global__ void nms_prepare_kernel(const double *__restrict__ polys, const double *__restrict__ scores, int n,
+                                   LanmsBuffers B)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        B.page_off[0] = 0;
+        B.page_off[1] = n;
+        *B.n_total = n;
+        B.cl_count[0] = n;
+        B.edge_count[0] = 0;
+        B.page_slack[0] = 0.0f;
+    }
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < 8; k++) B.cl_poly[(size_t)i * 8 + k] = polys[(size_t)i * 8 + k];
+        B.cl_score[i] = scores[i];
+        B.cl_key[i] = 0.0f;
+        B.cl_bbox[i] = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
+        B.cl_irr[i] = 1;
+        B.cl_orig[i] = i;
+        B.state[i] = 0;
+        B.pos_page[i] = 0;
+    }
+}
+
+size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool full)
+{
+    B = LanmsBuffers{};
+    B.page_off = bump.take<int32_t>(n_pages + 1);
+    B.n_total = bump.take<int32_t>(1);
+    B.hot_count = bump.take<int32_t>(1);
+    B.cl_count = bump.take<int32_t>(n_pages);
+    B.edge_count = bump.take<int32_t>(n_pages);
+    B.page_slack = bump.take<float>(n_pages);
+    B.pos_page = bump.take<int32_t>(n_max);
+    if (full) {
+        B.keys = bump.take<uint64_t>(n_max);
+        B.keys_tmp = bump.take<uint64_t>(n_max);
+        B.vals = bump.take<uint32_t>(n_max);
+        B.vals_tmp = bump.take<uint32_t>(n_max);
+        B.sq = bump.take<double>(n_max * 8);
+        B.ss = bump.take<float>(n_max);
+        B.mflag = bump.take<uint8_t>(n_max);
+        B.hot = bump.take<uint8_t>(n_max);
+        B.hot_list = bump.take<int32_t>(n_max);
+        B.run_end = bump.take<int32_t>(n_max);
+        B.run_poly = bump.take<double>(n_max * 8);
+        B.run_score = bump.take<double>(n_max);
+    }
+    B.cl_poly = bump.take<double>(n_max * 8);
+    B.cl_score = bump.take<double>(n_max);
+    B.cl_key = bump.take<float>(n_max);
+    B.cl_bbox = bump.take<float4>(n_max);
+    B.cl_irr = bump.take<uint8_t>(n_max);
+    B.cl_orig = bump.take<int32_t>(n_max);
+    B.edges = bump.take<uint64_t>(n_max * kEdgeFactor);
+    B.state = bump.take<uint8_t>(n_max);
+    B.blocked = bump.take<uint8_t>(n_max);
+    B.kept_list = bump.take<int32_t>(n_max);
+    return bump.off;
+}
+
+}  // namespace
+
+size_t msk_lanms_scratch(int n_pages, int cap_per_page)
+{
+    ms_bump probe{nullptr, 0, 0};
+    LanmsBuffers B;
+    size_t n_max = (size_t)n_pages * cap_per_page;
+    size_t core = carve(probe, B, n_pages, n_max, true);
+    return core + msk_sort_scratch((int64_t)n_max) + 4096;
+}
+
+size_t msk_standard_nms_scratch(int n)
+{
+    ms_bump probe{nullptr, 0, 0};
+    LanmsBuffers B;
+    return carve(probe, B, 1, (size_t)n, false) + 4096;
+}
+
+int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page, double thr,
+              float *quads_out, int32_t *counts_out, int32_t *flags, ms_bump bump, cudaStream_t st)
+{
+    if (n_pages <= 0) return MS_OK;
+    const size_t n_max = (size_t)n_pages * cap_per_page;
+    if (n_max >= (size_t)1 << 31) {
+        ms_set_error("lanms: n_pages*cap_per_page too large");
+        return MS_ERR_INVALID;
+    }
+    LanmsBuffers B;
+    carve(bump, B, n_pages, n_max, true);
+    if (!B.kept_list) {
+        ms_set_error("lanms: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    const int sms = ctx->num_sms;
+    lanms_offsets_kernel<<<1, 32, 0, st>>>(counts, n_pages, B.page_off, B.n_total, B.hot_count, B.edge_count);
+    MS_LAUNCH_CHECK(ctx);
+    {
+        size_t threads = n_max;
+        int grid = (int)((threads + 255) / 256);
+        lanms_keys_kernel<<<grid, 256, 0, st>>>(quads, counts, B.page_off, n_pages, cap_per_page, B.keys, B.vals);
+        MS_LAUNCH_CHECK(ctx);
+    }
+    int page_bits = 1;
+    while ((1 << page_bits) < n_pages) page_bits++;
+    int rc = msk_sort_pairs(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.n_total, (int64_t)n_max,
+                            n_pages > 1 ? 32 + page_bits : 32, bump, st);
+    if (rc != MS_OK) return rc;
+    lanms_gather_hot_kernel<<<sms * 8, 128, 0, st>>>(quads, B.keys, B.vals, B.page_off, B.n_total, thr, B);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_runs_kernel<<<sms * 4, 128, 0, st>>>(B.page_off, thr, B);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_clusters_kernel<<<n_pages, kResolveThreads, 0, st>>>(B.page_off, thr < 0 ? 1 : 0, B);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_resolve_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_emit_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out, nullptr);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int n, double thr, int32_t *keep_idx,
+                     int32_t *k_out, int32_t *flags, ms_bump bump, cudaStream_t st)
+{
+    if (n <= 0) return MS_OK;
+    LanmsBuffers B;
+    carve(bump, B, 1, (size_t)n, false);
+    if (!B.kept_list) {
+        ms_set_error("standard_nms: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    const int sms = ctx->num_sms;
+    nms_prepare_kernel<<<sms, 256, 0, st>>>(polys, scores, n, B);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_resolve_kernel<<<1, 1024, 0, st>>>(B.page_off, B);
+    MS_LAUNCH_CHECK(ctx);
+    lanms_emit_kernel<<<1, 1024, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+int msk_polygon_iou(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double *iou, cudaStream_t st)
+{
+    if (n <= 0) return MS_OK;
+    int grid = (int)((n + 127) / 128);
+    if (grid > ctx->num_sms * 16) grid = ctx->num_sms * 16;
+    iou_pairs_kernel<<<grid, 128, 0, st>>>(subj, clip, n, iou);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}

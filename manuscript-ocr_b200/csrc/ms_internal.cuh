@@ -1,0 +1,244 @@
+// Internal declarations shared by the sm_100a kernels and the C-ABI layer.
+// Everything here is compiled with --fmad=false: the reference's numpy / numba arithmetic never
+// fuses a*b+c, and keep/suppress decisions must be bit-identical ("hard parts").
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/manuscript_b200.h"
+
+#define MS_NUM_SMS_B200 148
+
+struct ms_ctx {
+    int device;
+    int num_sms;
+    char *arena;          // device scratch
+    size_t arena_bytes;
+    char *pinned;         // small pinned host staging (counts / flags read-back)
+    size_t pinned_bytes;
+    cudaStream_t own_stream;
+    int64_t launches;
+    // host-API device staging, grown on demand
+    char *stage;
+    size_t stage_bytes;
+    // ms_stage_timing: ring of per-batch event sets
+    int timing;
+    int timing_n;                 // batches recorded since the last read (<= MS_TIMING_RING)
+    cudaEvent_t *timing_ev;       // MS_TIMING_RING * (MS_N_STAGES + 1) events, created lazily
+};
+#define MS_TIMING_RING 256
+
+struct ms_bump {
+    char *base;
+    size_t off, cap;
+    template <typename T>
+    T *take(size_t n)
+    {
+        size_t a = (off + 255) & ~size_t(255);
+        size_t end = a + n * sizeof(T);
+        if (end > cap) {
+            off = end;  // remember the demand so a sizing pass can read it back
+            return nullptr;
+        }
+        off = end;
+        return reinterpret_cast<T *>(base + a);
+    }
+};
+
+void ms_set_error(const char *fmt, ...);
+int ms_check_cuda(cudaError_t e, const char *what);
+// bump allocator over ctx->arena; ms_arena_reserve grows it (synchronises the device when it does)
+int ms_arena_reserve(ms_ctx *ctx, size_t bytes);
+int ms_stage_reserve(ms_ctx *ctx, size_t bytes);
+
+
+#define MS_CUDA(call)                                                  \
+    do {                                                               \
+        int _rc = ms_check_cuda((call), #call);                        \
+        if (_rc != MS_OK) return _rc;                                  \
+    } while (0)
+
+#define MS_LAUNCH_CHECK(ctx)                                           \
+    do {                                                               \
+        (ctx)->launches++;                                             \
+        int _rc = ms_check_cuda(cudaGetLastError(), "kernel launch");  \
+        if (_rc != MS_OK) return _rc;                                  \
+    } while (0)
+
+// ---- stage launchers (device pointers, stream-ordered) -------------------------------------------
+// Every launcher takes its scratch as an ms_bump BY VALUE (stage-local; stages of one stream may
+// reuse the same bytes) sized by the matching msk_*_scratch().
+// decode.cu
+int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int H, int W, float thr,
+               double scale, int q, float *quads_out, int cap_per_page, int32_t *counts, int32_t *flags,
+               ms_bump bump, cudaStream_t st);
+size_t msk_decode_scratch(int n_pages, int H, int W, int q);
+// sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs, n on the device
+int msk_sort_pairs(ms_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
+                   const int32_t *n_dev, int64_t n_max, int end_bit, ms_bump bump, cudaStream_t st);
+size_t msk_sort_scratch(int64_t n_max);
+// lanms.cu
+int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+              double thr, float *quads_out, int32_t *counts_out, int32_t *flags, ms_bump bump, cudaStream_t st);
+size_t msk_lanms_scratch(int n_pages, int cap_per_page);
+int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int n, double thr,
+                     int32_t *keep_idx, int32_t *k_out, int32_t *flags, ms_bump bump, cudaStream_t st);
+size_t msk_standard_nms_scratch(int n);
+int msk_polygon_iou(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double *iou, cudaStream_t st);
+// boxes.cu
+int msk_expand(ms_ctx *ctx, const float *quads, int64_t n, double ew, double eh, float *out, cudaStream_t st);
+int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
+                   ms_bump bump, cudaStream_t st);
+size_t msk_east_boxes_scratch(int n_pages, int cap_per_page);
+int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                   const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
+                   int64_t crops_cap, int32_t *n_crops, ms_bump bump, cudaStream_t st);
+size_t msk_word_rects_scratch(int n_pages);
+int msk_word_rects_flat(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w, int min_text_size,
+                        int32_t *rects, uint8_t *valid, cudaStream_t st);
+// crop.cu
+int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
+             const int32_t *n_crops, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
+             uint8_t *canvas_u8, cudaStream_t st);
+
+// ---- device geometry: lanms.py:7-130 in float64, no fused multiply-add ------------------------------
+#define MS_MAXV 20  // lanms.py:34
+
+struct quad64 {
+    double v[8];
+};
+
+__device__ __forceinline__ double ms_shoelace(const double *p, int n)
+{
+    // lanms.py:7-14: sequential accumulation from 0.0, |.|/2
+    double acc = 0.0;
+    for (int i = 0; i < n; i++) {
+        int j = (i + 1 == n) ? 0 : i + 1;
+        acc = acc + (p[2 * i] * p[2 * j + 1] - p[2 * j] * p[2 * i + 1]);
+    }
+    return fabs(acc) / 2.0;
+}
+
+__device__ __forceinline__ bool ms_left_of(double ax, double ay, double bx, double by, double px, double py)
+{
+    // lanms.py:40-45
+    return (bx - ax) * (py - ay) - (by - ay) * (px - ax) >= 0;
+}
+
+__device__ __forceinline__ void ms_line_hit(double p1x, double p1y, double p2x, double p2y, double ax,
+                                            double ay, double bx, double by, double &ox, double &oy)
+{
+    // lanms.py:17-29
+    double ex = p2x - p1x, ey = p2y - p1y;
+    double lx = bx - ax, ly = by - ay;
+    double den = ex * ly - ey * lx;
+    double cx = ax - p1x, cy = ay - p1y;
+    if (den == 0) {
+        ox = p1x;
+        oy = p1y;
+        return;
+    }
+    double t = (cx * ly - cy * lx) / den;
+    ox = p1x + t * ex;
+    oy = p1y + t * ey;
+}
+
+// lanms.py:80-91 polygon_iou(subject, clip) for two quads.  `buf` is 4*MS_MAXV doubles of scratch
+// private to the calling thread (local or shared memory).
+static __device__ __noinline__ double ms_quad_iou(const double *s, const double *c, double *buf)
+{
+    double *cur = buf, *nxt = buf + 2 * MS_MAXV;
+    int n = 4;
+#pragma unroll
+    for (int k = 0; k < 8; k++) cur[k] = s[k];
+    for (int e = 0; e < 4; e++) {
+        double ax = c[2 * e], ay = c[2 * e + 1];
+        int e1 = (e + 1) & 3;
+        double bx = c[2 * e1], by = c[2 * e1 + 1];
+        int cnt = 0;
+        double px = cur[2 * (n - 1)], py = cur[2 * (n - 1) + 1];
+        bool pin = ms_left_of(ax, ay, bx, by, px, py);
+        for (int i = 0; i < n; i++) {
+            double qx = cur[2 * i], qy = cur[2 * i + 1];
+            bool cin = ms_left_of(ax, ay, bx, by, qx, qy);
+            if (cin) {
+                if (!pin) {
+                    ms_line_hit(px, py, qx, qy, ax, ay, bx, by, nxt[2 * cnt], nxt[2 * cnt + 1]);
+                    cnt++;
+                }
+                nxt[2 * cnt] = qx;
+                nxt[2 * cnt + 1] = qy;
+                cnt++;
+            } else if (pin) {
+                ms_line_hit(px, py, qx, qy, ax, ay, bx, by, nxt[2 * cnt], nxt[2 * cnt + 1]);
+                cnt++;
+            }
+            px = qx;
+            py = qy;
+            pin = cin;
+        }
+        double *t = cur;
+        cur = nxt;
+        nxt = t;
+        n = cnt;
+        if (n == 0) break;
+    }
+    double ia = 0.0;
+    if (n > 2) ia = ms_shoelace(cur, n);
+    double a1 = ms_shoelace(s, 4);
+    double a2 = ms_shoelace(c, 4);
+    double uni = a1 + a2 - ia;
+    if (uni <= 0) return 0.0;
+    return ia / uni;
+}
+
+// lanms.py:99-130 normalize_polygon(ref, poly) -> out
+__device__ __forceinline__ void ms_align_vertices(const double *ref, const double *poly, double *out)
+{
+    int best_dir = 0, best_start = 0;
+    double best = 1e20;
+    for (int s = 0; s < 4; s++) {
+        double d = 0.0;
+        for (int i = 0; i < 4; i++) {
+            int k = (s + i) & 3;
+            double dx = ref[2 * i] - poly[2 * k];
+            double dy = ref[2 * i + 1] - poly[2 * k + 1];
+            d = d + (dx * dx + dy * dy);
+        }
+        if (d < best) {
+            best = d;
+            best_start = s;
+            best_dir = 0;
+        }
+    }
+    for (int s = 0; s < 4; s++) {
+        double d = 0.0;
+        for (int i = 0; i < 4; i++) {
+            int k = (s - i) & 3;
+            double dx = ref[2 * i] - poly[2 * k];
+            double dy = ref[2 * i + 1] - poly[2 * k + 1];
+            d = d + (dx * dx + dy * dy);
+        }
+        if (d < best) {
+            best = d;
+            best_start = s;
+            best_dir = 1;
+        }
+    }
+    for (int i = 0; i < 4; i++) {
+        int k = best_dir == 0 ? (best_start + i) & 3 : (best_start - i) & 3;
+        out[2 * i] = poly[2 * k];
+        out[2 * i + 1] = poly[2 * k + 1];
+    }
+}
+
+// monotone u32 image of a float for radix sorting; numpy sort order (NaN last, -0 == +0)
+__device__ __forceinline__ uint32_t ms_orderable_f32(float f)
+{
+    if (f != f) return 0xFFFFFFFFu;
+    if (f == 0.0f) f = 0.0f;  // fold -0 onto +0
+    uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}

@@ -1,0 +1,30 @@
+"""manuscript_b200 -- B200-native (sm_100a) detector->recognizer hot path of manuscript-ocr.
+
+Host side of include/manuscript_b200.h: Python mirrors of the reference's function-level seam
+(`decode_quads_from_maps`, `locality_aware_nms`, `expand_boxes`, the EAST box filters, the
+Pipeline crop loop and the TRBA `ResizeAndPadA` batch assembly) that call the hand-written CUDA
+kernels through the C ABI.  There is no CPU fallback: importing works anywhere, every compute call
+needs libmanuscript_b200.so and a B200.
+"""
+from ._cabi import (  # noqa: F401
+    CABIError,
+    Context,
+    EastParams,
+    library_path,
+    load_library,
+)
+from .ops import (  # noqa: F401
+    convert_to_axis_aligned,
+    crop_resize_pad,
+    decode_quads_from_maps,
+    east_postprocess,
+    expand_boxes,
+    locality_aware_nms,
+    polygon_iou,
+    should_merge,
+    standard_nms,
+    word_rects,
+)
+from .batch import PageBatch, PageBatchResult, shard_pages  # noqa: F401
+
+__version__ = "0.1.0"

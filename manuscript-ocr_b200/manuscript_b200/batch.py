@@ -1,0 +1,181 @@
+"""Batched device path: score/geometry maps + page images of many pages -> boxes + TRBA crop batch.
+
+One call of ms_page_batch (include/manuscript_b200.h) runs, for every page of the batch and without a
+host round trip, what the reference runs page by page on the CPU:
+decode_quads_from_maps (utils.py:328) -> locality_aware_nms (lanms.py:156) -> expand_boxes (utils.py:384)
+-> EAST box filters (infer.py:134-233) -> Pipeline crop rectangles (_pipeline.py:125-137,204-221)
+-> ResizeAndPadA + normalise + stack (transforms.py:85-120,185-193; recognizers/_trba/__init__.py:382-390).
+
+torch is used for device memory and streams only.
+"""
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+
+from ._cabi import MS_FLAG_CAND_OVERFLOW, MS_FLAG_EDGE_OVERFLOW, MS_FLAG_INDEX_ERROR, CABIError, Context, EastParams, check
+
+
+def shard_pages(n_pages, world_size, rank):
+    """Contiguous page range of `rank`: page i belongs to rank i*world_size//n_pages.
+    Pages are independent through the whole path, so there is no collective -- results are gathered
+    on the host."""
+    if world_size < 1 or not (0 <= rank < world_size):
+        raise ValueError("bad world_size / rank")
+    lo = -(-rank * n_pages // world_size)  # ceil(rank*n/world)
+    hi = -(-(rank + 1) * n_pages // world_size)
+    return range(lo, hi)
+
+
+@dataclass
+class PageBatchResult:
+    boxes: object        # (P, cap_boxes, 9) f32: rows [0, box_counts[p]) are page p's final boxes
+    box_counts: object   # (P,) int32
+    crops: object        # (crops_cap, 5) int32 rows [page, x1, y1, x2, y2), first n_crops valid
+    n_crops: object      # () / (1,) int32
+    batch: object        # (crops_cap, 3, h, w) f32 on the device (None if not requested)
+    flags: object        # (P,) int32 MS_FLAG_* bits
+
+    def page_boxes(self, p):
+        return self.boxes[p, : int(self.box_counts[p])]
+
+
+def _raise_for_flags(flags):
+    f = int(np.bitwise_or.reduce(np.asarray(flags).reshape(-1))) if len(flags) else 0
+    if f & MS_FLAG_INDEX_ERROR:
+        raise IndexError("quantised pixel index outside the map (the reference raises IndexError at utils.py:370)")
+    if f & MS_FLAG_CAND_OVERFLOW:
+        raise CABIError(-3, "more boxes than cap_boxes on at least one page")
+    if f & MS_FLAG_EDGE_OVERFLOW:
+        raise CABIError(-3, "NMS suppression-edge buffer exceeded")
+
+
+class PageBatch:
+    """Reusable runner for one GPU.  Output buffers are allocated once per shape and reused."""
+
+    def __init__(self, device=0, params=None, min_text_size=5, out_hw=(32, 128), cap_boxes=4096, crops_cap=None,
+                 want_batch=True):
+        import torch
+
+        if not torch.cuda.is_available():
+            raise RuntimeError("manuscript_b200.PageBatch needs a CUDA device: there is no CPU fallback")
+        self.torch = torch
+        self.device = torch.device("cuda", int(device))
+        self.ctx = Context(int(device))
+        self.params = params if params is not None else EastParams.default()
+        self.min_text_size = int(min_text_size)
+        self.out_h, self.out_w = int(out_hw[0]), int(out_hw[1])
+        self.cap_boxes = int(cap_boxes)
+        self.crops_cap = crops_cap
+        self.want_batch = bool(want_batch)
+        self._bufs = {}
+        self._host = {}
+
+    # ---- device tensors in, device tensors out; stream-ordered, no synchronisation --------------------------------
+    def _device_bufs(self, n_pages):
+        torch = self.torch
+        key = n_pages
+        b = self._bufs.get(key)
+        if b is None:
+            cap = self.crops_cap if self.crops_cap is not None else n_pages * self.cap_boxes
+            dev = self.device
+            b = dict(
+                boxes=torch.empty((n_pages, self.cap_boxes, 9), dtype=torch.float32, device=dev),
+                counts=torch.zeros((n_pages,), dtype=torch.int32, device=dev),
+                crops=torch.zeros((cap, 5), dtype=torch.int32, device=dev),
+                n_crops=torch.zeros((1,), dtype=torch.int32, device=dev),
+                flags=torch.zeros((n_pages,), dtype=torch.int32, device=dev),
+                batch=(torch.empty((cap, 3, self.out_h, self.out_w), dtype=torch.float32, device=dev)
+                       if self.want_batch else None),
+                cap=cap,
+            )
+            self._bufs[key] = b
+        return b
+
+    def run(self, score, geo, pages=None):
+        """score (P,H,W) or (P,1,H,W) f32, geo (P,8,H,W) f32, pages (P,IH,IW,3) u8 -- CUDA tensors on this
+        runner's device.  Enqueues the whole path on the current stream and returns device tensors."""
+        torch = self.torch
+        if score.dim() == 4:
+            score = score[:, 0]
+        P, H, W = score.shape
+        assert geo.shape == (P, 8, H, W), geo.shape
+        assert score.is_cuda and geo.is_cuda and score.dtype == torch.float32 and geo.dtype == torch.float32
+        score = score.contiguous()
+        geo = geo.contiguous()
+        img_h = img_w = 0
+        if pages is not None:
+            assert pages.is_cuda and pages.dtype == torch.uint8 and pages.shape[0] == P and pages.shape[3] == 3
+            pages = pages.contiguous()
+            img_h, img_w = int(pages.shape[1]), int(pages.shape[2])
+        b = self._device_bufs(P)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        lib = self.ctx.lib
+        with torch.cuda.device(self.device):
+            check(lib.ms_page_batch(
+                self.ctx.handle, score.data_ptr(), geo.data_ptr(), pages.data_ptr() if pages is not None else None,
+                P, H, W, img_h, img_w, C.byref(self.params), self.min_text_size, self.out_h, self.out_w,
+                self.cap_boxes, b["boxes"].data_ptr(), b["counts"].data_ptr(), b["crops"].data_ptr(), b["cap"],
+                b["n_crops"].data_ptr(), b["batch"].data_ptr() if b["batch"] is not None else None, None,
+                b["flags"].data_ptr(), C.c_void_p(stream)))
+        return PageBatchResult(b["boxes"], b["counts"], b["crops"], b["n_crops"], b["batch"], b["flags"])
+
+    # ---- host buffers in, host results out (the crop batch stays on the device, as the reference leaves ------------
+    # ---- it on `self.device`, recognizers/_trba/__init__.py:288) ---------------------------------------------------
+    def _host_bufs(self, n_pages):
+        torch = self.torch
+        h = self._host.get(n_pages)
+        if h is None:
+            cap = self.crops_cap if self.crops_cap is not None else n_pages * self.cap_boxes
+            pin = dict(pin_memory=True)
+            h = dict(
+                boxes=torch.empty((n_pages, self.cap_boxes, 9), dtype=torch.float32, **pin),
+                counts=torch.zeros((n_pages,), dtype=torch.int32, **pin),
+                crops=torch.zeros((cap, 5), dtype=torch.int32, **pin),
+                n_crops=torch.zeros((1,), dtype=torch.int32, **pin),
+                flags=torch.zeros((n_pages,), dtype=torch.int32, **pin),
+                cap=cap,
+            )
+            self._host[n_pages] = h
+        return h
+
+    def run_host(self, score, geo, pages=None, check_flags=True):
+        """numpy arrays or (pinned) CPU torch tensors of the shapes of run().  Copies in, runs, copies the
+        boxes / counts / crop list back and synchronises (ms_page_batch_host)."""
+        torch = self.torch
+
+        def as_np(a, dtype):
+            if isinstance(a, torch.Tensor):
+                a = a.numpy()
+            a = np.asarray(a)
+            if a.dtype != dtype or not a.flags.c_contiguous:
+                a = np.ascontiguousarray(a, dtype=dtype)
+            return a
+
+        s = as_np(score, np.float32)
+        if s.ndim == 4:
+            s = s[:, 0]
+            s = np.ascontiguousarray(s)
+        g = as_np(geo, np.float32)
+        P, H, W = s.shape
+        assert g.shape == (P, 8, H, W), g.shape
+        img_h = img_w = 0
+        pg = None
+        if pages is not None:
+            pg = as_np(pages, np.uint8)
+            assert pg.shape[0] == P and pg.shape[3] == 3
+            img_h, img_w = pg.shape[1], pg.shape[2]
+        h = self._host_bufs(P)
+        dev_batch = C.c_void_p()
+        lib = self.ctx.lib
+        rc = lib.ms_page_batch_host(
+            self.ctx.handle, s.ctypes.data, g.ctypes.data, pg.ctypes.data if pg is not None else None, P, H, W,
+            img_h, img_w, C.byref(self.params), self.min_text_size, self.out_h, self.out_w, self.cap_boxes,
+            h["boxes"].data_ptr(), h["counts"].data_ptr(), h["crops"].data_ptr(), h["cap"], h["n_crops"].data_ptr(),
+            None, C.byref(dev_batch) if self.want_batch else None, h["flags"].data_ptr())
+        if check_flags:
+            check(rc)
+        elif rc not in (0, -3, -4):
+            check(rc)
+        return PageBatchResult(h["boxes"].numpy(), h["counts"].numpy(), h["crops"].numpy(), h["n_crops"].numpy(),
+                               dev_batch.value, h["flags"].numpy())

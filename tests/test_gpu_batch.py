@@ -1,0 +1,112 @@
+"""The batched device path (ms_page_batch) against the oracle chain page by page, plus
+size-independent properties at BASELINE.json's full shapes."""
+import numpy as np
+import pytest
+
+import synthdata
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+
+def oracle_page(score, geo, img, page, out_hw=(32, 128), min_text=5):
+    quads = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    nms = cpu.locality_aware_nms(quads, 0.2)
+    boxes = cpu.east_postprocess(nms, (page, page), target_size=page)
+    rects, valid = cpu.word_rects(boxes, page, page, min_text)
+    return quads, nms, boxes, rects[valid]
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+
+    assert torch.cuda.is_available()
+    return torch
+
+
+@pytest.mark.parametrize("page,words,n_pages", [(512, 80, 5), (1280, 500, 3)])
+def test_page_batch_vs_oracle(torch_cuda, page, words, n_pages):
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    seeds = list(range(40, 40 + n_pages))
+    score, geo, imgs = synthdata.make_batch(seeds, page, words)
+    # one empty page in the middle (ragged batch)
+    score[1] = 0.0
+    params = mb.EastParams.default(target_size=page)
+    runner = mb.PageBatch(device=0, params=params, cap_boxes=1024)
+    res = runner.run(torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(), torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    counts = res.box_counts.cpu().numpy()
+    boxes = res.boxes.cpu().numpy()
+    n_crops = int(res.n_crops.cpu()[0])
+    crops = res.crops.cpu().numpy()[:n_crops]
+    batch = res.batch[:n_crops].cpu().numpy()
+    assert int(res.flags.cpu().numpy().max()) == 0
+    k = 0
+    for p in range(n_pages):
+        _, _, want_boxes, want_rects = oracle_page(score[p], geo[p], imgs[p], page)
+        assert counts[p] == len(want_boxes)
+        np.testing.assert_array_equal(boxes[p, : counts[p]], want_boxes)
+        mine = crops[crops[:, 0] == p]
+        np.testing.assert_array_equal(mine[:, 1:], want_rects)
+        for r in want_rects[:: max(1, len(want_rects) // 25)]:
+            pass
+        for j, r in enumerate(want_rects):
+            if j % 7 == 0:
+                _, chw = cpu.crop_resize_pad(imgs[p], r, 32, 128)
+                np.testing.assert_array_equal(batch[k + j], chw)
+        k += len(want_rects)
+    assert k == n_crops and counts[1] == 0
+    # the same batch through the host-buffer entry point
+    res_h = runner.run_host(score, geo, imgs)
+    np.testing.assert_array_equal(res_h.box_counts, counts)
+    np.testing.assert_array_equal(res_h.boxes[0, : counts[0]], boxes[0, : counts[0]])
+    assert int(res_h.n_crops[0]) == n_crops
+    np.testing.assert_array_equal(res_h.crops[:n_crops], crops)
+
+
+def test_full_size_properties(torch_cuda):
+    """2048x2048 / ~2000 quads (BASELINE configs[2] shape), 2 pages: properties that need no oracle run --
+    page-permutation equivariance, idempotence of NMS on its own output, kept rows are descending in
+    score, every crop rectangle lies inside the page."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    page, words = 2048, 2000
+    score, geo, imgs = synthdata.make_batch([0, 1], page, words)
+    params = mb.EastParams.default(target_size=page)
+    runner = mb.PageBatch(device=0, params=params, cap_boxes=4096)
+    s, g, im = torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(), torch.from_numpy(imgs).cuda()
+    r1 = runner.run(s, g, im)
+    torch.cuda.synchronize()
+    c1, b1 = r1.box_counts.cpu().numpy().copy(), r1.boxes.cpu().numpy().copy()
+    n1 = int(r1.n_crops.cpu()[0])
+    crops1 = r1.crops.cpu().numpy()[:n1].copy()
+    sum1 = r1.batch[:n1].double().sum(dim=(1, 2, 3)).cpu().numpy().copy()
+    assert (c1 == words).all(), c1
+    r2 = runner.run(s.flip(0).contiguous(), g.flip(0).contiguous(), im.flip(0).contiguous())
+    torch.cuda.synchronize()
+    c2, b2 = r2.box_counts.cpu().numpy(), r2.boxes.cpu().numpy()
+    np.testing.assert_array_equal(c2, c1[::-1])
+    np.testing.assert_array_equal(b2[1, : c2[1]], b1[0, : c1[0]])
+    np.testing.assert_array_equal(b2[0, : c2[0]], b1[1, : c1[1]])
+    sum2 = r2.batch[:n1].double().sum(dim=(1, 2, 3)).cpu().numpy()
+    np.testing.assert_array_equal(np.sort(sum1), np.sort(sum2))  # checksum of per-crop checksums
+    assert (crops1[:, 1] >= 0).all() and (crops1[:, 3] <= page).all() and (crops1[:, 2] >= 0).all()
+    assert (crops1[:, 4] <= page).all() and (crops1[:, 3] > crops1[:, 1]).all()
+    # NMS output: descending score; running NMS again on it removes nothing
+    quads = mb.decode_quads_from_maps(score[0], geo[0], 0.6, 4.0, 2)
+    nms = mb.locality_aware_nms(quads, 0.2)
+    assert len(nms) == words and (np.diff(nms[:, 8]) <= 0).all()
+    again = mb.locality_aware_nms(nms, 0.2)
+    np.testing.assert_array_equal(rows(again), rows(nms))
+    # and the page agrees with the oracle end to end on a bounded sample (decode exact, NMS on the oracle)
+    np.testing.assert_array_equal(quads, cpu.decode_quads_from_maps(score[0], geo[0], 0.6, 4.0, 2))
+    np.testing.assert_array_equal(nms, cpu.locality_aware_nms(quads, 0.2))
+
+
+def rows(a):
+    a = np.ascontiguousarray(a)
+    return a[np.lexsort(a.T[::-1])]

@@ -1,0 +1,289 @@
+"""Parity of the CUDA path (through the C ABI, manuscript_b200.ops) against the committed golden
+vectors of the real reference and against the C oracle on seeded inputs.  Bit-exact everywhere:
+index sets, f64 IoU decisions, f32 coordinates, uint8 crop pixels (tolerance 0)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+import synthdata
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+PAGES = ["page_s0", "page_s1", "page_s2", "page_cfg1"]
+
+
+@pytest.fixture(scope="module")
+def ops():
+    import manuscript_b200 as mb
+
+    assert os.path.exists(mb.library_path()), "libmanuscript_b200.so not built"
+    return mb
+
+
+def sha(*arrs):
+    h = hashlib.sha256()
+    for a in arrs:
+        h.update(np.ascontiguousarray(a).tobytes())
+    return h.hexdigest()
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name + ".npz"))
+
+
+def rows_sorted(a):
+    a = np.ascontiguousarray(a)
+    return a[np.lexsort(a.T[::-1])]
+
+
+# ---- known-answer cases of the reference's tests/detectors/east/test_lanms.py:18-188 ---------------------------
+SQ4 = np.array([[0, 0], [4, 0], [4, 4], [0, 4]], dtype=np.float64)
+SQ4B = np.array([[2, 2], [6, 2], [6, 6], [2, 6]], dtype=np.float64)
+UNIT = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], dtype=np.float64)
+
+
+def test_kat_iou_and_merge(ops):
+    assert np.isclose(ops.polygon_iou(SQ4, SQ4B), 4 / 28, rtol=1e-5)
+    assert ops.polygon_iou(UNIT, UNIT) == pytest.approx(1.0)
+    assert ops.polygon_iou(UNIT, UNIT + 2) == pytest.approx(0.0)
+    assert ops.should_merge(SQ4, SQ4B, 0.1)
+    assert not ops.should_merge(SQ4, SQ4B, 0.2)
+    assert not ops.should_merge(UNIT, UNIT, 1.0)
+    assert ops.should_merge(UNIT, UNIT, 0.999)
+    rev = UNIT[::-1].copy()  # orientation quirk, SURVEY 8a-4
+    assert ops.polygon_iou(UNIT, rev) == 0.0
+    assert ops.polygon_iou(rev, rev) == 0.0
+
+
+def test_kat_standard_nms(ops):
+    polys = [SQ4, SQ4 + 1, SQ4 + 10]
+    kp, ks = ops.standard_nms(polys, [0.9, 0.8, 0.7], 0.1)
+    assert len(kp) == 2
+    np.testing.assert_array_equal(ks, [0.9, 0.7])
+
+
+def test_kat_lanms(ops):
+    boxes = np.array([[0, 0, 4, 0, 4, 4, 0, 4, 0.9], [1, 1, 5, 1, 5, 5, 1, 5, 0.8],
+                      [10, 10, 14, 10, 14, 14, 10, 14, 0.7], [11, 11, 15, 11, 15, 15, 11, 15, 0.6]], np.float32)
+    out = ops.locality_aware_nms(boxes, 0.1)
+    assert out.shape == (2, 9) and out.dtype == np.float32
+    np.testing.assert_array_equal(out, cpu.locality_aware_nms(boxes, 0.1))
+    assert ops.locality_aware_nms(np.zeros((0, 9), np.float32), 0.5).shape == (0, 9)
+    assert ops.locality_aware_nms(None, 0.5).shape == (0, 9)
+
+
+# ---- random polygon pairs: IoU bit-exact in f64, including irregular quads ----------------------------------------
+def test_polygon_iou_random_bitexact(ops):
+    rng = np.random.default_rng(5)
+    n = 20000
+    base = rng.uniform(0, 50, (n, 1, 2))
+    a = base + rng.uniform(-8, 8, (n, 4, 2))          # arbitrary quads: concave, self-intersecting, cw
+    b = base + rng.uniform(-8, 8, (n, 4, 2))
+    rect = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    a[: n // 2] = base[: n // 2] + rect * rng.uniform(2, 12, (n // 2, 1, 2))
+    b[: n // 2] = base[: n // 2] + rng.uniform(-3, 3, (n // 2, 1, 2)) + rect * rng.uniform(2, 12, (n // 2, 1, 2))
+    got = ops.polygon_iou(a, b)
+    want = np.array([cpu.polygon_iou(x, y) for x, y in zip(a, b)])
+    np.testing.assert_array_equal(got, want)
+    assert (want > 0.2).sum() > 1000 and (want == 0).sum() > 100
+
+
+# ---- whole page chains against the real reference's outputs ---------------------------------------------------------
+@pytest.mark.parametrize("name", PAGES)
+def test_page_chain_golden(ops, golden_dir, name):
+    g = load(golden_dir, name)
+    seed, page, words = int(g["seed"]), int(g["page"]), int(g["words"])
+    score, geo, _ = synthdata.make_maps(seed, page, words)
+    assert sha(score, geo) == str(g["input_sha"])
+    quads = ops.decode_quads_from_maps(score, geo.transpose(1, 2, 0), 0.6, 4.0, 2)
+    assert len(quads) == int(g["n_candidates"])
+    assert sha(quads) == str(g["quads_sha"])
+    nms = ops.locality_aware_nms(quads, 0.2)
+    np.testing.assert_array_equal(nms, g["lanms_stable"])
+    if name != "page_cfg1":  # no interacting x0 tie: equal to the unpatched reference as well
+        np.testing.assert_array_equal(nms, g["lanms_ref"])
+    orig_hw = tuple(int(v) for v in g["orig_hw"])
+    np.testing.assert_array_equal(ops.expand_boxes(nms, 0.9, 0.9), g["expanded"])
+    x = ops.east_postprocess(nms, orig_hw, target_size=page)
+    np.testing.assert_array_equal(x, g["aligned"])
+    x_noalign = ops.east_postprocess(nms, orig_hw, target_size=page, axis_aligned=False)
+    np.testing.assert_array_equal(x_noalign, g["anomalies"])
+    rects, valid = ops.word_rects(x, orig_hw[0], orig_hw[1], 5)
+    np.testing.assert_array_equal(valid, g["valid"])
+    np.testing.assert_array_equal(rects[valid], g["rects"][g["valid"]])
+    img = synthdata.make_page_image(seed, max(orig_hw))[: orig_hw[0], : orig_hw[1]]
+    assert sha(img) == str(g["image_sha"])
+    k = len(g["canvas32"])
+    batch, canvas = ops.crop_resize_pad(img, rects[valid][:k], 32, 128, want_canvas=True)
+    np.testing.assert_array_equal(canvas, g["canvas32"])  # 0 LSB
+    ref = ((canvas.astype(np.float32) - np.float32(127.5)) * np.float32(1 / 127.5)).transpose(0, 3, 1, 2)
+    np.testing.assert_array_equal(batch, ref)
+
+
+def test_box_filters_golden(ops, golden_dir):
+    g = load(golden_dir, "box_filters")
+    kw = dict(target_size=1, expand_w=0.0, expand_h=0.0)
+    c = ops.east_postprocess(g["boxes"], (1, 1), axis_aligned=False, remove_anomalies=False, **kw)
+    np.testing.assert_array_equal(rows_sorted(c), rows_sorted(g["contained"]))
+    np.testing.assert_array_equal(c, cpu.remove_fully_contained_boxes(g["boxes"]))
+    a = ops.east_postprocess(g["boxes"], (1, 1), axis_aligned=False, **kw)
+    np.testing.assert_array_equal(rows_sorted(a), rows_sorted(g["anomalies"]))
+    x = ops.east_postprocess(g["boxes"], (1, 1), **kw)
+    np.testing.assert_array_equal(rows_sorted(x), rows_sorted(g["aligned"]))
+
+
+def test_resize_pad_golden(ops, golden_dir):
+    g = load(golden_dir, "resize_pad")
+    img = synthdata.make_page_image(int(g["image_seed"]), 512)
+    assert sha(img) == str(g["image_sha"])
+    rects = g["rects"]
+    b32, c32 = ops.crop_resize_pad(img, rects, 32, 128, want_canvas=True)
+    c64 = ops.crop_resize_pad(img, rects, 64, 256, want_canvas=True, want_batch=False)
+    for i in range(len(rects)):
+        assert sha(c32[i]) == str(g["sha32"][i]), f"32x128 case {i} rect {rects[i]}"
+        assert sha(c64[i]) == str(g["sha64"][i]), f"64x256 case {i} rect {rects[i]}"
+    ref = ((c32.astype(np.float32) - np.float32(127.5)) * np.float32(1 / 127.5)).transpose(0, 3, 1, 2)
+    np.testing.assert_array_equal(b32, ref)
+
+
+# ---- seeded inputs against the oracle -------------------------------------------------------------------------------------
+@pytest.mark.parametrize("q", [1, 2, 4])
+@pytest.mark.parametrize("seed,page,words", [(11, 384, 60), (12, 640, 200)])
+def test_decode_vs_oracle(ops, seed, page, words, q):
+    score, geo, _ = synthdata.make_maps(seed, page, words)
+    for thr in (0.6, 0.25, 0.95):
+        a = ops.decode_quads_from_maps(score, geo, thr, 4.0, q)
+        b = cpu.decode_quads_from_maps(score, geo, thr, 4.0, q)
+        np.testing.assert_array_equal(a, b)
+    a = ops.decode_quads_from_maps(score, geo, 0.6, 3.7, q)  # inexact scale: f64 + f32 promotion path
+    np.testing.assert_array_equal(a, cpu.decode_quads_from_maps(score, geo, 0.6, 3.7, q))
+
+
+def test_decode_edge_cases(ops):
+    H = W = 8
+    score = np.zeros((H, W), np.float32)
+    geo = np.zeros((8, H, W), np.float32)
+    assert ops.decode_quads_from_maps(score, geo, 0.6, 4.0, 2).shape == (0, 9)
+    score[3, 3] = np.float32(0.6)
+    assert len(ops.decode_quads_from_maps(score, geo, 0.6, 4.0, 1)) == 0  # strict >
+    score[3, 3] = np.nextafter(np.float32(0.6), np.float32(1))
+    q = ops.decode_quads_from_maps(score, geo, 0.6, 4.0, 1)
+    assert q.shape == (1, 9) and q[0, 0] == 12.0 and q[0, 1] == 12.0
+    score[:] = 0
+    score[2, 2] = 0.9
+    score[2, 3] = 0.95
+    score[3, 3] = 0.1
+    q = ops.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    assert q.shape == (1, 9) and q[0, 8] == np.float32(0.1)
+    s7 = np.zeros((7, 7), np.float32)
+    s7[6, 0] = 0.9
+    with pytest.raises(IndexError):
+        ops.decode_quads_from_maps(s7, np.zeros((8, 7, 7), np.float32), 0.6, 4.0, 2)
+    # every pixel a candidate (the random-init case of SURVEY 8c: all 102 400 px -> 25 600 rows)
+    full = np.full((64, 96), 0.9, np.float32)
+    gg = np.random.default_rng(0).normal(0, 3, (8, 64, 96)).astype(np.float32)
+    np.testing.assert_array_equal(ops.decode_quads_from_maps(full, gg, 0.6, 4.0, 2),
+                                  cpu.decode_quads_from_maps(full, gg, 0.6, 4.0, 2))
+    np.testing.assert_array_equal(ops.decode_quads_from_maps(full, gg, 0.6, 4.0, 1),
+                                  cpu.decode_quads_from_maps(full, gg, 0.6, 4.0, 1))
+
+
+@pytest.mark.parametrize("thr", [0.05, 0.2, 0.5, 0.9])
+def test_lanms_vs_oracle(ops, thr):
+    for seed, page, words in [(21, 384, 60), (22, 640, 220), (23, 1024, 600)]:
+        score, geo, _ = synthdata.make_maps(seed, page, words)
+        quads = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+        np.testing.assert_array_equal(ops.locality_aware_nms(quads, thr), cpu.locality_aware_nms(quads, thr))
+
+
+def test_lanms_hard_cases(ops):
+    rng = np.random.default_rng(9)
+    # (a) one giant cluster: every box overlaps the running merge (longest speculative run)
+    n = 400
+    base = np.array([10, 10, 60, 10, 60, 30, 10, 30], np.float32)
+    boxes = np.tile(base, (n, 1)) + rng.normal(0, 0.3, (n, 8)).astype(np.float32)
+    boxes = np.concatenate([boxes, rng.uniform(0.5, 1, (n, 1)).astype(np.float32)], axis=1)
+    np.testing.assert_array_equal(ops.locality_aware_nms(boxes, 0.2), cpu.locality_aware_nms(boxes, 0.2))
+    # (b) exact duplicates + equal x0 + equal scores (tie rule = original index)
+    dup = np.repeat(boxes[:40], 5, axis=0)
+    dup[:, 8] = np.float32(0.75)
+    dup[::3, :8] += 100
+    np.testing.assert_array_equal(ops.locality_aware_nms(dup, 0.3), cpu.locality_aware_nms(dup, 0.3))
+    # (c) irregular quads: clockwise, self-intersecting, degenerate, mixed with regular ones
+    m = 600
+    c = rng.uniform(0, 200, (m, 1, 2))
+    quads = c + rng.uniform(-15, 15, (m, 4, 2))
+    rect = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    quads[:300] = c[:300] + rect * rng.uniform(5, 30, (300, 1, 2))
+    quads[300:330] = quads[300:330, ::-1]
+    quads[330:340] = quads[330:340, :1]  # all four vertices equal
+    b2 = np.concatenate([quads.reshape(m, 8), rng.uniform(0.3, 1, (m, 1))], axis=1).astype(np.float32)
+    for thr in (0.0, 0.1, 0.3, -1.0):
+        np.testing.assert_array_equal(ops.locality_aware_nms(b2, thr), cpu.locality_aware_nms(b2, thr))
+    # (d) a single box, two boxes
+    np.testing.assert_array_equal(ops.locality_aware_nms(b2[:1], 0.2), cpu.locality_aware_nms(b2[:1], 0.2))
+    np.testing.assert_array_equal(ops.locality_aware_nms(b2[:2], 0.2), cpu.locality_aware_nms(b2[:2], 0.2))
+    # (e) standard_nms index sets on the irregular mix (exact all-pairs mode)
+    keep = ops.standard_nms(quads, b2[:, 8].astype(np.float64), 0.1, return_index=True)
+    np.testing.assert_array_equal(keep, cpu.standard_nms(quads, b2[:, 8].astype(np.float64), 0.1, return_index=True))
+
+
+def test_expand_and_filters_vs_oracle(ops):
+    for seed, page, words, orig in [(31, 640, 200, (900, 700)), (32, 1024, 600, (1024, 1024))]:
+        score, geo, _ = synthdata.make_maps(seed, page, words)
+        nms = cpu.locality_aware_nms(cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2), 0.2)
+        for ew, eh in [(0.9, 0.9), (0.3, 0.7), (0.0, 0.5), (0.0, 0.0)]:
+            np.testing.assert_array_equal(ops.expand_boxes(nms, ew, eh), cpu.expand_boxes(nms, ew, eh))
+            for aa in (True, False):
+                got = ops.east_postprocess(nms, orig, target_size=page, expand_w=ew, expand_h=eh, axis_aligned=aa)
+                want = cpu.east_postprocess(nms, orig, target_size=page, expand_w=ew, expand_h=eh, axis_aligned=aa)
+                np.testing.assert_array_equal(got, want)
+    # nested boxes so that contained-box removal and the anomaly filter both fire
+    rng = np.random.default_rng(4)
+    n = 300
+    cxy = rng.uniform(50, 950, (n, 2))
+    wh = rng.uniform(10, 60, (n, 2))
+    wh[:5] *= 12  # area anomalies
+    rect = np.array([[-1, -1], [1, -1], [1, 1], [-1, 1]], float) / 2
+    q = (cxy[:, None, :] + rect[None] * wh[:, None, :]).reshape(n, 8)
+    inner = q[:60].reshape(60, 4, 2)
+    inner = inner.mean(axis=1, keepdims=True) + (inner - inner.mean(axis=1, keepdims=True)) * 0.5
+    boxes = np.concatenate([np.concatenate([q, inner.reshape(60, 8)]), rng.uniform(0.5, 1, (n + 60, 1))], axis=1)
+    boxes = boxes.astype(np.float32)
+    got = ops.east_postprocess(boxes, (1000, 1000), target_size=1000, expand_w=0.0, expand_h=0.0)
+    want = cpu.east_postprocess(boxes, (1000, 1000), target_size=1000, expand_w=0.0, expand_h=0.0)
+    np.testing.assert_array_equal(got, want)
+    assert len(want) < len(boxes) - 30
+
+
+def test_word_rects_and_crops_vs_oracle(ops):
+    rng = np.random.default_rng(8)
+    H, W = 300, 420
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    n = 400
+    xy = rng.uniform(-30, 450, (n, 4, 2)).astype(np.float32)
+    xy[:, :, 1] = rng.uniform(-30, 330, (n, 4)).astype(np.float32)
+    small = rng.uniform(0, 400, (n // 2, 1, 2)) + rng.uniform(0, 40, (n // 2, 4, 2))
+    xy[: n // 2] = small.astype(np.float32)
+    r_got, v_got = ops.word_rects(xy, H, W, 5)
+    r_want, v_want = cpu.word_rects(xy, H, W, 5)
+    np.testing.assert_array_equal(v_got, v_want)
+    np.testing.assert_array_equal(r_got[v_got], r_want[v_want])
+    assert 20 < v_want.sum() < n
+    rects = r_want[v_want]
+    for ih, iw in [(32, 128), (64, 256), (48, 100)]:
+        batch, canvas = ops.crop_resize_pad(img, rects, ih, iw, want_canvas=True)
+        for i, r in enumerate(rects):
+            c, chw = cpu.crop_resize_pad(img, r, ih, iw)
+            np.testing.assert_array_equal(canvas[i], c, err_msg=f"rect {r} -> {ih}x{iw}")
+            np.testing.assert_array_equal(batch[i], chw)
+
+
+def test_errors_are_loud(ops):
+    with pytest.raises(ValueError):
+        ops.decode_quads_from_maps(np.zeros((4, 4), np.float32), np.zeros((7, 4, 4), np.float32), 0.5, 4.0)
+    with pytest.raises(ValueError):
+        ops.locality_aware_nms(np.zeros((3, 8), np.float32), 0.2)

@@ -242,6 +242,8 @@ def east_postprocess(quads_nms, orig_size, target_size=1280, expand_w=0.9, expan
 # ---- _pipeline.py:125-137, 204-221 ----------------------------------------------------------------
 def word_rects(polys, img_h, img_w, min_text_size=5):
     """polys (n,4,2) or (n,8+) float -> (rects (n,4) int32 [x1,y1,x2,y2), valid (n,) bool)."""
+    if len(polys) == 0:
+        return np.zeros((0, 4), np.int32), np.zeros(0, bool)
     p = np.ascontiguousarray(polys, dtype=np.float32).reshape(len(polys), -1)[:, :8].copy()
     rects = np.zeros((len(p), 4), np.int32)
     valid = np.zeros(len(p), bool)

@@ -279,8 +279,8 @@ extern "C" int ms_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *cou
     }
     MS_TRY(ms_arena_reserve(ctx, msk_east_boxes_scratch(n_pages, cap_per_page)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
-    return msk_east_boxes(ctx, quads, counts, n_pages, cap_per_page, p, orig_hw, quads_out, counts_out, bump,
-                          (cudaStream_t)stream);
+    return msk_east_boxes(ctx, quads, counts, n_pages, cap_per_page, p, orig_hw, quads_out, cap_per_page, counts_out,
+                          nullptr, bump, (cudaStream_t)stream);
 }
 
 static size_t word_rects_scratch_full(int n_pages, int cap_per_page)
@@ -338,23 +338,6 @@ static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int c
     return fixed + stage + 4096;
 }
 
-__global__ void ms_copy_boxes_kernel(const float *__restrict__ src, const int32_t *__restrict__ counts, int n_pages,
-                                     int cap_src, int cap_dst, float *__restrict__ dst, int32_t *__restrict__ counts_dst,
-                                     int32_t *__restrict__ flags)
-{
-    // page-strided (cap_src) -> page-strided (cap_dst); rows beyond cap_dst are dropped and flagged
-    const int page = blockIdx.y;
-    int k = counts[page];
-    if (k > cap_dst) {
-        if (blockIdx.x == 0 && threadIdx.x == 0) atomicOr(flags + page, MS_FLAG_CAND_OVERFLOW);
-        k = cap_dst;
-    }
-    if (blockIdx.x == 0 && threadIdx.x == 0) counts_dst[page] = k;
-    const float *s = src + (size_t)page * cap_src * 9;
-    float *d = dst + (size_t)page * cap_dst * 9;
-    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < k * 9; i += gridDim.x * blockDim.x) d[i] = s[i];
-}
-
 extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
                              int map_h, int map_w, int img_h, int img_w, const ms_east_params *p, int min_text_size,
                              int out_h, int out_w, int cap_boxes, float *boxes_out, int32_t *box_counts,
@@ -390,12 +373,7 @@ extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, 
     // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
     ms_east_params pp = *p;
     MS_TRY(timing_mark(ctx, 2, st));
-    MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, &pp, nullptr, qa, ca, bump, st));
-    {
-        dim3 grid(8, n_pages);
-        ms_copy_boxes_kernel<<<grid, 256, 0, st>>>(qa, ca, n_pages, cap_c, cap_boxes, boxes_out, box_counts, flags);
-        MS_LAUNCH_CHECK(ctx);
-    }
+    MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, &pp, nullptr, boxes_out, cap_boxes, box_counts, flags, bump, st));
     MS_TRY(timing_mark(ctx, 3, st));
     if (want_crops) {
         MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, nullptr, img_h, img_w, min_text_size,
@@ -648,7 +626,7 @@ extern "C" int ms_east_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, co
     MS_CUDA(cudaMemcpyAsync(d_i, h, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
     MS_CUDA(cudaMemcpyAsync(d_in, quads, (size_t)n * 36, cudaMemcpyHostToDevice, st));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
-    MS_TRY(msk_east_boxes(ctx, d_in, d_i, 1, cap, p, d_i + 2, d_out, d_i + 1, bump, st));
+    MS_TRY(msk_east_boxes(ctx, d_in, d_i, 1, cap, p, d_i + 2, d_out, cap, d_i + 1, nullptr, bump, st));
     MS_CUDA(cudaMemcpyAsync(h + 8, d_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
     const int m = h[8];

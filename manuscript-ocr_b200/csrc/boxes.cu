@@ -150,10 +150,10 @@ __device__ __forceinline__ bool area_before(float aa, int ia, float ab, int ib)
 struct EastScratch {
     float *work;      // (P*cap, 9) expanded + scaled quads
     float *area;      // P*cap
-    int32_t *order;   // P*cap: box index at each area rank
-    int32_t *rank;    // P*cap
+    float4 *bbox;     // P*cap: vertex bounding box (exact min / max of the f32 coordinates)
     uint8_t *removed; // P*cap
     uint8_t *needseq; // P*cap
+    int32_t *seq;     // P*cap: the (rare) boxes resolved sequentially, in area-rank order
     float *karea;     // P*cap compacted areas / deviations
     float *kdev;
     int32_t *kidx;    // P*cap compacted indices
@@ -187,29 +187,16 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
     return s_warp[warp] + inc - v;
 }
 
-// One CTA per page: expand -> scale -> contained removal -> anomaly removal -> axis align.
-__global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict__ quads,
-                                                         const int32_t *__restrict__ counts, int cap,
-                                                         ms_east_params P, const int32_t *__restrict__ orig_hw,
-                                                         EastScratch S, float *__restrict__ out,
-                                                         int32_t *__restrict__ counts_out)
+// 1) expand (utils.py:384) + scale to the original image (infer.py:134-147) + area + bbox, all boxes of all pages
+__global__ void __launch_bounds__(256) east_prep_kernel(const float *__restrict__ quads,
+                                                        const int32_t *__restrict__ counts, int n_pages, int cap,
+                                                        ms_east_params P, const int32_t *__restrict__ orig_hw,
+                                                        EastScratch S)
 {
-    const int page = blockIdx.x;
-    const int K = counts[page];
-    const size_t pb = (size_t)page * cap;
-    float *work = S.work + pb * 9;
-    float *area = S.area + pb;
-    int32_t *order = S.order + pb, *rank = S.rank + pb, *kidx = S.kidx + pb;
-    uint8_t *removed = S.removed + pb, *needseq = S.needseq + pb;
-    float *karea = S.karea + pb, *kdev = S.kdev + pb;
-    __shared__ int s_warp[33];
-    __shared__ int s_flag;
-    __shared__ float s_thr;
-    __shared__ int s_apply;
-
-    // 1) expand (utils.py:384) + scale to the original image (infer.py:134-147)
     const bool ident = (P.expand_ratio_w == 0 && P.expand_ratio_h == 0);
     const float ex = (float)(1.0 + P.expand_ratio_w) - 1.0f, ey = (float)(1.0 + P.expand_ratio_h) - 1.0f;
+    const int page = blockIdx.y;
+    const int K = counts[page];
     int oh = P.target_size, ow = P.target_size;
     if (orig_hw) {
         oh = orig_hw[2 * page];
@@ -217,7 +204,8 @@ __global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict
     }
     const float sx = (float)((double)ow / (double)P.target_size);
     const float sy = (float)((double)oh / (double)P.target_size);
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+    const size_t pb = (size_t)page * cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
         float p[9], o[9];
 #pragma unroll
         for (int k = 0; k < 9; k++) p[k] = quads[(pb + i) * 9 + k];
@@ -227,58 +215,147 @@ __global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict
         } else {
             expand_quad(p, ex, ey, o);
         }
+        float x0 = INFINITY, x1 = -INFINITY, y0 = INFINITY, y1 = -INFINITY;
+        bool fin = true;
 #pragma unroll
         for (int v = 0; v < 4; v++) {
             o[2 * v] = o[2 * v] * sx;
             o[2 * v + 1] = o[2 * v + 1] * sy;
+            x0 = fminf(x0, o[2 * v]);
+            x1 = fmaxf(x1, o[2 * v]);
+            y0 = fminf(y0, o[2 * v + 1]);
+            y1 = fmaxf(y1, o[2 * v + 1]);
+            fin = fin && (fabsf(o[2 * v]) < 1e30f) && (fabsf(o[2 * v + 1]) < 1e30f);
         }
 #pragma unroll
-        for (int k = 0; k < 9; k++) work[(size_t)i * 9 + k] = o[k];
-        area[i] = quad_area_f32(o);
-        removed[i] = 0;
-        needseq[i] = 0;
+        for (int k = 0; k < 9; k++) S.work[(pb + i) * 9 + k] = o[k];
+        S.area[pb + i] = quad_area_f32(o);
+        // non-finite boxes get an "everything" box so the prefilter never rejects them
+        S.bbox[pb + i] = fin ? make_float4(x0, y0, x1, y1) : make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
+        S.removed[pb + i] = 0;
+        S.needseq[pb + i] = 0;
     }
-    __syncthreads();
+}
 
-    // 2) infer.py:194-214 contained-box removal, ascending-area scan with the stable tie rule
-    if (K > 1) {
-        for (int i = threadIdx.x; i < K; i += blockDim.x) {
-            float ai = area[i];
-            int r = 0;
-            for (int j = 0; j < K; j++) r += (j != i && area_before(area[j], j, ai, i)) ? 1 : 0;
-            rank[i] = r;
-            order[r] = i;
-        }
-        __syncthreads();
-        const float eps = (float)1e-6;
-        for (int i = threadIdx.x; i < K; i += blockDim.x) {
-            float qi[8];
+// 2) infer.py:194-214 contained-box removal, the pairwise part.  Box i is visited in ascending-area order
+//    (stable ties); a container j that comes LATER in that order is still kept when i is visited, so it
+//    removes i outright; a container that comes EARLIER only counts if it survived itself -> needseq.
+//    cv2.pointPolygonTest >= 0 implies the point lies inside the contour's vertex bounding box (the ray
+//    cast skips every edge otherwise), so bbox containment is an exact prefilter; the tiny margin only
+//    guards the sign of its double-precision cross product next to a vertex.
+constexpr int kContainThreads = 128;
+
+__global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int32_t *__restrict__ counts, int cap,
+                                                                       EastScratch S)
+{
+    const int page = blockIdx.y;
+    const int K = counts[page];
+    if (K <= 1) return;
+    const size_t pb = (size_t)page * cap;
+    const float *work = S.work + pb * 9;
+    const float *area = S.area + pb;
+    const float4 *bbox = S.bbox + pb;
+    __shared__ float4 s_bb[kContainThreads];
+    __shared__ float s_ar[kContainThreads];
+    const float eps = (float)1e-6;
+    for (int base_i = blockIdx.x * kContainThreads; base_i < K; base_i += gridDim.x * kContainThreads) {
+        const int i = base_i + threadIdx.x;
+        const bool live = i < K;
+        float qi[8];
+        float ai = 0.f;
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) {
 #pragma unroll
             for (int k = 0; k < 8; k++) qi[k] = work[(size_t)i * 9 + k];
-            const float ai = area[i];
-            const int ri = rank[i];
-            bool later_hit = false, earlier_hit = false;
-            for (int j = 0; j < K && !later_hit; j++) {
+            ai = area[i];
+            bi = bbox[i];
+        }
+        bool later_hit = false, earlier_hit = false;
+        for (int base_j = 0; base_j < K; base_j += kContainThreads) {
+            __syncthreads();
+            const int jj = base_j + threadIdx.x;
+            if (jj < K) {
+                float4 b = bbox[jj];
+                const float mx = 1e-4f * fmaxf(fabsf(b.x), fabsf(b.z)) + 1e-3f;
+                const float my = 1e-4f * fmaxf(fabsf(b.y), fabsf(b.w)) + 1e-3f;
+                s_bb[threadIdx.x] = make_float4(b.x - mx, b.y - my, b.z + mx, b.w + my);
+                s_ar[threadIdx.x] = area[jj];
+            }
+            __syncthreads();
+            if (!live || later_hit) continue;
+            const int nj = min(kContainThreads, K - base_j);
+            for (int t = 0; t < nj; t++) {
+                const int j = base_j + t;
+                const float aj = s_ar[t];
+                if (aj + eps < ai) continue;  // infer.py:208
+                const float4 bj = s_bb[t];
+                if (!(bi.x >= bj.x && bi.y >= bj.y && bi.z <= bj.z && bi.w <= bj.w)) continue;
                 if (j == i) continue;
-                if (area[j] + eps < ai) continue;  // infer.py:208
                 float qj[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
                 if (!quad_inside(qi, qj)) continue;
-                if (rank[j] > ri)
-                    later_hit = true;  // j is still unprocessed (kept) when i is visited
-                else
-                    earlier_hit = true;  // j's own fate decides
+                if (area_before(ai, i, aj, j)) {  // j is visited after i: still kept when i is visited
+                    later_hit = true;
+                    break;
+                }
+                earlier_hit = true;  // j's own fate decides
             }
-            removed[i] = later_hit ? 1 : 0;
-            needseq[i] = (!later_hit && earlier_hit) ? 1 : 0;
+        }
+        if (live) {
+            S.removed[pb + i] = later_hit ? 1 : 0;
+            S.needseq[pb + i] = (!later_hit && earlier_hit) ? 1 : 0;
+        }
+    }
+}
+
+// 3) one CTA per page: the rare sequential leftovers, then anomaly removal -> axis align -> write.
+__global__ void __launch_bounds__(512) east_finish_kernel(const int32_t *__restrict__ counts, int cap,
+                                                          ms_east_params P, EastScratch S, float *__restrict__ out,
+                                                          int out_cap, int32_t *__restrict__ counts_out,
+                                                          int32_t *__restrict__ flags)
+{
+    const int page = blockIdx.x;
+    const int K = counts[page];
+    const size_t pb = (size_t)page * cap;
+    const float *work = S.work + pb * 9;
+    const float *area = S.area + pb;
+    int32_t *kidx = S.kidx + pb, *seq = S.seq + pb;
+    uint8_t *removed = S.removed + pb;
+    const uint8_t *needseq = S.needseq + pb;
+    float *karea = S.karea + pb, *kdev = S.kdev + pb;
+    __shared__ int s_warp[33];
+    __shared__ int s_flag;
+    __shared__ float s_thr;
+    __shared__ int s_apply;
+    const float eps = (float)1e-6;
+
+    // boxes whose only containers precede them in the scan (near-equal areas, duplicates): gather them,
+    // order them by area rank and resolve each one cooperatively
+    int NS = 0;
+    for (int base = 0; base < K; base += blockDim.x) {
+        int i = base + threadIdx.x;
+        int k = (i < K && needseq[i]) ? 1 : 0;
+        int total;
+        int pos = block_excl_scan(k, s_warp, total);
+        if (k) kidx[NS + pos] = i;
+        NS += total;
+    }
+    __syncthreads();
+    if (NS > 0) {
+        for (int t = threadIdx.x; t < NS; t += blockDim.x) {
+            const int i = kidx[t];
+            const float ai = area[i];
+            int r = 0;
+            for (int u = 0; u < NS; u++) {
+                const int j = kidx[u];
+                r += (j != i && area_before(area[j], j, ai, i)) ? 1 : 0;
+            }
+            seq[r] = i;
         }
         __syncthreads();
-        // the rare boxes whose only containers precede them in the scan (near-equal areas, duplicates):
-        // resolved in rank order, each one cooperatively
-        for (int r = 0; r < K; r++) {
-            const int i = order[r];
-            if (!needseq[i]) continue;  // uniform: same value read by every thread
+        for (int r = 0; r < NS; r++) {
+            const int i = seq[r];
             if (threadIdx.x == 0) s_flag = 0;
             __syncthreads();
             float qi[8];
@@ -287,8 +364,10 @@ __global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict
             const float ai = area[i];
             bool hit = false;
             for (int j = threadIdx.x; j < K && !hit; j += blockDim.x) {
-                if (j == i || rank[j] > r || removed[j]) continue;
-                if (area[j] + eps < ai) continue;
+                if (j == i || removed[j]) continue;
+                const float aj = area[j];
+                if (!area_before(aj, j, ai, i)) continue;  // later boxes were handled by the pairwise pass
+                if (aj + eps < ai) continue;
                 float qj[8];
 #pragma unroll
                 for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
@@ -316,7 +395,7 @@ __global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict
     }
     __syncthreads();
 
-    // 3) infer.py:216-233 area anomalies: numpy f32 mean / std (pairwise sums), threshold in f32
+    // infer.py:216-233 area anomalies: numpy f32 mean / std (pairwise sums), threshold in f32
     if (threadIdx.x == 0) s_apply = 0;
     __syncthreads();
     if (P.remove_area_anomalies && K1 > 0 && K1 > P.anomaly_min_box_count) {
@@ -355,16 +434,16 @@ __global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict
     const bool apply = s_apply != 0;
     const float athr = s_thr;
 
-    // compaction 2 + 4) infer.py:149-172 axis alignment, write
+    // compaction 2 + infer.py:149-172 axis alignment, write (rows beyond out_cap are dropped and flagged)
     int K2 = 0;
     for (int base = 0; base < K1; base += blockDim.x) {
         int t = base + threadIdx.x;
         int k = (t < K1 && (!apply || karea[t] <= athr)) ? 1 : 0;
         int total;
         int pos = block_excl_scan(k, s_warp, total);
-        if (k) {
+        if (k && K2 + pos < out_cap) {
             const float *q = work + (size_t)kidx[t] * 9;
-            float *o = out + (pb + K2 + pos) * 9;
+            float *o = out + ((size_t)page * out_cap + K2 + pos) * 9;
             if (P.axis_aligned_output) {
                 float x0 = q[0], x1 = q[0], y0 = q[1], y1 = q[1];
 #pragma unroll
@@ -384,7 +463,13 @@ __global__ void __launch_bounds__(512) east_boxes_kernel(const float *__restrict
         }
         K2 += total;
     }
-    if (threadIdx.x == 0) counts_out[page] = K2;
+    if (threadIdx.x == 0) {
+        if (K2 > out_cap) {
+            if (flags) atomicOr(flags + page, MS_FLAG_CAND_OVERFLOW);
+            K2 = out_cap;
+        }
+        counts_out[page] = K2;
+    }
 }
 
 // ---- _pipeline.py:125-137, 204-221 ---------------------------------------------------------------------
@@ -525,10 +610,10 @@ void carve_east(ms_bump &bump, EastScratch &S, size_t n)
 {
     S.work = bump.take<float>(n * 9);
     S.area = bump.take<float>(n);
-    S.order = bump.take<int32_t>(n);
-    S.rank = bump.take<int32_t>(n);
+    S.bbox = bump.take<float4>(n);
     S.removed = bump.take<uint8_t>(n);
     S.needseq = bump.take<uint8_t>(n);
+    S.seq = bump.take<int32_t>(n);
     S.karea = bump.take<float>(n);
     S.kdev = bump.take<float>(n);
     S.kidx = bump.take<int32_t>(n);
@@ -555,11 +640,11 @@ size_t msk_east_boxes_scratch(int n_pages, int cap_per_page)
 }
 
 int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
-                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
-                   ms_bump bump, cudaStream_t st)
+                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int out_cap, int32_t *counts_out,
+                   int32_t *flags, ms_bump bump, cudaStream_t st)
 {
     if (n_pages <= 0) return MS_OK;
-    if (!p || p->target_size <= 0) {
+    if (!p || p->target_size <= 0 || out_cap <= 0) {
         ms_set_error("east_boxes: bad params");
         return MS_ERR_INVALID;
     }
@@ -569,8 +654,17 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
         ms_set_error("east_boxes: scratch too small");
         return MS_ERR_CAPACITY;
     }
+    // counts live on the device: grids are sized for a few thousand boxes per page and stride beyond that
+    int gx = (cap_per_page + 255) / 256;
+    if (gx > 16) gx = 16;
+    east_prep_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(quads, counts, n_pages, cap_per_page, *p, orig_hw, S);
+    MS_LAUNCH_CHECK(ctx);
+    gx = (cap_per_page + kContainThreads - 1) / kContainThreads;
+    if (gx > 32) gx = 32;
+    east_contain_kernel<<<dim3(gx, n_pages), kContainThreads, 0, st>>>(counts, cap_per_page, S);
+    MS_LAUNCH_CHECK(ctx);
     // device recursion in np_pairwise_f32: depth <= log2(cap/128) + 1 frames of a few dozen bytes
-    east_boxes_kernel<<<n_pages, 512, 0, st>>>(quads, counts, cap_per_page, *p, orig_hw, S, quads_out, counts_out);
+    east_finish_kernel<<<n_pages, 512, 0, st>>>(counts, cap_per_page, *p, S, quads_out, out_cap, counts_out, flags);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

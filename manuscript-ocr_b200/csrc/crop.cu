@@ -12,79 +12,65 @@
 //   same size:    copy
 // then paste at (x0=0, y0=(ih-new_h)//2) on a 255 canvas, (v - 127.5) * (1/127.5) in f32, HWC -> CHW.
 //
-// HBM roofline: per crop 3*w*h bytes gathered + 3*ih*iw*4 bytes written (49 152 B at 32x128): the
-// kernel is write dominated.  One CTA per crop (persistent grid); the canvas is assembled in shared
-// memory and streamed out with 16-byte coalesced stores.
+// HBM roofline: per crop 3*w*h source bytes read + 3*ih*iw*4 bytes written (49 152 B at 32x128): the
+// kernel is write dominated.
+//
+// Kernel shape (persistent CTAs, one crop per CTA iteration, double buffered):
+//   * warp 0 stages the NEXT crop's source rows into shared memory with TMA bulk copies
+//     (cp.async.bulk global->shared, one 16-byte-aligned span per row, completion on an mbarrier)
+//     while all warps resample the CURRENT crop out of the other buffer;
+//   * per-crop axis tables (OpenCV's decimation / linear coefficient tables) are built once per crop
+//     in shared memory -- the float64 table arithmetic runs nw+nh times, not nw*nh times;
+//   * resampled pixels are normalised and stored straight to the CHW batch (coalesced 4-byte stores
+//     along x); the 255-padding is written as constant 16-byte streaming stores.  No canvas round trip.
+//   * crops whose source rows do not fit the staging buffer read global memory directly (same code).
 #include "ms_internal.cuh"
 
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kMaxEntries = 10;  // cached decimation-table entries per axis (longer tables are recomputed)
+constexpr int kSrcBuf = 32 * 1024;  // bytes per staging buffer (two per CTA)
 
-struct AreaAxis {
-    // OpenCV computeResizeAreaTab for one destination index
-    int s_first;        // source index of the first entry
-    int n;              // number of entries
-    float a_first, a_mid, a_last;
-    bool has_first, has_last;
-    int s_mid0, s_mid1;  // full-weight source range [s_mid0, s_mid1)
+struct Plan {
+    int page, x1, y1, w, h;
+    int nw, nh, y0;
+    int interp;  // 0 copy, 1 linear, 2 area integer-ratio, 3 area general
+    int isx, isy;
+    int ok;
+    int staged;  // source rows staged through TMA into shared memory
+    int pitch;   // shared-memory row pitch (bytes) when staged
+    double scale_x, scale_y;
 };
 
-__device__ __forceinline__ AreaAxis area_axis(int d, double scale, int ssize)
-{
-    AreaAxis t;
-    double f1 = d * scale, f2 = f1 + scale;
-    double cell = fmin(scale, (double)ssize - f1);
-    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
-    s2 = min(s2, ssize - 1);
-    s1 = min(s1, s2);
-    t.has_first = (s1 - f1) > 1e-3;
-    t.a_first = (float)((s1 - f1) / cell);
-    t.s_mid0 = s1;
-    t.s_mid1 = s2;
-    t.a_mid = (float)(1.0 / cell);
-    t.has_last = (f2 - s2) > 1e-3;
-    t.a_last = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
-    t.s_first = t.has_first ? s1 - 1 : s1;
-    t.n = (t.has_first ? 1 : 0) + (s2 > s1 ? s2 - s1 : 0) + (t.has_last ? 1 : 0);
-    return t;
-}
-
-__device__ __forceinline__ float axis_weight(const AreaAxis &t, int e, int &src)
-{
-    // e-th entry in table order
-    if (t.has_first) {
-        if (e == 0) {
-            src = t.s_mid0 - 1;
-            return t.a_first;
-        }
-        e--;
-    }
-    int mid = t.s_mid1 - t.s_mid0;
-    if (mid < 0) mid = 0;
-    if (e < mid) {
-        src = t.s_mid0 + e;
-        return t.a_mid;
-    }
-    src = t.s_mid1;
-    return t.a_last;
-}
+// one destination index of one axis: the OpenCV coefficient table entry
+struct AxisEnt {
+    int s0;      // area: first source index; linear: left/top source index
+    int n;       // area: number of taps;     linear x: edge flag;  linear y: bottom source index
+    int nfirst;  // area: 1 if a partial first tap exists; linear: coefficient 0 (a0 / b0)
+    int nmid;    // area: number of full-weight taps;      linear: coefficient 1 (a1 / b1)
+    float af, am, al;
+    int pad;
+};
 
 __device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
 __device__ __forceinline__ unsigned char sat_u8(int v) { return (unsigned char)min(max(v, 0), 255); }
 
-struct Plan {
-    int w, h, nw, nh, x0, y0, interp;  // interp: 0 copy, 1 linear, 2 area-fast, 3 area-general
-    double scale_x, scale_y;
-    int isx, isy;
-};
-
-__device__ __forceinline__ Plan make_plan(int w, int h, int ih, int iw)
+__device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int img_h, int img_w, int ih, int iw,
+                                          const uint8_t *pages, size_t total_bytes, Plan &p)
 {
-    Plan p;
-    p.w = w;
-    p.h = h;
+    p.page = cr[0];
+    p.x1 = cr[1];
+    p.y1 = cr[2];
+    p.w = cr[3] - cr[1];
+    p.h = cr[4] - cr[2];
+    p.ok = p.page >= 0 && p.page < n_pages && p.w > 0 && p.h > 0 && p.x1 >= 0 && p.y1 >= 0 && cr[3] <= img_w &&
+           cr[4] <= img_h;
+    p.staged = 0;
+    p.pitch = 0;
+    p.nw = p.nh = p.y0 = p.interp = p.isx = p.isy = 0;
+    p.scale_x = p.scale_y = 1.0;
+    if (!p.ok) return;
+    const int w = p.w, h = p.h;
     // transforms.py:91-95
     double s1 = (double)ih / (double)max(h, 1), s2 = (double)iw / (double)max(w, 1);
     double sc = fmin(s1, s2);
@@ -93,7 +79,6 @@ __device__ __forceinline__ Plan make_plan(int w, int h, int ih, int iw)
     p.nw = min(p.nw, iw);
     p.nh = min(p.nh, ih);
     int shrink = (p.nh < h || p.nw < w);  // transforms.py:80-83
-    p.x0 = 0;
     p.y0 = (ih - p.nh) / 2;
     p.y0 = max(0, min(p.y0, ih - p.nh));
     p.scale_x = 1.0 / ((double)p.nw / (double)w);
@@ -108,200 +93,367 @@ __device__ __forceinline__ Plan make_plan(int w, int h, int ih, int iw)
         bool fast = fabs(p.scale_x - p.isx) < 2.220446049250313e-16 && fabs(p.scale_y - p.isy) < 2.220446049250313e-16;
         p.interp = fast ? 2 : 3;
     }
-    return p;
+    // staging: every row is copied as the 16-byte-aligned span that covers it
+    const int pitch = ((w * 3 + 15 + 15) & ~15);
+    const size_t stride = (size_t)img_w * 3;
+    const size_t first = (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+    const size_t last_end = first + (size_t)(h - 1) * stride + (size_t)w * 3;
+    const uintptr_t base = reinterpret_cast<uintptr_t>(pages);
+    const bool fits = (size_t)pitch * h <= (size_t)kSrcBuf;
+    // the last row's aligned span must not run past the end of the page tensor
+    const bool tail_ok = ((base + last_end + 15) & ~(uintptr_t)15) <= base + total_bytes;
+    if (fits && tail_ok && (base & 15) == 0) {
+        p.staged = 1;
+        p.pitch = pitch;
+    }
+}
+
+// OpenCV computeResizeAreaTab for destination index d
+__device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize)
+{
+    AxisEnt t;
+    double f1 = d * scale, f2 = f1 + scale;
+    double cell = fmin(scale, (double)ssize - f1);
+    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
+    s2 = min(s2, ssize - 1);
+    s1 = min(s1, s2);
+    const bool has_first = (s1 - f1) > 1e-3;
+    const bool has_last = (f2 - s2) > 1e-3;
+    t.af = (float)((s1 - f1) / cell);
+    t.am = (float)(1.0 / cell);
+    t.al = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
+    t.nfirst = has_first ? 1 : 0;
+    t.nmid = s2 > s1 ? s2 - s1 : 0;
+    t.s0 = has_first ? s1 - 1 : s1;
+    t.n = t.nfirst + t.nmid + (has_last ? 1 : 0);
+    t.pad = 0;
+    return t;
+}
+
+__device__ __forceinline__ float area_weight(const AxisEnt &t, int e)
+{
+    return e < t.nfirst ? t.af : (e < t.nfirst + t.nmid ? t.am : t.al);
+}
+
+__device__ __forceinline__ AxisEnt linear_entry_x(int dx, double scale, int w)
+{
+    AxisEnt t;
+    float fx = (float)((dx + 0.5) * scale - 0.5);
+    int sx = (int)floorf(fx);
+    fx -= sx;
+    if (sx < 0) {
+        fx = 0;
+        sx = 0;
+    }
+    const bool edge = sx + 1 >= w;
+    if (edge) {
+        fx = 0;
+        sx = w - 1;
+    }
+    t.s0 = sx;
+    t.n = edge ? 1 : 0;
+    t.nfirst = (short)cv_round((1.f - fx) * 2048.f);
+    t.nmid = (short)cv_round(fx * 2048.f);
+    t.af = t.am = t.al = 0.f;
+    t.pad = 0;
+    return t;
+}
+
+__device__ __forceinline__ AxisEnt linear_entry_y(int dy, double scale, int h)
+{
+    AxisEnt t;
+    float fy = (float)((dy + 0.5) * scale - 0.5);
+    int sy = (int)floorf(fy);
+    fy -= sy;
+    t.s0 = min(max(sy, 0), h - 1);
+    t.n = min(max(sy + 1, 0), h - 1);
+    t.nfirst = (short)cv_round((1.f - fy) * 2048.f);
+    t.nmid = (short)cv_round(fy * 2048.f);
+    t.af = t.am = t.al = 0.f;
+    t.pad = 0;
+    return t;
+}
+
+// ---- mbarrier + TMA bulk copy (sm_90+ PTX; SASS: SYNCS / UBLKCP) ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// warp 0: issue the row copies of one crop into `buf`
+__device__ __forceinline__ void stage_rows(const Plan &p, const uint8_t *pages, int img_h, int img_w, unsigned char *buf,
+                                           uint64_t *bar, int lane)
+{
+    const size_t stride = (size_t)img_w * 3;
+    const uint8_t *src = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+    uint32_t bytes = 0;
+    for (int r = lane; r < p.h; r += 32) {
+        const uint8_t *g = src + (size_t)r * stride;
+        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+        const uint32_t sz = (a + (uint32_t)p.w * 3 + 15) & ~15u;
+        tma_bulk_g2s(buf + (size_t)r * p.pitch, g - a, sz, bar);
+        bytes += sz;
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
+    if (lane == 0) mbar_expect_tx(bar, bytes);
+}
+
+// resample one destination pixel (3 channels); `row(sy)` gives the address of source pixel (x=0) of row sy
+template <typename RowFn>
+__device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, const AxisEnt *ty, int dx, int dy,
+                                            RowFn row, unsigned char &o0, unsigned char &o1, unsigned char &o2)
+{
+    if (p.interp == 0) {
+        const unsigned char *s = row(dy) + dx * 3;
+        o0 = s[0];
+        o1 = s[1];
+        o2 = s[2];
+    } else if (p.interp == 1) {
+        const AxisEnt ex = tx[dx], ey = ty[dy];
+        const unsigned char *S0 = row(ey.s0) + ex.s0 * 3;
+        const unsigned char *S1 = row(ey.n) + ex.s0 * 3;
+        const int a0 = ex.nfirst, a1 = ex.nmid, b0 = ey.nfirst, b1 = ey.nmid;
+        unsigned char o[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            int r0, r1;
+            if (ex.n) {
+                r0 = S0[c] * 2048;
+                r1 = S1[c] * 2048;
+            } else {
+                r0 = S0[c] * a0 + S0[c + 3] * a1;
+                r1 = S1[c] * a0 + S1[c + 3] * a1;
+            }
+            o[c] = (unsigned char)((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2);
+        }
+        o0 = o[0];
+        o1 = o[1];
+        o2 = o[2];
+    } else if (p.interp == 2) {
+        int s0 = 0, s1 = 0, s2 = 0;
+        for (int yy = 0; yy < p.isy; yy++) {
+            const unsigned char *s = row(dy * p.isy + yy) + (size_t)dx * p.isx * 3;
+            for (int xx = 0; xx < p.isx; xx++) {
+                s0 += s[xx * 3];
+                s1 += s[xx * 3 + 1];
+                s2 += s[xx * 3 + 2];
+            }
+        }
+        if (p.isx == 2 && p.isy == 2) {
+            o0 = (unsigned char)((s0 + 2) >> 2);
+            o1 = (unsigned char)((s1 + 2) >> 2);
+            o2 = (unsigned char)((s2 + 2) >> 2);
+        } else {
+            const float inv = 1.f / (float)(p.isx * p.isy);
+            o0 = sat_u8(cv_round((float)s0 * inv));
+            o1 = sat_u8(cv_round((float)s1 * inv));
+            o2 = sat_u8(cv_round((float)s2 * inv));
+        }
+    } else {
+        const AxisEnt ex = tx[dx], ey = ty[dy];
+        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+        for (int j = 0; j < ey.n; j++) {
+            const float beta = area_weight(ey, j);
+            const unsigned char *s = row(ey.s0 + j) + ex.s0 * 3;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            for (int e = 0; e < ex.n; e++) {
+                const float a = area_weight(ex, e);
+                b0 = b0 + (float)s[e * 3] * a;
+                b1 = b1 + (float)s[e * 3 + 1] * a;
+                b2 = b2 + (float)s[e * 3 + 2] * a;
+            }
+            if (j == 0) {
+                sum0 = beta * b0;
+                sum1 = beta * b1;
+                sum2 = beta * b2;
+            } else {
+                sum0 += beta * b0;
+                sum1 += beta * b1;
+                sum2 += beta * b2;
+            }
+        }
+        o0 = sat_u8(cv_round(sum0));
+        o1 = sat_u8(cv_round(sum1));
+        o2 = sat_u8(cv_round(sum2));
+    }
 }
 
 template <bool kWriteF32, bool kWriteU8>
-__global__ void __launch_bounds__(kThreads) crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int n_pages,
-                                                                   int img_h, int img_w,
-                                                                   const int32_t *__restrict__ crops,
-                                                                   const int32_t *__restrict__ n_crops_dev,
-                                                                   int64_t crops_cap, int ih, int iw,
-                                                                   float *__restrict__ batch,
-                                                                   uint8_t *__restrict__ canvas_out)
+__global__ void __launch_bounds__(kThreads, 3)
+    crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int n_pages, int img_h, int img_w,
+                           const int32_t *__restrict__ crops, const int32_t *__restrict__ n_crops_dev, int64_t crops_cap,
+                           int ih, int iw, float *__restrict__ batch, uint8_t *__restrict__ canvas_out, int vec_ok)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    float *lut = reinterpret_cast<float *>(smem);          // 256 floats
-    unsigned char *canvas = smem + 256 * sizeof(float);      // ih*iw*3 bytes (padded to 16)
-    const int canvas_bytes = ih * iw * 3;
-    {
-        const float inv = 1.0f / 127.5f;
-        for (int v = threadIdx.x; v < 256; v += kThreads) lut[v] = ((float)v - 127.5f) * inv;
-    }
+    extern __shared__ __align__(128) unsigned char smem[];
+    unsigned char *src_buf[2] = {smem, smem + kSrcBuf};
+    AxisEnt *tab_x = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);
+    AxisEnt *tab_y = tab_x + iw;
+    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ Plan s_plan[2];
+
     int64_t n_crops = *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
-    const size_t page_bytes = (size_t)img_h * img_w * 3;
     const size_t stride = (size_t)img_w * 3;
+    const size_t total_bytes = (size_t)n_pages * img_h * stride;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int plane = ih * iw;
+    const float inv = 1.0f / 127.5f;
 
-    for (int64_t ci = blockIdx.x; ci < n_crops; ci += gridDim.x) {
-        __syncthreads();  // previous canvas fully consumed
-        const int32_t *cr = crops + ci * 5;
-        const int page = cr[0], x1 = cr[1], y1 = cr[2], x2 = cr[3], y2 = cr[4];
-        const int w = x2 - x1, h = y2 - y1;
-        bool ok = page >= 0 && page < n_pages && w > 0 && h > 0 && x1 >= 0 && y1 >= 0 && x2 <= img_w && y2 <= img_h;
-        // 255 canvas (transforms.py:100)
-        {
-            uint32_t *c4 = reinterpret_cast<uint32_t *>(canvas);
-            for (int i = threadIdx.x; i < (canvas_bytes + 3) / 4; i += kThreads) c4[i] = 0xFFFFFFFFu;
+    if (threadIdx.x == 0) {
+        mbar_init(&s_bar[0], 1);
+        mbar_init(&s_bar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // prologue: plan + stage this CTA's first crop
+    if (warp == 0 && (int64_t)blockIdx.x < n_crops) {
+        if (lane == 0)
+            make_plan(crops + (int64_t)blockIdx.x * 5, n_pages, img_h, img_w, ih, iw, pages, total_bytes, s_plan[0]);
+    }
+    __syncthreads();
+    if (warp == 0 && (int64_t)blockIdx.x < n_crops && s_plan[0].staged)
+        stage_rows(s_plan[0], pages, img_h, img_w, src_buf[0], &s_bar[0], lane);
+
+    uint32_t phase0 = 0, phase1 = 0;
+    int it = 0;
+    for (int64_t ci = blockIdx.x; ci < n_crops; ci += gridDim.x, it++) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        // producer: plan + stage the next crop into the other buffer (free since the trailing barrier of
+        // the previous iteration)
+        const int64_t cn = ci + gridDim.x;
+        if (warp == 0 && cn < n_crops) {
+            if (lane == 0) make_plan(crops + cn * 5, n_pages, img_h, img_w, ih, iw, pages, total_bytes, s_plan[nxt]);
+            __syncwarp();
+            if (s_plan[nxt].staged) stage_rows(s_plan[nxt], pages, img_h, img_w, src_buf[nxt], &s_bar[nxt], lane);
         }
-        __syncthreads();
-        if (ok) {
-            const Plan p = make_plan(w, h, ih, iw);
-            const uint8_t *src = pages + (size_t)page * page_bytes + (size_t)y1 * stride + (size_t)x1 * 3;
-            const int npx = p.nw * p.nh;
-            for (int t = threadIdx.x; t < npx; t += kThreads) {
-                const int dy = t / p.nw, dx = t - dy * p.nw;
-                unsigned char o0, o1, o2;
-                if (p.interp == 0) {
-                    const uint8_t *s = src + (size_t)dy * stride + dx * 3;
-                    o0 = s[0];
-                    o1 = s[1];
-                    o2 = s[2];
-                } else if (p.interp == 1) {
-                    float fx = (float)((dx + 0.5) * p.scale_x - 0.5);
-                    int sx = (int)floorf(fx);
-                    fx -= sx;
-                    if (sx < 0) {
-                        fx = 0;
-                        sx = 0;
-                    }
-                    bool edge = sx + 1 >= w;
-                    if (edge) {
-                        fx = 0;
-                        sx = w - 1;
-                    }
-                    const int a0 = (short)cv_round((1.f - fx) * 2048.f), a1 = (short)cv_round(fx * 2048.f);
-                    float fy = (float)((dy + 0.5) * p.scale_y - 0.5);
-                    int sy = (int)floorf(fy);
-                    fy -= sy;
-                    const int b0 = (short)cv_round((1.f - fy) * 2048.f), b1 = (short)cv_round(fy * 2048.f);
-                    const int ya = min(max(sy, 0), h - 1), yb = min(max(sy + 1, 0), h - 1);
-                    const uint8_t *S0 = src + (size_t)ya * stride + sx * 3;
-                    const uint8_t *S1 = src + (size_t)yb * stride + sx * 3;
-                    unsigned char o[3];
-#pragma unroll
-                    for (int c = 0; c < 3; c++) {
-                        int r0, r1;
-                        if (edge) {
-                            r0 = S0[c] * 2048;
-                            r1 = S1[c] * 2048;
-                        } else {
-                            r0 = S0[c] * a0 + S0[c + 3] * a1;
-                            r1 = S1[c] * a0 + S1[c + 3] * a1;
-                        }
-                        o[c] = (unsigned char)((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2);
-                    }
-                    o0 = o[0];
-                    o1 = o[1];
-                    o2 = o[2];
-                } else if (p.interp == 2) {
-                    int sum[3] = {0, 0, 0};
-                    for (int yy = 0; yy < p.isy; yy++) {
-                        const uint8_t *s = src + (size_t)(dy * p.isy + yy) * stride + (size_t)dx * p.isx * 3;
-                        for (int xx = 0; xx < p.isx; xx++) {
-                            sum[0] += s[xx * 3];
-                            sum[1] += s[xx * 3 + 1];
-                            sum[2] += s[xx * 3 + 2];
-                        }
-                    }
-                    if (p.isx == 2 && p.isy == 2) {
-                        o0 = (unsigned char)((sum[0] + 2) >> 2);
-                        o1 = (unsigned char)((sum[1] + 2) >> 2);
-                        o2 = (unsigned char)((sum[2] + 2) >> 2);
-                    } else {
-                        const float inv = 1.f / (float)(p.isx * p.isy);
-                        o0 = sat_u8(cv_round((float)sum[0] * inv));
-                        o1 = sat_u8(cv_round((float)sum[1] * inv));
-                        o2 = sat_u8(cv_round((float)sum[2] * inv));
-                    }
-                } else {
-                    const AreaAxis tx = area_axis(dx, p.scale_x, w);
-                    const AreaAxis ty = area_axis(dy, p.scale_y, h);
-                    float wx[kMaxEntries];
-                    const bool cached = tx.n <= kMaxEntries;
-                    if (cached) {
-#pragma unroll
-                        for (int e = 0; e < kMaxEntries; e++) {
-                            int sxi;
-                            wx[e] = e < tx.n ? axis_weight(tx, e, sxi) : 0.f;
-                        }
-                    }
-                    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-                    for (int j = 0; j < ty.n; j++) {
-                        int sy;
-                        const float beta = axis_weight(ty, j, sy);
-                        const uint8_t *s = src + (size_t)sy * stride + (size_t)tx.s_first * 3;
-                        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-                        if (cached) {
-#pragma unroll
-                            for (int e = 0; e < kMaxEntries; e++) {
-                                if (e < tx.n) {
-                                    const float a = wx[e];
-                                    b0 = b0 + (float)s[e * 3] * a;
-                                    b1 = b1 + (float)s[e * 3 + 1] * a;
-                                    b2 = b2 + (float)s[e * 3 + 2] * a;
-                                }
-                            }
-                        } else {
-                            for (int e = 0; e < tx.n; e++) {
-                                int sxi;
-                                const float a = axis_weight(tx, e, sxi);
-                                b0 = b0 + (float)s[e * 3] * a;
-                                b1 = b1 + (float)s[e * 3 + 1] * a;
-                                b2 = b2 + (float)s[e * 3 + 2] * a;
-                            }
-                        }
-                        if (j == 0) {
-                            sum0 = beta * b0;
-                            sum1 = beta * b1;
-                            sum2 = beta * b2;
-                        } else {
-                            sum0 += beta * b0;
-                            sum1 += beta * b1;
-                            sum2 += beta * b2;
-                        }
-                    }
-                    o0 = sat_u8(cv_round(sum0));
-                    o1 = sat_u8(cv_round(sum1));
-                    o2 = sat_u8(cv_round(sum2));
-                }
-                unsigned char *d = canvas + ((size_t)(p.y0 + dy) * iw + (p.x0 + dx)) * 3;
-                d[0] = o0;
-                d[1] = o1;
-                d[2] = o2;
+        const Plan p = s_plan[cur];
+        // axis tables of the current crop
+        if (p.ok && (p.interp == 1 || p.interp == 3)) {
+            for (int t = threadIdx.x; t < p.nw + p.nh; t += kThreads) {
+                if (t < p.nw)
+                    tab_x[t] = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
+                else
+                    tab_y[t - p.nw] = p.interp == 3 ? area_entry(t - p.nw, p.scale_y, p.h)
+                                                   : linear_entry_y(t - p.nw, p.scale_y, p.h);
             }
         }
-        __syncthreads();
-        // stream the canvas out: normalised CHW f32 (16-byte stores) and / or the raw HWC bytes
+        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+        const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
+
+        // 255 padding (transforms.py:100) -> 1.0f after normalisation; everything outside the pasted rectangle
         if (kWriteF32) {
-            float *dst = batch + (size_t)ci * 3 * ih * iw;
-            const int plane = ih * iw;
-            if ((iw & 3) == 0) {
-                const int n4 = 3 * plane / 4;
-                for (int i = threadIdx.x; i < n4; i += kThreads) {
-                    int e = i * 4;
-                    int c = e / plane, rem = e - c * plane;  // 4 consecutive x of one (c, y)
-                    const unsigned char *s = canvas + (size_t)rem * 3 + c;
-                    float4 v = make_float4(lut[s[0]], lut[s[3]], lut[s[6]], lut[s[9]]);
-                    __stcs(reinterpret_cast<float4 *>(dst) + i, v);
+            const float one = (255.0f - 127.5f) * inv;
+            if (vec_ok) {
+                const float4 one4 = make_float4(one, one, one, one);
+                const int nw4 = (nw + 3) & ~3;
+                const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
+                for (int c = 0; c < 3; c++) {
+                    float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
+                    for (int i = threadIdx.x; i < top4; i += kThreads) __stcs(base4 + i, one4);
+                    float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
+                    for (int i = threadIdx.x; i < bot4; i += kThreads) __stcs(bot + i, one4);
+                    if (tail4 > 0) {
+                        for (int i = threadIdx.x; i < nh * tail4; i += kThreads) {
+                            int r = i / tail4, k = i - r * tail4;
+                            __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
+                                   one4);
+                        }
+                    }
+                    const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
+                    for (int i = threadIdx.x; i < nh * fr; i += kThreads) {
+                        int r = i / fr, k = i - r * fr;
+                        __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
+                    }
                 }
             } else {
                 for (int e = threadIdx.x; e < 3 * plane; e += kThreads) {
                     int c = e / plane, rem = e - c * plane;
-                    dst[e] = lut[canvas[(size_t)rem * 3 + c]];
+                    int y = rem / iw, x = rem - y * iw;
+                    if (!(y >= y0 && y < y0 + nh && x < nw)) dstf[e] = one;
                 }
             }
         }
         if (kWriteU8) {
-            uint8_t *dst = canvas_out + (size_t)ci * canvas_bytes;
-            if ((canvas_bytes & 3) == 0) {
-                const uint32_t *c4 = reinterpret_cast<const uint32_t *>(canvas);
-                uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);
-                for (int i = threadIdx.x; i < canvas_bytes / 4; i += kThreads) d4[i] = c4[i];
-            } else {
-                for (int i = threadIdx.x; i < canvas_bytes; i += kThreads) dst[i] = canvas[i];
+            for (int e = threadIdx.x; e < plane; e += kThreads) {
+                int y = e / iw, x = e - y * iw;
+                if (!(y >= y0 && y < y0 + nh && x < nw)) {
+                    dstu[(size_t)e * 3] = 255;
+                    dstu[(size_t)e * 3 + 1] = 255;
+                    dstu[(size_t)e * 3 + 2] = 255;
+                }
             }
         }
+        __syncthreads();  // tables visible
+        if (p.ok) {
+            if (p.staged) {
+                if (cur == 0) {
+                    mbar_wait(&s_bar[0], phase0);
+                    phase0 ^= 1;
+                } else {
+                    mbar_wait(&s_bar[1], phase1);
+                    phase1 ^= 1;
+                }
+            }
+            const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+            const unsigned char *sbuf = src_buf[cur];
+            const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 15);
+            const uint32_t sstep = (uint32_t)(stride & 15);  // per-row change of the 16-byte misalignment
+            const int npx = nw * nh;
+            const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
+            for (int t = threadIdx.x; t < npx; t += kThreads) {
+                const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
+                unsigned char o0, o1, o2;
+                if (p.staged) {
+                    auto row = [&](int sy) -> const unsigned char * {
+                        return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
+                    };
+                    resample_px(p, tab_x, tab_y, dx, dy, row, o0, o1, o2);
+                } else {
+                    auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
+                    resample_px(p, tab_x, tab_y, dx, dy, row, o0, o1, o2);
+                }
+                const int at = (y0 + dy) * iw + dx;
+                if (kWriteF32) {
+                    __stcs(dstf + at, ((float)o0 - 127.5f) * inv);
+                    __stcs(dstf + plane + at, ((float)o1 - 127.5f) * inv);
+                    __stcs(dstf + 2 * plane + at, ((float)o2 - 127.5f) * inv);
+                }
+                if (kWriteU8) {
+                    dstu[(size_t)at * 3] = o0;
+                    dstu[(size_t)at * 3 + 1] = o1;
+                    dstu[(size_t)at * 3 + 2] = o2;
+                }
+            }
+        }
+        __syncthreads();  // buffer `cur`, the tables and s_plan[cur] are free again
     }
 }
 
@@ -316,22 +468,27 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
         ms_set_error("crop: bad arguments");
         return MS_ERR_INVALID;
     }
-    size_t smem = 256 * sizeof(float) + (((size_t)out_h * out_w * 3 + 15) & ~size_t(15));
-    if (smem > 200 * 1024) {
-        ms_set_error("crop: canvas %dx%d does not fit in shared memory", out_h, out_w);
+    if ((int64_t)out_h * out_w > (1 << 20)) {
+        ms_set_error("crop: canvas %dx%d too large", out_h, out_w);
         return MS_ERR_INVALID;
     }
-    int per_sm = (int)((200 * 1024) / smem);
-    if (per_sm > 8) per_sm = 8;
+    const size_t smem = 2 * (size_t)kSrcBuf + (size_t)(out_h + out_w) * sizeof(AxisEnt);
+    if (smem > 220 * 1024) {
+        ms_set_error("crop: canvas %dx%d needs %zu bytes of shared memory", out_h, out_w, smem);
+        return MS_ERR_INVALID;
+    }
+    int per_sm = (int)((220 * 1024) / (smem + 1024));
+    if (per_sm > 3) per_sm = 3;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->num_sms * per_sm;
     if (grid > crops_cap) grid = crops_cap;
-#define MS_CROP_LAUNCH(F32, U8)                                                                                      \
-    do {                                                                                                             \
-        auto kfn = crop_resize_pad_kernel<F32, U8>;                                                                  \
-        if (smem > 48 * 1024) MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        kfn<<<(int)grid, kThreads, smem, st>>>(pages, n_pages, img_h, img_w, crops, n_crops, crops_cap, out_h, out_w, \
-                                              batch_f32, canvas_u8);                                                 \
+    const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
+#define MS_CROP_LAUNCH(F32, U8)                                                                                        \
+    do {                                                                                                               \
+        auto kfn = crop_resize_pad_kernel<F32, U8>;                                                                    \
+        MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        kfn<<<(int)grid, kThreads, smem, st>>>(pages, n_pages, img_h, img_w, crops, n_crops, crops_cap, out_h, out_w,  \
+                                              batch_f32, canvas_u8, vec_ok);                                           \
     } while (0)
     if (batch_f32 && canvas_u8)
         MS_CROP_LAUNCH(true, true);

@@ -394,9 +394,11 @@ __device__ __forceinline__ void eval_pair(int a, int b, int p0, int page, double
     }
 }
 
+// Warp per cluster.  irregular_only != 0: only irregular clusters are swept here (each against every other
+// box of its page); the regular ones are handled by lanms_pairs_tiled_kernel.
 __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t *__restrict__ page_off,
                                                                    const int32_t *__restrict__ n_total, double thr,
-                                                                   LanmsBuffers B, int32_t *flags)
+                                                                   LanmsBuffers B, int32_t *flags, int irregular_only)
 {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = *n_total;
@@ -415,6 +417,7 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
         const int C = B.cl_count[page];
         if (a >= C) continue;
         const bool a_irr = B.cl_irr[slot] != 0;
+        if (irregular_only && !a_irr) continue;
         const float4 ba = B.cl_bbox[slot];
         const float limit = ba.z + B.page_slack[page];
         // regular a: forward sweep; irregular a: every other box of the page (pairs of two irregular
@@ -468,6 +471,88 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
     }
 }
 
+// Regular clusters: thread per cluster a, candidates b > a streamed through shared memory in key (x0) order.
+// Keys ascend, so every b whose inflated bbox can touch a's lies in the window (a, last b with key <= maxx_a +
+// page_slack]; the CTA walks tiles until the first key of a tile passes the largest limit of its threads.
+// Bbox-overlapping pairs are queued per warp and evaluated 32 at a time (fp64 Sutherland-Hodgman).
+constexpr int kTile = 128;
+
+__global__ void __launch_bounds__(kTile) lanms_pairs_tiled_kernel(const int32_t *__restrict__ page_off, double thr,
+                                                                  LanmsBuffers B, int32_t *flags)
+{
+    const int page = blockIdx.y;
+    const int p0 = page_off[page];
+    const int C = B.cl_count[page];
+    const int edge_cap = (page_off[page + 1] - p0) * kEdgeFactor;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    __shared__ float4 s_bb[kTile];
+    __shared__ float s_key[kTile];
+    __shared__ uint8_t s_irr[kTile];
+    __shared__ float s_wlim[kTile / 32];
+    __shared__ int2 s_q[kTile / 32][kQueue];
+    int2 *q = s_q[warp];
+    int qn = 0;  // warp-uniform
+    double buf[4 * MS_MAXV];
+    const float slack = B.page_slack[page];
+
+    for (int base = blockIdx.x * kTile; base < C; base += gridDim.x * kTile) {
+        const int a = base + threadIdx.x;
+        const bool a_live = a < C && B.cl_irr[p0 + a] == 0;
+        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
+        float limit = -INFINITY;
+        if (a_live) {
+            ba = B.cl_bbox[p0 + a];
+            limit = ba.z + slack;
+        }
+        float wl = limit;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) wl = fmaxf(wl, __shfl_xor_sync(0xffffffffu, wl, off));
+        __syncthreads();  // previous tile loop done with s_wlim / tiles
+        if (lane == 0) s_wlim[warp] = wl;
+        __syncthreads();
+        float blk_limit = s_wlim[0];
+#pragma unroll
+        for (int w = 1; w < kTile / 32; w++) blk_limit = fmaxf(blk_limit, s_wlim[w]);
+
+        for (int tb = base + 1; tb < C; tb += kTile) {
+            __syncthreads();
+            const int bl = tb + threadIdx.x;
+            if (bl < C) {
+                s_bb[threadIdx.x] = B.cl_bbox[p0 + bl];
+                s_key[threadIdx.x] = B.cl_key[p0 + bl];
+                s_irr[threadIdx.x] = B.cl_irr[p0 + bl];
+            }
+            __syncthreads();
+            if (s_key[0] > blk_limit) break;  // uniform: nothing from here on can touch any a of this CTA
+            const int nb = min(kTile, C - tb);
+            if (wl == -INFINITY) continue;  // warp has no regular cluster in this tile of a's
+            for (int t = 0; t < nb; t++) {
+                const int b = tb + t;
+                if (s_key[t] > wl) break;  // warp-uniform
+                const float4 o = s_bb[t];
+                const bool hit = a_live && b > a && !s_irr[t] &&
+                                 !(o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y);
+                const uint32_t m = __ballot_sync(0xffffffffu, hit);
+                if (m == 0) continue;
+                if (hit) q[qn + __popc(m & ((1u << lane) - 1u))] = make_int2(a, b);
+                qn += __popc(m);
+                __syncwarp();
+                while (qn >= 32) {
+                    const int2 pr = q[qn - 32 + lane];
+                    __syncwarp();
+                    eval_pair(pr.x, pr.y, p0, page, thr, B, edge_cap, flags, buf);
+                    qn -= 32;
+                    __syncwarp();
+                }
+            }
+        }
+    }
+    if (lane < qn) {
+        const int2 pr = q[lane];
+        eval_pair(pr.x, pr.y, p0, page, thr, B, edge_cap, flags, buf);
+    }
+}
+
 // ---- 6. greedy recurrence in rounds (one CTA per page) ----------------------------------------------------------
 __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
 {
@@ -513,11 +598,9 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
     }
 }
 
-// ---- 7. kept clusters -> rows in stable descending-score order (one CTA per page) -------------------------------
-__global__ void __launch_bounds__(1024) lanms_emit_kernel(const int32_t *__restrict__ page_off, int cap,
-                                                          LanmsBuffers B, float *__restrict__ out,
-                                                          int32_t *__restrict__ counts_out,
-                                                          int32_t *__restrict__ keep_idx_out)
+// ---- 7. kept clusters -> rows in stable descending-score order ----------------------------------------------------
+__global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B,
+                                                          int32_t *__restrict__ counts_out)
 {
     const int page = blockIdx.x;
     const int p0 = page_off[page];
@@ -533,26 +616,58 @@ __global__ void __launch_bounds__(1024) lanms_emit_kernel(const int32_t *__restr
         if (k) kept[run_base + pos] = c;
         run_base += total;
     }
-    __syncthreads();
-    const int K = run_base;
-    if (threadIdx.x == 0) counts_out[page] = K;
-    for (int i = threadIdx.x; i < K; i += blockDim.x) {
-        int c = kept[i];
-        double sc = B.cl_score[p0 + c];
-        int oc = B.cl_orig[p0 + c];
+    if (threadIdx.x == 0) counts_out[page] = run_base;
+}
+
+constexpr int kRankThreads = 256;
+
+// rank of every kept cluster among the kept ones of its page (np.argsort(-scores, kind="stable") position)
+__global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t *__restrict__ page_off, int cap,
+                                                                  LanmsBuffers B, float *__restrict__ out,
+                                                                  const int32_t *__restrict__ counts_out,
+                                                                  int32_t *__restrict__ keep_idx_out)
+{
+    const int page = blockIdx.y;
+    const int p0 = page_off[page];
+    const int K = counts_out[page];
+    const int32_t *kept = B.kept_list + p0;
+    __shared__ double s_sc[kRankThreads];
+    __shared__ int s_oc[kRankThreads];
+    for (int base = blockIdx.x * kRankThreads; base < K; base += gridDim.x * kRankThreads) {
+        const int i = base + threadIdx.x;
+        const bool live = i < K;
+        int c = 0, oc = 0;
+        double sc = 0.0;
+        if (live) {
+            c = kept[i];
+            sc = B.cl_score[p0 + c];
+            oc = B.cl_orig[p0 + c];
+        }
         int rank = 0;
-        for (int j = 0; j < K; j++) {
-            int c2 = kept[j];
-            if (c2 != c && prio_before(B.cl_score[p0 + c2], B.cl_orig[p0 + c2], sc, oc)) rank++;
+        for (int tb = 0; tb < K; tb += kRankThreads) {
+            __syncthreads();
+            const int j = tb + threadIdx.x;
+            if (j < K) {
+                const int c2 = kept[j];
+                s_sc[threadIdx.x] = B.cl_score[p0 + c2];
+                s_oc[threadIdx.x] = B.cl_orig[p0 + c2];
+            }
+            __syncthreads();
+            const int nb = min(kRankThreads, K - tb);
+            if (live)
+                for (int t = 0; t < nb; t++)
+                    rank += (s_oc[t] != oc && prio_before(s_sc[t], s_oc[t], sc, oc)) ? 1 : 0;
         }
-        if (out) {
-            float *row = out + ((size_t)page * cap + rank) * 9;
-            const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
+        if (live) {
+            if (out) {
+                float *row = out + ((size_t)page * cap + rank) * 9;
+                const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
 #pragma unroll
-            for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
-            row[8] = (float)sc;
+                for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
+                row[8] = (float)sc;
+            }
+            if (keep_idx_out) keep_idx_out[(size_t)page * cap + rank] = oc;
         }
-        if (keep_idx_out) keep_idx_out[(size_t)page * cap + rank] = oc;
     }
 }
 
@@ -684,12 +799,26 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
     MS_LAUNCH_CHECK(ctx);
     lanms_clusters_kernel<<<n_pages, kResolveThreads, 0, st>>>(B.page_off, thr < 0 ? 1 : 0, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags);
+    {
+        // cluster counts live on the device: size the a-tile grid for a typical page and stride beyond it
+        int gx = (cap_per_page + kTile - 1) / kTile;
+        if (gx > 128) gx = 128;
+        lanms_pairs_tiled_kernel<<<dim3(gx, n_pages), kTile, 0, st>>>(B.page_off, thr, B, flags);
+        MS_LAUNCH_CHECK(ctx);
+    }
+    lanms_pairs_kernel<<<sms * 4, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 1);
     MS_LAUNCH_CHECK(ctx);
     lanms_resolve_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_emit_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out, nullptr);
+    lanms_kept_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, counts_out);
     MS_LAUNCH_CHECK(ctx);
+    {
+        int gx = (cap_per_page + kRankThreads - 1) / kRankThreads;
+        if (gx > 32) gx = 32;
+        lanms_emit_kernel<<<dim3(gx, n_pages), kRankThreads, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out,
+                                                                       nullptr);
+        MS_LAUNCH_CHECK(ctx);
+    }
     return MS_OK;
 }
 
@@ -706,12 +835,18 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
     const int sms = ctx->num_sms;
     nms_prepare_kernel<<<sms, 256, 0, st>>>(polys, scores, n, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags);
+    lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 0);
     MS_LAUNCH_CHECK(ctx);
     lanms_resolve_kernel<<<1, 1024, 0, st>>>(B.page_off, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_emit_kernel<<<1, 1024, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx);
+    lanms_kept_kernel<<<1, 1024, 0, st>>>(B.page_off, B, k_out);
     MS_LAUNCH_CHECK(ctx);
+    {
+        int gx = (n + kRankThreads - 1) / kRankThreads;
+        if (gx > 148) gx = 148;
+        lanms_emit_kernel<<<dim3(gx, 1), kRankThreads, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx);
+        MS_LAUNCH_CHECK(ctx);
+    }
     return MS_OK;
 }
 

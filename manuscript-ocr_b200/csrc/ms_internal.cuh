@@ -89,8 +89,8 @@ int msk_polygon_iou(ms_ctx *ctx, const double *subj, const double *clip, int64_t
 // boxes.cu
 int msk_expand(ms_ctx *ctx, const float *quads, int64_t n, double ew, double eh, float *out, cudaStream_t st);
 int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
-                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
-                   ms_bump bump, cudaStream_t st);
+                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int out_cap,
+                   int32_t *counts_out, int32_t *flags, ms_bump bump, cudaStream_t st);
 size_t msk_east_boxes_scratch(int n_pages, int cap_per_page);
 int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                    const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,

@@ -94,6 +94,9 @@ extern "C" int ms_create(int device, ms_ctx **out)
     c->device = device;
     c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : MS_NUM_SMS_B200;
     int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < 2 && rc == MS_OK; i++)
+        rc = ms_check_cuda(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming), "cudaEventCreate");
     if (rc == MS_OK) {
         c->pinned_bytes = 1 << 20;
         rc = ms_check_cuda(cudaMallocHost((void **)&c->pinned, c->pinned_bytes), "cudaMallocHost");
@@ -114,6 +117,12 @@ extern "C" void ms_destroy(ms_ctx *ctx)
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
     }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (int i = 0; i < 2; i++)
+        if (ctx->chunk_ev[i]) cudaEventDestroy(ctx->chunk_ev[i]);
     if (ctx->timing_ev) {
         for (int i = 0; i < MS_TIMING_RING * (MS_N_STAGES + 1); i++) cudaEventDestroy(ctx->timing_ev[i]);
         free(ctx->timing_ev);
@@ -301,7 +310,7 @@ extern "C" int ms_word_rects(ms_ctx *ctx, const float *quads, const int32_t *cou
     MS_TRY(ms_arena_reserve(ctx, word_rects_scratch_full(n_pages, cap_per_page)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     return msk_word_rects(ctx, quads, counts, n_pages, cap_per_page, img_hw, img_h, img_w, min_text_size, crops_out,
-                          crops_cap, n_crops, bump, (cudaStream_t)stream);
+                          crops_cap, n_crops, 0, 0, nullptr, bump, (cudaStream_t)stream);
 }
 
 extern "C" int ms_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w,
@@ -313,8 +322,10 @@ extern "C" int ms_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages
         ms_set_error("ms_crop_resize_pad: NULL pointer");
         return MS_ERR_INVALID;
     }
-    return msk_crop(ctx, pages, n_pages, img_h, img_w, crops, n_crops, crops_cap, out_h, out_w, batch_f32, canvas_u8,
-                    (cudaStream_t)stream);
+    MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(crops_cap)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_crop(ctx, pages, n_pages, img_h, img_w, crops, n_crops, nullptr, crops_cap, out_h, out_w, batch_f32,
+                    canvas_u8, bump, (cudaStream_t)stream);
 }
 
 // candidate capacity per page that can never overflow: one row per quantisation cell (utils.py:347-356)
@@ -325,7 +336,7 @@ static int cand_cap(int map_h, int map_w, int q)
     return (int)(c > 0x7fffffffLL ? 0x7fffffff : c);
 }
 
-static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c)
+static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap)
 {
     size_t fixed = 2 * al256((size_t)n_pages * cap_c * 9 * sizeof(float)) + 2 * al256((size_t)n_pages * sizeof(int32_t));
     size_t stage = msk_decode_scratch(n_pages, map_h, map_w, q);
@@ -335,7 +346,58 @@ static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int c
     if (s2 > stage) stage = s2;
     s2 = word_rects_scratch_full(n_pages, cap_c);
     if (s2 > stage) stage = s2;
+    s2 = msk_crop_scratch(crops_cap);
+    if (s2 > stage) stage = s2;
     return fixed + stage + 4096;
+}
+
+// One chunk of pages through the whole path.  `pages_all` / `total_pages` describe the page-image tensor the crop
+// rows index into; this call handles pages [page_base, page_base + n_pages) of it, whose maps start at score / geo
+// and whose boxes go to boxes_out / box_counts / flags (already offset by the caller).  append != 0 adds this
+// chunk's crops after the *n_crops rows already listed.
+static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages_all, int total_pages,
+                           int page_base, int n_pages, int map_h, int map_w, int img_h, int img_w,
+                           const ms_east_params *p, int min_text_size, int out_h, int out_w, int cap_boxes,
+                           float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
+                           int32_t *n_crops, int append, float *batch_f32, uint8_t *canvas_u8, int32_t *flags,
+                           cudaStream_t st)
+{
+    const bool want_crops = pages_all != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
+    const int q = p->quantization < 1 ? 1 : p->quantization;
+    const int cap_c = cand_cap(map_h, map_w, q);
+    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates
+    float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
+    int32_t *ca = bump.take<int32_t>(n_pages);
+    int32_t *cb = bump.take<int32_t>(n_pages);
+    int32_t *range = bump.take<int32_t>(2);
+    if (!range) {
+        ms_set_error("ms_page_batch: arena too small");
+        return MS_ERR_CAPACITY;
+    }
+    MS_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_pages * sizeof(int32_t), st));
+    MS_TRY(timing_mark(ctx, 0, st));
+    MS_TRY(msk_decode(ctx, score, geo, n_pages, map_h, map_w, p->score_thresh, p->scale, q, qa, cap_c, ca, flags, bump,
+                      st));
+    MS_TRY(timing_mark(ctx, 1, st));
+    MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
+    // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
+    MS_TRY(timing_mark(ctx, 2, st));
+    MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, boxes_out, cap_boxes, box_counts, flags, bump, st));
+    MS_TRY(timing_mark(ctx, 3, st));
+    if (want_crops) {
+        MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, nullptr, img_h, img_w, min_text_size,
+                              crops_out, crops_cap, n_crops, page_base, append, range, bump, st));
+        MS_TRY(timing_mark(ctx, 4, st));
+        if (batch_f32 || canvas_u8)
+            MS_TRY(msk_crop(ctx, pages_all, total_pages, img_h, img_w, crops_out, n_crops, range, crops_cap, out_h,
+                            out_w, batch_f32, canvas_u8, bump, st));
+    } else {
+        MS_TRY(timing_mark(ctx, 4, st));
+    }
+    MS_TRY(timing_mark(ctx, MS_N_STAGES, st));
+    return MS_OK;
 }
 
 extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
@@ -350,43 +412,9 @@ extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, 
         ms_set_error("ms_page_batch: bad arguments");
         return MS_ERR_INVALID;
     }
-    const bool want_crops = pages != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int q = p->quantization < 1 ? 1 : p->quantization;
-    const int cap_c = cand_cap(map_h, map_w, q);
-    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c)));
-    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
-    float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates, later the filtered boxes
-    float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
-    int32_t *ca = bump.take<int32_t>(n_pages);
-    int32_t *cb = bump.take<int32_t>(n_pages);
-    if (!cb) {
-        ms_set_error("ms_page_batch: arena too small");
-        return MS_ERR_CAPACITY;
-    }
-    MS_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_pages * sizeof(int32_t), st));
-    MS_TRY(timing_mark(ctx, 0, st));
-    MS_TRY(msk_decode(ctx, score, geo, n_pages, map_h, map_w, p->score_thresh, p->scale, q, qa, cap_c, ca, flags, bump,
-                      st));
-    MS_TRY(timing_mark(ctx, 1, st));
-    MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
-    // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
-    ms_east_params pp = *p;
-    MS_TRY(timing_mark(ctx, 2, st));
-    MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, &pp, nullptr, boxes_out, cap_boxes, box_counts, flags, bump, st));
-    MS_TRY(timing_mark(ctx, 3, st));
-    if (want_crops) {
-        MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, nullptr, img_h, img_w, min_text_size,
-                              crops_out, crops_cap, n_crops, bump, st));
-        MS_TRY(timing_mark(ctx, 4, st));
-        if (batch_f32 || canvas_u8)
-            MS_TRY(msk_crop(ctx, pages, n_pages, img_h, img_w, crops_out, n_crops, crops_cap, out_h, out_w, batch_f32,
-                            canvas_u8, st));
-    } else {
-        MS_TRY(timing_mark(ctx, 4, st));
-    }
-    MS_TRY(timing_mark(ctx, MS_N_STAGES, st));
-    return MS_OK;
+    return page_batch_impl(ctx, score, geo, pages, n_pages, 0, n_pages, map_h, map_w, img_h, img_w, p, min_text_size,
+                           out_h, out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, 0, batch_f32,
+                           canvas_u8, flags, (cudaStream_t)stream);
 }
 
 // =========================================================================================================
@@ -716,7 +744,9 @@ extern "C" int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img
         ms_rects_to_crops_kernel<<<grid, 256, 0, st>>>(d_rects, n, d_crops, d_n);
         MS_LAUNCH_CHECK(ctx);
     }
-    MS_TRY(msk_crop(ctx, d_page, 1, img_h, img_w, d_crops, d_n, n, out_h, out_w, d_f, d_u, st));
+    MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(n)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_crop(ctx, d_page, 1, img_h, img_w, d_crops, d_n, nullptr, n, out_h, out_w, d_f, d_u, bump, st));
     if (batch_f32) MS_CUDA(cudaMemcpyAsync(batch_f32, d_f, (size_t)n * one_f, cudaMemcpyDeviceToHost, st));
     if (canvas_u8) MS_CUDA(cudaMemcpyAsync(canvas_u8, d_u, (size_t)n * one_u, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
@@ -759,15 +789,33 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
         ms_set_error("ms_page_batch_host: staging too small");
         return MS_ERR_CAPACITY;
     }
-    cudaStream_t st = ctx->own_stream;
-    MS_CUDA(cudaMemcpyAsync(d_score, score, n_pages * plane * 4, cudaMemcpyHostToDevice, st));
-    MS_CUDA(cudaMemcpyAsync(d_geo, geo, n_pages * plane * 32, cudaMemcpyHostToDevice, st));
-    if (want_crops) {
-        MS_CUDA(cudaMemcpyAsync(d_pages, pages, n_pages * page_bytes, cudaMemcpyHostToDevice, st));
-        MS_CUDA(cudaMemsetAsync(d_nc, 0, sizeof(int32_t), st));
+    // Pipeline: pages are independent, so the batch is cut into chunks; the copy stream uploads chunk c+1 (maps +
+    // page images) while the compute stream runs chunk c.  PCIe is the floor of this entry point: 22 MB per
+    // 2048x2048 page against a few tens of microseconds of kernels.
+    cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream;
+    int chunk = (n_pages + 7) / 8;
+    if (chunk < 1) chunk = 1;
+    if (chunk > 8) chunk = 8;
+    if (want_crops) MS_CUDA(cudaMemsetAsync(d_nc, 0, sizeof(int32_t), st));
+    int k = 0;
+    for (int p0 = 0; p0 < n_pages; p0 += chunk, k++) {
+        const int np = n_pages - p0 < chunk ? n_pages - p0 : chunk;
+        cudaEvent_t ev = ctx->chunk_ev[k & 1];
+        // the event of chunk k-2 was consumed by the compute stream before chunk k-1 was queued; reuse is safe
+        MS_CUDA(cudaMemcpyAsync(d_score + (size_t)p0 * plane, score + (size_t)p0 * plane, np * plane * 4,
+                                cudaMemcpyHostToDevice, cs));
+        MS_CUDA(cudaMemcpyAsync(d_geo + (size_t)p0 * plane * 8, geo + (size_t)p0 * plane * 8, np * plane * 32,
+                                cudaMemcpyHostToDevice, cs));
+        if (want_crops)
+            MS_CUDA(cudaMemcpyAsync(d_pages + (size_t)p0 * page_bytes, pages + (size_t)p0 * page_bytes,
+                                    np * page_bytes, cudaMemcpyHostToDevice, cs));
+        MS_CUDA(cudaEventRecord(ev, cs));
+        MS_CUDA(cudaStreamWaitEvent(st, ev, 0));
+        MS_TRY(page_batch_impl(ctx, d_score + (size_t)p0 * plane, d_geo + (size_t)p0 * plane * 8, d_pages, n_pages, p0,
+                               np, map_h, map_w, img_h, img_w, p, min_text_size, out_h, out_w, cap_boxes,
+                               d_boxes + (size_t)p0 * cap_boxes * 9, d_cnt + p0, d_crops, crops_cap, d_nc, 1, d_batch,
+                               nullptr, d_flags + p0, st));
     }
-    MS_TRY(ms_page_batch(ctx, d_score, d_geo, d_pages, n_pages, map_h, map_w, img_h, img_w, p, min_text_size, out_h,
-                         out_w, cap_boxes, d_boxes, d_cnt, d_crops, crops_cap, d_nc, d_batch, nullptr, d_flags, st));
     MS_CUDA(cudaMemcpyAsync(box_counts, d_cnt, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaMemcpyAsync(flags, d_flags, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaMemcpyAsync(boxes_out, d_boxes, (size_t)n_pages * cap_boxes * 36, cudaMemcpyDeviceToHost, st));

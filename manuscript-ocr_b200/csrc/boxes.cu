@@ -578,23 +578,31 @@ __global__ void __launch_bounds__(256) word_rects_page_kernel(const float *__res
     if (threadIdx.x == 0) page_n[page] = run;
 }
 
+// append != 0: this call's crops go after the *n_crops rows already in the list (page chunks of one batch);
+// range[0..1] receives the [begin, end) rows this call produced (input of the crop kernels)
 __global__ void word_rects_offsets_kernel(const int32_t *__restrict__ page_n, int n_pages, int32_t *page_off,
-                                          int64_t crops_cap, int32_t *n_crops)
+                                          int64_t crops_cap, int32_t *n_crops, int append, int32_t *range)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
-        long long run = 0;
+        long long run = append ? *n_crops : 0;
+        const long long begin = run > crops_cap ? crops_cap : run;
         for (int p = 0; p < n_pages; p++) {
             page_off[p] = (int32_t)run;
             run += page_n[p];
         }
         page_off[n_pages] = (int32_t)run;
-        *n_crops = (int32_t)(run > crops_cap ? crops_cap : run);
+        const long long end = run > crops_cap ? crops_cap : run;
+        *n_crops = (int32_t)end;
+        if (range) {
+            range[0] = (int32_t)begin;
+            range[1] = (int32_t)end;
+        }
     }
 }
 
 __global__ void word_rects_pack_kernel(const int32_t *__restrict__ tmp, const int32_t *__restrict__ page_n,
                                        const int32_t *__restrict__ page_off, int n_pages, int cap, int64_t crops_cap,
-                                       int32_t *__restrict__ crops)
+                                       int page_base, int32_t *__restrict__ crops)
 {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p = (int)(g / cap), i = (int)(g % cap);
@@ -603,7 +611,7 @@ __global__ void word_rects_pack_kernel(const int32_t *__restrict__ tmp, const in
     if (dst >= crops_cap) return;
     const int32_t *s = tmp + ((size_t)p * cap + i) * 4;
     int32_t *d = crops + dst * 5;
-    d[0] = p; d[1] = s[0]; d[2] = s[1]; d[3] = s[2]; d[4] = s[3];
+    d[0] = page_base + p; d[1] = s[0]; d[2] = s[1]; d[3] = s[2]; d[4] = s[3];
 }
 
 void carve_east(ms_bump &bump, EastScratch &S, size_t n)
@@ -674,7 +682,8 @@ size_t msk_word_rects_scratch(int n_pages) { return (size_t)(2 * n_pages + 2) * 
 // NOTE: the page-strided temp list (n_pages*cap*4 int32) is taken from the bump as well.
 int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                    const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
-                   int64_t crops_cap, int32_t *n_crops, ms_bump bump, cudaStream_t st)
+                   int64_t crops_cap, int32_t *n_crops, int page_base, int append, int32_t *range, ms_bump bump,
+                   cudaStream_t st)
 {
     if (n_pages <= 0) return MS_OK;
     int32_t *page_n = bump.take<int32_t>(n_pages);
@@ -687,11 +696,11 @@ int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
     word_rects_page_kernel<<<n_pages, 256, 0, st>>>(quads, counts, cap_per_page, img_hw, img_h, img_w, min_text_size,
                                                     tmp, page_n);
     MS_LAUNCH_CHECK(ctx);
-    word_rects_offsets_kernel<<<1, 32, 0, st>>>(page_n, n_pages, page_off, crops_cap, n_crops);
+    word_rects_offsets_kernel<<<1, 32, 0, st>>>(page_n, n_pages, page_off, crops_cap, n_crops, append, range);
     MS_LAUNCH_CHECK(ctx);
     size_t threads = (size_t)n_pages * cap_per_page;
     word_rects_pack_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(tmp, page_n, page_off, n_pages, cap_per_page,
-                                                                         crops_cap, crops_out);
+                                                                         crops_cap, page_base, crops_out);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

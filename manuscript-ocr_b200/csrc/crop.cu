@@ -306,23 +306,55 @@ __device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, co
     }
 }
 
+// plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
+// critical path of the persistent resampling kernel
+__global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restrict__ pages, int n_pages, int img_h,
+                                                        int img_w, const int32_t *__restrict__ crops,
+                                                        const int32_t *__restrict__ n_crops_dev,
+                                                        const int32_t *__restrict__ range, int64_t crops_cap, int ih,
+                                                        int iw, Plan *__restrict__ plans)
+{
+    int64_t begin = range ? range[0] : 0;
+    int64_t n_crops = range ? range[1] : *n_crops_dev;
+    if (n_crops > crops_cap) n_crops = crops_cap;
+    const size_t total_bytes = (size_t)n_pages * img_h * (size_t)img_w * 3;
+    for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_crops;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        Plan p;
+        make_plan(crops + i * 5, n_pages, img_h, img_w, ih, iw, pages, total_bytes, p);
+        plans[i] = p;
+    }
+}
+
+__device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, AxisEnt *tab_y)
+{
+    if (!(p.ok && (p.interp == 1 || p.interp == 3))) return;
+    for (int t = threadIdx.x; t < p.nw + p.nh; t += kThreads) {
+        if (t < p.nw)
+            tab_x[t] = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
+        else
+            tab_y[t - p.nw] =
+                p.interp == 3 ? area_entry(t - p.nw, p.scale_y, p.h) : linear_entry_y(t - p.nw, p.scale_y, p.h);
+    }
+}
+
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, 3)
-    crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int n_pages, int img_h, int img_w,
-                           const int32_t *__restrict__ crops, const int32_t *__restrict__ n_crops_dev, int64_t crops_cap,
-                           int ih, int iw, float *__restrict__ batch, uint8_t *__restrict__ canvas_out, int vec_ok)
+    crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w, const Plan *__restrict__ plans,
+                           const int32_t *__restrict__ n_crops_dev, const int32_t *__restrict__ range,
+                           int64_t crops_cap, int ih, int iw, float *__restrict__ batch,
+                           uint8_t *__restrict__ canvas_out, int vec_ok)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     unsigned char *src_buf[2] = {smem, smem + kSrcBuf};
-    AxisEnt *tab_x = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);
-    AxisEnt *tab_y = tab_x + iw;
+    AxisEnt *tabs = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);  // [2][iw + ih]
+    const int tab_n = iw + ih;
     __shared__ __align__(8) uint64_t s_bar[2];
-    __shared__ Plan s_plan[2];
 
-    int64_t n_crops = *n_crops_dev;
+    const int64_t begin = range ? range[0] : 0;
+    int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
     const size_t stride = (size_t)img_w * 3;
-    const size_t total_bytes = (size_t)n_pages * img_h * stride;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
@@ -332,38 +364,22 @@ __global__ void __launch_bounds__(kThreads, 3)
         mbar_init(&s_bar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // prologue: plan + stage this CTA's first crop
-    if (warp == 0 && (int64_t)blockIdx.x < n_crops) {
-        if (lane == 0)
-            make_plan(crops + (int64_t)blockIdx.x * 5, n_pages, img_h, img_w, ih, iw, pages, total_bytes, s_plan[0]);
-    }
     __syncthreads();
-    if (warp == 0 && (int64_t)blockIdx.x < n_crops && s_plan[0].staged)
-        stage_rows(s_plan[0], pages, img_h, img_w, src_buf[0], &s_bar[0], lane);
+    if (begin + (int64_t)blockIdx.x >= n_crops) return;
+    // prologue: tables + staged rows of this CTA's first crop
+    Plan p = plans[begin + blockIdx.x];
+    build_tables(p, tabs, tabs + iw);
+    if (warp == 0 && p.staged) stage_rows(p, pages, img_h, img_w, src_buf[0], &s_bar[0], lane);
+    __syncthreads();
 
     uint32_t phase0 = 0, phase1 = 0;
     int it = 0;
-    for (int64_t ci = blockIdx.x; ci < n_crops; ci += gridDim.x, it++) {
+    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x, it++) {
         const int cur = it & 1, nxt = cur ^ 1;
-        // producer: plan + stage the next crop into the other buffer (free since the trailing barrier of
-        // the previous iteration)
         const int64_t cn = ci + gridDim.x;
-        if (warp == 0 && cn < n_crops) {
-            if (lane == 0) make_plan(crops + cn * 5, n_pages, img_h, img_w, ih, iw, pages, total_bytes, s_plan[nxt]);
-            __syncwarp();
-            if (s_plan[nxt].staged) stage_rows(s_plan[nxt], pages, img_h, img_w, src_buf[nxt], &s_bar[nxt], lane);
-        }
-        const Plan p = s_plan[cur];
-        // axis tables of the current crop
-        if (p.ok && (p.interp == 1 || p.interp == 3)) {
-            for (int t = threadIdx.x; t < p.nw + p.nh; t += kThreads) {
-                if (t < p.nw)
-                    tab_x[t] = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
-                else
-                    tab_y[t - p.nw] = p.interp == 3 ? area_entry(t - p.nw, p.scale_y, p.h)
-                                                   : linear_entry_y(t - p.nw, p.scale_y, p.h);
-            }
-        }
+        const bool has_next = cn < n_crops;
+        Plan pn;
+        if (has_next) pn = plans[cn];  // issued early; consumed after the padding stores below
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
         const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
@@ -375,21 +391,23 @@ __global__ void __launch_bounds__(kThreads, 3)
                 const float4 one4 = make_float4(one, one, one, one);
                 const int nw4 = (nw + 3) & ~3;
                 const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
+                const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
+#pragma unroll
                 for (int c = 0; c < 3; c++) {
                     float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
                     for (int i = threadIdx.x; i < top4; i += kThreads) __stcs(base4 + i, one4);
                     float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
                     for (int i = threadIdx.x; i < bot4; i += kThreads) __stcs(bot + i, one4);
                     if (tail4 > 0) {
+                        const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
                         for (int i = threadIdx.x; i < nh * tail4; i += kThreads) {
-                            int r = i / tail4, k = i - r * tail4;
+                            const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
                             __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
                                    one4);
                         }
                     }
-                    const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
                     for (int i = threadIdx.x; i < nh * fr; i += kThreads) {
-                        int r = i / fr, k = i - r * fr;
+                        const int r = i / fr, k = i - r * fr;
                         __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
                     }
                 }
@@ -411,7 +429,14 @@ __global__ void __launch_bounds__(kThreads, 3)
                 }
             }
         }
-        __syncthreads();  // tables visible
+
+        // producer side for the NEXT crop: TMA row copies into the other buffer + its axis tables (both were
+        // released by the trailing barrier of the previous iteration)
+        if (has_next) {
+            if (warp == 0 && pn.staged) stage_rows(pn, pages, img_h, img_w, src_buf[nxt], &s_bar[nxt], lane);
+            build_tables(pn, tabs + (size_t)nxt * tab_n, tabs + (size_t)nxt * tab_n + iw);
+        }
+
         if (p.ok) {
             if (p.staged) {
                 if (cur == 0) {
@@ -422,6 +447,7 @@ __global__ void __launch_bounds__(kThreads, 3)
                     phase1 ^= 1;
                 }
             }
+            const AxisEnt *tab_x = tabs + (size_t)cur * tab_n, *tab_y = tab_x + iw;
             const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
             const unsigned char *sbuf = src_buf[cur];
             const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 15);
@@ -453,15 +479,18 @@ __global__ void __launch_bounds__(kThreads, 3)
                 }
             }
         }
-        __syncthreads();  // buffer `cur`, the tables and s_plan[cur] are free again
+        __syncthreads();  // buffer `cur` and its tables are free; the next crop's tables are visible
+        p = pn;
     }
 }
 
 }  // namespace
 
+size_t msk_crop_scratch(int64_t crops_cap) { return (size_t)(crops_cap > 0 ? crops_cap : 0) * sizeof(Plan) + 1024; }
+
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
-             const int32_t *n_crops, int64_t crops_cap, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8,
-             cudaStream_t st)
+             const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
+             uint8_t *canvas_u8, ms_bump bump, cudaStream_t st)
 {
     if (crops_cap <= 0 || n_pages <= 0) return MS_OK;
     if (out_h <= 0 || out_w <= 0 || img_h <= 0 || img_w <= 0 || (!batch_f32 && !canvas_u8)) {
@@ -472,10 +501,22 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
         ms_set_error("crop: canvas %dx%d too large", out_h, out_w);
         return MS_ERR_INVALID;
     }
-    const size_t smem = 2 * (size_t)kSrcBuf + (size_t)(out_h + out_w) * sizeof(AxisEnt);
+    const size_t smem = 2 * (size_t)kSrcBuf + 2 * (size_t)(out_h + out_w) * sizeof(AxisEnt);
     if (smem > 220 * 1024) {
         ms_set_error("crop: canvas %dx%d needs %zu bytes of shared memory", out_h, out_w, smem);
         return MS_ERR_INVALID;
+    }
+    Plan *plans = bump.take<Plan>((size_t)crops_cap);
+    if (!plans) {
+        ms_set_error("crop: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    {
+        int64_t g = (crops_cap + 255) / 256;
+        if (g > (int64_t)ctx->num_sms * 8) g = (int64_t)ctx->num_sms * 8;
+        crop_plan_kernel<<<(int)g, 256, 0, st>>>(pages, n_pages, img_h, img_w, crops, n_crops, range, crops_cap, out_h,
+                                                 out_w, plans);
+        MS_LAUNCH_CHECK(ctx);
     }
     int per_sm = (int)((220 * 1024) / (smem + 1024));
     if (per_sm > 3) per_sm = 3;
@@ -487,7 +528,7 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     do {                                                                                                               \
         auto kfn = crop_resize_pad_kernel<F32, U8>;                                                                    \
         MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
-        kfn<<<(int)grid, kThreads, smem, st>>>(pages, n_pages, img_h, img_w, crops, n_crops, crops_cap, out_h, out_w,  \
+        kfn<<<(int)grid, kThreads, smem, st>>>(pages, img_h, img_w, plans, n_crops, range, crops_cap, out_h, out_w,    \
                                               batch_f32, canvas_u8, vec_ok);                                           \
     } while (0)
     if (batch_f32 && canvas_u8)

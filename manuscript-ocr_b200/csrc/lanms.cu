@@ -64,6 +64,9 @@ struct LanmsBuffers {
     uint8_t *state;      // 0 undecided / 1 kept / 2 suppressed
     uint8_t *blocked;
     int32_t *kept_list;
+    int32_t *irr_list;   // packed slots of the irregular clusters (all pages)
+    int32_t *irr_count;
+    uint64_t *kept_key;  // per kept entry: descending-score sort key
 };
 
 // ---- helpers ------------------------------------------------------------------------------------
@@ -131,7 +134,7 @@ __device__ __forceinline__ bool quad_regular_bbox(const double *p, float4 &bb)
 
 // ---- 0. page offsets ---------------------------------------------------------------------------------
 __global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_pages, int32_t *page_off,
-                                     int32_t *n_total, int32_t *hot_count, int32_t *edge_count)
+                                     int32_t *n_total, int32_t *hot_count, int32_t *edge_count, int32_t *irr_count)
 {
     // one thread: n_pages is small (<= a few thousand)
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -144,6 +147,7 @@ __global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_p
         page_off[n_pages] = run;
         *n_total = run;
         *hot_count = 0;
+        *irr_count = 0;
     }
 }
 
@@ -348,6 +352,7 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
             if (!reg) bb = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
             B.cl_bbox[slot] = bb;
             B.cl_irr[slot] = reg ? 0 : 1;
+            if (!reg) B.irr_list[atomicAdd(B.irr_count, 1)] = (int)slot;
             B.cl_orig[slot] = c;
             B.state[slot] = 0;
             if (reg) slack = fmaxf(slack, key - bb.x);
@@ -409,15 +414,16 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
     int qn = 0;  // warp-uniform
     double buf[4 * MS_MAXV];
     const int wid = blockIdx.x * kPairWarps + warp, nw = gridDim.x * kPairWarps;
+    const int n_items = irregular_only ? *B.irr_count : n;
 
-    for (int slot = wid; slot < n; slot += nw) {
+    for (int item = wid; item < n_items; item += nw) {
+        const int slot = irregular_only ? B.irr_list[item] : item;
         const int page = B.pos_page[slot];
         const int p0 = page_off[page];
         const int a = slot - p0;
         const int C = B.cl_count[page];
         if (a >= C) continue;
         const bool a_irr = B.cl_irr[slot] != 0;
-        if (irregular_only && !a_irr) continue;
         const float4 ba = B.cl_bbox[slot];
         const float limit = ba.z + B.page_slack[page];
         // regular a: forward sweep; irregular a: every other box of the page (pairs of two irregular
@@ -598,6 +604,16 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
     }
 }
 
+// position key of np.argsort(-scores, kind="stable"): ascending key == larger score first, NaN last, -0 == +0
+__device__ __forceinline__ uint64_t desc_score_key(double sc)
+{
+    if (sc != sc) return ~0ull;
+    if (sc == 0.0) sc = 0.0;
+    uint64_t u = (uint64_t)__double_as_longlong(sc);
+    u = (u >> 63) ? ~u : (u | 0x8000000000000000ull);  // ascending image
+    return ~u;
+}
+
 // ---- 7. kept clusters -> rows in stable descending-score order ----------------------------------------------------
 __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B,
                                                           int32_t *__restrict__ counts_out)
@@ -613,7 +629,10 @@ __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restr
         int k = (c < C && B.state[p0 + c] == 1) ? 1 : 0;
         int total;
         int pos = block_excl_scan_1024(k, s_warp, total);
-        if (k) kept[run_base + pos] = c;
+        if (k) {
+            kept[run_base + pos] = c;
+            B.kept_key[p0 + run_base + pos] = desc_score_key(B.cl_score[p0 + c]);
+        }
         run_base += total;
     }
     if (threadIdx.x == 0) counts_out[page] = run_base;
@@ -631,16 +650,17 @@ __global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t 
     const int p0 = page_off[page];
     const int K = counts_out[page];
     const int32_t *kept = B.kept_list + p0;
-    __shared__ double s_sc[kRankThreads];
+    __shared__ uint64_t s_key[kRankThreads];
     __shared__ int s_oc[kRankThreads];
+    const uint64_t *kkey = B.kept_key + p0;
     for (int base = blockIdx.x * kRankThreads; base < K; base += gridDim.x * kRankThreads) {
         const int i = base + threadIdx.x;
         const bool live = i < K;
         int c = 0, oc = 0;
-        double sc = 0.0;
+        uint64_t key = 0;
         if (live) {
             c = kept[i];
-            sc = B.cl_score[p0 + c];
+            key = kkey[i];
             oc = B.cl_orig[p0 + c];
         }
         int rank = 0;
@@ -648,15 +668,16 @@ __global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t 
             __syncthreads();
             const int j = tb + threadIdx.x;
             if (j < K) {
-                const int c2 = kept[j];
-                s_sc[threadIdx.x] = B.cl_score[p0 + c2];
-                s_oc[threadIdx.x] = B.cl_orig[p0 + c2];
+                s_key[threadIdx.x] = kkey[j];
+                s_oc[threadIdx.x] = B.cl_orig[p0 + kept[j]];
             }
             __syncthreads();
             const int nb = min(kRankThreads, K - tb);
             if (live)
-                for (int t = 0; t < nb; t++)
-                    rank += (s_oc[t] != oc && prio_before(s_sc[t], s_oc[t], sc, oc)) ? 1 : 0;
+                for (int t = 0; t < nb; t++) {
+                    const uint64_t k2 = s_key[t];
+                    rank += (k2 < key || (k2 == key && s_oc[t] < oc)) ? 1 : 0;
+                }
         }
         if (live) {
             if (out) {
@@ -664,7 +685,7 @@ __global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t 
                 const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
 #pragma unroll
                 for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
-                row[8] = (float)sc;
+                row[8] = (float)B.cl_score[p0 + c];
             }
             if (keep_idx_out) keep_idx_out[(size_t)page * cap + rank] = oc;
         }
@@ -742,6 +763,9 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     B.edges = bump.take<uint64_t>(n_max * kEdgeFactor);
     B.state = bump.take<uint8_t>(n_max);
     B.blocked = bump.take<uint8_t>(n_max);
+    B.irr_list = bump.take<int32_t>(n_max);
+    B.irr_count = bump.take<int32_t>(1);
+    B.kept_key = bump.take<uint64_t>(n_max);
     B.kept_list = bump.take<int32_t>(n_max);
     return bump.off;
 }
@@ -780,7 +804,8 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         return MS_ERR_CAPACITY;
     }
     const int sms = ctx->num_sms;
-    lanms_offsets_kernel<<<1, 32, 0, st>>>(counts, n_pages, B.page_off, B.n_total, B.hot_count, B.edge_count);
+    lanms_offsets_kernel<<<1, 32, 0, st>>>(counts, n_pages, B.page_off, B.n_total, B.hot_count, B.edge_count,
+                                           B.irr_count);
     MS_LAUNCH_CHECK(ctx);
     {
         size_t threads = n_max;

@@ -23,6 +23,8 @@ struct ms_ctx {
     char *stage;
     size_t stage_bytes;
     // ms_stage_timing: ring of per-batch event sets
+    cudaStream_t copy_stream;     // H2D stream of the pipelined host entry point
+    cudaEvent_t chunk_ev[2];
     int timing;
     int timing_n;                 // batches recorded since the last read (<= MS_TIMING_RING)
     cudaEvent_t *timing_ev;       // MS_TIMING_RING * (MS_N_STAGES + 1) events, created lazily
@@ -94,14 +96,16 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
 size_t msk_east_boxes_scratch(int n_pages, int cap_per_page);
 int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                    const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
-                   int64_t crops_cap, int32_t *n_crops, ms_bump bump, cudaStream_t st);
+                   int64_t crops_cap, int32_t *n_crops, int page_base, int append, int32_t *range, ms_bump bump,
+                   cudaStream_t st);
 size_t msk_word_rects_scratch(int n_pages);
 int msk_word_rects_flat(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w, int min_text_size,
                         int32_t *rects, uint8_t *valid, cudaStream_t st);
 // crop.cu
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
-             const int32_t *n_crops, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
-             uint8_t *canvas_u8, cudaStream_t st);
+             const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
+             uint8_t *canvas_u8, ms_bump bump, cudaStream_t st);
+size_t msk_crop_scratch(int64_t crops_cap);
 
 // ---- device geometry: lanms.py:7-130 in float64, no fused multiply-add ------------------------------
 #define MS_MAXV 20  // lanms.py:34

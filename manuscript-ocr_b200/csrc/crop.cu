@@ -29,7 +29,7 @@
 namespace {
 
 constexpr int kThreads = 256;
-constexpr int kSrcBuf = 32 * 1024;  // bytes per staging buffer (two per CTA)
+constexpr int kSrcBuf = 24 * 1024;  // bytes per staging buffer (two per CTA)
 
 struct Plan {
     int page, x1, y1, w, h;
@@ -94,7 +94,7 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
         p.interp = fast ? 2 : 3;
     }
     // staging: every row is copied as the 16-byte-aligned span that covers it
-    const int pitch = ((w * 3 + 15 + 15) & ~15);
+    const int pitch = ((w * 3 + 15 + 16 + 15) & ~15);  // span + 16 bytes the 4-tap fast path may over-read
     const size_t stride = (size_t)img_w * 3;
     const size_t first = (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
     const size_t last_end = first + (size_t)(h - 1) * stride + (size_t)w * 3;
@@ -306,6 +306,62 @@ __device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, co
     }
 }
 
+// u8 -> f32 without the conversion pipe: byte k of `v` is spliced under the exponent of 2^23, then 2^23 is
+// subtracted (exact for 0..255)
+__device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
+{
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+// INTER_AREA general path for one destination pixel when the horizontal table has <= 4 taps and the source
+// rows are staged: each row contributes 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit
+// shared-memory words; taps beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).
+// Same products and the same summation order as resample_px's general branch.
+__device__ __forceinline__ void resample_area4(const unsigned char *smem_base, uint32_t buf_off, int pitch, uint32_t a0,
+                                               uint32_t sstep, const AxisEnt &ex, const AxisEnt &ey, unsigned char &o0,
+                                               unsigned char &o1, unsigned char &o2)
+{
+    const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
+    float w[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) w[e] = e < ex.n ? area_weight(ex, e) : 0.f;
+    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
+    for (int j = 0; j < ey.n; j++) {
+        const float beta = area_weight(ey, j);
+        const uint32_t sy = (uint32_t)(ey.s0 + j);
+        const uint32_t o = buf_off + sy * (uint32_t)pitch + ((a0 + sy * sstep) & 15u) + (uint32_t)ex.s0 * 3u;
+        const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
+        const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
+        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
+                       v2 = __funnelshift_r(w2, w3, sh);
+        // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
+        float b0 = byte_f32(v0, 0x7650) * w[0];
+        float b1 = byte_f32(v0, 0x7651) * w[0];
+        float b2 = byte_f32(v0, 0x7652) * w[0];
+        b0 = b0 + byte_f32(v0, 0x7653) * w[1];
+        b1 = b1 + byte_f32(v1, 0x7650) * w[1];
+        b2 = b2 + byte_f32(v1, 0x7651) * w[1];
+        b0 = b0 + byte_f32(v1, 0x7652) * w[2];
+        b1 = b1 + byte_f32(v1, 0x7653) * w[2];
+        b2 = b2 + byte_f32(v2, 0x7650) * w[2];
+        b0 = b0 + byte_f32(v2, 0x7651) * w[3];
+        b1 = b1 + byte_f32(v2, 0x7652) * w[3];
+        b2 = b2 + byte_f32(v2, 0x7653) * w[3];
+        if (j == 0) {
+            sum0 = beta * b0;
+            sum1 = beta * b1;
+            sum2 = beta * b2;
+        } else {
+            sum0 += beta * b0;
+            sum1 += beta * b1;
+            sum2 += beta * b2;
+        }
+    }
+    o0 = sat_u8(cv_round(sum0));
+    o1 = sat_u8(cv_round(sum1));
+    o2 = sat_u8(cv_round(sum2));
+}
+
 // plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
 // critical path of the persistent resampling kernel
 __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restrict__ pages, int n_pages, int img_h,
@@ -346,7 +402,6 @@ __global__ void __launch_bounds__(kThreads, 3)
                            uint8_t *__restrict__ canvas_out, int vec_ok)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    unsigned char *src_buf[2] = {smem, smem + kSrcBuf};
     AxisEnt *tabs = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);  // [2][iw + ih]
     const int tab_n = iw + ih;
     __shared__ __align__(8) uint64_t s_bar[2];
@@ -369,7 +424,7 @@ __global__ void __launch_bounds__(kThreads, 3)
     // prologue: tables + staged rows of this CTA's first crop
     Plan p = plans[begin + blockIdx.x];
     build_tables(p, tabs, tabs + iw);
-    if (warp == 0 && p.staged) stage_rows(p, pages, img_h, img_w, src_buf[0], &s_bar[0], lane);
+    if (warp == 0 && p.staged) stage_rows(p, pages, img_h, img_w, smem, &s_bar[0], lane);
     __syncthreads();
 
     uint32_t phase0 = 0, phase1 = 0;
@@ -433,7 +488,7 @@ __global__ void __launch_bounds__(kThreads, 3)
         // producer side for the NEXT crop: TMA row copies into the other buffer + its axis tables (both were
         // released by the trailing barrier of the previous iteration)
         if (has_next) {
-            if (warp == 0 && pn.staged) stage_rows(pn, pages, img_h, img_w, src_buf[nxt], &s_bar[nxt], lane);
+            if (warp == 0 && pn.staged) stage_rows(pn, pages, img_h, img_w, smem + nxt * kSrcBuf, &s_bar[nxt], lane);
             build_tables(pn, tabs + (size_t)nxt * tab_n, tabs + (size_t)nxt * tab_n + iw);
         }
 
@@ -449,7 +504,7 @@ __global__ void __launch_bounds__(kThreads, 3)
             }
             const AxisEnt *tab_x = tabs + (size_t)cur * tab_n, *tab_y = tab_x + iw;
             const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-            const unsigned char *sbuf = src_buf[cur];
+            const unsigned char *sbuf = smem + cur * kSrcBuf;
             const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 15);
             const uint32_t sstep = (uint32_t)(stride & 15);  // per-row change of the 16-byte misalignment
             const int npx = nw * nh;
@@ -457,7 +512,9 @@ __global__ void __launch_bounds__(kThreads, 3)
             for (int t = threadIdx.x; t < npx; t += kThreads) {
                 const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
                 unsigned char o0, o1, o2;
-                if (p.staged) {
+                if (p.staged && p.interp == 3 && tab_x[dx].n <= 4) {
+                    resample_area4(smem, (uint32_t)(cur * kSrcBuf), p.pitch, a0, sstep, tab_x[dx], tab_y[dy], o0, o1, o2);
+                } else if (p.staged) {
                     auto row = [&](int sy) -> const unsigned char * {
                         return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
                     };

@@ -207,25 +207,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-// warp 0: issue the row copies of one crop into `buf`
-__device__ __forceinline__ void stage_rows(const Plan &p, const uint8_t *pages, int img_h, int img_w, unsigned char *buf,
-                                           uint64_t *bar, int lane)
-{
-    const size_t stride = (size_t)img_w * 3;
-    const uint8_t *src = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-    uint32_t bytes = 0;
-    for (int r = lane; r < p.h; r += 32) {
-        const uint8_t *g = src + (size_t)r * stride;
-        const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
-        const uint32_t sz = (a + (uint32_t)p.w * 3 + 15) & ~15u;
-        tma_bulk_g2s(buf + (size_t)r * p.pitch, g - a, sz, bar);
-        bytes += sz;
-    }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
-    if (lane == 0) mbar_expect_tx(bar, bytes);
-}
-
 // resample one destination pixel (3 channels); `row(sy)` gives the address of source pixel (x=0) of row sy
 template <typename RowFn>
 __device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, const AxisEnt *ty, int dx, int dy,
@@ -382,10 +363,11 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
     }
 }
 
-__device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, AxisEnt *tab_y)
+// producer warp: the coefficient tables of one crop, 32 lanes
+__device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, AxisEnt *tab_y, int lane)
 {
     if (!(p.ok && (p.interp == 1 || p.interp == 3))) return;
-    for (int t = threadIdx.x; t < p.nw + p.nh; t += kThreads) {
+    for (int t = lane; t < p.nw + p.nh; t += 32) {
         if (t < p.nw)
             tab_x[t] = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
         else
@@ -393,6 +375,72 @@ __device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, Axis
                 p.interp == 3 ? area_entry(t - p.nw, p.scale_y, p.h) : linear_entry_y(t - p.nw, p.scale_y, p.h);
     }
 }
+
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// producer warp: everything outside the pasted rectangle is the 255 canvas (transforms.py:100), 1.0f after
+// normalisation; written as constant 16-byte streaming stores
+template <bool kWriteF32, bool kWriteU8>
+__device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, float *dstf, uint8_t *dstu, int vec_ok,
+                                              int lane)
+{
+    const int plane = ih * iw;
+    const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
+    if (kWriteF32) {
+        const float one = (255.0f - 127.5f) * (1.0f / 127.5f);
+        if (vec_ok) {
+            const float4 one4 = make_float4(one, one, one, one);
+            const int nw4 = (nw + 3) & ~3;
+            const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
+            const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
+                for (int i = lane; i < top4; i += 32) __stcs(base4 + i, one4);
+                float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
+                for (int i = lane; i < bot4; i += 32) __stcs(bot + i, one4);
+                if (tail4 > 0) {
+                    const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
+                    for (int i = lane; i < nh * tail4; i += 32) {
+                        const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
+                        __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
+                               one4);
+                    }
+                }
+                for (int i = lane; i < nh * fr; i += 32) {
+                    const int r = i / fr, k = i - r * fr;
+                    __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
+                }
+            }
+        } else {
+            for (int e = lane; e < 3 * plane; e += 32) {
+                int c = e / plane, rem = e - c * plane;
+                int y = rem / iw, x = rem - y * iw;
+                if (!(y >= y0 && y < y0 + nh && x < nw)) dstf[e] = one;
+            }
+        }
+    }
+    if (kWriteU8) {
+        for (int e = lane; e < plane; e += 32) {
+            int y = e / iw, x = e - y * iw;
+            if (!(y >= y0 && y < y0 + nh && x < nw)) {
+                dstu[(size_t)e * 3] = 255;
+                dstu[(size_t)e * 3 + 1] = 255;
+                dstu[(size_t)e * 3 + 2] = 255;
+            }
+        }
+    }
+}
+
+// Warp-specialised persistent kernel.  Warp 0 (producer) walks this CTA's crops one ahead of the consumers: it
+// writes the crop's padding, waits until the stage buffer is released, copies the plan, issues the TMA row
+// copies, builds the axis tables and signals full[b].  Warps 1..7 (consumers) wait on full[b], resample the
+// pasted rectangle straight into the CHW batch and release the buffer on empty[b].  No CTA-wide barrier inside
+// the loop: consumer warps drift apart by up to one crop, which absorbs the uneven per-pixel tap counts.
+constexpr int kConsumerWarps = kThreads / 32 - 1;
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, 3)
@@ -404,7 +452,8 @@ __global__ void __launch_bounds__(kThreads, 3)
     extern __shared__ __align__(128) unsigned char smem[];
     AxisEnt *tabs = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);  // [2][iw + ih]
     const int tab_n = iw + ih;
-    __shared__ __align__(8) uint64_t s_bar[2];
+    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    __shared__ Plan s_plan[2];
 
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -415,105 +464,74 @@ __global__ void __launch_bounds__(kThreads, 3)
     const float inv = 1.0f / 127.5f;
 
     if (threadIdx.x == 0) {
-        mbar_init(&s_bar[0], 1);
-        mbar_init(&s_bar[1], 1);
+        mbar_init(&s_full[0], 1);
+        mbar_init(&s_full[1], 1);
+        mbar_init(&s_empty[0], kConsumerWarps);
+        mbar_init(&s_empty[1], kConsumerWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (begin + (int64_t)blockIdx.x >= n_crops) return;
-    // prologue: tables + staged rows of this CTA's first crop
-    Plan p = plans[begin + blockIdx.x];
-    build_tables(p, tabs, tabs + iw);
-    if (warp == 0 && p.staged) stage_rows(p, pages, img_h, img_w, smem, &s_bar[0], lane);
-    __syncthreads();
 
-    uint32_t phase0 = 0, phase1 = 0;
-    int it = 0;
-    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x, it++) {
-        const int cur = it & 1, nxt = cur ^ 1;
-        const int64_t cn = ci + gridDim.x;
-        const bool has_next = cn < n_crops;
-        Plan pn;
-        if (has_next) pn = plans[cn];  // issued early; consumed after the padding stores below
-        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
-        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
-        const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
-
-        // 255 padding (transforms.py:100) -> 1.0f after normalisation; everything outside the pasted rectangle
-        if (kWriteF32) {
-            const float one = (255.0f - 127.5f) * inv;
-            if (vec_ok) {
-                const float4 one4 = make_float4(one, one, one, one);
-                const int nw4 = (nw + 3) & ~3;
-                const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
-                const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
-#pragma unroll
-                for (int c = 0; c < 3; c++) {
-                    float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
-                    for (int i = threadIdx.x; i < top4; i += kThreads) __stcs(base4 + i, one4);
-                    float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
-                    for (int i = threadIdx.x; i < bot4; i += kThreads) __stcs(bot + i, one4);
-                    if (tail4 > 0) {
-                        const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
-                        for (int i = threadIdx.x; i < nh * tail4; i += kThreads) {
-                            const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
-                            __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
-                                   one4);
-                        }
-                    }
-                    for (int i = threadIdx.x; i < nh * fr; i += kThreads) {
-                        const int r = i / fr, k = i - r * fr;
-                        __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
-                    }
-                }
-            } else {
-                for (int e = threadIdx.x; e < 3 * plane; e += kThreads) {
-                    int c = e / plane, rem = e - c * plane;
-                    int y = rem / iw, x = rem - y * iw;
-                    if (!(y >= y0 && y < y0 + nh && x < nw)) dstf[e] = one;
-                }
-            }
-        }
-        if (kWriteU8) {
-            for (int e = threadIdx.x; e < plane; e += kThreads) {
-                int y = e / iw, x = e - y * iw;
-                if (!(y >= y0 && y < y0 + nh && x < nw)) {
-                    dstu[(size_t)e * 3] = 255;
-                    dstu[(size_t)e * 3 + 1] = 255;
-                    dstu[(size_t)e * 3 + 2] = 255;
-                }
-            }
-        }
-
-        // producer side for the NEXT crop: TMA row copies into the other buffer + its axis tables (both were
-        // released by the trailing barrier of the previous iteration)
-        if (has_next) {
-            if (warp == 0 && pn.staged) stage_rows(pn, pages, img_h, img_w, smem + nxt * kSrcBuf, &s_bar[nxt], lane);
-            build_tables(pn, tabs + (size_t)nxt * tab_n, tabs + (size_t)nxt * tab_n + iw);
-        }
-
-        if (p.ok) {
+    if (warp == 0) {
+        // ---------------- producer ----------------
+        int k = 0;
+        for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x, k++) {
+            const int b = k & 1;
+            const Plan p = plans[ci];
+            write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
+                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane);
+            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
+            if (lane == 0) s_plan[b] = p;
+            build_tables(p, tabs + (size_t)b * tab_n, tabs + (size_t)b * tab_n + iw, lane);
+            uint32_t bytes = 0;
             if (p.staged) {
-                if (cur == 0) {
-                    mbar_wait(&s_bar[0], phase0);
-                    phase0 ^= 1;
-                } else {
-                    mbar_wait(&s_bar[1], phase1);
-                    phase1 ^= 1;
+                const uint8_t *src = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+                unsigned char *buf = smem + b * kSrcBuf;
+                for (int r = lane; r < p.h; r += 32) {
+                    const uint8_t *g = src + (size_t)r * stride;
+                    const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
+                    const uint32_t sz = (a + (uint32_t)p.w * 3 + 15) & ~15u;
+                    tma_bulk_g2s(buf + (size_t)r * p.pitch, g - a, sz, &s_full[b]);
+                    bytes += sz;
                 }
+#pragma unroll
+                for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
             }
-            const AxisEnt *tab_x = tabs + (size_t)cur * tab_n, *tab_y = tab_x + iw;
+            __syncwarp();  // every lane's plan / table stores are ordered before lane 0's releasing arrive
+            if (lane == 0) {
+                if (bytes)
+                    mbar_expect_tx(&s_full[b], bytes);
+                else
+                    mbar_arrive(&s_full[b]);
+            }
+        }
+        return;
+    }
+
+    // ---------------- consumers ----------------
+    const int ct = (warp - 1) * 32 + lane;
+    constexpr int kCT = kConsumerWarps * 32;
+    int k = 0;
+    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x, k++) {
+        const int b = k & 1;
+        mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
+        const Plan p = s_plan[b];
+        if (p.ok) {
+            float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+            uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+            const int nw = p.nw, nh = p.nh, y0 = p.y0;
+            const AxisEnt *tab_x = tabs + (size_t)b * tab_n, *tab_y = tab_x + iw;
             const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-            const unsigned char *sbuf = smem + cur * kSrcBuf;
+            const unsigned char *sbuf = smem + b * kSrcBuf;
             const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 15);
             const uint32_t sstep = (uint32_t)(stride & 15);  // per-row change of the 16-byte misalignment
             const int npx = nw * nh;
             const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
-            for (int t = threadIdx.x; t < npx; t += kThreads) {
+            for (int t = ct; t < npx; t += kCT) {
                 const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
                 unsigned char o0, o1, o2;
                 if (p.staged && p.interp == 3 && tab_x[dx].n <= 4) {
-                    resample_area4(smem, (uint32_t)(cur * kSrcBuf), p.pitch, a0, sstep, tab_x[dx], tab_y[dy], o0, o1, o2);
+                    resample_area4(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, tab_x[dx], tab_y[dy], o0, o1, o2);
                 } else if (p.staged) {
                     auto row = [&](int sy) -> const unsigned char * {
                         return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
@@ -536,8 +554,8 @@ __global__ void __launch_bounds__(kThreads, 3)
                 }
             }
         }
-        __syncthreads();  // buffer `cur` and its tables are free; the next crop's tables are visible
-        p = pn;
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_empty[b]);
     }
 }
 

@@ -26,5 +26,14 @@ from .ops import (  # noqa: F401
     word_rects,
 )
 from .batch import PageBatch, PageBatchResult, shard_pages  # noqa: F401
+from .east import EAST, read_image  # noqa: F401
+from .pipeline import Pipeline  # noqa: F401
+from .reading_order import (  # noqa: F401
+    resolve_intersections,
+    sort_boxes_reading_order,
+    sort_boxes_reading_order_with_resolutions,
+)
+from .trba import TRBA  # noqa: F401
+from .types import Block, Page, Word  # noqa: F401
 
 __version__ = "0.1.0"

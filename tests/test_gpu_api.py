@@ -1,0 +1,170 @@
+"""The reference-facing classes (EAST / TRBA / Pipeline mirrors) on the GPU: the duck-typed contract pinned by the
+reference's tests/test_pipeline_api_compatibility.py:15-238, plus parity of what flows through them."""
+import os
+
+import numpy as np
+import pytest
+
+import synthdata
+from oracle import cpu
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mb():
+    import manuscript_b200 as m
+
+    return m
+
+
+def three_words(mb):
+    W = mb.Word
+    return [W(polygon=[[10.0, 10.0], [100.0, 10.0], [100.0, 50.0], [10.0, 50.0]], detection_confidence=0.95),
+            W(polygon=[[110.0, 10.0], [200.0, 10.0], [200.0, 50.0], [110.0, 50.0]], detection_confidence=0.92),
+            W(polygon=[[210.0, 10.0], [300.0, 10.0], [300.0, 50.0], [210.0, 50.0]], detection_confidence=0.88)]
+
+
+class DummyDetector:
+    def __init__(self, mb, return_type="dict", words=None):
+        self.mb, self.return_type, self.words = mb, return_type, words
+
+    def predict(self, image, vis=False, profile=False):
+        page = self.mb.Page(blocks=[self.mb.Block(words=self.words or three_words(self.mb))])
+        if self.return_type == "dict":
+            return {"page": page, "vis_image": None, "score_map": None, "geo_map": None}
+        if self.return_type == "tuple":
+            return (page, None)
+        return page
+
+
+class DummyRecognizer:
+    def __init__(self):
+        self.call_count = 0
+        self.seen = None
+
+    def predict(self, images):
+        self.call_count += 1
+        self.seen = images
+        return [{"text": f"word{i + 1}", "confidence": 0.9 - i * 0.05} for i, _ in enumerate(images)]
+
+
+@pytest.mark.parametrize("rt", ["dict", "tuple", "page"])
+def test_pipeline_duck_typed_detector_and_recognizer(mb, rt):
+    rec = DummyRecognizer()
+    pipe = mb.Pipeline(detector=DummyDetector(mb, rt), recognizer=rec)
+    img = np.random.default_rng(0).integers(0, 256, (100, 400, 3), dtype=np.uint8)
+    page = pipe.predict(img, recognize_text=True, vis=False)
+    assert isinstance(page, mb.Page) and len(page.blocks[0].words) == 3
+    assert [w.text for w in page.blocks[0].words] == ["word1", "word2", "word3"]
+    assert rec.call_count == 1 and len(rec.seen) == 3
+    # the crops are the reference's slices image[y1:y2, x1:x2] in reading order (_pipeline.py:204-221)
+    np.testing.assert_array_equal(rec.seen[0], img[10:50, 10:100])
+    np.testing.assert_array_equal(rec.seen[2], img[10:50, 210:300])
+    assert "word1 word2 word3" == pipe.get_text(page)
+    assert isinstance(pipe.predict(img, recognize_text=False), mb.Page)
+
+
+def test_pipeline_min_text_size_filter(mb):
+    small = [mb.Word(polygon=[[10.0, 10.0], [12.0, 10.0], [12.0, 12.0], [10.0, 12.0]], detection_confidence=0.95)]
+    rec = DummyRecognizer()
+    pipe = mb.Pipeline(detector=DummyDetector(mb, "dict", small), recognizer=rec, min_text_size=5)
+    pipe.predict(np.zeros((100, 400, 3), np.uint8))
+    assert rec.call_count == 0
+
+
+def test_pipeline_errors(mb):
+    class NoPage:
+        def predict(self, image, vis=False, profile=False):
+            return {"page": None}
+
+    with pytest.raises(RuntimeError):
+        mb.Pipeline(detector=NoPage(), recognizer=DummyRecognizer()).predict(np.zeros((10, 10, 3), np.uint8))
+    with pytest.raises(TypeError):
+        mb.read_image(123)
+    with pytest.raises(FileNotFoundError):
+        mb.read_image("/nonexistent/file.png")
+
+
+def test_east_predict_from_maps_golden(mb, golden_dir):
+    g = np.load(os.path.join(golden_dir, "page_s2.npz"))
+    seed, page, words = int(g["seed"]), int(g["page"]), int(g["words"])
+    score, geo, _ = synthdata.make_maps(seed, page, words)
+    det = mb.EAST(target_size=page)
+    orig_hw = tuple(int(v) for v in g["orig_hw"])
+    boxes = det.boxes_from_maps(score, geo, orig_hw)
+    np.testing.assert_array_equal(boxes, g["aligned"])
+    pg = det.predict_from_maps(score, geo, orig_hw)
+    assert len(pg.blocks) == 1 and len(pg.blocks[0].words) == len(g["aligned"])
+    w0 = pg.blocks[0].words[0]
+    assert w0.polygon[0] == (float(g["aligned"][0, 0]), float(g["aligned"][0, 1]))
+    assert w0.detection_confidence == float(g["aligned"][0, 8])
+    # non-default kwargs reach the kernels
+    det2 = mb.EAST(target_size=page, expand_ratio_w=0.3, expand_ratio_h=0.7, axis_aligned_output=False, iou_threshold=0.5)
+    q = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    want = cpu.east_postprocess(cpu.locality_aware_nms(q, 0.5), orig_hw, target_size=page, expand_w=0.3, expand_h=0.7,
+                                axis_aligned=False)
+    np.testing.assert_array_equal(det2.boxes_from_maps(score, geo, orig_hw), want)
+
+
+def test_east_predict_with_a_stub_network(mb):
+    """EAST.predict end to end with a stand-in network that replays synthetic maps (the real ResNet is outside
+    the path): result dict keys and Page contents as the reference's (infer.py:395-400)."""
+    import torch
+
+    page, words = 512, 60
+    score, geo, _ = synthdata.make_maps(5, page, words)
+
+    class Net:
+        def __call__(self, x):
+            assert x.shape == (1, 3, page, page) and x.is_cuda
+            return {"score": torch.from_numpy(score)[None, None].cuda(), "geometry": torch.from_numpy(geo)[None].cuda()}
+
+    det = mb.EAST(model=Net(), target_size=page)
+    img = synthdata.make_page_image(5, 700)[:600, :700]
+    out = det.predict(img, return_maps=True, sort_reading_order=True)
+    assert set(out) == {"page", "vis_image", "score_map", "geo_map"}
+    np.testing.assert_array_equal(out["score_map"], score)
+    q = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    want = cpu.east_postprocess(cpu.locality_aware_nms(q, 0.2), (600, 700), target_size=page)
+    got = sorted(tuple(np.float32(v) for pt in w.polygon for v in pt) for w in out["page"].blocks[0].words)
+    assert got == sorted(tuple(r[:8]) for r in want)
+    with pytest.raises(RuntimeError):
+        mb.EAST(target_size=page).predict(img)
+
+
+def test_trba_preprocess_matches_oracle(mb):
+    rng = np.random.default_rng(2)
+    crops = [rng.integers(0, 256, (int(h), int(w), 3), dtype=np.uint8)
+             for h, w in [(20, 60), (64, 256), (70, 300), (10, 10), (33, 500), (5, 7), (128, 64)]]
+    for ih, iw in [(64, 256), (32, 128)]:
+        rec = mb.TRBA(model=lambda b: [{"text": "x", "confidence": 0.5}] * len(b), img_h=ih, img_w=iw)
+        batch = rec.preprocess(crops).cpu().numpy()
+        for i, c in enumerate(crops):
+            _, chw = cpu.crop_resize_pad(c, np.array([0, 0, c.shape[1], c.shape[0]], np.int32), ih, iw)
+            np.testing.assert_array_equal(batch[i], chw)
+        res = rec.predict(crops, batch_size=3)
+        assert len(res) == len(crops) and res[0] == {"text": "x", "confidence": 0.5}
+    grey = rng.integers(0, 256, (20, 50), dtype=np.uint8)
+    b = mb.TRBA(model=None).preprocess([grey]).cpu().numpy()
+    _, chw = cpu.crop_resize_pad(np.repeat(grey[:, :, None], 3, 2), np.array([0, 0, 50, 20], np.int32), 64, 256)
+    np.testing.assert_array_equal(b[0], chw)
+
+
+def test_pipeline_with_b200_trba_feeds_device_batch(mb):
+    seen = {}
+
+    def model(batch):
+        seen["shape"], seen["cuda"] = tuple(batch.shape), batch.is_cuda
+        seen["batch"] = batch.cpu().numpy()
+        return [(f"t{i}", 0.5) for i in range(len(batch))]
+
+    rec = mb.TRBA(model=model, img_h=32, img_w=128)
+    pipe = mb.Pipeline(detector=DummyDetector(mb, "dict"), recognizer=rec)
+    img = np.random.default_rng(1).integers(0, 256, (100, 400, 3), dtype=np.uint8)
+    page = pipe.predict(img)
+    assert seen["shape"] == (3, 3, 32, 128) and seen["cuda"]
+    _, chw = cpu.crop_resize_pad(img, np.array([110, 10, 200, 50], np.int32), 32, 128)
+    np.testing.assert_array_equal(seen["batch"][1], chw)
+    assert [w.text for w in page.blocks[0].words] == ["t0", "t1", "t2"]
+    assert page.blocks[0].words[0].recognition_confidence == 0.5

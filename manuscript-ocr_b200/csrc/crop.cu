@@ -191,12 +191,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "{\n"
         ".reg .pred p;\n"
         "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning on issue slots
         : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
@@ -294,48 +294,50 @@ __device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
     return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)) - 8388608.0f;
 }
 
-// INTER_AREA general path for one destination pixel when the horizontal table has <= 4 taps and the source
-// rows are staged: each row contributes 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit
-// shared-memory words; taps beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).
-// Same products and the same summation order as resample_px's general branch.
+// INTER_AREA general path for one destination pixel when both tables have <= 4 taps and the source rows are
+// staged: each row contributes 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit shared-memory words;
+// taps beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).  wx / wy are the tap weights the
+// producer precomputed from the same table entries.  Same products and the same summation order as resample_px's
+// general branch.
 __device__ __forceinline__ void resample_area4(const unsigned char *smem_base, uint32_t buf_off, int pitch, uint32_t a0,
-                                               uint32_t sstep, const AxisEnt &ex, const AxisEnt &ey, unsigned char &o0,
-                                               unsigned char &o1, unsigned char &o2)
+                                               uint32_t sstep, int xs0, int ys0, int yn, const float4 wx,
+                                               const float4 wy, unsigned char &o0, unsigned char &o1, unsigned char &o2)
 {
     const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
-    float w[4];
-#pragma unroll
-    for (int e = 0; e < 4; e++) w[e] = e < ex.n ? area_weight(ex, e) : 0.f;
+    const float wyv[4] = {wy.x, wy.y, wy.z, wy.w};
     float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-    for (int j = 0; j < ey.n; j++) {
-        const float beta = area_weight(ey, j);
-        const uint32_t sy = (uint32_t)(ey.s0 + j);
-        const uint32_t o = buf_off + sy * (uint32_t)pitch + ((a0 + sy * sstep) & 15u) + (uint32_t)ex.s0 * 3u;
-        const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
-        const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
-        const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
-                       v2 = __funnelshift_r(w2, w3, sh);
-        // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
-        float b0 = byte_f32(v0, 0x7650) * w[0];
-        float b1 = byte_f32(v0, 0x7651) * w[0];
-        float b2 = byte_f32(v0, 0x7652) * w[0];
-        b0 = b0 + byte_f32(v0, 0x7653) * w[1];
-        b1 = b1 + byte_f32(v1, 0x7650) * w[1];
-        b2 = b2 + byte_f32(v1, 0x7651) * w[1];
-        b0 = b0 + byte_f32(v1, 0x7652) * w[2];
-        b1 = b1 + byte_f32(v1, 0x7653) * w[2];
-        b2 = b2 + byte_f32(v2, 0x7650) * w[2];
-        b0 = b0 + byte_f32(v2, 0x7651) * w[3];
-        b1 = b1 + byte_f32(v2, 0x7652) * w[3];
-        b2 = b2 + byte_f32(v2, 0x7653) * w[3];
-        if (j == 0) {
-            sum0 = beta * b0;
-            sum1 = beta * b1;
-            sum2 = beta * b2;
-        } else {
-            sum0 += beta * b0;
-            sum1 += beta * b1;
-            sum2 += beta * b2;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if (j < yn) {
+            const float beta = wyv[j];
+            const uint32_t sy = (uint32_t)(ys0 + j);
+            const uint32_t o = buf_off + sy * (uint32_t)pitch + ((a0 + sy * sstep) & 15u) + (uint32_t)xs0 * 3u;
+            const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
+            const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
+            const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
+                           v2 = __funnelshift_r(w2, w3, sh);
+            // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
+            float b0 = byte_f32(v0, 0x7650) * wx.x;
+            float b1 = byte_f32(v0, 0x7651) * wx.x;
+            float b2 = byte_f32(v0, 0x7652) * wx.x;
+            b0 = b0 + byte_f32(v0, 0x7653) * wx.y;
+            b1 = b1 + byte_f32(v1, 0x7650) * wx.y;
+            b2 = b2 + byte_f32(v1, 0x7651) * wx.y;
+            b0 = b0 + byte_f32(v1, 0x7652) * wx.z;
+            b1 = b1 + byte_f32(v1, 0x7653) * wx.z;
+            b2 = b2 + byte_f32(v2, 0x7650) * wx.z;
+            b0 = b0 + byte_f32(v2, 0x7651) * wx.w;
+            b1 = b1 + byte_f32(v2, 0x7652) * wx.w;
+            b2 = b2 + byte_f32(v2, 0x7653) * wx.w;
+            if (j == 0) {
+                sum0 = beta * b0;
+                sum1 = beta * b1;
+                sum2 = beta * b2;
+            } else {
+                sum0 += beta * b0;
+                sum1 += beta * b1;
+                sum2 += beta * b2;
+            }
         }
     }
     o0 = sat_u8(cv_round(sum0));
@@ -364,15 +366,27 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
 }
 
 // producer warp: the coefficient tables of one crop, 32 lanes
-__device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, AxisEnt *tab_y, int lane)
+__device__ __forceinline__ float4 tap_weights(const AxisEnt &e)
+{
+    return make_float4(0 < e.n ? area_weight(e, 0) : 0.f, 1 < e.n ? area_weight(e, 1) : 0.f,
+                       2 < e.n ? area_weight(e, 2) : 0.f, 3 < e.n ? area_weight(e, 3) : 0.f);
+}
+
+__device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, AxisEnt *tab_y, float4 *w_x, float4 *w_y,
+                                             int lane)
 {
     if (!(p.ok && (p.interp == 1 || p.interp == 3))) return;
     for (int t = lane; t < p.nw + p.nh; t += 32) {
-        if (t < p.nw)
-            tab_x[t] = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
-        else
-            tab_y[t - p.nw] =
-                p.interp == 3 ? area_entry(t - p.nw, p.scale_y, p.h) : linear_entry_y(t - p.nw, p.scale_y, p.h);
+        if (t < p.nw) {
+            const AxisEnt e = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
+            tab_x[t] = e;
+            if (p.interp == 3) w_x[t] = tap_weights(e);
+        } else {
+            const int d = t - p.nw;
+            const AxisEnt e = p.interp == 3 ? area_entry(d, p.scale_y, p.h) : linear_entry_y(d, p.scale_y, p.h);
+            tab_y[d] = e;
+            if (p.interp == 3) w_y[d] = tap_weights(e);
+        }
     }
 }
 
@@ -452,6 +466,7 @@ __global__ void __launch_bounds__(kThreads, 3)
     extern __shared__ __align__(128) unsigned char smem[];
     AxisEnt *tabs = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);  // [2][iw + ih]
     const int tab_n = iw + ih;
+    float4 *tabw = reinterpret_cast<float4 *>(tabs + 2 * (size_t)tab_n);  // [2][iw + ih] tap weights
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
     __shared__ Plan s_plan[2];
 
@@ -481,8 +496,7 @@ __global__ void __launch_bounds__(kThreads, 3)
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
                                               kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane);
             if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
-            if (lane == 0) s_plan[b] = p;
-            build_tables(p, tabs + (size_t)b * tab_n, tabs + (size_t)b * tab_n + iw, lane);
+            // TMA first: its latency overlaps the float64 table arithmetic below
             uint32_t bytes = 0;
             if (p.staged) {
                 const uint8_t *src = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
@@ -497,6 +511,9 @@ __global__ void __launch_bounds__(kThreads, 3)
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
             }
+            if (lane == 0) s_plan[b] = p;
+            build_tables(p, tabs + (size_t)b * tab_n, tabs + (size_t)b * tab_n + iw, tabw + (size_t)b * tab_n,
+                         tabw + (size_t)b * tab_n + iw, lane);
             __syncwarp();  // every lane's plan / table stores are ordered before lane 0's releasing arrive
             if (lane == 0) {
                 if (bytes)
@@ -530,8 +547,16 @@ __global__ void __launch_bounds__(kThreads, 3)
             for (int t = ct; t < npx; t += kCT) {
                 const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
                 unsigned char o0, o1, o2;
-                if (p.staged && p.interp == 3 && tab_x[dx].n <= 4) {
-                    resample_area4(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, tab_x[dx], tab_y[dy], o0, o1, o2);
+                int xs0 = 0, xn = 5, ys0 = 0, yn = 5;
+                if (p.staged && p.interp == 3) {
+                    xs0 = tab_x[dx].s0;
+                    xn = tab_x[dx].n;
+                    ys0 = tab_y[dy].s0;
+                    yn = tab_y[dy].n;
+                }
+                if (xn <= 4 && yn <= 4) {
+                    resample_area4(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, xs0, ys0, yn,
+                                   tabw[(size_t)b * tab_n + dx], tabw[(size_t)b * tab_n + iw + dy], o0, o1, o2);
                 } else if (p.staged) {
                     auto row = [&](int sy) -> const unsigned char * {
                         return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
@@ -576,7 +601,7 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
         ms_set_error("crop: canvas %dx%d too large", out_h, out_w);
         return MS_ERR_INVALID;
     }
-    const size_t smem = 2 * (size_t)kSrcBuf + 2 * (size_t)(out_h + out_w) * sizeof(AxisEnt);
+    const size_t smem = 2 * (size_t)kSrcBuf + 2 * (size_t)(out_h + out_w) * (sizeof(AxisEnt) + sizeof(float4));
     if (smem > 220 * 1024) {
         ms_set_error("crop: canvas %dx%d needs %zu bytes of shared memory", out_h, out_w, smem);
         return MS_ERR_INVALID;

@@ -33,7 +33,12 @@
 
 namespace {
 
-constexpr int kEdgeFactor = 16;  // suppression-edge capacity per candidate (overflow -> flag)
+constexpr int kEdgeFactor = 16;  // neighbour-pair capacity per candidate (overflow -> flag)
+constexpr int kGrid = 32;        // uniform grid per page for the neighbour search
+constexpr int kCells = kGrid * kGrid;
+// neighbour pair word: lo in bits 0..29, hi (higher NMS priority) in bits 30..59
+constexpr uint64_t kPairTrue = 1ull << 62;  // IoU already evaluated and > thr
+constexpr uint64_t kPairDone = 1ull << 63;  // nothing left to learn from this pair
 
 struct LanmsBuffers {
     int32_t *page_off;   // n_pages+1 exclusive offsets of candidate counts (packed space)
@@ -58,7 +63,13 @@ struct LanmsBuffers {
     uint8_t *cl_irr;
     int32_t *cl_orig;    // priority tie-break index (creation order)
     int32_t *cl_count;   // per page
-    float *page_slack;   // per page: max(key - minx) over regular clusters
+    float *page_ext;     // per page, 8 floats: minx, miny, cells per unit x / y, max bbox width / height
+    int32_t *cell_cnt;   // per page, kCells: regular clusters per grid cell
+    int32_t *cell_off;   // per page, kCells + 1
+    int32_t *cell_cur;   // per page, kCells: scatter cursors
+    int32_t *cl_cell;    // per cluster: its home cell
+    float4 *sb_bbox;     // clusters in cell order: inflated bbox ...
+    int32_t *sb_id;      // ... and cluster index
     uint64_t *edges;
     int32_t *edge_count; // per page
     uint8_t *state;      // 0 undecided / 1 kept / 2 suppressed
@@ -280,8 +291,9 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
     __shared__ int s_h[kResolveThreads], s_e[kResolveThreads];
     __shared__ int s_vh[kResolveThreads], s_ve[kResolveThreads];
     __shared__ int s_nvalid, s_klast;
-    __shared__ float s_slack[32];
+    __shared__ float s_red[32][6];
     if (threadIdx.x == 0) s_klast = p0 - 1;
+    for (int i = threadIdx.x; i < kCells; i += kResolveThreads) B.cell_cnt[(size_t)page * kCells + i] = 0;
     __syncthreads();
 
     // phase A: walk hot positions in order, accept a run iff its head lies beyond the last accepted run
@@ -322,7 +334,7 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
 
     // phase B: anchors (mflag == 0) in order are the clusters
     int run_base = 0;
-    float slack = 0.0f;
+    float e_minx = INFINITY, e_miny = INFINITY, e_maxx = -INFINITY, e_maxy = -INFINITY, e_w = 0.f, e_h = 0.f;
     for (int base = p0; base < p1; base += kResolveThreads) {
         int s = base + threadIdx.x;
         int anchor = (s < p1 && B.mflag[s] == 0) ? 1 : 0;
@@ -355,28 +367,81 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
             if (!reg) B.irr_list[atomicAdd(B.irr_count, 1)] = (int)slot;
             B.cl_orig[slot] = c;
             B.state[slot] = 0;
-            if (reg) slack = fmaxf(slack, key - bb.x);
+            if (reg) {
+                e_minx = fminf(e_minx, bb.x);
+                e_miny = fminf(e_miny, bb.y);
+                e_maxx = fmaxf(e_maxx, bb.z);
+                e_maxy = fmaxf(e_maxy, bb.w);
+                e_w = fmaxf(e_w, bb.z - bb.x);
+                e_h = fmaxf(e_h, bb.w - bb.y);
+            }
         }
         run_base += total;
     }
-    // page slack = max over regular clusters of (key - minx); keys are sorted, so every box that can
-    // overlap box a starts no later than maxx_a + slack in key order
+    // page extents of the regular clusters -> geometry of the neighbour-search grid
 #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) slack = fmaxf(slack, __shfl_xor_sync(0xffffffffu, slack, off));
-    if ((threadIdx.x & 31) == 0) s_slack[threadIdx.x >> 5] = slack;
+    for (int off = 16; off > 0; off >>= 1) {
+        e_minx = fminf(e_minx, __shfl_xor_sync(0xffffffffu, e_minx, off));
+        e_miny = fminf(e_miny, __shfl_xor_sync(0xffffffffu, e_miny, off));
+        e_maxx = fmaxf(e_maxx, __shfl_xor_sync(0xffffffffu, e_maxx, off));
+        e_maxy = fmaxf(e_maxy, __shfl_xor_sync(0xffffffffu, e_maxy, off));
+        e_w = fmaxf(e_w, __shfl_xor_sync(0xffffffffu, e_w, off));
+        e_h = fmaxf(e_h, __shfl_xor_sync(0xffffffffu, e_h, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        float *r = s_red[threadIdx.x >> 5];
+        r[0] = e_minx; r[1] = e_miny; r[2] = e_maxx; r[3] = e_maxy; r[4] = e_w; r[5] = e_h;
+    }
     __syncthreads();
     if (threadIdx.x == 0) {
-        float m = 0.0f;
-        for (int w = 0; w < kResolveThreads / 32; w++) m = fmaxf(m, s_slack[w]);
-        B.page_slack[page] = m;
+        float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY, mw = 0.f, mh = 0.f;
+        for (int w = 0; w < kResolveThreads / 32; w++) {
+            minx = fminf(minx, s_red[w][0]);
+            miny = fminf(miny, s_red[w][1]);
+            maxx = fmaxf(maxx, s_red[w][2]);
+            maxy = fmaxf(maxy, s_red[w][3]);
+            mw = fmaxf(mw, s_red[w][4]);
+            mh = fmaxf(mh, s_red[w][5]);
+        }
+        float *ext = B.page_ext + (size_t)page * 8;
+        const bool any = maxx >= minx;
+        const float sx = any ? fmaxf(maxx - minx, 1e-3f) : 1.f, sy = any ? fmaxf(maxy - miny, 1e-3f) : 1.f;
+        ext[0] = any ? minx : 0.f;
+        ext[1] = any ? miny : 0.f;
+        ext[2] = (float)kGrid / sx;
+        ext[3] = (float)kGrid / sy;
+        ext[4] = mw;
+        ext[5] = mh;
         B.cl_count[page] = run_base;
     }
 }
 
-// ---- 5. suppression edges: sweep in key order, bbox prefilter, fp64 clip -------------------------------------
+// ---- 5. neighbour pairs ---------------------------------------------------------------------------------------
+// Only pairs whose (inflated) bounding boxes overlap can have IoU > thr >= 0 when both quads are regular (convex,
+// positively oriented): those pairs are found with a uniform grid per page and stored UNEVALUATED -- the fp64 clip
+// runs lazily in the resolve step, only for pairs whose higher-priority box turned out to be kept.  Irregular quads
+// (and every quad when thr < 0) are paired with every other box of their page and evaluated eagerly.
 constexpr int kPairThreads = 128;
 constexpr int kPairWarps = kPairThreads / 32;
 constexpr int kQueue = 96;  // per-warp pending pairs (flush at >= 32)
+
+__device__ __forceinline__ int cell_coord(float v, float origin, float scale)
+{
+    // monotone in v: the same function maps box corners and search bounds
+    float f = (v - origin) * scale;
+    int c = f > 0.f ? (f < (float)(kGrid - 1) ? (int)f : kGrid - 1) : 0;
+    return c;
+}
+
+__device__ __forceinline__ void push_pair(int hi, int lo, uint64_t flag, int p0, int page, const LanmsBuffers &B,
+                                          int edge_cap, int32_t *flags)
+{
+    int e = atomicAdd(B.edge_count + page, 1);
+    if (e < edge_cap)
+        B.edges[(size_t)p0 * kEdgeFactor + e] = flag | ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
+    else
+        atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
+}
 
 __device__ __forceinline__ void eval_pair(int a, int b, int p0, int page, double thr, const LanmsBuffers &B,
                                           int edge_cap, int32_t *flags, double *buf)
@@ -389,18 +454,12 @@ __device__ __forceinline__ void eval_pair(int a, int b, int p0, int page, double
     bool a_first = prio_before(B.cl_score[sa], B.cl_orig[sa], B.cl_score[sb], B.cl_orig[sb]);
     // lanms.py:149 should_merge(polys[idx] (kept, earlier), polys[idx_j] (later))
     double iou = a_first ? ms_quad_iou(qa, qb, buf) : ms_quad_iou(qb, qa, buf);
-    if (iou > thr) {
-        int hi = a_first ? a : b, lo = a_first ? b : a;
-        int e = atomicAdd(B.edge_count + page, 1);
-        if (e < edge_cap)
-            B.edges[(size_t)p0 * kEdgeFactor + e] = ((uint64_t)(uint32_t)hi << 32) | (uint32_t)lo;
-        else
-            atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
-    }
+    if (iou > thr) push_pair(a_first ? a : b, a_first ? b : a, kPairTrue, p0, page, B, edge_cap, flags);
 }
 
-// Warp per cluster.  irregular_only != 0: only irregular clusters are swept here (each against every other
-// box of its page); the regular ones are handled by lanms_pairs_tiled_kernel.
+// Warp per listed cluster, paired with every other box of its page, IoU evaluated eagerly.  irregular_only != 0:
+// the items are the irregular clusters (pairs of two irregular boxes are produced once, by the one with the
+// smaller index); otherwise every slot is an item (standard_nms, where all boxes are flagged irregular).
 __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t *__restrict__ page_off,
                                                                    const int32_t *__restrict__ n_total, double thr,
                                                                    LanmsBuffers B, int32_t *flags, int irregular_only)
@@ -422,31 +481,10 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
         const int p0 = page_off[page];
         const int a = slot - p0;
         const int C = B.cl_count[page];
-        if (a >= C) continue;
-        const bool a_irr = B.cl_irr[slot] != 0;
-        const float4 ba = B.cl_bbox[slot];
-        const float limit = ba.z + B.page_slack[page];
-        // regular a: forward sweep; irregular a: every other box of the page (pairs of two irregular
-        // boxes are produced once, by the one with the smaller index)
-        int b0 = a_irr ? 0 : a + 1;
-        for (int bb = b0; bb < C; bb += 32) {
+        if (a >= C || B.cl_irr[slot] == 0) continue;
+        for (int bb = 0; bb < C; bb += 32) {
             int b = bb + lane;
-            bool live = b < C && b != a;
-            bool hit = false;
-            bool beyond = false;
-            if (live) {
-                size_t sb = (size_t)p0 + b;
-                bool b_irr = B.cl_irr[sb] != 0;
-                if (a_irr) {
-                    hit = !(b_irr && b < a);
-                } else {
-                    beyond = B.cl_key[sb] > limit;
-                    if (!b_irr && !beyond) {
-                        float4 o = B.cl_bbox[sb];
-                        hit = !(o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y);
-                    }
-                }
-            }
+            bool hit = b < C && b != a && !(B.cl_irr[(size_t)p0 + b] != 0 && b < a);
             uint32_t m = __ballot_sync(0xffffffffu, hit);
             if (hit) {
                 int pos = qn + __popc(m & ((1u << lane) - 1u));
@@ -465,8 +503,6 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
                 qn -= 32;
                 __syncwarp();
             }
-            // keys ascend: once every live lane is beyond the limit, nothing further can overlap
-            if (!a_irr && __all_sync(0xffffffffu, !live || beyond) && __any_sync(0xffffffffu, live && beyond)) break;
         }
     }
     if (lane < qn) {
@@ -477,90 +513,139 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
     }
 }
 
-// Regular clusters: thread per cluster a, candidates b > a streamed through shared memory in key (x0) order.
-// Keys ascend, so every b whose inflated bbox can touch a's lies in the window (a, last b with key <= maxx_a +
-// page_slack]; the CTA walks tiles until the first key of a tile passes the largest limit of its threads.
-// Bbox-overlapping pairs are queued per warp and evaluated 32 at a time (fp64 Sutherland-Hodgman).
-constexpr int kTile = 128;
+// grid binning of the regular clusters by the min corner of their inflated bbox
+__global__ void __launch_bounds__(256) nms_bin_count_kernel(const int32_t *__restrict__ page_off,
+                                                            const int32_t *__restrict__ n_total, LanmsBuffers B)
+{
+    const int n = *n_total;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        const int page = B.pos_page[slot];
+        const int c = slot - page_off[page];
+        if (c >= B.cl_count[page] || B.cl_irr[slot]) continue;
+        const float *ext = B.page_ext + (size_t)page * 8;
+        const float4 bb = B.cl_bbox[slot];
+        const int cell = cell_coord(bb.y, ext[1], ext[3]) * kGrid + cell_coord(bb.x, ext[0], ext[2]);
+        B.cl_cell[slot] = cell;
+        atomicAdd(B.cell_cnt + (size_t)page * kCells + cell, 1);
+    }
+}
 
-__global__ void __launch_bounds__(kTile) lanms_pairs_tiled_kernel(const int32_t *__restrict__ page_off, double thr,
-                                                                  LanmsBuffers B, int32_t *flags)
+__global__ void __launch_bounds__(kCells) nms_bin_scan_kernel(LanmsBuffers B)
+{
+    const int page = blockIdx.x;
+    __shared__ int s_warp[33];
+    const int v = B.cell_cnt[(size_t)page * kCells + threadIdx.x];
+    int total;
+    const int off = block_excl_scan_1024(v, s_warp, total);
+    B.cell_off[(size_t)page * (kCells + 1) + threadIdx.x] = off;
+    B.cell_cur[(size_t)page * kCells + threadIdx.x] = off;
+    if (threadIdx.x == 0) B.cell_off[(size_t)page * (kCells + 1) + kCells] = total;
+}
+
+__global__ void __launch_bounds__(256) nms_bin_scatter_kernel(const int32_t *__restrict__ page_off,
+                                                              const int32_t *__restrict__ n_total, LanmsBuffers B)
+{
+    const int n = *n_total;
+    for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
+        const int page = B.pos_page[slot];
+        const int p0 = page_off[page];
+        const int c = slot - p0;
+        if (c >= B.cl_count[page] || B.cl_irr[slot]) continue;
+        const int pos = atomicAdd(B.cell_cur + (size_t)page * kCells + B.cl_cell[slot], 1);
+        B.sb_bbox[(size_t)p0 + pos] = B.cl_bbox[slot];
+        B.sb_id[(size_t)p0 + pos] = c;
+    }
+}
+
+// thread per regular cluster a: every b > a whose bbox overlaps a's becomes an (unevaluated) neighbour pair,
+// oriented hi -> lo by NMS priority.  b's home cell holds its min corner, which lies in
+// [a.min - (max bbox size of the page), a.max]; each grid row of that range is one contiguous span of the
+// cell-ordered arrays.  Hits are kept per thread and appended with ONE atomic per CTA (same-address atomics per
+// hit serialise in L2 and cost more than the search itself).
+constexpr int kBinThreads = 256;
+constexpr int kMaxHits = 32;  // higher-index neighbours one cluster may have (overflow -> MS_FLAG_EDGE_OVERFLOW)
+
+__global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int32_t *__restrict__ page_off,
+                                                                       LanmsBuffers B, int32_t *flags)
 {
     const int page = blockIdx.y;
     const int p0 = page_off[page];
     const int C = B.cl_count[page];
+    const float *ext = B.page_ext + (size_t)page * 8;
+    const int32_t *coff = B.cell_off + (size_t)page * (kCells + 1);
     const int edge_cap = (page_off[page + 1] - p0) * kEdgeFactor;
+    const float ox = ext[0], oy = ext[1], sx = ext[2], sy = ext[3], mw = ext[4], mh = ext[5];
+    __shared__ int s_warp[kBinThreads / 32 + 1];
+    __shared__ int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ float4 s_bb[kTile];
-    __shared__ float s_key[kTile];
-    __shared__ uint8_t s_irr[kTile];
-    __shared__ float s_wlim[kTile / 32];
-    __shared__ int2 s_q[kTile / 32][kQueue];
-    int2 *q = s_q[warp];
-    int qn = 0;  // warp-uniform
-    double buf[4 * MS_MAXV];
-    const float slack = B.page_slack[page];
-
-    for (int base = blockIdx.x * kTile; base < C; base += gridDim.x * kTile) {
+    for (int base = blockIdx.x * kBinThreads; base < C; base += gridDim.x * kBinThreads) {
         const int a = base + threadIdx.x;
-        const bool a_live = a < C && B.cl_irr[p0 + a] == 0;
-        float4 ba = make_float4(0.f, 0.f, 0.f, 0.f);
-        float limit = -INFINITY;
-        if (a_live) {
-            ba = B.cl_bbox[p0 + a];
-            limit = ba.z + slack;
-        }
-        float wl = limit;
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) wl = fmaxf(wl, __shfl_xor_sync(0xffffffffu, wl, off));
-        __syncthreads();  // previous tile loop done with s_wlim / tiles
-        if (lane == 0) s_wlim[warp] = wl;
-        __syncthreads();
-        float blk_limit = s_wlim[0];
-#pragma unroll
-        for (int w = 1; w < kTile / 32; w++) blk_limit = fmaxf(blk_limit, s_wlim[w]);
-
-        for (int tb = base + 1; tb < C; tb += kTile) {
-            __syncthreads();
-            const int bl = tb + threadIdx.x;
-            if (bl < C) {
-                s_bb[threadIdx.x] = B.cl_bbox[p0 + bl];
-                s_key[threadIdx.x] = B.cl_key[p0 + bl];
-                s_irr[threadIdx.x] = B.cl_irr[p0 + bl];
-            }
-            __syncthreads();
-            if (s_key[0] > blk_limit) break;  // uniform: nothing from here on can touch any a of this CTA
-            const int nb = min(kTile, C - tb);
-            if (wl == -INFINITY) continue;  // warp has no regular cluster in this tile of a's
-            for (int t = 0; t < nb; t++) {
-                const int b = tb + t;
-                if (s_key[t] > wl) break;  // warp-uniform
-                const float4 o = s_bb[t];
-                const bool hit = a_live && b > a && !s_irr[t] &&
-                                 !(o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y);
-                const uint32_t m = __ballot_sync(0xffffffffu, hit);
-                if (m == 0) continue;
-                if (hit) q[qn + __popc(m & ((1u << lane) - 1u))] = make_int2(a, b);
-                qn += __popc(m);
-                __syncwarp();
-                while (qn >= 32) {
-                    const int2 pr = q[qn - 32 + lane];
-                    __syncwarp();
-                    eval_pair(pr.x, pr.y, p0, page, thr, B, edge_cap, flags, buf);
-                    qn -= 32;
-                    __syncwarp();
+        int hits[kMaxHits];
+        int cnt = 0;
+        bool over = false;
+        double sa = 0.0;
+        if (a < C && B.cl_irr[(size_t)p0 + a] == 0) {
+            const float4 ba = B.cl_bbox[(size_t)p0 + a];
+            sa = B.cl_score[(size_t)p0 + a];
+            const int cx0 = cell_coord(ba.x - mw, ox, sx), cx1 = cell_coord(ba.z, ox, sx);
+            const int cy0 = cell_coord(ba.y - mh, oy, sy), cy1 = cell_coord(ba.w, oy, sy);
+            for (int cy = cy0; cy <= cy1; cy++) {
+                const int pos1 = coff[cy * kGrid + cx1 + 1];
+                for (int pos = coff[cy * kGrid + cx0]; pos < pos1; pos++) {
+                    const int b = B.sb_id[(size_t)p0 + pos];
+                    if (b <= a) continue;
+                    const float4 o = B.sb_bbox[(size_t)p0 + pos];
+                    if (o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y) continue;
+                    if (cnt < kMaxHits)
+                        hits[cnt++] = b;
+                    else
+                        over = true;
                 }
             }
         }
-    }
-    if (lane < qn) {
-        const int2 pr = q[lane];
-        eval_pair(pr.x, pr.y, p0, page, thr, B, edge_cap, flags, buf);
+        // CTA-wide exclusive scan of the hit counts -> one reservation in the page's pair list
+        int inc = cnt;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            int t = __shfl_up_sync(0xffffffffu, inc, off);
+            if (lane >= off) inc += t;
+        }
+        __syncthreads();
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int run = 0;
+            for (int w = 0; w < kBinThreads / 32; w++) {
+                int t = s_warp[w];
+                s_warp[w] = run;
+                run += t;
+            }
+            s_base = run > 0 ? atomicAdd(B.edge_count + page, run) : 0;
+        }
+        __syncthreads();
+        int at = s_base + s_warp[warp] + inc - cnt;
+        if (over || (cnt > 0 && at + cnt > edge_cap)) atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
+        for (int k = 0; k < cnt; k++, at++) {
+            if (at >= edge_cap) break;
+            const int b = hits[k];
+            // cl_orig == cluster index for LANMS clusters; both are regular here
+            const bool a_first = prio_before(sa, a, B.cl_score[(size_t)p0 + b], b);
+            const int hi = a_first ? a : b, lo = a_first ? b : a;
+            B.edges[(size_t)p0 * kEdgeFactor + at] = ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
+        }
     }
 }
 
-// ---- 6. greedy recurrence in rounds (one CTA per page) ----------------------------------------------------------
-__global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
+// ---- 6. greedy recurrence in rounds (one CTA per page), IoU evaluated lazily ----------------------------------
+// keep[i] = !any(keep[j] and IoU(j, i) > thr for neighbours j of higher priority).  A box is decided once all its
+// higher-priority neighbours are; a pair is clipped (fp64 Sutherland-Hodgman, subject = the kept box as in
+// lanms.py:149) only when its higher box is kept and its lower box is still undecided -- in a text page that is
+// ~1/4 of the neighbour pairs.  Identical to the sequential loop because the predicate is a pure function of the
+// ordered pair.
+constexpr int kResolveWarps = 32;
+
+__global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, double thr,
+                                                             LanmsBuffers B)
 {
     const int page = blockIdx.x;
     const int p0 = page_off[page];
@@ -568,25 +653,69 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
     int E = B.edge_count[page];
     const int ecap = (page_off[page + 1] - p0) * kEdgeFactor;
     if (E > ecap) E = ecap;
-    const uint64_t *edges = B.edges + (size_t)p0 * kEdgeFactor;
+    uint64_t *edges = B.edges + (size_t)p0 * kEdgeFactor;
     uint8_t *state = B.state + p0;
     uint8_t *blocked = B.blocked + p0;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_undecided;
+    __shared__ int s_q[kResolveWarps][64];
+    int *q = s_q[warp];
+    double buf[4 * MS_MAXV];
+
+    auto clip = [&](int e) {
+        const uint64_t ed = edges[e];
+        const int hi = (int)((ed >> 30) & 0x3fffffffu), lo = (int)(ed & 0x3fffffffu);
+        double qh[8], ql[8];
+        load_quad(B.cl_poly + (size_t)(p0 + hi) * 8, qh);
+        load_quad(B.cl_poly + (size_t)(p0 + lo) * 8, ql);
+        if (ms_quad_iou(qh, ql, buf) > thr)
+            state[lo] = 2;
+        else
+            edges[e] = ed | kPairDone;
+    };
+
     while (true) {
         for (int c = threadIdx.x; c < C; c += blockDim.x) blocked[c] = 0;
         if (threadIdx.x == 0) s_undecided = 0;
         __syncthreads();
-        for (int e = threadIdx.x; e < E; e += blockDim.x) {
-            uint64_t ed = edges[e];
-            int hi = (int)(ed >> 32), lo = (int)(ed & 0xffffffffu);
-            if (state[lo] == 0) {
-                uint8_t sh = state[hi];
-                if (sh == 1)
-                    state[lo] = 2;
-                else if (sh == 0)
-                    blocked[lo] = 1;
+        int qn = 0;  // warp-uniform
+        for (int base = warp * 32; base < E; base += kResolveWarps * 32) {
+            const int e = base + lane;
+            bool need = false;
+            if (e < E) {
+                const uint64_t ed = edges[e];
+                if (!(ed & kPairDone)) {
+                    const int hi = (int)((ed >> 30) & 0x3fffffffu), lo = (int)(ed & 0x3fffffffu);
+                    if (state[lo] != 0) {
+                        edges[e] = ed | kPairDone;
+                    } else {
+                        const uint8_t sh = state[hi];
+                        if (sh == 1) {
+                            if (ed & kPairTrue)
+                                state[lo] = 2;
+                            else
+                                need = true;
+                        } else if (sh == 0) {
+                            blocked[lo] = 1;
+                        } else {
+                            edges[e] = ed | kPairDone;  // a suppressed box suppresses nothing
+                        }
+                    }
+                }
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, need);
+            if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = e;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) {
+                const int e2 = q[qn - 32 + lane];
+                __syncwarp();
+                clip(e2);
+                qn -= 32;
+                __syncwarp();
             }
         }
+        if (lane < qn) clip(q[lane]);
         __syncthreads();
         int und = 0;
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
@@ -715,7 +844,6 @@ __global__ void nms_prepare_kernel(const double *__restrict__ polys, const doubl
         *B.n_total = n;
         B.cl_count[0] = n;
         B.edge_count[0] = 0;
-        B.page_slack[0] = 0.0f;
     }
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
 #pragma unroll
@@ -738,7 +866,13 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     B.hot_count = bump.take<int32_t>(1);
     B.cl_count = bump.take<int32_t>(n_pages);
     B.edge_count = bump.take<int32_t>(n_pages);
-    B.page_slack = bump.take<float>(n_pages);
+    B.page_ext = bump.take<float>((size_t)n_pages * 8);
+    B.cell_cnt = bump.take<int32_t>((size_t)n_pages * kCells);
+    B.cell_off = bump.take<int32_t>((size_t)n_pages * (kCells + 1));
+    B.cell_cur = bump.take<int32_t>((size_t)n_pages * kCells);
+    B.cl_cell = bump.take<int32_t>(n_max);
+    B.sb_bbox = bump.take<float4>(n_max);
+    B.sb_id = bump.take<int32_t>(n_max);
     B.pos_page = bump.take<int32_t>(n_max);
     if (full) {
         B.keys = bump.take<uint64_t>(n_max);
@@ -825,15 +959,22 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
     lanms_clusters_kernel<<<n_pages, kResolveThreads, 0, st>>>(B.page_off, thr < 0 ? 1 : 0, B);
     MS_LAUNCH_CHECK(ctx);
     {
-        // cluster counts live on the device: size the a-tile grid for a typical page and stride beyond it
-        int gx = (cap_per_page + kTile - 1) / kTile;
-        if (gx > 128) gx = 128;
-        lanms_pairs_tiled_kernel<<<dim3(gx, n_pages), kTile, 0, st>>>(B.page_off, thr, B, flags);
+        int g = (int)((n_max + 255) / 256);
+        if (g > sms * 8) g = sms * 8;
+        nms_bin_count_kernel<<<g, 256, 0, st>>>(B.page_off, B.n_total, B);
+        MS_LAUNCH_CHECK(ctx);
+        nms_bin_scan_kernel<<<n_pages, kCells, 0, st>>>(B);
+        MS_LAUNCH_CHECK(ctx);
+        nms_bin_scatter_kernel<<<g, 256, 0, st>>>(B.page_off, B.n_total, B);
+        MS_LAUNCH_CHECK(ctx);
+        int gx = (cap_per_page + kBinThreads - 1) / kBinThreads;
+        if (gx > 64) gx = 64;
+        nms_pairs_binned_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B, flags);
         MS_LAUNCH_CHECK(ctx);
     }
     lanms_pairs_kernel<<<sms * 4, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 1);
     MS_LAUNCH_CHECK(ctx);
-    lanms_resolve_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B);
+    lanms_resolve_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, thr, B);
     MS_LAUNCH_CHECK(ctx);
     lanms_kept_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, counts_out);
     MS_LAUNCH_CHECK(ctx);
@@ -862,7 +1003,7 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
     MS_LAUNCH_CHECK(ctx);
     lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 0);
     MS_LAUNCH_CHECK(ctx);
-    lanms_resolve_kernel<<<1, 1024, 0, st>>>(B.page_off, B);
+    lanms_resolve_kernel<<<1, 1024, 0, st>>>(B.page_off, thr, B);
     MS_LAUNCH_CHECK(ctx);
     lanms_kept_kernel<<<1, 1024, 0, st>>>(B.page_off, B, k_out);
     MS_LAUNCH_CHECK(ctx);

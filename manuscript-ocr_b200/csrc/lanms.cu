@@ -77,6 +77,7 @@ struct LanmsBuffers {
     int32_t *kept_list;
     int32_t *irr_list;   // packed slots of the irregular clusters (all pages)
     int32_t *irr_count;
+    int32_t *und_flags;  // per page, 2 ints: "some box still undecided" of the current / previous round
     uint64_t *kept_key;  // per kept entry: descending-score sort key
 };
 
@@ -644,20 +645,32 @@ __global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int
 // ordered pair.
 constexpr int kResolveWarps = 32;
 
-__global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, double thr,
-                                                             LanmsBuffers B)
+__device__ __forceinline__ void cluster_sync_all()
 {
-    const int page = blockIdx.x;
+    // release / acquire at cluster scope: global-memory writes of every CTA of the cluster are visible afterwards
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// Launched as one thread-block cluster per page (1, 2, 4 or 8 CTAs): pages are few, so the cluster spreads one
+// page's pairs over several SMs; state lives in global memory and rounds are separated by cluster barriers.
+__global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, double thr,
+                                                             LanmsBuffers B, int32_t *__restrict__ und_flags)
+{
+    uint32_t crank, csize;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
+    asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
+    const int page = blockIdx.x / csize;
     const int p0 = page_off[page];
     const int C = B.cl_count[page];
     int E = B.edge_count[page];
     const int ecap = (page_off[page + 1] - p0) * kEdgeFactor;
     if (E > ecap) E = ecap;
     uint64_t *edges = B.edges + (size_t)p0 * kEdgeFactor;
-    uint8_t *state = B.state + p0;
-    uint8_t *blocked = B.blocked + p0;
+    volatile uint8_t *state = B.state + p0;
+    volatile uint8_t *blocked = B.blocked + p0;
+    volatile int32_t *und = und_flags + 2 * page;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    __shared__ int s_undecided;
+    const int gthread = crank * blockDim.x + threadIdx.x, gthreads = csize * blockDim.x;
     __shared__ int s_q[kResolveWarps][64];
     int *q = s_q[warp];
     double buf[4 * MS_MAXV];
@@ -674,16 +687,16 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
             edges[e] = ed | kPairDone;
     };
 
-    while (true) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) blocked[c] = 0;
-        if (threadIdx.x == 0) s_undecided = 0;
-        __syncthreads();
+    for (int round = 0;; round++) {
+        for (int c = gthread; c < C; c += gthreads) blocked[c] = 0;
+        if (gthread == 0) und[round & 1] = 0;
+        cluster_sync_all();
         int qn = 0;  // warp-uniform
-        for (int base = warp * 32; base < E; base += kResolveWarps * 32) {
+        for (int base = (crank * kResolveWarps + warp) * 32; base < E; base += csize * kResolveWarps * 32) {
             const int e = base + lane;
             bool need = false;
             if (e < E) {
-                const uint64_t ed = edges[e];
+                const uint64_t ed = edges[e];  // each pair word is only ever touched by this thread
                 if (!(ed & kPairDone)) {
                     const int hi = (int)((ed >> 30) & 0x3fffffffu), lo = (int)(ed & 0x3fffffffu);
                     if (state[lo] != 0) {
@@ -716,21 +729,42 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
             }
         }
         if (lane < qn) clip(q[lane]);
-        __syncthreads();
-        int und = 0;
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+        cluster_sync_all();
+        bool any_und = false;
+        for (int c = gthread; c < C; c += gthreads) {
             if (state[c] == 0) {
                 if (!blocked[c])
                     state[c] = 1;
                 else
-                    und = 1;
+                    any_und = true;
             }
         }
-        if (und) s_undecided = 1;
-        __syncthreads();
-        if (!s_undecided) break;
-        __syncthreads();
+        if (any_und) und[round & 1] = 1;
+        cluster_sync_all();
+        if (!und[round & 1]) break;
     }
+}
+
+static int launch_resolve(ms_ctx *ctx, int n_pages, const int32_t *page_off, double thr, const LanmsBuffers &B,
+                          int32_t *und_flags, cudaStream_t st)
+{
+    int cs = 1;
+    while (cs < 8 && n_pages * cs * 2 <= ctx->num_sms) cs *= 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(n_pages * cs), 1, 1);
+    cfg.blockDim = dim3(1024, 1, 1);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)cs;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MS_CUDA(cudaLaunchKernelEx(&cfg, lanms_resolve_kernel, page_off, thr, B, und_flags));
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
 }
 
 // position key of np.argsort(-scores, kind="stable"): ascending key == larger score first, NaN last, -0 == +0
@@ -899,6 +933,7 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     B.blocked = bump.take<uint8_t>(n_max);
     B.irr_list = bump.take<int32_t>(n_max);
     B.irr_count = bump.take<int32_t>(1);
+    B.und_flags = bump.take<int32_t>((size_t)n_pages * 2);
     B.kept_key = bump.take<uint64_t>(n_max);
     B.kept_list = bump.take<int32_t>(n_max);
     return bump.off;
@@ -974,8 +1009,10 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
     }
     lanms_pairs_kernel<<<sms * 4, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 1);
     MS_LAUNCH_CHECK(ctx);
-    lanms_resolve_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, thr, B);
-    MS_LAUNCH_CHECK(ctx);
+    {
+        int rc2 = launch_resolve(ctx, n_pages, B.page_off, thr, B, B.und_flags, st);
+        if (rc2 != MS_OK) return rc2;
+    }
     lanms_kept_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, counts_out);
     MS_LAUNCH_CHECK(ctx);
     {
@@ -1003,8 +1040,10 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
     MS_LAUNCH_CHECK(ctx);
     lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 0);
     MS_LAUNCH_CHECK(ctx);
-    lanms_resolve_kernel<<<1, 1024, 0, st>>>(B.page_off, thr, B);
-    MS_LAUNCH_CHECK(ctx);
+    {
+        int rc2 = launch_resolve(ctx, 1, B.page_off, thr, B, B.und_flags, st);
+        if (rc2 != MS_OK) return rc2;
+    }
     lanms_kept_kernel<<<1, 1024, 0, st>>>(B.page_off, B, k_out);
     MS_LAUNCH_CHECK(ctx);
     {

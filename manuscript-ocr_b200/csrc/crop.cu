@@ -28,7 +28,9 @@
 
 namespace {
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 192;   // 1 producer warp + 5 consumer warps; 4 CTAs per SM
+constexpr int kCtasPerSm = 4;
+constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
 constexpr int kSrcBuf = 24 * 1024;  // bytes per staging buffer (two per CTA)
 
 struct Plan {
@@ -209,8 +211,8 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 
 // resample one destination pixel (3 channels); `row(sy)` gives the address of source pixel (x=0) of row sy
 template <typename RowFn>
-__device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, const AxisEnt *ty, int dx, int dy,
-                                            RowFn row, unsigned char &o0, unsigned char &o1, unsigned char &o2)
+__device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, RowFn row, unsigned char &o0,
+                                            unsigned char &o1, unsigned char &o2)
 {
     if (p.interp == 0) {
         const unsigned char *s = row(dy) + dx * 3;
@@ -218,7 +220,7 @@ __device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, co
         o1 = s[1];
         o2 = s[2];
     } else if (p.interp == 1) {
-        const AxisEnt ex = tx[dx], ey = ty[dy];
+        const AxisEnt ex = linear_entry_x(dx, p.scale_x, p.w), ey = linear_entry_y(dy, p.scale_y, p.h);
         const unsigned char *S0 = row(ey.s0) + ex.s0 * 3;
         const unsigned char *S1 = row(ey.n) + ex.s0 * 3;
         const int a0 = ex.nfirst, a1 = ex.nmid, b0 = ey.nfirst, b1 = ey.nmid;
@@ -259,7 +261,8 @@ __device__ __forceinline__ void resample_px(const Plan &p, const AxisEnt *tx, co
             o2 = sat_u8(cv_round((float)s2 * inv));
         }
     } else {
-        const AxisEnt ex = tx[dx], ey = ty[dy];
+        // slow general path (tables longer than 4 taps, or rows not staged): entries computed per pixel
+        const AxisEnt ex = area_entry(dx, p.scale_x, p.w), ey = area_entry(dy, p.scale_y, p.h);
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
         for (int j = 0; j < ey.n; j++) {
             const float beta = area_weight(ey, j);
@@ -366,27 +369,22 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
 }
 
 // producer warp: the coefficient tables of one crop, 32 lanes
-__device__ __forceinline__ float4 tap_weights(const AxisEnt &e)
+// producer warp: the INTER_AREA coefficient tables of one crop for the 4-tap fast path, structure of arrays:
+// tab[0][i] = s0 | n << 16 (n = 0xffff when the entry has more than 4 taps), tab[1..4][i] = tap weights (0 beyond n).
+// x entries occupy [0, iw), y entries [iw, iw + ih) of every array.
+__device__ __forceinline__ void build_tables(const Plan &p, uint32_t *tab, int tab_n, int iw, int lane)
 {
-    return make_float4(0 < e.n ? area_weight(e, 0) : 0.f, 1 < e.n ? area_weight(e, 1) : 0.f,
-                       2 < e.n ? area_weight(e, 2) : 0.f, 3 < e.n ? area_weight(e, 3) : 0.f);
-}
-
-__device__ __forceinline__ void build_tables(const Plan &p, AxisEnt *tab_x, AxisEnt *tab_y, float4 *w_x, float4 *w_y,
-                                             int lane)
-{
-    if (!(p.ok && (p.interp == 1 || p.interp == 3))) return;
+    if (!(p.ok && p.staged && p.interp == 3)) return;
+    float *tw = reinterpret_cast<float *>(tab);
     for (int t = lane; t < p.nw + p.nh; t += 32) {
-        if (t < p.nw) {
-            const AxisEnt e = p.interp == 3 ? area_entry(t, p.scale_x, p.w) : linear_entry_x(t, p.scale_x, p.w);
-            tab_x[t] = e;
-            if (p.interp == 3) w_x[t] = tap_weights(e);
-        } else {
-            const int d = t - p.nw;
-            const AxisEnt e = p.interp == 3 ? area_entry(d, p.scale_y, p.h) : linear_entry_y(d, p.scale_y, p.h);
-            tab_y[d] = e;
-            if (p.interp == 3) w_y[d] = tap_weights(e);
-        }
+        const bool isx = t < p.nw;
+        const int d = isx ? t : t - p.nw;
+        const AxisEnt e = isx ? area_entry(d, p.scale_x, p.w) : area_entry(d, p.scale_y, p.h);
+        const int at = isx ? d : iw + d;
+        const bool fits = e.n <= 4 && e.s0 >= 0 && e.s0 < 65536;
+        tab[at] = fits ? ((uint32_t)e.s0 | ((uint32_t)e.n << 16)) : 0xffff0000u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) tw[(size_t)(1 + k) * tab_n + at] = k < e.n ? area_weight(e, k) : 0.f;
     }
 }
 
@@ -457,16 +455,15 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
 constexpr int kConsumerWarps = kThreads / 32 - 1;
 
 template <bool kWriteF32, bool kWriteU8>
-__global__ void __launch_bounds__(kThreads, 3)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
     crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w, const Plan *__restrict__ plans,
                            const int32_t *__restrict__ n_crops_dev, const int32_t *__restrict__ range,
                            int64_t crops_cap, int ih, int iw, float *__restrict__ batch,
                            uint8_t *__restrict__ canvas_out, int vec_ok)
 {
     extern __shared__ __align__(128) unsigned char smem[];
-    AxisEnt *tabs = reinterpret_cast<AxisEnt *>(smem + 2 * kSrcBuf);  // [2][iw + ih]
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + 2 * kSrcBuf);  // [2 stages][kTabWords][iw + ih]
     const int tab_n = iw + ih;
-    float4 *tabw = reinterpret_cast<float4 *>(tabs + 2 * (size_t)tab_n);  // [2][iw + ih] tap weights
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
     __shared__ Plan s_plan[2];
 
@@ -512,8 +509,7 @@ __global__ void __launch_bounds__(kThreads, 3)
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
             }
             if (lane == 0) s_plan[b] = p;
-            build_tables(p, tabs + (size_t)b * tab_n, tabs + (size_t)b * tab_n + iw, tabw + (size_t)b * tab_n,
-                         tabw + (size_t)b * tab_n + iw, lane);
+            build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane);
             __syncwarp();  // every lane's plan / table stores are ordered before lane 0's releasing arrive
             if (lane == 0) {
                 if (bytes)
@@ -537,7 +533,8 @@ __global__ void __launch_bounds__(kThreads, 3)
             float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
             uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
             const int nw = p.nw, nh = p.nh, y0 = p.y0;
-            const AxisEnt *tab_x = tabs + (size_t)b * tab_n, *tab_y = tab_x + iw;
+            const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
+            const float *tw = reinterpret_cast<const float *>(tab);
             const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
             const unsigned char *sbuf = smem + b * kSrcBuf;
             const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 15);
@@ -547,24 +544,26 @@ __global__ void __launch_bounds__(kThreads, 3)
             for (int t = ct; t < npx; t += kCT) {
                 const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
                 unsigned char o0, o1, o2;
-                int xs0 = 0, xn = 5, ys0 = 0, yn = 5;
+                uint32_t px = 0xffff0000u, py = 0xffff0000u;
                 if (p.staged && p.interp == 3) {
-                    xs0 = tab_x[dx].s0;
-                    xn = tab_x[dx].n;
-                    ys0 = tab_y[dy].s0;
-                    yn = tab_y[dy].n;
+                    px = tab[dx];
+                    py = tab[iw + dy];
                 }
-                if (xn <= 4 && yn <= 4) {
-                    resample_area4(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, xs0, ys0, yn,
-                                   tabw[(size_t)b * tab_n + dx], tabw[(size_t)b * tab_n + iw + dy], o0, o1, o2);
+                if ((px >> 16) <= 4u && (py >> 16) <= 4u) {
+                    const float4 wx = make_float4(tw[tab_n + dx], tw[2 * tab_n + dx], tw[3 * tab_n + dx],
+                                                  tw[4 * tab_n + dx]);
+                    const float4 wy = make_float4(tw[tab_n + iw + dy], tw[2 * tab_n + iw + dy], tw[3 * tab_n + iw + dy],
+                                                  tw[4 * tab_n + iw + dy]);
+                    resample_area4(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, (int)(px & 0xffffu),
+                                   (int)(py & 0xffffu), (int)(py >> 16), wx, wy, o0, o1, o2);
                 } else if (p.staged) {
                     auto row = [&](int sy) -> const unsigned char * {
                         return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
                     };
-                    resample_px(p, tab_x, tab_y, dx, dy, row, o0, o1, o2);
+                    resample_px(p, dx, dy, row, o0, o1, o2);
                 } else {
                     auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
-                    resample_px(p, tab_x, tab_y, dx, dy, row, o0, o1, o2);
+                    resample_px(p, dx, dy, row, o0, o1, o2);
                 }
                 const int at = (y0 + dy) * iw + dx;
                 if (kWriteF32) {
@@ -601,7 +600,7 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
         ms_set_error("crop: canvas %dx%d too large", out_h, out_w);
         return MS_ERR_INVALID;
     }
-    const size_t smem = 2 * (size_t)kSrcBuf + 2 * (size_t)(out_h + out_w) * (sizeof(AxisEnt) + sizeof(float4));
+    const size_t smem = 2 * (size_t)kSrcBuf + 2 * (size_t)(out_h + out_w) * kTabWords * sizeof(uint32_t);
     if (smem > 220 * 1024) {
         ms_set_error("crop: canvas %dx%d needs %zu bytes of shared memory", out_h, out_w, smem);
         return MS_ERR_INVALID;
@@ -618,8 +617,8 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
                                                  out_w, plans);
         MS_LAUNCH_CHECK(ctx);
     }
-    int per_sm = (int)((220 * 1024) / (smem + 1024));
-    if (per_sm > 3) per_sm = 3;
+    int per_sm = (int)((227 * 1024) / (smem + 1024 + 512));
+    if (per_sm > kCtasPerSm) per_sm = kCtasPerSm;
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->num_sms * per_sm;
     if (grid > crops_cap) grid = crops_cap;

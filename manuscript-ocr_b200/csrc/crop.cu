@@ -302,9 +302,10 @@ __device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
 // taps beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).  wx / wy are the tap weights the
 // producer precomputed from the same table entries.  Same products and the same summation order as resample_px's
 // general branch.
+template <bool kRowAligned>
 __device__ __forceinline__ void resample_area4(const unsigned char *smem_base, uint32_t buf_off, int pitch, uint32_t a0,
                                                uint32_t sstep, int xs0, int ys0, int yn, const float4 wx,
-                                               const float4 wy, unsigned char &o0, unsigned char &o1, unsigned char &o2)
+                                               const float4 wy, float &r0, float &r1, float &r2)
 {
     const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
     const float wyv[4] = {wy.x, wy.y, wy.z, wy.w};
@@ -314,7 +315,9 @@ __device__ __forceinline__ void resample_area4(const unsigned char *smem_base, u
         if (j < yn) {
             const float beta = wyv[j];
             const uint32_t sy = (uint32_t)(ys0 + j);
-            const uint32_t o = buf_off + sy * (uint32_t)pitch + ((a0 + sy * sstep) & 15u) + (uint32_t)xs0 * 3u;
+            // kRowAligned: the page stride is a multiple of 16, every row has the same misalignment a0
+            const uint32_t mis = kRowAligned ? a0 : ((a0 + sy * sstep) & 15u);
+            const uint32_t o = buf_off + sy * (uint32_t)pitch + mis + (uint32_t)xs0 * 3u;
             const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
             const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
             const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
@@ -343,9 +346,10 @@ __device__ __forceinline__ void resample_area4(const unsigned char *smem_base, u
             }
         }
     }
-    o0 = sat_u8(cv_round(sum0));
-    o1 = sat_u8(cv_round(sum1));
-    o2 = sat_u8(cv_round(sum2));
+    // cvRound (round half to even), kept as floats: the weights sum to 1 within rounding, so the value is in [0, 255]
+    r0 = rintf(sum0);
+    r1 = rintf(sum1);
+    r2 = rintf(sum2);
 }
 
 // plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
@@ -549,27 +553,40 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                     px = tab[dx];
                     py = tab[iw + dy];
                 }
+                float f0, f1, f2;
                 if ((px >> 16) <= 4u && (py >> 16) <= 4u) {
                     const float4 wx = make_float4(tw[tab_n + dx], tw[2 * tab_n + dx], tw[3 * tab_n + dx],
                                                   tw[4 * tab_n + dx]);
                     const float4 wy = make_float4(tw[tab_n + iw + dy], tw[2 * tab_n + iw + dy], tw[3 * tab_n + iw + dy],
                                                   tw[4 * tab_n + iw + dy]);
-                    resample_area4(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, (int)(px & 0xffffu),
-                                   (int)(py & 0xffffu), (int)(py >> 16), wx, wy, o0, o1, o2);
-                } else if (p.staged) {
-                    auto row = [&](int sy) -> const unsigned char * {
-                        return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
-                    };
-                    resample_px(p, dx, dy, row, o0, o1, o2);
+                    if (sstep == 0)
+                        resample_area4<true>(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, (int)(px & 0xffffu),
+                                             (int)(py & 0xffffu), (int)(py >> 16), wx, wy, f0, f1, f2);
+                    else
+                        resample_area4<false>(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, (int)(px & 0xffffu),
+                                              (int)(py & 0xffffu), (int)(py >> 16), wx, wy, f0, f1, f2);
+                    o0 = sat_u8((int)f0);  // only the uint8 canvas output uses these
+                    o1 = sat_u8((int)f1);
+                    o2 = sat_u8((int)f2);
                 } else {
-                    auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
-                    resample_px(p, dx, dy, row, o0, o1, o2);
+                    if (p.staged) {
+                        auto row = [&](int sy) -> const unsigned char * {
+                            return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
+                        };
+                        resample_px(p, dx, dy, row, o0, o1, o2);
+                    } else {
+                        auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
+                        resample_px(p, dx, dy, row, o0, o1, o2);
+                    }
+                    f0 = (float)o0;
+                    f1 = (float)o1;
+                    f2 = (float)o2;
                 }
                 const int at = (y0 + dy) * iw + dx;
                 if (kWriteF32) {
-                    __stcs(dstf + at, ((float)o0 - 127.5f) * inv);
-                    __stcs(dstf + plane + at, ((float)o1 - 127.5f) * inv);
-                    __stcs(dstf + 2 * plane + at, ((float)o2 - 127.5f) * inv);
+                    __stcs(dstf + at, (f0 - 127.5f) * inv);
+                    __stcs(dstf + plane + at, (f1 - 127.5f) * inv);
+                    __stcs(dstf + 2 * plane + at, (f2 - 127.5f) * inv);
                 }
                 if (kWriteU8) {
                     dstu[(size_t)at * 3] = o0;

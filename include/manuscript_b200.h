@@ -75,6 +75,12 @@ MS_API int ms_device_count(void);
 /* kernels launched by this context since creation (bench.py's gpu_launches) */
 MS_API int64_t ms_launch_count(const ms_ctx *ctx);
 
+/* NMS neighbour-pair capacity per candidate box (default 16).  The *_host entry points grow it (x4, up to 4096) and
+ * run again when a page overflows it; callers of the device entry points see MS_FLAG_EDGE_OVERFLOW in `flags` and
+ * raise it here before re-running. */
+MS_API int ms_set_edge_factor(ms_ctx *ctx, int pairs_per_candidate);
+MS_API int ms_get_edge_factor(const ms_ctx *ctx);
+
 /* Per-stage device timing of ms_page_batch (CUDA events recorded on the launch stream between the
  * stages; used by bench.py for the live roofline numbers).  Stages: 0 decode, 1 lanms, 2 expand+filters,
  * 3 word rects, 4 crop/resize/pad.  ms_stage_times waits for the recorded batches, writes the SUM of

@@ -93,6 +93,7 @@ extern "C" int ms_create(int device, ms_ctx **out)
     memset(c, 0, sizeof(*c));
     c->device = device;
     c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : MS_NUM_SMS_B200;
+    c->edge_factor = 16;
     int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (int i = 0; i < 2 && rc == MS_OK; i++)
@@ -134,6 +135,27 @@ extern "C" void ms_destroy(ms_ctx *ctx)
 }
 
 extern "C" int64_t ms_launch_count(const ms_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+extern "C" int ms_set_edge_factor(ms_ctx *ctx, int pairs_per_candidate)
+{
+    if (!ctx || pairs_per_candidate < 1 || pairs_per_candidate > 4096) {
+        ms_set_error("ms_set_edge_factor: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    ctx->edge_factor = pairs_per_candidate;
+    return MS_OK;
+}
+
+extern "C" int ms_get_edge_factor(const ms_ctx *ctx) { return ctx ? ctx->edge_factor : 0; }
+
+// dense candidates can exceed the NMS neighbour-pair capacity: the host entry points grow it and run again
+static bool grow_edge_factor(ms_ctx *ctx, int32_t flags)
+{
+    if (!(flags & MS_FLAG_EDGE_OVERFLOW) || (flags & (MS_FLAG_INDEX_ERROR | MS_FLAG_CAND_OVERFLOW))) return false;
+    if (ctx->edge_factor >= 4096) return false;
+    ctx->edge_factor *= 4;
+    return true;
+}
 
 extern "C" int ms_stage_timing(ms_ctx *ctx, int enable)
 {
@@ -270,7 +292,7 @@ extern "C" int ms_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, 
         ms_set_error("ms_lanms: bad arguments");
         return MS_ERR_INVALID;
     }
-    MS_TRY(ms_arena_reserve(ctx, msk_lanms_scratch(n_pages, cap_per_page)));
+    MS_TRY(ms_arena_reserve(ctx, msk_lanms_scratch(n_pages, cap_per_page, ctx->edge_factor)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     return msk_lanms(ctx, quads, counts, n_pages, cap_per_page, iou_threshold, quads_out, counts_out, flags, bump,
                      (cudaStream_t)stream);
@@ -336,11 +358,11 @@ static int cand_cap(int map_h, int map_w, int q)
     return (int)(c > 0x7fffffffLL ? 0x7fffffff : c);
 }
 
-static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap)
+static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap, int ef)
 {
     size_t fixed = 2 * al256((size_t)n_pages * cap_c * 9 * sizeof(float)) + 2 * al256((size_t)n_pages * sizeof(int32_t));
     size_t stage = msk_decode_scratch(n_pages, map_h, map_w, q);
-    size_t s2 = msk_lanms_scratch(n_pages, cap_c);
+    size_t s2 = msk_lanms_scratch(n_pages, cap_c, ef);
     if (s2 > stage) stage = s2;
     s2 = msk_east_boxes_scratch(n_pages, cap_c);
     if (s2 > stage) stage = s2;
@@ -365,7 +387,7 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
     const bool want_crops = pages_all != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
     const int q = p->quantization < 1 ? 1 : p->quantization;
     const int cap_c = cand_cap(map_h, map_w, q);
-    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0)));
+    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates
     float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
@@ -482,27 +504,32 @@ extern "C" int ms_lanms_host(ms_ctx *ctx, const float *boxes, int64_t n, double 
         return MS_ERR_INVALID;
     }
     const int cap = (int)n;
-    MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 36) + 1024));
-    MS_TRY(ms_arena_reserve(ctx, msk_lanms_scratch(1, cap)));
-    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
-    float *d_in = sb.take<float>((size_t)n * 9);
-    float *d_out = sb.take<float>((size_t)n * 9);
-    int32_t *d_cnt = sb.take<int32_t>(3);
-    if (!d_cnt) {
-        ms_set_error("ms_lanms_host: staging too small");
-        return MS_ERR_CAPACITY;
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    float *d_out = nullptr;
+    for (;;) {
+        MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 36) + 1024));
+        MS_TRY(ms_arena_reserve(ctx, msk_lanms_scratch(1, cap, ctx->edge_factor)));
+        ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+        float *d_in = sb.take<float>((size_t)n * 9);
+        d_out = sb.take<float>((size_t)n * 9);
+        int32_t *d_cnt = sb.take<int32_t>(3);
+        if (!d_cnt) {
+            ms_set_error("ms_lanms_host: staging too small");
+            return MS_ERR_CAPACITY;
+        }
+        cudaStream_t st = ctx->own_stream;
+        h[0] = cap;
+        h[1] = 0;
+        h[2] = 0;
+        MS_CUDA(cudaMemcpyAsync(d_cnt, h, 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+        MS_CUDA(cudaMemcpyAsync(d_in, boxes, (size_t)n * 36, cudaMemcpyHostToDevice, st));
+        ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+        MS_TRY(msk_lanms(ctx, d_in, d_cnt, 1, cap, iou_threshold, d_out, d_cnt + 1, d_cnt + 2, bump, st));
+        MS_CUDA(cudaMemcpyAsync(h + 4, d_cnt, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+        if (!grow_edge_factor(ctx, h[6])) break;
     }
     cudaStream_t st = ctx->own_stream;
-    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
-    h[0] = cap;
-    h[1] = 0;
-    h[2] = 0;
-    MS_CUDA(cudaMemcpyAsync(d_cnt, h, 3 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-    MS_CUDA(cudaMemcpyAsync(d_in, boxes, (size_t)n * 36, cudaMemcpyHostToDevice, st));
-    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
-    MS_TRY(msk_lanms(ctx, d_in, d_cnt, 1, cap, iou_threshold, d_out, d_cnt + 1, d_cnt + 2, bump, st));
-    MS_CUDA(cudaMemcpyAsync(h + 4, d_cnt, 3 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    MS_CUDA(cudaStreamSynchronize(st));
     MS_TRY(flags_to_rc(h[6], "locality_aware_nms"));
     const int m = h[5];
     if (m > 0) {
@@ -528,7 +555,7 @@ extern "C" int ms_standard_nms_host(ms_ctx *ctx, const double *polys, const doub
         return MS_ERR_INVALID;
     }
     MS_TRY(ms_stage_reserve(ctx, al256((size_t)n * 64) + al256((size_t)n * 8) + al256((size_t)n * 4) + 1024));
-    MS_TRY(ms_arena_reserve(ctx, msk_standard_nms_scratch((int)n)));
+    MS_TRY(ms_arena_reserve(ctx, msk_standard_nms_scratch((int)n, ctx->edge_factor)));
     ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
     double *d_p = sb.take<double>((size_t)n * 8);
     double *d_s = sb.take<double>((size_t)n);
@@ -547,6 +574,7 @@ extern "C" int ms_standard_nms_host(ms_ctx *ctx, const double *polys, const doub
     int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
     MS_CUDA(cudaMemcpyAsync(h, d_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
+    if (grow_edge_factor(ctx, h[1])) return ms_standard_nms_host(ctx, polys, scores, n, iou_threshold, keep_idx, k_out);
     MS_TRY(flags_to_rc(h[1], "standard_nms"));
     const int k = h[0];
     if (k > 0) {
@@ -823,6 +851,10 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     MS_CUDA(cudaStreamSynchronize(st));
     int32_t all = 0;
     for (int i = 0; i < n_pages; i++) all |= flags[i];
+    if (grow_edge_factor(ctx, all))
+        return ms_page_batch_host(ctx, score, geo, pages, n_pages, map_h, map_w, img_h, img_w, p, min_text_size, out_h,
+                                  out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, batch_f32_host,
+                                  batch_dev_out, flags);
     MS_TRY(flags_to_rc(all, "page_batch"));
     if (want_crops) {
         int64_t nc = *n_crops;

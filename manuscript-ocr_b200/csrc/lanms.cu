@@ -33,7 +33,8 @@
 
 namespace {
 
-constexpr int kEdgeFactor = 16;  // neighbour-pair capacity per candidate (overflow -> flag)
+// neighbour-pair capacity per candidate is LanmsBuffers::ef (ms_ctx::edge_factor; overflow -> MS_FLAG_EDGE_OVERFLOW,
+// the host entry points then retry with a larger factor)
 constexpr int kGrid = 32;        // uniform grid per page for the neighbour search
 constexpr int kCells = kGrid * kGrid;
 // neighbour pair word: lo in bits 0..29, hi (higher NMS priority) in bits 30..59
@@ -77,6 +78,9 @@ struct LanmsBuffers {
     int32_t *kept_list;
     int32_t *irr_list;   // packed slots of the irregular clusters (all pages)
     int32_t *irr_count;
+    int ef;              // neighbour-pair capacity per candidate
+    int32_t *page_redo;  // per page: a cluster had more than kMaxHits neighbours -> exact two-pass rebuild
+    int32_t *nb_cnt;     // two-pass rebuild: neighbours per cluster, then their exclusive offsets
     int32_t *und_flags;  // per page, 2 ints: "some box still undecided" of the current / previous round
     uint64_t *kept_key;  // per kept entry: descending-score sort key
 };
@@ -146,7 +150,8 @@ __device__ __forceinline__ bool quad_regular_bbox(const double *p, float4 &bb)
 
 // ---- 0. page offsets ---------------------------------------------------------------------------------
 __global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_pages, int32_t *page_off,
-                                     int32_t *n_total, int32_t *hot_count, int32_t *edge_count, int32_t *irr_count)
+                                     int32_t *n_total, int32_t *hot_count, int32_t *edge_count, int32_t *irr_count,
+                                     int32_t *page_redo)
 {
     // one thread: n_pages is small (<= a few thousand)
     if (threadIdx.x == 0 && blockIdx.x == 0) {
@@ -155,6 +160,7 @@ __global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_p
             page_off[p] = run;
             run += counts[p];
             edge_count[p] = 0;
+            page_redo[p] = 0;
         }
         page_off[n_pages] = run;
         *n_total = run;
@@ -439,7 +445,7 @@ __device__ __forceinline__ void push_pair(int hi, int lo, uint64_t flag, int p0,
 {
     int e = atomicAdd(B.edge_count + page, 1);
     if (e < edge_cap)
-        B.edges[(size_t)p0 * kEdgeFactor + e] = flag | ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
+        B.edges[(size_t)p0 * B.ef + e] = flag | ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
     else
         atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
 }
@@ -500,7 +506,7 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
                 int pg = qpage[idx];
                 __syncwarp();
                 eval_pair(pr.x, pr.y, page_off[pg], pg, thr, B,
-                          (page_off[pg + 1] - page_off[pg]) * kEdgeFactor, flags, buf);
+                          (page_off[pg + 1] - page_off[pg]) * B.ef, flags, buf);
                 qn -= 32;
                 __syncwarp();
             }
@@ -509,7 +515,7 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
     if (lane < qn) {
         int2 pr = q[lane];
         int pg = qpage[lane];
-        eval_pair(pr.x, pr.y, page_off[pg], pg, thr, B, (page_off[pg + 1] - page_off[pg]) * kEdgeFactor, flags,
+        eval_pair(pr.x, pr.y, page_off[pg], pg, thr, B, (page_off[pg + 1] - page_off[pg]) * B.ef, flags,
                   buf);
     }
 }
@@ -574,7 +580,7 @@ __global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int
     const int C = B.cl_count[page];
     const float *ext = B.page_ext + (size_t)page * 8;
     const int32_t *coff = B.cell_off + (size_t)page * (kCells + 1);
-    const int edge_cap = (page_off[page + 1] - p0) * kEdgeFactor;
+    const int edge_cap = (page_off[page + 1] - p0) * B.ef;
     const float ox = ext[0], oy = ext[1], sx = ext[2], sy = ext[3], mw = ext[4], mh = ext[5];
     __shared__ int s_warp[kBinThreads / 32 + 1];
     __shared__ int s_base;
@@ -625,15 +631,98 @@ __global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int
         }
         __syncthreads();
         int at = s_base + s_warp[warp] + inc - cnt;
-        if (over || (cnt > 0 && at + cnt > edge_cap)) atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
+        if (over) atomicOr(B.page_redo + page, 1);
+        if (cnt > 0 && at + cnt > edge_cap) atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
         for (int k = 0; k < cnt; k++, at++) {
             if (at >= edge_cap) break;
             const int b = hits[k];
             // cl_orig == cluster index for LANMS clusters; both are regular here
             const bool a_first = prio_before(sa, a, B.cl_score[(size_t)p0 + b], b);
             const int hi = a_first ? a : b, lo = a_first ? b : a;
-            B.edges[(size_t)p0 * kEdgeFactor + at] = ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
+            B.edges[(size_t)p0 * B.ef + at] = ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
         }
+    }
+}
+
+// Exact rebuild of a page's neighbour pairs when some cluster has more than kMaxHits of them (very dense
+// candidates, e.g. a score threshold below the background): count, scan, fill.  Pages that did not overflow
+// return at once.
+template <typename F>
+__device__ __forceinline__ void walk_neighbours(const LanmsBuffers &B, int p0, int page, int a, F f)
+{
+    const float *ext = B.page_ext + (size_t)page * 8;
+    const int32_t *coff = B.cell_off + (size_t)page * (kCells + 1);
+    const float4 ba = B.cl_bbox[(size_t)p0 + a];
+    const int cx0 = cell_coord(ba.x - ext[4], ext[0], ext[2]), cx1 = cell_coord(ba.z, ext[0], ext[2]);
+    const int cy0 = cell_coord(ba.y - ext[5], ext[1], ext[3]), cy1 = cell_coord(ba.w, ext[1], ext[3]);
+    for (int cy = cy0; cy <= cy1; cy++) {
+        const int pos1 = coff[cy * kGrid + cx1 + 1];
+        for (int pos = coff[cy * kGrid + cx0]; pos < pos1; pos++) {
+            const int b = B.sb_id[(size_t)p0 + pos];
+            if (b <= a) continue;
+            const float4 o = B.sb_bbox[(size_t)p0 + pos];
+            if (o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y) continue;
+            f(b);
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads) nms_redo_count_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
+{
+    const int page = blockIdx.y;
+    if (!B.page_redo[page]) return;
+    const int p0 = page_off[page];
+    const int C = B.cl_count[page];
+    for (int a = blockIdx.x * kBinThreads + threadIdx.x; a < C; a += gridDim.x * kBinThreads) {
+        int cnt = 0;
+        if (B.cl_irr[(size_t)p0 + a] == 0) walk_neighbours(B, p0, page, a, [&](int) { cnt++; });
+        B.nb_cnt[(size_t)p0 + a] = cnt;
+    }
+}
+
+__global__ void __launch_bounds__(1024) nms_redo_scan_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B,
+                                                             int32_t *flags)
+{
+    const int page = blockIdx.x;
+    if (!B.page_redo[page]) return;
+    const int p0 = page_off[page];
+    const int C = B.cl_count[page];
+    __shared__ int s_warp[33];
+    long long run = 0;
+    for (int base = 0; base < C; base += 1024) {
+        const int c = base + threadIdx.x;
+        const int v = c < C ? B.nb_cnt[(size_t)p0 + c] : 0;
+        int total;
+        const int off = block_excl_scan_1024(v, s_warp, total);
+        if (c < C) B.nb_cnt[(size_t)p0 + c] = (int)min(run + off, (long long)0x7fffffff);
+        run += total;
+    }
+    if (threadIdx.x == 0) {
+        const long long cap = (long long)(page_off[page + 1] - p0) * B.ef;
+        if (run > cap) atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
+        B.edge_count[page] = (int)min(run, cap);
+    }
+}
+
+__global__ void __launch_bounds__(kBinThreads) nms_redo_fill_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
+{
+    const int page = blockIdx.y;
+    if (!B.page_redo[page]) return;
+    const int p0 = page_off[page];
+    const int C = B.cl_count[page];
+    const long long cap = (long long)(page_off[page + 1] - p0) * B.ef;
+    for (int a = blockIdx.x * kBinThreads + threadIdx.x; a < C; a += gridDim.x * kBinThreads) {
+        if (B.cl_irr[(size_t)p0 + a]) continue;
+        long long at = B.nb_cnt[(size_t)p0 + a];
+        const double sa = B.cl_score[(size_t)p0 + a];
+        walk_neighbours(B, p0, page, a, [&](int b) {
+            if (at < cap) {
+                const bool a_first = prio_before(sa, a, B.cl_score[(size_t)p0 + b], b);
+                const int hi = a_first ? a : b, lo = a_first ? b : a;
+                B.edges[(size_t)p0 * B.ef + at] = ((uint64_t)(uint32_t)hi << 30) | (uint64_t)(uint32_t)lo;
+            }
+            at++;
+        });
     }
 }
 
@@ -663,9 +752,9 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
     const int p0 = page_off[page];
     const int C = B.cl_count[page];
     int E = B.edge_count[page];
-    const int ecap = (page_off[page + 1] - p0) * kEdgeFactor;
+    const int ecap = (page_off[page + 1] - p0) * B.ef;
     if (E > ecap) E = ecap;
-    uint64_t *edges = B.edges + (size_t)p0 * kEdgeFactor;
+    uint64_t *edges = B.edges + (size_t)p0 * B.ef;
     volatile uint8_t *state = B.state + p0;
     volatile uint8_t *blocked = B.blocked + p0;
     volatile int32_t *und = und_flags + 2 * page;
@@ -892,7 +981,7 @@ __global__ void nms_prepare_kernel(const double *__restrict__ polys, const doubl
     }
 }
 
-size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool full)
+size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool full, int ef)
 {
     B = LanmsBuffers{};
     B.page_off = bump.take<int32_t>(n_pages + 1);
@@ -928,7 +1017,10 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     B.cl_bbox = bump.take<float4>(n_max);
     B.cl_irr = bump.take<uint8_t>(n_max);
     B.cl_orig = bump.take<int32_t>(n_max);
-    B.edges = bump.take<uint64_t>(n_max * kEdgeFactor);
+    B.ef = ef;
+    B.edges = bump.take<uint64_t>(n_max * (size_t)ef);
+    B.page_redo = bump.take<int32_t>(n_pages);
+    B.nb_cnt = bump.take<int32_t>(n_max);
     B.state = bump.take<uint8_t>(n_max);
     B.blocked = bump.take<uint8_t>(n_max);
     B.irr_list = bump.take<int32_t>(n_max);
@@ -941,20 +1033,20 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
 
 }  // namespace
 
-size_t msk_lanms_scratch(int n_pages, int cap_per_page)
+size_t msk_lanms_scratch(int n_pages, int cap_per_page, int ef)
 {
     ms_bump probe{nullptr, 0, 0};
     LanmsBuffers B;
     size_t n_max = (size_t)n_pages * cap_per_page;
-    size_t core = carve(probe, B, n_pages, n_max, true);
+    size_t core = carve(probe, B, n_pages, n_max, true, ef);
     return core + msk_sort_scratch((int64_t)n_max) + 4096;
 }
 
-size_t msk_standard_nms_scratch(int n)
+size_t msk_standard_nms_scratch(int n, int ef)
 {
     ms_bump probe{nullptr, 0, 0};
     LanmsBuffers B;
-    return carve(probe, B, 1, (size_t)n, false) + 4096;
+    return carve(probe, B, 1, (size_t)n, false, ef) + 4096;
 }
 
 int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page, double thr,
@@ -967,14 +1059,14 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         return MS_ERR_INVALID;
     }
     LanmsBuffers B;
-    carve(bump, B, n_pages, n_max, true);
+    carve(bump, B, n_pages, n_max, true, ctx->edge_factor);
     if (!B.kept_list) {
         ms_set_error("lanms: scratch too small");
         return MS_ERR_CAPACITY;
     }
     const int sms = ctx->num_sms;
     lanms_offsets_kernel<<<1, 32, 0, st>>>(counts, n_pages, B.page_off, B.n_total, B.hot_count, B.edge_count,
-                                           B.irr_count);
+                                           B.irr_count, B.page_redo);
     MS_LAUNCH_CHECK(ctx);
     {
         size_t threads = n_max;
@@ -1006,6 +1098,12 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         if (gx > 64) gx = 64;
         nms_pairs_binned_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B, flags);
         MS_LAUNCH_CHECK(ctx);
+        nms_redo_count_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B);
+        MS_LAUNCH_CHECK(ctx);
+        nms_redo_scan_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, flags);
+        MS_LAUNCH_CHECK(ctx);
+        nms_redo_fill_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B);
+        MS_LAUNCH_CHECK(ctx);
     }
     lanms_pairs_kernel<<<sms * 4, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 1);
     MS_LAUNCH_CHECK(ctx);
@@ -1030,7 +1128,7 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
 {
     if (n <= 0) return MS_OK;
     LanmsBuffers B;
-    carve(bump, B, 1, (size_t)n, false);
+    carve(bump, B, 1, (size_t)n, false, ctx->edge_factor);
     if (!B.kept_list) {
         ms_set_error("standard_nms: scratch too small");
         return MS_ERR_CAPACITY;

@@ -23,6 +23,7 @@ struct ms_ctx {
     char *stage;
     size_t stage_bytes;
     // ms_stage_timing: ring of per-batch event sets
+    int edge_factor;              // NMS neighbour-pair capacity per candidate (grown by the host entry points)
     cudaStream_t copy_stream;     // H2D stream of the pipelined host entry point
     cudaEvent_t chunk_ev[2];
     int timing;
@@ -83,10 +84,10 @@ size_t msk_sort_scratch(int64_t n_max);
 // lanms.cu
 int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
               double thr, float *quads_out, int32_t *counts_out, int32_t *flags, ms_bump bump, cudaStream_t st);
-size_t msk_lanms_scratch(int n_pages, int cap_per_page);
+size_t msk_lanms_scratch(int n_pages, int cap_per_page, int ef);
 int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int n, double thr,
                      int32_t *keep_idx, int32_t *k_out, int32_t *flags, ms_bump bump, cudaStream_t st);
-size_t msk_standard_nms_scratch(int n);
+size_t msk_standard_nms_scratch(int n, int ef);
 int msk_polygon_iou(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double *iou, cudaStream_t st);
 // boxes.cu
 int msk_expand(ms_ctx *ctx, const float *quads, int64_t n, double ew, double eh, float *out, cudaStream_t st);

@@ -71,6 +71,8 @@ SIGNATURES = {
     "ms_destroy": (None, [_vp]),
     "ms_device_count": (_i, []),
     "ms_launch_count": (_i64, [_vp]),
+    "ms_set_edge_factor": (_i, [_vp, _i]),
+    "ms_get_edge_factor": (_i, [_vp]),
     "ms_stage_timing": (_i, [_vp, _i]),
     "ms_stage_times": (_i, [_vp, C.POINTER(_d)]),
     "ms_decode_quads_host": (_i, [_vp, _vp, _vp, _i, _i, _f, _d, _i, _vp, _i64, C.POINTER(_i64)]),
@@ -153,6 +155,22 @@ class Context:
     @property
     def launches(self):
         return int(self.lib.ms_launch_count(self.handle))
+
+    @property
+    def edge_factor(self):
+        return int(self.lib.ms_get_edge_factor(self.handle))
+
+    @edge_factor.setter
+    def edge_factor(self, k):
+        check(self.lib.ms_set_edge_factor(self.handle, int(k)))
+
+    def grow_edge_factor(self):
+        """x4 (the policy of the *_host entry points); False once the limit is reached."""
+        k = self.edge_factor
+        if k >= 4096:
+            return False
+        self.edge_factor = min(4096, k * 4)
+        return True
 
     STAGES = ("decode", "lanms", "east_boxes", "word_rects", "crop")
 

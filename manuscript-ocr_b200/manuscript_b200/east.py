@@ -13,7 +13,7 @@ from pathlib import Path
 
 import numpy as np
 
-from ._cabi import EastParams, check
+from ._cabi import MS_FLAG_EDGE_OVERFLOW, EastParams, check
 from .batch import PageBatch, _raise_for_flags
 from .reading_order import reorder_words
 from .types import Block, Page, Word
@@ -106,15 +106,21 @@ class EAST:
         meta[4] = int(orig_hw[0])
         meta[5] = int(orig_hw[1])
         p = r.params
-        with torch.cuda.device(self.device):
-            check(lib.ms_decode_quads(ctx.handle, s.data_ptr(), g.data_ptr(), 1, H, W, p.score_thresh, p.scale,
-                                      p.quantization, cand.data_ptr(), cap, meta[0:].data_ptr(), meta[3:].data_ptr(),
-                                      C.c_void_p(stream)))
-            check(lib.ms_lanms(ctx.handle, cand.data_ptr(), meta[0:].data_ptr(), 1, cap, p.iou_threshold,
-                               kept.data_ptr(), meta[1:].data_ptr(), meta[3:].data_ptr(), C.c_void_p(stream)))
-            check(lib.ms_east_boxes(ctx.handle, kept.data_ptr(), meta[1:].data_ptr(), 1, cap, C.byref(p),
-                                    meta[4:].data_ptr(), out.data_ptr(), meta[2:].data_ptr(), C.c_void_p(stream)))
-        m = meta.cpu().numpy()
+        while True:
+            meta[:4] = 0
+            with torch.cuda.device(self.device):
+                check(lib.ms_decode_quads(ctx.handle, s.data_ptr(), g.data_ptr(), 1, H, W, p.score_thresh, p.scale,
+                                          p.quantization, cand.data_ptr(), cap, meta[0:].data_ptr(),
+                                          meta[3:].data_ptr(), C.c_void_p(stream)))
+                check(lib.ms_lanms(ctx.handle, cand.data_ptr(), meta[0:].data_ptr(), 1, cap, p.iou_threshold,
+                                   kept.data_ptr(), meta[1:].data_ptr(), meta[3:].data_ptr(), C.c_void_p(stream)))
+                check(lib.ms_east_boxes(ctx.handle, kept.data_ptr(), meta[1:].data_ptr(), 1, cap, C.byref(p),
+                                        meta[4:].data_ptr(), out.data_ptr(), meta[2:].data_ptr(), C.c_void_p(stream)))
+            m = meta.cpu().numpy()
+            # very dense candidates: grow the NMS neighbour-pair capacity and run again
+            if (int(m[3]) & MS_FLAG_EDGE_OVERFLOW) and not (int(m[3]) & 3) and ctx.grow_edge_factor():
+                continue
+            break
         _raise_for_flags(m[3:4])
         return out[: int(m[2])].cpu().numpy()
 

@@ -110,3 +110,40 @@ def test_full_size_properties(torch_cuda):
 def rows(a):
     a = np.ascontiguousarray(a)
     return a[np.lexsort(a.T[::-1])]
+
+
+def test_stress_4096_page(torch_cuda):
+    """BASELINE configs[3]: one 4096x4096 page, ~10k quads, ~75k candidates (NMS-bound).  Decode is compared with
+    the oracle bit for bit; NMS through its properties (the O(n^2) oracle would take minutes): one box per word,
+    descending scores, idempotent, every kept box overlaps exactly one ground-truth word."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    page, words = 4096, 10000
+    score, geo, gt = synthdata.make_maps(3, page, words)
+    quads = mb.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    np.testing.assert_array_equal(quads, cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2))
+    assert len(quads) > 50000
+    nms = mb.locality_aware_nms(quads, 0.2)
+    assert len(nms) == words and (np.diff(nms[:, 8]) <= 0).all()
+    np.testing.assert_array_equal(rows(mb.locality_aware_nms(nms, 0.2)), rows(nms))
+    # each kept quad sits on its own word: nearest ground-truth centre is unique
+    cen = nms[:, :8].reshape(-1, 4, 2).mean(axis=1)
+    gcen = gt.mean(axis=1)
+    order = np.argsort(gcen[:, 1] * 8192 + gcen[:, 0])
+    # brute force in chunks
+    owner = np.empty(len(cen), np.int64)
+    for i in range(0, len(cen), 1000):
+        d = ((cen[i:i + 1000, None, :] - gcen[None, :, :]) ** 2).sum(-1)
+        owner[i:i + 1000] = d.argmin(1)
+    assert len(np.unique(owner)) == words
+    # the same page through the batched path
+    imgs = synthdata.make_page_image(3, page)[None]
+    runner = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page), cap_boxes=16384)
+    res = runner.run(torch.from_numpy(score[None]).cuda(), torch.from_numpy(geo[None]).cuda(),
+                     torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    assert int(res.flags.cpu()[0]) == 0 and int(res.box_counts.cpu()[0]) == words
+    want = cpu.east_postprocess(nms, (page, page), target_size=page)
+    np.testing.assert_array_equal(res.boxes[0, :words].cpu().numpy(), want)
+    del order

@@ -287,3 +287,23 @@ def test_errors_are_loud(ops):
         ops.decode_quads_from_maps(np.zeros((4, 4), np.float32), np.zeros((7, 4, 4), np.float32), 0.5, 4.0)
     with pytest.raises(ValueError):
         ops.locality_aware_nms(np.zeros((3, 8), np.float32), 0.2)
+
+
+def test_lanms_dense_candidates(ops):
+    """Far more overlapping neighbours per box than the default pair capacity (16 per candidate, 32 per cluster):
+    the exact two-pass rebuild and the capacity retry of the host entry points must give the oracle's answer."""
+    rng = np.random.default_rng(17)
+    n = 3000
+    rect = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    c = rng.uniform(0, 260, (n, 1, 2))
+    quads = c + rect * rng.uniform(15, 45, (n, 1, 2))
+    boxes = np.concatenate([quads.reshape(n, 8), rng.uniform(0.3, 1, (n, 1))], axis=1).astype(np.float32)
+    for thr in (0.2, 0.6):
+        np.testing.assert_array_equal(ops.locality_aware_nms(boxes, thr), cpu.locality_aware_nms(boxes, thr))
+    # every quantisation cell a candidate (score threshold below the background, SURVEY 8c): background geometry is
+    # zero there, so most quads are degenerate points -- the irregular all-pairs path
+    score, geo, _ = synthdata.make_maps(7, 512, 80)
+    q = cpu.decode_quads_from_maps(score, geo, -1.0, 4.0, 2)
+    assert len(q) == 64 * 64
+    np.testing.assert_array_equal(ops.decode_quads_from_maps(score, geo, -1.0, 4.0, 2), q)
+    np.testing.assert_array_equal(ops.locality_aware_nms(q, 0.2), cpu.locality_aware_nms(q, 0.2))

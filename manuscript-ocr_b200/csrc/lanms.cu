@@ -44,7 +44,7 @@ constexpr uint64_t kPairDone = 1ull << 63;  // nothing left to learn from this p
 struct LanmsBuffers {
     int32_t *page_off;   // n_pages+1 exclusive offsets of candidate counts (packed space)
     int32_t *n_total;    // == page_off[n_pages]
-    uint64_t *keys, *keys_tmp;
+    uint32_t *keys, *keys_tmp;  // orderable(x0) per candidate, sorted per page
     uint32_t *vals, *vals_tmp;
     double *sq;          // sorted candidate polys, 8 doubles each
     float *ss;           // sorted candidate scores (f32 exact)
@@ -169,23 +169,24 @@ __global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_p
     }
 }
 
-// ---- 1. sort keys (page | orderable x0), values = strided source row ---------------------------------
+// ---- 1. sort keys (orderable x0; pages are sorted separately), values = strided source row ---------------------------------
 __global__ void lanms_keys_kernel(const float *__restrict__ quads, const int32_t *__restrict__ counts,
                                   const int32_t *__restrict__ page_off, int n_pages, int cap,
-                                  uint64_t *__restrict__ keys, uint32_t *__restrict__ vals)
+                                  uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
+                                  int32_t *__restrict__ pos_page)
 {
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p = (int)(g / cap), i = (int)(g % cap);
     if (p >= n_pages || i >= counts[p]) return;
     size_t row = (size_t)p * cap + i;
     int dst = page_off[p] + i;
-    keys[dst] = ((uint64_t)p << 32) | ms_orderable_f32(quads[row * 9]);
+    keys[dst] = ms_orderable_f32(quads[row * 9]);
     vals[dst] = (uint32_t)row;
+    pos_page[dst] = p;
 }
 
 // ---- 2. gather into sorted order (f64) + hot bits -----------------------------------------------------
 __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__restrict__ quads,
-                                                               const uint64_t *__restrict__ keys,
                                                                const uint32_t *__restrict__ vals,
                                                                const int32_t *__restrict__ page_off,
                                                                const int32_t *__restrict__ n_total, double thr,
@@ -194,7 +195,7 @@ __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__re
     const int n = *n_total;
     double buf[4 * MS_MAXV];
     for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        int page = (int)(keys[s] >> 32);
+        int page = B.pos_page[s];
         const float *row = quads + (size_t)vals[s] * 9;
         double me[8];
 #pragma unroll
@@ -203,7 +204,6 @@ __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__re
 #pragma unroll
         for (int k = 0; k < 4; k++) dst[k] = make_double2(me[2 * k], me[2 * k + 1]);
         B.ss[s] = row[8];
-        B.pos_page[s] = page;
         B.mflag[s] = 0;
         bool is_hot = false;
         if (s > page_off[page]) {
@@ -890,15 +890,76 @@ __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restr
     if (threadIdx.x == 0) counts_out[page] = run_base;
 }
 
+// Pages with at most kSortMax kept boxes: order them with a bitonic sort in shared memory.  LANMS cluster scores are
+// float32 values (a max over float32 inputs), so (descending-score key, cluster index) packs into one 64-bit key
+// whose ascending order is exactly np.argsort(-scores, kind="stable").  Larger pages are left to the ranking kernel.
+constexpr int kSortMax = 4096;
+
+__global__ void __launch_bounds__(1024) lanms_sort_emit_kernel(const int32_t *__restrict__ page_off, int cap,
+                                                               LanmsBuffers B, float *__restrict__ out,
+                                                               const int32_t *__restrict__ counts_out,
+                                                               int32_t *__restrict__ rank_needed)
+{
+    const int page = blockIdx.x;
+    const int p0 = page_off[page];
+    const int K = counts_out[page];
+    if (K > kSortMax) {
+        if (threadIdx.x == 0) rank_needed[page] = 1;
+        return;
+    }
+    if (threadIdx.x == 0) rank_needed[page] = 0;
+    __shared__ uint64_t s_key[kSortMax];
+    const int32_t *kept = B.kept_list + p0;
+    int n = 1;
+    while (n < K) n <<= 1;
+    for (int i = threadIdx.x; i < n; i += 1024) {
+        uint64_t key = ~0ull;
+        if (i < K) {
+            const int c = kept[i];
+            const float sc = (float)B.cl_score[p0 + c];
+            const uint32_t k32 = (sc != sc) ? 0xFFFFFFFFu : ~ms_orderable_f32(sc);
+            key = ((uint64_t)k32 << 32) | (uint32_t)c;
+        }
+        s_key[i] = key;
+    }
+    __syncthreads();
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += 1024) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a = s_key[i], b = s_key[ixj];
+                    const bool up = (i & k) == 0;
+                    if ((a > b) == up) {
+                        s_key[i] = b;
+                        s_key[ixj] = a;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int r = threadIdx.x; r < K; r += 1024) {
+        const int c = (int)(s_key[r] & 0xffffffffu);
+        float *row = out + ((size_t)page * cap + r) * 9;
+        const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
+        row[8] = (float)B.cl_score[p0 + c];
+    }
+}
+
 constexpr int kRankThreads = 256;
 
 // rank of every kept cluster among the kept ones of its page (np.argsort(-scores, kind="stable") position)
 __global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t *__restrict__ page_off, int cap,
                                                                   LanmsBuffers B, float *__restrict__ out,
                                                                   const int32_t *__restrict__ counts_out,
-                                                                  int32_t *__restrict__ keep_idx_out)
+                                                                  int32_t *__restrict__ keep_idx_out,
+                                                                  const int32_t *__restrict__ rank_needed)
 {
     const int page = blockIdx.y;
+    if (rank_needed && !rank_needed[page]) return;
     const int p0 = page_off[page];
     const int K = counts_out[page];
     const int32_t *kept = B.kept_list + p0;
@@ -998,8 +1059,8 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     B.sb_id = bump.take<int32_t>(n_max);
     B.pos_page = bump.take<int32_t>(n_max);
     if (full) {
-        B.keys = bump.take<uint64_t>(n_max);
-        B.keys_tmp = bump.take<uint64_t>(n_max);
+        B.keys = bump.take<uint32_t>(n_max);
+        B.keys_tmp = bump.take<uint32_t>(n_max);
         B.vals = bump.take<uint32_t>(n_max);
         B.vals_tmp = bump.take<uint32_t>(n_max);
         B.sq = bump.take<double>(n_max * 8);
@@ -1039,7 +1100,7 @@ size_t msk_lanms_scratch(int n_pages, int cap_per_page, int ef)
     LanmsBuffers B;
     size_t n_max = (size_t)n_pages * cap_per_page;
     size_t core = carve(probe, B, n_pages, n_max, true, ef);
-    return core + msk_sort_scratch((int64_t)n_max) + 4096;
+    return core + msk_sort_pages_scratch(n_pages, cap_per_page) + 4096;
 }
 
 size_t msk_standard_nms_scratch(int n, int ef)
@@ -1071,15 +1132,13 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
     {
         size_t threads = n_max;
         int grid = (int)((threads + 255) / 256);
-        lanms_keys_kernel<<<grid, 256, 0, st>>>(quads, counts, B.page_off, n_pages, cap_per_page, B.keys, B.vals);
+        lanms_keys_kernel<<<grid, 256, 0, st>>>(quads, counts, B.page_off, n_pages, cap_per_page, B.keys, B.vals,
+                                                B.pos_page);
         MS_LAUNCH_CHECK(ctx);
     }
-    int page_bits = 1;
-    while ((1 << page_bits) < n_pages) page_bits++;
-    int rc = msk_sort_pairs(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.n_total, (int64_t)n_max,
-                            n_pages > 1 ? 32 + page_bits : 32, bump, st);
+    int rc = msk_sort_pages(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.page_off, n_pages, cap_per_page, bump, st);
     if (rc != MS_OK) return rc;
-    lanms_gather_hot_kernel<<<sms * 8, 128, 0, st>>>(quads, B.keys, B.vals, B.page_off, B.n_total, thr, B);
+    lanms_gather_hot_kernel<<<sms * 8, 128, 0, st>>>(quads, B.vals, B.page_off, B.n_total, thr, B);
     MS_LAUNCH_CHECK(ctx);
     lanms_runs_kernel<<<sms * 4, 128, 0, st>>>(B.page_off, thr, B);
     MS_LAUNCH_CHECK(ctx);
@@ -1116,8 +1175,11 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
     {
         int gx = (cap_per_page + kRankThreads - 1) / kRankThreads;
         if (gx > 32) gx = 32;
+        lanms_sort_emit_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out, B.page_redo);
+        MS_LAUNCH_CHECK(ctx);
+        // (page_redo is free again after the neighbour search: reused as the "rank needed" flag)
         lanms_emit_kernel<<<dim3(gx, n_pages), kRankThreads, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out,
-                                                                       nullptr);
+                                                                       nullptr, B.page_redo);
         MS_LAUNCH_CHECK(ctx);
     }
     return MS_OK;
@@ -1147,7 +1209,7 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
     {
         int gx = (n + kRankThreads - 1) / kRankThreads;
         if (gx > 148) gx = 148;
-        lanms_emit_kernel<<<dim3(gx, 1), kRankThreads, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx);
+        lanms_emit_kernel<<<dim3(gx, 1), kRankThreads, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx, nullptr);
         MS_LAUNCH_CHECK(ctx);
     }
     return MS_OK;

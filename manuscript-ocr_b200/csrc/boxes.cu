@@ -243,7 +243,7 @@ __global__ void __launch_bounds__(256) east_prep_kernel(const float *__restrict_
 //    cv2.pointPolygonTest >= 0 implies the point lies inside the contour's vertex bounding box (the ray
 //    cast skips every edge otherwise), so bbox containment is an exact prefilter; the tiny margin only
 //    guards the sign of its double-precision cross product next to a vertex.
-constexpr int kContainThreads = 128;
+constexpr int kContainThreads = 256;
 
 __global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int32_t *__restrict__ counts, int cap,
                                                                        EastScratch S)
@@ -284,22 +284,27 @@ __global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int
             __syncthreads();
             if (!live || later_hit) continue;
             const int nj = min(kContainThreads, K - base_j);
+            // branch-free prefilter, 4 candidates per trip; the exact test runs only for the rare survivors
+#pragma unroll 4
             for (int t = 0; t < nj; t++) {
-                const int j = base_j + t;
                 const float aj = s_ar[t];
-                if (aj + eps < ai) continue;  // infer.py:208
                 const float4 bj = s_bb[t];
-                if (!(bi.x >= bj.x && bi.y >= bj.y && bi.z <= bj.z && bi.w <= bj.w)) continue;
-                if (j == i) continue;
-                float qj[8];
+                const bool cand = !(aj + eps < ai) &&  // infer.py:208
+                                  bi.x >= bj.x && bi.y >= bj.y && bi.z <= bj.z && bi.w <= bj.w;
+                if (cand) {
+                    const int j = base_j + t;
+                    if (j != i && !later_hit) {
+                        float qj[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
-                if (!quad_inside(qi, qj)) continue;
-                if (area_before(ai, i, aj, j)) {  // j is visited after i: still kept when i is visited
-                    later_hit = true;
-                    break;
+                        for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
+                        if (quad_inside(qi, qj)) {
+                            if (area_before(ai, i, aj, j))
+                                later_hit = true;  // j is visited after i: still kept when i is visited
+                            else
+                                earlier_hit = true;  // j's own fate decides
+                        }
+                    }
                 }
-                earlier_hit = true;  // j's own fate decides
             }
         }
         if (live) {

@@ -335,7 +335,9 @@ def run_b200(a):
         barrier()
         nch = int(rh.n_crops[0])
         assert nch == n_crops and int(rh.box_counts.sum()) == n_boxes
-        h2d = h_score.numel() * 4 + h_geo.numel() * 4 + h_pages.numel()
+        # with quantisation 2 only the geometry rows the decode can read (odd rows) are uploaded (strided DMA)
+        geo_rows = M // 2 if (params.quantization == 2 and M % 2 == 0) else M
+        h2d = h_score.numel() * 4 + P * 8 * geo_rows * M * 4 + h_pages.numel()
         d2h = P * cap_boxes * 36 + P * 8 + 4 + nch * 20
         e2e = {"value": world * P * a.steps / t_e2e, "unit": "pages/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / a.steps,

@@ -382,7 +382,7 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
                            const ms_east_params *p, int min_text_size, int out_h, int out_w, int cap_boxes,
                            float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
                            int32_t *n_crops, int append, float *batch_f32, uint8_t *canvas_u8, int32_t *flags,
-                           cudaStream_t st)
+                           cudaStream_t st, int geo_compact = 0)
 {
     const bool want_crops = pages_all != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
     const int q = p->quantization < 1 ? 1 : p->quantization;
@@ -401,7 +401,7 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
     MS_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_pages * sizeof(int32_t), st));
     MS_TRY(timing_mark(ctx, 0, st));
     MS_TRY(msk_decode(ctx, score, geo, n_pages, map_h, map_w, p->score_thresh, p->scale, q, qa, cap_c, ca, flags, bump,
-                      st));
+                      st, geo_compact));
     MS_TRY(timing_mark(ctx, 1, st));
     MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
     // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
@@ -821,6 +821,11 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     // page images) while the compute stream runs chunk c.  PCIe is the floor of this entry point: 22 MB per
     // 2048x2048 page against a few tens of microseconds of kernels.
     cudaStream_t st = ctx->own_stream, cs = ctx->copy_stream;
+    // With quantisation q > 1 the decode reads geometry only at rows y % q == q / 2 (utils.py:347-376), so only those
+    // rows cross PCIe: one strided 2-D DMA per chunk into a compact (P, 8, H / q, W) tensor.
+    const int q = p->quantization < 1 ? 1 : p->quantization;
+    const int geo_compact = (q > 1 && map_h % q == 0) ? 1 : 0;
+    const size_t gplane = geo_compact ? (size_t)(map_h / q) * map_w : plane;
     int chunk = (n_pages + 7) / 8;
     if (chunk < 1) chunk = 1;
     if (chunk > 8) chunk = 8;
@@ -832,17 +837,22 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
         // the event of chunk k-2 was consumed by the compute stream before chunk k-1 was queued; reuse is safe
         MS_CUDA(cudaMemcpyAsync(d_score + (size_t)p0 * plane, score + (size_t)p0 * plane, np * plane * 4,
                                 cudaMemcpyHostToDevice, cs));
-        MS_CUDA(cudaMemcpyAsync(d_geo + (size_t)p0 * plane * 8, geo + (size_t)p0 * plane * 8, np * plane * 32,
-                                cudaMemcpyHostToDevice, cs));
+        if (geo_compact)
+            MS_CUDA(cudaMemcpy2DAsync(d_geo + (size_t)p0 * gplane * 8, (size_t)map_w * 4,
+                                      geo + (size_t)p0 * plane * 8 + (size_t)(q / 2) * map_w, (size_t)q * map_w * 4,
+                                      (size_t)map_w * 4, (size_t)np * 8 * (map_h / q), cudaMemcpyHostToDevice, cs));
+        else
+            MS_CUDA(cudaMemcpyAsync(d_geo + (size_t)p0 * plane * 8, geo + (size_t)p0 * plane * 8, np * plane * 32,
+                                    cudaMemcpyHostToDevice, cs));
         if (want_crops)
             MS_CUDA(cudaMemcpyAsync(d_pages + (size_t)p0 * page_bytes, pages + (size_t)p0 * page_bytes,
                                     np * page_bytes, cudaMemcpyHostToDevice, cs));
         MS_CUDA(cudaEventRecord(ev, cs));
         MS_CUDA(cudaStreamWaitEvent(st, ev, 0));
-        MS_TRY(page_batch_impl(ctx, d_score + (size_t)p0 * plane, d_geo + (size_t)p0 * plane * 8, d_pages, n_pages, p0,
+        MS_TRY(page_batch_impl(ctx, d_score + (size_t)p0 * plane, d_geo + (size_t)p0 * gplane * 8, d_pages, n_pages, p0,
                                np, map_h, map_w, img_h, img_w, p, min_text_size, out_h, out_w, cap_boxes,
                                d_boxes + (size_t)p0 * cap_boxes * 9, d_cnt + p0, d_crops, crops_cap, d_nc, 1, d_batch,
-                               nullptr, d_flags + p0, st));
+                               nullptr, d_flags + p0, st, geo_compact));
     }
     MS_CUDA(cudaMemcpyAsync(box_counts, d_cnt, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaMemcpyAsync(flags, d_flags, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));

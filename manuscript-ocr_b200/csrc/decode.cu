@@ -157,15 +157,18 @@ __global__ void __launch_bounds__(kThreads) decode_emit_kernel(const float *__re
                                                                const float *__restrict__ geo, DecodeGeom g,
                                                                double scale, const uint32_t *__restrict__ masks,
                                                                const int32_t *__restrict__ tile_base, int cap,
-                                                               float *__restrict__ out)
+                                                               float *__restrict__ out, int geo_compact)
 {
     const int page = blockIdx.y, tile = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ int s_word_base[kTileWords];
     __shared__ float s_rows[kWarps][32 * 9];
     const size_t plane = (size_t)g.H * g.W;
+    // geo_compact: the geometry tensor holds only the rows a quantised read can touch (y % q == q / 2), i.e.
+    // (P, 8, H / q, W) -- what ms_page_batch_host uploads
+    const size_t gplane = geo_compact ? (size_t)(g.H / g.q) * g.W : plane;
     const float *sc = score + (size_t)page * plane;
-    const float *ge = geo + (size_t)page * 8 * plane;
+    const float *ge = geo + (size_t)page * 8 * gplane;
     const uint32_t *mk = masks + (size_t)page * g.words;
 
     // exclusive prefix over the tile's 64 mask-word popcounts (two warps worth of data)
@@ -213,14 +216,15 @@ __global__ void __launch_bounds__(kThreads) decode_emit_kernel(const float *__re
             int cy = cell / g.CW, cx = cell - cy * g.CW;
             int y = g.q > 1 ? cy * g.q + g.q / 2 : cy;
             int x = g.q > 1 ? cx * g.q + g.q / 2 : cx;
-            size_t pix = (size_t)y * g.W + x;
+            const size_t pix = (size_t)y * g.W + x;
+            const size_t gpix = geo_compact ? (size_t)cy * g.W + x : pix;
             double xs = __dmul_rn((double)x, scale);
             double ys = __dmul_rn((double)y, scale);
             float *r = stage + rank * 9;
 #pragma unroll
             for (int v = 0; v < 4; v++) {
-                float dx = __ldg(ge + (size_t)(2 * v) * plane + pix);
-                float dy = __ldg(ge + (size_t)(2 * v + 1) * plane + pix);
+                float dx = __ldg(ge + (size_t)(2 * v) * gplane + gpix);
+                float dy = __ldg(ge + (size_t)(2 * v + 1) * gplane + gpix);
                 r[2 * v] = (float)__dadd_rn(xs, (double)__fmul_rn(dx, sc32));
                 r[2 * v + 1] = (float)__dadd_rn(ys, (double)__fmul_rn(dy, sc32));
             }
@@ -246,9 +250,13 @@ size_t msk_decode_scratch(int n_pages, int H, int W, int q)
 
 int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int H, int W, float thr,
                double scale, int q, float *quads_out, int cap_per_page, int32_t *counts, int32_t *flags,
-               ms_bump bump, cudaStream_t st)
+               ms_bump bump, cudaStream_t st, int geo_compact)
 {
     if (n_pages <= 0) return MS_OK;
+    if (geo_compact && (q < 2 || H % q != 0)) {
+        ms_set_error("decode: compact geometry needs q > 1 and H %% q == 0");
+        return MS_ERR_INVALID;
+    }
     if (H <= 0 || W <= 0 || q < 1 || cap_per_page <= 0) {
         ms_set_error("decode: bad shape H=%d W=%d q=%d cap=%d", H, W, q, cap_per_page);
         return MS_ERR_INVALID;
@@ -266,7 +274,8 @@ int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, i
     MS_LAUNCH_CHECK(ctx);
     decode_scan_kernel<<<n_pages, 256, 0, st>>>(tile_counts, g.tiles, cap_per_page, tile_base, counts, flags);
     MS_LAUNCH_CHECK(ctx);
-    decode_emit_kernel<<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page, quads_out);
+    decode_emit_kernel<<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page, quads_out,
+                                                  geo_compact);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

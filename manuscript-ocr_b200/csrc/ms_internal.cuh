@@ -75,7 +75,7 @@ int ms_stage_reserve(ms_ctx *ctx, size_t bytes);
 // decode.cu
 int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int H, int W, float thr,
                double scale, int q, float *quads_out, int cap_per_page, int32_t *counts, int32_t *flags,
-               ms_bump bump, cudaStream_t st);
+               ms_bump bump, cudaStream_t st, int geo_compact = 0);
 size_t msk_decode_scratch(int n_pages, int H, int W, int q);
 // sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs, n on the device
 int msk_sort_pairs(ms_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,

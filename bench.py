@@ -157,7 +157,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.gpu)], stdout=subprocess.PIPE,
+                                          "-lms", "20", "-i", str(self.gpu)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -342,6 +342,7 @@ def run_b200(a):
         e2e = {"value": world * P * a.steps / t_e2e, "unit": "pages/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / a.steps,
                "note": "ms_page_batch_host with pinned host buffers; crop batch left on the device for the recogniser"}
+    t_wall2 = time.perf_counter()
     if rank == 0:
         sampler.stop()
 
@@ -360,8 +361,17 @@ def run_b200(a):
         stages[k] = {"ms_per_step": ms, "share": v / max(sum(stage_ms.values()), 1e-12), "alg_bytes": int(alg[k]),
                      "gbs": gbs, "frac_of_hbm_peak": gbs / peak}
     dom = max(stage_ms, key=lambda k: stage_ms[k])
+    traffic, traffic_src = None, None
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel from the committed ncu --set full capture
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tj = json.load(f)
+        if tj.get("stage") == dom and tj.get("workload_pages") == P and tj.get("page") == S:
+            traffic, traffic_src = tj["dram_bytes_per_launch"], tj["source"]
+    except Exception:
+        pass
     roofline = {"kernel": dom, "bound": "hbm", "achieved": stages[dom]["gbs"], "peak": peak, "unit": "GB/s",
-                "frac": stages[dom]["gbs"] / peak, "traffic": None, "peak_source": peak_src,
+                "frac": stages[dom]["gbs"] / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src,
                 "alg_bytes_per_launch": int(alg[dom]), "ms_per_launch": stages[dom]["ms_per_step"]}
     whole = sum(alg.values()) / (ms_step * 1e-3) / 1e9
     line = {
@@ -377,7 +387,7 @@ def run_b200(a):
         "roofline": roofline,
         "whole_step": {"alg_bytes": int(sum(alg.values())), "gbs": whole, "frac_of_hbm_peak": whole / peak},
         "stages": stages,
-        "clocks": sampler.summary(t_wall0, t_wall1),
+        "clocks": sampler.summary(t_wall0, t_wall2),
     }
     if e2e is not None:
         line["e2e"] = e2e

@@ -57,6 +57,9 @@ def parse_args():
     ap.add_argument("--cpu-pages", type=int, default=8, help="pages in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--reading-order", action="store_true",
+                    help="also run the reading-order sort between the box filters and the crops (what Pipeline.predict "
+                         "does; not part of the BASELINE metric, reported under config.reading_order)")
     return ap.parse_args()
 
 
@@ -250,7 +253,7 @@ def run_b200(a):
     h_pages.copy_(torch.from_numpy(imgs_np))
     d_score, d_geo, d_pages = h_score.to(dev), h_geo.to(dev), h_pages.to(dev)
 
-    params = mb.EastParams.default(target_size=S)
+    params = mb.EastParams.default(target_size=S, sort_reading_order=1 if a.reading_order else 0)
     cap_boxes = 4096
     crops_cap = P * (a.words + a.words // 4 + 64)
     runner = mb.PageBatch(device=local, params=params, cap_boxes=cap_boxes, crops_cap=crops_cap, out_hw=(OUT_H, OUT_W))
@@ -381,6 +384,7 @@ def run_b200(a):
         "config": {"workload": workload_name(a), "pages_per_gpu": P, "page": S, "map": M, "words_per_page": a.words,
                    "candidates_per_page": n_cand / P, "boxes_per_page": n_boxes / P, "crops_per_page": n_crops / P,
                    "l2": "inputs (maps + pages) of one step exceed L2 (no flush needed)",
+                   "reading_order": bool(a.reading_order),
                    "parallelism": f"pages sharded over {world} GPU(s), no collective"},
         "boxes_per_sec": total_boxes * a.steps / (ms_total * 1e-3),
         "gpu_launches": int(launches),

@@ -62,6 +62,8 @@ typedef struct ms_east_params {
     int remove_area_anomalies;   /* 1    */
     double anomaly_sigma_threshold; /* 5.0 */
     int anomaly_min_box_count;   /* 30   */
+    int sort_reading_order;      /* 0: EAST.predict(sort_reading_order=False) default, infer.py:240;
+                                    1: what Pipeline.predict always does, _pipeline.py:105-123 */
 } ms_east_params;
 
 MS_API const char *ms_version(void);
@@ -130,6 +132,12 @@ MS_API int ms_east_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, const 
 MS_API int ms_word_rects_host(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w,
                        int min_text_size, int32_t *rects, uint8_t *valid);
 
+/* replaces sort_boxes_reading_order_with_resolutions, detectors/_east/utils.py:610-644 (default y_tol_ratio /
+ * x_gap_ratio), and the word re-matching of Pipeline.predict, _pipeline.py:105-123 (== infer.py:365-385):
+ * polys (n,8) f32 -> order (n) int32, order[r] = index of the word at reading position r (the reference's quirks
+ * with duplicate boxes included).  At most 4096 boxes. */
+MS_API int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n, int32_t *order);
+
 /* replaces ResizeAndPadA.apply + get_val_transform + the torch.stack of TRBA.predict,
  * recognizers/_trba/data/transforms.py:85-120,185-193 and recognizers/_trba/__init__.py:264-288,
  * 382-390: page (img_h,img_w,3) u8 + rects (n,4) -> batch (n,3,out_h,out_w) f32 normalised
@@ -156,6 +164,11 @@ MS_API int ms_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int 
 MS_API int ms_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                   const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int32_t *counts_out,
                   void *stream);
+
+/* utils.py:610-644 + _pipeline.py:105-123 for n_pages box lists (page-strided, <= 4096 boxes per page): order
+ * (n_pages*cap_per_page) int32 and, if quads_out != NULL (must not alias quads), the rows in reading order. */
+MS_API int ms_reading_order(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                     int32_t *order, float *quads_out, int32_t *flags, void *stream);
 
 /* _pipeline.py:125-137,204-221 for n_pages box lists: compacts the valid crops of all pages, in
  * (page, box) order, into crops_out rows of 5 int32 [page,x1,y1,x2,y2]; *n_crops (device int32). */

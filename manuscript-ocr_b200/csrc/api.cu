@@ -48,6 +48,7 @@ extern "C" void ms_east_params_default(ms_east_params *p)
     p->remove_area_anomalies = 1;
     p->anomaly_sigma_threshold = 5.0;
     p->anomaly_min_box_count = 30;
+    p->sort_reading_order = 0;
 }
 
 extern "C" int ms_device_count(void)
@@ -314,6 +315,62 @@ extern "C" int ms_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *cou
                           nullptr, bump, (cudaStream_t)stream);
 }
 
+extern "C" int ms_reading_order(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
+                                int32_t *order, float *quads_out, int32_t *flags, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!quads || !counts || !order || !flags || cap_per_page <= 0 || quads_out == quads) {
+        ms_set_error("ms_reading_order: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    MS_TRY(ms_arena_reserve(ctx, msk_reading_order_scratch(n_pages, cap_per_page)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_reading_order(ctx, quads, 9, counts, n_pages, cap_per_page, order, quads_out, flags, bump,
+                             (cudaStream_t)stream);
+}
+
+extern "C" int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n, int32_t *order)
+{
+    MS_CTX(ctx);
+    if (n < 0 || (n > 0 && (!polys8 || !order))) {
+        ms_set_error("ms_reading_order_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    if (n > 4096) {
+        ms_set_error("ms_reading_order_host: at most 4096 boxes per page (got %lld)", (long long)n);
+        return MS_ERR_CAPACITY;
+    }
+    const int cap = (int)n;
+    MS_TRY(ms_stage_reserve(ctx, al256((size_t)n * 32) + al256((size_t)n * 4) + 1024));
+    MS_TRY(ms_arena_reserve(ctx, msk_reading_order_scratch(1, cap)));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_p = sb.take<float>((size_t)n * 8);
+    int32_t *d_o = sb.take<int32_t>((size_t)n);
+    int32_t *d_i = sb.take<int32_t>(2);
+    if (!d_i) {
+        ms_set_error("ms_reading_order_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    h[0] = cap;
+    h[1] = 0;
+    MS_CUDA(cudaMemcpyAsync(d_i, h, 2 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_p, polys8, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_reading_order(ctx, d_p, 8, d_i, 1, cap, d_o, nullptr, d_i + 1, bump, st));
+    MS_CUDA(cudaMemcpyAsync(order, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(h + 4, d_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    if (h[4] & MS_FLAG_EDGE_OVERFLOW) {
+        ms_set_error("ms_reading_order_host: more than 32768 intersecting box pairs on the page");
+        return MS_ERR_CAPACITY;
+    }
+    return MS_OK;
+}
+
 static size_t word_rects_scratch_full(int n_pages, int cap_per_page)
 {
     return msk_word_rects_scratch(n_pages) + al256((size_t)n_pages * cap_per_page * 4 * sizeof(int32_t)) + 1024;
@@ -358,7 +415,8 @@ static int cand_cap(int map_h, int map_w, int q)
     return (int)(c > 0x7fffffffLL ? 0x7fffffff : c);
 }
 
-static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap, int ef)
+static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap, int ef,
+                                 int cap_boxes)
 {
     size_t fixed = 2 * al256((size_t)n_pages * cap_c * 9 * sizeof(float)) + 2 * al256((size_t)n_pages * sizeof(int32_t));
     size_t stage = msk_decode_scratch(n_pages, map_h, map_w, q);
@@ -367,6 +425,10 @@ static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int c
     s2 = msk_east_boxes_scratch(n_pages, cap_c);
     if (s2 > stage) stage = s2;
     s2 = word_rects_scratch_full(n_pages, cap_c);
+    if (s2 > stage) stage = s2;
+    // reading order: boxes + order scratch (cap_boxes <= cap_c rows per page) + its own scratch, next to east_boxes'
+    s2 = msk_east_boxes_scratch(n_pages, cap_c) + al256((size_t)n_pages * cap_boxes * 36) +
+         al256((size_t)n_pages * cap_boxes * 4) + msk_reading_order_scratch(n_pages, cap_boxes) + 1024;
     if (s2 > stage) stage = s2;
     s2 = msk_crop_scratch(crops_cap);
     if (s2 > stage) stage = s2;
@@ -387,7 +449,7 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
     const bool want_crops = pages_all != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
     const int q = p->quantization < 1 ? 1 : p->quantization;
     const int cap_c = cand_cap(map_h, map_w, q);
-    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor)));
+    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor, cap_boxes)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates
     float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
@@ -406,7 +468,19 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
     MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
     // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
     MS_TRY(timing_mark(ctx, 2, st));
-    MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, boxes_out, cap_boxes, box_counts, flags, bump, st));
+    if (p->sort_reading_order) {
+        // filtered boxes -> scratch, then into boxes_out in reading order (the order the crops are produced in)
+        float *tmp = bump.take<float>((size_t)n_pages * cap_boxes * 9);
+        int32_t *ord = bump.take<int32_t>((size_t)n_pages * cap_boxes);
+        if (!ord) {
+            ms_set_error("ms_page_batch: arena too small");
+            return MS_ERR_CAPACITY;
+        }
+        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, tmp, cap_boxes, box_counts, flags, bump, st));
+        MS_TRY(msk_reading_order(ctx, tmp, 9, box_counts, n_pages, cap_boxes, ord, boxes_out, flags, bump, st));
+    } else {
+        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, boxes_out, cap_boxes, box_counts, flags, bump, st));
+    }
     MS_TRY(timing_mark(ctx, 3, st));
     if (want_crops) {
         MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, nullptr, img_h, img_w, min_text_size,

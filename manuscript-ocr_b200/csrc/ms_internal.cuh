@@ -106,6 +106,10 @@ int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
 size_t msk_word_rects_scratch(int n_pages);
 int msk_word_rects_flat(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, int img_w, int min_text_size,
                         int32_t *rects, uint8_t *valid, cudaStream_t st);
+// reading_order.cu
+int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const int32_t *counts, int n_pages,
+                      int cap_per_page, int32_t *order, float *reordered, int32_t *flags, ms_bump bump, cudaStream_t st);
+size_t msk_reading_order_scratch(int n_pages, int cap_per_page);
 // crop.cu
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,

@@ -23,6 +23,7 @@ from .ops import (  # noqa: F401
     polygon_iou,
     should_merge,
     standard_nms,
+    word_reading_order,
     word_rects,
 )
 from .batch import PageBatch, PageBatchResult, shard_pages  # noqa: F401

@@ -43,6 +43,7 @@ class EastParams(C.Structure):
         ("remove_area_anomalies", C.c_int),
         ("anomaly_sigma_threshold", C.c_double),
         ("anomaly_min_box_count", C.c_int),
+        ("sort_reading_order", C.c_int),
     ]
 
     @classmethod
@@ -82,6 +83,8 @@ SIGNATURES = {
     "ms_expand_boxes_host": (_i, [_vp, _vp, _i64, _d, _d, _vp]),
     "ms_east_boxes_host": (_i, [_vp, _vp, _i64, C.POINTER(EastParams), _i, _i, _vp, C.POINTER(_i64)]),
     "ms_word_rects_host": (_i, [_vp, _vp, _i64, _i, _i, _i, _vp, _vp]),
+    "ms_reading_order_host": (_i, [_vp, _vp, _i64, _vp]),
+    "ms_reading_order": (_i, [_vp, _vp, _vp, _i, _i, _vp, _vp, _vp, _vp]),
     "ms_crop_resize_pad_host": (_i, [_vp, _vp, _i, _i, _vp, _i64, _i, _i, _vp, _vp]),
     "ms_decode_quads": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _vp, _i, _vp, _vp, _vp]),
     "ms_lanms": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),

@@ -159,6 +159,21 @@ def word_rects(polys, img_h, img_w, min_text_size=5, ctx=None):
     return rects, valid.astype(bool)
 
 
+# ---- detectors/_east/utils.py:610-644 + _pipeline.py:105-123 -----------------------------------------------------------
+def word_reading_order(polys, ctx=None):
+    """polys (n,4,2) or (n,>=8) float -> (n,) int32: index of the word at each reading position, exactly what
+    Pipeline.predict's sort + re-match loop produces (duplicates resolved the way the reference's dict / first-match
+    loops do).  At most 4096 boxes."""
+    n = len(polys)
+    order = np.zeros(n, np.int32)
+    if n == 0:
+        return order
+    p = np.ascontiguousarray(np.asarray(polys, dtype=np.float32).reshape(n, -1)[:, :8])
+    cx = _ctx(ctx)
+    check(cx.lib.ms_reading_order_host(cx.handle, _ptr(p), n, _ptr(order)))
+    return order
+
+
 # ---- recognizers/_trba/data/transforms.py:85-120,185-193 + recognizers/_trba/__init__.py:264-288,382-390 ------------
 def crop_resize_pad(page, rects, img_h=32, img_w=128, want_canvas=False, want_batch=True, ctx=None):
     """page (H,W,3) u8 RGB, rects (n,4) int32 [x1,y1,x2,y2) -> the TRBA input batch (n,3,img_h,img_w) f32

@@ -119,11 +119,18 @@ def int_bbox(polygon):
     return (x_min, y_min, x_max, y_max)
 
 
-def reorder_words(words):
+def reorder_words(words, on_device=True):
     """_pipeline.py:105-123 / infer.py:361-385: words re-ordered to follow the sorted boxes; each sorted box
-    picks the FIRST word with equal integer bbox (duplicates resolve the way the reference's loop does)."""
+    picks the FIRST word with equal integer bbox (duplicates resolve the way the reference's loop does).
+    Pages of up to 4096 words are ordered by the CUDA kernel (ms_reading_order_host); larger ones by the exact
+    host restatement below (this step is host logic in the reference too)."""
     if len(words) == 0:
         return []
+    if on_device and len(words) <= 4096 and all(len(w.polygon) == 4 for w in words):
+        from . import ops
+
+        polys = np.array([w.polygon for w in words], dtype=np.float32).reshape(len(words), 8)
+        return [words[int(i)] for i in ops.word_reading_order(polys)]
     keys = [tuple(int(v) for v in int_bbox(w.polygon)) for w in words]
     first = {}
     for i, k in enumerate(keys):

@@ -168,3 +168,57 @@ def test_pipeline_with_b200_trba_feeds_device_batch(mb):
     np.testing.assert_array_equal(seen["batch"][1], chw)
     assert [w.text for w in page.blocks[0].words] == ["t0", "t1", "t2"]
     assert page.blocks[0].words[0].recognition_confidence == 0.5
+
+
+def _boxes_to_polys(boxes):
+    b = np.asarray(boxes, np.float32).reshape(-1, 4)
+    x0, y0, x1, y1 = b[:, 0], b[:, 1], b[:, 2], b[:, 3]
+    return np.stack([x0, y0, x1, y0, x1, y1, x0, y1], axis=1)
+
+
+def _host_order(mb, boxes):
+    """Pipeline.predict's sort + re-match (host restatement pinned to the reference goldens) as word indices."""
+    keys = [tuple(int(v) for v in bx) for bx in boxes]
+    first = {}
+    for i, k in enumerate(keys):
+        first.setdefault(k, i)
+    return [first[tuple(int(v) for v in bx)] for bx in mb.sort_boxes_reading_order_with_resolutions(keys)]
+
+
+def test_reading_order_device_matches_reference_goldens(mb, golden_dir):
+    g = np.load(os.path.join(golden_dir, "reading_order.npz"))
+    for i in range(int(g["n_cases"])):
+        boxes = g[f"boxes_{i}"]
+        got = mb.word_reading_order(_boxes_to_polys(boxes))
+        # the golden holds the reference's sorted boxes; compare box sequences, then exact word indices vs the host mirror
+        np.testing.assert_array_equal(boxes[got].reshape(-1, 4), g[f"sorted_res_{i}"], err_msg=f"case {i}")
+        assert list(got) == _host_order(mb, boxes), f"case {i}"
+
+
+def test_reading_order_device_on_detector_output(mb):
+    """Expanded (heavily overlapping) detector boxes of a synthetic page, fractional coordinates included."""
+    page, words = 1280, 500
+    score, geo, _ = synthdata.make_maps(9, page, words)
+    q = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    boxes = cpu.east_postprocess(cpu.locality_aware_nms(q, 0.2), (page, page), target_size=page)
+    got = mb.word_reading_order(boxes[:, :8])
+    ib = []
+    for b in boxes[:, :8]:
+        xs, ys = np.trunc(b[0::2]).astype(np.int64), np.trunc(b[1::2]).astype(np.int64)
+        ib.append((int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())))
+    assert list(got) == _host_order(mb, ib)
+    assert sorted(set(got.tolist())) == sorted(set(range(len(boxes)))) or len(set(ib)) < len(ib)
+    # through the batched path: boxes come out in reading order and crops follow them
+    import torch
+
+    imgs = synthdata.make_page_image(9, page)[None]
+    params = mb.EastParams.default(target_size=page, sort_reading_order=1)
+    runner = mb.PageBatch(device=0, params=params, cap_boxes=1024)
+    res = runner.run(torch.from_numpy(score[None]).cuda(), torch.from_numpy(geo[None]).cuda(), torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    n = int(res.box_counts.cpu()[0])
+    assert n == len(boxes) and int(res.flags.cpu()[0]) == 0
+    np.testing.assert_array_equal(res.boxes[0, :n].cpu().numpy(), boxes[got])
+    rects, valid = cpu.word_rects(boxes[got], page, page, 5)
+    nc = int(res.n_crops.cpu()[0])
+    np.testing.assert_array_equal(res.crops[:nc].cpu().numpy()[:, 1:], rects[valid])

@@ -365,7 +365,7 @@ extern "C" int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n
     MS_CUDA(cudaMemcpyAsync(h + 4, d_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
     if (h[4] & MS_FLAG_EDGE_OVERFLOW) {
-        ms_set_error("ms_reading_order_host: more than 32768 intersecting box pairs on the page");
+        ms_set_error("ms_reading_order_host: more than 28672 intersecting box pairs on the page");
         return MS_ERR_CAPACITY;
     }
     return MS_OK;

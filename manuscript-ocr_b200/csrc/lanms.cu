@@ -59,7 +59,6 @@ struct LanmsBuffers {
     // clusters, stored at page_off[p] + c
     double *cl_poly;
     double *cl_score;
-    float *cl_key;
     float4 *cl_bbox;
     uint8_t *cl_irr;
     int32_t *cl_orig;    // priority tie-break index (creation order)
@@ -364,8 +363,6 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
 #pragma unroll
             for (int k = 0; k < 4; k++) dst[k] = make_double2(poly[2 * k], poly[2 * k + 1]);
             B.cl_score[slot] = score;
-            float key = (float)B.sq[(size_t)s * 8];  // anchor x0: the (sorted) sweep key
-            B.cl_key[slot] = key;
             float4 bb;
             bool reg = quad_regular_bbox(poly, bb) && !all_irregular;
             if (!reg) bb = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
@@ -1033,7 +1030,6 @@ __global__ void nms_prepare_kernel(const double *__restrict__ polys, const doubl
 #pragma unroll
         for (int k = 0; k < 8; k++) B.cl_poly[(size_t)i * 8 + k] = polys[(size_t)i * 8 + k];
         B.cl_score[i] = scores[i];
-        B.cl_key[i] = 0.0f;
         B.cl_bbox[i] = make_float4(-INFINITY, -INFINITY, INFINITY, INFINITY);
         B.cl_irr[i] = 1;
         B.cl_orig[i] = i;
@@ -1074,7 +1070,6 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     }
     B.cl_poly = bump.take<double>(n_max * 8);
     B.cl_score = bump.take<double>(n_max);
-    B.cl_key = bump.take<float>(n_max);
     B.cl_bbox = bump.take<float4>(n_max);
     B.cl_irr = bump.take<uint8_t>(n_max);
     B.cl_orig = bump.take<int32_t>(n_max);

@@ -77,11 +77,7 @@ int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, i
                double scale, int q, float *quads_out, int cap_per_page, int32_t *counts, int32_t *flags,
                ms_bump bump, cudaStream_t st, int geo_compact = 0);
 size_t msk_decode_scratch(int n_pages, int H, int W, int q);
-// sort.cu : stable LSD radix sort of (u64 key, u32 value) pairs, n on the device
-int msk_sort_pairs(ms_ctx *ctx, uint64_t *keys, uint32_t *vals, uint64_t *keys_tmp, uint32_t *vals_tmp,
-                   const int32_t *n_dev, int64_t n_max, int end_bit, ms_bump bump, cudaStream_t st);
-size_t msk_sort_scratch(int64_t n_max);
-// per-page segments [page_off[p], page_off[p+1]) of (u32 key, u32 value), 4 passes
+// sort.cu : stable LSD radix sort, per-page segments [page_off[p], page_off[p+1]) of (u32 key, u32 value), 4 passes
 int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
                    const int32_t *page_off, int n_pages, int cap_per_page, ms_bump bump, cudaStream_t st);
 size_t msk_sort_pages_scratch(int n_pages, int cap_per_page);

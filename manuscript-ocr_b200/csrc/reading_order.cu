@@ -8,15 +8,17 @@
 // without changing a single step: boxes only ever shrink towards their top-left corner, so a pair that does not
 // intersect initially never does (the sweeps visit only the initially intersecting pairs, in the reference's order,
 // and drop pairs that stopped intersecting); box centres are multiples of 0.5, so per-line means are exact integer
-// sums divided once.  One CTA per page: pair generation, sorting and the duplicate mapping are parallel, the sweeps
-// and the line assignment run on one thread / one warp out of shared memory.
+// sums divided once.  Within a sweep two pairs commute unless they share a box: every pair gets a dependency level
+// (1 + the level of the latest earlier pair touching either of its boxes) and the pairs of one level are applied in
+// parallel -- any order that respects the levels reproduces the sequential sweep.
+// One CTA per page, everything out of shared memory; the line assignment is a one-warp sequential scan.
 #include "ms_internal.cuh"
 
 namespace {
 
 constexpr int kRoThreads = 1024;
 constexpr int kRoMaxBoxes = 4096;   // boxes per page held in shared memory
-constexpr int kRoMaxPairs = 32768;  // initially intersecting pairs per page
+constexpr int kRoMaxPairs = 28672;  // initially intersecting pairs per page
 
 __device__ __forceinline__ int ro_trunc(float v)
 {
@@ -102,15 +104,20 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     extern __shared__ __align__(16) unsigned char ro_smem[];
     int4 *box = reinterpret_cast<int4 *>(ro_smem);                                   // kRoMaxBoxes
     uint32_t *pairs = reinterpret_cast<uint32_t *>(ro_smem + kRoMaxBoxes * 16);      // kRoMaxPairs
-    // after the sweeps the pair region is reused:
-    uint64_t *keys = reinterpret_cast<uint64_t *>(pairs);                            // kRoMaxBoxes u64   (32 KB)
-    long long *line_sum = reinterpret_cast<long long *>(pairs + 2 * kRoMaxBoxes);    // kRoMaxBoxes i64   (32 KB)
-    int *line_cnt = reinterpret_cast<int *>(pairs + 4 * kRoMaxBoxes);                // kRoMaxBoxes
-    int *line_rank = line_cnt + kRoMaxBoxes;                                         // kRoMaxBoxes
-    int *line_of = line_rank + kRoMaxBoxes;                                          // kRoMaxBoxes (by box index)
-    int *seq_of = line_of + kRoMaxBoxes;                                             // kRoMaxBoxes (by box index)
+    uint8_t *lv = reinterpret_cast<uint8_t *>(pairs + kRoMaxPairs);                  // kRoMaxPairs dependency levels
+    uint16_t *last_lv = reinterpret_cast<uint16_t *>(lv + kRoMaxPairs);              // kRoMaxBoxes
+    // after the sweeps the pair + level region (148 KB) is reused:
+    unsigned char *R = reinterpret_cast<unsigned char *>(pairs);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(R);                         // kRoMaxBoxes u64          @   0 K
+    long long *line_sum = reinterpret_cast<long long *>(R + 32 * 1024);       // per line: sum of y0 + y1  @  32 K
+    double *line_cy = reinterpret_cast<double *>(R + 64 * 1024);              // per line: mean centre     @  64 K
+    int *line_cnt = reinterpret_cast<int *>(R + 96 * 1024);                   // per line: members         @  96 K
+    uint16_t *line_rank = reinterpret_cast<uint16_t *>(R + 112 * 1024);       // per line                  @ 112 K
+    uint16_t *line_of = reinterpret_cast<uint16_t *>(R + 120 * 1024);         // per box                   @ 120 K
+    uint16_t *seq_of = reinterpret_cast<uint16_t *>(R + 128 * 1024);          // per box                   @ 128 K
+    int4 *obox_s = reinterpret_cast<int4 *>(R + 32 * 1024);                   // phase E: original boxes   @  32 K
     __shared__ int s_warp[33];
-    __shared__ int s_np, s_lines, s_avg_pos;
+    __shared__ int s_np, s_lines, s_avg_pos, s_changed, s_maxl;
     __shared__ long long s_hsum;
     __shared__ double s_ytol;
 
@@ -175,8 +182,58 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     }
     __syncthreads();
 
-    // C. the shrink sweeps (utils.py:521-545), sequential; pairs that stopped intersecting are dropped
+    // C. the shrink sweeps (utils.py:521-545).  Dependency levels first (one sequential pass over the pair list) ...
+    for (int k = threadIdx.x; k < K; k += kRoThreads) last_lv[k] = 0;
+    __syncthreads();
     if (threadIdx.x == 0) {
+        const int np = s_np;
+        int maxl = 0;
+        for (int p = 0; p < np; p++) {
+            const uint32_t pr = pairs[p];
+            const int i = (int)(pr >> 16), j = (int)(pr & 0xffffu);
+            const int l = max((int)last_lv[i], (int)last_lv[j]) + 1;
+            if (l > 255) {
+                maxl = -1;  // too deep for the byte-sized levels: sequential sweeps below
+                break;
+            }
+            last_lv[i] = last_lv[j] = (uint16_t)l;
+            lv[p] = (uint8_t)l;
+            maxl = max(maxl, l);
+        }
+        s_maxl = maxl;
+    }
+    __syncthreads();
+    if (s_maxl >= 0) {
+        // ... then up to 50 sweeps, each level's pairs in parallel; a pair that stopped intersecting gets level 0
+        const int np = s_np, maxl = s_maxl;
+        for (int sweep = 0; sweep < 50; sweep++) {
+            if (threadIdx.x == 0) s_changed = 0;
+            __syncthreads();
+            for (int l = 1; l <= maxl; l++) {
+                for (int p = threadIdx.x; p < np; p += kRoThreads) {
+                    if (lv[p] != l) continue;
+                    const uint32_t pr = pairs[p];
+                    const int i = (int)(pr >> 16), j = (int)(pr & 0xffffu);
+                    int4 a = box[i], c = box[j];
+                    if (ro_intersect(a, c)) {
+                        a.z = ro_shrink(a.x, a.z);
+                        a.w = ro_shrink(a.y, a.w);
+                        c.z = ro_shrink(c.x, c.z);
+                        c.w = ro_shrink(c.y, c.w);
+                        box[i] = a;
+                        box[j] = c;
+                        s_changed = 1;
+                    } else {
+                        lv[p] = 0;
+                    }
+                }
+                __syncthreads();
+            }
+            const int changed = s_changed;
+            __syncthreads();
+            if (!changed) break;
+        }
+    } else if (threadIdx.x == 0) {
         int np = s_np;
         for (int sweep = 0; sweep < 50; sweep++) {
             bool changed = false;
@@ -251,10 +308,7 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
                 for (int l0 = 0; l0 < L && found < 0; l0 += 32) {
                     const int l = l0 + lane;
                     bool ok = false;
-                    if (l < L) {
-                        const double line_cy = ((double)line_sum[l] * 0.5) / (double)line_cnt[l];
-                        ok = fabs(cy - line_cy) <= ytol;
-                    }
+                    if (l < L) ok = fabs(cy - line_cy[l]) <= ytol;
                     const uint32_t m = __ballot_sync(0xffffffffu, ok);
                     if (m) found = l0 + __ffs(m) - 1;
                 }
@@ -268,8 +322,10 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
                     line_sum[L] = s2;
                     line_cnt[L] = 1;
                 }
-                line_of[k] = found;
-                seq_of[k] = r;
+                // np.mean of the members' centres: exact sum (multiples of 0.5), one division
+                line_cy[found] = ((double)line_sum[found] * 0.5) / (double)line_cnt[found];
+                line_of[k] = (uint16_t)found;
+                seq_of[k] = (uint16_t)r;
             }
             found = __shfl_sync(0xffffffffu, found, 0);
             if (found == L) L++;
@@ -283,13 +339,13 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     {
         const int L = s_lines;
         for (int l = threadIdx.x; l < L; l += kRoThreads) {
-            const uint64_t key = ro_orderable(((double)line_sum[l] * 0.5) / (double)line_cnt[l]);
+            const uint64_t key = ro_orderable(line_cy[l]);
             int rank = 0;
             for (int m = 0; m < L; m++) {
-                const uint64_t km = ro_orderable(((double)line_sum[m] * 0.5) / (double)line_cnt[m]);
+                const uint64_t km = ro_orderable(line_cy[m]);
                 rank += (km < key || (km == key && m < l)) ? 1 : 0;
             }
-            line_rank[l] = rank;
+            line_rank[l] = (uint16_t)rank;
         }
     }
     __syncthreads();
@@ -315,7 +371,10 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     ro_bitonic(keys, n2);
     // position r holds the box with insertion order seq: map seq -> box index through the first sort's result.
     // seq_of[] is indexed by box; invert it into line_cnt[] (free now)
-    for (int k = threadIdx.x; k < K; k += kRoThreads) line_cnt[seq_of[k]] = k;
+    for (int k = threadIdx.x; k < K; k += kRoThreads) {
+        line_cnt[seq_of[k]] = k;
+        obox_s[k] = obox_g[pb + k];  // line_sum / line_cy are dead
+    }
     __syncthreads();
 
     // E. utils.py:639 (dict: the LAST box with equal compressed coordinates wins) and _pipeline.py:113-123 (the FIRST
@@ -331,10 +390,10 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
                 break;
             }
         }
-        const int4 ob = obox_g[pb + last];
+        const int4 ob = obox_s[last];
         int first = last;
         for (int w = 0; w < last; w++) {
-            const int4 ow = obox_g[pb + w];
+            const int4 ow = obox_s[w];
             if (ow.x == ob.x && ow.y == ob.y && ow.z == ob.z && ow.w == ob.w) {
                 first = w;
                 break;
@@ -367,8 +426,9 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
         ms_set_error("reading_order: scratch too small");
         return MS_ERR_CAPACITY;
     }
-    const size_t smem = (size_t)kRoMaxBoxes * 16 + (size_t)kRoMaxPairs * 4;
-    static_assert(kRoMaxPairs * 4 >= kRoMaxBoxes * (8 + 8 + 4 * 4), "pair region must hold the sort / line arrays");
+    const size_t smem = (size_t)kRoMaxBoxes * 16 + (size_t)kRoMaxPairs * 5 + (size_t)kRoMaxBoxes * 2;
+    static_assert(kRoMaxPairs * 5 + kRoMaxBoxes * 2 >= 136 * 1024 && kRoMaxBoxes == 4096,
+                  "pair + level region must hold the sort / line arrays laid out in the kernel");
     MS_CUDA(cudaFuncSetAttribute(reading_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     reading_order_kernel<<<n_pages, kRoThreads, smem, st>>>(boxes8, row_stride, counts, cap_per_page, obox, order,
                                                            reordered, flags);

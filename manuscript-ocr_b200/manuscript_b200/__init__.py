@@ -14,7 +14,6 @@ from ._cabi import (  # noqa: F401
     load_library,
 )
 from .ops import (  # noqa: F401
-    convert_to_axis_aligned,
     crop_resize_pad,
     decode_quads_from_maps,
     east_postprocess,

@@ -132,17 +132,6 @@ def east_postprocess(quads_nms, orig_size, target_size=1280, expand_w=0.9, expan
     return out[: m.value].copy()
 
 
-def convert_to_axis_aligned(quads, ctx=None):
-    """EAST._convert_to_axis_aligned (infer.py:149-172) alone: no expansion, unit scale, no filters."""
-    q = np.ascontiguousarray(quads, dtype=np.float32).reshape(-1, 9)
-    if len(q) == 0:
-        return q
-    # contained-box removal cannot be switched off in the fused kernel, so align box by box
-    out = [east_postprocess(q[i:i + 1], (1, 1), target_size=1, expand_w=0.0, expand_h=0.0, axis_aligned=True,
-                            remove_anomalies=False, ctx=ctx) for i in range(len(q))]
-    return np.concatenate(out, axis=0)
-
-
 # ---- _pipeline.py:125-137, 204-221 ---------------------------------------------------------------------------------
 def word_rects(polys, img_h, img_w, min_text_size=5, ctx=None):
     """polys (n,4,2) or (n,>=8) float -> rects (n,4) int32 [x1,y1,x2,y2) and valid (n,) bool: the int32

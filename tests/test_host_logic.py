@@ -88,7 +88,7 @@ def test_reorder_words_follows_pipeline_loop():
 
     words = [word(300.7, 10.2, 380.1, 40.9, "c"), word(10.5, 12.0, 90.0, 41.0, "a"), word(100.2, 11.0, 180.0, 40.0, "b"),
              word(10.1, 80.0, 120.9, 110.0, "d")]
-    assert [w.text for w in reorder_words(words)] == ["a", "b", "c", "d"]
+    assert [w.text for w in reorder_words(words, on_device=False)] == ["a", "b", "c", "d"]
     assert reorder_words([]) == []
 
 

@@ -215,6 +215,10 @@ def run_b200(a):
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # one process per GPU: stay on the cores (and NUMA node) next to this GPU before pinning host memory
+    from manuscript_b200.sharding import bind_to_gpu_cpus
+
+    cpus = bind_to_gpu_cpus(local)
     dist = None
     if world > 1:
         import torch.distributed as dist_mod
@@ -384,7 +388,7 @@ def run_b200(a):
         "config": {"workload": workload_name(a), "pages_per_gpu": P, "page": S, "map": M, "words_per_page": a.words,
                    "candidates_per_page": n_cand / P, "boxes_per_page": n_boxes / P, "crops_per_page": n_crops / P,
                    "l2": "inputs (maps + pages) of one step exceed L2 (no flush needed)",
-                   "reading_order": bool(a.reading_order),
+                   "reading_order": bool(a.reading_order), "host_cpus_rank0": (len(cpus) if cpus else None),
                    "parallelism": f"pages sharded over {world} GPU(s), no collective"},
         "boxes_per_sec": total_boxes * a.steps / (ms_total * 1e-3),
         "gpu_launches": int(launches),

@@ -35,4 +35,29 @@ def run_sharded(n_pages, page_fn, group=None):
     return gather_page_results(mine, world, group)
 
 
-__all__ = ["shard_pages", "gather_page_results", "run_sharded"]
+def bind_to_gpu_cpus(device_index):
+    """Pin this process to the CPU cores NVML reports as local to GPU `device_index` (same NUMA node / PCIe root), so
+    that the pinned host buffers it allocates afterwards are first-touched next to that GPU.  With one process per
+    GPU this keeps every rank's H2D stream on its own socket.  Returns the CPU set used, or None if NVML or the
+    affinity mask is unavailable (the binding is an optimisation, never a requirement)."""
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        allowed = os.sched_getaffinity(0)
+        words = (max(allowed) // 64) + 1 if allowed else 1
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, max(words, (os.cpu_count() or 64) // 64 + 1))
+        cpus = {w * 64 + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1}
+        cpus &= allowed
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return cpus
+    except Exception:
+        return None
+
+
+__all__ = ["shard_pages", "gather_page_results", "run_sharded", "bind_to_gpu_cpus"]

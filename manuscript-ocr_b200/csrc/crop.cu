@@ -15,15 +15,20 @@
 // HBM roofline: per crop 3*w*h source bytes read + 3*ih*iw*4 bytes written (49 152 B at 32x128): the
 // kernel is write dominated.
 //
-// Kernel shape (persistent CTAs, one crop per CTA iteration, double buffered):
-//   * warp 0 stages the NEXT crop's source rows into shared memory with TMA bulk copies
-//     (cp.async.bulk global->shared, one 16-byte-aligned span per row, completion on an mbarrier)
-//     while all warps resample the CURRENT crop out of the other buffer;
-//   * per-crop axis tables (OpenCV's decimation / linear coefficient tables) are built once per crop
-//     in shared memory -- the float64 table arithmetic runs nw+nh times, not nw*nh times;
-//   * resampled pixels are normalised and stored straight to the CHW batch (coalesced 4-byte stores
-//     along x); the 255-padding is written as constant 16-byte streaming stores.  No canvas round trip.
-//   * crops whose source rows do not fit the staging buffer read global memory directly (same code).
+// Kernels:
+//   crop_plan_kernel        thread per crop: the float64 sizing arithmetic of transforms.py:91-98, interpolation mode,
+//                           staging decision -> Plan
+//   crop_resize_pad_kernel  the crops with Plan::fast (INTER_AREA with shrink factors below 3 -- what shrinking a
+//                           word box to a 32- or 64-pixel-high canvas gives): persistent, warp specialised, 4 CTAs
+//                           per SM.  Warp 0 (producer) stages the next crop's source rows with TMA bulk copies
+//                           (cp.async.bulk global->shared, one 16-byte-aligned span per row, completion on an
+//                           mbarrier) into a double-buffered stage, builds OpenCV's coefficient tables in shared
+//                           memory (structure of arrays) and writes the 255-padding as constant 16-byte streaming
+//                           stores; warps 1..5 (consumers) resample column strips out of shared memory (aligned
+//                           32-bit loads + funnel shift + PRMT u8->f32, 4 taps) and store normalised pixels straight
+//                           into the CHW batch.  full / empty mbarriers, no CTA-wide barrier in the loop.
+//   crop_generic_kernel     every other crop (copy, INTER_LINEAR upscale, integer-ratio or long-table INTER_AREA,
+//                           rows too long for the stage): one CTA per crop from global memory, same arithmetic.
 #include "ms_internal.cuh"
 
 namespace {
@@ -39,7 +44,8 @@ struct Plan {
     int interp;  // 0 copy, 1 linear, 2 area integer-ratio, 3 area general
     int isx, isy;
     int ok;
-    int staged;  // source rows staged through TMA into shared memory
+    int staged;  // source rows can be staged through TMA into shared memory
+    int fast;    // handled by the persistent TMA kernel (INTER_AREA, shrink factors < 3, staged); else generic kernel
     int pitch;   // shared-memory row pitch (bytes) when staged
     double scale_x, scale_y;
 };
@@ -68,6 +74,7 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
     p.ok = p.page >= 0 && p.page < n_pages && p.w > 0 && p.h > 0 && p.x1 >= 0 && p.y1 >= 0 && cr[3] <= img_w &&
            cr[4] <= img_h;
     p.staged = 0;
+    p.fast = 0;
     p.pitch = 0;
     p.nw = p.nh = p.y0 = p.interp = p.isx = p.isy = 0;
     p.scale_x = p.scale_y = 1.0;
@@ -108,6 +115,8 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
         p.staged = 1;
         p.pitch = pitch;
     }
+    // a decimation window shorter than 3 source pixels touches at most 4 of them: every table entry has <= 4 taps
+    p.fast = p.staged && p.interp == 3 && p.scale_x < 2.999 && p.scale_y < 2.999 && p.w < 65536 && p.h < 65536;
 }
 
 // OpenCV computeResizeAreaTab for destination index d
@@ -209,11 +218,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-// resample one destination pixel (3 channels); `row(sy)` gives the address of source pixel (x=0) of row sy
-template <typename RowFn>
-__device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, RowFn row, unsigned char &o0,
-                                            unsigned char &o1, unsigned char &o2)
+// Exact but slow: any interpolation mode, any tap count; table entries recomputed per pixel, source read from global
+// memory.  Used by crop_generic_kernel for every crop the persistent TMA kernel does not take.
+__device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, const uint8_t *gsrc, size_t stride,
+                                            unsigned char &o0, unsigned char &o1, unsigned char &o2)
 {
+    auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
     if (p.interp == 0) {
         const unsigned char *s = row(dy) + dx * 3;
         o0 = s[0];
@@ -261,7 +271,6 @@ __device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, RowFn
             o2 = sat_u8(cv_round((float)s2 * inv));
         }
     } else {
-        // slow general path (tables longer than 4 taps, or rows not staged): entries computed per pixel
         const AxisEnt ex = area_entry(dx, p.scale_x, p.w), ey = area_entry(dy, p.scale_y, p.h);
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
         for (int j = 0; j < ey.n; j++) {
@@ -297,59 +306,30 @@ __device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
     return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)) - 8388608.0f;
 }
 
-// INTER_AREA general path for one destination pixel when both tables have <= 4 taps and the source rows are
-// staged: each row contributes 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit shared-memory words;
-// taps beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).  wx / wy are the tap weights the
-// producer precomputed from the same table entries.  Same products and the same summation order as resample_px's
-// general branch.
-template <bool kRowAligned>
-__device__ __forceinline__ void resample_area4(const unsigned char *smem_base, uint32_t buf_off, int pitch, uint32_t a0,
-                                               uint32_t sstep, int xs0, int ys0, int yn, const float4 wx,
-                                               const float4 wy, float &r0, float &r1, float &r2)
+// Horizontal pass of the INTER_AREA general path for one (source row, destination column) whose table has <= 4 taps,
+// out of the staged rows: 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit shared-memory words; taps
+// beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).  Same products and the same summation order as
+// resample_px's general branch.  `o` = shared-memory byte offset of the row's first tap.
+__device__ __forceinline__ void hrow_area4(const unsigned char *smem_base, uint32_t o, const float4 wx, float &b0,
+                                           float &b1, float &b2)
 {
     const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
-    const float wyv[4] = {wy.x, wy.y, wy.z, wy.w};
-    float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        if (j < yn) {
-            const float beta = wyv[j];
-            const uint32_t sy = (uint32_t)(ys0 + j);
-            // kRowAligned: the page stride is a multiple of 16, every row has the same misalignment a0
-            const uint32_t mis = kRowAligned ? a0 : ((a0 + sy * sstep) & 15u);
-            const uint32_t o = buf_off + sy * (uint32_t)pitch + mis + (uint32_t)xs0 * 3u;
-            const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
-            const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
-            const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh),
-                           v2 = __funnelshift_r(w2, w3, sh);
-            // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
-            float b0 = byte_f32(v0, 0x7650) * wx.x;
-            float b1 = byte_f32(v0, 0x7651) * wx.x;
-            float b2 = byte_f32(v0, 0x7652) * wx.x;
-            b0 = b0 + byte_f32(v0, 0x7653) * wx.y;
-            b1 = b1 + byte_f32(v1, 0x7650) * wx.y;
-            b2 = b2 + byte_f32(v1, 0x7651) * wx.y;
-            b0 = b0 + byte_f32(v1, 0x7652) * wx.z;
-            b1 = b1 + byte_f32(v1, 0x7653) * wx.z;
-            b2 = b2 + byte_f32(v2, 0x7650) * wx.z;
-            b0 = b0 + byte_f32(v2, 0x7651) * wx.w;
-            b1 = b1 + byte_f32(v2, 0x7652) * wx.w;
-            b2 = b2 + byte_f32(v2, 0x7653) * wx.w;
-            if (j == 0) {
-                sum0 = beta * b0;
-                sum1 = beta * b1;
-                sum2 = beta * b2;
-            } else {
-                sum0 += beta * b0;
-                sum1 += beta * b1;
-                sum2 += beta * b2;
-            }
-        }
-    }
-    // cvRound (round half to even), kept as floats: the weights sum to 1 within rounding, so the value is in [0, 255]
-    r0 = rintf(sum0);
-    r1 = rintf(sum1);
-    r2 = rintf(sum2);
+    const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
+    const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+    // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
+    b0 = byte_f32(v0, 0x7650) * wx.x;
+    b1 = byte_f32(v0, 0x7651) * wx.x;
+    b2 = byte_f32(v0, 0x7652) * wx.x;
+    b0 = b0 + byte_f32(v0, 0x7653) * wx.y;
+    b1 = b1 + byte_f32(v1, 0x7650) * wx.y;
+    b2 = b2 + byte_f32(v1, 0x7651) * wx.y;
+    b0 = b0 + byte_f32(v1, 0x7652) * wx.z;
+    b1 = b1 + byte_f32(v1, 0x7653) * wx.z;
+    b2 = b2 + byte_f32(v2, 0x7650) * wx.z;
+    b0 = b0 + byte_f32(v2, 0x7651) * wx.w;
+    b1 = b1 + byte_f32(v2, 0x7652) * wx.w;
+    b2 = b2 + byte_f32(v2, 0x7653) * wx.w;
 }
 
 // plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
@@ -372,13 +352,12 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
     }
 }
 
-// producer warp: the coefficient tables of one crop, 32 lanes
-// producer warp: the INTER_AREA coefficient tables of one crop for the 4-tap fast path, structure of arrays:
-// tab[0][i] = s0 | n << 16 (n = 0xffff when the entry has more than 4 taps), tab[1..4][i] = tap weights (0 beyond n).
-// x entries occupy [0, iw), y entries [iw, iw + ih) of every array.
+// producer warp: the INTER_AREA coefficient tables of one crop for the 4-tap path, structure of arrays:
+// tab[0][i] = s0 | n << 16, tab[1..4][i] = tap weights (0 beyond n); x entries occupy [0, iw), y entries
+// [iw, iw + ih) of every array.  Plan::fast guarantees n <= 4; an entry that violates it is stored with n = 0xffff
+// and makes the consumers hand the crop to the generic kernel.
 __device__ __forceinline__ void build_tables(const Plan &p, uint32_t *tab, int tab_n, int iw, int lane)
 {
-    if (!(p.ok && p.staged && p.interp == 3)) return;
     float *tw = reinterpret_cast<float *>(tab);
     for (int t = lane; t < p.nw + p.nh; t += 32) {
         const bool isx = t < p.nw;
@@ -397,11 +376,11 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// producer warp: everything outside the pasted rectangle is the 255 canvas (transforms.py:100), 1.0f after
-// normalisation; written as constant 16-byte streaming stores
+// Everything outside the pasted rectangle is the 255 canvas (transforms.py:100), 1.0f after normalisation; written
+// as constant 16-byte streaming stores by `nthreads` cooperating threads.
 template <bool kWriteF32, bool kWriteU8>
 __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, float *dstf, uint8_t *dstu, int vec_ok,
-                                              int lane)
+                                              int tid, int nthreads)
 {
     const int plane = ih * iw;
     const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
@@ -415,24 +394,24 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
 #pragma unroll
             for (int c = 0; c < 3; c++) {
                 float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
-                for (int i = lane; i < top4; i += 32) __stcs(base4 + i, one4);
+                for (int i = tid; i < top4; i += nthreads) __stcs(base4 + i, one4);
                 float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
-                for (int i = lane; i < bot4; i += 32) __stcs(bot + i, one4);
+                for (int i = tid; i < bot4; i += nthreads) __stcs(bot + i, one4);
                 if (tail4 > 0) {
                     const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
-                    for (int i = lane; i < nh * tail4; i += 32) {
+                    for (int i = tid; i < nh * tail4; i += nthreads) {
                         const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
                         __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
                                one4);
                     }
                 }
-                for (int i = lane; i < nh * fr; i += 32) {
+                for (int i = tid; i < nh * fr; i += nthreads) {
                     const int r = i / fr, k = i - r * fr;
                     __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
                 }
             }
         } else {
-            for (int e = lane; e < 3 * plane; e += 32) {
+            for (int e = tid; e < 3 * plane; e += nthreads) {
                 int c = e / plane, rem = e - c * plane;
                 int y = rem / iw, x = rem - y * iw;
                 if (!(y >= y0 && y < y0 + nh && x < nw)) dstf[e] = one;
@@ -440,7 +419,7 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
         }
     }
     if (kWriteU8) {
-        for (int e = lane; e < plane; e += 32) {
+        for (int e = tid; e < plane; e += nthreads) {
             int y = e / iw, x = e - y * iw;
             if (!(y >= y0 && y < y0 + nh && x < nw)) {
                 dstu[(size_t)e * 3] = 255;
@@ -451,11 +430,13 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
     }
 }
 
-// Warp-specialised persistent kernel.  Warp 0 (producer) walks this CTA's crops one ahead of the consumers: it
-// writes the crop's padding, waits until the stage buffer is released, copies the plan, issues the TMA row
-// copies, builds the axis tables and signals full[b].  Warps 1..7 (consumers) wait on full[b], resample the
-// pasted rectangle straight into the CHW batch and release the buffer on empty[b].  No CTA-wide barrier inside
-// the loop: consumer warps drift apart by up to one crop, which absorbs the uneven per-pixel tap counts.
+// Warp-specialised persistent kernel for the crops with Plan::fast.  Warp 0 (producer) walks this CTA's crops one
+// ahead of the consumers: it writes the crop's padding, waits until the stage buffer is released, issues the TMA row
+// copies, builds the axis tables and signals full[b].  Warps 1..5 (consumers) wait on full[b], resample the pasted
+// rectangle straight into the CHW batch and release the buffer on empty[b].  No CTA-wide barrier inside the loop.
+// Each consumer thread resamples a column strip (one destination column, G consecutive destination rows): with a
+// shrink factor near 2 neighbouring destination rows share their boundary source row, so a strip needs ~(2G + 1)
+// horizontal row sums instead of 3G; per-pixel arithmetic and its order are unchanged.
 constexpr int kConsumerWarps = kThreads / 32 - 1;
 
 template <bool kWriteF32, bool kWriteU8>
@@ -463,13 +444,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w, const Plan *__restrict__ plans,
                            const int32_t *__restrict__ n_crops_dev, const int32_t *__restrict__ range,
                            int64_t crops_cap, int ih, int iw, float *__restrict__ batch,
-                           uint8_t *__restrict__ canvas_out, int vec_ok)
+                           uint8_t *__restrict__ canvas_out, int vec_ok, uint8_t *__restrict__ redo)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + 2 * kSrcBuf);  // [2 stages][kTabWords][iw + ih]
     const int tab_n = iw + ih;
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
-    __shared__ Plan s_plan[2];
 
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -477,7 +457,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     const size_t stride = (size_t)img_w * 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int plane = ih * iw;
-    const float inv = 1.0f / 127.5f;
+    const uint32_t sstep = (uint32_t)(stride & 15);  // per-row change of the 16-byte misalignment
 
     if (threadIdx.x == 0) {
         mbar_init(&s_full[0], 1);
@@ -491,15 +471,16 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     if (warp == 0) {
         // ---------------- producer ----------------
         int k = 0;
-        for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x, k++) {
-            const int b = k & 1;
+        for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
             const Plan p = plans[ci];
+            if (!p.fast) continue;
+            const int b = k & 1;
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
-                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane);
+                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32);
             if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
             // TMA first: its latency overlaps the float64 table arithmetic below
             uint32_t bytes = 0;
-            if (p.staged) {
+            {
                 const uint8_t *src = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
                 unsigned char *buf = smem + b * kSrcBuf;
                 for (int r = lane; r < p.h; r += 32) {
@@ -512,15 +493,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
             }
-            if (lane == 0) s_plan[b] = p;
             build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane);
-            __syncwarp();  // every lane's plan / table stores are ordered before lane 0's releasing arrive
-            if (lane == 0) {
-                if (bytes)
-                    mbar_expect_tx(&s_full[b], bytes);
-                else
-                    mbar_arrive(&s_full[b]);
-            }
+            __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
+            if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
+            k++;
         }
         return;
     }
@@ -528,60 +504,77 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     // ---------------- consumers ----------------
     const int ct = (warp - 1) * 32 + lane;
     constexpr int kCT = kConsumerWarps * 32;
+    const float inv = 1.0f / 127.5f;
     int k = 0;
-    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x, k++) {
+    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
+        const Plan *pg = plans + ci;
+        if (!pg->fast) continue;
         const int b = k & 1;
+        const int nw = pg->nw, nh = pg->nh, y0 = pg->y0;
+        const uint32_t pitch = (uint32_t)pg->pitch;
+        const uint32_t a0 = (uint32_t)((reinterpret_cast<uintptr_t>(pages) + (size_t)pg->page * img_h * stride +
+                                        (size_t)pg->y1 * stride + (size_t)pg->x1 * 3) &
+                                       15);
+        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+        // strip height: keep the consumer threads evenly loaded
+        int G = 1;
+        {
+            int best = 0x7fffffff;
+            for (int g = 8; g >= 1; g >>= 1) {
+                const int items = ((nh + g - 1) / g) * nw;
+                const int cost = ((items + kCT - 1) / kCT) * (2 * g + 1);
+                if (cost < best) {
+                    best = cost;
+                    G = g;
+                }
+            }
+        }
+        const int nitems = ((nh + G - 1) / G) * nw;
+        const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
+        const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
+        const float *tw = reinterpret_cast<const float *>(tab);
+        const uint32_t stage_off = (uint32_t)(b * kSrcBuf);
+
         mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
-        const Plan p = s_plan[b];
-        if (p.ok) {
-            float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
-            uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
-            const int nw = p.nw, nh = p.nh, y0 = p.y0;
-            const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
-            const float *tw = reinterpret_cast<const float *>(tab);
-            const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-            const unsigned char *sbuf = smem + b * kSrcBuf;
-            const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(gsrc) & 15);
-            const uint32_t sstep = (uint32_t)(stride & 15);  // per-row change of the 16-byte misalignment
-            const int npx = nw * nh;
-            const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
-            for (int t = ct; t < npx; t += kCT) {
-                const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
-                unsigned char o0, o1, o2;
-                uint32_t px = 0xffff0000u, py = 0xffff0000u;
-                if (p.staged && p.interp == 3) {
-                    px = tab[dx];
-                    py = tab[iw + dy];
+        bool bad = false;
+        for (int t = ct; t < nitems; t += kCT) {
+            const int grp = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - grp * nw;
+            const uint32_t px = tab[dx];
+            bad = bad || (px >> 16) > 4u;
+            const float4 wx = make_float4(tw[tab_n + dx], tw[2 * tab_n + dx], tw[3 * tab_n + dx], tw[4 * tab_n + dx]);
+            const uint32_t xoff = stage_off + (px & 0xffffu) * 3u;
+            int last_r = -1;
+            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+            const int dy_end = min(nh, grp * G + G);
+            for (int dy = grp * G; dy < dy_end; dy++) {
+                const uint32_t py = tab[iw + dy];
+                bad = bad || (py >> 16) > 4u;
+                const int ys0 = (int)(py & 0xffffu), yn = min((int)(py >> 16), 4);
+                const float wyv[4] = {tw[tab_n + iw + dy], tw[2 * tab_n + iw + dy], tw[3 * tab_n + iw + dy],
+                                      tw[4 * tab_n + iw + dy]};
+                // row 0 is the previous destination row's last source row when the two share it (uniform branch);
+                // the other rows are independent horizontal passes
+                const uint32_t rbase = xoff + (uint32_t)ys0 * pitch;
+                if (ys0 != last_r) {
+                    const uint32_t mis = sstep == 0 ? a0 : ((a0 + (uint32_t)ys0 * sstep) & 15u);
+                    hrow_area4(smem, rbase + mis, wx, b0, b1, b2);
                 }
-                float f0, f1, f2;
-                if ((px >> 16) <= 4u && (py >> 16) <= 4u) {
-                    const float4 wx = make_float4(tw[tab_n + dx], tw[2 * tab_n + dx], tw[3 * tab_n + dx],
-                                                  tw[4 * tab_n + dx]);
-                    const float4 wy = make_float4(tw[tab_n + iw + dy], tw[2 * tab_n + iw + dy], tw[3 * tab_n + iw + dy],
-                                                  tw[4 * tab_n + iw + dy]);
-                    if (sstep == 0)
-                        resample_area4<true>(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, (int)(px & 0xffffu),
-                                             (int)(py & 0xffffu), (int)(py >> 16), wx, wy, f0, f1, f2);
-                    else
-                        resample_area4<false>(smem, (uint32_t)(b * kSrcBuf), p.pitch, a0, sstep, (int)(px & 0xffffu),
-                                              (int)(py & 0xffffu), (int)(py >> 16), wx, wy, f0, f1, f2);
-                    o0 = sat_u8((int)f0);  // only the uint8 canvas output uses these
-                    o1 = sat_u8((int)f1);
-                    o2 = sat_u8((int)f2);
-                } else {
-                    if (p.staged) {
-                        auto row = [&](int sy) -> const unsigned char * {
-                            return sbuf + (size_t)sy * p.pitch + ((a0 + (uint32_t)sy * sstep) & 15u);
-                        };
-                        resample_px(p, dx, dy, row, o0, o1, o2);
-                    } else {
-                        auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
-                        resample_px(p, dx, dy, row, o0, o1, o2);
+                float sum0 = wyv[0] * b0, sum1 = wyv[0] * b1, sum2 = wyv[0] * b2;
+#pragma unroll
+                for (int j = 1; j < 4; j++) {
+                    if (j < yn) {
+                        const uint32_t r = (uint32_t)(ys0 + j);
+                        const uint32_t mis = sstep == 0 ? a0 : ((a0 + r * sstep) & 15u);
+                        hrow_area4(smem, rbase + (uint32_t)j * pitch + mis, wx, b0, b1, b2);
+                        sum0 += wyv[j] * b0;
+                        sum1 += wyv[j] * b1;
+                        sum2 += wyv[j] * b2;
                     }
-                    f0 = (float)o0;
-                    f1 = (float)o1;
-                    f2 = (float)o2;
                 }
+                last_r = ys0 + yn - 1;  // b0..b2 hold that row's horizontal sums
+                // cvRound (half to even), kept as floats: the weights sum to 1 within rounding -> [0, 255]
+                const float f0 = rintf(sum0), f1 = rintf(sum1), f2 = rintf(sum2);
                 const int at = (y0 + dy) * iw + dx;
                 if (kWriteF32) {
                     __stcs(dstf + at, (f0 - 127.5f) * inv);
@@ -589,20 +582,72 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                     __stcs(dstf + 2 * plane + at, (f2 - 127.5f) * inv);
                 }
                 if (kWriteU8) {
-                    dstu[(size_t)at * 3] = o0;
-                    dstu[(size_t)at * 3 + 1] = o1;
-                    dstu[(size_t)at * 3 + 2] = o2;
+                    dstu[(size_t)at * 3] = sat_u8((int)f0);
+                    dstu[(size_t)at * 3 + 1] = sat_u8((int)f1);
+                    dstu[(size_t)at * 3 + 2] = sat_u8((int)f2);
                 }
             }
         }
+        if (bad) redo[ci] = 1;  // a table entry with more than 4 taps: the generic kernel redoes the crop
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[b]);
+        k++;
+    }
+}
+
+// Every crop the persistent kernel does not take (same size copy, INTER_LINEAR upscale, integer-ratio INTER_AREA,
+// shrink factors >= 3, rows too long for the stage, crops flagged `redo`): one CTA per crop, source read from global
+// memory, exact per-pixel arithmetic.  Also writes the all-padding canvas of invalid crops.
+template <bool kWriteF32, bool kWriteU8>
+__global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w,
+                                                           const Plan *__restrict__ plans,
+                                                           const int32_t *__restrict__ n_crops_dev,
+                                                           const int32_t *__restrict__ range, int64_t crops_cap, int ih,
+                                                           int iw, float *__restrict__ batch,
+                                                           uint8_t *__restrict__ canvas_out, int vec_ok,
+                                                           const uint8_t *__restrict__ redo)
+{
+    const int64_t begin = range ? range[0] : 0;
+    int64_t n_crops = range ? range[1] : *n_crops_dev;
+    if (n_crops > crops_cap) n_crops = crops_cap;
+    const size_t stride = (size_t)img_w * 3;
+    const int plane = ih * iw;
+    const float inv = 1.0f / 127.5f;
+    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
+        const Plan p = plans[ci];
+        if (p.fast && !redo[ci]) continue;
+        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+        write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
+        if (!p.ok) continue;
+        const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+        const int npx = p.nw * p.nh;
+        for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+            const int dy = t / p.nw, dx = t - dy * p.nw;
+            unsigned char o0, o1, o2;
+            resample_px(p, dx, dy, gsrc, stride, o0, o1, o2);
+            const int at = (p.y0 + dy) * iw + dx;
+            if (kWriteF32) {
+                dstf[at] = ((float)o0 - 127.5f) * inv;
+                dstf[plane + at] = ((float)o1 - 127.5f) * inv;
+                dstf[2 * plane + at] = ((float)o2 - 127.5f) * inv;
+            }
+            if (kWriteU8) {
+                dstu[(size_t)at * 3] = o0;
+                dstu[(size_t)at * 3 + 1] = o1;
+                dstu[(size_t)at * 3 + 2] = o2;
+            }
+        }
     }
 }
 
 }  // namespace
 
-size_t msk_crop_scratch(int64_t crops_cap) { return (size_t)(crops_cap > 0 ? crops_cap : 0) * sizeof(Plan) + 1024; }
+size_t msk_crop_scratch(int64_t crops_cap)
+{
+    const size_t n = (size_t)(crops_cap > 0 ? crops_cap : 0);
+    return n * sizeof(Plan) + n + 2048;
+}
 
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
@@ -623,10 +668,12 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
         return MS_ERR_INVALID;
     }
     Plan *plans = bump.take<Plan>((size_t)crops_cap);
-    if (!plans) {
+    uint8_t *redo = bump.take<uint8_t>((size_t)crops_cap);
+    if (!plans || !redo) {
         ms_set_error("crop: scratch too small");
         return MS_ERR_CAPACITY;
     }
+    MS_CUDA(cudaMemsetAsync(redo, 0, (size_t)crops_cap, st));
     {
         int64_t g = (crops_cap + 255) / 256;
         if (g > (int64_t)ctx->num_sms * 8) g = (int64_t)ctx->num_sms * 8;
@@ -639,13 +686,18 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->num_sms * per_sm;
     if (grid > crops_cap) grid = crops_cap;
+    int64_t ggrid = (int64_t)ctx->num_sms * 8;
+    if (ggrid > crops_cap) ggrid = crops_cap;
     const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
 #define MS_CROP_LAUNCH(F32, U8)                                                                                        \
     do {                                                                                                               \
         auto kfn = crop_resize_pad_kernel<F32, U8>;                                                                    \
         MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
         kfn<<<(int)grid, kThreads, smem, st>>>(pages, img_h, img_w, plans, n_crops, range, crops_cap, out_h, out_w,    \
-                                              batch_f32, canvas_u8, vec_ok);                                           \
+                                              batch_f32, canvas_u8, vec_ok, redo);                                     \
+        MS_LAUNCH_CHECK(ctx);                                                                                          \
+        crop_generic_kernel<F32, U8><<<(int)ggrid, 256, 0, st>>>(pages, img_h, img_w, plans, n_crops, range, crops_cap, \
+                                                                 out_h, out_w, batch_f32, canvas_u8, vec_ok, redo);   \
     } while (0)
     if (batch_f32 && canvas_u8)
         MS_CROP_LAUNCH(true, true);

@@ -613,31 +613,42 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__rest
     const size_t stride = (size_t)img_w * 3;
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
-    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
-        const Plan p = plans[ci];
-        if (p.fast && !redo[ci]) continue;
-        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
-        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
-        write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
-        if (!p.ok) continue;
-        const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-        const int npx = p.nw * p.nh;
-        for (int t = threadIdx.x; t < npx; t += blockDim.x) {
-            const int dy = t / p.nw, dx = t - dy * p.nw;
-            unsigned char o0, o1, o2;
-            resample_px(p, dx, dy, gsrc, stride, o0, o1, o2);
-            const int at = (p.y0 + dy) * iw + dx;
-            if (kWriteF32) {
-                dstf[at] = ((float)o0 - 127.5f) * inv;
-                dstf[plane + at] = ((float)o1 - 127.5f) * inv;
-                dstf[2 * plane + at] = ((float)o2 - 127.5f) * inv;
-            }
-            if (kWriteU8) {
-                dstu[(size_t)at * 3] = o0;
-                dstu[(size_t)at * 3 + 1] = o1;
-                dstu[(size_t)at * 3 + 2] = o2;
+    __shared__ int s_list[256];
+    __shared__ int s_n;
+    // each CTA scans 256 crops at a time (one per thread) for the few that are its business, then works through them
+    for (int64_t base = begin + (int64_t)blockIdx.x * 256; base < n_crops; base += (int64_t)gridDim.x * 256) {
+        if (threadIdx.x == 0) s_n = 0;
+        __syncthreads();
+        const int64_t mine = base + threadIdx.x;
+        if (mine < n_crops && (!plans[mine].fast || redo[mine])) s_list[atomicAdd(&s_n, 1)] = (int)(mine - base);
+        __syncthreads();
+        const int todo = s_n;
+        for (int li = 0; li < todo; li++) {
+            const int64_t ci = base + s_list[li];
+            const Plan p = plans[ci];
+            float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+            uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+            write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
+            const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+            const int npx = p.ok ? p.nw * p.nh : 0;
+            for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+                const int dy = t / p.nw, dx = t - dy * p.nw;
+                unsigned char o0, o1, o2;
+                resample_px(p, dx, dy, gsrc, stride, o0, o1, o2);
+                const int at = (p.y0 + dy) * iw + dx;
+                if (kWriteF32) {
+                    dstf[at] = ((float)o0 - 127.5f) * inv;
+                    dstf[plane + at] = ((float)o1 - 127.5f) * inv;
+                    dstf[2 * plane + at] = ((float)o2 - 127.5f) * inv;
+                }
+                if (kWriteU8) {
+                    dstu[(size_t)at * 3] = o0;
+                    dstu[(size_t)at * 3 + 1] = o1;
+                    dstu[(size_t)at * 3 + 2] = o2;
+                }
             }
         }
+        __syncthreads();  // s_list is reused by the next chunk
     }
 }
 

@@ -18,12 +18,12 @@ def main():
         v = v / 1e3 if unit == "ns" else (v * 1e3 if unit == "ms" else v)
         seq.append((name, v))
     own = [(n, v) for n, v in seq if not n.startswith("void at::") and "elementwise" not in n and "nccl" not in n]
-    # one step = from a decode_mark_kernel to the next crop kernel; take the last complete one
-    ends = [i for i, (n, _) in enumerate(own) if "crop_resize_pad" in n]
+    # one step = from a decode_mark_kernel up to (not including) the next one; take the last complete one
     starts = [i for i, (n, _) in enumerate(own) if "decode_mark" in n]
-    end = ends[-1]
-    start = max(s for s in starts if s < end)
-    step = own[start:end + 1]
+    crops = [i for i, (n, _) in enumerate(own) if "crop_resize_pad" in n]
+    start = max(s for s in starts if any(c > s for c in crops))
+    later = [s for s in starts if s > start]
+    step = own[start:(later[0] if later else len(own))]
     tot = sum(v for _, v in step)
     print(f"# {path}: last complete step, {len(step)} launches, {tot:.1f} us (cold-cache, serialised; compare shares)")
     agg = {}

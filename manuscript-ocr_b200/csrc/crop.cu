@@ -380,7 +380,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // as constant 16-byte streaming stores by `nthreads` cooperating threads.
 template <bool kWriteF32, bool kWriteU8>
 __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, float *dstf, uint8_t *dstu, int vec_ok,
-                                              int tid, int nthreads)
+                                              int tid, int nthreads, int c_begin = 0, int c_end = 3)
 {
     const int plane = ih * iw;
     const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
@@ -391,8 +391,7 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
             const int nw4 = (nw + 3) & ~3;
             const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
             const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
-#pragma unroll
-            for (int c = 0; c < 3; c++) {
+            for (int c = c_begin; c < c_end; c++) {
                 float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
                 for (int i = tid; i < top4; i += nthreads) __stcs(base4 + i, one4);
                 float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
@@ -411,14 +410,14 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
                 }
             }
         } else {
-            for (int e = tid; e < 3 * plane; e += nthreads) {
+            for (int e = c_begin * plane + tid; e < c_end * plane; e += nthreads) {
                 int c = e / plane, rem = e - c * plane;
                 int y = rem / iw, x = rem - y * iw;
                 if (!(y >= y0 && y < y0 + nh && x < nw)) dstf[e] = one;
             }
         }
     }
-    if (kWriteU8) {
+    if (kWriteU8 && c_begin == 0) {
         for (int e = tid; e < plane; e += nthreads) {
             int y = e / iw, x = e - y * iw;
             if (!(y >= y0 && y < y0 + nh && x < nw)) {
@@ -438,6 +437,7 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
 // shrink factor near 2 neighbouring destination rows share their boundary source row, so a strip needs ~(2G + 1)
 // horizontal row sums instead of 3G; per-pixel arithmetic and its order are unchanged.
 constexpr int kConsumerWarps = kThreads / 32 - 1;
+constexpr int kProducerChannels = 2;  // output channels whose padding the producer writes (the rest: consumers)
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -476,7 +476,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             if (!p.fast) continue;
             const int b = k & 1;
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
-                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32);
+                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
+                                              kProducerChannels);
             if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
             // TMA first: its latency overlaps the float64 table arithmetic below
             uint32_t bytes = 0;
@@ -536,6 +537,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         const float *tw = reinterpret_cast<const float *>(tab);
         const uint32_t stage_off = (uint32_t)(b * kSrcBuf);
 
+        // the padding of the remaining channel(s) is written by the consumers while the TMA copies are in flight
+        write_padding<kWriteF32, kWriteU8>(*pg, ih, iw, dstf, dstu, vec_ok, ct, kCT, kProducerChannels, 3);
         mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
         bool bad = false;
         for (int t = ct; t < nitems; t += kCT) {

@@ -33,11 +33,19 @@ class PageBatchResult:
     box_counts: object   # (P,) int32
     crops: object        # (crops_cap, 5) int32 rows [page, x1, y1, x2, y2), first n_crops valid
     n_crops: object      # () / (1,) int32
-    batch: object        # (crops_cap, 3, h, w) f32 on the device (None if not requested)
+    batch: object        # (crops_cap | n_crops, 3, h, w) f32 CUDA tensor (None if not requested)
     flags: object        # (P,) int32 MS_FLAG_* bits
 
     def page_boxes(self, p):
         return self.boxes[p, : int(self.box_counts[p])]
+
+
+class _DeviceArray:
+    """Minimal __cuda_array_interface__ holder: lets torch view library-owned device memory without a copy."""
+
+    def __init__(self, ptr, shape, typestr="<f4"):
+        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
+                                         "data": (int(ptr), False), "version": 2, "strides": None}
 
 
 def _raise_for_flags(flags):
@@ -177,5 +185,11 @@ class PageBatch:
             check(rc)
         elif rc not in (0, -3, -4):
             check(rc)
+        batch = None
+        n_crops = int(h["n_crops"][0])
+        if self.want_batch and dev_batch.value and n_crops > 0:
+            # the crop batch stays on the device (library-owned staging, valid until the next call on this runner)
+            batch = torch.as_tensor(_DeviceArray(dev_batch.value, (n_crops, 3, self.out_h, self.out_w)),
+                                    device=self.device)
         return PageBatchResult(h["boxes"].numpy(), h["counts"].numpy(), h["crops"].numpy(), h["n_crops"].numpy(),
-                               dev_batch.value, h["flags"].numpy())
+                               batch, h["flags"].numpy())

@@ -65,6 +65,15 @@ def test_page_batch_vs_oracle(torch_cuda, page, words, n_pages):
     np.testing.assert_array_equal(res_h.boxes[0, : counts[0]], boxes[0, : counts[0]])
     assert int(res_h.n_crops[0]) == n_crops
     np.testing.assert_array_equal(res_h.crops[:n_crops], crops)
+    assert res_h.batch.is_cuda and tuple(res_h.batch.shape) == (n_crops, 3, 32, 128)
+    np.testing.assert_array_equal(res_h.batch.cpu().numpy(), batch)  # device-resident batch of the host entry point
+    # capacity knob of the NMS neighbour-pair buffer (ms_set_edge_factor / ms_get_edge_factor)
+    assert runner.ctx.edge_factor == 16
+    runner.ctx.edge_factor = 64
+    assert runner.ctx.edge_factor == 64
+    res_k = runner.run_host(score, geo, imgs)
+    np.testing.assert_array_equal(res_k.box_counts, counts)
+    runner.ctx.edge_factor = 16
 
 
 def test_full_size_properties(torch_cuda):

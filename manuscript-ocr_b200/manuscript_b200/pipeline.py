@@ -1,11 +1,11 @@
 """Pipeline with the reference's duck-typed detector / recogniser contract (reference _pipeline.py:18-176).
 
-detector.predict(image, vis=False, profile=...) -> {"page": Page, ...} | (Page, ...) | Page
-recognizer.predict(List[np.ndarray RGB u8]) -> List[{"text", "confidence"}] (or (text, conf) tuples)
+    detector.predict(image, vis=False, profile=...)  ->  {"page": Page, ...} | (Page, ...) | Page
+    recognizer.predict(List[np.ndarray RGB u8])      ->  List[{"text", "confidence"}]  (or (text, conf) tuples)
 
-Between them: reading-order sort (host, as in the reference), the integer crop rectangles and -- when the
-recogniser is this package's TRBA -- crop + resize-and-pad + normalise straight into the recogniser's
-device batch in one kernel launch.  A foreign recogniser gets the list of uint8 crops it expects.
+Between the two calls sit the reading-order sort, the integer crop rectangles and -- when the recogniser is this
+package's TRBA -- crop + resize-and-pad + normalise straight into the recogniser's device batch, one kernel launch per
+recogniser batch.  A foreign recogniser gets the list of uint8 crops it expects (plain slices of the page image).
 """
 import time
 
@@ -17,6 +17,28 @@ from .reading_order import reorder_words
 from .trba import TRBA
 
 
+def _page_of(det_out):
+    """_pipeline.py:69-77: the three shapes a detector may answer in."""
+    if isinstance(det_out, dict):
+        page = det_out.get("page")
+    elif isinstance(det_out, tuple):
+        page = det_out[0]
+    else:
+        page = det_out
+    if page is None:
+        raise RuntimeError("Detector did not return a Page result.")
+    return page
+
+
+def _text_and_confidence(result):
+    """_pipeline.py:152-159: dict, (text, confidence) tuple or anything printable."""
+    if isinstance(result, dict):
+        return result.get("text", ""), result.get("confidence", None)
+    if isinstance(result, tuple) and len(result) == 2:
+        return result
+    return (str(result) if result is not None else ""), None
+
+
 class Pipeline:
     def __init__(self, detector=None, recognizer=None, min_text_size=5):
         if detector is None or recognizer is None:
@@ -26,18 +48,38 @@ class Pipeline:
         self.recognizer = recognizer
         self.min_text_size = min_text_size
 
+    # ---- the steps between detector and recogniser -------------------------------------------------------------
+    def _ordered_crop_rects(self, page, img_h, img_w):
+        """Reading order per block (_pipeline.py:105-123, mutates block.words like the reference), then the crop
+        rectangle of every word that passes the size filter (_pipeline.py:125-137, 204-221)."""
+        words, rects = [], []
+        for block in page.blocks:
+            block.words = reorder_words(block.words)
+            if not block.words:
+                continue
+            polys = np.array([w.polygon for w in block.words], dtype=np.float32).reshape(len(block.words), -1)
+            block_rects, valid = ops.word_rects(polys, img_h, img_w, self.min_text_size)
+            for word, rect, ok in zip(block.words, block_rects, valid):
+                if ok:
+                    words.append(word)
+                    rects.append(rect)
+        return words, (np.stack(rects).astype(np.int32) if rects else np.zeros((0, 4), np.int32))
+
+    def _recognise(self, image_array, rects):
+        rec = self.recognizer
+        if not isinstance(rec, TRBA):
+            return rec.predict([image_array[y1:y2, x1:x2] for x1, y1, x2, y2 in rects])
+        results = []
+        rgb = TRBA._as_rgb(image_array)
+        for i in range(0, len(rects), rec.batch_size):
+            batch = ops.crop_resize_pad(rgb, rects[i:i + rec.batch_size], rec.img_h, rec.img_w)
+            results.extend(rec.predict_batch(rec.torch.from_numpy(batch).to(rec.device)))
+        return results
+
+    # ---- the reference's public surface ---------------------------------------------------------------------------
     def predict(self, image, recognize_text=True, vis=False, profile=False):
-        start_time = time.time()
-        t0 = time.time()
-        det_out = self.detector.predict(image, vis=False, profile=profile)
-        if isinstance(det_out, dict):
-            page = det_out.get("page")
-        elif isinstance(det_out, tuple):
-            page = det_out[0]
-        else:
-            page = det_out
-        if page is None:
-            raise RuntimeError("Detector did not return a Page result.")
+        t_start = t0 = time.time()
+        page = _page_of(self.detector.predict(image, vis=False, profile=profile))
         if profile:
             print(f"Detection: {time.time() - t0:.3f}s")
         if vis:
@@ -47,57 +89,27 @@ class Pipeline:
             return page
 
         image_array = read_image(image)
-        img_h, img_w = image_array.shape[:2]
         t0 = time.time()
-        all_words, all_rects = [], []
-        for block in page.blocks:
-            block.words = reorder_words(block.words)  # _pipeline.py:105-123
-            if not block.words:
-                continue
-            polys = np.array([w.polygon for w in block.words], dtype=np.float32).reshape(len(block.words), -1)
-            rects, valid = ops.word_rects(polys, img_h, img_w, self.min_text_size)  # _pipeline.py:125-137,204-221
-            for w, r, ok in zip(block.words, rects, valid):
-                if ok:
-                    all_words.append(w)
-                    all_rects.append(r)
+        words, rects = self._ordered_crop_rects(page, *image_array.shape[:2])
         if profile:
-            print(f"Extract {len(all_words)} crops: {time.time() - t0:.3f}s")
-
-        if all_words:
+            print(f"Extract {len(words)} crops: {time.time() - t0:.3f}s")
+        if words:
             t0 = time.time()
-            rects = np.stack(all_rects).astype(np.int32)
-            if isinstance(self.recognizer, TRBA):
-                results = []
-                bs = self.recognizer.batch_size
-                img3 = TRBA._as_rgb(image_array)
-                for i in range(0, len(rects), bs):
-                    batch = ops.crop_resize_pad(img3, rects[i:i + bs], self.recognizer.img_h, self.recognizer.img_w)
-                    results.extend(self.recognizer.predict_batch(
-                        self.recognizer.torch.from_numpy(batch).to(self.recognizer.device)))
-            else:
-                crops = [image_array[r[1]:r[3], r[0]:r[2]] for r in rects]
-                results = self.recognizer.predict(crops)
+            results = self._recognise(image_array, rects)
             if profile:
                 print(f"Recognition: {time.time() - t0:.3f}s")
-            for word, result in zip(all_words, results):  # _pipeline.py:149-162
-                if isinstance(result, dict):
-                    text, confidence = result.get("text", ""), result.get("confidence", None)
-                elif isinstance(result, tuple) and len(result) == 2:
-                    text, confidence = result
-                else:
-                    text, confidence = (str(result) if result is not None else ""), None
-                word.text = text
-                word.recognition_confidence = confidence
+            for word, result in zip(words, results):
+                word.text, word.recognition_confidence = _text_and_confidence(result)
         if profile:
-            print(f"Pipeline total: {time.time() - start_time:.3f}s")
+            print(f"Pipeline total: {time.time() - t_start:.3f}s")
         return page
 
     def get_text(self, page):
-        """_pipeline.py:193-202."""
+        """_pipeline.py:193-202: one line per block, words left to right."""
         lines = []
         for block in page.blocks:
-            sorted_words = sorted(block.words, key=lambda w: min(p[0] for p in w.polygon))
-            texts = [w.text for w in sorted_words if getattr(w, "text", None)]
+            texts = [w.text for w in sorted(block.words, key=lambda w: min(pt[0] for pt in w.polygon))
+                     if getattr(w, "text", None)]
             if texts:
                 lines.append(" ".join(texts))
         return "\n".join(lines)

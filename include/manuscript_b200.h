@@ -13,6 +13,8 @@
  *     dependent sizes stay on the device (counts arrays), so a whole page batch runs without a
  *     host round trip.  Per-page outputs are "page-strided": page p owns rows
  *     [p*cap_per_page, p*cap_per_page + counts[p]).
+ *   - a context owns ONE scratch arena: use it from one thread and one stream at a time (one context per GPU
+ *     worker); calls on the same stream may follow each other without synchronisation.
  *   - return value: MS_OK or a negative MS_ERR_*; ms_last_error() gives a message.  No exceptions
  *     cross the boundary.  There is NO CPU fallback: without a CUDA device every call fails.
  *   - quads are rows of 9 float32: x0,y0,x1,y1,x2,y2,x3,y3,score (the reference's (N,9) layout).

@@ -426,12 +426,12 @@ static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int c
     if (s2 > stage) stage = s2;
     s2 = word_rects_scratch_full(n_pages, cap_c);
     if (s2 > stage) stage = s2;
-    // reading order: boxes + order scratch (cap_boxes <= cap_c rows per page) + its own scratch, next to east_boxes'
-    s2 = msk_east_boxes_scratch(n_pages, cap_c) + al256((size_t)n_pages * cap_boxes * 36) +
-         al256((size_t)n_pages * cap_boxes * 4) + msk_reading_order_scratch(n_pages, cap_boxes) + 1024;
+    s2 = msk_reading_order_scratch(n_pages, cap_boxes);
     if (s2 > stage) stage = s2;
     s2 = msk_crop_scratch(crops_cap);
     if (s2 > stage) stage = s2;
+    // reading order keeps the unsorted boxes and the order next to the candidates for the rest of the call
+    fixed += al256((size_t)n_pages * cap_boxes * 36) + al256((size_t)n_pages * cap_boxes * 4) + 512;
     return fixed + stage + 4096;
 }
 

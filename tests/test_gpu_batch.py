@@ -156,3 +156,39 @@ def test_stress_4096_page(torch_cuda):
     want = cpu.east_postprocess(nms, (page, page), target_size=page)
     np.testing.assert_array_equal(res.boxes[0, :words].cpu().numpy(), want)
     del order
+
+
+def test_host_entry_chunks_reading_order_and_odd_shapes(torch_cuda):
+    """ms_page_batch_host cuts the batch into chunks (H2D of chunk c+1 under the kernels of chunk c), uploads only the
+    geometry rows a quantised decode reads, and appends every chunk's crops: same results as the one-shot device
+    path, with the reading-order stage on, for 11 pages (chunks of 2) and for quantisation 1 / 4."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    page, words, n_pages = 512, 60, 11
+    score, geo, imgs = synthdata.make_batch(list(range(70, 70 + n_pages)), page, words)
+    score[4] = 0.0  # an empty page inside a chunk
+    for q, ro in [(2, 1), (1, 0), (4, 1)]:
+        params = mb.EastParams.default(target_size=page, quantization=q, sort_reading_order=ro)
+        runner = mb.PageBatch(device=0, params=params, cap_boxes=512)
+        res = runner.run(torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(), torch.from_numpy(imgs).cuda())
+        torch.cuda.synchronize()
+        counts = res.box_counts.cpu().numpy().copy()
+        boxes = res.boxes.cpu().numpy().copy()
+        n_crops = int(res.n_crops.cpu()[0])
+        crops = res.crops.cpu().numpy()[:n_crops].copy()
+        batch = res.batch[:n_crops].cpu().numpy().copy()
+        assert int(res.flags.cpu().numpy().max()) == 0 and counts[4] == 0 and n_crops > 0
+        rh = runner.run_host(score, geo, imgs)
+        np.testing.assert_array_equal(rh.box_counts, counts)
+        for p in range(n_pages):
+            np.testing.assert_array_equal(rh.boxes[p, : counts[p]], boxes[p, : counts[p]])
+        assert int(rh.n_crops[0]) == n_crops
+        np.testing.assert_array_equal(rh.crops[:n_crops], crops)
+        np.testing.assert_array_equal(rh.batch.cpu().numpy(), batch)
+        # page 0 against the oracle, in the order the stage promises
+        quads = cpu.decode_quads_from_maps(score[0], geo[0], 0.6, 4.0, q)
+        want = cpu.east_postprocess(cpu.locality_aware_nms(quads, 0.2), (page, page), target_size=page)
+        if ro:
+            want = want[mb.word_reading_order(want[:, :8])]
+        np.testing.assert_array_equal(boxes[0, : counts[0]], want)

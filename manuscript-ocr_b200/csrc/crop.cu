@@ -218,10 +218,12 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-// Exact but slow: any interpolation mode, any tap count; table entries recomputed per pixel, source read from global
-// memory.  Used by crop_generic_kernel for every crop the persistent TMA kernel does not take.
+// Any interpolation mode, any tap count, source read from global memory; ex / ey are the pixel's coefficient-table
+// entries (INTER_LINEAR or INTER_AREA general).  Used by crop_generic_kernel for every crop the persistent TMA kernel
+// does not take.
 __device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, const uint8_t *gsrc, size_t stride,
-                                            unsigned char &o0, unsigned char &o1, unsigned char &o2)
+                                            const AxisEnt &ex, const AxisEnt &ey, unsigned char &o0, unsigned char &o1,
+                                            unsigned char &o2)
 {
     auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
     if (p.interp == 0) {
@@ -230,7 +232,6 @@ __device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, const
         o1 = s[1];
         o2 = s[2];
     } else if (p.interp == 1) {
-        const AxisEnt ex = linear_entry_x(dx, p.scale_x, p.w), ey = linear_entry_y(dy, p.scale_y, p.h);
         const unsigned char *S0 = row(ey.s0) + ex.s0 * 3;
         const unsigned char *S1 = row(ey.n) + ex.s0 * 3;
         const int a0 = ex.nfirst, a1 = ex.nmid, b0 = ey.nfirst, b1 = ey.nmid;
@@ -271,7 +272,6 @@ __device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, const
             o2 = sat_u8(cv_round((float)s2 * inv));
         }
     } else {
-        const AxisEnt ex = area_entry(dx, p.scale_x, p.w), ey = area_entry(dy, p.scale_y, p.h);
         float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
         for (int j = 0; j < ey.n; j++) {
             const float beta = area_weight(ey, j);
@@ -598,60 +598,84 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     }
 }
 
-// Every crop the persistent kernel does not take (same size copy, INTER_LINEAR upscale, integer-ratio INTER_AREA,
-// shrink factors >= 3, rows too long for the stage, crops flagged `redo`): one CTA per crop, source read from global
-// memory, exact per-pixel arithmetic.  Also writes the all-padding canvas of invalid crops.
-template <bool kWriteF32, bool kWriteU8>
-__global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w,
-                                                           const Plan *__restrict__ plans,
-                                                           const int32_t *__restrict__ n_crops_dev,
-                                                           const int32_t *__restrict__ range, int64_t crops_cap, int ih,
-                                                           int iw, float *__restrict__ batch,
-                                                           uint8_t *__restrict__ canvas_out, int vec_ok,
-                                                           const uint8_t *__restrict__ redo)
+// Crops the persistent kernel does not take (same size copy, INTER_LINEAR upscale, integer-ratio INTER_AREA, shrink
+// factors >= 3, rows too long for the stage, invalid rectangles, crops flagged `redo`) are listed first ...
+__global__ void __launch_bounds__(256) crop_generic_list_kernel(const Plan *__restrict__ plans,
+                                                                const int32_t *__restrict__ n_crops_dev,
+                                                                const int32_t *__restrict__ range, int64_t crops_cap,
+                                                                const uint8_t *__restrict__ redo,
+                                                                int32_t *__restrict__ list, int32_t *__restrict__ list_n)
 {
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
+    for (int64_t ci = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < n_crops;
+         ci += (int64_t)gridDim.x * blockDim.x)
+        if (!plans[ci].fast || redo[ci]) list[atomicAdd(list_n, 1)] = (int32_t)ci;
+}
+
+// ... and resampled one CTA per crop from global memory with the same arithmetic: the CTA builds the crop's
+// coefficient tables in shared memory, then one thread per destination pixel.
+constexpr int kGenericMaxTab = 1024;  // table entries kept in shared memory (longer axes recompute per pixel)
+
+template <bool kWriteF32, bool kWriteU8>
+__global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w,
+                                                           const Plan *__restrict__ plans,
+                                                           const int32_t *__restrict__ list,
+                                                           const int32_t *__restrict__ list_n, int ih, int iw,
+                                                           float *__restrict__ batch,
+                                                           uint8_t *__restrict__ canvas_out, int vec_ok)
+{
+    __shared__ AxisEnt s_tab[kGenericMaxTab];
     const size_t stride = (size_t)img_w * 3;
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
-    __shared__ int s_list[256];
-    __shared__ int s_n;
-    // each CTA scans 256 crops at a time (one per thread) for the few that are its business, then works through them
-    for (int64_t base = begin + (int64_t)blockIdx.x * 256; base < n_crops; base += (int64_t)gridDim.x * 256) {
-        if (threadIdx.x == 0) s_n = 0;
-        __syncthreads();
-        const int64_t mine = base + threadIdx.x;
-        if (mine < n_crops && (!plans[mine].fast || redo[mine])) s_list[atomicAdd(&s_n, 1)] = (int)(mine - base);
-        __syncthreads();
-        const int todo = s_n;
-        for (int li = 0; li < todo; li++) {
-            const int64_t ci = base + s_list[li];
-            const Plan p = plans[ci];
-            float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
-            uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
-            write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
-            const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-            const int npx = p.ok ? p.nw * p.nh : 0;
-            for (int t = threadIdx.x; t < npx; t += blockDim.x) {
-                const int dy = t / p.nw, dx = t - dy * p.nw;
-                unsigned char o0, o1, o2;
-                resample_px(p, dx, dy, gsrc, stride, o0, o1, o2);
-                const int at = (p.y0 + dy) * iw + dx;
-                if (kWriteF32) {
-                    dstf[at] = ((float)o0 - 127.5f) * inv;
-                    dstf[plane + at] = ((float)o1 - 127.5f) * inv;
-                    dstf[2 * plane + at] = ((float)o2 - 127.5f) * inv;
-                }
-                if (kWriteU8) {
-                    dstu[(size_t)at * 3] = o0;
-                    dstu[(size_t)at * 3 + 1] = o1;
-                    dstu[(size_t)at * 3 + 2] = o2;
-                }
+    const int todo = *list_n;
+    for (int li = blockIdx.x; li < todo; li += gridDim.x) {
+        const int64_t ci = list[li];
+        const Plan p = plans[ci];
+        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+        write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
+        const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0;
+        const bool need_tab = p.ok && (p.interp == 1 || p.interp == 3);
+        const bool tab_ok = need_tab && nw + nh <= kGenericMaxTab;
+        __syncthreads();  // the previous crop's table is no longer read
+        if (tab_ok) {
+            for (int t = threadIdx.x; t < nw + nh; t += blockDim.x) {
+                const bool isx = t < nw;
+                const int d = isx ? t : t - nw;
+                s_tab[t] = p.interp == 3 ? (isx ? area_entry(d, p.scale_x, p.w) : area_entry(d, p.scale_y, p.h))
+                                         : (isx ? linear_entry_x(d, p.scale_x, p.w) : linear_entry_y(d, p.scale_y, p.h));
             }
         }
-        __syncthreads();  // s_list is reused by the next chunk
+        __syncthreads();
+        const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+        const int npx = nw * nh;
+        for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+            const int dy = t / nw, dx = t - dy * nw;
+            AxisEnt ex = {}, ey = {};
+            if (tab_ok) {
+                ex = s_tab[dx];
+                ey = s_tab[nw + dy];
+            } else if (need_tab) {
+                ex = p.interp == 3 ? area_entry(dx, p.scale_x, p.w) : linear_entry_x(dx, p.scale_x, p.w);
+                ey = p.interp == 3 ? area_entry(dy, p.scale_y, p.h) : linear_entry_y(dy, p.scale_y, p.h);
+            }
+            unsigned char o0, o1, o2;
+            resample_px(p, dx, dy, gsrc, stride, ex, ey, o0, o1, o2);
+            const int at = (p.y0 + dy) * iw + dx;
+            if (kWriteF32) {
+                dstf[at] = ((float)o0 - 127.5f) * inv;
+                dstf[plane + at] = ((float)o1 - 127.5f) * inv;
+                dstf[2 * plane + at] = ((float)o2 - 127.5f) * inv;
+            }
+            if (kWriteU8) {
+                dstu[(size_t)at * 3] = o0;
+                dstu[(size_t)at * 3 + 1] = o1;
+                dstu[(size_t)at * 3 + 2] = o2;
+            }
+        }
     }
 }
 
@@ -660,7 +684,7 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__rest
 size_t msk_crop_scratch(int64_t crops_cap)
 {
     const size_t n = (size_t)(crops_cap > 0 ? crops_cap : 0);
-    return n * sizeof(Plan) + n + 2048;
+    return n * sizeof(Plan) + n + n * sizeof(int32_t) + 4096;
 }
 
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
@@ -683,11 +707,14 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     }
     Plan *plans = bump.take<Plan>((size_t)crops_cap);
     uint8_t *redo = bump.take<uint8_t>((size_t)crops_cap);
-    if (!plans || !redo) {
+    int32_t *glist = bump.take<int32_t>((size_t)crops_cap);
+    int32_t *glist_n = bump.take<int32_t>(1);
+    if (!plans || !redo || !glist_n) {
         ms_set_error("crop: scratch too small");
         return MS_ERR_CAPACITY;
     }
     MS_CUDA(cudaMemsetAsync(redo, 0, (size_t)crops_cap, st));
+    MS_CUDA(cudaMemsetAsync(glist_n, 0, sizeof(int32_t), st));
     {
         int64_t g = (crops_cap + 255) / 256;
         if (g > (int64_t)ctx->num_sms * 8) g = (int64_t)ctx->num_sms * 8;
@@ -702,16 +729,25 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     if (grid > crops_cap) grid = crops_cap;
     int64_t ggrid = (int64_t)ctx->num_sms * 8;
     if (ggrid > crops_cap) ggrid = crops_cap;
+    int64_t lgrid = (crops_cap + 255) / 256;
+    if (lgrid > (int64_t)ctx->num_sms * 8) lgrid = (int64_t)ctx->num_sms * 8;
     const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
+    // cudaFuncSetAttribute is a synchronous driver call (milliseconds): once per context and kernel, not per launch
 #define MS_CROP_LAUNCH(F32, U8)                                                                                        \
     do {                                                                                                               \
         auto kfn = crop_resize_pad_kernel<F32, U8>;                                                                    \
-        MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                    \
+        int &granted = ctx->smem_attr[(F32 ? 1 : 0) + (U8 ? 2 : 0) - 1];                                               \
+        if ((int)smem > granted) {                                                                                     \
+            MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
+            granted = (int)smem;                                                                                       \
+        }                                                                                                              \
         kfn<<<(int)grid, kThreads, smem, st>>>(pages, img_h, img_w, plans, n_crops, range, crops_cap, out_h, out_w,    \
                                               batch_f32, canvas_u8, vec_ok, redo);                                     \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
-        crop_generic_kernel<F32, U8><<<(int)ggrid, 256, 0, st>>>(pages, img_h, img_w, plans, n_crops, range, crops_cap, \
-                                                                 out_h, out_w, batch_f32, canvas_u8, vec_ok, redo);   \
+        crop_generic_list_kernel<<<(int)lgrid, 256, 0, st>>>(plans, n_crops, range, crops_cap, redo, glist, glist_n);  \
+        MS_LAUNCH_CHECK(ctx);                                                                                          \
+        crop_generic_kernel<F32, U8><<<(int)ggrid, 256, 0, st>>>(pages, img_h, img_w, plans, glist, glist_n, out_h,    \
+                                                                 out_w, batch_f32, canvas_u8, vec_ok);                \
     } while (0)
     if (batch_f32 && canvas_u8)
         MS_CROP_LAUNCH(true, true);

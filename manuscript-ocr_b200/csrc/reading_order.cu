@@ -429,7 +429,10 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
     const size_t smem = (size_t)kRoMaxBoxes * 16 + (size_t)kRoMaxPairs * 5 + (size_t)kRoMaxBoxes * 2;
     static_assert(kRoMaxPairs * 5 + kRoMaxBoxes * 2 >= 136 * 1024 && kRoMaxBoxes == 4096,
                   "pair + level region must hold the sort / line arrays laid out in the kernel");
-    MS_CUDA(cudaFuncSetAttribute(reading_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((int)smem > ctx->smem_attr[3]) {  // a synchronous driver call: once per context
+        MS_CUDA(cudaFuncSetAttribute(reading_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        ctx->smem_attr[3] = (int)smem;
+    }
     reading_order_kernel<<<n_pages, kRoThreads, smem, st>>>(boxes8, row_stride, counts, cap_per_page, obox, order,
                                                            reordered, flags);
     MS_LAUNCH_CHECK(ctx);

@@ -258,7 +258,7 @@ def run_b200(a):
     d_score, d_geo, d_pages = h_score.to(dev), h_geo.to(dev), h_pages.to(dev)
 
     params = mb.EastParams.default(target_size=S, sort_reading_order=1 if a.reading_order else 0)
-    cap_boxes = 4096
+    cap_boxes = max(4096, 2 * a.words)
     crops_cap = P * (a.words + a.words // 4 + 64)
     runner = mb.PageBatch(device=local, params=params, cap_boxes=cap_boxes, crops_cap=crops_cap, out_hw=(OUT_H, OUT_W))
     ctx = runner.ctx

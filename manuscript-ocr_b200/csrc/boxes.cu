@@ -157,7 +157,31 @@ struct EastScratch {
     float *karea;     // P*cap compacted areas / deviations
     float *kdev;
     int32_t *kidx;    // P*cap compacted indices
+    // uniform grid over the boxes' min corners for the containment search
+    float *ext;       // P*8: min x / y of the min corners, cells per unit x / y, max box width / height, margin
+    int32_t *dense;   // P: 1 = the page holds a non-finite box -> all-pairs kernel
+    int32_t *cell_cnt, *cell_off, *cell_cur;  // P*kCells (+1)
+    int32_t *cell_of; // P*cap
+    float4 *sb_bbox;  // P*cap, cell order: bbox inflated by the prefilter margin
+    float *sb_area;   // P*cap
+    int32_t *sb_id;   // P*cap
 };
+
+constexpr int kEGrid = 32;
+constexpr int kECells = kEGrid * kEGrid;
+
+__device__ __forceinline__ int east_cell(float v, float origin, float scale)
+{
+    const float f = (v - origin) * scale;  // monotone in v: the same function maps corners and search bounds
+    return f > 0.f ? (f < (float)(kEGrid - 1) ? (int)f : kEGrid - 1) : 0;
+}
+
+__device__ __forceinline__ float4 east_inflate(const float4 b)
+{
+    const float mx = 1e-4f * fmaxf(fabsf(b.x), fabsf(b.z)) + 1e-3f;
+    const float my = 1e-4f * fmaxf(fabsf(b.y), fabsf(b.w)) + 1e-3f;
+    return make_float4(b.x - mx, b.y - my, b.z + mx, b.w + my);
+}
 
 __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 {
@@ -237,6 +261,161 @@ __global__ void __launch_bounds__(256) east_prep_kernel(const float *__restrict_
     }
 }
 
+// 1b) page extents + grid geometry (one CTA per page); pages with a non-finite box use the all-pairs kernel
+__global__ void __launch_bounds__(256) east_ext_kernel(const int32_t *__restrict__ counts, int cap, EastScratch S)
+{
+    const int page = blockIdx.x;
+    const int K = counts[page];
+    const size_t pb = (size_t)page * cap;
+    float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY, mw = 0.f, mh = 0.f, mabs = 0.f;
+    int bad = 0;
+    for (int i = threadIdx.x; i < K; i += blockDim.x) {
+        const float4 b = S.bbox[pb + i];
+        if (!(b.x > -INFINITY && b.z < INFINITY && b.y > -INFINITY && b.w < INFINITY)) {
+            bad = 1;
+            continue;
+        }
+        minx = fminf(minx, b.x);
+        miny = fminf(miny, b.y);
+        maxx = fmaxf(maxx, b.x);
+        maxy = fmaxf(maxy, b.y);
+        mw = fmaxf(mw, b.z - b.x);
+        mh = fmaxf(mh, b.w - b.y);
+        mabs = fmaxf(mabs, fmaxf(fmaxf(fabsf(b.x), fabsf(b.z)), fmaxf(fabsf(b.y), fabsf(b.w))));
+    }
+    __shared__ float s_r[8][7];
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
+    __syncthreads();
+    if (bad) s_bad = 1;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        minx = fminf(minx, __shfl_xor_sync(0xffffffffu, minx, off));
+        miny = fminf(miny, __shfl_xor_sync(0xffffffffu, miny, off));
+        maxx = fmaxf(maxx, __shfl_xor_sync(0xffffffffu, maxx, off));
+        maxy = fmaxf(maxy, __shfl_xor_sync(0xffffffffu, maxy, off));
+        mw = fmaxf(mw, __shfl_xor_sync(0xffffffffu, mw, off));
+        mh = fmaxf(mh, __shfl_xor_sync(0xffffffffu, mh, off));
+        mabs = fmaxf(mabs, __shfl_xor_sync(0xffffffffu, mabs, off));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        float *r = s_r[threadIdx.x >> 5];
+        r[0] = minx; r[1] = miny; r[2] = maxx; r[3] = maxy; r[4] = mw; r[5] = mh; r[6] = mabs;
+    }
+    for (int c = threadIdx.x; c < kECells; c += blockDim.x) S.cell_cnt[(size_t)page * kECells + c] = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int w = 1; w < 8; w++) {
+            s_r[0][0] = fminf(s_r[0][0], s_r[w][0]);
+            s_r[0][1] = fminf(s_r[0][1], s_r[w][1]);
+            s_r[0][2] = fmaxf(s_r[0][2], s_r[w][2]);
+            s_r[0][3] = fmaxf(s_r[0][3], s_r[w][3]);
+            s_r[0][4] = fmaxf(s_r[0][4], s_r[w][4]);
+            s_r[0][5] = fmaxf(s_r[0][5], s_r[w][5]);
+            s_r[0][6] = fmaxf(s_r[0][6], s_r[w][6]);
+        }
+        float *e = S.ext + (size_t)page * 8;
+        const bool any = s_r[0][2] >= s_r[0][0];
+        e[0] = any ? s_r[0][0] : 0.f;
+        e[1] = any ? s_r[0][1] : 0.f;
+        e[2] = (float)kEGrid / (any ? fmaxf(s_r[0][2] - s_r[0][0], 1e-3f) : 1.f);
+        e[3] = (float)kEGrid / (any ? fmaxf(s_r[0][3] - s_r[0][1], 1e-3f) : 1.f);
+        e[4] = s_r[0][4];
+        e[5] = s_r[0][5];
+        e[6] = 2e-4f * s_r[0][6] + 2e-3f;  // >= twice the largest per-box prefilter margin of the page
+        S.dense[page] = s_bad;
+    }
+}
+
+__global__ void __launch_bounds__(256) east_bin_count_kernel(const int32_t *__restrict__ counts, int cap, EastScratch S)
+{
+    const int page = blockIdx.y;
+    if (S.dense[page]) return;
+    const int K = counts[page];
+    const size_t pb = (size_t)page * cap;
+    const float *e = S.ext + (size_t)page * 8;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        const float4 b = S.bbox[pb + i];
+        const int cell = east_cell(b.y, e[1], e[3]) * kEGrid + east_cell(b.x, e[0], e[2]);
+        S.cell_of[pb + i] = cell;
+        atomicAdd(S.cell_cnt + (size_t)page * kECells + cell, 1);
+    }
+}
+
+__global__ void __launch_bounds__(kECells) east_bin_scan_kernel(EastScratch S)
+{
+    const int page = blockIdx.x;
+    __shared__ int s_warp[33];
+    const int v = S.cell_cnt[(size_t)page * kECells + threadIdx.x];
+    int total;
+    const int off = block_excl_scan(v, s_warp, total);
+    S.cell_off[(size_t)page * (kECells + 1) + threadIdx.x] = off;
+    S.cell_cur[(size_t)page * kECells + threadIdx.x] = off;
+    if (threadIdx.x == 0) S.cell_off[(size_t)page * (kECells + 1) + kECells] = total;
+}
+
+__global__ void __launch_bounds__(256) east_bin_scatter_kernel(const int32_t *__restrict__ counts, int cap, EastScratch S)
+{
+    const int page = blockIdx.y;
+    if (S.dense[page]) return;
+    const int K = counts[page];
+    const size_t pb = (size_t)page * cap;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        const int pos = atomicAdd(S.cell_cur + (size_t)page * kECells + S.cell_of[pb + i], 1);
+        S.sb_bbox[pb + pos] = east_inflate(S.bbox[pb + i]);
+        S.sb_area[pb + pos] = S.area[pb + i];
+        S.sb_id[pb + pos] = i;
+    }
+}
+
+// 2a) contained-box removal through the grid: box i can only lie inside a box j whose min corner is at most one box
+//     size (+ margin) up / left of i's; same classification as the all-pairs kernel below.
+__global__ void __launch_bounds__(256) east_contain_binned_kernel(const int32_t *__restrict__ counts, int cap,
+                                                                  EastScratch S)
+{
+    const int page = blockIdx.y;
+    if (S.dense[page]) return;
+    const int K = counts[page];
+    if (K <= 1) return;
+    const size_t pb = (size_t)page * cap;
+    const float *work = S.work + pb * 9;
+    const float *e = S.ext + (size_t)page * 8;
+    const int32_t *coff = S.cell_off + (size_t)page * (kECells + 1);
+    const float ox = e[0], oy = e[1], sx = e[2], sy = e[3], mw = e[4], mh = e[5], marg = e[6];
+    const float eps = (float)1e-6;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < K; i += gridDim.x * blockDim.x) {
+        float qi[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) qi[k] = work[(size_t)i * 9 + k];
+        const float ai = S.area[pb + i];
+        const float4 bi = S.bbox[pb + i];
+        const int cx0 = east_cell(bi.x - mw - marg, ox, sx), cx1 = east_cell(bi.x + marg, ox, sx);
+        const int cy0 = east_cell(bi.y - mh - marg, oy, sy), cy1 = east_cell(bi.y + marg, oy, sy);
+        bool later_hit = false, earlier_hit = false;
+        for (int cy = cy0; cy <= cy1 && !later_hit; cy++) {
+            const int pos1 = coff[cy * kEGrid + cx1 + 1];
+            for (int pos = coff[cy * kEGrid + cx0]; pos < pos1; pos++) {
+                const float aj = S.sb_area[pb + pos];
+                const float4 bj = S.sb_bbox[pb + pos];
+                if ((aj + eps < ai) || !(bi.x >= bj.x && bi.y >= bj.y && bi.z <= bj.z && bi.w <= bj.w)) continue;
+                const int j = S.sb_id[pb + pos];
+                if (j == i) continue;
+                float qj[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) qj[k] = work[(size_t)j * 9 + k];
+                if (!quad_inside(qi, qj)) continue;
+                if (area_before(ai, i, aj, j)) {  // j is visited after i: still kept when i is visited
+                    later_hit = true;
+                    break;
+                }
+                earlier_hit = true;  // j's own fate decides
+            }
+        }
+        S.removed[pb + i] = later_hit ? 1 : 0;
+        S.needseq[pb + i] = (!later_hit && earlier_hit) ? 1 : 0;
+    }
+}
+
 // 2) infer.py:194-214 contained-box removal, the pairwise part.  Box i is visited in ascending-area order
 //    (stable ties); a container j that comes LATER in that order is still kept when i is visited, so it
 //    removes i outright; a container that comes EARLIER only counts if it survived itself -> needseq.
@@ -249,6 +428,7 @@ __global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int
                                                                        EastScratch S)
 {
     const int page = blockIdx.y;
+    if (!S.dense[page]) return;  // the grid search handled this page
     const int K = counts[page];
     if (K <= 1) return;
     const size_t pb = (size_t)page * cap;
@@ -275,10 +455,7 @@ __global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int
             __syncthreads();
             const int jj = base_j + threadIdx.x;
             if (jj < K) {
-                float4 b = bbox[jj];
-                const float mx = 1e-4f * fmaxf(fabsf(b.x), fabsf(b.z)) + 1e-3f;
-                const float my = 1e-4f * fmaxf(fabsf(b.y), fabsf(b.w)) + 1e-3f;
-                s_bb[threadIdx.x] = make_float4(b.x - mx, b.y - my, b.z + mx, b.w + my);
+                s_bb[threadIdx.x] = east_inflate(bbox[jj]);
                 s_ar[threadIdx.x] = area[jj];
             }
             __syncthreads();
@@ -630,6 +807,19 @@ void carve_east(ms_bump &bump, EastScratch &S, size_t n)
     S.karea = bump.take<float>(n);
     S.kdev = bump.take<float>(n);
     S.kidx = bump.take<int32_t>(n);
+    S.cell_of = bump.take<int32_t>(n);
+    S.sb_bbox = bump.take<float4>(n);
+    S.sb_area = bump.take<float>(n);
+    S.sb_id = bump.take<int32_t>(n);
+}
+
+void carve_east_pages(ms_bump &bump, EastScratch &S, int n_pages)
+{
+    S.ext = bump.take<float>((size_t)n_pages * 8);
+    S.dense = bump.take<int32_t>(n_pages);
+    S.cell_cnt = bump.take<int32_t>((size_t)n_pages * kECells);
+    S.cell_off = bump.take<int32_t>((size_t)n_pages * (kECells + 1));
+    S.cell_cur = bump.take<int32_t>((size_t)n_pages * kECells);
 }
 
 }  // namespace
@@ -649,6 +839,7 @@ size_t msk_east_boxes_scratch(int n_pages, int cap_per_page)
     ms_bump probe{nullptr, 0, 0};
     EastScratch S;
     carve_east(probe, S, (size_t)n_pages * cap_per_page);
+    carve_east_pages(probe, S, n_pages);
     return probe.off + 4096;
 }
 
@@ -663,7 +854,8 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
     }
     EastScratch S;
     carve_east(bump, S, (size_t)n_pages * cap_per_page);
-    if (!S.kidx) {
+    carve_east_pages(bump, S, n_pages);
+    if (!S.sb_id || !S.cell_cur) {
         ms_set_error("east_boxes: scratch too small");
         return MS_ERR_CAPACITY;
     }
@@ -672,9 +864,19 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
     if (gx > 16) gx = 16;
     east_prep_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(quads, counts, n_pages, cap_per_page, *p, orig_hw, S);
     MS_LAUNCH_CHECK(ctx);
+    east_ext_kernel<<<n_pages, 256, 0, st>>>(counts, cap_per_page, S);
+    MS_LAUNCH_CHECK(ctx);
+    east_bin_count_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(counts, cap_per_page, S);
+    MS_LAUNCH_CHECK(ctx);
+    east_bin_scan_kernel<<<n_pages, kECells, 0, st>>>(S);
+    MS_LAUNCH_CHECK(ctx);
+    east_bin_scatter_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(counts, cap_per_page, S);
+    MS_LAUNCH_CHECK(ctx);
+    east_contain_binned_kernel<<<dim3(gx * 2, n_pages), 256, 0, st>>>(counts, cap_per_page, S);
+    MS_LAUNCH_CHECK(ctx);
     gx = (cap_per_page + kContainThreads - 1) / kContainThreads;
     if (gx > 32) gx = 32;
-    east_contain_kernel<<<dim3(gx, n_pages), kContainThreads, 0, st>>>(counts, cap_per_page, S);
+    east_contain_kernel<<<dim3(gx, n_pages), kContainThreads, 0, st>>>(counts, cap_per_page, S);  // dense pages only
     MS_LAUNCH_CHECK(ctx);
     // device recursion in np_pairwise_f32: depth <= log2(cap/128) + 1 frames of a few dozen bytes
     east_finish_kernel<<<n_pages, 512, 0, st>>>(counts, cap_per_page, *p, S, quads_out, out_cap, counts_out, flags);

@@ -865,7 +865,7 @@ __device__ __forceinline__ uint64_t desc_score_key(double sc)
 
 // ---- 7. kept clusters -> rows in stable descending-score order ----------------------------------------------------
 __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B,
-                                                          int32_t *__restrict__ counts_out)
+                                                          int32_t *__restrict__ counts_out, int f32_scores)
 {
     const int page = blockIdx.x;
     const int p0 = page_off[page];
@@ -881,6 +881,12 @@ __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restr
         if (k) {
             kept[run_base + pos] = c;
             B.kept_key[p0 + run_base + pos] = desc_score_key(B.cl_score[p0 + c]);
+            if (f32_scores) {
+                // LANMS cluster scores are float32 values: a 32-bit descending key for the large-page radix sort
+                const float sc = (float)B.cl_score[p0 + c];
+                B.keys[p0 + run_base + pos] = (sc != sc) ? 0xFFFFFFFFu : ~ms_orderable_f32(sc);
+                B.vals[p0 + run_base + pos] = (uint32_t)c;
+            }
         }
         run_base += total;
     }
@@ -894,17 +900,12 @@ constexpr int kSortMax = 4096;
 
 __global__ void __launch_bounds__(1024) lanms_sort_emit_kernel(const int32_t *__restrict__ page_off, int cap,
                                                                LanmsBuffers B, float *__restrict__ out,
-                                                               const int32_t *__restrict__ counts_out,
-                                                               int32_t *__restrict__ rank_needed)
+                                                               const int32_t *__restrict__ counts_out)
 {
     const int page = blockIdx.x;
     const int p0 = page_off[page];
     const int K = counts_out[page];
-    if (K > kSortMax) {
-        if (threadIdx.x == 0) rank_needed[page] = 1;
-        return;
-    }
-    if (threadIdx.x == 0) rank_needed[page] = 0;
+    if (K > kSortMax) return;  // ordered by the segmented radix sort + lanms_emit_sorted_kernel
     __shared__ uint64_t s_key[kSortMax];
     const int32_t *kept = B.kept_list + p0;
     int n = 1;
@@ -938,6 +939,25 @@ __global__ void __launch_bounds__(1024) lanms_sort_emit_kernel(const int32_t *__
     }
     for (int r = threadIdx.x; r < K; r += 1024) {
         const int c = (int)(s_key[r] & 0xffffffffu);
+        float *row = out + ((size_t)page * cap + r) * 9;
+        const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
+#pragma unroll
+        for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
+        row[8] = (float)B.cl_score[p0 + c];
+    }
+}
+
+// pages with more than kSortMax kept boxes: B.vals holds the cluster indices in output order after the radix sort
+__global__ void __launch_bounds__(256) lanms_emit_sorted_kernel(const int32_t *__restrict__ page_off, int cap,
+                                                                LanmsBuffers B, float *__restrict__ out,
+                                                                const int32_t *__restrict__ counts_out)
+{
+    const int page = blockIdx.y;
+    const int K = counts_out[page];
+    if (K <= kSortMax) return;
+    const int p0 = page_off[page];
+    for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < K; r += gridDim.x * blockDim.x) {
+        const int c = (int)B.vals[p0 + r];
         float *row = out + ((size_t)page * cap + r) * 9;
         const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
 #pragma unroll
@@ -1131,7 +1151,8 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
                                                 B.pos_page);
         MS_LAUNCH_CHECK(ctx);
     }
-    int rc = msk_sort_pages(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.page_off, n_pages, cap_per_page, bump, st);
+    int rc = msk_sort_pages(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.page_off, nullptr, -1, n_pages, cap_per_page,
+                            bump, st);
     if (rc != MS_OK) return rc;
     lanms_gather_hot_kernel<<<sms * 8, 128, 0, st>>>(quads, B.vals, B.page_off, B.n_total, thr, B);
     MS_LAUNCH_CHECK(ctx);
@@ -1165,16 +1186,19 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         int rc2 = launch_resolve(ctx, n_pages, B.page_off, thr, B, B.und_flags, st);
         if (rc2 != MS_OK) return rc2;
     }
-    lanms_kept_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, counts_out);
+    lanms_kept_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, counts_out, 1);
     MS_LAUNCH_CHECK(ctx);
     {
         int gx = (cap_per_page + kRankThreads - 1) / kRankThreads;
         if (gx > 32) gx = 32;
-        lanms_sort_emit_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out, B.page_redo);
+        lanms_sort_emit_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out);
         MS_LAUNCH_CHECK(ctx);
-        // (page_redo is free again after the neighbour search: reused as the "rank needed" flag)
-        lanms_emit_kernel<<<dim3(gx, n_pages), kRankThreads, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out,
-                                                                       nullptr, B.page_redo);
+        // pages with more kept boxes than the shared-memory sort holds: stable radix sort of (descending score key,
+        // cluster index) -- the kernels return at once for the other pages
+        int rc2 = msk_sort_pages(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.page_off, counts_out, kSortMax, n_pages,
+                                 cap_per_page, bump, st);
+        if (rc2 != MS_OK) return rc2;
+        lanms_emit_sorted_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out);
         MS_LAUNCH_CHECK(ctx);
     }
     return MS_OK;
@@ -1199,7 +1223,7 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
         int rc2 = launch_resolve(ctx, 1, B.page_off, thr, B, B.und_flags, st);
         if (rc2 != MS_OK) return rc2;
     }
-    lanms_kept_kernel<<<1, 1024, 0, st>>>(B.page_off, B, k_out);
+    lanms_kept_kernel<<<1, 1024, 0, st>>>(B.page_off, B, k_out, 0);
     MS_LAUNCH_CHECK(ctx);
     {
         int gx = (n + kRankThreads - 1) / kRankThreads;

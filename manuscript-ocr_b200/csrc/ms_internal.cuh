@@ -80,7 +80,8 @@ int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, i
 size_t msk_decode_scratch(int n_pages, int H, int W, int q);
 // sort.cu : stable LSD radix sort, per-page segments [page_off[p], page_off[p+1]) of (u32 key, u32 value), 4 passes
 int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
-                   const int32_t *page_off, int n_pages, int cap_per_page, ms_bump bump, cudaStream_t st);
+                   const int32_t *page_off, const int32_t *seg_len, int skip_le, int n_pages, int cap_per_page,
+                   ms_bump bump, cudaStream_t st);
 size_t msk_sort_pages_scratch(int n_pages, int cap_per_page);
 // lanms.cu
 int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,

@@ -18,13 +18,16 @@ constexpr int kRadix = 256;
 // Every page's (u32 key, u32 value) segment [page_off[p], page_off[p+1]) is sorted on its own.
 // Pages hold a few tiles each, so a CTA derives its tile's digit bases directly from the page's tile histograms
 // (no scan kernel) and a 32-bit key needs 4 passes of 2 launches.
+// seg_len == NULL: segment p is [page_off[p], page_off[p+1]); otherwise it starts at page_off[p] and holds seg_len[p]
+// items.  Segments of at most skip_le items are left alone (the caller orders those another way).
 __global__ void __launch_bounds__(kThreads) seg_hist_kernel(const uint32_t *__restrict__ keys,
-                                                            const int32_t *__restrict__ page_off, int tiles_max, int shift,
-                                                            int32_t *__restrict__ hist)
+                                                            const int32_t *__restrict__ page_off,
+                                                            const int32_t *__restrict__ seg_len, int skip_le,
+                                                            int tiles_max, int shift, int32_t *__restrict__ hist)
 {
     const int page = blockIdx.y, tile = blockIdx.x;
-    const int p0 = page_off[page], n = page_off[page + 1] - p0;
-    if (tile * kTile >= n) return;
+    const int p0 = page_off[page], n = seg_len ? seg_len[page] : page_off[page + 1] - p0;
+    if (n <= skip_le || tile * kTile >= n) return;
     __shared__ int s_h[kRadix];
     for (int d = threadIdx.x; d < kRadix; d += kThreads) s_h[d] = 0;
     __syncthreads();
@@ -40,14 +43,16 @@ __global__ void __launch_bounds__(kThreads) seg_hist_kernel(const uint32_t *__re
 
 __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *__restrict__ keys,
                                                                const uint32_t *__restrict__ vals,
-                                                               const int32_t *__restrict__ page_off, int tiles_max,
-                                                               int shift, const int32_t *__restrict__ hist,
+                                                               const int32_t *__restrict__ page_off,
+                                                               const int32_t *__restrict__ seg_len, int skip_le,
+                                                               int tiles_max, int shift,
+                                                               const int32_t *__restrict__ hist,
                                                                uint32_t *__restrict__ keys_out,
                                                                uint32_t *__restrict__ vals_out)
 {
     const int page = blockIdx.y, tile = blockIdx.x;
-    const int p0 = page_off[page], n = page_off[page + 1] - p0;
-    if (tile * kTile >= n) return;
+    const int p0 = page_off[page], n = seg_len ? seg_len[page] : page_off[page + 1] - p0;
+    if (n <= skip_le || tile * kTile >= n) return;
     const int tiles = (n + kTile - 1) / kTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_cnt[kWarps][kRadix];  // per-warp digit counts, then running write cursors
@@ -127,7 +132,8 @@ size_t msk_sort_pages_scratch(int n_pages, int cap_per_page)
 
 // Stable sort of every page's (u32 key, u32 value) segment; the result ends in (keys, vals), tmp is clobbered.
 int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
-                   const int32_t *page_off, int n_pages, int cap_per_page, ms_bump bump, cudaStream_t st)
+                   const int32_t *page_off, const int32_t *seg_len, int skip_le, int n_pages, int cap_per_page,
+                   ms_bump bump, cudaStream_t st)
 {
     if (n_pages <= 0 || cap_per_page <= 0) return MS_OK;
     static_assert(kThreads == kRadix, "seg_scatter_kernel maps one thread per digit");
@@ -140,9 +146,10 @@ int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_t
     uint32_t *kin = keys, *kout = keys_tmp, *vin = vals, *vout = vals_tmp;
     const dim3 grid(tiles_max, n_pages);
     for (int pass = 0; pass < 4; pass++) {
-        seg_hist_kernel<<<grid, kThreads, 0, st>>>(kin, page_off, tiles_max, 8 * pass, hist);
+        seg_hist_kernel<<<grid, kThreads, 0, st>>>(kin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist);
         MS_LAUNCH_CHECK(ctx);
-        seg_scatter_kernel<<<grid, kThreads, 0, st>>>(kin, vin, page_off, tiles_max, 8 * pass, hist, kout, vout);
+        seg_scatter_kernel<<<grid, kThreads, 0, st>>>(kin, vin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist, kout,
+                                                      vout);
         MS_LAUNCH_CHECK(ctx);
         uint32_t *t = kin;
         kin = kout;

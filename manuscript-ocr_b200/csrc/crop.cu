@@ -727,6 +727,7 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     if (per_sm < 1) per_sm = 1;
     int64_t grid = (int64_t)ctx->num_sms * per_sm;
     if (grid > crops_cap) grid = crops_cap;
+    // one CTA per listed crop, many in flight: a generic crop reads global memory byte by byte and is latency bound
     int64_t ggrid = (int64_t)ctx->num_sms * 8;
     if (ggrid > crops_cap) ggrid = crops_cap;
     int64_t lgrid = (crops_cap + 255) / 256;

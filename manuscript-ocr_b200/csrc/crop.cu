@@ -102,13 +102,16 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
         bool fast = fabs(p.scale_x - p.isx) < 2.220446049250313e-16 && fabs(p.scale_y - p.isy) < 2.220446049250313e-16;
         p.interp = fast ? 2 : 3;
     }
-    // staging: every row is copied as the 16-byte-aligned span that covers it
-    const int pitch = ((w * 3 + 15 + 16 + 15) & ~15);  // span + 16 bytes the 4-tap fast path may over-read
+    // staging: every row is copied as the 16-byte-aligned span that covers it; the pitch is exactly that span (the
+    // 4-tap reads may run up to 16 bytes past a row -- into the next row, or into the slack kept after the last one).
+    // When the page stride is a multiple of 16 every row has the same misalignment, otherwise assume the worst (15).
     const size_t stride = (size_t)img_w * 3;
     const size_t first = (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
     const size_t last_end = first + (size_t)(h - 1) * stride + (size_t)w * 3;
     const uintptr_t base = reinterpret_cast<uintptr_t>(pages);
-    const bool fits = (size_t)pitch * h <= (size_t)kSrcBuf;
+    const int mis = (stride & 15) == 0 ? (int)((base + first) & 15) : 15;
+    const int pitch = (mis + w * 3 + 15) & ~15;
+    const bool fits = (size_t)pitch * h + 16 <= (size_t)kSrcBuf;
     // the last row's aligned span must not run past the end of the page tensor
     const bool tail_ok = ((base + last_end + 15) & ~(uintptr_t)15) <= base + total_bytes;
     if (fits && tail_ok && (base & 15) == 0) {

@@ -192,3 +192,35 @@ def test_host_entry_chunks_reading_order_and_odd_shapes(torch_cuda):
         if ro:
             want = want[mb.word_reading_order(want[:, :8])]
         np.testing.assert_array_equal(boxes[0, : counts[0]], want)
+
+
+def test_boxes_only_and_capacity_flags(torch_cuda):
+    """Without page images the batch stops after the box filters; a page with more boxes than cap_boxes is flagged
+    (device path) / raises (host path) instead of being silently truncated."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    page, words = 512, 80
+    score, geo, imgs = synthdata.make_batch([90, 91], page, words)
+    params = mb.EastParams.default(target_size=page)
+    runner = mb.PageBatch(device=0, params=params, cap_boxes=256, want_batch=False)
+    res = runner.run(torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(), None)
+    torch.cuda.synchronize()
+    counts = res.box_counts.cpu().numpy()
+    assert (counts == words).all() and int(res.flags.cpu().numpy().max()) == 0 and res.batch is None
+    want = oracle_page(score[1], geo[1], imgs[1], page)[2]
+    np.testing.assert_array_equal(res.boxes[1, : counts[1]].cpu().numpy(), want)
+
+    small = mb.PageBatch(device=0, params=params, cap_boxes=32)
+    r2 = small.run(torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(), torch.from_numpy(imgs).cuda())
+    torch.cuda.synchronize()
+    assert (r2.flags.cpu().numpy() & 1).all() and (r2.box_counts.cpu().numpy() == 32).all()
+    with pytest.raises(mb.CABIError) as e:
+        small.run_host(score, geo, imgs)
+    assert e.value.code == -3
+    # odd map size with quantisation 2: the reference raises IndexError (utils.py:370)
+    bad_score = np.zeros((1, 7, 8), np.float32)
+    bad_score[0, 6, 0] = 0.9
+    with pytest.raises(IndexError):
+        mb.PageBatch(device=0, params=mb.EastParams.default(target_size=32), cap_boxes=8, want_batch=False).run_host(
+            bad_score, np.zeros((1, 8, 7, 8), np.float32), None)

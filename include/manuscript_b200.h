@@ -147,6 +147,16 @@ MS_API int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n, in
 MS_API int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const int32_t *rects,
                             int64_t n, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8);
 
+/* ms_quad_crop_resize_pad for one page with HOST buffers: quads (n,8) f32, sizes_out (n,2) int32 or NULL. */
+MS_API int ms_quad_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quads,
+                                 int64_t n, int min_text_size, int border_mode, int border_value, int out_h,
+                                 int out_w, float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out);
+/* The rectified patch of one quad alone (h x w x 3 u8, row-major) -- the cv2.warpPerspective call above.  *w,*h get
+ * the patch size ((0,0): no patch); MS_ERR_CAPACITY (with *w,*h set) when it does not fit patch_cap bytes. */
+MS_API int ms_warp_quad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quad, int border_mode,
+                      int border_value, uint8_t *patch_out, int64_t patch_cap, int *w, int *h);
+
+
 /* ---------------------------------------------------------------------------------------------
  * DEVICE entry points: a batch of pages, stream-ordered, no host synchronisation.
  * ------------------------------------------------------------------------------------------- */
@@ -184,6 +194,21 @@ MS_API int ms_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts,
 MS_API int ms_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w,
                        const int32_t *crops, const int32_t *n_crops, int64_t crops_cap, int out_h,
                        int out_w, float *batch_f32, uint8_t *canvas_u8, void *stream);
+
+/* SURVEY 8f-4, an EXTENSION (the reference crops axis-aligned rectangles only, _pipeline.py:204-221; todo.md:1):
+ * rectified crops of rotated quads.  For every quad (rows of quad_stride >= 8 floats x0,y0..x3,y3 in the order
+ * top-left, top-right, bottom-right, bottom-left):
+ *   w,h   = round-half-even of the longer of each pair of opposite edges; no patch when a side is < max(2,
+ *           min_text_size) or > 32767, a coordinate is not finite or the 4-point system is singular
+ *   patch = cv2.warpPerspective(page, cv2.getPerspectiveTransform(rect(w,h), quad), (w,h),
+ *                               INTER_LINEAR | WARP_INVERSE_MAP, border)        (bit-exact, see quadcrop.cu)
+ * then the ResizeAndPadA + normalise of ms_crop_resize_pad.  Output row i belongs to quad i; a quad without a patch
+ * gives an all-padding canvas and sizes_out (w,h) = (0,0).  border_mode 0 = BORDER_CONSTANT with border_value on all
+ * channels, 1 = BORDER_REPLICATE.  Pages at most 32767 pixels on a side.  page_of (n) int32 or NULL (all page 0). */
+MS_API int ms_quad_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w,
+                            const float *quads, int quad_stride, const int32_t *page_of, int64_t n,
+                            int min_text_size, int border_mode, int border_value, int out_h, int out_w,
+                            float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out, void *stream);
 
 /* decode -> LANMS -> expand/filters -> word rects -> crop batch in one call (device buffers).
  * boxes_out (n_pages*cap_boxes,9), box_counts (n_pages); crops_out/n_crops/batch as above. */

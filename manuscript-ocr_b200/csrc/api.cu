@@ -466,7 +466,7 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
                       st, geo_compact));
     MS_TRY(timing_mark(ctx, 1, st));
     MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
-    // expand + EAST filters; orig size == target size here (pages are fed at target resolution)
+    // expand + EAST filters; boxes are scaled to the page images' size (infer.py:134-147: the original image), or target_size
     MS_TRY(timing_mark(ctx, 2, st));
     if (p->sort_reading_order) {
         // filtered boxes -> scratch, then into boxes_out in reading order (the order the crops are produced in)
@@ -476,10 +476,12 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
             ms_set_error("ms_page_batch: arena too small");
             return MS_ERR_CAPACITY;
         }
-        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, tmp, cap_boxes, box_counts, flags, bump, st));
+        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, tmp, cap_boxes, box_counts, flags, bump, st,
+                              img_h, img_w));
         MS_TRY(msk_reading_order(ctx, tmp, 9, box_counts, n_pages, cap_boxes, ord, boxes_out, flags, bump, st));
     } else {
-        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, boxes_out, cap_boxes, box_counts, flags, bump, st));
+        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, boxes_out, cap_boxes, box_counts, flags, bump,
+                              st, img_h, img_w));
     }
     MS_TRY(timing_mark(ctx, 3, st));
     if (want_crops) {
@@ -951,5 +953,95 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
         }
     }
     if (batch_dev_out) *batch_dev_out = d_batch;
+    return MS_OK;
+}
+
+// ---- rectified crops of rotated quads (an extension; see quadcrop.cu) ------------------------------------
+extern "C" int ms_quad_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w,
+                                       const float *quads, int quad_stride, const int32_t *page_of, int64_t n,
+                                       int min_text_size, int border_mode, int border_value, int out_h, int out_w,
+                                       float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out, void *stream)
+{
+    MS_CTX(ctx);
+    if (n < 0 || (n > 0 && (!pages || !quads))) {
+        ms_set_error("ms_quad_crop_resize_pad: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    MS_TRY(ms_arena_reserve(ctx, msk_quad_crop_scratch(n)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_quad_crop(ctx, pages, n_pages, img_h, img_w, quads, quad_stride, page_of, n, min_text_size, border_mode,
+                         border_value, out_h, out_w, batch_f32, canvas_u8, sizes_out, bump, (cudaStream_t)stream);
+}
+
+extern "C" int ms_quad_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quads,
+                                            int64_t n, int min_text_size, int border_mode, int border_value, int out_h,
+                                            int out_w, float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out)
+{
+    MS_CTX(ctx);
+    if (n < 0 || img_h <= 0 || img_w <= 0 || out_h <= 0 || out_w <= 0 || (n > 0 && (!page || !quads)) ||
+        (!batch_f32 && !canvas_u8) || n >= (int64_t)1 << 30) {
+        ms_set_error("ms_quad_crop_resize_pad_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    const size_t page_bytes = (size_t)img_h * img_w * 3;
+    const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float), one_u = (size_t)3 * out_h * out_w;
+    size_t need = al256(page_bytes) + al256((size_t)n * 32) + al256((size_t)n * 8) + 1024;
+    if (batch_f32) need += al256((size_t)n * one_f);
+    if (canvas_u8) need += al256((size_t)n * one_u);
+    MS_TRY(ms_stage_reserve(ctx, need));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    uint8_t *d_page = sb.take<uint8_t>(page_bytes);
+    float *d_quads = sb.take<float>((size_t)n * 8);
+    int32_t *d_sizes = sb.take<int32_t>((size_t)n * 2);
+    float *d_f = batch_f32 ? sb.take<float>((size_t)n * 3 * out_h * out_w) : nullptr;
+    uint8_t *d_u = canvas_u8 ? sb.take<uint8_t>((size_t)n * one_u) : nullptr;
+    if (!d_sizes || (batch_f32 && !d_f) || (canvas_u8 && !d_u)) {
+        ms_set_error("ms_quad_crop_resize_pad_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_page, page, page_bytes, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_quads, quads, (size_t)n * 32, cudaMemcpyHostToDevice, st));
+    MS_TRY(ms_arena_reserve(ctx, msk_quad_crop_scratch(n)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_quad_crop(ctx, d_page, 1, img_h, img_w, d_quads, 8, nullptr, n, min_text_size, border_mode, border_value,
+                         out_h, out_w, d_f, d_u, d_sizes, bump, st));
+    if (batch_f32) MS_CUDA(cudaMemcpyAsync(batch_f32, d_f, (size_t)n * one_f, cudaMemcpyDeviceToHost, st));
+    if (canvas_u8) MS_CUDA(cudaMemcpyAsync(canvas_u8, d_u, (size_t)n * one_u, cudaMemcpyDeviceToHost, st));
+    if (sizes_out) MS_CUDA(cudaMemcpyAsync(sizes_out, d_sizes, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+extern "C" int ms_warp_quad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quad,
+                                 int border_mode, int border_value, uint8_t *patch_out, int64_t patch_cap, int *w, int *h)
+{
+    MS_CTX(ctx);
+    if (!page || !quad || !w || !h || img_h <= 0 || img_w <= 0 || patch_cap < 0 || (patch_cap > 0 && !patch_out)) {
+        ms_set_error("ms_warp_quad_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    const size_t page_bytes = (size_t)img_h * img_w * 3;
+    MS_TRY(ms_stage_reserve(ctx, al256(page_bytes) + al256(32) + al256((size_t)patch_cap) + 1024));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    uint8_t *d_page = sb.take<uint8_t>(page_bytes);
+    float *d_quad = sb.take<float>(8);
+    uint8_t *d_patch = sb.take<uint8_t>((size_t)patch_cap + 1);
+    if (!d_patch) {
+        ms_set_error("ms_warp_quad_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_page, page, page_bytes, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_quad, quad, 32, cudaMemcpyHostToDevice, st));
+    MS_TRY(ms_arena_reserve(ctx, 8192));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    MS_TRY(msk_quad_warp(ctx, d_page, img_h, img_w, d_quad, border_mode, border_value, d_patch, (size_t)patch_cap, w, h,
+                         bump, st));
+    const size_t bytes = (size_t)(*w) * (*h) * 3;
+    if (bytes) MS_CUDA(cudaMemcpyAsync(patch_out, d_patch, bytes, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
     return MS_OK;
 }

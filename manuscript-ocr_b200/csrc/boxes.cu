@@ -215,13 +215,13 @@ __device__ __forceinline__ int block_excl_scan(int v, int *s_warp, int &total)
 __global__ void __launch_bounds__(256) east_prep_kernel(const float *__restrict__ quads,
                                                         const int32_t *__restrict__ counts, int n_pages, int cap,
                                                         ms_east_params P, const int32_t *__restrict__ orig_hw,
-                                                        EastScratch S)
+                                                        int orig_h, int orig_w, EastScratch S)
 {
     const bool ident = (P.expand_ratio_w == 0 && P.expand_ratio_h == 0);
     const float ex = (float)(1.0 + P.expand_ratio_w) - 1.0f, ey = (float)(1.0 + P.expand_ratio_h) - 1.0f;
     const int page = blockIdx.y;
     const int K = counts[page];
-    int oh = P.target_size, ow = P.target_size;
+    int oh = orig_h > 0 ? orig_h : P.target_size, ow = orig_w > 0 ? orig_w : P.target_size;
     if (orig_hw) {
         oh = orig_hw[2 * page];
         ow = orig_hw[2 * page + 1];
@@ -845,7 +845,7 @@ size_t msk_east_boxes_scratch(int n_pages, int cap_per_page)
 
 int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                    const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int out_cap, int32_t *counts_out,
-                   int32_t *flags, ms_bump bump, cudaStream_t st)
+                   int32_t *flags, ms_bump bump, cudaStream_t st, int orig_h, int orig_w)
 {
     if (n_pages <= 0) return MS_OK;
     if (!p || p->target_size <= 0 || out_cap <= 0) {
@@ -862,7 +862,7 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
     // counts live on the device: grids are sized for a few thousand boxes per page and stride beyond that
     int gx = (cap_per_page + 255) / 256;
     if (gx > 16) gx = 16;
-    east_prep_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(quads, counts, n_pages, cap_per_page, *p, orig_hw, S);
+    east_prep_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(quads, counts, n_pages, cap_per_page, *p, orig_hw, orig_h, orig_w, S);
     MS_LAUNCH_CHECK(ctx);
     east_ext_kernel<<<n_pages, 256, 0, st>>>(counts, cap_per_page, S);
     MS_LAUNCH_CHECK(ctx);

@@ -29,7 +29,7 @@
 //                           into the CHW batch.  full / empty mbarriers, no CTA-wide barrier in the loop.
 //   crop_generic_kernel     every other crop (copy, INTER_LINEAR upscale, integer-ratio or long-table INTER_AREA,
 //                           rows too long for the stage): one CTA per crop from global memory, same arithmetic.
-#include "ms_internal.cuh"
+#include "crop_common.cuh"
 
 namespace {
 
@@ -37,31 +37,6 @@ constexpr int kThreads = 192;   // 1 producer warp + 5 consumer warps; 4 CTAs pe
 constexpr int kCtasPerSm = 4;
 constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
 constexpr int kSrcBuf = 24 * 1024;  // bytes per staging buffer (two per CTA)
-
-struct Plan {
-    int page, x1, y1, w, h;
-    int nw, nh, y0;
-    int interp;  // 0 copy, 1 linear, 2 area integer-ratio, 3 area general
-    int isx, isy;
-    int ok;
-    int staged;  // source rows can be staged through TMA into shared memory
-    int fast;    // handled by the persistent TMA kernel (INTER_AREA, shrink factors < 3, staged); else generic kernel
-    int pitch;   // shared-memory row pitch (bytes) when staged
-    double scale_x, scale_y;
-};
-
-// one destination index of one axis: the OpenCV coefficient table entry
-struct AxisEnt {
-    int s0;      // area: first source index; linear: left/top source index
-    int n;       // area: number of taps;     linear x: edge flag;  linear y: bottom source index
-    int nfirst;  // area: 1 if a partial first tap exists; linear: coefficient 0 (a0 / b0)
-    int nmid;    // area: number of full-weight taps;      linear: coefficient 1 (a1 / b1)
-    float af, am, al;
-    int pad;
-};
-
-__device__ __forceinline__ int cv_round(float v) { return __float2int_rn(v); }
-__device__ __forceinline__ unsigned char sat_u8(int v) { return (unsigned char)min(max(v, 0), 255); }
 
 __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int img_h, int img_w, int ih, int iw,
                                           const uint8_t *pages, size_t total_bytes, Plan &p)
@@ -80,28 +55,7 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
     p.scale_x = p.scale_y = 1.0;
     if (!p.ok) return;
     const int w = p.w, h = p.h;
-    // transforms.py:91-95
-    double s1 = (double)ih / (double)max(h, 1), s2 = (double)iw / (double)max(w, 1);
-    double sc = fmin(s1, s2);
-    p.nw = max(1, (int)rint(w * sc));  // python round(): half to even
-    p.nh = max(1, (int)rint(h * sc));
-    p.nw = min(p.nw, iw);
-    p.nh = min(p.nh, ih);
-    int shrink = (p.nh < h || p.nw < w);  // transforms.py:80-83
-    p.y0 = (ih - p.nh) / 2;
-    p.y0 = max(0, min(p.y0, ih - p.nh));
-    p.scale_x = 1.0 / ((double)p.nw / (double)w);
-    p.scale_y = 1.0 / ((double)p.nh / (double)h);
-    p.isx = (int)rint(p.scale_x);
-    p.isy = (int)rint(p.scale_y);
-    if (p.nw == w && p.nh == h)
-        p.interp = 0;
-    else if (!shrink)
-        p.interp = 1;
-    else {
-        bool fast = fabs(p.scale_x - p.isx) < 2.220446049250313e-16 && fabs(p.scale_y - p.isy) < 2.220446049250313e-16;
-        p.interp = fast ? 2 : 3;
-    }
+    plan_resize(w, h, ih, iw, p);
     // staging: every row is copied as the 16-byte-aligned span that covers it; the pitch is exactly that span (the
     // 4-tap reads may run up to 16 bytes past a row -- into the next row, or into the slack kept after the last one).
     // When the page stride is a multiple of 16 every row has the same misalignment, otherwise assume the worst (15).
@@ -122,71 +76,6 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
     p.fast = p.staged && p.interp == 3 && p.scale_x < 2.999 && p.scale_y < 2.999 && p.w < 65536 && p.h < 65536;
 }
 
-// OpenCV computeResizeAreaTab for destination index d
-__device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize)
-{
-    AxisEnt t;
-    double f1 = d * scale, f2 = f1 + scale;
-    double cell = fmin(scale, (double)ssize - f1);
-    int s1 = (int)ceil(f1), s2 = (int)floor(f2);
-    s2 = min(s2, ssize - 1);
-    s1 = min(s1, s2);
-    const bool has_first = (s1 - f1) > 1e-3;
-    const bool has_last = (f2 - s2) > 1e-3;
-    t.af = (float)((s1 - f1) / cell);
-    t.am = (float)(1.0 / cell);
-    t.al = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
-    t.nfirst = has_first ? 1 : 0;
-    t.nmid = s2 > s1 ? s2 - s1 : 0;
-    t.s0 = has_first ? s1 - 1 : s1;
-    t.n = t.nfirst + t.nmid + (has_last ? 1 : 0);
-    t.pad = 0;
-    return t;
-}
-
-__device__ __forceinline__ float area_weight(const AxisEnt &t, int e)
-{
-    return e < t.nfirst ? t.af : (e < t.nfirst + t.nmid ? t.am : t.al);
-}
-
-__device__ __forceinline__ AxisEnt linear_entry_x(int dx, double scale, int w)
-{
-    AxisEnt t;
-    float fx = (float)((dx + 0.5) * scale - 0.5);
-    int sx = (int)floorf(fx);
-    fx -= sx;
-    if (sx < 0) {
-        fx = 0;
-        sx = 0;
-    }
-    const bool edge = sx + 1 >= w;
-    if (edge) {
-        fx = 0;
-        sx = w - 1;
-    }
-    t.s0 = sx;
-    t.n = edge ? 1 : 0;
-    t.nfirst = (short)cv_round((1.f - fx) * 2048.f);
-    t.nmid = (short)cv_round(fx * 2048.f);
-    t.af = t.am = t.al = 0.f;
-    t.pad = 0;
-    return t;
-}
-
-__device__ __forceinline__ AxisEnt linear_entry_y(int dy, double scale, int h)
-{
-    AxisEnt t;
-    float fy = (float)((dy + 0.5) * scale - 0.5);
-    int sy = (int)floorf(fy);
-    fy -= sy;
-    t.s0 = min(max(sy, 0), h - 1);
-    t.n = min(max(sy + 1, 0), h - 1);
-    t.nfirst = (short)cv_round((1.f - fy) * 2048.f);
-    t.nmid = (short)cv_round(fy * 2048.f);
-    t.af = t.am = t.al = 0.f;
-    t.pad = 0;
-    return t;
-}
 
 // ---- mbarrier + TMA bulk copy (sm_90+ PTX; SASS: SYNCS / UBLKCP) ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -221,86 +110,6 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
                  : "memory");
 }
 
-// Any interpolation mode, any tap count, source read from global memory; ex / ey are the pixel's coefficient-table
-// entries (INTER_LINEAR or INTER_AREA general).  Used by crop_generic_kernel for every crop the persistent TMA kernel
-// does not take.
-__device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, const uint8_t *gsrc, size_t stride,
-                                            const AxisEnt &ex, const AxisEnt &ey, unsigned char &o0, unsigned char &o1,
-                                            unsigned char &o2)
-{
-    auto row = [&](int sy) -> const unsigned char * { return gsrc + (size_t)sy * stride; };
-    if (p.interp == 0) {
-        const unsigned char *s = row(dy) + dx * 3;
-        o0 = s[0];
-        o1 = s[1];
-        o2 = s[2];
-    } else if (p.interp == 1) {
-        const unsigned char *S0 = row(ey.s0) + ex.s0 * 3;
-        const unsigned char *S1 = row(ey.n) + ex.s0 * 3;
-        const int a0 = ex.nfirst, a1 = ex.nmid, b0 = ey.nfirst, b1 = ey.nmid;
-        unsigned char o[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-            int r0, r1;
-            if (ex.n) {
-                r0 = S0[c] * 2048;
-                r1 = S1[c] * 2048;
-            } else {
-                r0 = S0[c] * a0 + S0[c + 3] * a1;
-                r1 = S1[c] * a0 + S1[c + 3] * a1;
-            }
-            o[c] = (unsigned char)((((b0 * (r0 >> 4)) >> 16) + ((b1 * (r1 >> 4)) >> 16) + 2) >> 2);
-        }
-        o0 = o[0];
-        o1 = o[1];
-        o2 = o[2];
-    } else if (p.interp == 2) {
-        int s0 = 0, s1 = 0, s2 = 0;
-        for (int yy = 0; yy < p.isy; yy++) {
-            const unsigned char *s = row(dy * p.isy + yy) + (size_t)dx * p.isx * 3;
-            for (int xx = 0; xx < p.isx; xx++) {
-                s0 += s[xx * 3];
-                s1 += s[xx * 3 + 1];
-                s2 += s[xx * 3 + 2];
-            }
-        }
-        if (p.isx == 2 && p.isy == 2) {
-            o0 = (unsigned char)((s0 + 2) >> 2);
-            o1 = (unsigned char)((s1 + 2) >> 2);
-            o2 = (unsigned char)((s2 + 2) >> 2);
-        } else {
-            const float inv = 1.f / (float)(p.isx * p.isy);
-            o0 = sat_u8(cv_round((float)s0 * inv));
-            o1 = sat_u8(cv_round((float)s1 * inv));
-            o2 = sat_u8(cv_round((float)s2 * inv));
-        }
-    } else {
-        float sum0 = 0.f, sum1 = 0.f, sum2 = 0.f;
-        for (int j = 0; j < ey.n; j++) {
-            const float beta = area_weight(ey, j);
-            const unsigned char *s = row(ey.s0 + j) + ex.s0 * 3;
-            float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-            for (int e = 0; e < ex.n; e++) {
-                const float a = area_weight(ex, e);
-                b0 = b0 + (float)s[e * 3] * a;
-                b1 = b1 + (float)s[e * 3 + 1] * a;
-                b2 = b2 + (float)s[e * 3 + 2] * a;
-            }
-            if (j == 0) {
-                sum0 = beta * b0;
-                sum1 = beta * b1;
-                sum2 = beta * b2;
-            } else {
-                sum0 += beta * b0;
-                sum1 += beta * b1;
-                sum2 += beta * b2;
-            }
-        }
-        o0 = sat_u8(cv_round(sum0));
-        o1 = sat_u8(cv_round(sum1));
-        o2 = sat_u8(cv_round(sum2));
-    }
-}
 
 // u8 -> f32 without the conversion pipe: byte k of `v` is spliced under the exponent of 2^23, then 2^23 is
 // subtracted (exact for 0..255)
@@ -379,58 +188,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
-// Everything outside the pasted rectangle is the 255 canvas (transforms.py:100), 1.0f after normalisation; written
-// as constant 16-byte streaming stores by `nthreads` cooperating threads.
-template <bool kWriteF32, bool kWriteU8>
-__device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, float *dstf, uint8_t *dstu, int vec_ok,
-                                              int tid, int nthreads, int c_begin = 0, int c_end = 3)
-{
-    const int plane = ih * iw;
-    const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
-    if (kWriteF32) {
-        const float one = (255.0f - 127.5f) * (1.0f / 127.5f);
-        if (vec_ok) {
-            const float4 one4 = make_float4(one, one, one, one);
-            const int nw4 = (nw + 3) & ~3;
-            const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
-            const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
-            for (int c = c_begin; c < c_end; c++) {
-                float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
-                for (int i = tid; i < top4; i += nthreads) __stcs(base4 + i, one4);
-                float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
-                for (int i = tid; i < bot4; i += nthreads) __stcs(bot + i, one4);
-                if (tail4 > 0) {
-                    const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
-                    for (int i = tid; i < nh * tail4; i += nthreads) {
-                        const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
-                        __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
-                               one4);
-                    }
-                }
-                for (int i = tid; i < nh * fr; i += nthreads) {
-                    const int r = i / fr, k = i - r * fr;
-                    __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
-                }
-            }
-        } else {
-            for (int e = c_begin * plane + tid; e < c_end * plane; e += nthreads) {
-                int c = e / plane, rem = e - c * plane;
-                int y = rem / iw, x = rem - y * iw;
-                if (!(y >= y0 && y < y0 + nh && x < nw)) dstf[e] = one;
-            }
-        }
-    }
-    if (kWriteU8 && c_begin == 0) {
-        for (int e = tid; e < plane; e += nthreads) {
-            int y = e / iw, x = e - y * iw;
-            if (!(y >= y0 && y < y0 + nh && x < nw)) {
-                dstu[(size_t)e * 3] = 255;
-                dstu[(size_t)e * 3 + 1] = 255;
-                dstu[(size_t)e * 3 + 2] = 255;
-            }
-        }
-    }
-}
 
 // Warp-specialised persistent kernel for the crops with Plan::fast.  Warp 0 (producer) walks this CTA's crops one
 // ahead of the consumers: it writes the crop's padding, waits until the stage buffer is released, issues the TMA row
@@ -653,7 +410,7 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__rest
             }
         }
         __syncthreads();
-        const uint8_t *gsrc = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+        const PitchedSrc gsrc{pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3, stride};
         const int npx = nw * nh;
         for (int t = threadIdx.x; t < npx; t += blockDim.x) {
             const int dy = t / nw, dx = t - dy * nw;
@@ -666,7 +423,7 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__rest
                 ey = p.interp == 3 ? area_entry(dy, p.scale_y, p.h) : linear_entry_y(dy, p.scale_y, p.h);
             }
             unsigned char o0, o1, o2;
-            resample_px(p, dx, dy, gsrc, stride, ex, ey, o0, o1, o2);
+            resample_px(p, dx, dy, gsrc, ex, ey, o0, o1, o2);
             const int at = (p.y0 + dy) * iw + dx;
             if (kWriteF32) {
                 dstf[at] = ((float)o0 - 127.5f) * inv;

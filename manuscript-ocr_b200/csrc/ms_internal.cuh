@@ -24,7 +24,8 @@ struct ms_ctx {
     size_t stage_bytes;
     // ms_stage_timing: ring of per-batch event sets
     int edge_factor;              // NMS neighbour-pair capacity per candidate (grown by the host entry points)
-    int smem_attr[4];             // largest dynamic shared-memory size already granted to: crop f32 / u8 / both, reading order
+    int smem_attr[8];             // largest dynamic shared-memory size already granted to: crop f32 / u8 / both, reading
+                                  // order, quad crop f32 / u8 / both
     cudaStream_t copy_stream;     // H2D stream of the pipelined host entry point
     cudaEvent_t chunk_ev[2];
     int timing;
@@ -95,7 +96,8 @@ int msk_polygon_iou(ms_ctx *ctx, const double *subj, const double *clip, int64_t
 int msk_expand(ms_ctx *ctx, const float *quads, int64_t n, double ew, double eh, float *out, cudaStream_t st);
 int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                    const ms_east_params *p, const int32_t *orig_hw, float *quads_out, int out_cap,
-                   int32_t *counts_out, int32_t *flags, ms_bump bump, cudaStream_t st);
+                   int32_t *counts_out, int32_t *flags, ms_bump bump, cudaStream_t st, int orig_h = 0,
+                   int orig_w = 0);  // orig_hw == NULL: every page is (orig_h, orig_w), or target_size when <= 0
 size_t msk_east_boxes_scratch(int n_pages, int cap_per_page);
 int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                    const int32_t *img_hw, int img_h, int img_w, int min_text_size, int32_t *crops_out,
@@ -113,6 +115,14 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
              uint8_t *canvas_u8, ms_bump bump, cudaStream_t st);
 size_t msk_crop_scratch(int64_t crops_cap);
+// quadcrop.cu
+int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const float *quads,
+                  int quad_stride, const int32_t *page_of, int64_t n, int min_text_size, int border_mode,
+                  int border_value, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out,
+                  ms_bump bump, cudaStream_t st);
+size_t msk_quad_crop_scratch(int64_t n);
+int msk_quad_warp(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quad_dev, int border_mode,
+                  int border_value, uint8_t *patch_dev, size_t patch_cap, int *w, int *h, ms_bump bump, cudaStream_t st);
 
 // ---- device geometry: lanms.py:7-130 in float64, no fused multiply-add ------------------------------
 #define MS_MAXV 20  // lanms.py:34

@@ -1,0 +1,435 @@
+// Rectified crops of rotated word quads -> resize-and-pad -> normalise -> CHW float32 batch.
+//
+// NOT a reference behaviour: the reference crops the axis-aligned bounding rectangle of every polygon
+// (_pipeline.py:204-221) and lists the rotated crop as future work (todo.md:1).  The operation is defined through the
+// OpenCV calls a maintainer would write,
+//     w, h  = round-half-even of the longer of each pair of opposite quad edges (float64); no patch if a side is < 2
+//             or > 32767
+//     Minv  = cv2.getPerspectiveTransform([[0,0],[w-1,0],[w-1,h-1],[0,h-1]], quad)
+//     patch = cv2.warpPerspective(page, Minv, (w, h), INTER_LINEAR | WARP_INVERSE_MAP, borderMode, borderValue)
+// followed by exactly the ResizeAndPadA + normalise of crop.cu, and restated bit for bit from OpenCV's
+// imgproc/imgwarp.cpp + core/matrix_decomp.cpp (checked against cv2 4.13 via tests/golden/quad_warp.npz):
+//   * the 8x8 system with float32 products in columns 6-7, LU with partial pivoting in float64 (eps = 100 ulp)
+//   * destination coordinates evaluated in blocks of bw0 columns: X0 = M0*bx + M1*y + M2, then (X0 + M0*x1) * (32/W),
+//     rounded half-to-even to 5 fractional bits
+//   * 15-bit bilinear weights (32-ay)(32-ax)*32 ..., with the integer-position entry {32767, 0, 0, 1};
+//     (sum + 2^14) >> 15; BORDER_CONSTANT substitutes the value per tap, BORDER_REPLICATE clamps the tap.
+//
+// Kernels: quad_plan_kernel (thread per quad: size, homography, resize plan) and quad_crop_kernel (CTA per quad:
+// warp the patch into shared memory -- or evaluate it on the fly when it is larger than the stage -- then the same
+// per-pixel resampling as crop_generic_kernel).  HBM traffic per quad: the touched page pixels + 3*ih*iw*4 bytes out.
+#include "crop_common.cuh"
+
+namespace {
+
+constexpr int kQcThreads = 256;
+constexpr int kQcPatchBytes = 40 * 1024;  // shared-memory patch stage (e.g. 260 x 52 pixels)
+constexpr int kQcMaxTab = 1024;
+
+struct QuadPlan {
+    double m[9];  // patch (x, y, 1) -> page (X, Y, W)
+    int page, w, h, bw0;
+    int ok, staged, pad0, pad1;
+};
+
+// oracle quad_patch_size: edge lengths in float64 from the float32 vertices
+__device__ __forceinline__ bool quad_patch_size(const float *q, int &w, int &h)
+{
+    double x[4], y[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        x[v] = (double)q[2 * v];
+        y[v] = (double)q[2 * v + 1];
+    }
+    auto edge = [&](int a, int b) {
+        const double dx = x[b] - x[a], dy = y[b] - y[a];
+        return sqrt(dx * dx + dy * dy);
+    };
+    const double e01 = edge(0, 1), e32 = edge(3, 2), e03 = edge(0, 3), e12 = edge(1, 2);
+    const double ew = e32 > e01 ? e32 : e01, eh = e12 > e03 ? e12 : e03;  // Python max(a, b)
+    w = h = 0;
+    if (!(isfinite(e01) && isfinite(e32) && isfinite(e03) && isfinite(e12))) return false;
+    if (ew > 32767.0 || eh > 32767.0) return false;  // beyond the 16-bit coordinates of the remap
+    w = (int)rint(ew);
+    h = (int)rint(eh);
+    return w >= 2 && h >= 2;
+}
+
+// cv2.getPerspectiveTransform(rect(w,h), quad): imgwarp.cpp builds the system, matrix_decomp.cpp LUImpl solves it
+__device__ bool perspective_from_rect(const float *q, int w, int h, double *m)
+{
+    const float sx[4] = {0.f, (float)(w - 1), (float)(w - 1), 0.f};
+    const float sy[4] = {0.f, 0.f, (float)(h - 1), (float)(h - 1)};
+    double a[8][8], b[8];
+    for (int i = 0; i < 4; i++) {
+        const float dx = q[2 * i], dy = q[2 * i + 1];
+        a[i][0] = a[i + 4][3] = sx[i];
+        a[i][1] = a[i + 4][4] = sy[i];
+        a[i][2] = a[i + 4][5] = 1.0;
+        a[i][3] = a[i][4] = a[i][5] = a[i + 4][0] = a[i + 4][1] = a[i + 4][2] = 0.0;
+        a[i][6] = (double)(-sx[i] * dx);  // float32 products (Point2f arithmetic)
+        a[i][7] = (double)(-sy[i] * dx);
+        a[i + 4][6] = (double)(-sx[i] * dy);
+        a[i + 4][7] = (double)(-sy[i] * dy);
+        b[i] = dx;
+        b[i + 4] = dy;
+    }
+    const double eps = 2.220446049250313e-16 * 100;
+    for (int i = 0; i < 8; i++) {
+        int k = i;
+        for (int j = i + 1; j < 8; j++)
+            if (fabs(a[j][i]) > fabs(a[k][i])) k = j;
+        if (fabs(a[k][i]) < eps) return false;
+        if (k != i) {
+            for (int j = i; j < 8; j++) {
+                const double t = a[i][j];
+                a[i][j] = a[k][j];
+                a[k][j] = t;
+            }
+            const double t = b[i];
+            b[i] = b[k];
+            b[k] = t;
+        }
+        const double d = -1 / a[i][i];
+        for (int j = i + 1; j < 8; j++) {
+            const double alpha = a[j][i] * d;
+            for (int c = i + 1; c < 8; c++) a[j][c] += alpha * a[i][c];
+            b[j] += alpha * b[i];
+        }
+    }
+    for (int i = 7; i >= 0; i--) {
+        double s = b[i];
+        for (int c = i + 1; c < 8; c++) s -= a[i][c] * b[c];
+        b[i] = s / a[i][i];
+    }
+    for (int i = 0; i < 8; i++) m[i] = b[i];
+    m[8] = 1.0;
+    return true;
+}
+
+__global__ void __launch_bounds__(128) quad_plan_kernel(const float *__restrict__ quads, int quad_stride,
+                                                        const int32_t *__restrict__ page_of, int64_t n, int n_pages,
+                                                        int min_text_size, int ih, int iw, QuadPlan *__restrict__ qplans,
+                                                        Plan *__restrict__ plans, int32_t *__restrict__ sizes_out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const float *q = quads + i * quad_stride;
+        QuadPlan qp;
+        Plan p;
+        p.page = p.x1 = p.y1 = p.w = p.h = p.nw = p.nh = p.y0 = p.interp = p.isx = p.isy = 0;
+        p.ok = p.staged = p.fast = p.pitch = 0;
+        p.scale_x = p.scale_y = 1.0;
+        qp.page = page_of ? page_of[i] : 0;
+        qp.ok = qp.staged = qp.pad0 = qp.pad1 = 0;
+        qp.bw0 = 1;
+#pragma unroll
+        for (int k = 0; k < 9; k++) qp.m[k] = 0.0;
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) v[k] = q[k];
+        bool ok = qp.page >= 0 && qp.page < n_pages && quad_patch_size(v, qp.w, qp.h);
+        ok = ok && qp.w >= min_text_size && qp.h >= min_text_size;  // _pipeline.py:130-133 applied to the patch
+        ok = ok && perspective_from_rect(v, qp.w, qp.h, qp.m);
+        if (ok) {
+            // WarpPerspectiveInvoker's block width for a (w, h) destination
+            const int bh0 = min(16, qp.h);
+            qp.bw0 = min(1024 / bh0, qp.w);
+            qp.ok = 1;
+            qp.staged = (size_t)qp.w * qp.h * 3 <= (size_t)kQcPatchBytes;
+            p.w = qp.w;
+            p.h = qp.h;
+            p.ok = 1;
+            plan_resize(qp.w, qp.h, ih, iw, p);
+        } else {
+            qp.w = qp.h = 0;
+        }
+        qplans[i] = qp;
+        plans[i] = p;
+        if (sizes_out) {
+            sizes_out[2 * i] = qp.w;
+            sizes_out[2 * i + 1] = qp.h;
+        }
+    }
+}
+
+struct PageView {
+    const uint8_t *px;  // (img_h, img_w, 3)
+    int img_h, img_w, replicate, bval;
+};
+
+// one patch pixel: WarpPerspectiveInvoker's coordinates + remapBilinear's fixed-point interpolation
+__device__ __forceinline__ void warp_px(const QuadPlan &qp, const PageView &pg, int x, int y, int &c0, int &c1, int &c2)
+{
+    const int bx = (x / qp.bw0) * qp.bw0, x1 = x - bx;
+    const double X0 = (qp.m[0] * bx + qp.m[1] * y) + qp.m[2];
+    const double Y0 = (qp.m[3] * bx + qp.m[4] * y) + qp.m[5];
+    const double W0 = (qp.m[6] * bx + qp.m[7] * y) + qp.m[8];
+    double W = W0 + qp.m[6] * x1;
+    W = W != 0.0 ? 32.0 / W : 0.0;
+    double fX = (X0 + qp.m[0] * x1) * W, fY = (Y0 + qp.m[3] * x1) * W;
+    // std::max((double)INT_MIN, std::min((double)INT_MAX, v)): a NaN ends up as INT_MAX
+    fX = fX < 2147483647.0 ? fX : 2147483647.0;
+    fX = -2147483648.0 < fX ? fX : -2147483648.0;
+    fY = fY < 2147483647.0 ? fY : 2147483647.0;
+    fY = -2147483648.0 < fY ? fY : -2147483648.0;
+    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
+    const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
+    const int ax = X & 31, ay = Y & 31;
+    int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
+    if ((ax | ay) == 0) {  // initInterTab2D: saturate_cast<short>(32768) = 32767, the missing unit goes to tap (1,1)
+        w00 = 32767;
+        w11 = 1;
+    }
+    const int H = pg.img_h, Wd = pg.img_w;
+    int t[4][3];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        int yy = sy + (k >> 1), xx = sx + (k & 1);
+        const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < Wd;
+        if (inside || pg.replicate) {
+            yy = min(max(yy, 0), H - 1);
+            xx = min(max(xx, 0), Wd - 1);
+            const uint8_t *s = pg.px + ((size_t)yy * Wd + xx) * 3;
+            t[k][0] = s[0];
+            t[k][1] = s[1];
+            t[k][2] = s[2];
+        } else {
+            t[k][0] = t[k][1] = t[k][2] = pg.bval;
+        }
+    }
+    auto mix = [&](int c) { return (t[0][c] * w00 + t[1][c] * w01 + t[2][c] * w10 + t[3][c] * w11 + (1 << 14)) >> 15; };
+    c0 = min(max(mix(0), 0), 255);
+    c1 = min(max(mix(1), 0), 255);
+    c2 = min(max(mix(2), 0), 255);
+}
+
+// patch too large for the stage: every tap is evaluated where it is used
+struct WarpSrc {
+    const QuadPlan *qp;
+    PageView pg;
+    __device__ __forceinline__ int at(int sy, int b) const
+    {
+        const int x = b / 3, c = b - 3 * x;
+        int c0, c1, c2;
+        warp_px(*qp, pg, x, sy, c0, c1, c2);
+        return c == 0 ? c0 : (c == 1 ? c1 : c2);
+    }
+};
+
+template <bool kWriteF32, bool kWriteU8, class Src>
+__device__ __forceinline__ void resample_canvas(const Plan &p, const Src &src, const AxisEnt *s_tab, bool tab_ok,
+                                                bool need_tab, int ih, int iw, float *dstf, uint8_t *dstu)
+{
+    const int plane = ih * iw;
+    const float inv = 1.0f / 127.5f;
+    const int nw = p.nw, nh = p.nh, npx = nw * nh;
+    for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+        const int dy = t / nw, dx = t - dy * nw;
+        AxisEnt ex = {}, ey = {};
+        if (tab_ok) {
+            ex = s_tab[dx];
+            ey = s_tab[nw + dy];
+        } else if (need_tab) {
+            ex = p.interp == 3 ? area_entry(dx, p.scale_x, p.w) : linear_entry_x(dx, p.scale_x, p.w);
+            ey = p.interp == 3 ? area_entry(dy, p.scale_y, p.h) : linear_entry_y(dy, p.scale_y, p.h);
+        }
+        unsigned char o0, o1, o2;
+        resample_px(p, dx, dy, src, ex, ey, o0, o1, o2);
+        const int at = (p.y0 + dy) * iw + dx;
+        if (kWriteF32) {
+            dstf[at] = ((float)o0 - 127.5f) * inv;
+            dstf[plane + at] = ((float)o1 - 127.5f) * inv;
+            dstf[2 * plane + at] = ((float)o2 - 127.5f) * inv;
+        }
+        if (kWriteU8) {
+            dstu[(size_t)at * 3] = o0;
+            dstu[(size_t)at * 3 + 1] = o1;
+            dstu[(size_t)at * 3 + 2] = o2;
+        }
+    }
+}
+
+template <bool kWriteF32, bool kWriteU8>
+__global__ void __launch_bounds__(kQcThreads) quad_crop_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w,
+                                                               const QuadPlan *__restrict__ qplans,
+                                                               const Plan *__restrict__ plans, int64_t n, int replicate,
+                                                               int bval, int ih, int iw, float *__restrict__ batch,
+                                                               uint8_t *__restrict__ canvas_out, int vec_ok)
+{
+    extern __shared__ __align__(16) unsigned char qc_smem[];
+    AxisEnt *s_tab = reinterpret_cast<AxisEnt *>(qc_smem);                 // kQcMaxTab entries
+    unsigned char *qc_patch = qc_smem + kQcMaxTab * sizeof(AxisEnt);       // kQcPatchBytes
+    __shared__ QuadPlan s_qp;
+    const int plane = ih * iw;
+    for (int64_t ci = blockIdx.x; ci < n; ci += gridDim.x) {
+        __syncthreads();  // the previous quad's plan, patch and tables are no longer read
+        if (threadIdx.x == 0) s_qp = qplans[ci];
+        const Plan p = plans[ci];
+        float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
+        uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
+        write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
+        if (!p.ok) continue;  // uniform across the CTA
+        const bool need_tab = p.interp == 1 || p.interp == 3;
+        const bool tab_ok = need_tab && p.nw + p.nh <= kQcMaxTab;
+        if (tab_ok) {
+            for (int t = threadIdx.x; t < p.nw + p.nh; t += blockDim.x) {
+                const bool isx = t < p.nw;
+                const int d = isx ? t : t - p.nw;
+                s_tab[t] = p.interp == 3 ? (isx ? area_entry(d, p.scale_x, p.w) : area_entry(d, p.scale_y, p.h))
+                                         : (isx ? linear_entry_x(d, p.scale_x, p.w) : linear_entry_y(d, p.scale_y, p.h));
+            }
+        }
+        __syncthreads();
+        const QuadPlan &qp = s_qp;
+        const PageView pg{pages + (size_t)qp.page * img_h * (size_t)img_w * 3, img_h, img_w, replicate, bval};
+        if (qp.staged) {
+            const int npx = qp.w * qp.h;
+            for (int t = threadIdx.x; t < npx; t += blockDim.x) {
+                const int y = t / qp.w, x = t - y * qp.w;
+                int c0, c1, c2;
+                warp_px(qp, pg, x, y, c0, c1, c2);
+                qc_patch[t * 3] = (unsigned char)c0;
+                qc_patch[t * 3 + 1] = (unsigned char)c1;
+                qc_patch[t * 3 + 2] = (unsigned char)c2;
+            }
+            __syncthreads();
+            const PitchedSrc src{qc_patch, (size_t)qp.w * 3};
+            resample_canvas<kWriteF32, kWriteU8>(p, src, s_tab, tab_ok, need_tab, ih, iw, dstf, dstu);
+        } else {
+            const WarpSrc src{&qp, pg};
+            resample_canvas<kWriteF32, kWriteU8>(p, src, s_tab, tab_ok, need_tab, ih, iw, dstf, dstu);
+        }
+    }
+}
+
+// the patch alone (row-major h x w x 3), for one planned quad
+__global__ void __launch_bounds__(256) quad_warp_kernel(const uint8_t *__restrict__ page, int img_h, int img_w,
+                                                        const QuadPlan *__restrict__ qplan, int replicate, int bval,
+                                                        uint8_t *__restrict__ patch)
+{
+    __shared__ QuadPlan s_qp;
+    if (threadIdx.x == 0) s_qp = *qplan;
+    __syncthreads();
+    const QuadPlan &qp = s_qp;
+    if (!qp.ok) return;
+    const PageView pg{page, img_h, img_w, replicate, bval};
+    const int64_t npx = (int64_t)qp.w * qp.h;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < npx; t += (int64_t)gridDim.x * blockDim.x) {
+        const int y = (int)(t / qp.w), x = (int)(t - (int64_t)y * qp.w);
+        int c0, c1, c2;
+        warp_px(qp, pg, x, y, c0, c1, c2);
+        patch[t * 3] = (unsigned char)c0;
+        patch[t * 3 + 1] = (unsigned char)c1;
+        patch[t * 3 + 2] = (unsigned char)c2;
+    }
+}
+
+}  // namespace
+
+size_t msk_quad_crop_scratch(int64_t n)
+{
+    const size_t k = (size_t)(n > 0 ? n : 0);
+    return k * (sizeof(QuadPlan) + sizeof(Plan)) + 4096;
+}
+
+#define MS_TRY(expr)                 \
+    do {                             \
+        int _r = (expr);             \
+        if (_r != MS_OK) return _r;  \
+    } while (0)
+
+static int quad_args_ok(int n_pages, int img_h, int img_w, int border_mode, int border_value, const char *who)
+{
+    if (n_pages <= 0 || img_h <= 0 || img_w <= 0 || img_h > 32767 || img_w > 32767) {
+        ms_set_error("%s: pages must be 1..32767 pixels on a side (16-bit remap coordinates), got %dx%d", who, img_h, img_w);
+        return MS_ERR_INVALID;
+    }
+    if (border_mode < 0 || border_mode > 1 || border_value < 0 || border_value > 255) {
+        ms_set_error("%s: border_mode must be 0 (constant) or 1 (replicate), border_value 0..255", who);
+        return MS_ERR_INVALID;
+    }
+    return MS_OK;
+}
+
+int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const float *quads,
+                  int quad_stride, const int32_t *page_of, int64_t n, int min_text_size, int border_mode,
+                  int border_value, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out,
+                  ms_bump bump, cudaStream_t st)
+{
+    if (n <= 0) return MS_OK;
+    MS_TRY(quad_args_ok(n_pages, img_h, img_w, border_mode, border_value, "quad_crop"));
+    if (out_h <= 0 || out_w <= 0 || quad_stride < 8 || (!batch_f32 && !canvas_u8) ||
+        (int64_t)out_h * out_w > (1 << 20)) {
+        ms_set_error("quad_crop: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    QuadPlan *qplans = bump.take<QuadPlan>((size_t)n);
+    Plan *plans = bump.take<Plan>((size_t)n);
+    if (!qplans || !plans) {
+        ms_set_error("quad_crop: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    int64_t pg = (n + 127) / 128;
+    if (pg > (int64_t)ctx->num_sms * 16) pg = (int64_t)ctx->num_sms * 16;
+    quad_plan_kernel<<<(int)pg, 128, 0, st>>>(quads, quad_stride, page_of, n, n_pages, min_text_size, out_h, out_w,
+                                             qplans, plans, sizes_out);
+    MS_LAUNCH_CHECK(ctx);
+    int64_t grid = (int64_t)ctx->num_sms * 3;  // 40 KB stage + 32 KB tables: three CTAs per SM
+    if (grid > n) grid = n;
+    const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
+    const int smem = kQcPatchBytes + kQcMaxTab * (int)sizeof(AxisEnt);
+    // cudaFuncSetAttribute is a synchronous driver call: once per context and kernel
+#define MS_QC_LAUNCH(F32, U8)                                                                                          \
+    do {                                                                                                               \
+        auto kfn = quad_crop_kernel<F32, U8>;                                                                          \
+        int &granted = ctx->smem_attr[4 + (F32 ? 1 : 0) + (U8 ? 2 : 0) - 1];                                           \
+        if (smem > granted) {                                                                                          \
+            MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
+            granted = smem;                                                                                            \
+        }                                                                                                              \
+        kfn<<<(int)grid, kQcThreads, smem, st>>>(pages, img_h, img_w, qplans, plans, n, border_mode, border_value,     \
+                                                 out_h, out_w, batch_f32, canvas_u8, vec_ok);                         \
+    } while (0)
+    if (batch_f32 && canvas_u8)
+        MS_QC_LAUNCH(true, true);
+    else if (batch_f32)
+        MS_QC_LAUNCH(true, false);
+    else
+        MS_QC_LAUNCH(false, true);
+#undef MS_QC_LAUNCH
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+// One quad's patch.  *w / *h receive the patch size (0, 0: no patch); the pixels are produced only when they fit
+// patch_cap bytes (device memory).  Synchronises `st` to read the size back.
+int msk_quad_warp(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quad_dev, int border_mode,
+                  int border_value, uint8_t *patch_dev, size_t patch_cap, int *w, int *h, ms_bump bump, cudaStream_t st)
+{
+    MS_TRY(quad_args_ok(1, img_h, img_w, border_mode, border_value, "quad_warp"));
+    QuadPlan *qplan = bump.take<QuadPlan>(1);
+    Plan *plan = bump.take<Plan>(1);
+    int32_t *size = bump.take<int32_t>(2);
+    if (!qplan || !plan || !size) {
+        ms_set_error("quad_warp: scratch too small");
+        return MS_ERR_CAPACITY;
+    }
+    quad_plan_kernel<<<1, 128, 0, st>>>(quad_dev, 8, nullptr, 1, 1, 0, 32, 128, qplan, plan, size);
+    MS_LAUNCH_CHECK(ctx);
+    int32_t hs[2] = {0, 0};
+    MS_CUDA(cudaMemcpyAsync(hs, size, sizeof(hs), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    *w = hs[0];
+    *h = hs[1];
+    const size_t need = (size_t)hs[0] * hs[1] * 3;
+    if (need == 0) return MS_OK;
+    if (need > patch_cap) {
+        ms_set_error("quad_warp: the %dx%d patch needs %zu bytes, capacity %zu", hs[0], hs[1], need, patch_cap);
+        return MS_ERR_CAPACITY;
+    }
+    int64_t grid = ((int64_t)hs[0] * hs[1] + 255) / 256;
+    if (grid > (int64_t)ctx->num_sms * 8) grid = (int64_t)ctx->num_sms * 8;
+    quad_warp_kernel<<<(int)grid, 256, 0, st>>>(page, img_h, img_w, qplan, border_mode, border_value, patch_dev);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}

@@ -20,8 +20,10 @@ from .ops import (  # noqa: F401
     expand_boxes,
     locality_aware_nms,
     polygon_iou,
+    quad_crop_resize_pad,
     should_merge,
     standard_nms,
+    warp_quad,
     word_reading_order,
     word_rects,
 )

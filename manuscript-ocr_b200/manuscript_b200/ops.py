@@ -184,5 +184,61 @@ def crop_resize_pad(page, rects, img_h=32, img_w=128, want_canvas=False, want_ba
     return batch if want_batch else canvas
 
 
+# ---- rectified crops of rotated quads -- an extension, the reference crops bounding rectangles only -----
+_BORDER = {"constant": 0, "replicate": 1}
+
+
+def warp_quad(page, quad, border="constant", border_value=0, ctx=None):
+    """The rectified (h,w,3) u8 patch of one quad (x0,y0..x3,y3: top-left, top-right, bottom-right, bottom-left):
+    cv2.warpPerspective(page, cv2.getPerspectiveTransform(rect(w,h), quad), (w,h), INTER_LINEAR | WARP_INVERSE_MAP,
+    border) with w,h the rounded longer opposite edges.  None when the quad has no patch (a side < 2 pixels,
+    non-finite coordinates or a singular 4-point system)."""
+    pg = np.ascontiguousarray(page, dtype=np.uint8)
+    if pg.ndim != 3 or pg.shape[2] != 3:
+        raise ValueError(f"page must be (H,W,3) uint8, got {pg.shape}")
+    q = np.ascontiguousarray(np.asarray(quad, dtype=np.float32).reshape(-1)[:8])
+    cx = _ctx(ctx)
+    w, h = C.c_int(0), C.c_int(0)
+    cap = 1 << 16
+    while True:
+        patch = np.empty(cap, np.uint8)
+        rc = cx.lib.ms_warp_quad_host(cx.handle, _ptr(pg), pg.shape[0], pg.shape[1], _ptr(q), _BORDER[border],
+                                      int(border_value), _ptr(patch), cap, C.byref(w), C.byref(h))
+        need = w.value * h.value * 3
+        if rc == -3 and need > cap:  # MS_ERR_CAPACITY: the size is known now
+            cap = need
+            continue
+        check(rc)
+        break
+    if need == 0:
+        return None
+    return patch[:need].reshape(h.value, w.value, 3).copy()
+
+
+def quad_crop_resize_pad(page, quads, img_h=32, img_w=128, min_text_size=5, border="constant", border_value=0,
+                         want_canvas=False, want_batch=True, ctx=None):
+    """page (H,W,3) u8, quads (n,4,2) or (n,>=8) float -> (batch and/or canvases as crop_resize_pad, valid (n,) bool).
+    Row i belongs to quad i; rows of quads without a patch (or smaller than min_text_size on a side) are all padding
+    and valid[i] is False."""
+    pg = np.ascontiguousarray(page, dtype=np.uint8)
+    if pg.ndim != 3 or pg.shape[2] != 3:
+        raise ValueError(f"page must be (H,W,3) uint8, got {pg.shape}")
+    n = len(quads)
+    q = np.ascontiguousarray(np.asarray(quads, dtype=np.float32).reshape(n, -1)[:, :8]) if n else np.zeros((0, 8), np.float32)
+    batch = np.empty((n, 3, img_h, img_w), np.float32) if want_batch else None
+    canvas = np.empty((n, img_h, img_w, 3), np.uint8) if want_canvas else None
+    sizes = np.zeros((n, 2), np.int32)
+    if n:
+        cx = _ctx(ctx)
+        check(cx.lib.ms_quad_crop_resize_pad_host(cx.handle, _ptr(pg), pg.shape[0], pg.shape[1], _ptr(q), n,
+                                                  int(min_text_size), _BORDER[border], int(border_value), int(img_h),
+                                                  int(img_w), _ptr(batch) if want_batch else None,
+                                                  _ptr(canvas) if want_canvas else None, _ptr(sizes)))
+    valid = sizes[:, 0] > 0
+    if want_batch and want_canvas:
+        return batch, canvas, valid
+    return (batch if want_batch else canvas), valid
+
+
 __all__ = [n for n in dir() if not n.startswith("_") and n not in ("C", "np", "EastParams", "check", "default_context")]
 _ = _cabi

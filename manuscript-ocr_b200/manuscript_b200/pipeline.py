@@ -40,13 +40,16 @@ def _text_and_confidence(result):
 
 
 class Pipeline:
-    def __init__(self, detector=None, recognizer=None, min_text_size=5):
+    def __init__(self, detector=None, recognizer=None, min_text_size=5, rotated_crops=False):
         if detector is None or recognizer is None:
             raise ValueError("Pipeline(detector=..., recognizer=...) are required: the default EAST()/TRBA() of the "
                              "reference download network weights, which are outside this package")
         self.detector = detector
         self.recognizer = recognizer
         self.min_text_size = min_text_size
+        # EXTENSION (reference todo.md:1): rectify every word quad with a perspective warp instead of
+        # cutting its bounding rectangle.  Off by default = the reference's behaviour.
+        self.rotated_crops = bool(rotated_crops)
 
     # ---- the steps between detector and recogniser -------------------------------------------------------------
     def _ordered_crop_rects(self, page, img_h, img_w):
@@ -64,6 +67,26 @@ class Pipeline:
                     words.append(word)
                     rects.append(rect)
         return words, (np.stack(rects).astype(np.int32) if rects else np.zeros((0, 4), np.int32))
+
+    def _recognise_rotated(self, image_array, words):
+        """rotated_crops=True: one rectified patch per word quad; words without a patch (smaller than min_text_size on
+        a side, degenerate) are skipped like the reference skips small boxes.  Returns (kept words, results)."""
+        rec = self.recognizer
+        rgb = TRBA._as_rgb(image_array)
+        quads = np.array([w.polygon for w in words], dtype=np.float32).reshape(len(words), -1)[:, :8]
+        if not isinstance(rec, TRBA):
+            patches = [ops.warp_quad(rgb, q) for q in quads]
+            keep = [i for i, p in enumerate(patches)
+                    if p is not None and min(p.shape[:2]) >= self.min_text_size]
+            return [words[i] for i in keep], rec.predict([patches[i] for i in keep])
+        results, kept = [], []
+        for i in range(0, len(words), rec.batch_size):
+            batch, valid = ops.quad_crop_resize_pad(rgb, quads[i:i + rec.batch_size], rec.img_h, rec.img_w,
+                                                    self.min_text_size)
+            if valid.any():
+                results.extend(rec.predict_batch(rec.torch.from_numpy(batch[valid]).to(rec.device)))
+                kept.extend(w for w, ok in zip(words[i:i + rec.batch_size], valid) if ok)
+        return kept, results
 
     def _recognise(self, image_array, rects):
         rec = self.recognizer
@@ -95,7 +118,10 @@ class Pipeline:
             print(f"Extract {len(words)} crops: {time.time() - t0:.3f}s")
         if words:
             t0 = time.time()
-            results = self._recognise(image_array, rects)
+            if self.rotated_crops:
+                words, results = self._recognise_rotated(image_array, [w for b in page.blocks for w in b.words])
+            else:
+                results = self._recognise(image_array, rects)
             if profile:
                 print(f"Recognition: {time.time() - t0:.3f}s")
             for word, result in zip(words, results):

@@ -284,3 +284,135 @@ def crop_resize_pad(page, rect, img_h, img_w):
     if rc != 0:
         raise ValueError(f"bad crop rect {rect}: {rc}")
     return canvas, chw
+
+
+# ---- rectified crops of rotated quads.  NOT a reference behaviour (the reference crops the axis-aligned
+# ---- bounding rectangle, _pipeline.py:204-221; todo.md:1 lists the rotated crop as future work).  Defined here as
+# ----   w, h  = round-half-even of the longer of each pair of opposite edges (float64); no patch if a side is < 2 or > 32767
+# ----           or the 4-point system is singular
+# ----   Minv  = cv2.getPerspectiveTransform([[0,0],[w-1,0],[w-1,h-1],[0,h-1]], quad)
+# ----   patch = cv2.warpPerspective(page, Minv, (w, h), INTER_LINEAR | WARP_INVERSE_MAP, borderMode, borderValue)
+# ---- and restated from OpenCV's imgproc/imgwarp.cpp (opencv-python pin >=4.5,<5; checked against cv2 4.13 through
+# ---- tests/golden/quad_warp.npz): LU with partial pivoting in float64, the 32x32-blocked coordinate evaluation,
+# ---- 5 fractional bits, 15-bit bilinear weights including the {32767,0,0,1} entry of the integer position.
+def quad_patch_size(quad):
+    q = np.asarray(quad, dtype=np.float32).reshape(-1)[:8].astype(np.float64).reshape(4, 2)
+
+    def edge(a, b):
+        dx, dy = q[b, 0] - q[a, 0], q[b, 1] - q[a, 1]
+        return np.sqrt(dx * dx + dy * dy)
+
+    with np.errstate(invalid="ignore", over="ignore"):
+        ew, eh = max(edge(0, 1), edge(3, 2)), max(edge(0, 3), edge(1, 2))
+    if not (np.isfinite(ew) and np.isfinite(eh)):
+        return 0, 0
+    if ew > 32767.0 or eh > 32767.0:  # beyond the 16-bit coordinates of the remap
+        return 0, 0
+    w, h = int(np.rint(ew)), int(np.rint(eh))
+    return (w, h) if w >= 2 and h >= 2 else (0, 0)  # a 1-pixel side makes the 4-point system singular
+
+
+def perspective_transform(src, dst):
+    """cv2.getPerspectiveTransform(src, dst) (imgwarp.cpp getPerspectiveTransform + matrix_decomp.cpp LUImpl)."""
+    src = np.asarray(src, np.float32).reshape(4, 2)
+    dst = np.asarray(dst, np.float32).reshape(4, 2)
+    a = np.zeros((8, 8))
+    b = np.zeros(8)
+    with np.errstate(over="ignore", invalid="ignore"):
+        for i in range(4):
+            a[i][0] = a[i + 4][3] = src[i][0]
+            a[i][1] = a[i + 4][4] = src[i][1]
+            a[i][2] = a[i + 4][5] = 1
+            a[i][6] = np.float32(-src[i][0] * dst[i][0])  # float32 products, as Point2f arithmetic gives
+            a[i][7] = np.float32(-src[i][1] * dst[i][0])
+            a[i + 4][6] = np.float32(-src[i][0] * dst[i][1])
+            a[i + 4][7] = np.float32(-src[i][1] * dst[i][1])
+            b[i], b[i + 4] = dst[i][0], dst[i][1]
+        eps = np.finfo(np.float64).eps * 100
+        for i in range(8):
+            k = i
+            for j in range(i + 1, 8):
+                if abs(a[j][i]) > abs(a[k][i]):
+                    k = j
+            if abs(a[k][i]) < eps:  # singular (cv2 switches to another solver here): the quad has no patch
+                return None
+            if k != i:
+                a[[i, k], i:] = a[[k, i], i:]
+                b[[i, k]] = b[[k, i]]
+            d = -1 / a[i][i]
+            for j in range(i + 1, 8):
+                alpha = a[j][i] * d
+                a[j, i + 1:] += alpha * a[i, i + 1:]
+                b[j] += alpha * b[i]
+        for i in range(7, -1, -1):
+            s = b[i]
+            for k in range(i + 1, 8):
+                s -= a[i][k] * b[k]
+            b[i] = s / a[i][i]
+    return np.append(b, 1.0).reshape(3, 3)
+
+
+def warp_perspective_inverse(page, minv, w, h, border="constant", border_value=0):
+    """cv2.warpPerspective(page, minv, (w,h), INTER_LINEAR|WARP_INVERSE_MAP, BORDER_CONSTANT|BORDER_REPLICATE) for u8x3."""
+    img = np.ascontiguousarray(page, dtype=np.uint8)
+    H, W = img.shape[:2]
+    M = np.asarray(minv, np.float64).reshape(-1)
+    bh0 = min(16, h)
+    bw0 = min(1024 // bh0, w)
+    ys, xs = np.mgrid[0:h, 0:w]
+    bx = (xs // bw0) * bw0
+    x1 = xs - bx
+    with np.errstate(all="ignore"):
+        X0 = (M[0] * bx + M[1] * ys) + M[2]
+        Y0 = (M[3] * bx + M[4] * ys) + M[5]
+        W0 = (M[6] * bx + M[7] * ys) + M[8]
+        Wv = W0 + M[6] * x1
+        Wv = np.where(Wv != 0, 32.0 / Wv, 0.0)
+        # std::max(INT_MIN, std::min(INT_MAX, v)): a NaN stays in the first argument's slot -> INT_MAX, then INT_MAX
+        fX = (X0 + M[0] * x1) * Wv
+        fY = (Y0 + M[3] * x1) * Wv
+        fX = np.where(np.isnan(fX), 2147483647.0, np.maximum(-2147483648.0, np.minimum(2147483647.0, fX)))
+        fY = np.where(np.isnan(fY), 2147483647.0, np.maximum(-2147483648.0, np.minimum(2147483647.0, fY)))
+    X = np.rint(fX).astype(np.int64)
+    Y = np.rint(fY).astype(np.int64)
+    sx = np.clip(X >> 5, -32768, 32767)
+    sy = np.clip(Y >> 5, -32768, 32767)
+    ax, ay = X & 31, Y & 31
+    w00, w01 = (32 - ay) * (32 - ax) * 32, (32 - ay) * ax * 32
+    w10, w11 = ay * (32 - ax) * 32, ay * ax * 32
+    z = (ax == 0) & (ay == 0)
+    w00 = np.where(z, 32767, w00)
+    w11 = np.where(z, 1, w11)
+
+    def tap(yy, xx):
+        v = img[np.clip(yy, 0, H - 1), np.clip(xx, 0, W - 1)].astype(np.int64)
+        if border != "replicate":
+            v[~((yy >= 0) & (yy < H) & (xx >= 0) & (xx < W))] = border_value
+        return v
+
+    acc = (tap(sy, sx) * w00[..., None] + tap(sy, sx + 1) * w01[..., None] + tap(sy + 1, sx) * w10[..., None]
+           + tap(sy + 1, sx + 1) * w11[..., None])
+    return np.clip((acc + (1 << 14)) >> 15, 0, 255).astype(np.uint8)
+
+
+def warp_quad(page, quad, border="constant", border_value=0):
+    """The rectified (h, w, 3) u8 patch of one quad (x0,y0..x3,y3: top-left, top-right, bottom-right, bottom-left)."""
+    w, h = quad_patch_size(quad)
+    if w == 0:
+        return None
+    q = np.asarray(quad, dtype=np.float32).reshape(-1)[:8].reshape(4, 2)
+    rect = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], np.float32)
+    m = perspective_transform(rect, q)
+    return None if m is None else warp_perspective_inverse(page, m, w, h, border, border_value)
+
+
+def quad_crop_resize_pad(page, quad, img_h, img_w, min_text_size=5, border="constant", border_value=0):
+    """warp_quad -> ResizeAndPadA canvas + normalised CHW (as crop_resize_pad); (None, None) when the patch is smaller
+    than min_text_size on a side (the rule of _pipeline.py:130-133 applied to the patch)."""
+    w, h = quad_patch_size(quad)
+    if w < min_text_size or h < min_text_size or w == 0:
+        return None, None
+    patch = warp_quad(page, quad, border, border_value)
+    if patch is None:
+        return None, None
+    return crop_resize_pad(patch, (0, 0, w, h), img_h, img_w)

@@ -222,3 +222,85 @@ def test_reading_order_device_on_detector_output(mb):
     rects, valid = cpu.word_rects(boxes[got], page, page, 5)
     nc = int(res.n_crops.cpu()[0])
     np.testing.assert_array_equal(res.crops[:nc].cpu().numpy()[:, 1:], rects[valid])
+
+
+# ---- SURVEY 8f-4 (extension): rotated crops through the Pipeline and the device entry point ---------------------------
+def test_pipeline_rotated_crops(mb):
+    W = mb.Word
+    words = [W(polygon=[[20.0, 30.0], [110.0, 18.0], [114.0, 48.0], [24.0, 60.0]], detection_confidence=0.9),
+             W(polygon=[[150.0, 20.0], [153.0, 20.0], [153.0, 23.0], [150.0, 23.0]], detection_confidence=0.9),  # 3 px
+             W(polygon=[[200.0, 40.0], [330.0, 60.0], [326.0, 90.0], [196.0, 70.0]], detection_confidence=0.9)]
+    img = np.random.default_rng(5).integers(0, 256, (120, 400, 3), dtype=np.uint8)
+    seen = {}
+
+    def model(batch):
+        seen["batch"] = batch.cpu().numpy()
+        return [(f"t{i}", 0.5) for i in range(len(batch))]
+
+    pipe = mb.Pipeline(detector=DummyDetector(mb, "dict", words), recognizer=mb.TRBA(model=model, img_h=32, img_w=128),
+                       rotated_crops=True)
+    page = pipe.predict(img)
+    got = {tuple(w.polygon[0]): w.text for w in page.blocks[0].words}
+    assert seen["batch"].shape == (2, 3, 32, 128)
+    assert got[(150.0, 20.0)] is None and {got[(20.0, 30.0)], got[(200.0, 40.0)]} == {"t0", "t1"}
+    first = [w for w in page.blocks[0].words if w.text == "t0"][0]
+    _, chw = cpu.quad_crop_resize_pad(img, np.array(first.polygon, np.float32).reshape(-1), 32, 128)
+    np.testing.assert_array_equal(seen["batch"][0], chw)
+
+    # a foreign recogniser receives the rectified uint8 patches
+    class Rec:
+        def predict(self, images):
+            self.images = images
+            return [{"text": "p", "confidence": 1.0} for _ in images]
+
+    rec = Rec()
+    mb.Pipeline(detector=DummyDetector(mb, "dict", words), recognizer=rec, rotated_crops=True).predict(img)
+    assert len(rec.images) == 2
+    np.testing.assert_array_equal(rec.images[0], cpu.warp_quad(img, np.array(first.polygon, np.float32).reshape(-1)))
+
+
+def test_quad_crop_device_entry(mb):
+    """ms_quad_crop_resize_pad on device buffers: two pages, box rows of 9 floats (quad + score) as the detector
+    stage leaves them, page_of per quad, launched on a torch stream."""
+    import ctypes as C
+
+    import torch
+
+    rng = np.random.default_rng(9)
+    pages = rng.integers(0, 256, (2, 300, 500, 3), dtype=np.uint8)
+    n = 50
+    rows = np.zeros((n, 9), np.float32)
+    for i in range(n):
+        cx, cy, ww, hh, a = rng.uniform(50, 450), rng.uniform(40, 260), rng.uniform(20, 150), rng.uniform(6, 50), \
+            rng.uniform(-0.4, 0.4)
+        c, s = np.cos(a), np.sin(a)
+        q = np.array([[-ww / 2, -hh / 2], [ww / 2, -hh / 2], [ww / 2, hh / 2], [-ww / 2, hh / 2]]) @ np.array(
+            [[c, s], [-s, c]]) + [cx, cy]
+        rows[i, :8] = q.reshape(-1)
+        rows[i, 8] = 0.9
+    page_of = rng.integers(0, 2, n).astype(np.int32)
+    page_of[3] = 7  # out of range: no patch
+    d_pages, d_rows, d_po = torch.from_numpy(pages).cuda(), torch.from_numpy(rows).cuda(), torch.from_numpy(page_of).cuda()
+    batch = torch.empty((n, 3, 32, 128), dtype=torch.float32, device="cuda")
+    sizes = torch.zeros((n, 2), dtype=torch.int32, device="cuda")
+    ctx = mb.Context(0)
+    stream = torch.cuda.Stream()
+    with torch.cuda.stream(stream):
+        before = ctx.launches
+        rc = ctx.lib.ms_quad_crop_resize_pad(ctx.handle, d_pages.data_ptr(), 2, 300, 500, d_rows.data_ptr(), 9,
+                                             d_po.data_ptr(), n, 5, 1, 0, 32, 128, batch.data_ptr(), None,
+                                             sizes.data_ptr(), C.c_void_p(stream.cuda_stream))
+        assert rc == 0, mb._cabi.last_error()
+        assert ctx.launches - before == 2
+    stream.synchronize()
+    got, sz = batch.cpu().numpy(), sizes.cpu().numpy()
+    for i in range(n):
+        if page_of[i] > 1:
+            assert tuple(sz[i]) == (0, 0) and (got[i] == 1.0).all()
+            continue
+        assert tuple(sz[i]) == cpu.quad_patch_size(rows[i, :8])
+        _, chw = cpu.quad_crop_resize_pad(pages[page_of[i]], rows[i, :8], 32, 128, 5, "replicate")
+        if chw is None:
+            assert tuple(sz[i]) == (0, 0)
+        else:
+            np.testing.assert_array_equal(got[i], chw)

@@ -76,6 +76,36 @@ def test_page_batch_vs_oracle(torch_cuda, page, words, n_pages):
     runner.ctx.edge_factor = 16
 
 
+def test_page_batch_original_size_pages(torch_cuda):
+    """Maps of a 512-target detector, page images at their original (non-square, larger) size: the boxes are
+    scaled to the original image (infer.py:134-147) before the filters and the crops are cut from it
+    (_pipeline.py:125-137), as EAST.predict + Pipeline.predict do."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    target, oh, ow = 512, 1100, 830
+    score, geo, _ = synthdata.make_batch([7, 8], target, 80)
+    rng = np.random.default_rng(3)
+    imgs = rng.integers(0, 256, (2, oh, ow, 3), dtype=np.uint8)
+    runner = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=target), cap_boxes=1024)
+    res = runner.run_host(score, geo, imgs)
+    n_crops = int(res.n_crops[0])
+    batch = res.batch.cpu().numpy()
+    k = 0
+    for p in range(2):
+        quads = cpu.decode_quads_from_maps(score[p], geo[p], 0.6, 4.0, 2)
+        nms = cpu.locality_aware_nms(quads, 0.2)
+        want = cpu.east_postprocess(nms, (oh, ow), target_size=target)
+        rects, valid = cpu.word_rects(want, oh, ow, 5)
+        rects = rects[valid]
+        np.testing.assert_array_equal(res.page_boxes(p), want)
+        np.testing.assert_array_equal(res.crops[k:k + len(rects), 1:], rects)
+        for j in range(0, len(rects), 5):
+            np.testing.assert_array_equal(batch[k + j], cpu.crop_resize_pad(imgs[p], rects[j], 32, 128)[1])
+        k += len(rects)
+    assert k == n_crops and k > 50
+
+
 def test_full_size_properties(torch_cuda):
     """2048x2048 / ~2000 quads (BASELINE configs[2] shape), 2 pages: properties that need no oracle run --
     page-permutation equivariance, idempotence of NMS on its own output, kept rows are descending in

@@ -307,3 +307,73 @@ def test_lanms_dense_candidates(ops):
     assert len(q) == 64 * 64
     np.testing.assert_array_equal(ops.decode_quads_from_maps(score, geo, -1.0, 4.0, 2), q)
     np.testing.assert_array_equal(ops.locality_aware_nms(q, 0.2), cpu.locality_aware_nms(q, 0.2))
+
+
+# ---- rectified crops of rotated quads (an extension; cv2 is the specification) ------------------------
+def test_quad_warp_golden(ops, golden_dir):
+    """ms_warp_quad_host against cv2.warpPerspective's own output, both border modes, bit for bit."""
+    g = np.load(os.path.join(golden_dir, "quad_warp.npz"))
+    rng = np.random.default_rng(int(g["seed"]))
+    H, W = (int(v) for v in g["page_hw"])
+    page = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    off = 0
+    bv = int(g["border_value"])
+    for q, (w, h) in zip(g["quads"], g["sizes"]):
+        got = ops.warp_quad(page, q, "constant", bv)
+        if w == 0:
+            assert got is None
+            continue
+        n = int(w) * int(h) * 3
+        assert got.shape == (h, w, 3)
+        np.testing.assert_array_equal(got.reshape(-1), g["const"][off:off + n])
+        np.testing.assert_array_equal(ops.warp_quad(page, q, "replicate").reshape(-1), g["repl"][off:off + n])
+        off += n
+    assert off == len(g["const"])
+
+
+def _random_quads(rng, n, H, W, wmax, hmax):
+    out = []
+    for _ in range(n):
+        cx, cy = rng.uniform(0, W), rng.uniform(0, H)
+        ww, hh = rng.uniform(3, wmax), rng.uniform(3, hmax)
+        ang = rng.uniform(-0.7, 0.7)
+        c, s = np.cos(ang), np.sin(ang)
+        q = np.array([[-ww / 2, -hh / 2], [ww / 2, -hh / 2], [ww / 2, hh / 2], [-ww / 2, hh / 2]]) @ np.array(
+            [[c, s], [-s, c]]) + [cx, cy]
+        out.append((q + rng.uniform(-2, 2, q.shape)).reshape(-1))
+    return np.array(out, np.float32)
+
+
+@pytest.mark.parametrize("out_hw", [(32, 128), (64, 256)])
+def test_quad_crop_vs_oracle(ops, out_hw):
+    """Warp + ResizeAndPadA + normalise against the oracle chain: small quads (INTER_LINEAR upscale), typical word
+    quads (INTER_AREA), patches larger than the shared-memory stage (evaluated on the fly), quads hanging over the
+    page border, quads below min_text_size and degenerate ones (no patch -> all-padding row, valid False)."""
+    ih, iw = out_hw
+    rng = np.random.default_rng(77)
+    H, W = 400, 700
+    page = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    quads = np.concatenate([
+        _random_quads(rng, 40, H, W, 30, 12),      # small: upscale / below min_text_size
+        _random_quads(rng, 60, H, W, 200, 60),     # word-sized
+        _random_quads(rng, 6, H, W, 600, 90)[:, :],  # larger than the 40 KB stage
+        np.array([[5, 5, 5.2, 5, 5.2, 5.2, 5, 5.2], [10, 20, 74, 20, 74, 36, 10, 36],
+                  [np.nan, 0, 50, 0, 50, 20, 0, 20], [0, 0, 3e38, 0, 3e38, 20, 0, 20]], np.float32),
+    ])
+    for border, bv in (("constant", 0), ("replicate", 0), ("constant", 200)):
+        batch, canvas, valid = ops.quad_crop_resize_pad(page, quads, ih, iw, 5, border, bv, want_canvas=True)
+        n_valid = 0
+        for i, q in enumerate(quads):
+            want_canvas, want_chw = cpu.quad_crop_resize_pad(page, q, ih, iw, 5, border, bv)
+            if want_canvas is None:
+                assert not valid[i]
+                assert (canvas[i] == 255).all() and (batch[i] == 1.0).all()
+                continue
+            assert valid[i], (i, q)
+            n_valid += 1
+            np.testing.assert_array_equal(canvas[i], want_canvas, err_msg=f"quad {i} {border}")
+            np.testing.assert_array_equal(batch[i], want_chw)
+        assert n_valid >= 80 and not valid[-1] and not valid[-2] and not valid[-4] and valid[-3]
+    # patch alone, larger than one launch wave of the single-quad kernel
+    big = np.array([20, 30, 660, 60, 650, 360, 15, 330], np.float32)
+    np.testing.assert_array_equal(ops.warp_quad(page, big, "replicate"), cpu.warp_quad(page, big, "replicate"))

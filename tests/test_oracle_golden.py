@@ -164,3 +164,34 @@ def test_live_reference_random_pages():
         for thr in (0.05, 0.2, 0.5):
             np.testing.assert_array_equal(cpu.locality_aware_nms(a, thr), rs.locality_aware_nms(a, thr))
         np.testing.assert_array_equal(cpu.expand_boxes(a[:50], 0.3, 0.7), ru.expand_boxes(a[:50], 0.3, 0.7))
+
+
+def _quad_warp_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "quad_warp.npz"))
+    rng = np.random.default_rng(int(g["seed"]))
+    H, W = (int(v) for v in g["page_hw"])
+    return g, rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+
+
+def test_quad_warp_golden(golden_dir):
+    """SURVEY 8f-4 (an extension, no reference function): the oracle's getPerspectiveTransform / warpPerspective
+    restatement against cv2's own output (tests/golden/make_golden_quad_warp.py), bit for bit."""
+    g, page = _quad_warp_golden(golden_dir)
+    off = 0
+    n_patches = 0
+    for q, (w, h), m in zip(g["quads"], g["sizes"], g["mats"]):
+        assert cpu.quad_patch_size(q) == (w, h)
+        if w == 0:
+            assert cpu.warp_quad(page, q) is None
+            assert cpu.quad_crop_resize_pad(page, q, 32, 128) == (None, None)
+            continue
+        rect = np.array([[0, 0], [w - 1, 0], [w - 1, h - 1], [0, h - 1]], np.float32)
+        mine = cpu.perspective_transform(rect, q.reshape(4, 2))
+        np.testing.assert_array_equal(mine.view(np.uint64), m.view(np.uint64))
+        n = int(w) * int(h) * 3
+        bv = int(g["border_value"])
+        np.testing.assert_array_equal(cpu.warp_quad(page, q, "constant", bv).reshape(-1), g["const"][off:off + n])
+        np.testing.assert_array_equal(cpu.warp_quad(page, q, "replicate").reshape(-1), g["repl"][off:off + n])
+        off += n
+        n_patches += 1
+    assert off == len(g["const"]) and n_patches >= 40

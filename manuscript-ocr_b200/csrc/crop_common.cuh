@@ -262,4 +262,141 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
     }
 }
 
+// u8 -> f32 without the conversion pipe: byte k of `v` is spliced under the exponent of 2^23, then 2^23 is
+// subtracted (exact for 0..255)
+__device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
+{
+    return __uint_as_float(__byte_perm(v, 0x4B000000u, sel)) - 8388608.0f;
+}
+
+// Horizontal pass of the INTER_AREA general path for one (source row, destination column) whose table has <= 4 taps,
+// out of the staged rows: 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit shared-memory words; taps
+// beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).  Same products and the same summation order as
+// resample_px's general branch.  `o` = shared-memory byte offset of the row's first tap.
+__device__ __forceinline__ void hrow_area4(const unsigned char *smem_base, uint32_t o, const float4 wx, float &b0,
+                                           float &b1, float &b2)
+{
+    const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
+    const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
+    const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
+    const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
+    // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
+    b0 = byte_f32(v0, 0x7650) * wx.x;
+    b1 = byte_f32(v0, 0x7651) * wx.x;
+    b2 = byte_f32(v0, 0x7652) * wx.x;
+    b0 = b0 + byte_f32(v0, 0x7653) * wx.y;
+    b1 = b1 + byte_f32(v1, 0x7650) * wx.y;
+    b2 = b2 + byte_f32(v1, 0x7651) * wx.y;
+    b0 = b0 + byte_f32(v1, 0x7652) * wx.z;
+    b1 = b1 + byte_f32(v1, 0x7653) * wx.z;
+    b2 = b2 + byte_f32(v2, 0x7650) * wx.z;
+    b0 = b0 + byte_f32(v2, 0x7651) * wx.w;
+    b1 = b1 + byte_f32(v2, 0x7652) * wx.w;
+    b2 = b2 + byte_f32(v2, 0x7653) * wx.w;
+}
+
+// The INTER_AREA coefficient tables of one crop for the 4-tap path, structure of arrays:
+// tab[0][i] = s0 | n << 16, tab[1..4][i] = tap weights (0 beyond n); x entries occupy [0, iw), y entries
+// [iw, iw + ih) of every array.  Plan::fast guarantees n <= 4; an entry that violates it is stored with n = 0xffff
+// and makes the consumers hand the crop to the generic kernel.
+__device__ __forceinline__ void build_tables(const Plan &p, uint32_t *tab, int tab_n, int iw, int tid,
+                                             int nthreads = 32)
+{
+    float *tw = reinterpret_cast<float *>(tab);
+    for (int t = tid; t < p.nw + p.nh; t += nthreads) {
+        const bool isx = t < p.nw;
+        const int d = isx ? t : t - p.nw;
+        const AxisEnt e = isx ? area_entry(d, p.scale_x, p.w) : area_entry(d, p.scale_y, p.h);
+        const int at = isx ? d : iw + d;
+        const bool fits = e.n <= 4 && e.s0 >= 0 && e.s0 < 65536;
+        tab[at] = fits ? ((uint32_t)e.s0 | ((uint32_t)e.n << 16)) : 0xffff0000u;
+#pragma unroll
+        for (int k = 0; k < 4; k++) tw[(size_t)(1 + k) * tab_n + at] = k < e.n ? area_weight(e, k) : 0.f;
+    }
+}
+
+// INTER_AREA general path for a crop whose axis tables have <= 4 taps per entry (shrink factors below 3), source
+// rows in shared memory `pitch` bytes apart starting at byte `stage_off` (+ the 16-byte misalignment a0, which
+// advances by sstep per row), SoA tables from build_tables.  kCT cooperating threads (index ct) each resample column
+// strips (one destination column, G consecutive destination rows): with a shrink factor near 2 neighbouring
+// destination rows share their boundary source row, so a strip needs ~(2G + 1) horizontal row sums instead of 3G;
+// per-pixel arithmetic and its order are those of resample_px's general branch.  Returns true when a table entry
+// had more than 4 taps (the caller redoes the crop with resample_px).
+template <bool kWriteF32, bool kWriteU8, int kCT>
+__device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t stage_off, uint32_t pitch, uint32_t a0,
+                                             uint32_t sstep, const uint32_t *tab, int tab_n, int ih, int iw, int nw,
+                                             int nh, int y0, float *dstf, uint8_t *dstu, int ct)
+{
+    const int plane = ih * iw;
+    const float inv = 1.0f / 127.5f;
+    // strip height: keep the threads evenly loaded
+    int G = 1;
+    {
+        int best = 0x7fffffff;
+        for (int g = 8; g >= 1; g >>= 1) {
+            const int items = ((nh + g - 1) / g) * nw;
+            const int cost = ((items + kCT - 1) / kCT) * (2 * g + 1);
+            if (cost < best) {
+                best = cost;
+                G = g;
+            }
+        }
+    }
+    const int nitems = ((nh + G - 1) / G) * nw;
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
+    const float *tw = reinterpret_cast<const float *>(tab);
+    bool bad = false;
+    for (int t = ct; t < nitems; t += kCT) {
+        const int grp = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - grp * nw;
+        const uint32_t px = tab[dx];
+        bad = bad || (px >> 16) > 4u;
+        const float4 wx = make_float4(tw[tab_n + dx], tw[2 * tab_n + dx], tw[3 * tab_n + dx], tw[4 * tab_n + dx]);
+        const uint32_t xoff = stage_off + (px & 0xffffu) * 3u;
+        int last_r = -1;
+        float b0 = 0.f, b1 = 0.f, b2 = 0.f;
+        const int dy_end = min(nh, grp * G + G);
+        for (int dy = grp * G; dy < dy_end; dy++) {
+            const uint32_t py = tab[iw + dy];
+            bad = bad || (py >> 16) > 4u;
+            const int ys0 = (int)(py & 0xffffu), yn = min((int)(py >> 16), 4);
+            const float wyv[4] = {tw[tab_n + iw + dy], tw[2 * tab_n + iw + dy], tw[3 * tab_n + iw + dy],
+                                  tw[4 * tab_n + iw + dy]};
+            // row 0 is the previous destination row's last source row when the two share it (uniform branch);
+            // the other rows are independent horizontal passes
+            const uint32_t rbase = xoff + (uint32_t)ys0 * pitch;
+            if (ys0 != last_r) {
+                const uint32_t mis = sstep == 0 ? a0 : ((a0 + (uint32_t)ys0 * sstep) & 15u);
+                hrow_area4(smem, rbase + mis, wx, b0, b1, b2);
+            }
+            float sum0 = wyv[0] * b0, sum1 = wyv[0] * b1, sum2 = wyv[0] * b2;
+#pragma unroll
+            for (int j = 1; j < 4; j++) {
+                if (j < yn) {
+                    const uint32_t r = (uint32_t)(ys0 + j);
+                    const uint32_t mis = sstep == 0 ? a0 : ((a0 + r * sstep) & 15u);
+                    hrow_area4(smem, rbase + (uint32_t)j * pitch + mis, wx, b0, b1, b2);
+                    sum0 += wyv[j] * b0;
+                    sum1 += wyv[j] * b1;
+                    sum2 += wyv[j] * b2;
+                }
+            }
+            last_r = ys0 + yn - 1;  // b0..b2 hold that row's horizontal sums
+            // cvRound (half to even), kept as floats: the weights sum to 1 within rounding -> [0, 255]
+            const float f0 = rintf(sum0), f1 = rintf(sum1), f2 = rintf(sum2);
+            const int at = (y0 + dy) * iw + dx;
+            if (kWriteF32) {
+                __stcs(dstf + at, (f0 - 127.5f) * inv);
+                __stcs(dstf + plane + at, (f1 - 127.5f) * inv);
+                __stcs(dstf + 2 * plane + at, (f2 - 127.5f) * inv);
+            }
+            if (kWriteU8) {
+                dstu[(size_t)at * 3] = sat_u8((int)f0);
+                dstu[(size_t)at * 3 + 1] = sat_u8((int)f1);
+                dstu[(size_t)at * 3 + 2] = sat_u8((int)f2);
+            }
+        }
+    }
+    return bad;
+}
+
 }  // namespace

@@ -24,12 +24,12 @@ namespace {
 
 constexpr int kQcThreads = 256;
 constexpr int kQcPatchBytes = 40 * 1024;  // shared-memory patch stage (e.g. 260 x 52 pixels)
-constexpr int kQcMaxTab = 1024;
+constexpr int kQcMaxTab = 384;            // AxisEnt entries (nw + nh of a 64 x 256 canvas is 320)
 
 struct QuadPlan {
     double m[9];  // patch (x, y, 1) -> page (X, Y, W)
     int page, w, h, bw0;
-    int ok, staged, pad0, pad1;
+    int ok, pad0, pad1, pad2;
 };
 
 // oracle quad_patch_size: edge lengths in float64 from the float32 vertices
@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(128) quad_plan_kernel(const float *__restrict_
         p.ok = p.staged = p.fast = p.pitch = 0;
         p.scale_x = p.scale_y = 1.0;
         qp.page = page_of ? page_of[i] : 0;
-        qp.ok = qp.staged = qp.pad0 = qp.pad1 = 0;
+        qp.ok = qp.pad0 = qp.pad1 = qp.pad2 = 0;
         qp.bw0 = 1;
 #pragma unroll
         for (int k = 0; k < 9; k++) qp.m[k] = 0.0;
@@ -135,11 +135,11 @@ __global__ void __launch_bounds__(128) quad_plan_kernel(const float *__restrict_
             const int bh0 = min(16, qp.h);
             qp.bw0 = min(1024 / bh0, qp.w);
             qp.ok = 1;
-            qp.staged = (size_t)qp.w * qp.h * 3 <= (size_t)kQcPatchBytes;
             p.w = qp.w;
             p.h = qp.h;
             p.ok = 1;
             plan_resize(qp.w, qp.h, ih, iw, p);
+            p.staged = (size_t)qp.w * qp.h * 3 <= (size_t)kQcPatchBytes;  // the patch fits the shared-memory stage
         } else {
             qp.w = qp.h = 0;
         }
@@ -157,22 +157,9 @@ struct PageView {
     int img_h, img_w, replicate, bval;
 };
 
-// one patch pixel: WarpPerspectiveInvoker's coordinates + remapBilinear's fixed-point interpolation
-__device__ __forceinline__ void warp_px(const QuadPlan &qp, const PageView &pg, int x, int y, int &c0, int &c1, int &c2)
+// remapBilinear's fixed-point interpolation at the 5-fractional-bit position (X, Y)
+__device__ __forceinline__ void sample_px(const PageView &pg, int X, int Y, int &c0, int &c1, int &c2)
 {
-    const int bx = (x / qp.bw0) * qp.bw0, x1 = x - bx;
-    const double X0 = (qp.m[0] * bx + qp.m[1] * y) + qp.m[2];
-    const double Y0 = (qp.m[3] * bx + qp.m[4] * y) + qp.m[5];
-    const double W0 = (qp.m[6] * bx + qp.m[7] * y) + qp.m[8];
-    double W = W0 + qp.m[6] * x1;
-    W = W != 0.0 ? 32.0 / W : 0.0;
-    double fX = (X0 + qp.m[0] * x1) * W, fY = (Y0 + qp.m[3] * x1) * W;
-    // std::max((double)INT_MIN, std::min((double)INT_MAX, v)): a NaN ends up as INT_MAX
-    fX = fX < 2147483647.0 ? fX : 2147483647.0;
-    fX = -2147483648.0 < fX ? fX : -2147483648.0;
-    fY = fY < 2147483647.0 ? fY : 2147483647.0;
-    fY = -2147483648.0 < fY ? fY : -2147483648.0;
-    const int X = __double2int_rn(fX), Y = __double2int_rn(fY);
     const int sx = min(max(X >> 5, -32768), 32767), sy = min(max(Y >> 5, -32768), 32767);
     const int ax = X & 31, ay = Y & 31;
     int w00 = (32 - ay) * (32 - ax) * 32, w01 = (32 - ay) * ax * 32, w10 = ay * (32 - ax) * 32, w11 = ay * ax * 32;
@@ -181,26 +168,99 @@ __device__ __forceinline__ void warp_px(const QuadPlan &qp, const PageView &pg, 
         w11 = 1;
     }
     const int H = pg.img_h, Wd = pg.img_w;
-    int t[4][3];
+    int t0[3], t1[3], t2[3], t3[3];
+    if (sx >= 0 && sy >= 0 && sx + 1 < Wd && sy + 1 < H) {  // all four taps inside: two 6-byte runs
+        const uint8_t *s = pg.px + ((size_t)sy * Wd + sx) * 3;
+        const uint8_t *r = s + (size_t)Wd * 3;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        int yy = sy + (k >> 1), xx = sx + (k & 1);
-        const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < Wd;
-        if (inside || pg.replicate) {
-            yy = min(max(yy, 0), H - 1);
-            xx = min(max(xx, 0), Wd - 1);
-            const uint8_t *s = pg.px + ((size_t)yy * Wd + xx) * 3;
-            t[k][0] = s[0];
-            t[k][1] = s[1];
-            t[k][2] = s[2];
-        } else {
-            t[k][0] = t[k][1] = t[k][2] = pg.bval;
+        for (int c = 0; c < 3; c++) {
+            t0[c] = s[c];
+            t1[c] = s[3 + c];
+            t2[c] = r[c];
+            t3[c] = r[3 + c];
+        }
+    } else {
+        auto tap = [&](int yy, int xx, int *t) {
+            const bool inside = yy >= 0 && yy < H && xx >= 0 && xx < Wd;
+            if (inside || pg.replicate) {
+                yy = min(max(yy, 0), H - 1);
+                xx = min(max(xx, 0), Wd - 1);
+                const uint8_t *s = pg.px + ((size_t)yy * Wd + xx) * 3;
+                t[0] = s[0];
+                t[1] = s[1];
+                t[2] = s[2];
+            } else {
+                t[0] = t[1] = t[2] = pg.bval;
+            }
+        };
+        tap(sy, sx, t0);
+        tap(sy, sx + 1, t1);
+        tap(sy + 1, sx, t2);
+        tap(sy + 1, sx + 1, t3);
+    }
+    auto mix = [&](int c) { return (t0[c] * w00 + t1[c] * w01 + t2[c] * w10 + t3[c] * w11 + (1 << 14)) >> 15; };
+    // the weights are non-negative and sum to 2^15: the result is already within [0, 255]
+    c0 = mix(0);
+    c1 = mix(1);
+    c2 = mix(2);
+}
+
+// WarpPerspectiveInvoker's destination -> source coordinates: (X0, Y0, W0) are the terms of the block start
+// (bx, y), x1 the column inside the block
+__device__ __forceinline__ void warp_xy(const QuadPlan &qp, double X0, double Y0, double W0, int x1, int &X, int &Y)
+{
+    double W = W0 + qp.m[6] * x1;
+    W = W != 0.0 ? 32.0 / W : 0.0;
+    double fX = (X0 + qp.m[0] * x1) * W, fY = (Y0 + qp.m[3] * x1) * W;
+    // std::max((double)INT_MIN, std::min((double)INT_MAX, v)): a NaN ends up as INT_MAX
+    fX = fX < 2147483647.0 ? fX : 2147483647.0;
+    fX = -2147483648.0 < fX ? fX : -2147483648.0;
+    fY = fY < 2147483647.0 ? fY : 2147483647.0;
+    fY = -2147483648.0 < fY ? fY : -2147483648.0;
+    X = __double2int_rn(fX);
+    Y = __double2int_rn(fY);
+}
+
+__device__ __forceinline__ void block_terms(const QuadPlan &qp, int bx, int y, double &X0, double &Y0, double &W0)
+{
+    X0 = (qp.m[0] * bx + qp.m[1] * y) + qp.m[2];
+    Y0 = (qp.m[3] * bx + qp.m[4] * y) + qp.m[5];
+    W0 = (qp.m[6] * bx + qp.m[7] * y) + qp.m[8];
+}
+
+// one patch pixel at (x, y)
+__device__ __forceinline__ void warp_px(const QuadPlan &qp, const PageView &pg, int x, int y, int &c0, int &c1, int &c2)
+{
+    const int bx = (x / qp.bw0) * qp.bw0;
+    double X0, Y0, W0;
+    block_terms(qp, bx, y, X0, Y0, W0);
+    int X, Y;
+    warp_xy(qp, X0, Y0, W0, x - bx, X, Y);
+    sample_px(pg, X, Y, c0, c1, c2);
+}
+
+// rows [row0, row0 + step, ...) of the patch by one warp each, lanes along x inside every coordinate block: no
+// integer division, the block terms are evaluated once per (row, block)
+__device__ __forceinline__ void warp_rows(const QuadPlan &qp, const PageView &pg, unsigned char *patch, size_t pitch,
+                                          int row0, int row_step, int lane)
+{
+    for (int y = row0; y < qp.h; y += row_step) {
+        unsigned char *dst = patch + (size_t)y * pitch;
+        for (int bx = 0; bx < qp.w; bx += qp.bw0) {
+            double X0, Y0, W0;
+            block_terms(qp, bx, y, X0, Y0, W0);
+            const int bw = min(qp.bw0, qp.w - bx);
+            for (int x1 = lane; x1 < bw; x1 += 32) {
+                int X, Y, c0, c1, c2;
+                warp_xy(qp, X0, Y0, W0, x1, X, Y);
+                sample_px(pg, X, Y, c0, c1, c2);
+                unsigned char *d = dst + (size_t)(bx + x1) * 3;
+                d[0] = (unsigned char)c0;
+                d[1] = (unsigned char)c1;
+                d[2] = (unsigned char)c2;
+            }
         }
     }
-    auto mix = [&](int c) { return (t[0][c] * w00 + t[1][c] * w01 + t[2][c] * w10 + t[3][c] * w11 + (1 << 14)) >> 15; };
-    c0 = min(max(mix(0), 0), 255);
-    c1 = min(max(mix(1), 0), 255);
-    c2 = min(max(mix(2), 0), 255);
 }
 
 // patch too large for the stage: every tap is evaluated where it is used
@@ -250,17 +310,22 @@ __device__ __forceinline__ void resample_canvas(const Plan &p, const Src &src, c
 }
 
 template <bool kWriteF32, bool kWriteU8>
-__global__ void __launch_bounds__(kQcThreads) quad_crop_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w,
-                                                               const QuadPlan *__restrict__ qplans,
-                                                               const Plan *__restrict__ plans, int64_t n, int replicate,
-                                                               int bval, int ih, int iw, float *__restrict__ batch,
-                                                               uint8_t *__restrict__ canvas_out, int vec_ok)
+__global__ void __launch_bounds__(kQcThreads, 3) quad_crop_kernel(const uint8_t *__restrict__ pages, int img_h,
+                                                                  int img_w, const QuadPlan *__restrict__ qplans,
+                                                                  const Plan *__restrict__ plans, int64_t n,
+                                                                  int replicate, int bval, int ih, int iw,
+                                                                  float *__restrict__ batch,
+                                                                  uint8_t *__restrict__ canvas_out, int vec_ok)
 {
+    // [patch stage kQcPatchBytes + 16][tables: AxisEnt[kQcMaxTab] for resample_px, or the SoA tables of area4_strips]
     extern __shared__ __align__(16) unsigned char qc_smem[];
-    AxisEnt *s_tab = reinterpret_cast<AxisEnt *>(qc_smem);                 // kQcMaxTab entries
-    unsigned char *qc_patch = qc_smem + kQcMaxTab * sizeof(AxisEnt);       // kQcPatchBytes
+    unsigned char *qc_patch = qc_smem;
+    AxisEnt *s_tab = reinterpret_cast<AxisEnt *>(qc_smem + kQcPatchBytes + 16);
+    uint32_t *soa = reinterpret_cast<uint32_t *>(s_tab);
     __shared__ QuadPlan s_qp;
-    const int plane = ih * iw;
+    const int plane = ih * iw, tab_n = iw + ih;
+    const bool soa_fits = (size_t)tab_n * 5 * sizeof(uint32_t) <= (size_t)kQcMaxTab * sizeof(AxisEnt);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t ci = blockIdx.x; ci < n; ci += gridDim.x) {
         __syncthreads();  // the previous quad's plan, patch and tables are no longer read
         if (threadIdx.x == 0) s_qp = qplans[ci];
@@ -269,9 +334,13 @@ __global__ void __launch_bounds__(kQcThreads) quad_crop_kernel(const uint8_t *__
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
         write_padding<kWriteF32, kWriteU8>(p, ih, iw, dstf, dstu, vec_ok, threadIdx.x, blockDim.x);
         if (!p.ok) continue;  // uniform across the CTA
+        // crop.cu's 4-tap INTER_AREA path applies to a staged patch shrunk by factors below 3
+        const bool strips = p.staged && soa_fits && p.interp == 3 && p.scale_x < 2.999 && p.scale_y < 2.999;
         const bool need_tab = p.interp == 1 || p.interp == 3;
         const bool tab_ok = need_tab && p.nw + p.nh <= kQcMaxTab;
-        if (tab_ok) {
+        if (strips) {
+            build_tables(p, soa, tab_n, iw, threadIdx.x, kQcThreads);
+        } else if (tab_ok) {
             for (int t = threadIdx.x; t < p.nw + p.nh; t += blockDim.x) {
                 const bool isx = t < p.nw;
                 const int d = isx ? t : t - p.nw;
@@ -282,19 +351,23 @@ __global__ void __launch_bounds__(kQcThreads) quad_crop_kernel(const uint8_t *__
         __syncthreads();
         const QuadPlan &qp = s_qp;
         const PageView pg{pages + (size_t)qp.page * img_h * (size_t)img_w * 3, img_h, img_w, replicate, bval};
-        if (qp.staged) {
-            const int npx = qp.w * qp.h;
-            for (int t = threadIdx.x; t < npx; t += blockDim.x) {
-                const int y = t / qp.w, x = t - y * qp.w;
-                int c0, c1, c2;
-                warp_px(qp, pg, x, y, c0, c1, c2);
-                qc_patch[t * 3] = (unsigned char)c0;
-                qc_patch[t * 3 + 1] = (unsigned char)c1;
-                qc_patch[t * 3 + 2] = (unsigned char)c2;
-            }
+        if (p.staged) {
+            const size_t pitch = (size_t)qp.w * 3;
+            warp_rows(qp, pg, qc_patch, pitch, warp, kQcThreads / 32, lane);
             __syncthreads();
-            const PitchedSrc src{qc_patch, (size_t)qp.w * 3};
-            resample_canvas<kWriteF32, kWriteU8>(p, src, s_tab, tab_ok, need_tab, ih, iw, dstf, dstu);
+            bool redo = !strips;
+            if (strips)
+                redo = __syncthreads_or(area4_strips<kWriteF32, kWriteU8, kQcThreads>(
+                    qc_smem, 0u, (uint32_t)pitch, 0u, 0u, soa, tab_n, ih, iw, p.nw, p.nh, p.y0, dstf, dstu, threadIdx.x));
+            if (redo) {
+                if (strips) {  // an entry with more than 4 taps after all: per-pixel entries, no table
+                    resample_canvas<kWriteF32, kWriteU8>(p, PitchedSrc{qc_patch, pitch}, s_tab, false, need_tab, ih, iw,
+                                                         dstf, dstu);
+                } else {
+                    resample_canvas<kWriteF32, kWriteU8>(p, PitchedSrc{qc_patch, pitch}, s_tab, tab_ok, need_tab, ih,
+                                                         iw, dstf, dstu);
+                }
+            }
         } else {
             const WarpSrc src{&qp, pg};
             resample_canvas<kWriteF32, kWriteU8>(p, src, s_tab, tab_ok, need_tab, ih, iw, dstf, dstu);
@@ -374,10 +447,10 @@ int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int
     quad_plan_kernel<<<(int)pg, 128, 0, st>>>(quads, quad_stride, page_of, n, n_pages, min_text_size, out_h, out_w,
                                              qplans, plans, sizes_out);
     MS_LAUNCH_CHECK(ctx);
-    int64_t grid = (int64_t)ctx->num_sms * 3;  // 40 KB stage + 32 KB tables: three CTAs per SM
+    int64_t grid = (int64_t)ctx->num_sms * 3;  // 40 KB stage + 12 KB tables, <= 85 registers: three CTAs per SM
     if (grid > n) grid = n;
     const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
-    const int smem = kQcPatchBytes + kQcMaxTab * (int)sizeof(AxisEnt);
+    const int smem = kQcPatchBytes + 16 + kQcMaxTab * (int)sizeof(AxisEnt);
     // cudaFuncSetAttribute is a synchronous driver call: once per context and kernel
 #define MS_QC_LAUNCH(F32, U8)                                                                                          \
     do {                                                                                                               \

@@ -170,8 +170,9 @@ __device__ __forceinline__ void sample_px(const PageView &pg, int X, int Y, int 
     const int H = pg.img_h, Wd = pg.img_w;
     int t0[3], t1[3], t2[3], t3[3];
     if (sx >= 0 && sy >= 0 && sx + 1 < Wd && sy + 1 < H) {  // all four taps inside: two 6-byte runs
-        const uint8_t *s = pg.px + ((size_t)sy * Wd + sx) * 3;
-        const uint8_t *r = s + (size_t)Wd * 3;
+        // a page is at most 32767 x 32767 x 3 bytes: the offset fits 32 bits
+        const uint8_t *s = pg.px + ((uint32_t)sy * (uint32_t)Wd + (uint32_t)sx) * 3u;
+        const uint8_t *r = s + (uint32_t)Wd * 3u;
 #pragma unroll
         for (int c = 0; c < 3; c++) {
             t0[c] = s[c];
@@ -185,7 +186,7 @@ __device__ __forceinline__ void sample_px(const PageView &pg, int X, int Y, int 
             if (inside || pg.replicate) {
                 yy = min(max(yy, 0), H - 1);
                 xx = min(max(xx, 0), Wd - 1);
-                const uint8_t *s = pg.px + ((size_t)yy * Wd + xx) * 3;
+                const uint8_t *s = pg.px + ((uint32_t)yy * (uint32_t)Wd + (uint32_t)xx) * 3u;
                 t[0] = s[0];
                 t[1] = s[1];
                 t[2] = s[2];
@@ -211,14 +212,11 @@ __device__ __forceinline__ void warp_xy(const QuadPlan &qp, double X0, double Y0
 {
     double W = W0 + qp.m[6] * x1;
     W = W != 0.0 ? 32.0 / W : 0.0;
-    double fX = (X0 + qp.m[0] * x1) * W, fY = (Y0 + qp.m[3] * x1) * W;
-    // std::max((double)INT_MIN, std::min((double)INT_MAX, v)): a NaN ends up as INT_MAX
-    fX = fX < 2147483647.0 ? fX : 2147483647.0;
-    fX = -2147483648.0 < fX ? fX : -2147483648.0;
-    fY = fY < 2147483647.0 ? fY : 2147483647.0;
-    fY = -2147483648.0 < fY ? fY : -2147483648.0;
-    X = __double2int_rn(fX);
-    Y = __double2int_rn(fY);
+    const double fX = (X0 + qp.m[0] * x1) * W, fY = (Y0 + qp.m[3] * x1) * W;
+    // saturate_cast<int>(std::max((double)INT_MIN, std::min((double)INT_MAX, v))): the conversion instruction already
+    // saturates to [INT_MIN, INT_MAX] (round half to even, as cvRound); a NaN comes out of the min/max as INT_MAX
+    X = fX != fX ? INT_MAX : __double2int_rn(fX);
+    Y = fY != fY ? INT_MAX : __double2int_rn(fY);
 }
 
 __device__ __forceinline__ void block_terms(const QuadPlan &qp, int bx, int y, double &X0, double &Y0, double &W0)
@@ -310,7 +308,7 @@ __device__ __forceinline__ void resample_canvas(const Plan &p, const Src &src, c
 }
 
 template <bool kWriteF32, bool kWriteU8>
-__global__ void __launch_bounds__(kQcThreads, 3) quad_crop_kernel(const uint8_t *__restrict__ pages, int img_h,
+__global__ void __launch_bounds__(kQcThreads, 4) quad_crop_kernel(const uint8_t *__restrict__ pages, int img_h,
                                                                   int img_w, const QuadPlan *__restrict__ qplans,
                                                                   const Plan *__restrict__ plans, int64_t n,
                                                                   int replicate, int bval, int ih, int iw,
@@ -447,7 +445,7 @@ int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int
     quad_plan_kernel<<<(int)pg, 128, 0, st>>>(quads, quad_stride, page_of, n, n_pages, min_text_size, out_h, out_w,
                                              qplans, plans, sizes_out);
     MS_LAUNCH_CHECK(ctx);
-    int64_t grid = (int64_t)ctx->num_sms * 3;  // 40 KB stage + 12 KB tables, <= 85 registers: three CTAs per SM
+    int64_t grid = (int64_t)ctx->num_sms * 4;  // 40 KB stage + 12 KB tables, 64 registers: four CTAs per SM
     if (grid > n) grid = n;
     const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
     const int smem = kQcPatchBytes + 16 + kQcMaxTab * (int)sizeof(AxisEnt);

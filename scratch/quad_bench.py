@@ -11,7 +11,7 @@ rng = np.random.default_rng(0)
 pages = torch.randint(0, 256, (P, S, S, 3), dtype=torch.uint8, device="cuda")
 rows = np.zeros((P * K, 8), np.float32)
 cx, cy = rng.uniform(60, S - 60, P * K), rng.uniform(30, S - 30, P * K)
-ww, hh, a = rng.uniform(40, 140, P * K), rng.uniform(14, 40, P * K), rng.uniform(-0.15, 0.15, P * K)
+ww, hh, a = rng.uniform(100, 200, P * K), rng.uniform(28, 44, P * K), rng.uniform(-0.15, 0.15, P * K)  # bench.py's word boxes: ~150 x 35
 c, s = np.cos(a), np.sin(a)
 for k, (sx, sy) in enumerate([(-1, -1), (1, -1), (1, 1), (-1, 1)]):
     rows[:, 2 * k] = cx + sx * ww / 2 * c - sy * hh / 2 * s

@@ -37,7 +37,29 @@ def cases():
             rows.append((x - 8, 30 + r * 40 - 6 + int(rng.integers(-3, 4)), x + w + 8, 30 + r * 40 + 30))
             x += w + 6
     out.append(np.array(rows, np.int64))
+    # larger random pages (the device kernel's grid-based pair generation starts at 256 boxes): duplicates, zero-size
+    # boxes, a box over half the page, negative and large coordinates, dense chains of overlaps
+    for seed, n, span in [(1, 700, 900), (2, 1500, 2000), (3, 400, 60000), (4, 300, 300)]:
+        out.append(large_random(seed, n, span))
+    # every box flat: avg_h == 0, the x-gap condition (<= avg_h * inf = NaN) never holds
+    r8 = np.random.default_rng(8)
+    x0, y0 = r8.integers(0, 500, 300), r8.integers(0, 500, 300)
+    out.append(np.stack([x0, y0, x0 + r8.integers(1, 40, 300), y0], axis=1).astype(np.int64))
     return out
+
+
+def large_random(seed, n, span):
+    rng = np.random.default_rng(seed)
+    x0 = rng.integers(-50, span, n)
+    y0 = rng.integers(-50, span, n)
+    w = rng.integers(0, max(8, span // 12), n)
+    h = rng.integers(0, max(6, span // 40), n)
+    boxes = np.stack([x0, y0, x0 + w, y0 + h], axis=1).astype(np.int64)
+    boxes[5] = boxes[17]
+    boxes[40] = boxes[17]
+    boxes[61, 3] = boxes[61, 1]
+    boxes[62] = (0, 0, span // 2, span // 2)
+    return boxes
 
 
 def main():

@@ -778,40 +778,56 @@ __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__re
         if (gthread == 0) und[round & 1] = 0;
         cluster_sync_all();
         int qn = 0;  // warp-uniform
-        for (int base = (crank * kResolveWarps + warp) * 32; base < E; base += csize * kResolveWarps * 32) {
-            const int e = base + lane;
-            bool need = false;
-            if (e < E) {
-                const uint64_t ed = edges[e];  // each pair word is only ever touched by this thread
-                if (!(ed & kPairDone)) {
-                    const int hi = (int)((ed >> 30) & 0x3fffffffu), lo = (int)(ed & 0x3fffffffu);
-                    if (state[lo] != 0) {
-                        edges[e] = ed | kPairDone;
-                    } else {
-                        const uint8_t sh = state[hi];
-                        if (sh == 1) {
-                            if (ed & kPairTrue)
-                                state[lo] = 2;
-                            else
-                                need = true;
-                        } else if (sh == 0) {
-                            blocked[lo] = 1;
-                        } else {
-                            edges[e] = ed | kPairDone;  // a suppressed box suppresses nothing
-                        }
-                    }
+        // kEB pairs per lane and iteration: the pair words, then the two state bytes of every pair, are independent
+        // loads in flight together (the loop is bound by their latency, not by bandwidth).  A state byte read a
+        // little early is at worst a stale 0, which only defers the pair to the next round.
+        constexpr int kEB = 4;
+        for (int base = (crank * kResolveWarps + warp) * 32 * kEB; base < E; base += csize * kResolveWarps * 32 * kEB) {
+            uint64_t ed[kEB];
+            uint8_t slo[kEB], shi[kEB];
+#pragma unroll
+            for (int k = 0; k < kEB; k++) {
+                const int e = base + k * 32 + lane;
+                ed[k] = e < E ? edges[e] : kPairDone;  // each pair word is only ever touched by this thread
+            }
+#pragma unroll
+            for (int k = 0; k < kEB; k++) {
+                slo[k] = shi[k] = 0;
+                if (!(ed[k] & kPairDone)) {
+                    slo[k] = state[(int)(ed[k] & 0x3fffffffu)];
+                    shi[k] = state[(int)((ed[k] >> 30) & 0x3fffffffu)];
                 }
             }
-            const uint32_t m = __ballot_sync(0xffffffffu, need);
-            if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = e;
-            qn += __popc(m);
-            __syncwarp();
-            if (qn >= 32) {
-                const int e2 = q[qn - 32 + lane];
+#pragma unroll
+            for (int k = 0; k < kEB; k++) {
+                const int e = base + k * 32 + lane;
+                bool need = false;
+                if (!(ed[k] & kPairDone)) {
+                    const int lo = (int)(ed[k] & 0x3fffffffu);
+                    if (slo[k] != 0) {
+                        edges[e] = ed[k] | kPairDone;
+                    } else if (shi[k] == 1) {
+                        if (ed[k] & kPairTrue)
+                            state[lo] = 2;
+                        else
+                            need = true;
+                    } else if (shi[k] == 0) {
+                        blocked[lo] = 1;
+                    } else {
+                        edges[e] = ed[k] | kPairDone;  // a suppressed box suppresses nothing
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, need);
+                if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = e;
+                qn += __popc(m);
                 __syncwarp();
-                clip(e2);
-                qn -= 32;
-                __syncwarp();
+                if (qn >= 32) {
+                    const int e2 = q[qn - 32 + lane];
+                    __syncwarp();
+                    clip(e2);
+                    qn -= 32;
+                    __syncwarp();
+                }
             }
         }
         if (lane < qn) clip(q[lane]);

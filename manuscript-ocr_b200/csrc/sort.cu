@@ -11,8 +11,8 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kWarps = kThreads / 32;
-constexpr int kItemsPerWarp = 1024;                 // each warp owns a contiguous strip of the tile
-constexpr int kTile = kWarps * kItemsPerWarp;       // 8192 keys per CTA
+constexpr int kItemsPerWarp = 256;                  // each warp owns a contiguous strip of the tile
+constexpr int kTile = kWarps * kItemsPerWarp;       // 2048 keys per CTA: a 15k-candidate page is 8 CTAs
 constexpr int kRadix = 256;
 
 // Every page's (u32 key, u32 value) segment [page_off[p], page_off[p+1]) is sorted on its own.

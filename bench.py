@@ -57,6 +57,7 @@ def parse_args():
     ap.add_argument("--cpu-pages", type=int, default=8, help="pages in the bounded cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the reading-order and rotated-quad-crop timings")
     ap.add_argument("--reading-order", action="store_true",
                     help="also run the reading-order sort between the box filters and the crops (what Pipeline.predict "
                          "does; not part of the BASELINE metric, reported under config.reading_order)")
@@ -353,6 +354,64 @@ def run_b200(a):
     if rank == 0:
         sampler.stop()
 
+    # ---- variants (not the BASELINE metric; N = 1 only, outside both timed regions' clocks) ------------------------
+    variants = None
+    if world == 1 and not a.no_variants:
+        variants = {}
+
+        def timed(fn, reps=5):
+            for _ in range(2):
+                fn()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(reps):
+                fn()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+
+        if not a.reading_order:  # the step as Pipeline.predict runs it: boxes and crops in reading order
+            ro = mb.PageBatch(device=local, params=mb.EastParams.default(target_size=S, sort_reading_order=1),
+                              cap_boxes=cap_boxes, crops_cap=crops_cap, out_hw=(OUT_H, OUT_W))
+            ms_ro = timed(lambda: ro.run(d_score, d_geo, d_pages))
+            variants["with_reading_order"] = {"ms_per_step": ms_ro, "pages_per_s": P / (ms_ro * 1e-3),
+                                              "note": "ms_east_params.sort_reading_order = 1 (utils.py:610-644 + "
+                                                      "_pipeline.py:105-123 on the device)"}
+            del ro
+        # rotated-quad crops (SURVEY 8f-4 extension): this step's boxes, each turned by up to +-0.15 rad about its centre
+        import ctypes as C
+
+        bx = res.boxes.cpu().numpy()
+        quads, page_of = [], []
+        rng = np.random.default_rng(1)
+        for pg in range(P):
+            q = bx[pg, : counts[pg], :8].reshape(-1, 4, 2).astype(np.float64)
+            c = q.mean(axis=1, keepdims=True)
+            ang = rng.uniform(-0.15, 0.15, len(q))
+            rot = np.stack([np.stack([np.cos(ang), -np.sin(ang)], -1), np.stack([np.sin(ang), np.cos(ang)], -1)], -2)
+            quads.append((np.einsum("nij,nkj->nki", rot, q - c) + c).reshape(-1, 8))
+            page_of.append(np.full(len(q), pg, np.int32))
+        quads = torch.from_numpy(np.concatenate(quads).astype(np.float32)).to(dev)
+        page_of = torch.from_numpy(np.concatenate(page_of)).to(dev)
+        nq = int(quads.shape[0])
+        qbatch = torch.empty((nq, 3, OUT_H, OUT_W), dtype=torch.float32, device=dev)
+        qsizes = torch.zeros((nq, 2), dtype=torch.int32, device=dev)
+
+        def quad_run():
+            mb._cabi.check(ctx.lib.ms_quad_crop_resize_pad(
+                ctx.handle, d_pages.data_ptr(), P, S, S, quads.data_ptr(), 8, page_of.data_ptr(), nq, 5, 1, 0, OUT_H,
+                OUT_W, qbatch.data_ptr(), None, qsizes.data_ptr(), C.c_void_p(stream.cuda_stream)))
+
+        ms_q = timed(quad_run)
+        sz = qsizes.cpu().numpy().astype(np.int64)
+        q_bytes = 3 * int((sz[:, 0] * sz[:, 1]).sum()) + 3 * OUT_H * OUT_W * 4 * nq
+        variants["rotated_quad_crop"] = {"ms_per_launch": ms_q, "quads": nq, "patches": int((sz[:, 0] > 0).sum()),
+                                         "alg_bytes": q_bytes, "gbs": q_bytes / (ms_q * 1e-3) / 1e9,
+                                         "note": "ms_quad_crop_resize_pad: cv2.warpPerspective-exact rectified crops "
+                                                 "(extension, not a reference behaviour)"}
+        del qbatch, quads
+
     total_boxes = sum_over_ranks(float(n_boxes))
     if rank != 0:
         if dist is not None:
@@ -399,6 +458,11 @@ def run_b200(a):
     }
     if e2e is not None:
         line["e2e"] = e2e
+    if variants:
+        for v in variants.values():
+            if "gbs" in v:
+                v["frac_of_hbm_peak"] = v["gbs"] / peak
+        line["variants"] = variants
     if world == 1 and not a.no_cpu_baseline:
         pps, _, dt = cpu_baseline(a, a.cpu_pages, 1)
         line["cpu_baseline"] = {"value": pps, "unit": "pages/s", "cores": 1, "kind": "port",

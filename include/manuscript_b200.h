@@ -218,6 +218,16 @@ MS_API int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, cons
                   int32_t *crops_out, int64_t crops_cap, int32_t *n_crops, float *batch_f32,
                   uint8_t *canvas_u8, int32_t *flags, void *stream);
 
+/* ms_page_batch for page images of their OWN sizes (a batch of originals: EAST.predict resizes each to target_size,
+ * so the maps are uniform while the images are not).  page_ptrs (n_pages) device pointers to (h_i, w_i, 3) u8
+ * images, page_hw (n_pages,2) int32 on the device.  Boxes are scaled to each page's size (infer.py:134-147) and the
+ * crops cut from its pixels.  Images whose base address is 16-byte aligned use the TMA path. */
+MS_API int ms_page_batch_ragged(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *const *page_ptrs,
+                         const int32_t *page_hw, int n_pages, int map_h, int map_w, const ms_east_params *p,
+                         int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
+                         int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
+                         float *batch_f32, uint8_t *canvas_u8, int32_t *flags, void *stream);
+
 /* Same path with HOST buffers (pinned or pageable): H2D of maps + pages, the batch, D2H of boxes,
  * counts, crop list and (optionally, if batch_f32_host != NULL) the crop batch.  When
  * batch_dev_out != NULL the crop batch stays on the device and its pointer is returned there
@@ -227,6 +237,14 @@ MS_API int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *geo,
                        int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
                        int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
                        float *batch_f32_host, float **batch_dev_out, int32_t *flags);
+
+/* ms_page_batch_ragged with HOST buffers: pages (n_pages) host pointers, page_hw (n_pages,2) int32 on the host;
+ * outputs as ms_page_batch_host. */
+MS_API int ms_page_batch_ragged_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *const *pages,
+                              const int32_t *page_hw, int n_pages, int map_h, int map_w, const ms_east_params *p,
+                              int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
+                              int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
+                              float *batch_f32_host, float **batch_dev_out, int32_t *flags);
 
 #ifdef __cplusplus
 }

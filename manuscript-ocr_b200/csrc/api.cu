@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <new>
+#include <vector>
 
 #include "ms_internal.cuh"
 
@@ -444,9 +445,13 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
                            const ms_east_params *p, int min_text_size, int out_h, int out_w, int cap_boxes,
                            float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
                            int32_t *n_crops, int append, float *batch_f32, uint8_t *canvas_u8, int32_t *flags,
-                           cudaStream_t st, int geo_compact = 0)
+                           cudaStream_t st, int geo_compact = 0, const uint8_t *const *page_ptrs = nullptr,
+                           const int32_t *page_hw = nullptr)
 {
-    const bool want_crops = pages_all != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
+    // page_ptrs / page_hw (device, indexed by the global page number): page images of their own sizes
+    const bool ragged = page_ptrs != nullptr && page_hw != nullptr;
+    const int32_t *hw_here = ragged ? page_hw + 2 * (size_t)page_base : nullptr;  // this chunk's pages
+    const bool want_crops = (pages_all != nullptr || ragged) && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
     const int q = p->quantization < 1 ? 1 : p->quantization;
     const int cap_c = cand_cap(map_h, map_w, q);
     MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor, cap_boxes)));
@@ -476,21 +481,21 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
             ms_set_error("ms_page_batch: arena too small");
             return MS_ERR_CAPACITY;
         }
-        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, tmp, cap_boxes, box_counts, flags, bump, st,
+        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, hw_here, tmp, cap_boxes, box_counts, flags, bump, st,
                               img_h, img_w));
         MS_TRY(msk_reading_order(ctx, tmp, 9, box_counts, n_pages, cap_boxes, ord, boxes_out, flags, bump, st));
     } else {
-        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, nullptr, boxes_out, cap_boxes, box_counts, flags, bump,
+        MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, hw_here, boxes_out, cap_boxes, box_counts, flags, bump,
                               st, img_h, img_w));
     }
     MS_TRY(timing_mark(ctx, 3, st));
     if (want_crops) {
-        MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, nullptr, img_h, img_w, min_text_size,
+        MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, hw_here, img_h, img_w, min_text_size,
                               crops_out, crops_cap, n_crops, page_base, append, range, bump, st));
         MS_TRY(timing_mark(ctx, 4, st));
         if (batch_f32 || canvas_u8)
             MS_TRY(msk_crop(ctx, pages_all, total_pages, img_h, img_w, crops_out, n_crops, range, crops_cap, out_h,
-                            out_w, batch_f32, canvas_u8, bump, st));
+                            out_w, batch_f32, canvas_u8, bump, st, page_ptrs, page_hw));
     } else {
         MS_TRY(timing_mark(ctx, 4, st));
     }
@@ -857,6 +862,23 @@ extern "C" int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img
     return MS_OK;
 }
 
+extern "C" int ms_page_batch_ragged(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *const *page_ptrs,
+                                    const int32_t *page_hw, int n_pages, int map_h, int map_w, const ms_east_params *p,
+                                    int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
+                                    int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
+                                    float *batch_f32, uint8_t *canvas_u8, int32_t *flags, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!score || !geo || !p || !page_ptrs || !page_hw || !boxes_out || !box_counts || !flags || cap_boxes <= 0) {
+        ms_set_error("ms_page_batch_ragged: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    return page_batch_impl(ctx, score, geo, nullptr, n_pages, 0, n_pages, map_h, map_w, 0, 0, p, min_text_size, out_h,
+                           out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, 0, batch_f32,
+                           canvas_u8, flags, (cudaStream_t)stream, 0, page_ptrs, page_hw);
+}
+
 extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
                                   int map_h, int map_w, int img_h, int img_w, const ms_east_params *p,
                                   int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,
@@ -1043,5 +1065,93 @@ extern "C" int ms_warp_quad_host(ms_ctx *ctx, const uint8_t *page, int img_h, in
     const size_t bytes = (size_t)(*w) * (*h) * 3;
     if (bytes) MS_CUDA(cudaMemcpyAsync(patch_out, d_patch, bytes, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
+// ---- page images of their own sizes (a batch of originals, as EAST.predict + Pipeline.predict see them) ------------------
+// Host buffers: pages[i] -> (page_hw[2i], page_hw[2i+1], 3) u8.  Maps are uploaded whole, the images one by one into a
+// packed staging buffer (256-byte aligned starts); one pass, no chunk pipelining.
+extern "C" int ms_page_batch_ragged_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *const *pages,
+                                         const int32_t *page_hw, int n_pages, int map_h, int map_w,
+                                         const ms_east_params *p, int min_text_size, int out_h, int out_w, int cap_boxes,
+                                         float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
+                                         int32_t *n_crops, float *batch_f32_host, float **batch_dev_out, int32_t *flags)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!score || !geo || !p || !pages || !page_hw || !boxes_out || !box_counts || !flags || !crops_out || !n_crops ||
+        cap_boxes <= 0 || map_h <= 0 || map_w <= 0 || crops_cap <= 0) {
+        ms_set_error("ms_page_batch_ragged_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    size_t img_total = 0;
+    for (int i = 0; i < n_pages; i++) {
+        if (!pages[i] || page_hw[2 * i] <= 0 || page_hw[2 * i + 1] <= 0) {
+            ms_set_error("ms_page_batch_ragged_host: page %d is empty", i);
+            return MS_ERR_INVALID;
+        }
+        img_total += al256((size_t)page_hw[2 * i] * page_hw[2 * i + 1] * 3);
+    }
+    const bool want_batch = batch_f32_host || batch_dev_out;
+    const size_t plane = (size_t)map_h * map_w;
+    const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float);
+    size_t need = al256(n_pages * plane * 4) + al256(n_pages * plane * 32) + al256((size_t)n_pages * cap_boxes * 36) +
+                  4 * al256((size_t)n_pages * 8) + img_total + al256((size_t)crops_cap * 20) + 8192;
+    if (want_batch) need += al256((size_t)crops_cap * one_f);
+    MS_TRY(ms_stage_reserve(ctx, need));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    float *d_score = sb.take<float>(n_pages * plane);
+    float *d_geo = sb.take<float>(n_pages * plane * 8);
+    float *d_boxes = sb.take<float>((size_t)n_pages * cap_boxes * 9);
+    int32_t *d_cnt = sb.take<int32_t>(n_pages);
+    int32_t *d_flags = sb.take<int32_t>(n_pages);
+    const uint8_t **d_ptrs = sb.take<const uint8_t *>(n_pages);
+    int32_t *d_hw = sb.take<int32_t>((size_t)n_pages * 2);
+    int32_t *d_crops = sb.take<int32_t>((size_t)crops_cap * 5);
+    int32_t *d_nc = sb.take<int32_t>(1);
+    float *d_batch = want_batch ? sb.take<float>((size_t)crops_cap * 3 * out_h * out_w) : nullptr;
+    uint8_t *d_img = sb.take<uint8_t>(img_total);
+    if (!d_img || (want_batch && !d_batch)) {
+        ms_set_error("ms_page_batch_ragged_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    std::vector<const uint8_t *> h_ptrs(n_pages);
+    size_t off = 0;
+    for (int i = 0; i < n_pages; i++) {
+        const size_t bytes = (size_t)page_hw[2 * i] * page_hw[2 * i + 1] * 3;
+        h_ptrs[i] = d_img + off;
+        MS_CUDA(cudaMemcpyAsync(d_img + off, pages[i], bytes, cudaMemcpyHostToDevice, st));
+        off += al256(bytes);
+    }
+    MS_CUDA(cudaMemcpyAsync(d_ptrs, h_ptrs.data(), (size_t)n_pages * sizeof(void *), cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_hw, page_hw, (size_t)n_pages * 8, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_score, score, n_pages * plane * 4, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_geo, geo, n_pages * plane * 32, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaStreamSynchronize(st));  // h_ptrs is pageable host memory on this frame
+    MS_TRY(page_batch_impl(ctx, d_score, d_geo, nullptr, n_pages, 0, n_pages, map_h, map_w, 0, 0, p, min_text_size, out_h,
+                           out_w, cap_boxes, d_boxes, d_cnt, d_crops, crops_cap, d_nc, 0, d_batch, nullptr, d_flags, st, 0,
+                           d_ptrs, d_hw));
+    MS_CUDA(cudaMemcpyAsync(box_counts, d_cnt, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(flags, d_flags, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(boxes_out, d_boxes, (size_t)n_pages * cap_boxes * 36, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaMemcpyAsync(n_crops, d_nc, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    int32_t all = 0;
+    for (int i = 0; i < n_pages; i++) all |= flags[i];
+    if (grow_edge_factor(ctx, all))
+        return ms_page_batch_ragged_host(ctx, score, geo, pages, page_hw, n_pages, map_h, map_w, p, min_text_size, out_h,
+                                         out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops,
+                                         batch_f32_host, batch_dev_out, flags);
+    MS_TRY(flags_to_rc(all, "page_batch_ragged"));
+    int64_t nc = *n_crops;
+    if (nc > crops_cap) nc = crops_cap;
+    if (nc > 0) {
+        MS_CUDA(cudaMemcpyAsync(crops_out, d_crops, (size_t)nc * 20, cudaMemcpyDeviceToHost, st));
+        if (batch_f32_host)
+            MS_CUDA(cudaMemcpyAsync(batch_f32_host, d_batch, (size_t)nc * one_f, cudaMemcpyDeviceToHost, st));
+        MS_CUDA(cudaStreamSynchronize(st));
+    }
+    if (batch_dev_out) *batch_dev_out = d_batch;
     return MS_OK;
 }

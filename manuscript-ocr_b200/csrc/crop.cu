@@ -38,44 +38,54 @@ constexpr int kCtasPerSm = 4;
 constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
 constexpr int kSrcBuf = 24 * 1024;  // bytes per staging buffer (two per CTA)
 
+// Pages are either one (n_pages, img_h, img_w, 3) tensor, or -- page_ptrs != NULL -- separate images of their own
+// sizes: page_ptrs[p] -> (page_hw[2p], page_hw[2p+1], 3) bytes.
 __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int img_h, int img_w, int ih, int iw,
-                                          const uint8_t *pages, size_t total_bytes, Plan &p)
+                                          const uint8_t *pages, const uint8_t *const *page_ptrs,
+                                          const int32_t *page_hw, Plan &p)
 {
     p.page = cr[0];
     p.x1 = cr[1];
     p.y1 = cr[2];
     p.w = cr[3] - cr[1];
     p.h = cr[4] - cr[2];
-    p.ok = p.page >= 0 && p.page < n_pages && p.w > 0 && p.h > 0 && p.x1 >= 0 && p.y1 >= 0 && cr[3] <= img_w &&
-           cr[4] <= img_h;
     p.staged = 0;
     p.fast = 0;
     p.pitch = 0;
+    p.stride = 0;
+    p.src = nullptr;
     p.nw = p.nh = p.y0 = p.interp = p.isx = p.isy = 0;
     p.scale_x = p.scale_y = 1.0;
+    p.ok = p.page >= 0 && p.page < n_pages;
+    if (!p.ok) return;
+    const int H = page_ptrs ? page_hw[2 * p.page] : img_h, W = page_ptrs ? page_hw[2 * p.page + 1] : img_w;
+    const uint8_t *page0 = page_ptrs ? page_ptrs[p.page] : pages + (size_t)p.page * img_h * (size_t)img_w * 3;
+    p.ok = page0 != nullptr && H > 0 && W > 0 && p.w > 0 && p.h > 0 && p.x1 >= 0 && p.y1 >= 0 && cr[3] <= W && cr[4] <= H;
     if (!p.ok) return;
     const int w = p.w, h = p.h;
     plan_resize(w, h, ih, iw, p);
     // staging: every row is copied as the 16-byte-aligned span that covers it; the pitch is exactly that span (the
     // 4-tap reads may run up to 16 bytes past a row -- into the next row, or into the slack kept after the last one).
     // When the page stride is a multiple of 16 every row has the same misalignment, otherwise assume the worst (15).
-    const size_t stride = (size_t)img_w * 3;
-    const size_t first = (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
-    const size_t last_end = first + (size_t)(h - 1) * stride + (size_t)w * 3;
-    const uintptr_t base = reinterpret_cast<uintptr_t>(pages);
-    const int mis = (stride & 15) == 0 ? (int)((base + first) & 15) : 15;
+    const size_t stride = (size_t)W * 3;
+    p.stride = (int)stride;
+    p.src = page0 + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+    const uintptr_t first = reinterpret_cast<uintptr_t>(p.src);
+    const uintptr_t last_end = first + (size_t)(h - 1) * stride + (size_t)w * 3;
+    // the copies may not leave the memory that holds the pages: the whole tensor, or this page's own image
+    const uintptr_t lo = reinterpret_cast<uintptr_t>(page_ptrs ? page0 : pages);
+    const uintptr_t hi = page_ptrs ? lo + (size_t)H * stride : lo + (size_t)n_pages * img_h * (size_t)img_w * 3;
+    const int mis = (stride & 15) == 0 ? (int)(first & 15) : 15;
     const int pitch = (mis + w * 3 + 15) & ~15;
     const bool fits = (size_t)pitch * h + 16 <= (size_t)kSrcBuf;
-    // the last row's aligned span must not run past the end of the page tensor
-    const bool tail_ok = ((base + last_end + 15) & ~(uintptr_t)15) <= base + total_bytes;
-    if (fits && tail_ok && (base & 15) == 0) {
+    const bool tail_ok = ((last_end + 15) & ~(uintptr_t)15) <= hi;
+    if (fits && tail_ok && (lo & 15) == 0) {
         p.staged = 1;
         p.pitch = pitch;
     }
     // a decimation window shorter than 3 source pixels touches at most 4 of them: every table entry has <= 4 taps
     p.fast = p.staged && p.interp == 3 && p.scale_x < 2.999 && p.scale_y < 2.999 && p.w < 65536 && p.h < 65536;
 }
-
 
 // ---- mbarrier + TMA bulk copy (sm_90+ PTX; SASS: SYNCS / UBLKCP) ----------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -113,7 +123,9 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 
 // plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
 // critical path of the persistent resampling kernel
-__global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restrict__ pages, int n_pages, int img_h,
+__global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restrict__ pages,
+                                                        const uint8_t *const *__restrict__ page_ptrs,
+                                                        const int32_t *__restrict__ page_hw, int n_pages, int img_h,
                                                         int img_w, const int32_t *__restrict__ crops,
                                                         const int32_t *__restrict__ n_crops_dev,
                                                         const int32_t *__restrict__ range, int64_t crops_cap, int ih,
@@ -122,11 +134,10 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
     int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
-    const size_t total_bytes = (size_t)n_pages * img_h * (size_t)img_w * 3;
     for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_crops;
          i += (int64_t)gridDim.x * blockDim.x) {
         Plan p;
-        make_plan(crops + i * 5, n_pages, img_h, img_w, ih, iw, pages, total_bytes, p);
+        make_plan(crops + i * 5, n_pages, img_h, img_w, ih, iw, pages, page_ptrs, page_hw, p);
         plans[i] = p;
     }
 }
@@ -149,8 +160,7 @@ constexpr int kProducerChannels = 2;  // output channels whose padding the produ
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-    crop_resize_pad_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w, const Plan *__restrict__ plans,
-                           const int32_t *__restrict__ n_crops_dev, const int32_t *__restrict__ range,
+    crop_resize_pad_kernel(const Plan *__restrict__ plans, const int32_t *__restrict__ n_crops_dev, const int32_t *__restrict__ range,
                            int64_t crops_cap, int ih, int iw, float *__restrict__ batch,
                            uint8_t *__restrict__ canvas_out, int vec_ok, uint8_t *__restrict__ redo)
 {
@@ -162,10 +172,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
-    const size_t stride = (size_t)img_w * 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int plane = ih * iw;
-    const uint32_t sstep = (uint32_t)(stride & 15);  // per-row change of the 16-byte misalignment
 
     if (threadIdx.x == 0) {
         mbar_init(&s_full[0], 1);
@@ -190,7 +198,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             // TMA first: its latency overlaps the float64 table arithmetic below
             uint32_t bytes = 0;
             {
-                const uint8_t *src = pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3;
+                const uint8_t *src = p.src;
+                const size_t stride = (size_t)p.stride;
                 unsigned char *buf = smem + b * kSrcBuf;
                 for (int r = lane; r < p.h; r += 32) {
                     const uint8_t *g = src + (size_t)r * stride;
@@ -220,9 +229,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         const int b = k & 1;
         const int nw = pg->nw, nh = pg->nh, y0 = pg->y0;
         const uint32_t pitch = (uint32_t)pg->pitch;
-        const uint32_t a0 = (uint32_t)((reinterpret_cast<uintptr_t>(pages) + (size_t)pg->page * img_h * stride +
-                                        (size_t)pg->y1 * stride + (size_t)pg->x1 * 3) &
-                                       15);
+        const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(pg->src) & 15);
+        const uint32_t sstep = (uint32_t)pg->stride & 15u;  // per-row change of the 16-byte misalignment
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
         const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
@@ -259,15 +267,13 @@ __global__ void __launch_bounds__(256) crop_generic_list_kernel(const Plan *__re
 constexpr int kGenericMaxTab = 1024;  // table entries kept in shared memory (longer axes recompute per pixel)
 
 template <bool kWriteF32, bool kWriteU8>
-__global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__restrict__ pages, int img_h, int img_w,
-                                                           const Plan *__restrict__ plans,
+__global__ void __launch_bounds__(256) crop_generic_kernel(const Plan *__restrict__ plans,
                                                            const int32_t *__restrict__ list,
                                                            const int32_t *__restrict__ list_n, int ih, int iw,
                                                            float *__restrict__ batch,
                                                            uint8_t *__restrict__ canvas_out, int vec_ok)
 {
     __shared__ AxisEnt s_tab[kGenericMaxTab];
-    const size_t stride = (size_t)img_w * 3;
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
     const int todo = *list_n;
@@ -290,7 +296,7 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const uint8_t *__rest
             }
         }
         __syncthreads();
-        const PitchedSrc gsrc{pages + (size_t)p.page * img_h * stride + (size_t)p.y1 * stride + (size_t)p.x1 * 3, stride};
+        const PitchedSrc gsrc{p.src, (size_t)p.stride};
         const int npx = nw * nh;
         for (int t = threadIdx.x; t < npx; t += blockDim.x) {
             const int dy = t / nw, dx = t - dy * nw;
@@ -329,10 +335,11 @@ size_t msk_crop_scratch(int64_t crops_cap)
 
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
-             uint8_t *canvas_u8, ms_bump bump, cudaStream_t st)
+             uint8_t *canvas_u8, ms_bump bump, cudaStream_t st, const uint8_t *const *page_ptrs, const int32_t *page_hw)
 {
     if (crops_cap <= 0 || n_pages <= 0) return MS_OK;
-    if (out_h <= 0 || out_w <= 0 || img_h <= 0 || img_w <= 0 || (!batch_f32 && !canvas_u8)) {
+    const bool ragged = page_ptrs != nullptr && page_hw != nullptr;
+    if (out_h <= 0 || out_w <= 0 || (!ragged && (img_h <= 0 || img_w <= 0 || !pages)) || (!batch_f32 && !canvas_u8)) {
         ms_set_error("crop: bad arguments");
         return MS_ERR_INVALID;
     }
@@ -358,7 +365,8 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     {
         int64_t g = (crops_cap + 255) / 256;
         if (g > (int64_t)ctx->num_sms * 8) g = (int64_t)ctx->num_sms * 8;
-        crop_plan_kernel<<<(int)g, 256, 0, st>>>(pages, n_pages, img_h, img_w, crops, n_crops, range, crops_cap, out_h,
+        crop_plan_kernel<<<(int)g, 256, 0, st>>>(pages, ragged ? page_ptrs : nullptr, page_hw, n_pages, img_h, img_w,
+                                                 crops, n_crops, range, crops_cap, out_h,
                                                  out_w, plans);
         MS_LAUNCH_CHECK(ctx);
     }
@@ -382,12 +390,12 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
             MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
             granted = (int)smem;                                                                                       \
         }                                                                                                              \
-        kfn<<<(int)grid, kThreads, smem, st>>>(pages, img_h, img_w, plans, n_crops, range, crops_cap, out_h, out_w,    \
+        kfn<<<(int)grid, kThreads, smem, st>>>(plans, n_crops, range, crops_cap, out_h, out_w,                        \
                                               batch_f32, canvas_u8, vec_ok, redo);                                     \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
         crop_generic_list_kernel<<<(int)lgrid, 256, 0, st>>>(plans, n_crops, range, crops_cap, redo, glist, glist_n);  \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
-        crop_generic_kernel<F32, U8><<<(int)ggrid, 256, 0, st>>>(pages, img_h, img_w, plans, glist, glist_n, out_h,    \
+        crop_generic_kernel<F32, U8><<<(int)ggrid, 256, 0, st>>>(plans, glist, glist_n, out_h,                        \
                                                                  out_w, batch_f32, canvas_u8, vec_ok);                \
     } while (0)
     if (batch_f32 && canvas_u8)

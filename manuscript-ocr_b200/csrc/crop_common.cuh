@@ -14,6 +14,8 @@ struct Plan {
     int staged;  // source rows can be staged through TMA into shared memory
     int fast;    // handled by the persistent TMA kernel (INTER_AREA, shrink factors < 3, staged); else generic kernel
     int pitch;   // shared-memory row pitch (bytes) when staged
+    int stride;  // bytes between source rows (3 * width of the crop's page)
+    const uint8_t *src;  // first source byte of the crop (row y1, column x1 of its page)
     double scale_x, scale_y;
 };
 

@@ -113,7 +113,8 @@ size_t msk_reading_order_scratch(int n_pages, int cap_per_page);
 // crop.cu
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
-             uint8_t *canvas_u8, ms_bump bump, cudaStream_t st);
+             uint8_t *canvas_u8, ms_bump bump, cudaStream_t st, const uint8_t *const *page_ptrs = nullptr,
+             const int32_t *page_hw = nullptr);  // page_ptrs / page_hw (device): pages of their own sizes
 size_t msk_crop_scratch(int64_t crops_cap);
 // quadcrop.cu
 int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const float *quads,

@@ -117,7 +117,8 @@ __global__ void __launch_bounds__(128) quad_plan_kernel(const float *__restrict_
         QuadPlan qp;
         Plan p;
         p.page = p.x1 = p.y1 = p.w = p.h = p.nw = p.nh = p.y0 = p.interp = p.isx = p.isy = 0;
-        p.ok = p.staged = p.fast = p.pitch = 0;
+        p.ok = p.staged = p.fast = p.pitch = p.stride = 0;
+        p.src = nullptr;
         p.scale_x = p.scale_y = 1.0;
         qp.page = page_of ? page_of[i] : 0;
         qp.ok = qp.pad0 = qp.pad1 = qp.pad2 = 0;

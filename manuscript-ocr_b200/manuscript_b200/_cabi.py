@@ -97,6 +97,10 @@ SIGNATURES = {
     "ms_crop_resize_pad": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _i64, _i, _i, _vp, _vp, _vp]),
     "ms_page_batch": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(EastParams), _i, _i, _i, _i, _vp, _vp,
                            _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "ms_page_batch_ragged": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(EastParams), _i, _i, _i, _i, _vp, _vp,
+                                  _vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "ms_page_batch_ragged_host": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, C.POINTER(EastParams), _i, _i, _i, _i, _vp,
+                                       _vp, _vp, _i64, _vp, _vp, C.POINTER(_vp), _vp]),
     "ms_page_batch_host": (_i, [_vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, C.POINTER(EastParams), _i, _i, _i, _i, _vp,
                                 _vp, _vp, _i64, _vp, _vp, C.POINTER(_vp), _vp]),
 }

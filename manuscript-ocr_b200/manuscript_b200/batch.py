@@ -128,6 +128,67 @@ class PageBatch:
                 b["flags"].data_ptr(), C.c_void_p(stream)))
         return PageBatchResult(b["boxes"], b["counts"], b["crops"], b["n_crops"], b["batch"], b["flags"])
 
+    def run_ragged(self, score, geo, pages):
+        """As run(), for page images of their own sizes: `pages` is a list of P CUDA uint8 tensors (H_i, W_i, 3) -- the
+        original images, while the maps come from the detector's fixed target_size.  Boxes are scaled to each page's
+        size and crops are cut from its pixels (EAST.predict + Pipeline.predict semantics)."""
+        torch = self.torch
+        if score.dim() == 4:
+            score = score[:, 0]
+        P, H, W = score.shape
+        assert geo.shape == (P, 8, H, W) and len(pages) == P
+        assert score.is_cuda and geo.is_cuda and score.dtype == torch.float32 and geo.dtype == torch.float32
+        score, geo = score.contiguous(), geo.contiguous()
+        keep = []
+        for pg in pages:
+            assert pg.is_cuda and pg.dtype == torch.uint8 and pg.dim() == 3 and pg.shape[2] == 3
+            keep.append(pg.contiguous())
+        ptrs = torch.tensor([pg.data_ptr() for pg in keep], dtype=torch.int64).to(self.device)
+        hw = torch.tensor([[pg.shape[0], pg.shape[1]] for pg in keep], dtype=torch.int32).to(self.device)
+        b = self._device_bufs(P)
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            check(self.ctx.lib.ms_page_batch_ragged(
+                self.ctx.handle, score.data_ptr(), geo.data_ptr(), ptrs.data_ptr(), hw.data_ptr(), P, H, W,
+                C.byref(self.params), self.min_text_size, self.out_h, self.out_w, self.cap_boxes, b["boxes"].data_ptr(),
+                b["counts"].data_ptr(), b["crops"].data_ptr(), b["cap"], b["n_crops"].data_ptr(),
+                b["batch"].data_ptr() if b["batch"] is not None else None, None, b["flags"].data_ptr(),
+                C.c_void_p(stream)))
+        res = PageBatchResult(b["boxes"], b["counts"], b["crops"], b["n_crops"], b["batch"], b["flags"])
+        res._keepalive = (keep, ptrs, hw)  # the kernels read them after this call returns
+        return res
+
+    def run_host_ragged(self, score, geo, pages, check_flags=True):
+        """As run_host(), `pages` a list of P numpy uint8 arrays (H_i, W_i, 3) of their own sizes."""
+        torch = self.torch
+        s = np.ascontiguousarray(score, dtype=np.float32)
+        if s.ndim == 4:
+            s = np.ascontiguousarray(s[:, 0])
+        g = np.ascontiguousarray(geo, dtype=np.float32)
+        P, H, W = s.shape
+        assert g.shape == (P, 8, H, W) and len(pages) == P
+        imgs = [np.ascontiguousarray(pg, dtype=np.uint8) for pg in pages]
+        for im in imgs:
+            assert im.ndim == 3 and im.shape[2] == 3
+        ptrs = (C.c_void_p * P)(*[im.ctypes.data for im in imgs])
+        hw = np.array([[im.shape[0], im.shape[1]] for im in imgs], np.int32)
+        h = self._host_bufs(P)
+        dev_batch = C.c_void_p()
+        rc = self.ctx.lib.ms_page_batch_ragged_host(
+            self.ctx.handle, s.ctypes.data, g.ctypes.data, ptrs, hw.ctypes.data, P, H, W, C.byref(self.params),
+            self.min_text_size, self.out_h, self.out_w, self.cap_boxes, h["boxes"].data_ptr(), h["counts"].data_ptr(),
+            h["crops"].data_ptr(), h["cap"], h["n_crops"].data_ptr(), None,
+            C.byref(dev_batch) if self.want_batch else None, h["flags"].data_ptr())
+        if check_flags or rc not in (0, -3, -4):
+            check(rc)
+        batch = None
+        n_crops = int(h["n_crops"][0])
+        if self.want_batch and dev_batch.value and n_crops > 0:
+            batch = torch.as_tensor(_DeviceArray(dev_batch.value, (n_crops, 3, self.out_h, self.out_w)),
+                                    device=self.device)
+        return PageBatchResult(h["boxes"].numpy(), h["counts"].numpy(), h["crops"].numpy(), h["n_crops"].numpy(),
+                               batch, h["flags"].numpy())
+
     # ---- host buffers in, host results out (the crop batch stays on the device, as the reference leaves ------------
     # ---- it on `self.device`, recognizers/_trba/__init__.py:288) ---------------------------------------------------
     def _host_bufs(self, n_pages):

@@ -254,3 +254,43 @@ def test_boxes_only_and_capacity_flags(torch_cuda):
     with pytest.raises(IndexError):
         mb.PageBatch(device=0, params=mb.EastParams.default(target_size=32), cap_boxes=8, want_batch=False).run_host(
             bad_score, np.zeros((1, 8, 7, 8), np.float32), None)
+
+
+def test_page_batch_ragged_originals(torch_cuda):
+    """A batch of original images of different sizes (one narrower than 16 pixels' alignment, one with an odd width so
+    that its rows start at every misalignment) with maps of one 512-target detector: per page, boxes scaled to that
+    page's size, crops cut from its pixels -- through the device entry (list of CUDA tensors) and the host entry."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    target = 512
+    sizes = [(700, 900), (512, 512), (333, 1001), (1200, 640)]
+    seeds = [21, 22, 23, 24]
+    score, geo, _ = synthdata.make_batch(seeds, target, 70)
+    rng = np.random.default_rng(4)
+    imgs = [rng.integers(0, 256, (h, w, 3), dtype=np.uint8) for h, w in sizes]
+    runner = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=target), cap_boxes=1024)
+    res_d = runner.run_ragged(torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(),
+                              [torch.from_numpy(im).cuda() for im in imgs])
+    torch.cuda.synchronize()
+    res_h = runner.run_host_ragged(score, geo, imgs)
+    n = int(res_h.n_crops[0])
+    assert int(res_d.n_crops.cpu()[0]) == n
+    np.testing.assert_array_equal(res_d.crops[:n].cpu().numpy(), res_h.crops[:n])
+    np.testing.assert_array_equal(res_d.batch[:n].cpu().numpy(), res_h.batch.cpu().numpy())
+    batch = res_h.batch.cpu().numpy()
+    k = 0
+    for p, (oh, ow) in enumerate(sizes):
+        nms = cpu.locality_aware_nms(cpu.decode_quads_from_maps(score[p], geo[p], 0.6, 4.0, 2), 0.2)
+        want = cpu.east_postprocess(nms, (oh, ow), target_size=target)
+        rects, valid = cpu.word_rects(want, oh, ow, 5)
+        rects = rects[valid]
+        np.testing.assert_array_equal(res_h.page_boxes(p), want)
+        np.testing.assert_array_equal(res_d.boxes[p, : len(want)].cpu().numpy(), want)
+        rows = res_h.crops[k:k + len(rects)]
+        assert (rows[:, 0] == p).all()
+        np.testing.assert_array_equal(rows[:, 1:], rects)
+        for j in range(0, len(rects), 3):
+            np.testing.assert_array_equal(batch[k + j], cpu.crop_resize_pad(imgs[p], rects[j], 32, 128)[1])
+        k += len(rects)
+    assert k == n and n > 150

@@ -411,6 +411,20 @@ def run_b200(a):
                                          "note": "ms_quad_crop_resize_pad: cv2.warpPerspective-exact rectified crops "
                                                  "(extension, not a reference behaviour)"}
         del qbatch, quads
+        # one 1280x1280 page (BASELINE configs[1]): ~50 short launches, so the call is launch-bound; a repeated call is
+        # replayed as a CUDA graph (second occurrence on), MS_B200_NO_GRAPHS=1 keeps direct launches
+        s1, g1, i1 = synthdata.make_batch([7], 1280, 500)
+        d1 = [torch.from_numpy(x).to(dev) for x in (s1, g1, i1)]
+        one = mb.PageBatch(device=local, params=mb.EastParams.default(target_size=1280), cap_boxes=2048,
+                           out_hw=(OUT_H, OUT_W))
+        ms_graph = timed(lambda: one.run(*d1), reps=20)
+        os.environ["MS_B200_NO_GRAPHS"] = "1"  # read when a context is created
+        one_d = mb.PageBatch(device=local, params=mb.EastParams.default(target_size=1280), cap_boxes=2048,
+                             out_hw=(OUT_H, OUT_W))
+        del os.environ["MS_B200_NO_GRAPHS"]
+        ms_direct = timed(lambda: one_d.run(*d1), reps=20)
+        variants["single_page_1280"] = {"ms_graph_replay": ms_graph, "ms_direct_launches": ms_direct,
+                                        "note": "device-resident, one page per call, 500 words"}
 
     total_boxes = sum_over_ranks(float(n_boxes))
     if rank != 0:

@@ -96,6 +96,7 @@ extern "C" int ms_create(int device, ms_ctx **out)
     c->device = device;
     c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : MS_NUM_SMS_B200;
     c->edge_factor = 16;
+    c->graphs_enabled = getenv("MS_B200_NO_GRAPHS") ? 0 : 1;
     int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (int i = 0; i < 2 && rc == MS_OK; i++)
@@ -130,6 +131,8 @@ extern "C" void ms_destroy(ms_ctx *ctx)
         for (int i = 0; i < MS_TIMING_RING * (MS_N_STAGES + 1); i++) cudaEventDestroy(ctx->timing_ev[i]);
         free(ctx->timing_ev);
     }
+    for (int i = 0; i < MS_GRAPH_SLOTS; i++)
+        if (ctx->graphs[i].exec) cudaGraphExecDestroy(ctx->graphs[i].exec);
     if (ctx->arena) cudaFree(ctx->arena);
     if (ctx->stage) cudaFree(ctx->stage);
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
@@ -503,6 +506,79 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
     return MS_OK;
 }
 
+// ms_page_batch / ms_page_batch_ragged: direct launches the first time a call is seen, graph capture (on the
+// context's own stream, nothing executes) at its second occurrence, replay on the caller's stream from then on.
+// Stage timing needs the events between the stages, so it always launches directly.
+static int page_batch_cached(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages,
+                             const uint8_t *const *page_ptrs, const int32_t *page_hw, int n_pages, int map_h, int map_w,
+                             int img_h, int img_w, const ms_east_params *p, int min_text_size, int out_h, int out_w,
+                             int cap_boxes, float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
+                             int32_t *n_crops, float *batch_f32, uint8_t *canvas_u8, int32_t *flags, cudaStream_t st)
+{
+    auto direct = [&](cudaStream_t s) {
+        return page_batch_impl(ctx, score, geo, pages, n_pages, 0, n_pages, map_h, map_w, img_h, img_w, p, min_text_size,
+                               out_h, out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, 0, batch_f32,
+                               canvas_u8, flags, s, 0, page_ptrs, page_hw);
+    };
+    if (!ctx->graphs_enabled || ctx->timing) return direct(st);
+    ms_pb_key key;
+    memset(&key, 0, sizeof(key));
+    const void *ptrs[14] = {score, geo, pages, page_ptrs, page_hw, boxes_out, box_counts, crops_out, n_crops, batch_f32,
+                            canvas_u8, flags, ctx->arena, nullptr};
+    memcpy(key.ptr, ptrs, sizeof(ptrs));
+    const long long nums[12] = {n_pages, map_h, map_w, img_h, img_w, min_text_size, out_h, out_w, cap_boxes,
+                                (long long)crops_cap, ctx->edge_factor, (long long)ctx->arena_bytes};
+    memcpy(key.num, nums, sizeof(nums));
+    memcpy(&key.params, p, sizeof(ms_east_params));
+    ms_graph_entry *e = nullptr;
+    for (int i = 0; i < MS_GRAPH_SLOTS; i++)
+        if (ctx->graphs[i].used && memcmp(&ctx->graphs[i].key, &key, sizeof(key)) == 0) e = &ctx->graphs[i];
+    if (e && e->exec) {
+        e->used = ++ctx->graph_clock;
+        MS_CUDA(cudaGraphLaunch(e->exec, st));
+        ctx->launches += e->launches;
+        return MS_OK;
+    }
+    if (e && !e->failed) {  // second occurrence: the arenas and kernel attributes were settled by the first
+        e->used = ++ctx->graph_clock;
+        const int64_t l0 = ctx->launches;
+        cudaStream_t cap = ctx->own_stream;
+        if (cudaStreamBeginCapture(cap, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = direct(cap);
+            cudaGraph_t g = nullptr;
+            const cudaError_t ce = cudaStreamEndCapture(cap, &g);
+            const bool same_arena = ctx->arena == (char *)key.ptr[12] && (long long)ctx->arena_bytes == key.num[11];
+            if (rc == MS_OK && ce == cudaSuccess && g && same_arena &&
+                cudaGraphInstantiate(&e->exec, g, 0) == cudaSuccess) {
+                e->launches = ctx->launches - l0;
+                ctx->launches = l0;
+                cudaGraphDestroy(g);
+                MS_CUDA(cudaGraphLaunch(e->exec, st));
+                ctx->launches += e->launches;
+                return MS_OK;
+            }
+            if (g) cudaGraphDestroy(g);
+            e->exec = nullptr;
+        }
+        cudaGetLastError();  // a failed capture is not an error of the call: launch directly from now on
+        ctx->launches = l0;
+        e->failed = 1;
+        return direct(st);
+    }
+    if (!e) {  // first occurrence: remember it (least recently used slot)
+        int slot = 0;
+        for (int i = 1; i < MS_GRAPH_SLOTS; i++)
+            if (ctx->graphs[i].used < ctx->graphs[slot].used) slot = i;
+        if (ctx->graphs[slot].exec) cudaGraphExecDestroy(ctx->graphs[slot].exec);
+        memset(&ctx->graphs[slot], 0, sizeof(ms_graph_entry));
+        ctx->graphs[slot].key = key;
+        ctx->graphs[slot].used = ++ctx->graph_clock;
+    }
+    const int rc = direct(st);
+    // the first run may have grown the arena: the remembered key then never matches again and is simply evicted
+    return rc;
+}
+
 extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,
                              int map_h, int map_w, int img_h, int img_w, const ms_east_params *p, int min_text_size,
                              int out_h, int out_w, int cap_boxes, float *boxes_out, int32_t *box_counts,
@@ -515,9 +591,9 @@ extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, 
         ms_set_error("ms_page_batch: bad arguments");
         return MS_ERR_INVALID;
     }
-    return page_batch_impl(ctx, score, geo, pages, n_pages, 0, n_pages, map_h, map_w, img_h, img_w, p, min_text_size,
-                           out_h, out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, 0, batch_f32,
-                           canvas_u8, flags, (cudaStream_t)stream);
+    return page_batch_cached(ctx, score, geo, pages, nullptr, nullptr, n_pages, map_h, map_w, img_h, img_w, p,
+                             min_text_size, out_h, out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops,
+                             batch_f32, canvas_u8, flags, (cudaStream_t)stream);
 }
 
 // =========================================================================================================
@@ -874,9 +950,9 @@ extern "C" int ms_page_batch_ragged(ms_ctx *ctx, const float *score, const float
         ms_set_error("ms_page_batch_ragged: bad arguments");
         return MS_ERR_INVALID;
     }
-    return page_batch_impl(ctx, score, geo, nullptr, n_pages, 0, n_pages, map_h, map_w, 0, 0, p, min_text_size, out_h,
-                           out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, 0, batch_f32,
-                           canvas_u8, flags, (cudaStream_t)stream, 0, page_ptrs, page_hw);
+    return page_batch_cached(ctx, score, geo, nullptr, page_ptrs, page_hw, n_pages, map_h, map_w, 0, 0, p, min_text_size,
+                             out_h, out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, batch_f32,
+                             canvas_u8, flags, (cudaStream_t)stream);
 }
 
 extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages, int n_pages,

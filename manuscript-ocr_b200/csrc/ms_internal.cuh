@@ -10,6 +10,22 @@
 
 #define MS_NUM_SMS_B200 148
 
+// One recorded ms_page_batch call (all arguments) and, from its second occurrence on, the CUDA graph of its launches.
+struct ms_pb_key {
+    const void *ptr[14];
+    long long num[12];
+    ms_east_params params;
+};
+struct ms_graph_entry {
+    ms_pb_key key;
+    int used, failed;
+    cudaGraphExec_t exec;
+    int64_t launches;  // kernels per replay (for ms_launch_count)
+    char *arena;       // the scratch arena the graph's kernels point into
+    size_t arena_bytes;
+};
+#define MS_GRAPH_SLOTS 4
+
 struct ms_ctx {
     int device;
     int num_sms;
@@ -31,6 +47,11 @@ struct ms_ctx {
     int timing;
     int timing_n;                 // batches recorded since the last read (<= MS_TIMING_RING)
     cudaEvent_t *timing_ev;       // MS_TIMING_RING * (MS_N_STAGES + 1) events, created lazily
+    // A batch is ~50 short launches: a repeated ms_page_batch call (same buffers, sizes and parameters -- a serving
+    // loop) is captured into a CUDA graph at its second occurrence and replayed afterwards.
+    int graphs_enabled;           // 0 with MS_B200_NO_GRAPHS=1 in the environment
+    int graph_clock;
+    ms_graph_entry graphs[MS_GRAPH_SLOTS];
 };
 #define MS_TIMING_RING 256
 

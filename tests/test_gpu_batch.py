@@ -294,3 +294,46 @@ def test_page_batch_ragged_originals(torch_cuda):
             np.testing.assert_array_equal(batch[k + j], cpu.crop_resize_pad(imgs[p], rects[j], 32, 128)[1])
         k += len(rects)
     assert k == n and n > 150
+
+
+def test_repeated_batches_replay_a_cuda_graph(torch_cuda):
+    """A repeated ms_page_batch call (same buffers and sizes) is captured into a CUDA graph at its second occurrence
+    and replayed afterwards: same results, same launch accounting, and new data in the same buffers is honoured."""
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    page = 512
+    score, geo, imgs = synthdata.make_batch([61, 62], page, 60)
+    score2, geo2, imgs2 = synthdata.make_batch([63, 64], page, 45)
+    runner = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page), cap_boxes=512)
+    s, g, im = torch.from_numpy(score).cuda(), torch.from_numpy(geo).cuda(), torch.from_numpy(imgs).cuda()
+
+    def snapshot():
+        r = runner.run(s, g, im)
+        torch.cuda.synchronize()
+        n = int(r.n_crops.cpu()[0])
+        return (r.box_counts.cpu().numpy().copy(), r.boxes.cpu().numpy().copy(), r.crops[:n].cpu().numpy().copy(),
+                r.batch[:n].cpu().numpy().copy())
+
+    l0 = runner.ctx.launches
+    first = snapshot()       # direct launches
+    per_call = runner.ctx.launches - l0
+    second = snapshot()      # captured + replayed
+    third = snapshot()       # replayed
+    assert runner.ctx.launches - l0 == 3 * per_call and per_call > 20
+    for a, b, c in zip(first, second, third):
+        np.testing.assert_array_equal(a, b)
+        np.testing.assert_array_equal(a, c)
+    # new pages written into the same device buffers
+    s.copy_(torch.from_numpy(score2)), g.copy_(torch.from_numpy(geo2)), im.copy_(torch.from_numpy(imgs2))
+    fourth = snapshot()
+    fresh = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page), cap_boxes=512)
+    r = fresh.run(s.clone(), g.clone(), im.clone())
+    torch.cuda.synchronize()
+    n = int(r.n_crops.cpu()[0])
+    np.testing.assert_array_equal(fourth[0], r.box_counts.cpu().numpy())
+    np.testing.assert_array_equal(fourth[2], r.crops[:n].cpu().numpy())
+    np.testing.assert_array_equal(fourth[3], r.batch[:n].cpu().numpy())
+    assert not np.array_equal(first[0], fourth[0])
+    _, _, want_boxes, _ = oracle_page(score2[1], geo2[1], imgs2[1], page)
+    np.testing.assert_array_equal(fourth[1][1, : fourth[0][1]], want_boxes)

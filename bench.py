@@ -343,13 +343,20 @@ def run_b200(a):
         barrier()
         nch = int(rh.n_crops[0])
         assert nch == n_crops and int(rh.box_counts.sum()) == n_boxes
-        # with quantisation 2 only the geometry rows the decode can read (odd rows) are uploaded (strided DMA)
-        geo_rows = M // 2 if (params.quantization == 2 and M % 2 == 0) else M
-        h2d = h_score.numel() * 4 + P * 8 * geo_rows * M * 4 + h_pages.numel()
+        # Geometry: the pinned host tensor is not uploaded -- the decode kernel gathers the candidate cells straight from
+        # it over PCIe (zero copy).  Counted as one 32-byte sector per candidate and plane, an upper bound (neighbouring
+        # candidates share sectors).  MS_B200_NO_ZEROCOPY=1 uploads the rows a quantised decode can read instead.
+        if os.environ.get("MS_B200_NO_ZEROCOPY"):
+            geo_rows = M // 2 if (params.quantization == 2 and M % 2 == 0) else M
+            geo_bytes, geo_how = P * 8 * geo_rows * M * 4, "geometry rows uploaded (strided DMA)"
+        else:
+            geo_bytes, geo_how = n_cand * 8 * 32, "geometry gathered from pinned host memory by the decode kernel (zero copy)"
+        h2d = h_score.numel() * 4 + geo_bytes + h_pages.numel()
         d2h = P * cap_boxes * 36 + P * 8 + 4 + nch * 20
         e2e = {"value": world * P * a.steps / t_e2e, "unit": "pages/s", "h2d_bytes_per_step": int(h2d),
                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * t_e2e / a.steps,
-               "note": "ms_page_batch_host with pinned host buffers; crop batch left on the device for the recogniser"}
+               "note": "ms_page_batch_host with pinned host buffers; " + geo_how +
+                       "; crop batch left on the device for the recogniser"}
     t_wall2 = time.perf_counter()
     if rank == 0:
         sampler.stop()

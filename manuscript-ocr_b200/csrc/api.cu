@@ -972,14 +972,25 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     const size_t plane = (size_t)map_h * map_w;
     const size_t page_bytes = (size_t)img_h * img_w * 3;
     const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float);
-    size_t need = al256(n_pages * plane * 4) + al256(n_pages * plane * 32) + al256((size_t)n_pages * cap_boxes * 36) +
-                  2 * al256((size_t)n_pages * 4) + 4096;
+    // The decode reads the geometry only at the candidate cells (a few per cent of the tensor).  When the caller's
+    // geometry lives in pinned host memory the kernel gathers it straight from there over PCIe (zero copy) instead
+    // of uploading the tensor; pageable buffers are uploaded.
+    const float *geo_mapped = nullptr;
+    if (!getenv("MS_B200_NO_ZEROCOPY")) {
+        cudaPointerAttributes at;
+        if (cudaPointerGetAttributes(&at, geo) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
+            geo_mapped = static_cast<const float *>(at.devicePointer);
+        else
+            cudaGetLastError();
+    }
+    size_t need = al256(n_pages * plane * 4) + (geo_mapped ? 256 : al256(n_pages * plane * 32)) +
+                  al256((size_t)n_pages * cap_boxes * 36) + 2 * al256((size_t)n_pages * 4) + 4096;
     if (want_crops) need += al256(n_pages * page_bytes) + al256((size_t)crops_cap * 20) + 256;
     if (want_batch) need += al256((size_t)crops_cap * one_f);
     MS_TRY(ms_stage_reserve(ctx, need));
     ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
     float *d_score = sb.take<float>(n_pages * plane);
-    float *d_geo = sb.take<float>(n_pages * plane * 8);
+    float *d_geo = geo_mapped ? nullptr : sb.take<float>(n_pages * plane * 8);
     float *d_boxes = sb.take<float>((size_t)n_pages * cap_boxes * 9);
     int32_t *d_cnt = sb.take<int32_t>(n_pages);
     int32_t *d_flags = sb.take<int32_t>(n_pages);
@@ -998,7 +1009,7 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     // With quantisation q > 1 the decode reads geometry only at rows y % q == q / 2 (utils.py:347-376), so only those
     // rows cross PCIe: one strided 2-D DMA per chunk into a compact (P, 8, H / q, W) tensor.
     const int q = p->quantization < 1 ? 1 : p->quantization;
-    const int geo_compact = (q > 1 && map_h % q == 0) ? 1 : 0;
+    const int geo_compact = (!geo_mapped && q > 1 && map_h % q == 0) ? 1 : 0;
     const size_t gplane = geo_compact ? (size_t)(map_h / q) * map_w : plane;
     int chunk = (n_pages + 7) / 8;
     if (chunk < 1) chunk = 1;
@@ -1011,7 +1022,9 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
         // the event of chunk k-2 was consumed by the compute stream before chunk k-1 was queued; reuse is safe
         MS_CUDA(cudaMemcpyAsync(d_score + (size_t)p0 * plane, score + (size_t)p0 * plane, np * plane * 4,
                                 cudaMemcpyHostToDevice, cs));
-        if (geo_compact)
+        if (geo_mapped) {
+            // nothing to upload
+        } else if (geo_compact)
             MS_CUDA(cudaMemcpy2DAsync(d_geo + (size_t)p0 * gplane * 8, (size_t)map_w * 4,
                                       geo + (size_t)p0 * plane * 8 + (size_t)(q / 2) * map_w, (size_t)q * map_w * 4,
                                       (size_t)map_w * 4, (size_t)np * 8 * (map_h / q), cudaMemcpyHostToDevice, cs));
@@ -1023,7 +1036,8 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
                                     np * page_bytes, cudaMemcpyHostToDevice, cs));
         MS_CUDA(cudaEventRecord(ev, cs));
         MS_CUDA(cudaStreamWaitEvent(st, ev, 0));
-        MS_TRY(page_batch_impl(ctx, d_score + (size_t)p0 * plane, d_geo + (size_t)p0 * gplane * 8, d_pages, n_pages, p0,
+        const float *geo_chunk = geo_mapped ? geo_mapped + (size_t)p0 * plane * 8 : d_geo + (size_t)p0 * gplane * 8;
+        MS_TRY(page_batch_impl(ctx, d_score + (size_t)p0 * plane, geo_chunk, d_pages, n_pages, p0,
                                np, map_h, map_w, img_h, img_w, p, min_text_size, out_h, out_w, cap_boxes,
                                d_boxes + (size_t)p0 * cap_boxes * 9, d_cnt + p0, d_crops, crops_cap, d_nc, 1, d_batch,
                                nullptr, d_flags + p0, st, geo_compact));

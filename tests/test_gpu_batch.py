@@ -67,6 +67,14 @@ def test_page_batch_vs_oracle(torch_cuda, page, words, n_pages):
     np.testing.assert_array_equal(res_h.crops[:n_crops], crops)
     assert res_h.batch.is_cuda and tuple(res_h.batch.shape) == (n_crops, 3, 32, 128)
     np.testing.assert_array_equal(res_h.batch.cpu().numpy(), batch)  # device-resident batch of the host entry point
+    # pinned host tensors: the geometry is not uploaded, the decode kernel gathers it from host memory (zero copy)
+    pin = [torch.from_numpy(a).pin_memory() for a in (score, geo, imgs)]
+    res_p = runner.run_host(*pin)
+    np.testing.assert_array_equal(res_p.box_counts, counts)
+    for p in range(n_pages):
+        np.testing.assert_array_equal(res_p.boxes[p, : counts[p]], boxes[p, : counts[p]])
+    np.testing.assert_array_equal(res_p.crops[:n_crops], crops)
+    np.testing.assert_array_equal(res_p.batch.cpu().numpy(), batch)
     # capacity knob of the NMS neighbour-pair buffer (ms_set_edge_factor / ms_get_edge_factor)
     assert runner.ctx.edge_factor == 16
     runner.ctx.edge_factor = 64

@@ -82,6 +82,9 @@ struct LanmsBuffers {
     int32_t *nb_cnt;     // two-pass rebuild: neighbours per cluster, then their exclusive offsets
     int32_t *und_flags;  // per page, 2 ints: "some box still undecided" of the current / previous round
     uint64_t *kept_key;  // per kept entry: descending-score sort key
+    int32_t *acc_count;  // per page: accepted merge runs
+    int32_t *ext_acc;    // per page, 8 ints: extent accumulators (ordered-int images of floats)
+    int32_t *ext_done;   // per page: cluster-building CTAs that have contributed
 };
 
 // ---- helpers ------------------------------------------------------------------------------------
@@ -288,68 +291,143 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &tot
     return s_warp[warp] + inc - v;
 }
 
-__global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const int32_t *__restrict__ page_off,
-                                                                         int all_irregular, LanmsBuffers B)
+// 4a. one CTA per page: the page's hot positions in order, the accepted runs among them (a run is accepted iff its
+//     head lies beyond the end of the last accepted run -- a sequential walk, done by one thread over shared memory),
+//     and for every accepted run the number of merged positions before it.  Clusters = positions outside the runs.
+constexpr int kAcceptBatch = 4096;  // hot positions walked per round out of shared memory
+
+__global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
 {
     const int page = blockIdx.x;
     const int p0 = page_off[page], p1 = page_off[page + 1];
     __shared__ int s_warp[33];
-    __shared__ int s_h[kResolveThreads], s_e[kResolveThreads];
-    __shared__ int s_vh[kResolveThreads], s_ve[kResolveThreads];
-    __shared__ int s_nvalid, s_klast;
-    __shared__ float s_red[32][6];
-    if (threadIdx.x == 0) s_klast = p0 - 1;
+    __shared__ int s_h[kAcceptBatch], s_e[kAcceptBatch];
+    __shared__ int s_klast, s_nacc, s_merged, s_nv;
+    int32_t *hot_sorted = B.cl_cell + p0;  // scratch until the neighbour grid is built
+    int32_t *acc_h = B.kept_list + p0, *acc_e = B.nb_cnt + p0, *acc_pm = B.sb_id + p0;
+    if (threadIdx.x == 0) {
+        s_klast = p0 - 1;
+        s_nacc = 0;
+        s_merged = 0;
+        B.ext_done[page] = 0;
+        int32_t *acc = B.ext_acc + (size_t)page * 8;
+        acc[0] = acc[1] = INT_MAX;  // min x, min y (ordered-int images of floats)
+        acc[2] = acc[3] = INT_MIN;  // max x, max y
+        acc[4] = acc[5] = 0;        // max width, max height (non-negative floats order like their bits)
+    }
     for (int i = threadIdx.x; i < kCells; i += kResolveThreads) B.cell_cnt[(size_t)page * kCells + i] = 0;
-    __syncthreads();
-
-    // phase A: walk hot positions in order, accept a run iff its head lies beyond the last accepted run
-    for (int base = p0; base < p1; base += kResolveThreads) {
-        int s = base + threadIdx.x;
-        int flag = (s < p1 && B.hot[s]) ? 1 : 0;
+    // hot positions of the page, ascending: 8 consecutive positions per thread and round
+    int nh = 0;
+    for (int base = p0; base < p1; base += kResolveThreads * 8) {
+        const int s0 = base + threadIdx.x * 8;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (s0 + k < p1 && B.hot[s0 + k]) bits |= 1u << k;
         int total;
-        int pos = block_excl_scan_1024(flag, s_warp, total);
-        if (flag) {
-            s_h[pos] = s;
-            s_e[pos] = B.run_end[s];
+        int pos = nh + block_excl_scan_1024(__popc(bits), s_warp, total);
+        while (bits) {
+            const int k = __ffs(bits) - 1;
+            bits &= bits - 1;
+            hot_sorted[pos++] = s0 + k;
+        }
+        nh += total;
+    }
+    __syncthreads();
+    for (int b0 = 0; b0 < nh; b0 += kAcceptBatch) {
+        const int nb = min(kAcceptBatch, nh - b0);
+        for (int j = threadIdx.x; j < nb; j += kResolveThreads) {
+            const int h = hot_sorted[b0 + j];
+            s_h[j] = h;
+            s_e[j] = B.run_end[h];
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int klast = s_klast, nv = 0;
-            for (int j = 0; j < total; j++) {
-                int h = s_h[j];
+            int klast = s_klast, nacc = s_nacc, merged = s_merged, nv = 0;
+            for (int j = 0; j < nb; j++) {
+                const int h = s_h[j];
                 if (h > klast) {
                     klast = s_e[j];
-                    s_vh[nv] = h;
-                    s_ve[nv] = klast;
+                    acc_pm[nacc + nv] = merged;  // merged positions before this run
+                    merged += klast - h;
+                    s_h[nv] = h;                 // compacted in place (nv <= j)
+                    s_e[nv] = klast;
                     nv++;
                 }
             }
             s_klast = klast;
-            s_nvalid = nv;
+            s_merged = merged;
+            s_nv = nv;
         }
         __syncthreads();
-        for (int j = threadIdx.x; j < s_nvalid; j += kResolveThreads) {
-            int h = s_vh[j], e = s_ve[j];
-            B.mflag[h] = 2;
-            for (int i = h + 1; i < e; i++) B.mflag[i] = 1;
+        const int nacc = s_nacc, nv = s_nv;
+        for (int j = threadIdx.x; j < nv; j += kResolveThreads) {
+            acc_h[nacc + j] = s_h[j];
+            acc_e[nacc + j] = s_e[j];
         }
+        __syncthreads();
+        if (threadIdx.x == 0) s_nacc = nacc + nv;
         __syncthreads();
     }
-    __threadfence_block();
-    __syncthreads();
+    if (threadIdx.x == 0) {
+        B.acc_count[page] = s_nacc;
+        B.cl_count[page] = (p1 - p0) - s_merged;
+    }
+}
 
-    // phase B: anchors (mflag == 0) in order are the clusters
-    int run_base = 0;
+__device__ __forceinline__ int float_ordered(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+// 4b. thread per position, any number of CTAs per page: a position outside every accepted run anchors a cluster --
+//     the run that starts right after it if there is one, else the box itself; its cluster index is its position
+//     minus the merged positions before it (binary search in the page's accepted runs).
+constexpr int kBuildThreads = 256;
+constexpr int kBuildRuns = 1024;  // accepted runs searched out of shared memory
+
+__global__ void __launch_bounds__(kBuildThreads) lanms_build_clusters_kernel(const int32_t *__restrict__ page_off,
+                                                                             int all_irregular, LanmsBuffers B)
+{
+    const int page = blockIdx.y;
+    const int p0 = page_off[page], p1 = page_off[page + 1];
+    __shared__ int s_h[kBuildRuns], s_e[kBuildRuns], s_pm[kBuildRuns];
+    __shared__ float s_red[kBuildThreads / 32][6];
+    const int nacc = B.acc_count[page];
+    const int32_t *acc_h = B.kept_list + p0, *acc_e = B.nb_cnt + p0, *acc_pm = B.sb_id + p0;
+    const bool in_smem = nacc <= kBuildRuns;
+    if (in_smem) {
+        for (int j = threadIdx.x; j < nacc; j += kBuildThreads) {
+            s_h[j] = acc_h[j];
+            s_e[j] = acc_e[j];
+            s_pm[j] = acc_pm[j];
+        }
+    }
+    __syncthreads();
+    const int *gh = in_smem ? s_h : acc_h, *ge = in_smem ? s_e : acc_e, *gpm = in_smem ? s_pm : acc_pm;
+    // last accepted run whose head is <= s (-1: none)
+    auto run_at = [&](int s) {
+        int lo = 0, hi = nacc;
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (gh[mid] <= s)
+                lo = mid + 1;
+            else
+                hi = mid;
+        }
+        return lo - 1;
+    };
     float e_minx = INFINITY, e_miny = INFINITY, e_maxx = -INFINITY, e_maxy = -INFINITY, e_w = 0.f, e_h = 0.f;
-    for (int base = p0; base < p1; base += kResolveThreads) {
-        int s = base + threadIdx.x;
-        int anchor = (s < p1 && B.mflag[s] == 0) ? 1 : 0;
-        int total;
-        int pos = block_excl_scan_1024(anchor, s_warp, total);
-        if (anchor) {
-            int c = run_base + pos;
-            size_t slot = (size_t)p0 + c;
-            bool has_run = (s + 1 < p1) && (B.mflag[s + 1] == 2);
+    for (int s = p0 + blockIdx.x * kBuildThreads + threadIdx.x; s < p1; s += gridDim.x * kBuildThreads) {
+        const int r = run_at(s);
+        const bool inside = r >= 0 && s < ge[r];
+        if (!inside) {
+            const int merged_before = r >= 0 ? gpm[r] + (ge[r] - gh[r]) : 0;
+            const int c = (s - p0) - merged_before;
+            const size_t slot = (size_t)p0 + c;
+            const bool has_run = r + 1 < nacc && gh[r + 1] == s + 1;
             double poly[8];
             double score;
             if (has_run) {
@@ -380,9 +458,9 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
                 e_h = fmaxf(e_h, bb.w - bb.y);
             }
         }
-        run_base += total;
     }
-    // page extents of the regular clusters -> geometry of the neighbour-search grid
+    // page extents of the regular clusters -> geometry of the neighbour-search grid: CTA reduction, one set of
+    // atomics per CTA, and the last CTA of the page turns the accumulators into the grid geometry
 #pragma unroll
     for (int off = 16; off > 0; off >>= 1) {
         e_minx = fminf(e_minx, __shfl_xor_sync(0xffffffffu, e_minx, off));
@@ -399,7 +477,7 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
     __syncthreads();
     if (threadIdx.x == 0) {
         float minx = INFINITY, miny = INFINITY, maxx = -INFINITY, maxy = -INFINITY, mw = 0.f, mh = 0.f;
-        for (int w = 0; w < kResolveThreads / 32; w++) {
+        for (int w = 0; w < kBuildThreads / 32; w++) {
             minx = fminf(minx, s_red[w][0]);
             miny = fminf(miny, s_red[w][1]);
             maxx = fmaxf(maxx, s_red[w][2]);
@@ -407,16 +485,31 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_clusters_kernel(const i
             mw = fmaxf(mw, s_red[w][4]);
             mh = fmaxf(mh, s_red[w][5]);
         }
-        float *ext = B.page_ext + (size_t)page * 8;
-        const bool any = maxx >= minx;
-        const float sx = any ? fmaxf(maxx - minx, 1e-3f) : 1.f, sy = any ? fmaxf(maxy - miny, 1e-3f) : 1.f;
-        ext[0] = any ? minx : 0.f;
-        ext[1] = any ? miny : 0.f;
-        ext[2] = (float)kGrid / sx;
-        ext[3] = (float)kGrid / sy;
-        ext[4] = mw;
-        ext[5] = mh;
-        B.cl_count[page] = run_base;
+        int32_t *acc = B.ext_acc + (size_t)page * 8;
+        if (maxx >= minx) {
+            atomicMin(&acc[0], float_ordered(minx));
+            atomicMin(&acc[1], float_ordered(miny));
+            atomicMax(&acc[2], float_ordered(maxx));
+            atomicMax(&acc[3], float_ordered(maxy));
+            atomicMax(&acc[4], __float_as_int(mw));
+            atomicMax(&acc[5], __float_as_int(mh));
+        }
+        __threadfence();
+        if (atomicAdd(&B.ext_done[page], 1) == (int)gridDim.x - 1) {  // every CTA of the page passes here
+            __threadfence();
+            const volatile int32_t *va = acc;
+            const bool any = va[2] != INT_MIN;
+            const float fminx = ordered_float(va[0]), fminy = ordered_float(va[1]);
+            const float fmaxx = ordered_float(va[2]), fmaxy = ordered_float(va[3]);
+            const float sx = any ? fmaxf(fmaxx - fminx, 1e-3f) : 1.f, sy = any ? fmaxf(fmaxy - fminy, 1e-3f) : 1.f;
+            float *ext = B.page_ext + (size_t)page * 8;
+            ext[0] = any ? fminx : 0.f;
+            ext[1] = any ? fminy : 0.f;
+            ext[2] = (float)kGrid / sx;
+            ext[3] = (float)kGrid / sy;
+            ext[4] = __int_as_float(va[4]);
+            ext[5] = __int_as_float(va[5]);
+        }
     }
 }
 
@@ -1120,6 +1213,9 @@ size_t carve(ms_bump &bump, LanmsBuffers &B, int n_pages, size_t n_max, bool ful
     B.und_flags = bump.take<int32_t>((size_t)n_pages * 2);
     B.kept_key = bump.take<uint64_t>(n_max);
     B.kept_list = bump.take<int32_t>(n_max);
+    B.acc_count = bump.take<int32_t>(n_pages);
+    B.ext_acc = bump.take<int32_t>((size_t)n_pages * 8);
+    B.ext_done = bump.take<int32_t>(n_pages);
     return bump.off;
 }
 
@@ -1174,7 +1270,17 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
     MS_LAUNCH_CHECK(ctx);
     lanms_runs_kernel<<<sms * 4, 128, 0, st>>>(B.page_off, thr, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_clusters_kernel<<<n_pages, kResolveThreads, 0, st>>>(B.page_off, thr < 0 ? 1 : 0, B);
+    lanms_accept_kernel<<<n_pages, kResolveThreads, 0, st>>>(B.page_off, B);
+    MS_LAUNCH_CHECK(ctx);
+    {
+        // a few CTAs per page, each striding over the page's positions (the counts live on the device)
+        int gx = (cap_per_page + kBuildThreads - 1) / kBuildThreads;
+        const int want = (sms * 8 + n_pages - 1) / n_pages;
+        if (gx > want) gx = want;
+        if (gx < 1) gx = 1;
+        lanms_build_clusters_kernel<<<dim3((unsigned)gx, (unsigned)n_pages), kBuildThreads, 0, st>>>(
+            B.page_off, thr < 0 ? 1 : 0, B);
+    }
     MS_LAUNCH_CHECK(ctx);
     {
         int g = (int)((n_max + 255) / 256);

@@ -168,6 +168,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + 2 * kSrcBuf);  // [2 stages][kTabWords][iw + ih]
     const int tab_n = iw + ih;
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
+    __shared__ int s_x3[2];  // per stage: every x entry of the crop has at most 3 taps
 
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -211,7 +212,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
             }
-            build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane);
+            const bool x3 = __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane));
+            if (lane == 0) s_x3[b] = x3 ? 1 : 0;
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
             if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
             k++;
@@ -237,8 +239,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         // the padding of the remaining channel(s) is written by the consumers while the TMA copies are in flight
         write_padding<kWriteF32, kWriteU8>(*pg, ih, iw, dstf, dstu, vec_ok, ct, kCT, kProducerChannels, 3);
         mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
-        const bool bad = area4_strips<kWriteF32, kWriteU8, kCT>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep, tab, tab_n,
-                                                                ih, iw, nw, nh, y0, dstf, dstu, ct);
+        // three x taps at most (shrink factor below 2, nearly every word box): a quarter of the horizontal work less
+        const bool bad = s_x3[b] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
+                                                                             tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct)
+                                 : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
+                                                                             tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct);
         if (bad) redo[ci] = 1;  // a table entry with more than 4 taps: the generic kernel redoes the crop
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[b]);

@@ -59,8 +59,22 @@ __device__ __forceinline__ void plan_resize(int w, int h, int ih, int iw, Plan &
     }
 }
 
-// OpenCV computeResizeAreaTab for destination index d
-__device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize)
+// (float)(num / den) for 0 <= num <= den, given inv = 1.0 / den (correctly rounded): num * inv is within two double
+// ulps of the quotient, so it rounds to the same float unless it sits that close to the midpoint between two floats
+// (the 29 bits below float precision near 100...0) -- then, and for tiny values, the division itself is evaluated.
+__device__ __noinline__ float div_to_float_slow(double num, double den) { return (float)(num / den); }
+__device__ __forceinline__ float div_to_float(double num, double den, double inv)
+{
+    const double q = num * inv;
+    const unsigned lo = (unsigned)__double2loint(q) & 0x1fffffffu;
+    if (num == 0.0) return 0.f;  // exact, and common (a window that starts or ends on a pixel boundary)
+    if (lo - 0x0ffffff0u <= 0x20u || !(q > 1e-30)) return div_to_float_slow(num, den);
+    return (float)q;
+}
+
+// OpenCV computeResizeAreaTab for destination index d.  inv_scale = 1.0 / scale, computed once per axis: every entry
+// but a clipped last one divides by `scale`, and the three quotients of an entry come out of one reciprocal.
+__device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize, double inv_scale)
 {
     AxisEnt t;
     double f1 = d * scale, f2 = f1 + scale;
@@ -70,9 +84,16 @@ __device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize)
     s1 = min(s1, s2);
     const bool has_first = (s1 - f1) > 1e-3;
     const bool has_last = (f2 - s2) > 1e-3;
-    t.af = (float)((s1 - f1) / cell);
-    t.am = (float)(1.0 / cell);
-    t.al = (float)(fmin(fmin(f2 - s2, 1.0), cell) / cell);
+    const double n_first = s1 - f1, n_last = fmin(fmin(f2 - s2, 1.0), cell);
+    if (cell == scale && n_first >= 0.0 && n_last >= 0.0) {
+        t.af = div_to_float(n_first, cell, inv_scale);
+        t.am = (float)inv_scale;
+        t.al = div_to_float(n_last, cell, inv_scale);
+    } else {  // the clipped last entry of an axis
+        t.af = div_to_float_slow(n_first, cell);
+        t.am = div_to_float_slow(1.0, cell);
+        t.al = div_to_float_slow(n_last, cell);
+    }
     t.nfirst = has_first ? 1 : 0;
     t.nmid = s2 > s1 ? s2 - s1 : 0;
     t.s0 = has_first ? s1 - 1 : s1;
@@ -80,6 +101,7 @@ __device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize)
     t.pad = 0;
     return t;
 }
+__device__ __forceinline__ AxisEnt area_entry(int d, double scale, int ssize) { return area_entry(d, scale, ssize, 1.0 / scale); }
 
 __device__ __forceinline__ float area_weight(const AxisEnt &t, int e)
 {
@@ -275,12 +297,16 @@ __device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
 // out of the staged rows: 12 contiguous bytes (4 taps x RGB) fetched as aligned 32-bit shared-memory words; taps
 // beyond n carry weight 0 (x + 0*y == x exactly, every term is >= 0).  Same products and the same summation order as
 // resample_px's general branch.  `o` = shared-memory byte offset of the row's first tap.
+// kTaps = 3: every x entry of the crop has at most 3 taps (always the case for a shrink factor below 2), so the fourth
+// tap -- weight 0, an exact no-op -- and the word that only it needs are not touched.
+template <int kTaps>
 __device__ __forceinline__ void hrow_area4(const unsigned char *smem_base, uint32_t o, const float4 wx, float &b0,
                                            float &b1, float &b2)
 {
     const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
     const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
-    const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2], w3 = smem32[wi + 3];
+    const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2];
+    const uint32_t w3 = kTaps > 3 ? smem32[wi + 3] : 0u;
     const uint32_t v0 = __funnelshift_r(w0, w1, sh), v1 = __funnelshift_r(w1, w2, sh), v2 = __funnelshift_r(w2, w3, sh);
     // bytes: tap0 = v0.b0..b2, tap1 = v0.b3 v1.b0 v1.b1, tap2 = v1.b2 v1.b3 v2.b0, tap3 = v2.b1..b3
     b0 = byte_f32(v0, 0x7650) * wx.x;
@@ -292,29 +318,36 @@ __device__ __forceinline__ void hrow_area4(const unsigned char *smem_base, uint3
     b0 = b0 + byte_f32(v1, 0x7652) * wx.z;
     b1 = b1 + byte_f32(v1, 0x7653) * wx.z;
     b2 = b2 + byte_f32(v2, 0x7650) * wx.z;
-    b0 = b0 + byte_f32(v2, 0x7651) * wx.w;
-    b1 = b1 + byte_f32(v2, 0x7652) * wx.w;
-    b2 = b2 + byte_f32(v2, 0x7653) * wx.w;
+    if (kTaps > 3) {
+        b0 = b0 + byte_f32(v2, 0x7651) * wx.w;
+        b1 = b1 + byte_f32(v2, 0x7652) * wx.w;
+        b2 = b2 + byte_f32(v2, 0x7653) * wx.w;
+    }
 }
 
 // The INTER_AREA coefficient tables of one crop for the 4-tap path, structure of arrays:
 // tab[0][i] = s0 | n << 16, tab[1..4][i] = tap weights (0 beyond n); x entries occupy [0, iw), y entries
 // [iw, iw + ih) of every array.  Plan::fast guarantees n <= 4; an entry that violates it is stored with n = 0xffff
 // and makes the consumers hand the crop to the generic kernel.
-__device__ __forceinline__ void build_tables(const Plan &p, uint32_t *tab, int tab_n, int iw, int tid,
+// Returns whether every x entry built by this thread has at most 3 taps (the caller combines the threads' answers).
+__device__ __forceinline__ bool build_tables(const Plan &p, uint32_t *tab, int tab_n, int iw, int tid,
                                              int nthreads = 32)
 {
     float *tw = reinterpret_cast<float *>(tab);
+    bool x3 = true;
+    const double inv_x = 1.0 / p.scale_x, inv_y = 1.0 / p.scale_y;
     for (int t = tid; t < p.nw + p.nh; t += nthreads) {
         const bool isx = t < p.nw;
         const int d = isx ? t : t - p.nw;
-        const AxisEnt e = isx ? area_entry(d, p.scale_x, p.w) : area_entry(d, p.scale_y, p.h);
+        const AxisEnt e = isx ? area_entry(d, p.scale_x, p.w, inv_x) : area_entry(d, p.scale_y, p.h, inv_y);
         const int at = isx ? d : iw + d;
         const bool fits = e.n <= 4 && e.s0 >= 0 && e.s0 < 65536;
+        x3 = x3 && !(isx && e.n > 3);
         tab[at] = fits ? ((uint32_t)e.s0 | ((uint32_t)e.n << 16)) : 0xffff0000u;
 #pragma unroll
         for (int k = 0; k < 4; k++) tw[(size_t)(1 + k) * tab_n + at] = k < e.n ? area_weight(e, k) : 0.f;
     }
+    return x3;
 }
 
 // INTER_AREA general path for a crop whose axis tables have <= 4 taps per entry (shrink factors below 3), source
@@ -324,7 +357,7 @@ __device__ __forceinline__ void build_tables(const Plan &p, uint32_t *tab, int t
 // destination rows share their boundary source row, so a strip needs ~(2G + 1) horizontal row sums instead of 3G;
 // per-pixel arithmetic and its order are those of resample_px's general branch.  Returns true when a table entry
 // had more than 4 taps (the caller redoes the crop with resample_px).
-template <bool kWriteF32, bool kWriteU8, int kCT>
+template <bool kWriteF32, bool kWriteU8, int kCT, int kTaps>
 __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t stage_off, uint32_t pitch, uint32_t a0,
                                              uint32_t sstep, const uint32_t *tab, int tab_n, int ih, int iw, int nw,
                                              int nh, int y0, float *dstf, uint8_t *dstu, int ct)
@@ -368,7 +401,7 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
             const uint32_t rbase = xoff + (uint32_t)ys0 * pitch;
             if (ys0 != last_r) {
                 const uint32_t mis = sstep == 0 ? a0 : ((a0 + (uint32_t)ys0 * sstep) & 15u);
-                hrow_area4(smem, rbase + mis, wx, b0, b1, b2);
+                hrow_area4<kTaps>(smem, rbase + mis, wx, b0, b1, b2);
             }
             float sum0 = wyv[0] * b0, sum1 = wyv[0] * b1, sum2 = wyv[0] * b2;
 #pragma unroll
@@ -376,7 +409,7 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
                 if (j < yn) {
                     const uint32_t r = (uint32_t)(ys0 + j);
                     const uint32_t mis = sstep == 0 ? a0 : ((a0 + r * sstep) & 15u);
-                    hrow_area4(smem, rbase + (uint32_t)j * pitch + mis, wx, b0, b1, b2);
+                    hrow_area4<kTaps>(smem, rbase + (uint32_t)j * pitch + mis, wx, b0, b1, b2);
                     sum0 += wyv[j] * b0;
                     sum1 += wyv[j] * b1;
                     sum2 += wyv[j] * b2;

@@ -337,8 +337,9 @@ __global__ void __launch_bounds__(kQcThreads, 4) quad_crop_kernel(const uint8_t 
         const bool strips = p.staged && soa_fits && p.interp == 3 && p.scale_x < 2.999 && p.scale_y < 2.999;
         const bool need_tab = p.interp == 1 || p.interp == 3;
         const bool tab_ok = need_tab && p.nw + p.nh <= kQcMaxTab;
+        bool x3_mine = true;
         if (strips) {
-            build_tables(p, soa, tab_n, iw, threadIdx.x, kQcThreads);
+            x3_mine = build_tables(p, soa, tab_n, iw, threadIdx.x, kQcThreads);
         } else if (tab_ok) {
             for (int t = threadIdx.x; t < p.nw + p.nh; t += blockDim.x) {
                 const bool isx = t < p.nw;
@@ -347,7 +348,7 @@ __global__ void __launch_bounds__(kQcThreads, 4) quad_crop_kernel(const uint8_t 
                                          : (isx ? linear_entry_x(d, p.scale_x, p.w) : linear_entry_y(d, p.scale_y, p.h));
             }
         }
-        __syncthreads();
+        const bool x3 = __syncthreads_and(x3_mine) != 0;  // also the barrier after the tables
         const QuadPlan &qp = s_qp;
         const PageView pg{pages + (size_t)qp.page * img_h * (size_t)img_w * 3, img_h, img_w, replicate, bval};
         if (p.staged) {
@@ -356,8 +357,11 @@ __global__ void __launch_bounds__(kQcThreads, 4) quad_crop_kernel(const uint8_t 
             __syncthreads();
             bool redo = !strips;
             if (strips)
-                redo = __syncthreads_or(area4_strips<kWriteF32, kWriteU8, kQcThreads>(
-                    qc_smem, 0u, (uint32_t)pitch, 0u, 0u, soa, tab_n, ih, iw, p.nw, p.nh, p.y0, dstf, dstu, threadIdx.x));
+                redo = __syncthreads_or(
+                    x3 ? area4_strips<kWriteF32, kWriteU8, kQcThreads, 3>(qc_smem, 0u, (uint32_t)pitch, 0u, 0u, soa, tab_n, ih,
+                                                                          iw, p.nw, p.nh, p.y0, dstf, dstu, threadIdx.x)
+                       : area4_strips<kWriteF32, kWriteU8, kQcThreads, 4>(qc_smem, 0u, (uint32_t)pitch, 0u, 0u, soa, tab_n, ih,
+                                                                          iw, p.nw, p.nh, p.y0, dstf, dstu, threadIdx.x));
             if (redo) {
                 if (strips) {  // an entry with more than 4 taps after all: per-pixel entries, no table
                     resample_canvas<kWriteF32, kWriteU8>(p, PitchedSrc{qc_patch, pitch}, s_tab, false, need_tab, ih, iw,

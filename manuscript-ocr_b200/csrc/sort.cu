@@ -25,20 +25,24 @@ __global__ void __launch_bounds__(kThreads) seg_hist_kernel(const uint32_t *__re
                                                             const int32_t *__restrict__ seg_len, int skip_le,
                                                             int tiles_max, int shift, int32_t *__restrict__ hist)
 {
-    const int page = blockIdx.y, tile = blockIdx.x;
+    const int page = blockIdx.y;
     const int p0 = page_off[page], n = seg_len ? seg_len[page] : page_off[page + 1] - p0;
-    if (n <= skip_le || tile * kTile >= n) return;
+    if (n <= skip_le) return;
     __shared__ int s_h[kRadix];
-    for (int d = threadIdx.x; d < kRadix; d += kThreads) s_h[d] = 0;
-    __syncthreads();
-    const int base = tile * kTile;
-    for (int i = threadIdx.x; i < kTile; i += kThreads) {
-        const int idx = base + i;
-        if (idx < n) atomicAdd(&s_h[(keys[p0 + idx] >> shift) & 0xFF], 1);
+    // the segment lengths live on the device: a few CTAs per page stride over its tiles
+    for (int tile = blockIdx.x; tile * kTile < n; tile += gridDim.x) {
+        for (int d = threadIdx.x; d < kRadix; d += kThreads) s_h[d] = 0;
+        __syncthreads();
+        const int base = tile * kTile;
+        for (int i = threadIdx.x; i < kTile; i += kThreads) {
+            const int idx = base + i;
+            if (idx < n) atomicAdd(&s_h[(keys[p0 + idx] >> shift) & 0xFF], 1);
+        }
+        __syncthreads();
+        int32_t *h = hist + ((size_t)page * tiles_max + tile) * kRadix;
+        for (int d = threadIdx.x; d < kRadix; d += kThreads) h[d] = s_h[d];
+        __syncthreads();
     }
-    __syncthreads();
-    int32_t *h = hist + ((size_t)page * tiles_max + tile) * kRadix;
-    for (int d = threadIdx.x; d < kRadix; d += kThreads) h[d] = s_h[d];
 }
 
 __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *__restrict__ keys,
@@ -50,14 +54,15 @@ __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *_
                                                                uint32_t *__restrict__ keys_out,
                                                                uint32_t *__restrict__ vals_out)
 {
-    const int page = blockIdx.y, tile = blockIdx.x;
+    const int page = blockIdx.y;
     const int p0 = page_off[page], n = seg_len ? seg_len[page] : page_off[page + 1] - p0;
-    if (n <= skip_le || tile * kTile >= n) return;
+    if (n <= skip_le) return;
     const int tiles = (n + kTile - 1) / kTile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     __shared__ int s_cnt[kWarps][kRadix];  // per-warp digit counts, then running write cursors
     __shared__ int s_base[kRadix];         // first output slot of (digit, this tile) inside the page
     __shared__ int s_wsum[kWarps];
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
     // digit d of this tile starts after every smaller digit of the whole page and digit d of the earlier tiles
     {
         const int d = threadIdx.x;  // kThreads == kRadix
@@ -120,6 +125,8 @@ __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *_
             vals_out[p0 + pos] = v;
         }
     }
+    __syncthreads();  // the shared tables are rebuilt for the next tile
+    }
 }
 
 }  // namespace
@@ -144,7 +151,12 @@ int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_t
         return MS_ERR_CAPACITY;
     }
     uint32_t *kin = keys, *kout = keys_tmp, *vin = vals, *vout = vals_tmp;
-    const dim3 grid(tiles_max, n_pages);
+    // segment lengths are device data: launch at most a few CTAs per page and let them stride over the page's tiles
+    int gx = tiles_max;
+    const int want = (ctx->num_sms * 8 + n_pages - 1) / n_pages;
+    if (gx > want) gx = want;
+    if (gx < 1) gx = 1;
+    const dim3 grid(gx, n_pages);
     for (int pass = 0; pass < 4; pass++) {
         seg_hist_kernel<<<grid, kThreads, 0, st>>>(kin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist);
         MS_LAUNCH_CHECK(ctx);

@@ -190,11 +190,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         int k = 0;
         for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
             const Plan p = plans[ci];
+            if (ci + gridDim.x < n_crops) {  // the next plan is on its way while this crop is set up
+                const char *nx = reinterpret_cast<const char *>(plans + ci + gridDim.x);
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + sizeof(Plan) - 1));
+            }
             if (!p.fast) continue;
             const int b = k & 1;
-            write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
-                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
-                                              kProducerChannels);
+            // The consumers wait for the source rows and the tables, not for the padding: copies and tables first.
             if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
             // TMA first: its latency overlaps the float64 table arithmetic below
             uint32_t bytes = 0;
@@ -216,6 +219,9 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             if (lane == 0) s_x3[b] = x3 ? 1 : 0;
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
             if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
+            write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
+                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
+                                              kProducerChannels);
             k++;
         }
         return;

@@ -196,31 +196,73 @@ __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__re
 {
     const int n = *n_total;
     double buf[4 * MS_MAXV];
-    for (int s = blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x) {
-        int page = B.pos_page[s];
-        const float *row = quads + (size_t)vals[s] * 9;
-        double me[8];
+    __shared__ int s_q[128 / 32][64];  // per warp: positions whose IoU with the predecessor has to be evaluated
+    const int lane = threadIdx.x & 31;
+    int *q = s_q[threadIdx.x >> 5];
+    int qn = 0;  // warp-uniform
+    // lanms.py:180 IoU(subject = box s, clip = box s - 1) > thr.  In x0 order most neighbours lie in different text
+    // rows: when the clip quad is regular (convex, positively oriented -- Sutherland-Hodgman then returns the true
+    // intersection) and the subject's corners all lie beyond one side of its inflated bounding box, the intersection is
+    // empty and the IoU is exactly 0, which is not > thr for thr >= 0.  The few positions that need the float64 clip
+    // are queued per warp and evaluated 32 at a time, so that a warp never clips for one lane's sake.
+    auto evaluate = [&](int s) {
+        const float *row = quads + (size_t)vals[s] * 9, *prow = quads + (size_t)vals[s - 1] * 9;
+        double me[8], pv[8];
 #pragma unroll
-        for (int k = 0; k < 8; k++) me[k] = (double)row[k];
-        double2 *dst = reinterpret_cast<double2 *>(B.sq + (size_t)s * 8);
-#pragma unroll
-        for (int k = 0; k < 4; k++) dst[k] = make_double2(me[2 * k], me[2 * k + 1]);
-        B.ss[s] = row[8];
-        B.mflag[s] = 0;
-        bool is_hot = false;
-        if (s > page_off[page]) {
-            const float *prow = quads + (size_t)vals[s - 1] * 9;
-            double pv[8];
-#pragma unroll
-            for (int k = 0; k < 8; k++) pv[k] = (double)prow[k];
-            is_hot = ms_quad_iou(me, pv, buf) > thr;  // lanms.py:180 subject = new box, clip = last
+        for (int k = 0; k < 8; k++) {
+            me[k] = (double)row[k];
+            pv[k] = (double)prow[k];
         }
-        B.hot[s] = is_hot ? 1 : 0;
-        if (is_hot) {
-            int slot = atomicAdd(B.hot_count, 1);
-            B.hot_list[slot] = s;
+        if (ms_quad_iou(me, pv, buf) > thr) {
+            B.hot[s] = 1;
+            B.hot_list[atomicAdd(B.hot_count, 1)] = s;
+        }
+    };
+    const int stride = gridDim.x * blockDim.x;
+    for (int s0 = blockIdx.x * blockDim.x; s0 < n; s0 += stride) {  // warp-uniform trip count
+        const int s = s0 + threadIdx.x;
+        bool need = false;
+        if (s < n) {
+            const int page = B.pos_page[s];
+            const float *row = quads + (size_t)vals[s] * 9;
+            double me[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) me[k] = (double)row[k];
+            double2 *dst = reinterpret_cast<double2 *>(B.sq + (size_t)s * 8);
+#pragma unroll
+            for (int k = 0; k < 4; k++) dst[k] = make_double2(me[2 * k], me[2 * k + 1]);
+            B.ss[s] = row[8];
+            B.hot[s] = 0;
+            if (s > page_off[page]) {
+                const float *prow = quads + (size_t)vals[s - 1] * 9;
+                double pv[8];
+#pragma unroll
+                for (int k = 0; k < 8; k++) pv[k] = (double)prow[k];
+                bool disjoint = false;
+                float4 pb;
+                if (thr >= 0.0 && quad_regular_bbox(pv, pb)) {
+                    const double mnx = fmin(fmin(me[0], me[2]), fmin(me[4], me[6]));
+                    const double mxx = fmax(fmax(me[0], me[2]), fmax(me[4], me[6]));
+                    const double mny = fmin(fmin(me[1], me[3]), fmin(me[5], me[7]));
+                    const double mxy = fmax(fmax(me[1], me[3]), fmax(me[5], me[7]));
+                    disjoint = mnx > (double)pb.z || mxx < (double)pb.x || mny > (double)pb.w || mxy < (double)pb.y;
+                }
+                need = !disjoint;
+            }
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, need);
+        if (need) q[qn + __popc(m & ((1u << lane) - 1u))] = s;
+        qn += __popc(m);
+        __syncwarp();
+        if (qn >= 32) {
+            const int s2 = q[qn - 32 + lane];
+            __syncwarp();
+            evaluate(s2);
+            qn -= 32;
+            __syncwarp();
         }
     }
+    if (lane < qn) evaluate(q[lane]);
 }
 
 // ---- 3. speculative runs from every hot position ---------------------------------------------------------

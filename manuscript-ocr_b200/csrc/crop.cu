@@ -20,20 +20,21 @@
 //                           staging decision -> Plan
 //   crop_resize_pad_kernel  the crops with Plan::fast (INTER_AREA with shrink factors below 3 -- what shrinking a
 //                           word box to a 32- or 64-pixel-high canvas gives): persistent, warp specialised, 4 CTAs
-//                           per SM.  Warp 0 (producer) stages the next crop's source rows with TMA bulk copies
-//                           (cp.async.bulk global->shared, one 16-byte-aligned span per row, completion on an
-//                           mbarrier) into a double-buffered stage, builds OpenCV's coefficient tables in shared
-//                           memory (structure of arrays) and writes the 255-padding as constant 16-byte streaming
-//                           stores; warps 1..5 (consumers) resample column strips out of shared memory (aligned
-//                           32-bit loads + funnel shift + PRMT u8->f32, 4 taps) and store normalised pixels straight
-//                           into the CHW batch.  full / empty mbarriers, no CTA-wide barrier in the loop.
+//                           of 7 warps per SM.  Warp 0 (copy warp) stages the next crop's source rows with TMA bulk
+//                           copies (cp.async.bulk global->shared, one 16-byte-aligned span per row, completion on an
+//                           mbarrier) into a double-buffered stage; warp 1 (table warp) builds OpenCV's coefficient
+//                           tables in shared memory (structure of arrays) and writes the 255-padding as constant
+//                           16-byte streaming stores; warps 2..6 (consumers) resample column strips out of shared
+//                           memory (aligned 32-bit loads + funnel shift + PRMT u8->f32, 3 or 4 taps) and store
+//                           normalised pixels straight into the CHW batch.  full / empty mbarriers, no CTA-wide
+//                           barrier in the loop.
 //   crop_generic_kernel     every other crop (copy, INTER_LINEAR upscale, integer-ratio or long-table INTER_AREA,
 //                           rows too long for the stage): one CTA per crop from global memory, same arithmetic.
 #include "crop_common.cuh"
 
 namespace {
 
-constexpr int kThreads = 192;   // 1 producer warp + 5 consumer warps; 4 CTAs per SM
+constexpr int kThreads = 224;   // copy warp + table/padding warp + 5 consumer warps; 4 CTAs per SM
 constexpr int kCtasPerSm = 4;
 constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
 constexpr int kSrcBuf = 24 * 1024;  // bytes per staging buffer (two per CTA)
@@ -148,15 +149,20 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 
-// Warp-specialised persistent kernel for the crops with Plan::fast.  Warp 0 (producer) walks this CTA's crops one
-// ahead of the consumers: it writes the crop's padding, waits until the stage buffer is released, issues the TMA row
-// copies, builds the axis tables and signals full[b].  Warps 1..5 (consumers) wait on full[b], resample the pasted
-// rectangle straight into the CHW batch and release the buffer on empty[b].  No CTA-wide barrier inside the loop.
+// Warp-specialised persistent kernel for the crops with Plan::fast.  Two producer warps walk this CTA's crops one
+// ahead of the consumers: warp 0 (copy warp) waits until the stage buffer is released and issues the TMA row copies;
+// warp 1 (table warp) waits for the same release, builds the axis tables, signals, and then writes the crop's padding
+// (which nobody waits for).  full[b] completes when both have arrived and the copied bytes have landed.  Warps 2..6
+// (consumers) wait on full[b], resample the pasted rectangle straight into the CHW batch and release the buffer on
+// empty[b].  No CTA-wide barrier inside the loop.  Measured per crop (clock64, r1q build with one producer warp):
+// copies 5.8 k cycles (the per-row copy-request rate), tables 4.2 k, padding 2.8 k per channel, consumers ~15 k --
+// one producer warp doing all of it was the critical path, and the consumers had a third of the padding on top.
 // Each consumer thread resamples a column strip (one destination column, G consecutive destination rows): with a
 // shrink factor near 2 neighbouring destination rows share their boundary source row, so a strip needs ~(2G + 1)
 // horizontal row sums instead of 3G; per-pixel arithmetic and its order are unchanged.
-constexpr int kConsumerWarps = kThreads / 32 - 1;
-constexpr int kProducerChannels = 2;  // output channels whose padding the producer writes (the rest: consumers)
+constexpr int kProducerWarps = 2;
+constexpr int kConsumerWarps = kThreads / 32 - kProducerWarps;
+constexpr int kProducerChannels = 3;  // output channels whose padding the table warp writes (the rest: consumers)
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -177,8 +183,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     const int plane = ih * iw;
 
     if (threadIdx.x == 0) {
-        mbar_init(&s_full[0], 1);
-        mbar_init(&s_full[1], 1);
+        mbar_init(&s_full[0], 2);  // the copy warp (with the byte count) and the table warp
+        mbar_init(&s_full[1], 2);
         mbar_init(&s_empty[0], kConsumerWarps);
         mbar_init(&s_empty[1], kConsumerWarps);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     __syncthreads();
 
     if (warp == 0) {
-        // ---------------- producer ----------------
+        // ---------------- copy warp: the crop's source rows, one bulk copy per row ----------------
         int k = 0;
         for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
             const Plan p = plans[ci];
@@ -197,9 +203,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             }
             if (!p.fast) continue;
             const int b = k & 1;
-            // The consumers wait for the source rows and the tables, not for the padding: copies and tables first.
             if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
-            // TMA first: its latency overlaps the float64 table arithmetic below
             uint32_t bytes = 0;
             {
                 const uint8_t *src = p.src;
@@ -215,10 +219,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 #pragma unroll
                 for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
             }
+            if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
+            k++;
+        }
+        return;
+    }
+    if (warp == 1) {
+        // ---------------- table warp: OpenCV's axis tables, then two thirds of the padding ----------------
+        int k = 0;
+        for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
+            const Plan p = plans[ci];
+            if (!p.fast) continue;
+            const int b = k & 1;
+            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
             const bool x3 = __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane));
             if (lane == 0) s_x3[b] = x3 ? 1 : 0;
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
-            if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
+            if (lane == 0) mbar_arrive(&s_full[b]);
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
                                               kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
                                               kProducerChannels);
@@ -228,7 +245,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     }
 
     // ---------------- consumers ----------------
-    const int ct = (warp - 1) * 32 + lane;
+    const int ct = (warp - kProducerWarps) * 32 + lane;
     constexpr int kCT = kConsumerWarps * 32;
     int k = 0;
     for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {

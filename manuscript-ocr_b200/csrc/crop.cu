@@ -162,7 +162,6 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // horizontal row sums instead of 3G; per-pixel arithmetic and its order are unchanged.
 constexpr int kProducerWarps = 2;
 constexpr int kConsumerWarps = kThreads / 32 - kProducerWarps;
-constexpr int kProducerChannels = 3;  // output channels whose padding the table warp writes (the rest: consumers)
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
@@ -174,7 +173,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + 2 * kSrcBuf);  // [2 stages][kTabWords][iw + ih]
     const int tab_n = iw + ih;
     __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
-    __shared__ int s_x3[2];  // per stage: every x entry of the crop has at most 3 taps
+    // per stage, published by the table warp: the crop (index, -1 = no more crops) and what the consumers need of its
+    // plan, so that they never touch the plan array in global memory
+    __shared__ long long s_ci[2];
+    __shared__ int s_meta[2][8];  // nw, nh, y0, pitch, misalignment of row 0, its change per row, <= 3 x taps
 
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -222,6 +224,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
             k++;
         }
+        {  // the end-of-work signal (published by the table warp) needs this warp's arrival too
+            const int b = k & 1;
+            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
+            if (lane == 0) mbar_arrive(&s_full[b]);
+        }
         return;
     }
     if (warp == 1) {
@@ -233,13 +240,29 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             const int b = k & 1;
             if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
             const bool x3 = __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane));
-            if (lane == 0) s_x3[b] = x3 ? 1 : 0;
+            if (lane == 0) {
+                s_ci[b] = ci;
+                s_meta[b][0] = p.nw;
+                s_meta[b][1] = p.nh;
+                s_meta[b][2] = p.y0;
+                s_meta[b][3] = p.pitch;
+                s_meta[b][4] = (int)(reinterpret_cast<uintptr_t>(p.src) & 15);
+                s_meta[b][5] = p.stride & 15;  // per-row change of the 16-byte misalignment
+                s_meta[b][6] = x3 ? 1 : 0;
+            }
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
             if (lane == 0) mbar_arrive(&s_full[b]);
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
-                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
-                                              kProducerChannels);
+                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0, 3);
             k++;
+        }
+        {  // no more crops
+            const int b = k & 1;
+            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
+            if (lane == 0) {
+                s_ci[b] = -1;
+                mbar_arrive(&s_full[b]);
+            }
         }
         return;
     }
@@ -247,30 +270,24 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     // ---------------- consumers ----------------
     const int ct = (warp - kProducerWarps) * 32 + lane;
     constexpr int kCT = kConsumerWarps * 32;
-    int k = 0;
-    for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
-        const Plan *pg = plans + ci;
-        if (!pg->fast) continue;
+    for (int k = 0;; k++) {
         const int b = k & 1;
-        const int nw = pg->nw, nh = pg->nh, y0 = pg->y0;
-        const uint32_t pitch = (uint32_t)pg->pitch;
-        const uint32_t a0 = (uint32_t)(reinterpret_cast<uintptr_t>(pg->src) & 15);
-        const uint32_t sstep = (uint32_t)pg->stride & 15u;  // per-row change of the 16-byte misalignment
+        mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
+        const int64_t ci = s_ci[b];
+        if (ci < 0) break;
+        const int nw = s_meta[b][0], nh = s_meta[b][1], y0 = s_meta[b][2];
+        const uint32_t pitch = (uint32_t)s_meta[b][3], a0 = (uint32_t)s_meta[b][4], sstep = (uint32_t)s_meta[b][5];
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
         const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
-        // the padding of the remaining channel(s) is written by the consumers while the TMA copies are in flight
-        write_padding<kWriteF32, kWriteU8>(*pg, ih, iw, dstf, dstu, vec_ok, ct, kCT, kProducerChannels, 3);
-        mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
         // three x taps at most (shrink factor below 2, nearly every word box): a quarter of the horizontal work less
-        const bool bad = s_x3[b] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
-                                                                             tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct)
-                                 : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
-                                                                             tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct);
+        const bool bad = s_meta[b][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
+                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct)
+                                      : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
+                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct);
         if (bad) redo[ci] = 1;  // a table entry with more than 4 taps: the generic kernel redoes the crop
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[b]);
-        k++;
     }
 }
 

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     // per stage, published by the table warp: the crop (index, -1 = no more crops) and what the consumers need of its
     // plan, so that they never touch the plan array in global memory
     __shared__ long long s_ci[2];
-    __shared__ int s_meta[2][8];  // nw, nh, y0, pitch, misalignment of row 0, its change per row, <= 3 x taps
+    __shared__ int s_meta[2][8];  // nw, nh, y0, pitch, misalignment of row 0, its change per row, <= 3 x taps, strip height
 
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -249,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                 s_meta[b][4] = (int)(reinterpret_cast<uintptr_t>(p.src) & 15);
                 s_meta[b][5] = p.stride & 15;  // per-row change of the 16-byte misalignment
                 s_meta[b][6] = x3 ? 1 : 0;
+                s_meta[b][7] = strip_height<kConsumerWarps * 32>(p.nw, p.nh);
             }
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
             if (lane == 0) mbar_arrive(&s_full[b]);
@@ -277,14 +278,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         if (ci < 0) break;
         const int nw = s_meta[b][0], nh = s_meta[b][1], y0 = s_meta[b][2];
         const uint32_t pitch = (uint32_t)s_meta[b][3], a0 = (uint32_t)s_meta[b][4], sstep = (uint32_t)s_meta[b][5];
+        const int G = s_meta[b][7];
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
         const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
         // three x taps at most (shrink factor below 2, nearly every word box): a quarter of the horizontal work less
         const bool bad = s_meta[b][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
-                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct)
+                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct, G)
                                       : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
-                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct);
+                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct, G);
         if (bad) redo[ci] = 1;  // a table entry with more than 4 taps: the generic kernel redoes the crop
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[b]);

@@ -357,26 +357,30 @@ __device__ __forceinline__ bool build_tables(const Plan &p, uint32_t *tab, int t
 // destination rows share their boundary source row, so a strip needs ~(2G + 1) horizontal row sums instead of 3G;
 // per-pixel arithmetic and its order are those of resample_px's general branch.  Returns true when a table entry
 // had more than 4 taps (the caller redoes the crop with resample_px).
+// strip height (destination rows per thread item) that keeps kCT threads evenly loaded
+template <int kCT>
+__device__ __forceinline__ int strip_height(int nw, int nh)
+{
+    int G = 1, best = 0x7fffffff;
+    for (int g = 8; g >= 1; g >>= 1) {
+        const int items = ((nh + g - 1) / g) * nw;
+        const int cost = ((items + kCT - 1) / kCT) * (2 * g + 1);
+        if (cost < best) {
+            best = cost;
+            G = g;
+        }
+    }
+    return G;
+}
+
 template <bool kWriteF32, bool kWriteU8, int kCT, int kTaps>
 __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t stage_off, uint32_t pitch, uint32_t a0,
                                              uint32_t sstep, const uint32_t *tab, int tab_n, int ih, int iw, int nw,
-                                             int nh, int y0, float *dstf, uint8_t *dstu, int ct)
+                                             int nh, int y0, float *dstf, uint8_t *dstu, int ct, int G_in = 0)
 {
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
-    // strip height: keep the threads evenly loaded
-    int G = 1;
-    {
-        int best = 0x7fffffff;
-        for (int g = 8; g >= 1; g >>= 1) {
-            const int items = ((nh + g - 1) / g) * nw;
-            const int cost = ((items + kCT - 1) / kCT) * (2 * g + 1);
-            if (cost < best) {
-                best = cost;
-                G = g;
-            }
-        }
-    }
+    const int G = G_in > 0 ? G_in : strip_height<kCT>(nw, nh);
     const int nitems = ((nh + G - 1) / G) * nw;
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
     const float *tw = reinterpret_cast<const float *>(tab);

@@ -248,22 +248,27 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
             const int nw4 = (nw + 3) & ~3;
             const int top4 = y0 * iw / 4, bot4 = (ih - y0 - nh) * iw / 4, tail4 = (iw - nw4) / 4;
             const int fr = nw4 - nw;  // scalar fringe [nw, nw4)
-            for (int c = c_begin; c < c_end; c++) {
-                float4 *base4 = reinterpret_cast<float4 *>(dstf + (size_t)c * plane);
-                for (int i = tid; i < top4; i += nthreads) __stcs(base4 + i, one4);
-                float4 *bot = base4 + (size_t)(y0 + nh) * iw / 4;
-                for (int i = tid; i < bot4; i += nthreads) __stcs(bot + i, one4);
-                if (tail4 > 0) {
-                    const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
-                    for (int i = tid; i < nh * tail4; i += nthreads) {
-                        const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
-                        __stcs(reinterpret_cast<float4 *>(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw4) + k,
-                               one4);
-                    }
+            // the pasted rectangle sits at the same place in every channel: one index computation, a store per channel
+            float4 *top = reinterpret_cast<float4 *>(dstf);
+            float4 *bot = reinterpret_cast<float4 *>(dstf + (size_t)(y0 + nh) * iw);
+            const int plane4 = plane / 4;
+            for (int i = tid; i < top4; i += nthreads)
+                for (int c = c_begin; c < c_end; c++) __stcs(top + (size_t)c * plane4 + i, one4);
+            for (int i = tid; i < bot4; i += nthreads)
+                for (int c = c_begin; c < c_end; c++) __stcs(bot + (size_t)c * plane4 + i, one4);
+            if (tail4 > 0) {
+                const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
+                for (int i = tid; i < nh * tail4; i += nthreads) {
+                    const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
+                    float4 *at = reinterpret_cast<float4 *>(dstf + (size_t)(y0 + r) * iw + nw4) + k;
+                    for (int c = c_begin; c < c_end; c++) __stcs(at + (size_t)c * plane4, one4);
                 }
+            }
+            if (fr > 0) {
                 for (int i = tid; i < nh * fr; i += nthreads) {
                     const int r = i / fr, k = i - r * fr;
-                    __stcs(dstf + (size_t)c * plane + (size_t)(y0 + r) * iw + nw + k, one);
+                    float *at = dstf + (size_t)(y0 + r) * iw + nw + k;
+                    for (int c = c_begin; c < c_end; c++) __stcs(at + (size_t)c * plane, one);
                 }
             }
         } else {

@@ -696,10 +696,12 @@ __global__ void __launch_bounds__(256) nms_bin_scatter_kernel(const int32_t *__r
     }
 }
 
-// thread per regular cluster a: every b > a whose bbox overlaps a's becomes an (unevaluated) neighbour pair,
-// oriented hi -> lo by NMS priority.  b's home cell holds its min corner, which lies in
-// [a.min - (max bbox size of the page), a.max]; each grid row of that range is one contiguous span of the
-// cell-ordered arrays.  Hits are kept per thread and appended with ONE atomic per CTA (same-address atomics per
+// thread per regular cluster a: every b whose bbox overlaps a's and that a OWNS becomes an (unevaluated) neighbour
+// pair, oriented hi -> lo by NMS priority.  Of two overlapping boxes the one with the smaller (min x, index) owns the
+// pair: the other's min x then lies in [a.min x, a.max x], so the search needs no margin in x (it was the page's
+// largest box width, half of the cells walked), and every pair is still produced exactly once.  b's home cell holds
+// its min corner; in y it lies in [a.min y - (max bbox height of the page), a.max y]; each grid row of that range is
+// one contiguous span of the cell-ordered arrays.  Hits are kept per thread and appended with ONE atomic per CTA (same-address atomics per
 // hit serialise in L2 and cost more than the search itself).
 constexpr int kBinThreads = 256;
 constexpr int kMaxHits = 32;  // higher-index neighbours one cluster may have (overflow -> MS_FLAG_EDGE_OVERFLOW)
@@ -713,7 +715,7 @@ __global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int
     const float *ext = B.page_ext + (size_t)page * 8;
     const int32_t *coff = B.cell_off + (size_t)page * (kCells + 1);
     const int edge_cap = (page_off[page + 1] - p0) * B.ef;
-    const float ox = ext[0], oy = ext[1], sx = ext[2], sy = ext[3], mw = ext[4], mh = ext[5];
+    const float ox = ext[0], oy = ext[1], sx = ext[2], sy = ext[3], mh = ext[5];
     __shared__ int s_warp[kBinThreads / 32 + 1];
     __shared__ int s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -726,15 +728,16 @@ __global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int
         if (a < C && B.cl_irr[(size_t)p0 + a] == 0) {
             const float4 ba = B.cl_bbox[(size_t)p0 + a];
             sa = B.cl_score[(size_t)p0 + a];
-            const int cx0 = cell_coord(ba.x - mw, ox, sx), cx1 = cell_coord(ba.z, ox, sx);
+            // x: only boxes whose min x lies in [a.min x, a.max x] (see the ownership rule above) -- no max-width margin
+            const int cx0 = cell_coord(ba.x, ox, sx), cx1 = cell_coord(ba.z, ox, sx);
             const int cy0 = cell_coord(ba.y - mh, oy, sy), cy1 = cell_coord(ba.w, oy, sy);
             for (int cy = cy0; cy <= cy1; cy++) {
                 const int pos1 = coff[cy * kGrid + cx1 + 1];
                 for (int pos = coff[cy * kGrid + cx0]; pos < pos1; pos++) {
-                    const int b = B.sb_id[(size_t)p0 + pos];
-                    if (b <= a) continue;
                     const float4 o = B.sb_bbox[(size_t)p0 + pos];
-                    if (o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y) continue;
+                    if (o.x > ba.z || o.x < ba.x || o.y > ba.w || o.w < ba.y) continue;
+                    const int b = B.sb_id[(size_t)p0 + pos];
+                    if (o.x == ba.x && b <= a) continue;
                     if (cnt < kMaxHits)
                         hits[cnt++] = b;
                     else
@@ -785,15 +788,15 @@ __device__ __forceinline__ void walk_neighbours(const LanmsBuffers &B, int p0, i
     const float *ext = B.page_ext + (size_t)page * 8;
     const int32_t *coff = B.cell_off + (size_t)page * (kCells + 1);
     const float4 ba = B.cl_bbox[(size_t)p0 + a];
-    const int cx0 = cell_coord(ba.x - ext[4], ext[0], ext[2]), cx1 = cell_coord(ba.z, ext[0], ext[2]);
+    const int cx0 = cell_coord(ba.x, ext[0], ext[2]), cx1 = cell_coord(ba.z, ext[0], ext[2]);
     const int cy0 = cell_coord(ba.y - ext[5], ext[1], ext[3]), cy1 = cell_coord(ba.w, ext[1], ext[3]);
     for (int cy = cy0; cy <= cy1; cy++) {
         const int pos1 = coff[cy * kGrid + cx1 + 1];
         for (int pos = coff[cy * kGrid + cx0]; pos < pos1; pos++) {
-            const int b = B.sb_id[(size_t)p0 + pos];
-            if (b <= a) continue;
             const float4 o = B.sb_bbox[(size_t)p0 + pos];
-            if (o.x > ba.z || o.z < ba.x || o.y > ba.w || o.w < ba.y) continue;
+            if (o.x > ba.z || o.x < ba.x || o.y > ba.w || o.w < ba.y) continue;  // same ownership rule as the binned kernel
+            const int b = B.sb_id[(size_t)p0 + pos];
+            if (o.x == ba.x && b <= a) continue;
             f(b);
         }
     }

@@ -231,6 +231,38 @@ def test_lanms_hard_cases(ops):
     np.testing.assert_array_equal(keep, cpu.standard_nms(quads, b2[:, 8].astype(np.float64), 0.1, return_index=True))
 
 
+@pytest.mark.parametrize("thr", [0.0, 0.05, 0.2, 0.5, 0.8])
+def test_nms_pairs_around_the_threshold(ops, thr):
+    """The resolve step decides most pairs of regular quads by a shrink-and-contain bound before it clips
+    (csrc/lanms.cu iou_above_by_containment).  Pairs whose IoU lies on both sides of the threshold, close to it and
+    far from it, rotated and of unequal size, arranged so that the two boxes of a pair are never neighbours in the
+    x0 order (the merge scan leaves them alone and the NMS has to judge them): same rows as the oracle, bit for bit."""
+    rng = np.random.default_rng(int(thr * 100) + 5)
+    rows, cols = 24, 40
+    rect = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    boxes = []
+    for r in range(rows):
+        for c in range(cols):
+            w, h = rng.uniform(30, 60), rng.uniform(10, 20)
+            org = np.array([c * 90.0 + r * 3.7, r * 40.0])
+            a = org + rect * [w, h]
+            # second box: shifted / scaled so that the IoU is spread around thr (and sometimes far above it)
+            target = np.clip(thr + rng.uniform(-0.15, 0.15), 0.0, 0.98) if rng.random() < 0.7 else rng.uniform(0.6, 0.98)
+            shift = w * (1 - target) / (1 + target)  # IoU of two equal rectangles shifted along x
+            sc = rng.uniform(0.9, 1.1)
+            b = org + [shift, rng.uniform(-0.5, 0.5)] + rect * [w * sc, h * sc]
+            for qd in (a, b):
+                th = rng.uniform(-0.06, 0.06)
+                rot = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]])
+                ctr = qd.mean(0)
+                boxes.append(np.concatenate([((qd - ctr) @ rot.T + ctr).ravel(), [rng.uniform(0.3, 1.0)]]))
+    b = np.asarray(boxes, np.float32)
+    b = b[rng.permutation(len(b))]
+    got, want = ops.locality_aware_nms(b, thr), cpu.locality_aware_nms(b, thr)
+    assert 0 < len(want) < len(b)
+    np.testing.assert_array_equal(got, want)
+
+
 def test_expand_and_filters_vs_oracle(ops):
     for seed, page, words, orig in [(31, 640, 200, (900, 700)), (32, 1024, 600, (1024, 1024))]:
         score, geo, _ = synthdata.make_maps(seed, page, words)

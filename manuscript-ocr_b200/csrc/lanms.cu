@@ -344,7 +344,7 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
     const int p0 = page_off[page], p1 = page_off[page + 1];
     __shared__ int s_warp[33];
     __shared__ int s_h[kAcceptBatch], s_e[kAcceptBatch];
-    __shared__ int s_klast, s_nacc, s_merged, s_nv;
+    __shared__ int s_klast, s_nacc, s_merged;
     int32_t *hot_sorted = B.cl_cell + p0;  // scratch until the neighbour grid is built
     int32_t *acc_h = B.kept_list + p0, *acc_e = B.nb_cnt + p0, *acc_pm = B.sb_id + p0;
     if (threadIdx.x == 0) {
@@ -385,30 +385,34 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            int klast = s_klast, nacc = s_nacc, merged = s_merged, nv = 0;
-            for (int j = 0; j < nb; j++) {
-                const int h = s_h[j];
-                if (h > klast) {
-                    klast = s_e[j];
-                    acc_pm[nacc + nv] = merged;  // merged positions before this run
-                    merged += klast - h;
-                    s_h[nv] = h;                 // compacted in place (nv <= j)
-                    s_e[nv] = klast;
-                    nv++;
+            // The walk is one dependent chain; keep it to a compare and a select per position: the positions are
+            // read four ahead (nothing in the loop stores to shared memory, so the loads do not wait for the
+            // decisions) and an accepted run goes straight to global memory with stores nobody waits for.
+            int klast = s_klast, nacc = s_nacc, merged = s_merged;
+            for (int j = 0; j < nb; j += 4) {
+                int h[4], e[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const bool in = j + u < nb;
+                    h[u] = in ? s_h[j + u] : INT_MIN;  // never beyond klast
+                    e[u] = in ? s_e[j + u] : 0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (h[u] > klast) {
+                        klast = e[u];
+                        __stcg(acc_pm + nacc, merged);  // merged positions before this run
+                        __stcg(acc_h + nacc, h[u]);
+                        __stcg(acc_e + nacc, e[u]);
+                        merged += e[u] - h[u];
+                        nacc++;
+                    }
                 }
             }
             s_klast = klast;
             s_merged = merged;
-            s_nv = nv;
+            s_nacc = nacc;
         }
-        __syncthreads();
-        const int nacc = s_nacc, nv = s_nv;
-        for (int j = threadIdx.x; j < nv; j += kResolveThreads) {
-            acc_h[nacc + j] = s_h[j];
-            acc_e[nacc + j] = s_e[j];
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) s_nacc = nacc + nv;
         __syncthreads();
     }
     if (threadIdx.x == 0) {

@@ -34,10 +34,16 @@ __global__ void __launch_bounds__(kThreads) seg_hist_kernel(const uint32_t *__re
         for (int d = threadIdx.x; d < kRadix; d += kThreads) s_h[d] = 0;
         __syncthreads();
         const int base = tile * kTile;
-        for (int i = threadIdx.x; i < kTile; i += kThreads) {
-            const int idx = base + i;
-            if (idx < n) atomicAdd(&s_h[(keys[p0 + idx] >> shift) & 0xFF], 1);
+        // all of the thread's keys are requested before the first one is counted (one round trip, not eight)
+        uint32_t kk[kTile / kThreads];
+#pragma unroll
+        for (int u = 0; u < kTile / kThreads; u++) {
+            const int idx = base + u * kThreads + threadIdx.x;
+            kk[u] = idx < n ? keys[p0 + idx] : 0u;
         }
+#pragma unroll
+        for (int u = 0; u < kTile / kThreads; u++)
+            if (base + u * kThreads + threadIdx.x < n) atomicAdd(&s_h[(kk[u] >> shift) & 0xFF], 1);
         __syncthreads();
         int32_t *h = hist + ((size_t)page * tiles_max + tile) * kRadix;
         for (int d = threadIdx.x; d < kRadix; d += kThreads) h[d] = s_h[d];
@@ -62,7 +68,20 @@ __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *_
     __shared__ int s_cnt[kWarps][kRadix];  // per-warp digit counts, then running write cursors
     __shared__ int s_base[kRadix];         // first output slot of (digit, this tile) inside the page
     __shared__ int s_wsum[kWarps];
+    constexpr int kPerLane = kItemsPerWarp / 32;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+    // this lane's keys and values of the warp's strip: requested once, up front, together with the histogram reads
+    // below (the count and the ordered walk both use them; three dependent round trips to L2 become one)
+    uint32_t kk[kPerLane], vv[kPerLane];
+    {
+        const int wb = tile * kTile + warp * kItemsPerWarp;
+#pragma unroll
+        for (int u = 0; u < kPerLane; u++) {
+            const int idx = wb + u * 32 + lane;
+            kk[u] = idx < n ? keys[p0 + idx] : 0u;
+            vv[u] = idx < n ? vals[p0 + idx] : 0u;
+        }
+    }
     // digit d of this tile starts after every smaller digit of the whole page and digit d of the earlier tiles
     {
         const int d = threadIdx.x;  // kThreads == kRadix
@@ -89,10 +108,9 @@ __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *_
     for (int i = threadIdx.x; i < kWarps * kRadix; i += kThreads) (&s_cnt[0][0])[i] = 0;
     __syncthreads();
     const int wbase = tile * kTile + warp * kItemsPerWarp;
-    for (int i = lane; i < kItemsPerWarp; i += 32) {
-        const int idx = wbase + i;
-        if (idx < n) atomicAdd(&s_cnt[warp][(keys[p0 + idx] >> shift) & 0xFF], 1);
-    }
+#pragma unroll
+    for (int u = 0; u < kPerLane; u++)
+        if (wbase + u * 32 + lane < n) atomicAdd(&s_cnt[warp][(kk[u] >> shift) & 0xFF], 1);
     __syncthreads();
     for (int d = threadIdx.x; d < kRadix; d += kThreads) {
         int run = s_base[d];
@@ -105,12 +123,13 @@ __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *_
     }
     __syncthreads();
     // ordered walk; equal digits inside a 32-key group are ranked by lane
-    for (int i0 = 0; i0 < kItemsPerWarp; i0 += 32) {
-        const int idx = wbase + i0 + lane;
+#pragma unroll
+    for (int u = 0; u < kPerLane; u++) {
+        const int idx = wbase + u * 32 + lane;
         const bool live = idx < n;
         if (!__any_sync(0xffffffffu, live)) break;
-        const uint32_t k = live ? keys[p0 + idx] : 0;
-        const uint32_t v = live ? vals[p0 + idx] : 0;
+        const uint32_t k = kk[u];
+        const uint32_t v = vv[u];
         const int d = live ? (int)((k >> shift) & 0xFF) : -1 - lane;  // dead lanes match nobody
         const uint32_t peers = __match_any_sync(0xffffffffu, d);
         const int rank = __popc(peers & ((1u << lane) - 1u));

@@ -134,6 +134,65 @@ __device__ float np_pairwise_f32(const float *a, int n)
     }
 }
 
+// The same sum by a whole CTA, bit for bit: numpy's recursion splits the vector into leaves of at most 128 elements
+// and adds the leaf sums pairwise in a fixed tree.  Thread 0 lists the leaves (the split rule only), every leaf is
+// summed by its own thread with the 8-accumulator loop above, thread 0 adds the leaf sums in the recursion's order.
+// One thread summing 2000 areas twice out of global memory was half of east_finish_kernel's time.
+constexpr int kPwLeafCap = 1024;
+
+__device__ void pw_leaves(int off, int n, int *loff, int *llen, int &cnt)
+{
+    if (n <= 128) {
+        if (cnt < kPwLeafCap) {
+            loff[cnt] = off;
+            llen[cnt] = n;
+        }
+        cnt++;
+    } else {
+        int n2 = n / 2;
+        n2 -= n2 % 8;
+        pw_leaves(off, n2, loff, llen, cnt);
+        pw_leaves(off + n2, n - n2, loff, llen, cnt);
+    }
+}
+
+__device__ float pw_combine(int n, const float *lsum, int &cnt)
+{
+    if (n <= 128) return lsum[cnt++];
+    int n2 = n / 2;
+    n2 -= n2 % 8;
+    const float lo = pw_combine(n2, lsum, cnt);
+    const float hi = pw_combine(n - n2, lsum, cnt);
+    return lo + hi;
+}
+
+// called by every thread of the CTA; s_loff / s_llen / s_lsum hold kPwLeafCap entries each
+__device__ float np_pairwise_f32_cta(const float *a, int n, int *s_loff, int *s_llen, float *s_lsum, int *s_cnt,
+                                     float *s_out)
+{
+    if (threadIdx.x == 0) {
+        int c = 0;
+        pw_leaves(0, n, s_loff, s_llen, c);
+        *s_cnt = c;
+    }
+    __syncthreads();
+    const int c = *s_cnt;
+    if (c > kPwLeafCap) {
+        if (threadIdx.x == 0) *s_out = np_pairwise_f32(a, n);
+    } else {
+        for (int t = threadIdx.x; t < c; t += blockDim.x) s_lsum[t] = np_pairwise_f32(a + s_loff[t], s_llen[t]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            int k = 0;
+            *s_out = pw_combine(n, s_lsum, k);
+        }
+    }
+    __syncthreads();
+    const float r = *s_out;
+    __syncthreads();  // s_out and the leaf tables may be reused by the next call
+    return r;
+}
+
 __device__ __forceinline__ bool area_before(float aa, int ia, float ab, int ib)
 {
     // position in np.argsort(areas, kind="stable"): ascending, NaN last, ties by index
@@ -581,17 +640,16 @@ __global__ void __launch_bounds__(512) east_finish_kernel(const int32_t *__restr
     if (threadIdx.x == 0) s_apply = 0;
     __syncthreads();
     if (P.remove_area_anomalies && K1 > 0 && K1 > P.anomaly_min_box_count) {
-        __shared__ float s_mean;
-        if (threadIdx.x == 0) s_mean = np_pairwise_f32(karea, K1) / (float)K1;
-        __syncthreads();
-        const float mean32 = s_mean;
+        __shared__ int s_loff[kPwLeafCap], s_llen[kPwLeafCap], s_pwcnt;
+        __shared__ float s_lsum[kPwLeafCap], s_pwout;
+        const float mean32 = np_pairwise_f32_cta(karea, K1, s_loff, s_llen, s_lsum, &s_pwcnt, &s_pwout) / (float)K1;
         for (int i = threadIdx.x; i < K1; i += blockDim.x) {
             float d = karea[i] - mean32;
             kdev[i] = d * d;
         }
         __syncthreads();
+        const float var32 = np_pairwise_f32_cta(kdev, K1, s_loff, s_llen, s_lsum, &s_pwcnt, &s_pwout) / (float)K1;
         if (threadIdx.x == 0) {
-            float var32 = np_pairwise_f32(kdev, K1) / (float)K1;
             float std32 = sqrtf(var32);
             double stdv = (double)std32;
             if (stdv != 0.0) {

@@ -336,15 +336,15 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &tot
 // 4a. one CTA per page: the page's hot positions in order, the accepted runs among them (a run is accepted iff its
 //     head lies beyond the end of the last accepted run -- a sequential walk, done by one thread over shared memory),
 //     and for every accepted run the number of merged positions before it.  Clusters = positions outside the runs.
-constexpr int kAcceptBatch = 4096;  // hot positions walked per round out of shared memory
+constexpr int kAcceptBatch = 2048;  // hot positions walked per round out of shared memory
 
 __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
 {
     const int page = blockIdx.x;
     const int p0 = page_off[page], p1 = page_off[page + 1];
     __shared__ int s_warp[33];
-    __shared__ int s_h[kAcceptBatch], s_e[kAcceptBatch];
-    __shared__ int s_klast, s_nacc, s_merged;
+    __shared__ int s_h[kAcceptBatch], s_e[kAcceptBatch], s_sel[kAcceptBatch];
+    __shared__ int s_klast, s_nacc, s_merged, s_nv;
     int32_t *hot_sorted = B.cl_cell + p0;  // scratch until the neighbour grid is built
     int32_t *acc_h = B.kept_list + p0, *acc_e = B.nb_cnt + p0, *acc_pm = B.sb_id + p0;
     if (threadIdx.x == 0) {
@@ -376,6 +376,7 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
         nh += total;
     }
     __syncthreads();
+    int nacc = 0, merged = 0;  // CTA-uniform: accepted runs so far, merged positions so far
     for (int b0 = 0; b0 < nh; b0 += kAcceptBatch) {
         const int nb = min(kAcceptBatch, nh - b0);
         for (int j = threadIdx.x; j < nb; j += kResolveThreads) {
@@ -385,10 +386,10 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            // The walk is one dependent chain; keep it to a compare and a select per position: the positions are
-            // read four ahead (nothing in the loop stores to shared memory, so the loads do not wait for the
-            // decisions) and an accepted run goes straight to global memory with stores nobody waits for.
-            int klast = s_klast, nacc = s_nacc, merged = s_merged;
+            // The walk is one dependent chain and a lone warp issues an instruction every 5-6 cycles: it keeps to a
+            // compare, a select and one predicated store per position (which positions are accepted); everything
+            // else about an accepted run is computed by the whole CTA afterwards.  Positions are read four ahead.
+            int klast = s_klast, nv = 0;
             for (int j = 0; j < nb; j += 4) {
                 int h[4], e[4];
 #pragma unroll
@@ -401,20 +402,41 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
                 for (int u = 0; u < 4; u++) {
                     if (h[u] > klast) {
                         klast = e[u];
-                        __stcg(acc_pm + nacc, merged);  // merged positions before this run
-                        __stcg(acc_h + nacc, h[u]);
-                        __stcg(acc_e + nacc, e[u]);
-                        merged += e[u] - h[u];
-                        nacc++;
+                        s_sel[nv++] = j + u;
                     }
                 }
             }
             s_klast = klast;
-            s_merged = merged;
-            s_nacc = nacc;
+            s_nv = nv;
         }
         __syncthreads();
+        const int nv = s_nv;
+        // accepted runs of this batch, in order: head, end, merged positions before the run (exclusive running sum)
+        for (int t0 = 0; t0 < nv; t0 += kResolveThreads) {
+            const int t = t0 + threadIdx.x;
+            int h = 0, e = 0;
+            if (t < nv) {
+                const int j = s_sel[t];
+                h = s_h[j];
+                e = s_e[j];
+            }
+            int total;
+            const int before = block_excl_scan_1024(e - h, s_warp, total);
+            if (t < nv) {
+                acc_h[nacc + t] = h;
+                acc_e[nacc + t] = e;
+                acc_pm[nacc + t] = merged + before;
+            }
+            merged += total;
+        }
+        nacc += nv;
+        __syncthreads();  // s_h / s_e / s_sel are refilled by the next batch
     }
+    if (threadIdx.x == 0) {
+        s_nacc = nacc;
+        s_merged = merged;
+    }
+    __syncthreads();
     if (threadIdx.x == 0) {
         B.acc_count[page] = s_nacc;
         B.cl_count[page] = (p1 - p0) - s_merged;

@@ -1123,20 +1123,28 @@ __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restr
     __shared__ int s_warp[33];
     int32_t *kept = B.kept_list + p0;
     int run_base = 0;
-    for (int base = 0; base < C; base += 1024) {
-        int c = base + threadIdx.x;
-        int k = (c < C && B.state[p0 + c] == 1) ? 1 : 0;
+    // 8 consecutive clusters per thread and round: the state bytes of a round are independent loads in flight together
+    // and a 14k-cluster page needs two block scans instead of fourteen
+    for (int base = 0; base < C; base += 1024 * 8) {
+        const int c0 = base + threadIdx.x * 8;
+        uint32_t bits = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            if (c0 + k < C && B.state[p0 + c0 + k] == 1) bits |= 1u << k;
         int total;
-        int pos = block_excl_scan_1024(k, s_warp, total);
-        if (k) {
-            kept[run_base + pos] = c;
-            B.kept_key[p0 + run_base + pos] = desc_score_key(B.cl_score[p0 + c]);
+        int pos = run_base + block_excl_scan_1024(__popc(bits), s_warp, total);
+        while (bits) {
+            const int c = c0 + __ffs(bits) - 1;
+            bits &= bits - 1;
+            kept[pos] = c;
+            B.kept_key[p0 + pos] = desc_score_key(B.cl_score[p0 + c]);
             if (f32_scores) {
                 // LANMS cluster scores are float32 values: a 32-bit descending key for the large-page radix sort
                 const float sc = (float)B.cl_score[p0 + c];
-                B.keys[p0 + run_base + pos] = (sc != sc) ? 0xFFFFFFFFu : ~ms_orderable_f32(sc);
-                B.vals[p0 + run_base + pos] = (uint32_t)c;
+                B.keys[p0 + pos] = (sc != sc) ? 0xFFFFFFFFu : ~ms_orderable_f32(sc);
+                B.vals[p0 + pos] = (uint32_t)c;
             }
+            pos++;
         }
         run_base += total;
     }
@@ -1171,22 +1179,31 @@ __global__ void __launch_bounds__(1024) lanms_sort_emit_kernel(const int32_t *__
         s_key[i] = key;
     }
     __syncthreads();
+    // Bitonic network, one compare-exchange PAIR per thread and stage (pair pr -> element i: a zero bit inserted at
+    // log2 j), so no lane idles.  A page is one CTA on one SM and the sort is bound by that SM's issue rate, so
+    // instructions per stage are what counts.  Stages with j <= 32 stay inside the 64-element block a warp owns
+    // (pairs 32w .. 32w + 31): between two such stages a warp barrier is enough; any stage next to a wider one needs
+    // the CTA barrier.
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n; i += 1024) {
-                const int ixj = i ^ j;
-                if (ixj > i) {
-                    const uint64_t a = s_key[i], b = s_key[ixj];
-                    const bool up = (i & k) == 0;
-                    if ((a > b) == up) {
-                        s_key[i] = b;
-                        s_key[ixj] = a;
-                    }
+            const bool first = j == (k >> 1);
+            if (first ? j <= 32 : j <= 16)
+                __syncwarp();
+            else
+                __syncthreads();
+            for (int pr = threadIdx.x; pr < (n >> 1); pr += 1024) {
+                const int i = ((pr & ~(j - 1)) << 1) | (pr & (j - 1));
+                const int ixj = i | j;
+                const uint64_t a = s_key[i], b = s_key[ixj];
+                const bool up = (i & k) == 0;
+                if ((a > b) == up) {
+                    s_key[i] = b;
+                    s_key[ixj] = a;
                 }
             }
-            __syncthreads();
         }
     }
+    __syncthreads();
     for (int r = threadIdx.x; r < K; r += 1024) {
         const int c = (int)(s_key[r] & 0xffffffffu);
         float *row = out + ((size_t)page * cap + r) * 9;

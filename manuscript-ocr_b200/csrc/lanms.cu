@@ -1204,24 +1204,18 @@ __global__ void __launch_bounds__(1024) lanms_sort_emit_kernel(const int32_t *__
         }
     }
     __syncthreads();
-    for (int r = threadIdx.x; r < K; r += 1024) {
-        const int c = (int)(s_key[r] & 0xffffffffu);
-        float *row = out + ((size_t)page * cap + r) * 9;
-        const double *poly = B.cl_poly + (size_t)(p0 + c) * 8;
-#pragma unroll
-        for (int k2 = 0; k2 < 8; k2++) row[k2] = (float)poly[k2];  // lanms.py:207 astype(float32)
-        row[8] = (float)B.cl_score[p0 + c];
-    }
+    // the order only: the rows are gathered by lanms_emit_sorted_kernel, which has the whole GPU instead of one SM
+    for (int r = threadIdx.x; r < K; r += 1024) B.vals[p0 + r] = (uint32_t)(s_key[r] & 0xffffffffu);
 }
 
-// pages with more than kSortMax kept boxes: B.vals holds the cluster indices in output order after the radix sort
+// B.vals holds every page's kept cluster indices in output order (shared-memory sort, or the radix sort for pages
+// with more than kSortMax kept boxes): gather the rows
 __global__ void __launch_bounds__(256) lanms_emit_sorted_kernel(const int32_t *__restrict__ page_off, int cap,
                                                                 LanmsBuffers B, float *__restrict__ out,
                                                                 const int32_t *__restrict__ counts_out)
 {
     const int page = blockIdx.y;
     const int K = counts_out[page];
-    if (K <= kSortMax) return;
     const int p0 = page_off[page];
     for (int r = blockIdx.x * blockDim.x + threadIdx.x; r < K; r += gridDim.x * blockDim.x) {
         const int c = (int)B.vals[p0 + r];

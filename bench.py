@@ -45,6 +45,9 @@ OUT_H, OUT_W = 32, 128
 FALLBACK_HBM_GBS = 6650.0
 
 
+_REAL_STDOUT = None  # set when stdout's descriptor is redirected (multi-rank runs)
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -144,7 +147,7 @@ def run_reference(a):
         "cpu_baseline": {"value": value, "unit": "pages/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "pages/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT or sys.stdout, flush=True)
 
 
 # ---- clocks ----------------------------------------------------------------------------------------------------------
@@ -225,6 +228,12 @@ def run_b200(a):
         import torch.distributed as dist_mod
 
         dist = dist_mod
+        # stdout carries ONE JSON line: whatever libraries print to file descriptor 1 from here on (NCCL's version
+        # banner at communicator creation) goes to stderr; rank 0 writes the line to the real stdout at the end
+        global _REAL_STDOUT
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
 
     def barrier():
@@ -489,7 +498,7 @@ def run_b200(a):
         line["cpu_baseline"] = {"value": pps, "unit": "pages/s", "cores": 1, "kind": "port",
                                 "sample": f"{a.cpu_pages} pages of the same workload through the C oracle "
                                           f"(oracle/oracle.c), 1 thread, {dt:.1f} s"}
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_REAL_STDOUT or sys.stdout, flush=True)
     if dist is not None:
         dist.destroy_process_group()
 

@@ -119,6 +119,13 @@ MS_API int ms_standard_nms_host(ms_ctx *ctx, const double *polys, const double *
  * subj,clip (n,4,2) f64 -> iou (n) f64. */
 MS_API int ms_polygon_iou_host(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double *iou);
 
+/* TEST-ONLY (not a reference interface): the device predicates that let the NMS skip the float64 clip of lanms.py:80-96
+ * for a pair of quads.  out[i] bit 0 = both quads "regular" (convex, positively oriented, well conditioned); bit 1 =
+ * regular and IoU(subj, clip) > thr PROVEN by the shrink-and-contain bound.  tests/ assert that bit 1
+ * never contradicts the float64 IoU of the oracle. */
+MS_API int ms_test_iou_proved_host(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double thr,
+                            uint8_t *out);
+
 /* replaces expand_boxes, detectors/_east/utils.py:384 (called infer.py:340). */
 MS_API int ms_expand_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, double expand_w, double expand_h,
                          float *out);
@@ -230,8 +237,12 @@ MS_API int ms_page_batch_ragged(ms_ctx *ctx, const float *score, const float *ge
 
 /* Same path with HOST buffers (pinned or pageable): H2D of maps + pages, the batch, D2H of boxes,
  * counts, crop list and (optionally, if batch_f32_host != NULL) the crop batch.  When
- * batch_dev_out != NULL the crop batch stays on the device and its pointer is returned there
- * (as the reference leaves it on `self.device`, recognizers/_trba/__init__.py:288). */
+ * batch_dev_out != NULL the crop batch stays on the device (as the reference leaves it on `self.device`,
+ * recognizers/_trba/__init__.py:288):
+ *   *batch_dev_out != NULL on entry  -> a CALLER-OWNED device buffer of crops_cap crops; the batch is written there;
+ *   *batch_dev_out == NULL on entry  -> the batch is written to library-owned staging memory and its address is
+ *                                       returned; it is valid only until the NEXT call on this context (which may
+ *                                       overwrite or free it).  Prefer the caller-owned form. */
 MS_API int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages,
                        int n_pages, int map_h, int map_w, int img_h, int img_w, const ms_east_params *p,
                        int min_text_size, int out_h, int out_w, int cap_boxes, float *boxes_out,

@@ -20,8 +20,9 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "--fmad=false", "-std=c++17",
     "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
-    "-shared", "-cudart", "static",
 ]
+LINK_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "static"]
+OBJ_DIR = os.path.join(HERE, "build")
 
 
 def _nvcc():
@@ -29,6 +30,11 @@ def _nvcc():
         if cand and (os.path.sep not in cand or os.path.exists(cand)):
             return cand
     return "nvcc"
+
+
+def _headers():
+    return [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))] + \
+           [os.path.join(INCLUDE, "manuscript_b200.h"), __file__]
 
 
 def needs_build():
@@ -40,14 +46,25 @@ def needs_build():
 
 
 def build(force=False, verbose=False):
+    """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link."""
     if not force and not needs_build():
         return OUT
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-o", OUT, *[os.path.join(CSRC, s) for s in SOURCES]]
-    if verbose:
-        cmd.insert(1, "-Xptxas")
-        cmd.insert(2, "-v")
-        print(" ".join(cmd))
-    subprocess.run(cmd, check=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr_t = max(os.path.getmtime(h) for h in _headers())
+    jobs, objs = [], []
+    for src in SOURCES:
+        s, o = os.path.join(CSRC, src), os.path.join(OBJ_DIR, src[:-3] + ".o")
+        objs.append(o)
+        if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
+            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", "-o", o, s]
+            if verbose:
+                cmd[1:1] = ["-Xptxas", "-v"]
+                print(" ".join(cmd))
+            jobs.append((src, subprocess.Popen(cmd)))
+    failed = [src for src, p in jobs if p.wait() != 0]
+    if failed:
+        raise subprocess.CalledProcessError(1, f"nvcc -c {failed}")
+    subprocess.run([_nvcc(), *LINK_FLAGS, "-o", OUT, *objs], check=True)
     return OUT
 
 

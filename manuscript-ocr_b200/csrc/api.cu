@@ -529,7 +529,19 @@ static int page_batch_cached(ms_ctx *ctx, const float *score, const float *geo, 
     const long long nums[12] = {n_pages, map_h, map_w, img_h, img_w, min_text_size, out_h, out_w, cap_boxes,
                                 (long long)crops_cap, ctx->edge_factor, (long long)ctx->arena_bytes};
     memcpy(key.num, nums, sizeof(nums));
-    memcpy(&key.params, p, sizeof(ms_east_params));
+    // field by field: the caller's struct may carry indeterminate padding bytes, which must not take part in the key
+    key.params.score_thresh = p->score_thresh;
+    key.params.scale = p->scale;
+    key.params.quantization = p->quantization;
+    key.params.iou_threshold = p->iou_threshold;
+    key.params.expand_ratio_w = p->expand_ratio_w;
+    key.params.expand_ratio_h = p->expand_ratio_h;
+    key.params.target_size = p->target_size;
+    key.params.axis_aligned_output = p->axis_aligned_output;
+    key.params.remove_area_anomalies = p->remove_area_anomalies;
+    key.params.anomaly_sigma_threshold = p->anomaly_sigma_threshold;
+    key.params.anomaly_min_box_count = p->anomaly_min_box_count;
+    key.params.sort_reading_order = p->sort_reading_order;
     ms_graph_entry *e = nullptr;
     for (int i = 0; i < MS_GRAPH_SLOTS; i++)
         if (ctx->graphs[i].used && memcmp(&ctx->graphs[i].key, &key, sizeof(key)) == 0) e = &ctx->graphs[i];
@@ -780,6 +792,33 @@ extern "C" int ms_polygon_iou_host(ms_ctx *ctx, const double *subj, const double
     return MS_OK;
 }
 
+extern "C" int ms_test_iou_proved_host(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double thr,
+                                       uint8_t *out)
+{
+    MS_CTX(ctx);
+    if (n < 0 || (n > 0 && (!subj || !clip || !out))) {
+        ms_set_error("ms_test_iou_proved_host: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    if (n == 0) return MS_OK;
+    MS_TRY(ms_stage_reserve(ctx, 2 * al256((size_t)n * 64) + al256((size_t)n) + 1024));
+    ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
+    double *d_a = sb.take<double>((size_t)n * 8);
+    double *d_b = sb.take<double>((size_t)n * 8);
+    uint8_t *d_o = sb.take<uint8_t>((size_t)n);
+    if (!d_o) {
+        ms_set_error("ms_test_iou_proved_host: staging too small");
+        return MS_ERR_CAPACITY;
+    }
+    cudaStream_t st = ctx->own_stream;
+    MS_CUDA(cudaMemcpyAsync(d_a, subj, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_b, clip, (size_t)n * 64, cudaMemcpyHostToDevice, st));
+    MS_TRY(msk_iou_proved(ctx, d_a, d_b, n, thr, d_o, st));
+    MS_CUDA(cudaMemcpyAsync(out, d_o, (size_t)n, cudaMemcpyDeviceToHost, st));
+    MS_CUDA(cudaStreamSynchronize(st));
+    return MS_OK;
+}
+
 extern "C" int ms_expand_boxes_host(ms_ctx *ctx, const float *quads, int64_t n, double expand_w, double expand_h,
                                     float *out)
 {
@@ -969,6 +1008,8 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     }
     const bool want_crops = pages != nullptr && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
     const bool want_batch = want_crops && (batch_f32_host || batch_dev_out);
+    // *batch_dev_out != NULL on entry: a caller-owned device buffer of crops_cap crops that receives the batch
+    float *caller_batch = (want_batch && batch_dev_out) ? *batch_dev_out : nullptr;
     const size_t plane = (size_t)map_h * map_w;
     const size_t page_bytes = (size_t)img_h * img_w * 3;
     const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float);
@@ -986,7 +1027,7 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     size_t need = al256(n_pages * plane * 4) + (geo_mapped ? 256 : al256(n_pages * plane * 32)) +
                   al256((size_t)n_pages * cap_boxes * 36) + 2 * al256((size_t)n_pages * 4) + 4096;
     if (want_crops) need += al256(n_pages * page_bytes) + al256((size_t)crops_cap * 20) + 256;
-    if (want_batch) need += al256((size_t)crops_cap * one_f);
+    if (want_batch && !caller_batch) need += al256((size_t)crops_cap * one_f);
     MS_TRY(ms_stage_reserve(ctx, need));
     ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
     float *d_score = sb.take<float>(n_pages * plane);
@@ -997,7 +1038,7 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     uint8_t *d_pages = want_crops ? sb.take<uint8_t>(n_pages * page_bytes) : nullptr;
     int32_t *d_crops = want_crops ? sb.take<int32_t>((size_t)crops_cap * 5) : nullptr;
     int32_t *d_nc = want_crops ? sb.take<int32_t>(1) : nullptr;
-    float *d_batch = want_batch ? sb.take<float>((size_t)crops_cap * 3 * out_h * out_w) : nullptr;
+    float *d_batch = !want_batch ? nullptr : caller_batch ? caller_batch : sb.take<float>((size_t)crops_cap * 3 * out_h * out_w);
     if (!d_flags || (want_crops && !d_nc) || (want_batch && !d_batch)) {
         ms_set_error("ms_page_batch_host: staging too small");
         return MS_ERR_CAPACITY;
@@ -1183,11 +1224,12 @@ extern "C" int ms_page_batch_ragged_host(ms_ctx *ctx, const float *score, const 
         img_total += al256((size_t)page_hw[2 * i] * page_hw[2 * i + 1] * 3);
     }
     const bool want_batch = batch_f32_host || batch_dev_out;
+    float *caller_batch = batch_dev_out ? *batch_dev_out : nullptr;  // caller-owned device buffer (see ms_page_batch_host)
     const size_t plane = (size_t)map_h * map_w;
     const size_t one_f = (size_t)3 * out_h * out_w * sizeof(float);
     size_t need = al256(n_pages * plane * 4) + al256(n_pages * plane * 32) + al256((size_t)n_pages * cap_boxes * 36) +
                   4 * al256((size_t)n_pages * 8) + img_total + al256((size_t)crops_cap * 20) + 8192;
-    if (want_batch) need += al256((size_t)crops_cap * one_f);
+    if (want_batch && !caller_batch) need += al256((size_t)crops_cap * one_f);
     MS_TRY(ms_stage_reserve(ctx, need));
     ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
     float *d_score = sb.take<float>(n_pages * plane);
@@ -1199,7 +1241,7 @@ extern "C" int ms_page_batch_ragged_host(ms_ctx *ctx, const float *score, const 
     int32_t *d_hw = sb.take<int32_t>((size_t)n_pages * 2);
     int32_t *d_crops = sb.take<int32_t>((size_t)crops_cap * 5);
     int32_t *d_nc = sb.take<int32_t>(1);
-    float *d_batch = want_batch ? sb.take<float>((size_t)crops_cap * 3 * out_h * out_w) : nullptr;
+    float *d_batch = !want_batch ? nullptr : caller_batch ? caller_batch : sb.take<float>((size_t)crops_cap * 3 * out_h * out_w);
     uint8_t *d_img = sb.take<uint8_t>(img_total);
     if (!d_img || (want_batch && !d_batch)) {
         ms_set_error("ms_page_batch_ragged_host: staging too small");

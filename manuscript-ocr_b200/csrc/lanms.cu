@@ -1296,6 +1296,22 @@ __global__ void iou_pairs_kernel(const double *__restrict__ subj, const double *
     }
 }
 
+// test-only (ms_test_iou_proved_host): the two predicates the resolve kernel uses to skip the float64 clip, evaluated
+// by the device functions themselves.  bit 0: both quads regular (quad_regular_bbox); bit 1: regular and
+// iou_above_by_containment(a, b, thr) -- "IoU(a, b) > thr is proven".
+__global__ void iou_proved_kernel(const double *__restrict__ subj, const double *__restrict__ clip, int64_t n,
+                                  double thr, uint8_t *__restrict__ out)
+{
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        double a[8], b[8];
+        load_quad(subj + i * 8, a);
+        load_quad(clip + i * 8, b);
+        float4 bb;
+        const bool reg = quad_regular_bbox(a, bb) && quad_regular_bbox(b, bb);
+        out[i] = (uint8_t)((reg ? 1 : 0) | ((reg && iou_above_by_containment(a, b, thr)) ? 2 : 0));
+    }
+}
+
 // clusters given directly (standard_nms): every box is treated as irregular => exact all-pairs mode
 __global__ void nms_prepare_kernel(const double *__restrict__ polys, const double *__restrict__ scores, int n,
                                    LanmsBuffers B)
@@ -1505,6 +1521,17 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
         lanms_emit_kernel<<<dim3(gx, 1), kRankThreads, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx, nullptr);
         MS_LAUNCH_CHECK(ctx);
     }
+    return MS_OK;
+}
+
+int msk_iou_proved(ms_ctx *ctx, const double *subj, const double *clip, int64_t n, double thr, uint8_t *out,
+                   cudaStream_t st)
+{
+    if (n <= 0) return MS_OK;
+    int grid = (int)((n + 127) / 128);
+    if (grid > ctx->num_sms * 16) grid = ctx->num_sms * 16;
+    iou_proved_kernel<<<grid, 128, 0, st>>>(subj, clip, n, thr, out);
+    MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }
 

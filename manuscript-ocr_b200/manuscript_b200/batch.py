@@ -29,6 +29,11 @@ def shard_pages(n_pages, world_size, rank):
 
 @dataclass
 class PageBatchResult:
+    """Results of one batch.  They are VALID ONLY WHEN `flags` is all zero (see raise_for_flags): a page flagged
+    MS_FLAG_EDGE_OVERFLOW was resolved with suppression edges missing (boxes that should be gone are returned),
+    MS_FLAG_CAND_OVERFLOW means rows were truncated at cap_boxes, MS_FLAG_INDEX_ERROR is where the reference raises
+    IndexError (utils.py:370).  The tensors are owned by the PageBatch runner and are overwritten by its next call of
+    the same kind and page count: clone() what has to outlive it."""
     boxes: object        # (P, cap_boxes, 9) f32: rows [0, box_counts[p]) are page p's final boxes
     box_counts: object   # (P,) int32
     crops: object        # (crops_cap, 5) int32 rows [page, x1, y1, x2, y2), first n_crops valid
@@ -39,13 +44,15 @@ class PageBatchResult:
     def page_boxes(self, p):
         return self.boxes[p, : int(self.box_counts[p])]
 
+    def flags_host(self):
+        """The per-page flags as a numpy array (device results: one small D2H copy, synchronises the stream)."""
+        f = self.flags
+        return f.cpu().numpy() if hasattr(f, "cpu") else np.asarray(f)
 
-class _DeviceArray:
-    """Minimal __cuda_array_interface__ holder: lets torch view library-owned device memory without a copy."""
-
-    def __init__(self, ptr, shape, typestr="<f4"):
-        self.__cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
-                                         "data": (int(ptr), False), "version": 2, "strides": None}
+    def raise_for_flags(self):
+        """IndexError / CABIError exactly as the *_host entry points raise them; returns self when all pages are clean."""
+        _raise_for_flags(self.flags_host())
+        return self
 
 
 def _raise_for_flags(flags):
@@ -100,9 +107,22 @@ class PageBatch:
             self._bufs[key] = b
         return b
 
-    def run(self, score, geo, pages=None):
+    def run(self, score, geo, pages=None, sync=False):
         """score (P,H,W) or (P,1,H,W) f32, geo (P,8,H,W) f32, pages (P,IH,IW,3) u8 -- CUDA tensors on this
-        runner's device.  Enqueues the whole path on the current stream and returns device tensors."""
+        runner's device.  Enqueues the whole path on the current stream and returns device tensors.
+
+        sync=False (default): nothing is read back; the results are valid only if `result.flags` is all zero --
+        call result.raise_for_flags() (one small D2H copy) before trusting them.
+        sync=True: reads the flags, grows the NMS neighbour-pair capacity and runs again on MS_FLAG_EDGE_OVERFLOW
+        (the policy of the *_host entry points) and raises IndexError / CABIError for the other flags."""
+        if sync:
+            while True:
+                res = self.run(score, geo, pages, sync=False)
+                f = int(np.bitwise_or.reduce(res.flags_host().reshape(-1))) if len(res.flags) else 0
+                if (f & MS_FLAG_EDGE_OVERFLOW) and not (f & (MS_FLAG_INDEX_ERROR | MS_FLAG_CAND_OVERFLOW)) \
+                        and self.ctx.grow_edge_factor():
+                    continue
+                return res.raise_for_flags()
         torch = self.torch
         if score.dim() == 4:
             score = score[:, 0]
@@ -128,10 +148,18 @@ class PageBatch:
                 b["flags"].data_ptr(), C.c_void_p(stream)))
         return PageBatchResult(b["boxes"], b["counts"], b["crops"], b["n_crops"], b["batch"], b["flags"])
 
-    def run_ragged(self, score, geo, pages):
+    def run_ragged(self, score, geo, pages, sync=False):
         """As run(), for page images of their own sizes: `pages` is a list of P CUDA uint8 tensors (H_i, W_i, 3) -- the
         original images, while the maps come from the detector's fixed target_size.  Boxes are scaled to each page's
-        size and crops are cut from its pixels (EAST.predict + Pipeline.predict semantics)."""
+        size and crops are cut from its pixels (EAST.predict + Pipeline.predict semantics).  `sync` as in run()."""
+        if sync:
+            while True:
+                res = self.run_ragged(score, geo, pages, sync=False)
+                f = int(np.bitwise_or.reduce(res.flags_host().reshape(-1))) if len(res.flags) else 0
+                if (f & MS_FLAG_EDGE_OVERFLOW) and not (f & (MS_FLAG_INDEX_ERROR | MS_FLAG_CAND_OVERFLOW)) \
+                        and self.ctx.grow_edge_factor():
+                    continue
+                return res.raise_for_flags()
         torch = self.torch
         if score.dim() == 4:
             score = score[:, 0]
@@ -173,7 +201,7 @@ class PageBatch:
         ptrs = (C.c_void_p * P)(*[im.ctypes.data for im in imgs])
         hw = np.array([[im.shape[0], im.shape[1]] for im in imgs], np.int32)
         h = self._host_bufs(P)
-        dev_batch = C.c_void_p()
+        dev_batch = C.c_void_p(h["batch"].data_ptr() if self.want_batch else None)
         rc = self.ctx.lib.ms_page_batch_ragged_host(
             self.ctx.handle, s.ctypes.data, g.ctypes.data, ptrs, hw.ctypes.data, P, H, W, C.byref(self.params),
             self.min_text_size, self.out_h, self.out_w, self.cap_boxes, h["boxes"].data_ptr(), h["counts"].data_ptr(),
@@ -181,11 +209,8 @@ class PageBatch:
             C.byref(dev_batch) if self.want_batch else None, h["flags"].data_ptr())
         if check_flags or rc not in (0, -3, -4):
             check(rc)
-        batch = None
         n_crops = int(h["n_crops"][0])
-        if self.want_batch and dev_batch.value and n_crops > 0:
-            batch = torch.as_tensor(_DeviceArray(dev_batch.value, (n_crops, 3, self.out_h, self.out_w)),
-                                    device=self.device)
+        batch = h["batch"][:n_crops] if self.want_batch and n_crops > 0 else None
         return PageBatchResult(h["boxes"].numpy(), h["counts"].numpy(), h["crops"].numpy(), h["n_crops"].numpy(),
                                batch, h["flags"].numpy())
 
@@ -203,6 +228,9 @@ class PageBatch:
                 crops=torch.zeros((cap, 5), dtype=torch.int32, **pin),
                 n_crops=torch.zeros((1,), dtype=torch.int32, **pin),
                 flags=torch.zeros((n_pages,), dtype=torch.int32, **pin),
+                # the crop batch stays on the device; the runner owns it (never freed under a live view)
+                batch=(torch.empty((cap, 3, self.out_h, self.out_w), dtype=torch.float32, device=self.device)
+                       if self.want_batch else None),
                 cap=cap,
             )
             self._host[n_pages] = h
@@ -210,7 +238,12 @@ class PageBatch:
 
     def run_host(self, score, geo, pages=None, check_flags=True):
         """numpy arrays or (pinned) CPU torch tensors of the shapes of run().  Copies in, runs, copies the
-        boxes / counts / crop list back and synchronises (ms_page_batch_host)."""
+        boxes / counts / crop list back and synchronises (ms_page_batch_host).  On MS_FLAG_EDGE_OVERFLOW the library
+        grows the NMS pair capacity and runs again; other flags raise (check_flags=False returns them instead).
+
+        Lifetime: `result.batch` is a view of a device tensor this runner owns and reuses -- it stays valid memory for
+        the runner's life, but the next run_host call with the same page count overwrites it (clone() to keep it);
+        the numpy results are views of the runner's pinned host buffers with the same rule."""
         torch = self.torch
 
         def as_np(a, dtype):
@@ -235,7 +268,7 @@ class PageBatch:
             assert pg.shape[0] == P and pg.shape[3] == 3
             img_h, img_w = pg.shape[1], pg.shape[2]
         h = self._host_bufs(P)
-        dev_batch = C.c_void_p()
+        dev_batch = C.c_void_p(h["batch"].data_ptr() if self.want_batch else None)
         lib = self.ctx.lib
         rc = lib.ms_page_batch_host(
             self.ctx.handle, s.ctypes.data, g.ctypes.data, pg.ctypes.data if pg is not None else None, P, H, W,
@@ -246,11 +279,7 @@ class PageBatch:
             check(rc)
         elif rc not in (0, -3, -4):
             check(rc)
-        batch = None
         n_crops = int(h["n_crops"][0])
-        if self.want_batch and dev_batch.value and n_crops > 0:
-            # the crop batch stays on the device (library-owned staging, valid until the next call on this runner)
-            batch = torch.as_tensor(_DeviceArray(dev_batch.value, (n_crops, 3, self.out_h, self.out_w)),
-                                    device=self.device)
+        batch = h["batch"][:n_crops] if self.want_batch and n_crops > 0 else None
         return PageBatchResult(h["boxes"].numpy(), h["counts"].numpy(), h["crops"].numpy(), h["n_crops"].numpy(),
                                batch, h["flags"].numpy())

@@ -37,6 +37,8 @@ def lib():
         L.orc_polygon_intersection.argtypes = [_f64p, C.c_int, _f64p, C.c_int, _f64p]
         L.orc_polygon_iou.restype = C.c_double
         L.orc_polygon_iou.argtypes = [_f64p, _f64p]
+        L.orc_polygon_iou_batch.restype = None
+        L.orc_polygon_iou_batch.argtypes = [_f64p, _f64p, C.c_longlong, _f64p]
         L.orc_should_merge.restype = C.c_int
         L.orc_should_merge.argtypes = [_f64p, _f64p, C.c_double]
         L.orc_normalize_polygon.restype = None
@@ -111,6 +113,16 @@ def polygon_intersection(poly1, poly2):
 
 def polygon_iou(poly1, poly2):
     return float(lib().orc_polygon_iou(_poly(poly1), _poly(poly2)))
+
+
+def polygon_iou_batch(polys1, polys2):
+    """(n,4,2) x (n,4,2) -> (n,) f64, lanms.py:80-91 per pair."""
+    a = np.ascontiguousarray(polys1, dtype=np.float64).reshape(-1, 8)
+    b = np.ascontiguousarray(polys2, dtype=np.float64).reshape(-1, 8)
+    assert a.shape == b.shape
+    out = np.empty(len(a), np.float64)
+    lib().orc_polygon_iou_batch(a, b, len(a), out)
+    return out
 
 
 def should_merge(poly1, poly2, iou_threshold):

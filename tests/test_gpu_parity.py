@@ -409,3 +409,91 @@ def test_quad_crop_vs_oracle(ops, out_hw):
     # patch alone, larger than one launch wave of the single-quad kernel
     big = np.array([20, 30, 660, 60, 650, 360, 15, 330], np.float32)
     np.testing.assert_array_equal(ops.warp_quad(page, big, "replicate"), cpu.warp_quad(page, big, "replicate"))
+
+
+# ---- the NMS shortcut predicates themselves (test-only C-ABI entry ms_test_iou_proved_host) ---------------------
+def _rot(q, th, ctr=None):
+    ctr = q.mean(1, keepdims=True) if ctr is None else ctr
+    rot = np.stack([np.stack([np.cos(th), -np.sin(th)], -1), np.stack([np.sin(th), np.cos(th)], -1)], -2)
+    return np.einsum("nij,nkj->nki", rot, q - ctr) + ctr
+
+
+def _predicate_pairs(rng, n, thr):
+    """Four families of quad pairs, n each, (n,4,2) float64, positively oriented unless stated."""
+    rect = np.array([[0, 0], [1, 0], [1, 1], [0, 1]], float)
+    out = []
+    # A: unrelated sizes / shifts / rotations anywhere on pages up to 16384 px
+    w, h = rng.uniform(4, 400, (n, 1, 1)), rng.uniform(3, 120, (n, 1, 1))
+    wh = np.concatenate([w, h], axis=2)
+    org = rng.uniform(0, 16384, (n, 1, 2))
+    a = rect[None] * wh + org + rng.normal(0, 0.02, (n, 4, 2)) * wh
+    frac = rng.uniform(-1.0, 1.0, (n, 1, 2)) * rng.choice([0.02, 0.2, 0.6, 1.0], (n, 1, 1))
+    b = rect[None] * wh * rng.uniform(0.5, 1.6, (n, 1, 1)) + org + frac * wh + rng.normal(0, 0.02, (n, 4, 2)) * wh
+    out.append((_rot(a, rng.uniform(-0.4, 0.4, n)), _rot(b, rng.uniform(-0.4, 0.4, n))))
+    # B: slivers -- parallelograms whose corner angle has |sin| between 3e-4 and 5e-3 (the regularity bound is 1e-3),
+    #    and edges between 3e-4 and 5e-3 px (bound 1e-3); the partner is the same quad moved a little
+    s = 10.0 ** rng.uniform(-3.5, -2.3, n)
+    L = rng.uniform(10, 300, n)
+    H = np.where(rng.random(n) < 0.5, rng.uniform(5, 60, n), 10.0 ** rng.uniform(-3.5, -2.3, n))
+    ang = np.arcsin(np.clip(s, 0, 1)) * np.where(rng.random(n) < 0.7, 1.0, 300.0)  # some clearly regular
+    u = np.stack([L, np.zeros(n)], -1)
+    v = np.stack([H * np.cos(ang), H * np.sin(ang)], -1)
+    org = rng.uniform(0, 16384, (n, 2))
+    a = np.stack([org, org + u, org + u + v, org + v], axis=1)
+    b = a + rng.normal(0, 1.0, (n, 1, 2)) * 10.0 ** rng.uniform(-4, 0.5, (n, 1, 1))
+    th = rng.uniform(-3.1, 3.1, n)
+    out.append((_rot(a, th), _rot(b, th, a.mean(1, keepdims=True))))
+    # C: candidates of one word -- the same quad plus decode noise, at large coordinates
+    w, h = rng.uniform(20, 300, (n, 1, 1)), rng.uniform(8, 80, (n, 1, 1))
+    wh = np.concatenate([w, h], axis=2)
+    org = rng.uniform(0, 16384, (n, 1, 2))
+    a = _rot(rect[None] * wh + org, rng.uniform(-0.1, 0.1, n))
+    b = a + rng.normal(0, 1.0, (n, 4, 2)) * 10.0 ** rng.uniform(-2, 0.7, (n, 1, 1))
+    out.append((a, b))
+    # D: IoU steered to the threshold: equal rectangles shifted along x by w(1-t)/(1+t), t = thr +- tiny
+    w, h = rng.uniform(20, 300, (n, 1, 1)), rng.uniform(8, 80, (n, 1, 1))
+    wh = np.concatenate([w, h], axis=2)
+    t = np.clip(thr + rng.normal(0, 1.0, n) * 10.0 ** rng.uniform(-6, -1, n), 1e-9, 0.999)
+    shift = w[:, 0, 0] * (1 - t) / (1 + t)
+    org = rng.uniform(0, 16384, (n, 1, 2))
+    a = rect[None] * wh + org
+    b = a + np.stack([shift, np.zeros(n)], -1)[:, None, :]
+    th = rng.uniform(-0.2, 0.2, n)
+    out.append((_rot(a, th), _rot(b, th, a.mean(1, keepdims=True))))  # one rigid motion for the pair
+    return out
+
+
+@pytest.mark.parametrize("thr", [0.0, 0.2, 0.8])
+def test_containment_predicate_on_the_device(ops, thr):
+    """csrc/lanms.cu iou_above_by_containment / quad_regular_bbox, evaluated BY THE DEVICE FUNCTIONS on 1.4 million
+    pairs per threshold (coordinates up to 16384, slivers on both sides of the 1e-3 regularity bounds, same-word
+    candidates, IoU steered onto the threshold): "proven above" never contradicts the oracle's float64
+    Sutherland-Hodgman IoU (lanms.py:80-96), and the shortcut still decides most same-word pairs."""
+    import ctypes as C
+
+    from manuscript_b200._cabi import check, default_context
+
+    rng = np.random.default_rng(int(thr * 100) + 77)
+    n = 350_000
+    ctx = default_context()
+    total = proved_total = 0
+    for fam, (a, b) in zip("ABCD", _predicate_pairs(rng, n, thr)):
+        a, b = np.ascontiguousarray(a), np.ascontiguousarray(b)
+        out = np.zeros(len(a), np.uint8)
+        check(ctx.lib.ms_test_iou_proved_host(ctx.handle, a.ctypes.data, b.ctypes.data, len(a), float(thr),
+                                              out.ctypes.data))
+        iou = cpu.polygon_iou_batch(a, b)
+        regular, proved = (out & 1) != 0, (out & 2) != 0
+        assert not np.any(proved & ~regular), fam
+        bad = proved & ~(iou > thr)
+        assert not bad.any(), (fam, thr, int(bad.sum()), a[bad][:1], b[bad][:1], iou[bad][:1])
+        if fam == "B":  # both sides of the regularity bound are present
+            assert 0.05 < regular.mean() < 0.95, regular.mean()
+        if fam == "C" and thr < 0.5:  # (for thr >= ~0.74 the bound would need lam^2 >= 0.9 and is never tried)
+            clear = iou > min(0.97, thr + 0.4 * (1 - thr) + 0.1)
+            assert clear.sum() > 1000 and proved[clear].mean() > 0.6, (clear.sum(), proved[clear].mean())
+        if fam == "D":  # on the threshold the bound must stay silent (it promises a 6 % margin)
+            assert not np.any(proved & (iou <= thr * 1.02 + 1e-12))
+        total += len(a)
+        proved_total += int(proved.sum())
+    assert total >= 1_000_000 and (proved_total > 100_000 or thr >= 0.5)

@@ -168,6 +168,14 @@ MS_API int ms_warp_quad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int im
  * DEVICE entry points: a batch of pages, stream-ordered, no host synchronisation.
  * ------------------------------------------------------------------------------------------- */
 
+/* replaces the input preparation of EAST.predict, detectors/_east/infer.py:301-305: cv2.resize(img, (T, T))
+ * [INTER_LINEAR on uint8, aspect not preserved] -> ToTensor (x / 255) -> Normalize(0.5, 0.5).  page (img_h,img_w,3)
+ * u8 RGB on the device -> out_f32 (3,target_h,target_w) f32 (the network input) and/or out_u8 (target_h,target_w,3)
+ * (the resized image itself; either may be NULL).  With it the page crosses PCIe once: the original is uploaded,
+ * the detector input is made on the device, and the crops are cut from the same upload. */
+MS_API int ms_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, int target_h, int target_w,
+                      float *out_f32, uint8_t *out_u8, void *stream);
+
 /* utils.py:328 for n_pages maps.  score (n_pages,map_h,map_w), geo (n_pages,8,map_h,map_w).
  * quads_out (n_pages*cap_per_page,9); counts (n_pages) int32; flags (n_pages) int32 (OR-ed). */
 MS_API int ms_decode_quads(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int map_h, int map_w,

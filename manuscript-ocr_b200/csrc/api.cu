@@ -405,10 +405,17 @@ extern "C" int ms_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_pages
         ms_set_error("ms_crop_resize_pad: NULL pointer");
         return MS_ERR_INVALID;
     }
-    MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(crops_cap)));
+    MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(crops_cap, n_pages)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     return msk_crop(ctx, pages, n_pages, img_h, img_w, crops, n_crops, nullptr, crops_cap, out_h, out_w, batch_f32,
                     canvas_u8, bump, (cudaStream_t)stream);
+}
+
+extern "C" int ms_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, int target_h, int target_w,
+                                 float *out_f32, uint8_t *out_u8, void *stream)
+{
+    MS_CTX(ctx);
+    return msk_detector_input(ctx, page, img_h, img_w, target_h, target_w, out_f32, out_u8, (cudaStream_t)stream);
 }
 
 // candidate capacity per page that can never overflow: one row per quantisation cell (utils.py:347-356)
@@ -420,7 +427,7 @@ static int cand_cap(int map_h, int map_w, int q)
 }
 
 static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap, int ef,
-                                 int cap_boxes)
+                                 int cap_boxes, int total_pages)
 {
     size_t fixed = 2 * al256((size_t)n_pages * cap_c * 9 * sizeof(float)) + 2 * al256((size_t)n_pages * sizeof(int32_t));
     size_t stage = msk_decode_scratch(n_pages, map_h, map_w, q);
@@ -432,7 +439,7 @@ static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int c
     if (s2 > stage) stage = s2;
     s2 = msk_reading_order_scratch(n_pages, cap_boxes);
     if (s2 > stage) stage = s2;
-    s2 = msk_crop_scratch(crops_cap);
+    s2 = msk_crop_scratch(crops_cap, total_pages);
     if (s2 > stage) stage = s2;
     // reading order keeps the unsorted boxes and the order next to the candidates for the rest of the call
     fixed += al256((size_t)n_pages * cap_boxes * 36) + al256((size_t)n_pages * cap_boxes * 4) + 512;
@@ -457,7 +464,7 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
     const bool want_crops = (pages_all != nullptr || ragged) && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
     const int q = p->quantization < 1 ? 1 : p->quantization;
     const int cap_c = cand_cap(map_h, map_w, q);
-    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor, cap_boxes)));
+    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor, cap_boxes, total_pages)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates
     float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
@@ -968,7 +975,7 @@ extern "C" int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img
         ms_rects_to_crops_kernel<<<grid, 256, 0, st>>>(d_rects, n, d_crops, d_n);
         MS_LAUNCH_CHECK(ctx);
     }
-    MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(n)));
+    MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(n, 1)));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     MS_TRY(msk_crop(ctx, d_page, 1, img_h, img_w, d_crops, d_n, nullptr, n, out_h, out_w, d_f, d_u, bump, st));
     if (batch_f32) MS_CUDA(cudaMemcpyAsync(batch_f32, d_f, (size_t)n * one_f, cudaMemcpyDeviceToHost, st));

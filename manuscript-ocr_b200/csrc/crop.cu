@@ -37,7 +37,9 @@ namespace {
 constexpr int kThreads = 224;   // copy warp + table/padding warp + 5 consumer warps; 4 CTAs per SM
 constexpr int kCtasPerSm = 4;
 constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
-constexpr int kSrcBuf = 24 * 1024;  // bytes per staging buffer (two per CTA)
+constexpr int kSrcBuf = 24 * 1024;  // largest staged crop (bytes); the staging ring of a CTA holds at least one
+constexpr int kSlots = 3;       // crops in flight per CTA (ring slots: metadata + tables per slot, bytes from the ring)
+constexpr int kBandsY = 64, kCellsX = 8;  // work-list buckets per page: (row band, x cell)
 
 // Pages are either one (n_pages, img_h, img_w, 3) tensor, or -- page_ptrs != NULL -- separate images of their own
 // sizes: page_ptrs[p] -> (page_hw[2p], page_hw[2p+1], 3) bytes.
@@ -123,14 +125,24 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 
 
 // plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
-// critical path of the persistent resampling kernel
+// critical path of the persistent resampling kernel.  Fast crops are also counted into their work-list bucket
+// (page, row band, x cell): the persistent kernel walks the crops in bucket order, so that overlapping word boxes are
+// resampled within microseconds of each other and their shared source rows come out of L2 instead of DRAM.
+__device__ __forceinline__ int crop_bucket(const Plan &p, const int32_t *page_hw, int img_h, int img_w, int n_pages)
+{
+    const int H = page_hw ? page_hw[2 * p.page] : img_h, W = page_hw ? page_hw[2 * p.page + 1] : img_w;
+    const int by = min(kBandsY - 1, (int)(((int64_t)p.y1 * kBandsY) / max(H, 1)));
+    const int bx = min(kCellsX - 1, (int)(((int64_t)p.x1 * kCellsX) / max(W, 1)));
+    return (min(p.page, n_pages - 1) * kBandsY + by) * kCellsX + bx;
+}
+
 __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restrict__ pages,
                                                         const uint8_t *const *__restrict__ page_ptrs,
                                                         const int32_t *__restrict__ page_hw, int n_pages, int img_h,
                                                         int img_w, const int32_t *__restrict__ crops,
                                                         const int32_t *__restrict__ n_crops_dev,
                                                         const int32_t *__restrict__ range, int64_t crops_cap, int ih,
-                                                        int iw, Plan *__restrict__ plans)
+                                                        int iw, Plan *__restrict__ plans, int32_t *__restrict__ hist)
 {
     int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -140,6 +152,65 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
         Plan p;
         make_plan(crops + i * 5, n_pages, img_h, img_w, ih, iw, pages, page_ptrs, page_hw, p);
         plans[i] = p;
+        if (p.fast) atomicAdd(&hist[crop_bucket(p, page_ptrs ? page_hw : nullptr, img_h, img_w, n_pages)], 1);
+    }
+}
+
+// exclusive scan of the bucket counts (one CTA); hist becomes the buckets' write cursors, *n_work the number of fast crops
+__global__ void __launch_bounds__(1024) crop_bucket_scan_kernel(int32_t *__restrict__ hist, int n_buckets,
+                                                                int32_t *__restrict__ n_work)
+{
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    const int per = (n_buckets + 1023) / 1024;
+    const int lo = min(n_buckets, (int)threadIdx.x * per), hi = min(n_buckets, lo + per);
+    int sum = 0;
+    for (int i = lo; i < hi; i++) sum += hist[i];
+    int incl = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= o) wi += v;
+        }
+        s_warp[lane] = wi - w;
+        if (lane == 31) *n_work = wi;
+    }
+    __syncthreads();
+    int run = s_warp[warp] + incl - sum;
+    for (int i = lo; i < hi; i++) {
+        const int c = hist[i];
+        hist[i] = run;
+        run += c;
+    }
+}
+
+// work[cursor of the crop's bucket ++] = crop index (order inside a bucket is arbitrary: it only shapes the schedule)
+__global__ void __launch_bounds__(256) crop_bucket_scatter_kernel(const Plan *__restrict__ plans,
+                                                                  const int32_t *__restrict__ page_hw, int n_pages,
+                                                                  int img_h, int img_w,
+                                                                  const int32_t *__restrict__ n_crops_dev,
+                                                                  const int32_t *__restrict__ range, int64_t crops_cap,
+                                                                  int32_t *__restrict__ cursors, int32_t *__restrict__ work)
+{
+    int64_t begin = range ? range[0] : 0;
+    int64_t n_crops = range ? range[1] : *n_crops_dev;
+    if (n_crops > crops_cap) n_crops = crops_cap;
+    for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_crops;
+         i += (int64_t)gridDim.x * blockDim.x) {
+        const Plan p = plans[i];
+        if (p.fast) work[atomicAdd(&cursors[crop_bucket(p, page_hw, img_h, img_w, n_pages)], 1)] = (int32_t)i;
     }
 }
 
@@ -149,14 +220,18 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 }
 
 
-// Warp-specialised persistent kernel for the crops with Plan::fast.  Two producer warps walk this CTA's crops one
-// ahead of the consumers: warp 0 (copy warp) waits until the stage buffer is released and issues the TMA row copies;
-// warp 1 (table warp) waits for the same release, builds the axis tables, signals, and then writes the crop's padding
-// (which nobody waits for).  full[b] completes when both have arrived and the copied bytes have landed.  Warps 2..6
-// (consumers) wait on full[b], resample the pasted rectangle straight into the CHW batch and release the buffer on
-// empty[b].  No CTA-wide barrier inside the loop.  Measured per crop (clock64, r1q build with one producer warp):
-// copies 5.8 k cycles (the per-row copy-request rate), tables 4.2 k, padding 2.8 k per channel, consumers ~15 k --
-// one producer warp doing all of it was the critical path, and the consumers had a third of the padding on top.
+// Warp-specialised persistent kernel for the crops with Plan::fast.  Two producer warps run ahead of the consumers:
+// warp 0 (copy warp) takes the next crop of the work list (a global ticket counter: a CTA that drew narrow words simply
+// draws more of them), reserves the crop's bytes in the CTA's staging RING, tells the table warp which crop it is and
+// issues the TMA row copies; warp 1 (table warp) builds the axis tables, signals, and then writes the crop's padding
+// (which nobody waits for).  Up to kSlots crops are in flight per CTA; a slot owns its metadata and tables, its source
+// rows take exactly the bytes they need from the ring (a narrow word does not hold a 24 KB stage), so the producers
+// can be several crops ahead of the consumers and the differences between crops average out.  full[s] completes when
+// both producers have arrived and the copied bytes have landed.  Warps 2..6 (consumers) wait on full[s], resample the
+// pasted rectangle straight into the CHW batch and release the slot (and its ring bytes) on empty[s].  No CTA-wide
+// barrier inside the loop.  History (profiles/README.md): with two fixed 24 KB stages the consumers waited on `full`
+// 24 % of their time and the copy warp on `empty` 33 % of its -- producer and consumer periods are equal on average,
+// so a two-deep pipeline stalls on every fluctuation.
 // Each consumer thread resamples a column strip (one destination column, G consecutive destination rows): with a
 // shrink factor near 2 neighbouring destination rows share their boundary source row, so a strip needs ~(2G + 1)
 // horizontal row sums instead of 3G; per-pixel arithmetic and its order are unchanged.
@@ -165,105 +240,146 @@ constexpr int kConsumerWarps = kThreads / 32 - kProducerWarps;
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-    crop_resize_pad_kernel(const Plan *__restrict__ plans, const int32_t *__restrict__ n_crops_dev, const int32_t *__restrict__ range,
-                           int64_t crops_cap, int ih, int iw, float *__restrict__ batch,
-                           uint8_t *__restrict__ canvas_out, int vec_ok, uint8_t *__restrict__ redo)
+    crop_resize_pad_kernel(const Plan *__restrict__ plans, const int32_t *__restrict__ work,
+                           const int32_t *__restrict__ n_work_dev, int32_t *__restrict__ ticket, int ring_bytes, int ih,
+                           int iw, float *__restrict__ batch, uint8_t *__restrict__ canvas_out, int vec_ok,
+                           uint8_t *__restrict__ redo)
 {
-    extern __shared__ __align__(128) unsigned char smem[];
-    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + 2 * kSrcBuf);  // [2 stages][kTabWords][iw + ih]
+    extern __shared__ __align__(128) unsigned char smem[];  // [ring_bytes] staging ring, then kSlots table sets
     const int tab_n = iw + ih;
-    __shared__ __align__(8) uint64_t s_full[2], s_empty[2];
-    // per stage, published by the table warp: the crop (index, -1 = no more crops) and what the consumers need of its
-    // plan, so that they never touch the plan array in global memory
-    __shared__ long long s_ci[2];
-    __shared__ int s_meta[2][8];  // nw, nh, y0, pitch, misalignment of row 0, its change per row, <= 3 x taps, strip height
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + ring_bytes);  // [kSlots][kTabWords][iw + ih]
+    __shared__ __align__(8) uint64_t s_full[kSlots], s_empty[kSlots], s_tick[kSlots];
+    // per slot: the crop (index, -1 = no more crops) and what the consumers need of its plan, so that they never touch
+    // the plan array in global memory
+    __shared__ int s_next[kSlots];    // copy warp -> table warp: crop index of the slot
+    __shared__ int s_off[kSlots];     // copy warp -> consumers: ring offset of the crop's first row
+    __shared__ long long s_ci[kSlots];
+    __shared__ int s_meta[kSlots][8];  // nw, nh, y0, pitch, misalignment of row 0, its change per row, <= 3 x taps, strip height
 
-    const int64_t begin = range ? range[0] : 0;
-    int64_t n_crops = range ? range[1] : *n_crops_dev;
-    if (n_crops > crops_cap) n_crops = crops_cap;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int plane = ih * iw;
 
     if (threadIdx.x == 0) {
-        mbar_init(&s_full[0], 2);  // the copy warp (with the byte count) and the table warp
-        mbar_init(&s_full[1], 2);
-        mbar_init(&s_empty[0], kConsumerWarps);
-        mbar_init(&s_empty[1], kConsumerWarps);
+#pragma unroll
+        for (int i = 0; i < kSlots; i++) {
+            mbar_init(&s_full[i], 2);  // the copy warp (with the byte count) and the table warp
+            mbar_init(&s_empty[i], kConsumerWarps);
+            mbar_init(&s_tick[i], 1);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
 
     if (warp == 0) {
-        // ---------------- copy warp: the crop's source rows, one bulk copy per row ----------------
-        int k = 0;
-        for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
-            const Plan p = plans[ci];
-            if (ci + gridDim.x < n_crops) {  // the next plan is on its way while this crop is set up
-                const char *nx = reinterpret_cast<const char *>(plans + ci + gridDim.x);
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
-                asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + sizeof(Plan) - 1));
+        // ---------------- copy warp: tickets, ring space, one bulk copy per source row ----------------
+        const int n_work = *n_work_dev;
+        int q_off[kSlots], q_len[kSlots];  // ring intervals of the slots (len 0: free)
+#pragma unroll
+        for (int i = 0; i < kSlots; i++) q_off[i] = q_len[i] = 0;
+        int head = 0;        // where the newest crop ended
+        int oldest = 0;      // first crop (sequence number) whose slot has not been seen released
+        int t = 0;
+        if (lane == 0) t = atomicAdd(ticket, 1);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        for (int k = 0;; k++) {
+            const int s = k % kSlots;
+            const int ci = t < n_work ? work[t] : -1;
+            // the slot's previous crop (k - kSlots) must be done before its metadata / tables are reused
+            while (oldest + kSlots <= k) {
+                mbar_wait(&s_empty[oldest % kSlots], (uint32_t)((oldest / kSlots) & 1));
+                q_len[oldest % kSlots] = 0;
+                oldest++;
             }
-            if (!p.fast) continue;
-            const int b = k & 1;
-            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
+            if (ci < 0) {  // no more crops: tell the table warp, which tells the consumers
+                if (lane == 0) {
+                    s_next[s] = -1;
+                    mbar_arrive(&s_tick[s]);
+                    mbar_arrive(&s_full[s]);
+                }
+                break;
+            }
+            const Plan p = plans[ci];
+            if (lane == 0) t = atomicAdd(ticket, 1);  // the next ticket travels while this crop is set up
+            const int need = (p.pitch * p.h + 16 + 127) & ~127;
+            int off;
+            for (;;) {  // first fit at `head`, else at 0; else wait for the oldest crop in flight
+                auto free_at = [&](int c) {
+                    bool ok = c + need <= ring_bytes;
+#pragma unroll
+                    for (int i = 0; i < kSlots; i++) ok = ok && (q_len[i] == 0 || c + need <= q_off[i] || q_off[i] + q_len[i] <= c);
+                    return ok;
+                };
+                if (free_at(head)) {
+                    off = head;
+                    break;
+                }
+                if (free_at(0)) {
+                    off = 0;
+                    break;
+                }
+                // oldest < k here: with nothing in flight the whole ring is free and `need` fits by construction
+                mbar_wait(&s_empty[oldest % kSlots], (uint32_t)((oldest / kSlots) & 1));
+                q_len[oldest % kSlots] = 0;
+                oldest++;
+            }
+            q_off[s] = off;
+            q_len[s] = need;
+            head = off + need;
+            if (lane == 0) {
+                s_next[s] = ci;
+                s_off[s] = off;
+                mbar_arrive(&s_tick[s]);  // release: the table warp and (through full) the consumers see both
+            }
             uint32_t bytes = 0;
             {
                 const uint8_t *src = p.src;
                 const size_t stride = (size_t)p.stride;
-                unsigned char *buf = smem + b * kSrcBuf;
+                unsigned char *buf = smem + off;
                 for (int r = lane; r < p.h; r += 32) {
                     const uint8_t *g = src + (size_t)r * stride;
                     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
                     const uint32_t sz = (a + (uint32_t)p.w * 3 + 15) & ~15u;
-                    tma_bulk_g2s(buf + (size_t)r * p.pitch, g - a, sz, &s_full[b]);
+                    tma_bulk_g2s(buf + (size_t)r * p.pitch, g - a, sz, &s_full[s]);
                     bytes += sz;
                 }
 #pragma unroll
-                for (int off = 16; off > 0; off >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, off);
+                for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
             }
-            if (lane == 0) mbar_expect_tx(&s_full[b], bytes);
-            k++;
-        }
-        {  // the end-of-work signal (published by the table warp) needs this warp's arrival too
-            const int b = k & 1;
-            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
-            if (lane == 0) mbar_arrive(&s_full[b]);
+            if (lane == 0) mbar_expect_tx(&s_full[s], bytes);
+            t = __shfl_sync(0xffffffffu, t, 0);
         }
         return;
     }
     if (warp == 1) {
-        // ---------------- table warp: OpenCV's axis tables, then two thirds of the padding ----------------
-        int k = 0;
-        for (int64_t ci = begin + blockIdx.x; ci < n_crops; ci += gridDim.x) {
+        // ---------------- table warp: OpenCV's axis tables, then all of the padding ----------------
+        for (int k = 0;; k++) {
+            const int s = k % kSlots;
+            mbar_wait(&s_tick[s], (uint32_t)((k / kSlots) & 1));
+            const int ci = s_next[s];
+            if (ci < 0) {
+                if (lane == 0) {
+                    s_ci[s] = -1;
+                    mbar_arrive(&s_full[s]);
+                }
+                break;
+            }
             const Plan p = plans[ci];
-            if (!p.fast) continue;
-            const int b = k & 1;
-            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
-            const bool x3 = __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)b * kTabWords * tab_n, tab_n, iw, lane));
+            const bool x3 = __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)s * kTabWords * tab_n, tab_n, iw, lane));
             if (lane == 0) {
-                s_ci[b] = ci;
-                s_meta[b][0] = p.nw;
-                s_meta[b][1] = p.nh;
-                s_meta[b][2] = p.y0;
-                s_meta[b][3] = p.pitch;
-                s_meta[b][4] = (int)(reinterpret_cast<uintptr_t>(p.src) & 15);
-                s_meta[b][5] = p.stride & 15;  // per-row change of the 16-byte misalignment
-                s_meta[b][6] = x3 ? 1 : 0;
-                s_meta[b][7] = strip_height<kConsumerWarps * 32>(p.nw, p.nh);
+                s_ci[s] = ci;
+                s_meta[s][0] = p.nw;
+                s_meta[s][1] = p.nh;
+                s_meta[s][2] = p.y0;
+                s_meta[s][3] = p.pitch;
+                s_meta[s][4] = (int)(reinterpret_cast<uintptr_t>(p.src) & 15);
+                s_meta[s][5] = p.stride & 15;  // per-row change of the 16-byte misalignment
+                s_meta[s][6] = x3 ? 1 : 0;
+                s_meta[s][7] = strip_height<kConsumerWarps * 32>(p.nw, p.nh);
             }
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
-            if (lane == 0) mbar_arrive(&s_full[b]);
+            if (lane == 0) mbar_arrive(&s_full[s]);
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
                                               kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0, 3);
-            k++;
-        }
-        {  // no more crops
-            const int b = k & 1;
-            if (k >= 2) mbar_wait(&s_empty[b], (uint32_t)(((k >> 1) - 1) & 1));
-            if (lane == 0) {
-                s_ci[b] = -1;
-                mbar_arrive(&s_full[b]);
-            }
         }
         return;
     }
@@ -272,24 +388,25 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     const int ct = (warp - kProducerWarps) * 32 + lane;
     constexpr int kCT = kConsumerWarps * 32;
     for (int k = 0;; k++) {
-        const int b = k & 1;
-        mbar_wait(&s_full[b], (uint32_t)((k >> 1) & 1));
-        const int64_t ci = s_ci[b];
+        const int s = k % kSlots;
+        mbar_wait(&s_full[s], (uint32_t)((k / kSlots) & 1));
+        const int64_t ci = s_ci[s];
         if (ci < 0) break;
-        const int nw = s_meta[b][0], nh = s_meta[b][1], y0 = s_meta[b][2];
-        const uint32_t pitch = (uint32_t)s_meta[b][3], a0 = (uint32_t)s_meta[b][4], sstep = (uint32_t)s_meta[b][5];
-        const int G = s_meta[b][7];
+        const int nw = s_meta[s][0], nh = s_meta[s][1], y0 = s_meta[s][2];
+        const uint32_t pitch = (uint32_t)s_meta[s][3], a0 = (uint32_t)s_meta[s][4], sstep = (uint32_t)s_meta[s][5];
+        const int G = s_meta[s][7];
+        const uint32_t stage_off = (uint32_t)s_off[s];
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
-        const uint32_t *tab = tabs + (size_t)b * kTabWords * tab_n;
+        const uint32_t *tab = tabs + (size_t)s * kTabWords * tab_n;
         // three x taps at most (shrink factor below 2, nearly every word box): a quarter of the horizontal work less
-        const bool bad = s_meta[b][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
+        const bool bad = s_meta[s][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, stage_off, pitch, a0, sstep,
                                                                                   tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct, G)
-                                      : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, (uint32_t)(b * kSrcBuf), pitch, a0, sstep,
+                                      : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, stage_off, pitch, a0, sstep,
                                                                                   tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct, G);
         if (bad) redo[ci] = 1;  // a table entry with more than 4 taps: the generic kernel redoes the crop
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_empty[b]);
+        if (lane == 0) mbar_arrive(&s_empty[s]);
     }
 }
 
@@ -372,12 +489,73 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const Plan *__restric
     }
 }
 
+// ---- detector input (the caller side of the path, EAST.predict infer.py:301-305) ---------------------------------
+// cv2.resize(img, (T, T)) -- INTER_LINEAR on uint8 (11-bit fixed-point coefficients, aspect NOT preserved), then
+// torchvision ToTensor (x / 255) and Normalize(0.5, 0.5) ((x - 0.5) / 0.5), written as the (3, T, T) float32 network
+// input.  Same arithmetic as resample_px's linear branch (the oracle's orc_resize_linear_u8c3, pinned to cv2 for
+// shrinking and enlarging); a thread per destination pixel, the source page is read through L2.  This is what lets
+// the page cross PCIe once: the original image is uploaded, the resized detector input is made on the device.
+__global__ void __launch_bounds__(256) detector_input_kernel(const uint8_t *__restrict__ page, int H, int W, int th,
+                                                             int tw, float *__restrict__ out_f32,
+                                                             uint8_t *__restrict__ out_u8)
+{
+    const double scale_x = 1.0 / ((double)tw / (double)W), scale_y = 1.0 / ((double)th / (double)H);
+    const bool same = (th == H && tw == W);  // cv2.resize returns a copy
+    const size_t plane = (size_t)th * tw;
+    const PitchedSrc src{page, (size_t)W * 3};
+    Plan p;
+    p.interp = same ? 0 : 1;
+    p.isx = p.isy = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < plane; i += (size_t)gridDim.x * blockDim.x) {
+        const int dy = (int)(i / tw), dx = (int)(i - (size_t)dy * tw);
+        AxisEnt ex = {}, ey = {};
+        if (!same) {
+            ex = linear_entry_x(dx, scale_x, W);
+            ey = linear_entry_y(dy, scale_y, H);
+        }
+        unsigned char o0, o1, o2;
+        resample_px(p, dx, dy, src, ex, ey, o0, o1, o2);
+        if (out_f32) {
+            out_f32[i] = ((float)o0 / 255.0f - 0.5f) / 0.5f;
+            out_f32[plane + i] = ((float)o1 / 255.0f - 0.5f) / 0.5f;
+            out_f32[2 * plane + i] = ((float)o2 / 255.0f - 0.5f) / 0.5f;
+        }
+        if (out_u8) {
+            out_u8[i * 3] = o0;
+            out_u8[i * 3 + 1] = o1;
+            out_u8[i * 3 + 2] = o2;
+        }
+    }
+}
+
 }  // namespace
 
-size_t msk_crop_scratch(int64_t crops_cap)
+int msk_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, int target_h, int target_w,
+                       float *out_f32, uint8_t *out_u8, cudaStream_t st)
+{
+    if (!page || img_h <= 0 || img_w <= 0 || target_h <= 0 || target_w <= 0 || (!out_f32 && !out_u8)) {
+        ms_set_error("detector_input: bad arguments");
+        return MS_ERR_INVALID;
+    }
+    const size_t n = (size_t)target_h * target_w;
+    size_t grid = (n + 255) / 256;
+    if (grid > (size_t)ctx->num_sms * 16) grid = (size_t)ctx->num_sms * 16;
+    detector_input_kernel<<<(int)grid, 256, 0, st>>>(page, img_h, img_w, target_h, target_w, out_f32, out_u8);
+    MS_LAUNCH_CHECK(ctx);
+    return MS_OK;
+}
+
+// scratch that depends on the page count as well: the work-list buckets
+static size_t crop_bucket_count(int n_pages)
+{
+    size_t b = (size_t)(n_pages > 0 ? n_pages : 1) * kBandsY * kCellsX;
+    return b > ((size_t)1 << 22) ? ((size_t)1 << 22) : b;
+}
+
+size_t msk_crop_scratch(int64_t crops_cap, int n_pages)
 {
     const size_t n = (size_t)(crops_cap > 0 ? crops_cap : 0);
-    return n * sizeof(Plan) + n + n * sizeof(int32_t) + 4096;
+    return n * sizeof(Plan) + n + 2 * n * sizeof(int32_t) + crop_bucket_count(n_pages) * sizeof(int32_t) + 8192;
 }
 
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
@@ -394,39 +572,49 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
         ms_set_error("crop: canvas %dx%d too large", out_h, out_w);
         return MS_ERR_INVALID;
     }
-    const size_t smem = 2 * (size_t)kSrcBuf + 2 * (size_t)(out_h + out_w) * kTabWords * sizeof(uint32_t);
-    if (smem > 220 * 1024) {
-        ms_set_error("crop: canvas %dx%d needs %zu bytes of shared memory", out_h, out_w, smem);
+    // shared memory of the persistent kernel: kSlots table sets + the staging ring, which gets what is left of an SM's
+    // 227 KB split over the CTAs per SM (1 KB per CTA is reserved by the system, ~0.5 KB is static)
+    const size_t tab_bytes = (size_t)kSlots * (size_t)(out_h + out_w) * kTabWords * sizeof(uint32_t);
+    const size_t min_ring = (size_t)kSrcBuf + 128;
+    int per_sm = kCtasPerSm;
+    while (per_sm > 1 && (227 * 1024) / per_sm < (int)(tab_bytes + min_ring + 1024 + 512)) per_sm--;
+    if ((227 * 1024) / per_sm < (int)(tab_bytes + min_ring + 1024 + 512)) {
+        ms_set_error("crop: canvas %dx%d needs %zu bytes of shared memory", out_h, out_w, tab_bytes + min_ring);
         return MS_ERR_INVALID;
     }
+    size_t ring = ((size_t)(227 * 1024) / per_sm - 1024 - 512 - tab_bytes) & ~(size_t)127;
+    if (ring > 96 * 1024) ring = 96 * 1024;
+    const size_t smem = ring + tab_bytes;
+    const int n_buckets = (int)crop_bucket_count(n_pages);
     Plan *plans = bump.take<Plan>((size_t)crops_cap);
     uint8_t *redo = bump.take<uint8_t>((size_t)crops_cap);
     int32_t *glist = bump.take<int32_t>((size_t)crops_cap);
-    int32_t *glist_n = bump.take<int32_t>(1);
-    if (!plans || !redo || !glist_n) {
+    int32_t *work = bump.take<int32_t>((size_t)crops_cap);
+    int32_t *hist = bump.take<int32_t>((size_t)n_buckets);
+    int32_t *cnt = bump.take<int32_t>(4);  // generic-list length, fast-crop count, ticket counter
+    if (!plans || !redo || !cnt) {
         ms_set_error("crop: scratch too small");
         return MS_ERR_CAPACITY;
     }
+    int32_t *glist_n = cnt, *n_work = cnt + 1, *ticket = cnt + 2;
     MS_CUDA(cudaMemsetAsync(redo, 0, (size_t)crops_cap, st));
-    MS_CUDA(cudaMemsetAsync(glist_n, 0, sizeof(int32_t), st));
-    {
-        int64_t g = (crops_cap + 255) / 256;
-        if (g > (int64_t)ctx->num_sms * 8) g = (int64_t)ctx->num_sms * 8;
-        crop_plan_kernel<<<(int)g, 256, 0, st>>>(pages, ragged ? page_ptrs : nullptr, page_hw, n_pages, img_h, img_w,
-                                                 crops, n_crops, range, crops_cap, out_h,
-                                                 out_w, plans);
-        MS_LAUNCH_CHECK(ctx);
-    }
-    int per_sm = (int)((227 * 1024) / (smem + 1024 + 512));
-    if (per_sm > kCtasPerSm) per_sm = kCtasPerSm;
-    if (per_sm < 1) per_sm = 1;
+    MS_CUDA(cudaMemsetAsync(hist, 0, (size_t)n_buckets * sizeof(int32_t), st));
+    MS_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(int32_t), st));
+    int64_t lgrid = (crops_cap + 255) / 256;
+    if (lgrid > (int64_t)ctx->num_sms * 8) lgrid = (int64_t)ctx->num_sms * 8;
+    crop_plan_kernel<<<(int)lgrid, 256, 0, st>>>(pages, ragged ? page_ptrs : nullptr, page_hw, n_pages, img_h, img_w, crops,
+                                                 n_crops, range, crops_cap, out_h, out_w, plans, hist);
+    MS_LAUNCH_CHECK(ctx);
+    crop_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, n_work);
+    MS_LAUNCH_CHECK(ctx);
+    crop_bucket_scatter_kernel<<<(int)lgrid, 256, 0, st>>>(plans, ragged ? page_hw : nullptr, n_pages, img_h, img_w, n_crops,
+                                                           range, crops_cap, hist, work);
+    MS_LAUNCH_CHECK(ctx);
     int64_t grid = (int64_t)ctx->num_sms * per_sm;
     if (grid > crops_cap) grid = crops_cap;
     // one CTA per listed crop, many in flight: a generic crop reads global memory byte by byte and is latency bound
     int64_t ggrid = (int64_t)ctx->num_sms * 8;
     if (ggrid > crops_cap) ggrid = crops_cap;
-    int64_t lgrid = (crops_cap + 255) / 256;
-    if (lgrid > (int64_t)ctx->num_sms * 8) lgrid = (int64_t)ctx->num_sms * 8;
     const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
     // cudaFuncSetAttribute is a synchronous driver call (milliseconds): once per context and kernel, not per launch
 #define MS_CROP_LAUNCH(F32, U8)                                                                                        \
@@ -437,8 +625,8 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
             MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
             granted = (int)smem;                                                                                       \
         }                                                                                                              \
-        kfn<<<(int)grid, kThreads, smem, st>>>(plans, n_crops, range, crops_cap, out_h, out_w,                        \
-                                              batch_f32, canvas_u8, vec_ok, redo);                                     \
+        kfn<<<(int)grid, kThreads, smem, st>>>(plans, work, n_work, ticket, (int)ring, out_h, out_w, batch_f32,      \
+                                              canvas_u8, vec_ok, redo);                                               \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
         crop_generic_list_kernel<<<(int)lgrid, 256, 0, st>>>(plans, n_crops, range, crops_cap, redo, glist, glist_n);  \
         MS_LAUNCH_CHECK(ctx);                                                                                          \

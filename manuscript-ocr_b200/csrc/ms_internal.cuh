@@ -138,7 +138,9 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
              uint8_t *canvas_u8, ms_bump bump, cudaStream_t st, const uint8_t *const *page_ptrs = nullptr,
              const int32_t *page_hw = nullptr);  // page_ptrs / page_hw (device): pages of their own sizes
-size_t msk_crop_scratch(int64_t crops_cap);
+int msk_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, int target_h, int target_w,
+                       float *out_f32, uint8_t *out_u8, cudaStream_t st);
+size_t msk_crop_scratch(int64_t crops_cap, int n_pages);
 // quadcrop.cu
 int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const float *quads,
                   int quad_stride, const int32_t *page_of, int64_t n, int min_text_size, int border_mode,

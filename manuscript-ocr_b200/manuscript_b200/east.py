@@ -3,9 +3,10 @@
 Mirrors `EAST` (reference detectors/_east/infer.py:28-132 constructor kwargs, 235-402 predict): image ->
 resize -> network -> score / geometry maps -> decode -> LANMS -> expand -> scale -> box filters -> Page.
 The network (a ResNet-FPN, reference detectors/_east/east.py) is outside the hot path and is supplied by the
-caller as any callable / nn.Module returning {"score": (1,1,H,W), "geometry": (1,8,H,W)}; everything after it runs
-in the CUDA kernels of this package and the maps never leave the device (the reference's
-`.cpu().numpy()` at infer.py:312-313 is gone).
+caller as any callable / nn.Module returning {"score": (1,1,H,W), "geometry": (1,8,H,W)}.  Everything around it runs
+in the CUDA kernels of this package: the ORIGINAL image is uploaded once, the resized + normalised network input is made
+on the device (ms_detector_input = cv2.resize INTER_LINEAR + ToTensor + Normalize, infer.py:301-305), and the maps never
+leave the device (the reference's `.cpu().numpy()` at infer.py:312-313 is gone).
 """
 import ctypes as C
 import time
@@ -15,31 +16,26 @@ import numpy as np
 
 from ._cabi import MS_FLAG_EDGE_OVERFLOW, EastParams, check
 from .batch import PageBatch, _raise_for_flags
+from .imaging import read_image, visualize_page
 from .reading_order import reorder_words
 from .types import Block, Page, Word
 
+DEFAULT_WEIGHTS = Path.home() / ".manuscript" / "east" / "east_quad_23_05.pth"  # infer.py:101-103
 
-def read_image(img_or_path):
-    """reference detectors/_east/utils.py:477-497: path -> RGB uint8 array, ndarray passes through."""
-    if isinstance(img_or_path, (str, Path)):
-        import cv2
 
-        img = cv2.imread(str(img_or_path))
-        if img is None:
-            try:
-                from PIL import Image
-
-                with Image.open(str(img_or_path)) as pil_img:
-                    img = np.array(pil_img.convert("RGB"))
-            except Exception as e:
-                raise FileNotFoundError(f"Cannot read image with cv2 or PIL: {img_or_path}. Error: {e}")
-        else:
-            img = cv2.cvtColor(img, cv2.COLOR_BGR2RGB)
-    elif isinstance(img_or_path, np.ndarray):
-        img = img_or_path
-    else:
-        raise TypeError(f"Unsupported type for image input: {type(img_or_path)}")
-    return img
+def words_from_boxes(boxes):
+    """(K, 9) float32 rows -> list of Word (infer.py:359-363).  Scores that pydantic would reject (outside 0..1, NaN)
+    go through the validating constructor so that the reference's ValidationError is raised; the others skip the
+    per-word validation, which would otherwise cost more than the kernels."""
+    b = np.asarray(boxes, dtype=np.float32).reshape(-1, 9)
+    if len(b) == 0:
+        return []
+    coords = b[:, :8].astype(np.float64).tolist()
+    scores = b[:, 8].astype(np.float64).tolist()
+    ok = bool(np.all((b[:, 8] >= 0.0) & (b[:, 8] <= 1.0)))
+    make = Word.model_construct if ok else Word
+    return [make(polygon=[(c[0], c[1]), (c[2], c[3]), (c[4], c[5]), (c[6], c[7])], detection_confidence=s, text=None,
+                 recognition_confidence=None) for c, s in zip(coords, scores)]
 
 
 class EAST:
@@ -65,10 +61,30 @@ class EAST:
         self.remove_area_anomalies = remove_area_anomalies
         self.anomaly_sigma_threshold = anomaly_sigma_threshold
         self.anomaly_min_box_count = anomaly_min_box_count
+        self.cap_boxes = int(cap_boxes)
         self._runner = PageBatch(device=self.device.index or 0, params=self._params(), cap_boxes=cap_boxes,
                                  want_batch=False)
+        self._page_buf = {}   # (h, w) -> persistent device image: stable addresses let repeated calls replay a CUDA graph
+        self._input_buf = None
 
-    def _params(self):
+    @classmethod
+    def from_pretrained(cls, weights_path=None, **kwargs):
+        """What the reference's `EAST()` does (infer.py:94-112): the released weights from
+        ~/.manuscript/east/east_quad_23_05.pth (downloaded there by the reference; this package has no network code)
+        inside the reference's own network module.  FileNotFoundError when the weights are missing -- what the
+        reference's torch.load raises offline -- and ImportError when the reference package that defines the network
+        (manuscript.detectors._east.east.EASTModel) is not installed next to this one."""
+        path = Path(weights_path) if weights_path is not None else DEFAULT_WEIGHTS
+        if not path.exists():
+            raise FileNotFoundError(f"EAST weights not found: {path} (the reference downloads them on first use; "
+                                    "pass EAST(model=...) or weights_path=...)")
+        from manuscript.detectors._east.east import EASTModel  # the network is outside this package
+
+        det = cls(model=None, **kwargs)
+        det.model = EASTModel(pretrained_backbone=False, pretrained_model_path=str(path)).to(det.device).eval()
+        return det
+
+    def _params(self, **over):
         return EastParams.default(
             score_thresh=float(np.float32(self.score_thresh)), scale=1.0 / self.score_geo_scale,
             quantization=int(self.quantization), iou_threshold=float(self.iou_threshold),
@@ -76,7 +92,7 @@ class EAST:
             target_size=int(self.target_size), axis_aligned_output=int(bool(self.axis_aligned_output)),
             remove_area_anomalies=int(bool(self.remove_area_anomalies)),
             anomaly_sigma_threshold=float(self.anomaly_sigma_threshold),
-            anomaly_min_box_count=int(self.anomaly_min_box_count))
+            anomaly_min_box_count=int(self.anomaly_min_box_count), **over)
 
     # ---- the hot path: maps (device or host) -> final boxes (K,9) float32 on the host -----------------------------
     def boxes_from_maps(self, score_map, geo_map, orig_hw):
@@ -124,27 +140,50 @@ class EAST:
         _raise_for_flags(m[3:4])
         return out[: int(m[2])].cpu().numpy()
 
-    def _forward(self, img):
-        """infer.py:301-313: resize to target_size^2 (aspect not preserved), ToTensor, Normalize(0.5,0.5), network."""
-        import cv2
-
+    # ---- image -> device, device image -> network input -> maps (nothing returns to the host) --------------------
+    def upload(self, img):
+        """(H, W, 3) uint8 RGB host array -> the same image on the device, in a buffer this detector keeps per image
+        size.  This is the ONE host-to-device copy of pixels per page: the detector input and the word crops are both
+        made from it."""
         torch = self.torch
+        a = np.asarray(img)
+        if a.ndim != 3 or a.shape[2] != 3 or a.dtype != np.uint8:
+            raise ValueError(f"EAST expects an (H, W, 3) uint8 RGB image, got shape {a.shape} dtype {a.dtype}")
+        a = np.ascontiguousarray(a)
+        buf = self._page_buf.get(a.shape[:2])
+        if buf is None:
+            if len(self._page_buf) >= 4:
+                self._page_buf.clear()
+            buf = self._page_buf[a.shape[:2]] = torch.empty(a.shape, dtype=torch.uint8, device=self.device)
+        buf.copy_(torch.from_numpy(a), non_blocking=True)
+        return buf
+
+    def network_input(self, page_dev):
+        """infer.py:301-305 on the device: (H, W, 3) u8 CUDA tensor -> (1, 3, T, T) f32, bit-identical to
+        cv2.resize(img, (T, T)) -> ToTensor -> Normalize(0.5, 0.5)."""
+        torch = self.torch
+        T = self.target_size
+        if self._input_buf is None or self._input_buf.shape[-1] != T:
+            self._input_buf = torch.empty((1, 3, T, T), dtype=torch.float32, device=self.device)
+        r = self._runner
+        stream = torch.cuda.current_stream(self.device).cuda_stream
+        with torch.cuda.device(self.device):
+            check(r.ctx.lib.ms_detector_input(r.ctx.handle, page_dev.data_ptr(), int(page_dev.shape[0]),
+                                              int(page_dev.shape[1]), T, T, self._input_buf.data_ptr(), None,
+                                              C.c_void_p(stream)))
+        return self._input_buf
+
+    def maps_from_device_page(self, page_dev):
+        """Device image -> (score (1,H',W'), geometry (8,H',W')) CUDA tensors (infer.py:301-313 without the host)."""
         if self.model is None:
             raise RuntimeError("EAST(model=...) is required for predict(): the detector network is outside this "
                                "package (use boxes_from_maps / predict_from_maps when the maps already exist)")
-        resized = cv2.resize(img, (self.target_size, self.target_size))
-        t = torch.from_numpy(np.ascontiguousarray(resized)).to(self.device).permute(2, 0, 1).float().div_(255.0)
-        t = (t - 0.5) / 0.5
-        with torch.no_grad():
-            out = self.model(t.unsqueeze(0))
+        with self.torch.no_grad():
+            out = self.model(self.network_input(page_dev))
         return out["score"][0], out["geometry"][0]
 
     def predict_from_maps(self, score_map, geo_map, orig_hw, sort_reading_order=False):
-        quads = self.boxes_from_maps(score_map, geo_map, orig_hw)
-        words = []
-        for quad in quads:
-            pts = quad[:8].reshape(4, 2)
-            words.append(Word(polygon=pts.tolist(), detection_confidence=float(quad[8])))  # infer.py:359-363
+        words = words_from_boxes(self.boxes_from_maps(score_map, geo_map, orig_hw))
         if sort_reading_order and len(words) > 0:
             words = reorder_words(words)  # infer.py:366-385
         return Page(blocks=[Block(words=words)])
@@ -153,7 +192,7 @@ class EAST:
         """Same contract as the reference's EAST.predict: dict with "page", "vis_image", "score_map", "geo_map"."""
         img = read_image(img_or_path)
         t0 = time.time()
-        score, geo = self._forward(img)
+        score, geo = self.maps_from_device_page(self.upload(img))
         if profile:
             self.torch.cuda.synchronize()
             print(f"  Model inference: {time.time() - t0:.3f}s")
@@ -162,13 +201,9 @@ class EAST:
         if profile:
             print(f"  Decode + NMS + box filters (device): {time.time() - t0:.3f}s")
             print(f"    Boxes after NMS: {sum(len(b.words) for b in page.blocks)}")
-        vis_img = None
-        if vis:
-            raise NotImplementedError("visualisation is outside the hot path: pass the returned Page to the "
-                                      "reference's visualize_page (the Page type is field-compatible)")
         return {
             "page": page,
-            "vis_image": vis_img,
+            "vis_image": visualize_page(img, page, show_order=sort_reading_order) if vis else None,  # infer.py:392-393
             "score_map": score[0].cpu().numpy() if return_maps else None,
             "geo_map": geo.cpu().numpy() if return_maps else None,
         }

@@ -196,13 +196,24 @@ __global__ void __launch_bounds__(1024) crop_bucket_scan_kernel(int32_t *__restr
     }
 }
 
-// work[cursor of the crop's bucket ++] = crop index (order inside a bucket is arbitrary: it only shapes the schedule)
+// What the copy warp of the persistent kernel needs of a crop, in work-list order (32 bytes, one broadcast load).
+struct __align__(16) CopyDesc {
+    const uint8_t *src;  // first source byte of the crop
+    int stride;          // bytes between source rows
+    int pitch;           // bytes between staged rows
+    int w, h;            // crop size in pixels
+    int ci;              // crop index (output slot)
+    int pad;
+};
+
+// work[cursor of the crop's bucket ++] = the crop's copy descriptor (order inside a bucket is arbitrary: it only shapes
+// the schedule)
 __global__ void __launch_bounds__(256) crop_bucket_scatter_kernel(const Plan *__restrict__ plans,
                                                                   const int32_t *__restrict__ page_hw, int n_pages,
                                                                   int img_h, int img_w,
                                                                   const int32_t *__restrict__ n_crops_dev,
                                                                   const int32_t *__restrict__ range, int64_t crops_cap,
-                                                                  int32_t *__restrict__ cursors, int32_t *__restrict__ work)
+                                                                  int32_t *__restrict__ cursors, CopyDesc *__restrict__ work)
 {
     int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
@@ -210,7 +221,17 @@ __global__ void __launch_bounds__(256) crop_bucket_scatter_kernel(const Plan *__
     for (int64_t i = begin + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_crops;
          i += (int64_t)gridDim.x * blockDim.x) {
         const Plan p = plans[i];
-        if (p.fast) work[atomicAdd(&cursors[crop_bucket(p, page_hw, img_h, img_w, n_pages)], 1)] = (int32_t)i;
+        if (p.fast) {
+            CopyDesc d;
+            d.src = p.src;
+            d.stride = p.stride;
+            d.pitch = p.pitch;
+            d.w = p.w;
+            d.h = p.h;
+            d.ci = (int)i;
+            d.pad = 0;
+            work[atomicAdd(&cursors[crop_bucket(p, page_hw, img_h, img_w, n_pages)], 1)] = d;
+        }
     }
 }
 
@@ -240,7 +261,7 @@ constexpr int kConsumerWarps = kThreads / 32 - kProducerWarps;
 
 template <bool kWriteF32, bool kWriteU8>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
-    crop_resize_pad_kernel(const Plan *__restrict__ plans, const int32_t *__restrict__ work,
+    crop_resize_pad_kernel(const Plan *__restrict__ plans, const CopyDesc *__restrict__ work,
                            const int32_t *__restrict__ n_work_dev, int32_t *__restrict__ ticket, int ring_bytes, int ih,
                            int iw, float *__restrict__ batch, uint8_t *__restrict__ canvas_out, int vec_ok,
                            uint8_t *__restrict__ redo)
@@ -272,25 +293,48 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 
     if (warp == 0) {
         // ---------------- copy warp: tickets, ring space, one bulk copy per source row ----------------
+        // Software pipeline: while crop k is being copied, the descriptor of crop k+1 and the ticket of crop k+2 are in
+        // flight, so neither the atomic nor the descriptor load is on the warp's critical path.
         const int n_work = *n_work_dev;
         int q_off[kSlots], q_len[kSlots];  // ring intervals of the slots (len 0: free)
 #pragma unroll
         for (int i = 0; i < kSlots; i++) q_off[i] = q_len[i] = 0;
         int head = 0;        // where the newest crop ended
         int oldest = 0;      // first crop (sequence number) whose slot has not been seen released
-        int t = 0;
-        if (lane == 0) t = atomicAdd(ticket, 1);
-        t = __shfl_sync(0xffffffffu, t, 0);
+        auto load_desc = [&](int t) {
+            CopyDesc d;
+            if (t < n_work) {
+                const uint4 *q = reinterpret_cast<const uint4 *>(work + t);
+                const uint4 a = q[0], b = q[1];
+                d.src = reinterpret_cast<const uint8_t *>(((uint64_t)a.y << 32) | a.x);
+                d.stride = (int)a.z;
+                d.pitch = (int)a.w;
+                d.w = (int)b.x;
+                d.h = (int)b.y;
+                d.ci = (int)b.z;
+            } else {
+                d.src = nullptr;
+                d.stride = d.pitch = d.w = d.h = 0;
+                d.ci = -1;
+            }
+            d.pad = 0;
+            return d;
+        };
+        int t1 = 0;
+        if (lane == 0) t1 = atomicAdd(ticket, 1);
+        CopyDesc cur = load_desc(__shfl_sync(0xffffffffu, t1, 0));
+        if (lane == 0) t1 = atomicAdd(ticket, 1);  // ticket of crop 1
         for (int k = 0;; k++) {
             const int s = k % kSlots;
-            const int ci = t < n_work ? work[t] : -1;
+            const CopyDesc nxt = load_desc(__shfl_sync(0xffffffffu, t1, 0));  // crop k+1: lands during this crop's copies
+            if (lane == 0 && cur.ci >= 0) t1 = atomicAdd(ticket, 1);           // ticket of crop k+2
             // the slot's previous crop (k - kSlots) must be done before its metadata / tables are reused
             while (oldest + kSlots <= k) {
                 mbar_wait(&s_empty[oldest % kSlots], (uint32_t)((oldest / kSlots) & 1));
                 q_len[oldest % kSlots] = 0;
                 oldest++;
             }
-            if (ci < 0) {  // no more crops: tell the table warp, which tells the consumers
+            if (cur.ci < 0) {  // no more crops: tell the table warp, which tells the consumers
                 if (lane == 0) {
                     s_next[s] = -1;
                     mbar_arrive(&s_tick[s]);
@@ -298,9 +342,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                 }
                 break;
             }
-            const Plan p = plans[ci];
-            if (lane == 0) t = atomicAdd(ticket, 1);  // the next ticket travels while this crop is set up
-            const int need = (p.pitch * p.h + 16 + 127) & ~127;
+            const int need = (cur.pitch * cur.h + 16 + 127) & ~127;
             int off;
             for (;;) {  // first fit at `head`, else at 0; else wait for the oldest crop in flight
                 auto free_at = [&](int c) {
@@ -326,27 +368,27 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             q_len[s] = need;
             head = off + need;
             if (lane == 0) {
-                s_next[s] = ci;
+                s_next[s] = cur.ci;
                 s_off[s] = off;
                 mbar_arrive(&s_tick[s]);  // release: the table warp and (through full) the consumers see both
             }
             uint32_t bytes = 0;
             {
-                const uint8_t *src = p.src;
-                const size_t stride = (size_t)p.stride;
+                const uint8_t *src = cur.src;
+                const size_t stride = (size_t)cur.stride;
                 unsigned char *buf = smem + off;
-                for (int r = lane; r < p.h; r += 32) {
+                for (int r = lane; r < cur.h; r += 32) {
                     const uint8_t *g = src + (size_t)r * stride;
                     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
-                    const uint32_t sz = (a + (uint32_t)p.w * 3 + 15) & ~15u;
-                    tma_bulk_g2s(buf + (size_t)r * p.pitch, g - a, sz, &s_full[s]);
+                    const uint32_t sz = (a + (uint32_t)cur.w * 3 + 15) & ~15u;
+                    tma_bulk_g2s(buf + (size_t)r * cur.pitch, g - a, sz, &s_full[s]);
                     bytes += sz;
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
             }
             if (lane == 0) mbar_expect_tx(&s_full[s], bytes);
-            t = __shfl_sync(0xffffffffu, t, 0);
+            cur = nxt;
         }
         return;
     }
@@ -555,7 +597,7 @@ static size_t crop_bucket_count(int n_pages)
 size_t msk_crop_scratch(int64_t crops_cap, int n_pages)
 {
     const size_t n = (size_t)(crops_cap > 0 ? crops_cap : 0);
-    return n * sizeof(Plan) + n + 2 * n * sizeof(int32_t) + crop_bucket_count(n_pages) * sizeof(int32_t) + 8192;
+    return n * sizeof(Plan) + n + n * sizeof(int32_t) + n * sizeof(CopyDesc) + crop_bucket_count(n_pages) * sizeof(int32_t) + 8192;
 }
 
 int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_w, const int32_t *crops,
@@ -589,7 +631,7 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     Plan *plans = bump.take<Plan>((size_t)crops_cap);
     uint8_t *redo = bump.take<uint8_t>((size_t)crops_cap);
     int32_t *glist = bump.take<int32_t>((size_t)crops_cap);
-    int32_t *work = bump.take<int32_t>((size_t)crops_cap);
+    CopyDesc *work = bump.take<CopyDesc>((size_t)crops_cap);
     int32_t *hist = bump.take<int32_t>((size_t)n_buckets);
     int32_t *cnt = bump.take<int32_t>(4);  // generic-list length, fast-crop count, ticket counter
     if (!plans || !redo || !cnt) {

@@ -28,7 +28,8 @@ from .ops import (  # noqa: F401
     word_rects,
 )
 from .batch import PageBatch, PageBatchResult, shard_pages  # noqa: F401
-from .east import EAST, read_image  # noqa: F401
+from .east import EAST  # noqa: F401
+from .imaging import read_image, visualize_page  # noqa: F401
 from .pipeline import Pipeline  # noqa: F401
 from .reading_order import (  # noqa: F401
     resolve_intersections,

@@ -85,6 +85,7 @@ class PageBatch:
         self.want_batch = bool(want_batch)
         self._bufs = {}
         self._host = {}
+        self._ragged_tables = {}
 
     # ---- device tensors in, device tensors out; stream-ordered, no synchronisation --------------------------------
     def _device_bufs(self, n_pages):
@@ -171,8 +172,17 @@ class PageBatch:
         for pg in pages:
             assert pg.is_cuda and pg.dtype == torch.uint8 and pg.dim() == 3 and pg.shape[2] == 3
             keep.append(pg.contiguous())
-        ptrs = torch.tensor([pg.data_ptr() for pg in keep], dtype=torch.int64).to(self.device)
-        hw = torch.tensor([[pg.shape[0], pg.shape[1]] for pg in keep], dtype=torch.int32).to(self.device)
+        # the pointer / size tables live on the device; the same pages (a serving loop over persistent buffers) reuse
+        # the same tables, so that the call's arguments repeat and the library replays its CUDA graph
+        sig = tuple((pg.data_ptr(), int(pg.shape[0]), int(pg.shape[1])) for pg in keep)
+        cached = self._ragged_tables.get(sig)
+        if cached is None:
+            if len(self._ragged_tables) >= 8:
+                self._ragged_tables.clear()
+            cached = self._ragged_tables[sig] = (
+                torch.tensor([v[0] for v in sig], dtype=torch.int64).to(self.device),
+                torch.tensor([[v[1], v[2]] for v in sig], dtype=torch.int32).to(self.device))
+        ptrs, hw = cached
         b = self._device_bufs(P)
         stream = torch.cuda.current_stream(self.device).cuda_stream
         with torch.cuda.device(self.device):

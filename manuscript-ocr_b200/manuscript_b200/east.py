@@ -203,7 +203,7 @@ class EAST:
             print(f"    Boxes after NMS: {sum(len(b.words) for b in page.blocks)}")
         return {
             "page": page,
-            "vis_image": visualize_page(img, page, show_order=sort_reading_order) if vis else None,  # infer.py:392-393
+            "vis_image": visualize_page(img, page, show_order=False) if vis else None,  # infer.py:390
             "score_map": score[0].cpu().numpy() if return_maps else None,
             "geo_map": geo.cpu().numpy() if return_maps else None,
         }

@@ -13,8 +13,6 @@ O(n^2) per sweep in pure Python; this restatement is exact but prunes the work:
 
 It stays on the host: the sweep is a sequential recurrence over (i, j) in index order.
 """
-import math
-
 import numpy as np
 
 
@@ -137,5 +135,3 @@ def reorder_words(words, on_device=True):
         first.setdefault(k, i)
     return [words[first[tuple(int(v) for v in bx)]] for bx in sort_boxes_reading_order_with_resolutions(keys)]
 
-
-_ = math

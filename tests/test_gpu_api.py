@@ -304,3 +304,174 @@ def test_quad_crop_device_entry(mb):
             assert tuple(sz[i]) == (0, 0)
         else:
             np.testing.assert_array_equal(got[i], chw)
+
+
+# ---- the rest of the reference's Pipeline surface (tests/test_pipeline_api_compatibility.py:95-238, case by case) ------
+def test_pipeline_non_tuple_recognizer_confidence(mb):
+    pipe = mb.Pipeline(detector=DummyDetector(mb), recognizer=DummyRecognizer())
+    page = pipe.predict(np.zeros((100, 400, 3), np.uint8), recognize_text=True, vis=False)
+    assert page.blocks[0].words[0].text == "word1" and page.blocks[0].words[0].recognition_confidence == 0.9
+
+
+def test_pipeline_without_recognition(mb):
+    rec = DummyRecognizer()
+    page = mb.Pipeline(detector=DummyDetector(mb), recognizer=rec).predict(np.zeros((100, 400, 3), np.uint8),
+                                                                          recognize_text=False, vis=False)
+    assert rec.call_count == 0 and page.blocks[0].words[0].text is None
+
+
+def test_pipeline_with_visualization(mb):
+    """reference test :177-188: vis=True returns (Page, PIL.Image); also with recognize_text=False (_pipeline.py:81-87)
+    and from EAST.predict (infer.py:390)."""
+    from PIL import Image
+
+    pipe = mb.Pipeline(detector=DummyDetector(mb), recognizer=DummyRecognizer())
+    img = np.zeros((100, 400, 3), np.uint8)
+    page, vis_img = pipe.predict(img, recognize_text=True, vis=True)
+    assert isinstance(page, mb.Page) and isinstance(vis_img, Image.Image) and vis_img.size == (400, 100)
+    assert np.asarray(vis_img).any()  # something was drawn
+    page2, vis2 = pipe.predict(img, recognize_text=False, vis=True)
+    assert isinstance(page2, mb.Page) and isinstance(vis2, Image.Image)
+
+
+def test_pipeline_get_text_and_process_batch(mb):
+    pipe = mb.Pipeline(detector=DummyDetector(mb), recognizer=DummyRecognizer())
+    img = np.zeros((100, 400, 3), np.uint8)
+    text = pipe.get_text(pipe.predict(img))
+    assert "word1" in text and "word2" in text and "word3" in text
+    pages = pipe.process_batch([img, img])
+    assert len(pages) == 2 and all(isinstance(p, mb.Page) for p in pages)
+    assert all(isinstance(p, mb.Page) for p in pipe.process_batch([img], vis=True))
+
+
+def test_pipeline_pil_input_and_defaults(mb, tmp_path, monkeypatch):
+    from PIL import Image
+
+    rng = np.random.default_rng(3)
+    arr = rng.integers(0, 256, (100, 400, 3), dtype=np.uint8)
+    rec = DummyRecognizer()
+    page = mb.Pipeline(detector=DummyDetector(mb), recognizer=rec).predict(Image.fromarray(arr))
+    np.testing.assert_array_equal(rec.seen[1], arr[10:50, 110:200])
+    assert [w.text for w in page.blocks[0].words] == ["word1", "word2", "word3"]
+    f = tmp_path / "page.png"
+    Image.fromarray(arr).save(f)
+    np.testing.assert_array_equal(mb.read_image(str(f)), arr)
+    np.testing.assert_array_equal(mb.read_image(f), arr)
+    # Pipeline() builds EAST() / TRBA() from the released weights like the reference (_pipeline.py:52-54); without them
+    # (no network here) that is a FileNotFoundError, as the reference's torch.load raises
+    monkeypatch.setenv("HOME", str(tmp_path))
+    import manuscript_b200.east as east_mod
+    import manuscript_b200.trba as trba_mod
+
+    monkeypatch.setattr(east_mod, "DEFAULT_WEIGHTS", tmp_path / "east.pth")
+    monkeypatch.setattr(trba_mod, "DEFAULT_DIR", tmp_path / "trba")
+    with pytest.raises(FileNotFoundError):
+        mb.Pipeline()
+    with pytest.raises(FileNotFoundError):
+        mb.Pipeline(detector=DummyDetector(mb))
+
+
+def test_detector_input_matches_cv2_and_torchvision_formula(mb):
+    """ms_detector_input = cv2.resize(img, (T, T)) [INTER_LINEAR] -> x / 255 -> (x - 0.5) / 0.5 (infer.py:301-305),
+    bit for bit, shrinking, enlarging, by exactly 2, and unchanged."""
+    import ctypes as C
+
+    import cv2
+    import torch
+
+    rng = np.random.default_rng(11)
+    ctx = mb.Context(0)
+    for (h, w), t in [((333, 517), 256), ((700, 900), 512), ((100, 180), 256), ((512, 512), 256), ((256, 256), 256),
+                      ((1031, 777), 640), ((64, 2000), 128)]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        d_img = torch.from_numpy(img).cuda()
+        out = torch.empty((3, t, t), dtype=torch.float32, device="cuda")
+        u8 = torch.empty((t, t, 3), dtype=torch.uint8, device="cuda")
+        rc = ctx.lib.ms_detector_input(ctx.handle, d_img.data_ptr(), h, w, t, t, out.data_ptr(), u8.data_ptr(),
+                                       C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, mb._cabi.last_error()
+        torch.cuda.synchronize()
+        want_u8 = cv2.resize(img, (t, t))
+        np.testing.assert_array_equal(u8.cpu().numpy(), want_u8, err_msg=f"{(h, w)} -> {t}")
+        tt = torch.from_numpy(want_u8).permute(2, 0, 1).float().div(255.0)
+        want = ((tt - 0.5) / 0.5).numpy()
+        np.testing.assert_array_equal(out.cpu().numpy(), want)
+        np.testing.assert_array_equal(want_u8, cpu.cv_resize(img, (t, t), "linear"))  # and the oracle agrees with cv2
+
+
+def test_pipeline_fused_route_is_device_resident_and_exact(mb):
+    """mb.EAST + mb.TRBA: one upload of the page, maps / boxes / crops never leave the device, the recogniser network
+    reads views of the batch the crop kernel wrote.  Results against the oracle chain: boxes in the reference's
+    reading order, every crop bit-exact, text written back to the right words."""
+    import torch
+
+    target, words = 512, 60
+    score, geo, _ = synthdata.make_maps(5, target, words)
+    img = synthdata.make_page_image(5, 700)[:600, :700].copy()
+    net_in = {}
+
+    class Net:
+        def __call__(self, x):
+            net_in["x"] = x
+            return {"score": torch.from_numpy(score)[None, None].cuda(), "geometry": torch.from_numpy(geo)[None].cuda()}
+
+    batches = []
+
+    def rec_model(batch):
+        assert batch.is_cuda
+        batches.append(batch)
+        return [(f"w{sum(len(b) for b in batches) - len(batch) + i}", 0.75) for i in range(len(batch))]
+
+    det = mb.EAST(model=Net(), target_size=target)
+    rec = mb.TRBA(model=rec_model, img_h=32, img_w=128, batch_size=32)
+    uploads = []
+    orig_upload = det.upload
+    det.upload = lambda a: (uploads.append(a.nbytes), orig_upload(a))[1]
+    pipe = mb.Pipeline(detector=det, recognizer=rec)
+    page = pipe.predict(img)
+    assert pipe.last_route == "fused" and uploads == [img.nbytes]  # the page crossed PCIe once
+    # the network input was made on the device from that upload: cv2.resize + ToTensor + Normalize
+    import cv2
+
+    tt = torch.from_numpy(cv2.resize(img, (target, target))).permute(2, 0, 1).float().div(255.0)
+    np.testing.assert_array_equal(net_in["x"][0].cpu().numpy(), ((tt - 0.5) / 0.5).numpy())
+    # oracle chain + the reference's reading order (host restatement, pinned to the reference goldens)
+    q = cpu.decode_quads_from_maps(score, geo, 0.6, 4.0, 2)
+    boxes = cpu.east_postprocess(cpu.locality_aware_nms(q, 0.2), (600, 700), target_size=target)
+    ib = []
+    for b in boxes[:, :8]:
+        xs, ys = np.trunc(b[0::2]).astype(np.int64), np.trunc(b[1::2]).astype(np.int64)
+        ib.append((int(xs.min()), int(ys.min()), int(xs.max()), int(ys.max())))
+    want = boxes[_host_order(mb, ib)]
+    got_words = page.blocks[0].words
+    assert len(got_words) == len(want)
+    got = np.array([[v for pt in w.polygon for v in pt] + [w.detection_confidence] for w in got_words], np.float32)
+    np.testing.assert_array_equal(got, want)
+    rects, valid = cpu.word_rects(want, 600, 700, 5)
+    all_crops = torch.cat(batches).cpu().numpy()
+    assert len(all_crops) == int(valid.sum()) and all(len(b) <= 32 for b in batches)
+    for j, r in enumerate(rects[valid]):
+        np.testing.assert_array_equal(all_crops[j], cpu.crop_resize_pad(img, r, 32, 128)[1])
+    texts = [w.text for w, ok in zip(got_words, valid) if ok]
+    assert texts == [f"w{i}" for i in range(len(texts))]
+    assert all(w.text is None for w, ok in zip(got_words, valid) if not ok)
+    assert got_words[0].recognition_confidence == 0.75
+    # same answer as the generic route (any detector + this TRBA: the page is uploaded once, crops stay on the device)
+    batches.clear()
+    dummy = DummyDetector(mb, "dict", [mb.Word(polygon=[tuple(p) for p in b[:8].reshape(4, 2).tolist()],
+                                               detection_confidence=float(b[8])) for b in boxes])
+    pipe2 = mb.Pipeline(detector=dummy, recognizer=rec)
+    page2 = pipe2.predict(img)
+    assert pipe2.last_route == "device_crops"
+    np.testing.assert_array_equal(torch.cat(batches).cpu().numpy(), all_crops)
+    assert [w.polygon for w in page2.blocks[0].words] == [w.polygon for w in got_words]
+    # vis=True on the fused route
+    from PIL import Image
+
+    batches.clear()
+    pg, vis_img = pipe.predict(img, vis=True)
+    assert isinstance(vis_img, Image.Image) and len(pg.blocks[0].words) == len(want)
+    # a repeated call on the same buffers replays the library's CUDA graph and gives the same page
+    batches.clear()
+    again = pipe.predict(img)
+    assert [w.polygon for w in again.blocks[0].words] == [w.polygon for w in got_words]

@@ -78,3 +78,21 @@ def test_lanms_four_to_two_and_empty():
     assert out.shape == (2, 9) and out.dtype == np.float32
     assert cpu.locality_aware_nms(np.zeros((0, 9), np.float32), 0.5).shape == (0, 9)
     assert cpu.locality_aware_nms(None, 0.5).shape == (0, 9)
+
+
+def test_linear_resize_matches_cv2_when_shrinking_and_enlarging():
+    """orc_resize_linear_u8c3 against cv2.resize(INTER_LINEAR) itself: the detector-input resize of EAST.predict
+    (infer.py:304) shrinks whole pages, a case the ResizeAndPadA goldens (INTER_LINEAR only when enlarging) do not
+    contain.  Third-party arithmetic: pinned to the OpenCV in this image (4.x)."""
+    import cv2
+    import numpy as np
+
+    from oracle import cpu
+
+    rng = np.random.default_rng(21)
+    for (h, w), (dh, dw) in [((333, 517), (256, 256)), ((700, 900), (512, 512)), ((100, 180), (256, 256)),
+                             ((512, 512), (256, 256)), ((1031, 777), (640, 640)), ((64, 2000), (128, 128)),
+                             ((37, 41), (300, 7)), ((5, 5), (1, 1))]:
+        img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+        np.testing.assert_array_equal(cpu.cv_resize(img, (dw, dh), "linear"), cv2.resize(img, (dw, dh)),
+                                      err_msg=f"{(h, w)} -> {(dh, dw)}")

@@ -45,8 +45,12 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link."""
+def build(force=False, verbose=False, defines=(), out=None, obj_dir=None):
+    """One object per .cu (compiled in parallel, rebuilt only when the source or a header is newer), then one link.
+    `defines` / `out` / `obj_dir` build an experiment variant (extra -D flags) next to the product library."""
+    global OUT, OBJ_DIR
+    if out is not None:
+        OUT, OBJ_DIR, force = out, obj_dir or (out + ".obj"), True
     if not force and not needs_build():
         return OUT
     os.makedirs(OBJ_DIR, exist_ok=True)
@@ -56,7 +60,7 @@ def build(force=False, verbose=False):
         s, o = os.path.join(CSRC, src), os.path.join(OBJ_DIR, src[:-3] + ".o")
         objs.append(o)
         if force or not os.path.exists(o) or os.path.getmtime(o) < max(os.path.getmtime(s), hdr_t):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-c", "-o", o, s]
+            cmd = [_nvcc(), *NVCC_FLAGS, *[f"-D{d}" for d in defines], "-I", INCLUDE, "-c", "-o", o, s]
             if verbose:
                 cmd[1:1] = ["-Xptxas", "-v"]
                 print(" ".join(cmd))
@@ -69,4 +73,12 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    # python build.py [--force] [--verbose] [--variant NAME -DFOO=1 ...]  (variant -> manuscript_b200/libvariant_NAME.so)
+    args = sys.argv[1:]
+    if "--variant" in args:
+        name = args[args.index("--variant") + 1]
+        defs = [a[2:] for a in args if a.startswith("-D")]
+        print(build(defines=defs, out=os.path.join(HERE, "manuscript_b200", f"libvariant_{name}.so"),
+                    obj_dir=os.path.join(HERE, "build", f"variant_{name}")))
+    else:
+        print(build(force="--force" in args, verbose="--verbose" in args))

@@ -37,9 +37,16 @@ namespace {
 constexpr int kThreads = 224;   // copy warp + table/padding warp + 5 consumer warps; 4 CTAs per SM
 constexpr int kCtasPerSm = 4;
 constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
-constexpr int kSrcBuf = 24 * 1024;  // largest staged crop (bytes); the staging ring of a CTA holds at least one
+constexpr int kSrcBuf = 40 * 1024;  // largest staged crop (bytes); the staging ring of a CTA holds at least one
 constexpr int kSlots = 3;       // crops in flight per CTA (ring slots: metadata + tables per slot, bytes from the ring)
-constexpr int kBandsY = 64, kCellsX = 8;  // work-list buckets per page: (row band, x cell)
+constexpr int kBandsY = 64, kCellsX = 8;
+#ifndef MS_COPY_PAD_CHANNELS
+#define MS_COPY_PAD_CHANNELS 0
+#endif
+constexpr int kCopyPadChannels = MS_COPY_PAD_CHANNELS;  // float32 padding channels written by the copy warp
+#ifndef MS_CROP_WAIT_NS
+#define MS_CROP_WAIT_NS 100u
+#endif  // work-list buckets per page: (row band, x cell)
 
 // Pages are either one (n_pages, img_h, img_w, 3) tensor, or -- page_ptrs != NULL -- separate images of their own
 // sizes: page_ptrs[p] -> (page_hw[2p], page_hw[2p+1], 3) bytes.
@@ -103,16 +110,20 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+    // A failed try sleeps before the next one: a waiting warp that retries every few tens of cycles takes issue slots
+    // from the warps that do the arithmetic (r2c capture: a quarter of all executed instructions were retries).
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
         "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
+        "WAIT_%=:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
         "DONE_%=:\n"
         "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(0x989680u)  // suspend-time hint: sleep in hardware instead of spinning on issue slots
+        "r"(parity), "r"(MS_CROP_WAIT_NS)
         : "memory");
 }
 __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
@@ -201,9 +212,10 @@ struct __align__(16) CopyDesc {
     const uint8_t *src;  // first source byte of the crop
     int stride;          // bytes between source rows
     int pitch;           // bytes between staged rows
-    int w, h;            // crop size in pixels
+    int wh;              // crop size in pixels: w | h << 16 (both < 65536 for a fast crop)
+    int nwh;             // pasted size: nw | nh << 16
     int ci;              // crop index (output slot)
-    int pad;
+    int y0;              // first canvas row of the pasted rectangle
 };
 
 // work[cursor of the crop's bucket ++] = the crop's copy descriptor (order inside a bucket is arbitrary: it only shapes
@@ -226,10 +238,10 @@ __global__ void __launch_bounds__(256) crop_bucket_scatter_kernel(const Plan *__
             d.src = p.src;
             d.stride = p.stride;
             d.pitch = p.pitch;
-            d.w = p.w;
-            d.h = p.h;
+            d.wh = p.w | (p.h << 16);
+            d.nwh = p.nw | (p.nh << 16);
             d.ci = (int)i;
-            d.pad = 0;
+            d.y0 = p.y0;
             work[atomicAdd(&cursors[crop_bucket(p, page_hw, img_h, img_w, n_pages)], 1)] = d;
         }
     }
@@ -309,15 +321,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                 d.src = reinterpret_cast<const uint8_t *>(((uint64_t)a.y << 32) | a.x);
                 d.stride = (int)a.z;
                 d.pitch = (int)a.w;
-                d.w = (int)b.x;
-                d.h = (int)b.y;
+                d.wh = (int)b.x;
+                d.nwh = (int)b.y;
                 d.ci = (int)b.z;
+                d.y0 = (int)b.w;
             } else {
                 d.src = nullptr;
-                d.stride = d.pitch = d.w = d.h = 0;
+                d.stride = d.pitch = d.wh = d.nwh = d.y0 = 0;
                 d.ci = -1;
             }
-            d.pad = 0;
             return d;
         };
         int t1 = 0;
@@ -342,7 +354,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                 }
                 break;
             }
-            const int need = (cur.pitch * cur.h + 16 + 127) & ~127;
+            const int cw = cur.wh & 0xffff, chh = (int)((uint32_t)cur.wh >> 16);
+            const int need = (cur.pitch * chh + 16 + 127) & ~127;
             int off;
             for (;;) {  // first fit at `head`, else at 0; else wait for the oldest crop in flight
                 auto free_at = [&](int c) {
@@ -377,17 +390,26 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                 const uint8_t *src = cur.src;
                 const size_t stride = (size_t)cur.stride;
                 unsigned char *buf = smem + off;
-                for (int r = lane; r < cur.h; r += 32) {
+                for (int r = lane; r < chh; r += 32) {
                     const uint8_t *g = src + (size_t)r * stride;
                     const uint32_t a = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15);
-                    const uint32_t sz = (a + (uint32_t)cur.w * 3 + 15) & ~15u;
+                    const uint32_t sz = (a + (uint32_t)cw * 3 + 15) & ~15u;
+#if !defined(MS_EXP_NO_COPY)
                     tma_bulk_g2s(buf + (size_t)r * cur.pitch, g - a, sz, &s_full[s]);
                     bytes += sz;
+#endif
                 }
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) bytes += __shfl_xor_sync(0xffffffffu, bytes, o);
             }
             if (lane == 0) mbar_expect_tx(&s_full[s], bytes);
+            // this warp's share of the crop's padding (kCopyPadChannels of the three channels): a lone warp's stores
+            // proceed at one 128-byte line per ~25 cycles, so all the padding on the table warp made that warp the
+            // kernel's critical path (profiles/README.md, r2d experiments)
+            if (kCopyPadChannels > 0)
+                write_padding<kWriteF32, kWriteU8>(cur.nwh & 0xffff, (int)((uint32_t)cur.nwh >> 16), cur.y0, ih, iw,
+                                                   kWriteF32 ? batch + (size_t)cur.ci * 3 * plane : nullptr, nullptr, vec_ok,
+                                                   lane, 32, 3 - kCopyPadChannels, 3);
             cur = nxt;
         }
         return;
@@ -420,8 +442,11 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             }
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
             if (lane == 0) mbar_arrive(&s_full[s]);
+#if !defined(MS_EXP_NO_PAD)
             write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
-                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0, 3);
+                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
+                                              kWriteF32 ? 3 - kCopyPadChannels : 3);
+#endif
         }
         return;
     }
@@ -441,11 +466,25 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
         const uint32_t *tab = tabs + (size_t)s * kTabWords * tab_n;
-        // three x taps at most (shrink factor below 2, nearly every word box): a quarter of the horizontal work less
-        const bool bad = s_meta[s][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, stage_off, pitch, a0, sstep,
-                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct, G)
-                                      : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, stage_off, pitch, a0, sstep,
-                                                                                  tab, tab_n, ih, iw, nw, nh, y0, dstf, dstu, ct, G);
+        // three x taps at most (shrink factor below 2, most word boxes): a quarter of the horizontal work less; a page
+        // stride that is a multiple of 16 bytes (sstep == 0): no per-row misalignment arithmetic
+        bool bad = false;
+#if defined(MS_EXP_NO_CONSUME)
+        if (false)
+#else
+        if (sstep == 0)
+#endif
+            bad = s_meta[s][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3, true>(smem, stage_off, pitch, a0, 0u, tab, tab_n, ih,
+                                                                                 iw, nw, nh, y0, dstf, dstu, ct, G)
+                               : area4_strips<kWriteF32, kWriteU8, kCT, 4, true>(smem, stage_off, pitch, a0, 0u, tab, tab_n, ih,
+                                                                                 iw, nw, nh, y0, dstf, dstu, ct, G);
+#if !defined(MS_EXP_NO_CONSUME)
+        else
+            bad = s_meta[s][6] ? area4_strips<kWriteF32, kWriteU8, kCT, 3>(smem, stage_off, pitch, a0, sstep, tab, tab_n, ih, iw,
+                                                                           nw, nh, y0, dstf, dstu, ct, G)
+                               : area4_strips<kWriteF32, kWriteU8, kCT, 4>(smem, stage_off, pitch, a0, sstep, tab, tab_n, ih, iw,
+                                                                           nw, nh, y0, dstf, dstu, ct, G);
+#endif
         if (bad) redo[ci] = 1;  // a table entry with more than 4 taps: the generic kernel redoes the crop
         __syncwarp();
         if (lane == 0) mbar_arrive(&s_empty[s]);

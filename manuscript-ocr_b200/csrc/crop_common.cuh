@@ -5,6 +5,22 @@
 
 namespace {
 
+// store policy of the batch writes (experiment switch): 0 = evict-first streaming stores, 1 = default, 2 = write-through
+#ifndef MS_CROP_STORE
+#define MS_CROP_STORE 0
+#endif
+template <class T>
+__device__ __forceinline__ void ms_store(T *p, const T &v)
+{
+#if MS_CROP_STORE == 0
+    __stcs(p, v);
+#elif MS_CROP_STORE == 1
+    *p = v;
+#else
+    __stwt(p, v);
+#endif
+}
+
 struct Plan {
     int page, x1, y1, w, h;
     int nw, nh, y0;
@@ -236,11 +252,10 @@ __device__ __forceinline__ void resample_px(const Plan &p, int dx, int dy, const
 // Everything outside the pasted rectangle is the 255 canvas (transforms.py:100), 1.0f after normalisation; written
 // as constant 16-byte streaming stores by `nthreads` cooperating threads.
 template <bool kWriteF32, bool kWriteU8>
-__device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, float *dstf, uint8_t *dstu, int vec_ok,
-                                              int tid, int nthreads, int c_begin = 0, int c_end = 3)
+__device__ __forceinline__ void write_padding(int nw, int nh, int y0, int ih, int iw, float *dstf, uint8_t *dstu,
+                                              int vec_ok, int tid, int nthreads, int c_begin = 0, int c_end = 3)
 {
     const int plane = ih * iw;
-    const int nw = p.ok ? p.nw : 0, nh = p.ok ? p.nh : 0, y0 = p.ok ? p.y0 : 0;
     if (kWriteF32) {
         const float one = (255.0f - 127.5f) * (1.0f / 127.5f);
         if (vec_ok) {
@@ -253,22 +268,31 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
             float4 *bot = reinterpret_cast<float4 *>(dstf + (size_t)(y0 + nh) * iw);
             const int plane4 = plane / 4;
             for (int i = tid; i < top4; i += nthreads)
-                for (int c = c_begin; c < c_end; c++) __stcs(top + (size_t)c * plane4 + i, one4);
+                for (int c = c_begin; c < c_end; c++) ms_store(top + (size_t)c * plane4 + i, one4);
             for (int i = tid; i < bot4; i += nthreads)
-                for (int c = c_begin; c < c_end; c++) __stcs(bot + (size_t)c * plane4 + i, one4);
+                for (int c = c_begin; c < c_end; c++) ms_store(bot + (size_t)c * plane4 + i, one4);
             if (tail4 > 0) {
-                const uint32_t mg = 0xFFFFFFFFu / (uint32_t)tail4 + 1u;
-                for (int i = tid; i < nh * tail4; i += nthreads) {
-                    const int r = tail4 == 1 ? i : (int)__umulhi((uint32_t)i, mg), k = i - r * tail4;
-                    float4 *at = reinterpret_cast<float4 *>(dstf + (size_t)(y0 + r) * iw + nw4) + k;
-                    for (int c = c_begin; c < c_end; c++) __stcs(at + (size_t)c * plane4, one4);
+                // right of the pasted rectangle: a thread owns one 16-byte column (and, when the tail is narrower than
+                // the thread count, one of `split` row phases) and walks down the rows -- per row one pointer
+                // increment and a store per channel, no index arithmetic (a lone warp runs at its dependent-issue
+                // latency: the previous per-element division made this loop 5 600 cycles per crop)
+                const int split = max(1, nthreads / tail4);
+                const int col = tid % tail4, phase = tid / tail4;
+                if (phase < split) {
+                    float4 *at = reinterpret_cast<float4 *>(dstf + (size_t)(y0 + phase) * iw + nw4) + col;
+                    const size_t step = (size_t)split * iw / 4;
+                    for (int k = col; k < tail4; k += nthreads) {  // (tails wider than the thread count: several columns)
+                        float4 *p4 = at + (k - col);
+                        for (int r = phase; r < nh; r += split, p4 += step)
+                            for (int c = c_begin; c < c_end; c++) ms_store(p4 + (size_t)c * plane4, one4);
+                    }
                 }
             }
             if (fr > 0) {
                 for (int i = tid; i < nh * fr; i += nthreads) {
                     const int r = i / fr, k = i - r * fr;
                     float *at = dstf + (size_t)(y0 + r) * iw + nw + k;
-                    for (int c = c_begin; c < c_end; c++) __stcs(at + (size_t)c * plane, one);
+                    for (int c = c_begin; c < c_end; c++) ms_store(at + (size_t)c * plane, one);
                 }
             }
         } else {
@@ -291,6 +315,14 @@ __device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, flo
     }
 }
 
+template <bool kWriteF32, bool kWriteU8>
+__device__ __forceinline__ void write_padding(const Plan &p, int ih, int iw, float *dstf, uint8_t *dstu, int vec_ok,
+                                              int tid, int nthreads, int c_begin = 0, int c_end = 3)
+{
+    write_padding<kWriteF32, kWriteU8>(p.ok ? p.nw : 0, p.ok ? p.nh : 0, p.ok ? p.y0 : 0, ih, iw, dstf, dstu, vec_ok, tid,
+                                       nthreads, c_begin, c_end);
+}
+
 // u8 -> f32 without the conversion pipe: byte k of `v` is spliced under the exponent of 2^23, then 2^23 is
 // subtracted (exact for 0..255)
 __device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
@@ -304,10 +336,79 @@ __device__ __forceinline__ float byte_f32(uint32_t v, uint32_t sel)
 // resample_px's general branch.  `o` = shared-memory byte offset of the row's first tap.
 // kTaps = 3: every x entry of the crop has at most 3 taps (always the case for a shrink factor below 2), so the fourth
 // tap -- weight 0, an exact no-op -- and the word that only it needs are not touched.
+// Packed float32 pairs (sm_100 FADD2 / FMUL2): two IEEE round-to-nearest operations per issue slot, same results as
+// two scalar instructions.  Only conversions and PRODUCTS are packed: ptxas contracts mul.f32x2 + add.f32x2 into FFMA2
+// even with --fmad=false, which would change the rounding, so every sum stays a scalar FADD on one half of a pair.
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float &lo, float &hi)
+{
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ unsigned long long f2_pack_bits(uint32_t lo, uint32_t hi)
+{
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "r"(lo), "r"(hi));
+    return v;
+}
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi)
+{
+    unsigned long long v;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(v) : "f"(lo), "f"(hi));
+    return v;
+}
+__device__ __forceinline__ unsigned long long f2_add(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b)
+{
+    unsigned long long r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// bytes k0 and k1 of `va` / `vb` as two floats: (2^23 + byte) spliced by PRMT, then one packed subtraction of 2^23
+__device__ __forceinline__ unsigned long long bytes2_f32(uint32_t va, uint32_t sa, uint32_t vb, uint32_t sb)
+{
+    const unsigned long long magic = f2_pack(-8388608.0f, -8388608.0f);
+    return f2_add(f2_pack_bits(__byte_perm(va, 0x4B000000u, sa), __byte_perm(vb, 0x4B000000u, sb)), magic);
+}
+
+#ifndef MS_CROP_PACKED
+#define MS_CROP_PACKED 1
+#endif
+
 template <int kTaps>
 __device__ __forceinline__ void hrow_area4(const unsigned char *smem_base, uint32_t o, const float4 wx, float &b0,
                                            float &b1, float &b2)
 {
+#if MS_CROP_PACKED
+    const uint32_t *smem32p = reinterpret_cast<const uint32_t *>(smem_base);
+    const uint32_t wip = o >> 2, shp = (o & 3u) * 8u;
+    const uint32_t q0 = smem32p[wip], q1 = smem32p[wip + 1], q2 = smem32p[wip + 2];
+    const uint32_t q3 = kTaps > 3 ? smem32p[wip + 3] : 0u;
+    const uint32_t u0 = __funnelshift_r(q0, q1, shp), u1 = __funnelshift_r(q1, q2, shp), u2 = __funnelshift_r(q2, q3, shp);
+    // bytes: tap0 = u0.b0..b2, tap1 = u0.b3 u1.b0 u1.b1, tap2 = u1.b2 u1.b3 u2.b0, tap3 = u2.b1..b3
+    float p00, p01, p02, p10, p11, p12, p20, p21, p22;
+    f2_unpack(f2_mul(bytes2_f32(u0, 0x7650, u0, 0x7651), f2_pack(wx.x, wx.x)), p00, p01);  // tap 0: channels 0, 1
+    f2_unpack(f2_mul(bytes2_f32(u0, 0x7652, u0, 0x7653), f2_pack(wx.x, wx.y)), p02, p10);  // tap 0 ch 2, tap 1 ch 0
+    f2_unpack(f2_mul(bytes2_f32(u1, 0x7650, u1, 0x7651), f2_pack(wx.y, wx.y)), p11, p12);  // tap 1: channels 1, 2
+    f2_unpack(f2_mul(bytes2_f32(u1, 0x7652, u1, 0x7653), f2_pack(wx.z, wx.z)), p20, p21);  // tap 2: channels 0, 1
+    if (kTaps > 3) {
+        float p30, p31, p32;
+        f2_unpack(f2_mul(bytes2_f32(u2, 0x7650, u2, 0x7651), f2_pack(wx.z, wx.w)), p22, p30);  // tap 2 ch 2, tap 3 ch 0
+        f2_unpack(f2_mul(bytes2_f32(u2, 0x7652, u2, 0x7653), f2_pack(wx.w, wx.w)), p31, p32);  // tap 3: channels 1, 2
+        b0 = ((p00 + p10) + p20) + p30;
+        b1 = ((p01 + p11) + p21) + p31;
+        b2 = ((p02 + p12) + p22) + p32;
+    } else {
+        p22 = byte_f32(u2, 0x7650) * wx.z;
+        b0 = (p00 + p10) + p20;
+        b1 = (p01 + p11) + p21;
+        b2 = (p02 + p12) + p22;
+    }
+    return;
+#endif
     const uint32_t *smem32 = reinterpret_cast<const uint32_t *>(smem_base);
     const uint32_t wi = o >> 2, sh = (o & 3u) * 8u;
     const uint32_t w0 = smem32[wi], w1 = smem32[wi + 1], w2 = smem32[wi + 2];
@@ -378,7 +479,9 @@ __device__ __forceinline__ int strip_height(int nw, int nh)
     return G;
 }
 
-template <bool kWriteF32, bool kWriteU8, int kCT, int kTaps>
+// kAligned: the caller guarantees sstep == 0 (source row stride a multiple of 16 bytes: every staged row has the same
+// misalignment a0), so the per-row misalignment arithmetic disappears.
+template <bool kWriteF32, bool kWriteU8, int kCT, int kTaps, bool kAligned = false>
 __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t stage_off, uint32_t pitch, uint32_t a0,
                                              uint32_t sstep, const uint32_t *tab, int tab_n, int ih, int iw, int nw,
                                              int nh, int y0, float *dstf, uint8_t *dstu, int ct, int G_in = 0)
@@ -409,7 +512,7 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
             // the other rows are independent horizontal passes
             const uint32_t rbase = xoff + (uint32_t)ys0 * pitch;
             if (ys0 != last_r) {
-                const uint32_t mis = sstep == 0 ? a0 : ((a0 + (uint32_t)ys0 * sstep) & 15u);
+                const uint32_t mis = (kAligned || sstep == 0) ? a0 : ((a0 + (uint32_t)ys0 * sstep) & 15u);
                 hrow_area4<kTaps>(smem, rbase + mis, wx, b0, b1, b2);
             }
             float sum0 = wyv[0] * b0, sum1 = wyv[0] * b1, sum2 = wyv[0] * b2;
@@ -417,7 +520,7 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
             for (int j = 1; j < 4; j++) {
                 if (j < yn) {
                     const uint32_t r = (uint32_t)(ys0 + j);
-                    const uint32_t mis = sstep == 0 ? a0 : ((a0 + r * sstep) & 15u);
+                    const uint32_t mis = (kAligned || sstep == 0) ? a0 : ((a0 + r * sstep) & 15u);
                     hrow_area4<kTaps>(smem, rbase + (uint32_t)j * pitch + mis, wx, b0, b1, b2);
                     sum0 += wyv[j] * b0;
                     sum1 += wyv[j] * b1;
@@ -429,9 +532,9 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
             const float f0 = rintf(sum0), f1 = rintf(sum1), f2 = rintf(sum2);
             const int at = (y0 + dy) * iw + dx;
             if (kWriteF32) {
-                __stcs(dstf + at, (f0 - 127.5f) * inv);
-                __stcs(dstf + plane + at, (f1 - 127.5f) * inv);
-                __stcs(dstf + 2 * plane + at, (f2 - 127.5f) * inv);
+                ms_store(dstf + at, (f0 - 127.5f) * inv);
+                ms_store(dstf + plane + at, (f1 - 127.5f) * inv);
+                ms_store(dstf + 2 * plane + at, (f2 - 127.5f) * inv);
             }
             if (kWriteU8) {
                 dstu[(size_t)at * 3] = sat_u8((int)f0);

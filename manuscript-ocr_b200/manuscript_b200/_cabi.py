@@ -112,7 +112,8 @@ _lock = threading.Lock()
 
 
 def library_path():
-    return os.path.join(HERE, _LIB_NAME)
+    # MS_B200_LIB: an experiment build of the same library (manuscript-ocr_b200/build.py --variant), for A/B timing
+    return os.environ.get("MS_B200_LIB") or os.path.join(HERE, _LIB_NAME)
 
 
 def load_library():

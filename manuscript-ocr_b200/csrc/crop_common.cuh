@@ -479,6 +479,43 @@ __device__ __forceinline__ int strip_height(int nw, int nh)
     return G;
 }
 
+// INTER_AREA with both scale factors exactly 2 (cv2's integer fast path: (sum of the 2 x 2 block + 2) >> 2), source rows
+// staged like area4_strips'; a thread per destination pixel.  A word box exactly twice the canvas height is common
+// (2.5 % of the benchmark's crops), and its rounding differs from the float-table path, so it has its own routine.
+template <bool kWriteF32, bool kWriteU8, int kCT>
+__device__ __forceinline__ void area2x2_pixels(const unsigned char *smem, uint32_t stage_off, uint32_t pitch, uint32_t a0,
+                                               uint32_t sstep, int ih, int iw, int nw, int nh, int y0, float *dstf,
+                                               uint8_t *dstu, int ct)
+{
+    const int plane = ih * iw;
+    const float inv = 1.0f / 127.5f;
+    const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;
+    for (int t = ct; t < nw * nh; t += kCT) {
+        const int dy = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - dy * nw;
+        int s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+        for (int yy = 0; yy < 2; yy++) {
+            const uint32_t r = (uint32_t)(2 * dy + yy);
+            const unsigned char *row = smem + stage_off + r * pitch + ((a0 + r * sstep) & 15u) + 6u * (uint32_t)dx;
+            s0 += row[0] + row[3];
+            s1 += row[1] + row[4];
+            s2 += row[2] + row[5];
+        }
+        const int o0 = (s0 + 2) >> 2, o1 = (s1 + 2) >> 2, o2 = (s2 + 2) >> 2;
+        const int at = (y0 + dy) * iw + dx;
+        if (kWriteF32) {
+            ms_store(dstf + at, ((float)o0 - 127.5f) * inv);
+            ms_store(dstf + plane + at, ((float)o1 - 127.5f) * inv);
+            ms_store(dstf + 2 * plane + at, ((float)o2 - 127.5f) * inv);
+        }
+        if (kWriteU8) {
+            dstu[(size_t)at * 3] = (unsigned char)o0;
+            dstu[(size_t)at * 3 + 1] = (unsigned char)o1;
+            dstu[(size_t)at * 3 + 2] = (unsigned char)o2;
+        }
+    }
+}
+
 // kAligned: the caller guarantees sstep == 0 (source row stride a multiple of 16 bytes: every staged row has the same
 // misalignment a0), so the per-row misalignment arithmetic disappears.
 template <bool kWriteF32, bool kWriteU8, int kCT, int kTaps, bool kAligned = false>

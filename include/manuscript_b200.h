@@ -243,7 +243,8 @@ MS_API int ms_page_batch_ragged(ms_ctx *ctx, const float *score, const float *ge
                          int32_t *box_counts, int32_t *crops_out, int64_t crops_cap, int32_t *n_crops,
                          float *batch_f32, uint8_t *canvas_u8, int32_t *flags, void *stream);
 
-/* Same path with HOST buffers (pinned or pageable): H2D of maps + pages, the batch, D2H of boxes,
+/* Same path with HOST buffers (pinned or pageable; `score` / `geo` may also be DEVICE pointers of this context's
+ * device -- maps a detector left on the GPU are used in place and only the page images cross PCIe): H2D of maps + pages, the batch, D2H of boxes,
  * counts, crop list and (optionally, if batch_f32_host != NULL) the crop batch.  When
  * batch_dev_out != NULL the crop batch stays on the device (as the reference leaves it on `self.device`,
  * recognizers/_trba/__init__.py:288):

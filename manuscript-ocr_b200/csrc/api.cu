@@ -1024,20 +1024,28 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     // geometry lives in pinned host memory the kernel gathers it straight from there over PCIe (zero copy) instead
     // of uploading the tensor; pageable buffers are uploaded.
     const float *geo_mapped = nullptr;
-    if (!getenv("MS_B200_NO_ZEROCOPY")) {
+    const float *score_dev = nullptr;  // maps that already live on this device (the detector ran here) are used in place
+    {
         cudaPointerAttributes at;
-        if (cudaPointerGetAttributes(&at, geo) == cudaSuccess && at.type == cudaMemoryTypeHost && at.devicePointer)
-            geo_mapped = static_cast<const float *>(at.devicePointer);
-        else
+        if (cudaPointerGetAttributes(&at, geo) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeDevice && at.device == ctx->device)
+                geo_mapped = geo;
+            else if (at.type == cudaMemoryTypeHost && at.devicePointer && !getenv("MS_B200_NO_ZEROCOPY"))
+                geo_mapped = static_cast<const float *>(at.devicePointer);
+        } else
+            cudaGetLastError();
+        if (cudaPointerGetAttributes(&at, score) == cudaSuccess) {
+            if (at.type == cudaMemoryTypeDevice && at.device == ctx->device) score_dev = score;
+        } else
             cudaGetLastError();
     }
-    size_t need = al256(n_pages * plane * 4) + (geo_mapped ? 256 : al256(n_pages * plane * 32)) +
+    size_t need = (score_dev ? 256 : al256(n_pages * plane * 4)) + (geo_mapped ? 256 : al256(n_pages * plane * 32)) +
                   al256((size_t)n_pages * cap_boxes * 36) + 2 * al256((size_t)n_pages * 4) + 4096;
     if (want_crops) need += al256(n_pages * page_bytes) + al256((size_t)crops_cap * 20) + 256;
     if (want_batch && !caller_batch) need += al256((size_t)crops_cap * one_f);
     MS_TRY(ms_stage_reserve(ctx, need));
     ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
-    float *d_score = sb.take<float>(n_pages * plane);
+    float *d_score = score_dev ? const_cast<float *>(score_dev) : sb.take<float>(n_pages * plane);
     float *d_geo = geo_mapped ? nullptr : sb.take<float>(n_pages * plane * 8);
     float *d_boxes = sb.take<float>((size_t)n_pages * cap_boxes * 9);
     int32_t *d_cnt = sb.take<int32_t>(n_pages);
@@ -1068,8 +1076,9 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
         const int np = n_pages - p0 < chunk ? n_pages - p0 : chunk;
         cudaEvent_t ev = ctx->chunk_ev[k & 1];
         // the event of chunk k-2 was consumed by the compute stream before chunk k-1 was queued; reuse is safe
-        MS_CUDA(cudaMemcpyAsync(d_score + (size_t)p0 * plane, score + (size_t)p0 * plane, np * plane * 4,
-                                cudaMemcpyHostToDevice, cs));
+        if (!score_dev)
+            MS_CUDA(cudaMemcpyAsync(d_score + (size_t)p0 * plane, score + (size_t)p0 * plane, np * plane * 4,
+                                    cudaMemcpyHostToDevice, cs));
         if (geo_mapped) {
             // nothing to upload
         } else if (geo_compact)
@@ -1092,7 +1101,6 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
     }
     MS_CUDA(cudaMemcpyAsync(box_counts, d_cnt, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaMemcpyAsync(flags, d_flags, (size_t)n_pages * 4, cudaMemcpyDeviceToHost, st));
-    MS_CUDA(cudaMemcpyAsync(boxes_out, d_boxes, (size_t)n_pages * cap_boxes * 36, cudaMemcpyDeviceToHost, st));
     if (want_crops) MS_CUDA(cudaMemcpyAsync(n_crops, d_nc, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
     int32_t all = 0;
@@ -1101,6 +1109,16 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
         return ms_page_batch_host(ctx, score, geo, pages, n_pages, map_h, map_w, img_h, img_w, p, min_text_size, out_h,
                                   out_w, cap_boxes, boxes_out, box_counts, crops_out, crops_cap, n_crops, batch_f32_host,
                                   batch_dev_out, flags);
+    // the boxes come back page by page, only the rows each page has (counts are known now): 36 bytes per box instead
+    // of cap_boxes rows per page; a page's copy runs up to the following pages' rows when they are adjacent anyway
+    {
+        int max_cnt = 0;
+        for (int i = 0; i < n_pages; i++) max_cnt = box_counts[i] > max_cnt ? box_counts[i] : max_cnt;
+        if (max_cnt > cap_boxes) max_cnt = cap_boxes;
+        if (max_cnt > 0)
+            MS_CUDA(cudaMemcpy2DAsync(boxes_out, (size_t)cap_boxes * 36, d_boxes, (size_t)cap_boxes * 36, (size_t)max_cnt * 36,
+                                      (size_t)n_pages, cudaMemcpyDeviceToHost, st));
+    }
     MS_TRY(flags_to_rc(all, "page_batch"));
     if (want_crops) {
         int64_t nc = *n_crops;
@@ -1109,9 +1127,9 @@ extern "C" int ms_page_batch_host(ms_ctx *ctx, const float *score, const float *
             MS_CUDA(cudaMemcpyAsync(crops_out, d_crops, (size_t)nc * 20, cudaMemcpyDeviceToHost, st));
             if (batch_f32_host)
                 MS_CUDA(cudaMemcpyAsync(batch_f32_host, d_batch, (size_t)nc * one_f, cudaMemcpyDeviceToHost, st));
-            MS_CUDA(cudaStreamSynchronize(st));
         }
     }
+    MS_CUDA(cudaStreamSynchronize(st));
     if (batch_dev_out) *batch_dev_out = d_batch;
     return MS_OK;
 }

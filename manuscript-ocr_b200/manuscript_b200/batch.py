@@ -247,7 +247,8 @@ class PageBatch:
         return h
 
     def run_host(self, score, geo, pages=None, check_flags=True):
-        """numpy arrays or (pinned) CPU torch tensors of the shapes of run().  Copies in, runs, copies the
+        """numpy arrays or (pinned) CPU torch tensors of the shapes of run(); score / geo may also be CUDA tensors of
+        this GPU (maps the detector left on the device: used in place, only the page images are uploaded).  Copies in, runs, copies the
         boxes / counts / crop list back and synchronises (ms_page_batch_host).  On MS_FLAG_EDGE_OVERFLOW the library
         grows the NMS pair capacity and runs again; other flags raise (check_flags=False returns them instead).
 
@@ -256,8 +257,19 @@ class PageBatch:
         the numpy results are views of the runner's pinned host buffers with the same rule."""
         torch = self.torch
 
+        class _Dev:  # a CUDA tensor passed where a host array is expected: the library uses it in place
+            def __init__(self, t):
+                assert t.dtype == torch.float32 and t.device == self_device, "device maps must be float32 on this GPU"
+                self.t = t.contiguous()
+                self.shape, self.ndim = tuple(self.t.shape), self.t.dim()
+                self.ctypes = type("P", (), {"data": self.t.data_ptr()})
+
+        self_device = self.device
+
         def as_np(a, dtype):
             if isinstance(a, torch.Tensor):
+                if a.is_cuda:
+                    return _Dev(a)
                 a = a.numpy()
             a = np.asarray(a)
             if a.dtype != dtype or not a.flags.c_contiguous:
@@ -266,8 +278,7 @@ class PageBatch:
 
         s = as_np(score, np.float32)
         if s.ndim == 4:
-            s = s[:, 0]
-            s = np.ascontiguousarray(s)
+            s = as_np(score[:, 0], np.float32) if isinstance(s, _Dev) else np.ascontiguousarray(s[:, 0])
         g = as_np(geo, np.float32)
         P, H, W = s.shape
         assert g.shape == (P, 8, H, W), g.shape

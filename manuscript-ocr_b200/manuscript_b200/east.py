@@ -23,19 +23,33 @@ from .types import Block, Page, Word
 DEFAULT_WEIGHTS = Path.home() / ".manuscript" / "east" / "east_quad_23_05.pth"  # infer.py:101-103
 
 
+_WORD_FIELDS = frozenset(("polygon", "detection_confidence"))
+
+
 def words_from_boxes(boxes):
     """(K, 9) float32 rows -> list of Word (infer.py:359-363).  Scores that pydantic would reject (outside 0..1, NaN)
-    go through the validating constructor so that the reference's ValidationError is raised; the others skip the
-    per-word validation, which would otherwise cost more than the kernels."""
+    go through the validating constructor so that the reference's ValidationError is raised; valid rows are built the
+    way BaseModel.model_construct builds them (same attributes, fields_set = the two the reference passes) but without
+    its per-field bookkeeping, which at ~2000 words per page would cost more than every kernel of the path together."""
     b = np.asarray(boxes, dtype=np.float32).reshape(-1, 9)
     if len(b) == 0:
         return []
-    coords = b[:, :8].astype(np.float64).tolist()
+    xy = b[:, :8].astype(np.float64)
+    pts = list(zip(xy[:, 0::2].ravel().tolist(), xy[:, 1::2].ravel().tolist()))  # all (x, y) tuples, made in C
     scores = b[:, 8].astype(np.float64).tolist()
-    ok = bool(np.all((b[:, 8] >= 0.0) & (b[:, 8] <= 1.0)))
-    make = Word.model_construct if ok else Word
-    return [make(polygon=[(c[0], c[1]), (c[2], c[3]), (c[4], c[5]), (c[6], c[7])], detection_confidence=s, text=None,
-                 recognition_confidence=None) for c, s in zip(coords, scores)]
+    if not bool(np.all((b[:, 8] >= 0.0) & (b[:, 8] <= 1.0))):
+        return [Word(polygon=pts[4 * i:4 * i + 4], detection_confidence=s) for i, s in enumerate(scores)]
+    out = []
+    new, setattr_ = object.__new__, object.__setattr__
+    for i, s in enumerate(scores):
+        w = new(Word)
+        setattr_(w, "__dict__", {"polygon": pts[4 * i:4 * i + 4], "detection_confidence": s, "text": None,
+                                 "recognition_confidence": None})
+        setattr_(w, "__pydantic_fields_set__", set(_WORD_FIELDS))
+        setattr_(w, "__pydantic_extra__", None)
+        setattr_(w, "__pydantic_private__", None)
+        out.append(w)
+    return out
 
 
 class EAST:

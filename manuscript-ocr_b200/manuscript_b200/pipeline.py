@@ -124,12 +124,15 @@ class Pipeline:
             results = []
             batch = res.batch[:n]                               # a view of the batch the crop kernel wrote
             for i in range(0, n, rec.batch_size):               # recognizers/_trba/__init__.py:382: chunks of 32
-                results.extend(rec.predict_batch(batch[i:i + rec.batch_size]))
+                results.extend(rec.model(batch[i:i + rec.batch_size]))
             if profile:
                 torch.cuda.synchronize()
                 print(f"Recognition: {time.time() - t0:.3f}s")
-            for j, result in zip(np.flatnonzero(valid), results):
-                words[j].text, words[j].recognition_confidence = _text_and_confidence(result)
+            for j, result in zip(np.flatnonzero(valid).tolist(), results):
+                text, conf = _text_and_confidence(result)
+                d = words[j].__dict__  # Word has no validate_assignment (nor has the reference's): plain attribute writes
+                d["text"], d["recognition_confidence"] = text, conf
+                words[j].__pydantic_fields_set__.update(("text", "recognition_confidence"))
         return page
 
     # ---- routes 2 and 3: a Page from any detector ---------------------------------------------------------------------

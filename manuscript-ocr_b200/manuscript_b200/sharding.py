@@ -23,6 +23,54 @@ def gather_page_results(local_results, world_size=None, group=None):
     return out
 
 
+def gather_to_root(local_results, root=0, group=None):
+    """As gather_page_results, but only `root` receives the corpus (BASELINE configs[4]: "results are gathered on the
+    host"): returns the list in global page order on root, None elsewhere."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()):
+        return list(local_results)
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    gathered = [None] * world if rank == root else None
+    dist.gather_object(list(local_results), gathered, dst=root, group=group)
+    if rank != root:
+        return None
+    out = []
+    for part in gathered:
+        out.extend(part)
+    return out
+
+
+def prefer_numa_node_of_gpu(device_index):
+    """Ask the kernel to place this process's future allocations (the pinned host buffers) on the NUMA node the GPU hangs
+    off, even when the CPU set cannot be narrowed (a container whose cpuset shows one socket): set_mempolicy(
+    MPOL_PREFERRED, node).  Returns the node, or None when it is unknown or the call is refused (best effort)."""
+    import ctypes
+    import os
+
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(int(device_index))).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]
+        with open(f"/sys/bus/pci/devices/{bdf}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        libc = ctypes.CDLL(None, use_errno=True)
+        mask = ctypes.c_ulong(1 << node)
+        MPOL_PREFERRED, SYS_set_mempolicy = 1, 238  # x86_64
+        if os.uname().machine != "x86_64":
+            return None
+        rc = libc.syscall(SYS_set_mempolicy, MPOL_PREFERRED, ctypes.byref(mask), ctypes.c_ulong(64))
+        return node if rc == 0 else None
+    except Exception:
+        return None
+
+
 def run_sharded(n_pages, page_fn, group=None):
     """Run page_fn(page_index) for this rank's shard and gather every page's result on the host."""
     import torch.distributed as dist
@@ -60,4 +108,5 @@ def bind_to_gpu_cpus(device_index):
         return None
 
 
-__all__ = ["shard_pages", "gather_page_results", "run_sharded", "bind_to_gpu_cpus"]
+__all__ = ["shard_pages", "gather_page_results", "gather_to_root", "run_sharded", "bind_to_gpu_cpus",
+           "prefer_numa_node_of_gpu"]

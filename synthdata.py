@@ -48,7 +48,7 @@ def _rect(cx, cy, w, h, ang):
     return np.stack([x, y], axis=2)
 
 
-def make_maps(seed, page=1280, n_words=500, stride=4, noise=0.05, halo=2.0, bg_hi=0.3):
+def make_maps(seed, page=1280, n_words=500, stride=4, noise=0.05, halo=2.0, bg_hi=0.3, shrink=0.3):
     """Returns score (M,M) f32, geo (8,M,M) f32 [network layout], gt quads (n,4,2) f64."""
     rng = np.random.default_rng(seed)
     M = page // stride
@@ -57,7 +57,7 @@ def make_maps(seed, page=1280, n_words=500, stride=4, noise=0.05, halo=2.0, bg_h
     geo = np.zeros((8, M, M), np.float32)
 
     # shrunk score region, in map pixels, in each word's local frame
-    r = 0.3 * np.minimum(w, h)
+    r = shrink * np.minimum(w, h)
     hw_s = (w / 2 - r) / stride
     hh_s = (h / 2 - r) / stride
     mcx, mcy = cx / stride, cy / stride
@@ -93,10 +93,10 @@ def make_page_image(seed, page=1280, channels=3):
     return rng.integers(0, 256, (page, page, channels), dtype=np.uint8)
 
 
-def make_batch(seeds, page, n_words, with_images=True):
+def make_batch(seeds, page, n_words, with_images=True, shrink=0.3):
     scores, geos, imgs = [], [], []
     for s in seeds:
-        sc, ge, _ = make_maps(s, page, n_words)
+        sc, ge, _ = make_maps(s, page, n_words, shrink=shrink)
         scores.append(sc)
         geos.append(ge)
         if with_images:

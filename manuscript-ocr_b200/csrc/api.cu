@@ -265,6 +265,11 @@ static int flags_to_rc(int32_t f, const char *where)
         ms_set_error("%s: NMS suppression-edge buffer exceeded", where);
         return MS_ERR_CAPACITY;
     }
+    if (f & MS_FLAG_ORDER_OVERFLOW) {
+        ms_set_error("%s: a page exceeds the device reading-order capacity (4096 boxes / 28672 intersecting pairs); run "
+                     "with sort_reading_order = 0 and order the boxes on the host", where);
+        return MS_ERR_CAPACITY;
+    }
     return MS_OK;
 }
 
@@ -343,7 +348,7 @@ extern "C" int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n
     }
     if (n == 0) return MS_OK;
     if (n > 4096) {
-        ms_set_error("ms_reading_order_host: at most 4096 boxes per page (got %lld)", (long long)n);
+        ms_set_error("ms_reading_order_host: more than 4096 boxes on the page (got %lld)", (long long)n);
         return MS_ERR_CAPACITY;
     }
     const int cap = (int)n;
@@ -368,7 +373,7 @@ extern "C" int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n
     MS_CUDA(cudaMemcpyAsync(order, d_o, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaMemcpyAsync(h + 4, d_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
-    if (h[4] & MS_FLAG_EDGE_OVERFLOW) {
+    if (h[4] & MS_FLAG_ORDER_OVERFLOW) {
         ms_set_error("ms_reading_order_host: more than 28672 intersecting box pairs on the page");
         return MS_ERR_CAPACITY;
     }

@@ -134,9 +134,17 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     const int page = blockIdx.x;
     const int K = counts[page];
     const size_t pb = (size_t)page * cap;
+    // beyond the capacity of this kernel the page keeps its detection order and is flagged (the host side orders it)
+    auto keep_detection_order = [&]() {
+        if (threadIdx.x == 0) atomicOr(flags + page, MS_FLAG_ORDER_OVERFLOW);
+        for (int k = threadIdx.x; k < K; k += kRoThreads) {
+            order[pb + k] = k;
+            if (reordered)
+                for (int c = 0; c < row_stride; c++) reordered[(pb + k) * row_stride + c] = boxes8[(pb + k) * row_stride + c];
+        }
+    };
     if (K > kRoMaxBoxes) {
-        if (threadIdx.x == 0) atomicOr(flags + page, MS_FLAG_CAND_OVERFLOW);
-        for (int k = threadIdx.x; k < K; k += kRoThreads) order[pb + k] = k;
+        keep_detection_order();
         return;
     }
     // A. integer boxes (_pipeline.py:105-109)
@@ -322,10 +330,13 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
             }
         }
     }
+    if (overflow) {  // uniform over the CTA: `run` comes out of block scans
+        keep_detection_order();
+        return;
+    }
     if (threadIdx.x == 0) {
         s_np = run;
         row_start[K] = (uint16_t)run;
-        if (overflow) atomicOr(flags + page, MS_FLAG_EDGE_OVERFLOW);
     }
     __syncthreads();
 

@@ -20,6 +20,7 @@ MS_ERR_NO_DEVICE = -5
 MS_FLAG_CAND_OVERFLOW = 1
 MS_FLAG_INDEX_ERROR = 2
 MS_FLAG_EDGE_OVERFLOW = 4
+MS_FLAG_ORDER_OVERFLOW = 8
 
 
 class CABIError(RuntimeError):

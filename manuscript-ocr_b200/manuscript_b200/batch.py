@@ -13,7 +13,8 @@ from dataclasses import dataclass
 
 import numpy as np
 
-from ._cabi import MS_FLAG_CAND_OVERFLOW, MS_FLAG_EDGE_OVERFLOW, MS_FLAG_INDEX_ERROR, CABIError, Context, EastParams, check
+from ._cabi import (MS_FLAG_CAND_OVERFLOW, MS_FLAG_EDGE_OVERFLOW, MS_FLAG_INDEX_ERROR, MS_FLAG_ORDER_OVERFLOW, CABIError,
+                    Context, EastParams, check)
 
 
 def shard_pages(n_pages, world_size, rank):
@@ -32,7 +33,8 @@ class PageBatchResult:
     """Results of one batch.  They are VALID ONLY WHEN `flags` is all zero (see raise_for_flags): a page flagged
     MS_FLAG_EDGE_OVERFLOW was resolved with suppression edges missing (boxes that should be gone are returned),
     MS_FLAG_CAND_OVERFLOW means rows were truncated at cap_boxes, MS_FLAG_INDEX_ERROR is where the reference raises
-    IndexError (utils.py:370).  The tensors are owned by the PageBatch runner and are overwritten by its next call of
+    IndexError (utils.py:370), MS_FLAG_ORDER_OVERFLOW (only with sort_reading_order) means the page is correct but still
+    in detection order.  The tensors are owned by the PageBatch runner and are overwritten by its next call of
     the same kind and page count: clone() what has to outlive it."""
     boxes: object        # (P, cap_boxes, 9) f32: rows [0, box_counts[p]) are page p's final boxes
     box_counts: object   # (P,) int32
@@ -49,20 +51,35 @@ class PageBatchResult:
         f = self.flags
         return f.cpu().numpy() if hasattr(f, "cpu") else np.asarray(f)
 
-    def raise_for_flags(self):
-        """IndexError / CABIError exactly as the *_host entry points raise them; returns self when all pages are clean."""
-        _raise_for_flags(self.flags_host())
+    def raise_for_flags(self, allow_order_overflow=False):
+        """IndexError / CABIError exactly as the *_host entry points raise them; returns self when all pages are clean.
+        allow_order_overflow: pages flagged MS_FLAG_ORDER_OVERFLOW (valid, but in detection order) do not raise."""
+        _raise_for_flags(self.flags_host(), allow_order_overflow)
         return self
 
+    def order_overflow_pages(self):
+        """Indices of the pages whose reading order was left to the host (MS_FLAG_ORDER_OVERFLOW)."""
+        return np.flatnonzero(self.flags_host().reshape(-1) & MS_FLAG_ORDER_OVERFLOW)
 
-def _raise_for_flags(flags):
+
+class ReadingOrderCapacity(CABIError):
+    """MS_FLAG_ORDER_OVERFLOW: the results are valid but in detection order; order them with the host restatement
+    (manuscript_b200.reading_order) -- Pipeline.predict and reorder_words do that by themselves."""
+
+
+def _raise_for_flags(flags, allow_order_overflow=False):
     f = int(np.bitwise_or.reduce(np.asarray(flags).reshape(-1))) if len(flags) else 0
+    if allow_order_overflow:
+        f &= ~MS_FLAG_ORDER_OVERFLOW
     if f & MS_FLAG_INDEX_ERROR:
         raise IndexError("quantised pixel index outside the map (the reference raises IndexError at utils.py:370)")
     if f & MS_FLAG_CAND_OVERFLOW:
         raise CABIError(-3, "more boxes than cap_boxes on at least one page")
     if f & MS_FLAG_EDGE_OVERFLOW:
         raise CABIError(-3, "NMS suppression-edge buffer exceeded")
+    if f & MS_FLAG_ORDER_OVERFLOW:
+        raise ReadingOrderCapacity(-3, "a page exceeds the device reading-order capacity (4096 boxes / 28672 intersecting "
+                                       "pairs): its boxes and crops are in detection order")
 
 
 class PageBatch:
@@ -149,7 +166,7 @@ class PageBatch:
                 b["flags"].data_ptr(), C.c_void_p(stream)))
         return PageBatchResult(b["boxes"], b["counts"], b["crops"], b["n_crops"], b["batch"], b["flags"])
 
-    def run_ragged(self, score, geo, pages, sync=False):
+    def run_ragged(self, score, geo, pages, sync=False, allow_order_overflow=False):
         """As run(), for page images of their own sizes: `pages` is a list of P CUDA uint8 tensors (H_i, W_i, 3) -- the
         original images, while the maps come from the detector's fixed target_size.  Boxes are scaled to each page's
         size and crops are cut from its pixels (EAST.predict + Pipeline.predict semantics).  `sync` as in run()."""
@@ -160,7 +177,7 @@ class PageBatch:
                 if (f & MS_FLAG_EDGE_OVERFLOW) and not (f & (MS_FLAG_INDEX_ERROR | MS_FLAG_CAND_OVERFLOW)) \
                         and self.ctx.grow_edge_factor():
                     continue
-                return res.raise_for_flags()
+                return res.raise_for_flags(allow_order_overflow)
         torch = self.torch
         if score.dim() == 4:
             score = score[:, 0]

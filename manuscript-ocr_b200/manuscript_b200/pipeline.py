@@ -107,10 +107,17 @@ class Pipeline:
         page_dev = det.upload(img)                              # the one H2D copy of pixels
         score, geo = det.maps_from_device_page(page_dev)        # network input + maps stay on the device
         runner = self._fused_runner()
-        res = runner.run_ragged(score[None] if score.dim() == 2 else score, geo[None], [page_dev], sync=True)
+        res = runner.run_ragged(score[None] if score.dim() == 2 else score, geo[None], [page_dev], sync=True,
+                                allow_order_overflow=True)
         k = int(res.box_counts[0])
         n = int(res.n_crops[0])
         boxes = res.boxes[0, :k].cpu().numpy()                  # D2H: K x 36 bytes
+        if len(res.order_overflow_pages()):
+            # more boxes (or intersecting pairs) than the device reading-order kernel holds: the boxes came back in
+            # detection order; order them with the host restatement and cut the crops from the uploaded page
+            page = Page(blocks=[Block(words=words_from_boxes(boxes))])
+            self.last_route = "fused+host_order"
+            return self._finish_from_page(page, img, profile, page_dev=page_dev)
         crops = res.crops[:n].cpu().numpy()                     # D2H: n x 20 bytes
         if profile:
             print(f"Detection + crops (device): {time.time() - t0:.3f}s")
@@ -183,16 +190,27 @@ class Pipeline:
             results.extend(rec.predict_batch(kept_batch[i:i + rec.batch_size]))
         return [w for w, ok in zip(words, valid) if ok], results
 
-    def _recognise(self, image_array, rects):
+    def _finish_from_page(self, page, image_array, profile, page_dev=None):
+        """Routes 2 / 3 from a detector's Page: reading order, crop rectangles, recognition, text written back."""
+        words, rects = self._ordered_crop_rects(page, *image_array.shape[:2])
+        if words:
+            results = self._recognise(image_array, rects, page_dev=page_dev)
+            for word, result in zip(words, results):
+                word.text, word.recognition_confidence = _text_and_confidence(result)
+        return page
+
+    def _recognise(self, image_array, rects, page_dev=None):
         rec = self.recognizer
         if not isinstance(rec, TRBA):
             self.last_route = "host_crops"
             return rec.predict([image_array[y1:y2, x1:x2] for x1, y1, x2, y2 in rects])
         # the page goes to the device once; every recogniser batch is cut from that copy and never visits the host
-        self.last_route = "device_crops"
+        if self.last_route != "fused+host_order":
+            self.last_route = "device_crops"
         torch = rec.torch
-        rgb = np.ascontiguousarray(TRBA._as_rgb(image_array))
-        page_dev = torch.from_numpy(rgb).to(rec.device)
+        if page_dev is None:
+            rgb = np.ascontiguousarray(TRBA._as_rgb(image_array))
+            page_dev = torch.from_numpy(rgb).to(rec.device)
         crops = np.zeros((len(rects), 5), np.int32)
         crops[:, 1:] = rects
         batch = rec.crops_to_batch(page_dev, torch.from_numpy(crops).to(rec.device), len(rects))

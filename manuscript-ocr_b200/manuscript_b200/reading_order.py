@@ -117,14 +117,29 @@ def int_bbox(polygon):
     return (x_min, y_min, x_max, y_max)
 
 
+def host_word_order(polys8):
+    """(n, 8) float polygons -> (n,) int32, order[r] = index of the word at reading position r: _pipeline.py:105-123 on
+    the host (int32 truncation, sort with resolutions, first word of equal integer box).  float32 -> int32 truncation
+    is done the way np.array(polygon, dtype=np.int32) does it."""
+    p = np.asarray(polys8, dtype=np.float64).reshape(len(polys8), -1)[:, :8]
+    ip = p.astype(np.int32)
+    xs, ys = ip[:, 0::2], ip[:, 1::2]
+    keys = list(zip(xs.min(1).tolist(), ys.min(1).tolist(), xs.max(1).tolist(), ys.max(1).tolist()))
+    first = {}
+    for i, k in enumerate(keys):
+        first.setdefault(k, i)
+    return np.array([first[tuple(int(v) for v in bx)] for bx in sort_boxes_reading_order_with_resolutions(keys)],
+                    dtype=np.int32)
+
+
 def reorder_words(words, on_device=True):
     """_pipeline.py:105-123 / infer.py:361-385: words re-ordered to follow the sorted boxes; each sorted box
     picks the FIRST word with equal integer bbox (duplicates resolve the way the reference's loop does).
-    Pages of up to 4096 words are ordered by the CUDA kernel (ms_reading_order_host); larger ones by the exact
-    host restatement below (this step is host logic in the reference too)."""
+    Ordered by the CUDA kernel (ms_reading_order_host) up to its capacity, by the exact host restatement beyond
+    (this step is host logic in the reference too)."""
     if len(words) == 0:
         return []
-    if on_device and len(words) <= 4096 and all(len(w.polygon) == 4 for w in words):
+    if on_device and all(len(w.polygon) == 4 for w in words):
         from . import ops
 
         polys = np.array([w.polygon for w in words], dtype=np.float32).reshape(len(words), 8)
@@ -134,4 +149,3 @@ def reorder_words(words, on_device=True):
     for i, k in enumerate(keys):
         first.setdefault(k, i)
     return [words[first[tuple(int(v) for v in bx)]] for bx in sort_boxes_reading_order_with_resolutions(keys)]
-

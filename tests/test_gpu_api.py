@@ -475,3 +475,58 @@ def test_pipeline_fused_route_is_device_resident_and_exact(mb):
     batches.clear()
     again = pipe.predict(img)
     assert [w.polygon for w in again.blocks[0].words] == [w.polygon for w in got_words]
+
+
+# ---- reading order beyond the device kernel's capacity: flagged, never wrong, ordered by the host restatement ----------
+def test_reading_order_beyond_device_capacity(mb, golden_dir):
+    """BASELINE configs[3] (10 000 boxes > 4096) and a page of 3000 boxes with > 28 672 intersecting pairs: the device
+    stage leaves the page in detection order and flags it (MS_FLAG_ORDER_OVERFLOW); word_reading_order / reorder_words /
+    Pipeline.predict then use the exact host restatement.  The 10 000-box order is the REAL reference's (committed by
+    tests/golden/make_golden_large.py)."""
+    import torch
+
+    from manuscript_b200._cabi import MS_FLAG_ORDER_OVERFLOW
+
+    g = np.load(os.path.join(golden_dir, "large_pages.npz"))
+    page, words = 4096, 10000
+    score, geo, _ = synthdata.make_maps(3, page, words)
+    img = synthdata.make_page_image(3, page)
+    plain = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page), cap_boxes=16384, want_batch=False)
+    final = plain.run(torch.from_numpy(score[None]).cuda(), torch.from_numpy(geo[None]).cuda(), None,
+                      sync=True).page_boxes(0).cpu().numpy()
+    assert len(final) == int(g["cfg3_n_final"])
+    order = mb.word_reading_order(final[:, :8])            # 10 000 boxes: host restatement
+    np.testing.assert_array_equal(order, g["cfg3_order"])  # == the reference's order
+    ro = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page, sort_reading_order=1), cap_boxes=16384,
+                      crops_cap=12000)
+    res = ro.run(torch.from_numpy(score[None]).cuda(), torch.from_numpy(geo[None]).cuda(),
+                 torch.from_numpy(img[None]).cuda(), sync=False)
+    torch.cuda.synchronize()
+    assert int(res.flags.cpu()[0]) == MS_FLAG_ORDER_OVERFLOW and list(res.order_overflow_pages()) == [0]
+    np.testing.assert_array_equal(res.page_boxes(0).cpu().numpy(), final)  # detection order, every row intact
+    with pytest.raises(mb.CABIError):
+        res.raise_for_flags()
+    res.raise_for_flags(allow_order_overflow=True)
+
+    # the whole thing through Pipeline.predict: fused route, host order, crops cut from the one uploaded page
+    class Net:
+        def __call__(self, x):
+            return {"score": torch.from_numpy(score)[None, None].cuda(), "geometry": torch.from_numpy(geo)[None].cuda()}
+
+    seen = []
+    rec = mb.TRBA(model=lambda b: (seen.append(len(b)), [("t", 0.5)] * len(b))[1], img_h=32, img_w=128, batch_size=512)
+    pipe = mb.Pipeline(detector=mb.EAST(model=Net(), target_size=page, cap_boxes=16384), recognizer=rec)
+    pg = pipe.predict(img)
+    assert pipe.last_route == "fused+host_order"
+    got = np.array([[v for pt in w.polygon for v in pt] for w in pg.blocks[0].words], np.float32)
+    np.testing.assert_array_equal(got, final[g["cfg3_order"], :8])
+    assert sum(seen) == sum(1 for w in pg.blocks[0].words if w.text == "t") == 10000
+
+    # <= 4096 boxes but far too many intersecting pairs
+    rng = np.random.default_rng(7)
+    n = 3000
+    x0, y0 = rng.integers(0, 300, n), rng.integers(0, 300, n)
+    bx = np.stack([x0, y0, x0 + rng.integers(20, 80, n), y0 + rng.integers(10, 40, n)], axis=1)
+    polys = _boxes_to_polys(bx)
+    got = mb.word_reading_order(polys)
+    assert list(got) == _host_order(mb, bx)

@@ -264,7 +264,7 @@ def run_b200(a):
     dev = torch.device("cuda", local)
     # one process per GPU: stay on the cores (and NUMA node) next to this GPU before pinning host memory; when the
     # container's CPU set hides the GPU's socket, at least ask for the memory to be placed there
-    from manuscript_b200.sharding import bind_to_gpu_cpus, gather_to_root, prefer_numa_node_of_gpu, shard_pages
+    from manuscript_b200.sharding import bind_to_gpu_cpus, gather_boxes_via_shm, prefer_numa_node_of_gpu, shard_pages
 
     cpus = bind_to_gpu_cpus(local)
     numa_node = prefer_numa_node_of_gpu(local)
@@ -280,6 +280,9 @@ def run_b200(a):
         _REAL_STDOUT = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
         dist.init_process_group("nccl", device_id=dev)
+    # results are gathered on the HOST (BASELINE configs[4]): a gloo group carries the pickled per-page results, the
+    # NCCL group only the barriers and the reductions of the timings
+    host_group = dist.new_group(backend="gloo") if dist is not None else None
 
     def barrier():
         if dist is not None:
@@ -476,30 +479,35 @@ def run_b200(a):
         n_mine = len(mine)
 
         def corpus_pass():
-            out = []
+            cnts, rows = [], []
             for c0 in range(0, n_mine, P):
                 n = min(P, n_mine - c0)
                 r = runner.run_host(h_score[:n], h_geo[:n], h_pages[:n])
                 cnt = r.box_counts[:n].copy()
-                out.extend((int(mine[c0 + i]), r.boxes[i, : cnt[i]].copy()) for i in range(n))
-            return out
+                cnts.append(cnt)
+                rows.extend(r.boxes[i, : cnt[i]].copy() for i in range(n))
+            return np.concatenate(cnts), np.concatenate(rows)
 
         corpus_pass()
+        gather_boxes_via_shm(np.zeros(1, np.int32), np.zeros((1, 9), np.float32), group=host_group)  # connections up
         barrier()
         torch.cuda.synchronize()
         t0 = time.perf_counter()
-        local_res = corpus_pass()
-        gathered = gather_to_root(local_res)
+        local_cnt, local_rows = corpus_pass()
+        gathered = gather_boxes_via_shm(local_cnt, local_rows, group=host_group)
         t_corpus = max_over_ranks(time.perf_counter() - t0)
         barrier()
         if rank == 0:
-            assert [g[0] for g in gathered] == list(range(a.corpus)), "gathered corpus is not in page order"
+            g_cnt, g_rows = gathered
+            assert len(g_cnt) == a.corpus and len(g_rows) == int(g_cnt.sum()), "gathered corpus is incomplete"
+            assert np.array_equal(g_rows[: int(g_cnt[0])], local_rows[: int(local_cnt[0])])
             corpus = {"pages": a.corpus, "pages_per_s": a.corpus / t_corpus, "seconds": t_corpus, "scaling": "strong",
-                      "boxes_gathered": int(sum(len(g[1]) for g in gathered)),
+                      "boxes_gathered": int(len(g_rows)),
                       "note": f"BASELINE configs[4]: {a.corpus} page instances (this rank's {P} synthetic pages, cycled) "
                               f"page-sharded over {world} GPU(s) by shard_pages, every chunk of {P} pages through "
                               "ms_page_batch_host from pinned host memory, every page's boxes gathered on rank 0's host "
-                              "(gather_object) inside the timed region; crop batches stay on their GPU for the recogniser"}
+                              "(POSIX shared memory between the ranks of the box, sizes and barriers over a gloo group) inside the timed region; crop batches stay on their GPU "
+                              "for the recogniser"}
     t_wall2 = time.perf_counter()
     if rank == 0:
         sampler.stop()

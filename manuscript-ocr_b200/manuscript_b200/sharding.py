@@ -41,6 +41,95 @@ def gather_to_root(local_results, root=0, group=None):
     return out
 
 
+def gather_boxes_to_root(counts, rows, root=0, group=None):
+    """Host gather of a rank's per-page results without pickling: counts (n_pages_local,) int32 and rows (sum(counts), 9)
+    float32 (its pages' boxes, concatenated in page order) go to `root` as two flat CPU tensors over `group` (gloo).
+    Returns (counts_all, rows_all) in global page order on root -- ranks own contiguous page ranges, so rank order is page
+    order -- and None elsewhere."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    counts = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1)
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 9)
+    if not (dist.is_available() and dist.is_initialized()):
+        return counts, rows
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    sizes = torch.tensor([len(counts), len(rows)], dtype=torch.int64)
+    all_sizes = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    max_p, max_r = int(max(t[0] for t in all_sizes)), int(max(t[1] for t in all_sizes))
+    c_pad = torch.zeros(max_p, dtype=torch.int32)
+    c_pad[: len(counts)] = torch.from_numpy(counts)
+    r_pad = torch.zeros((max_r, 9), dtype=torch.float32)
+    r_pad[: len(rows)] = torch.from_numpy(rows)
+    c_all = [torch.empty_like(c_pad) for _ in range(world)] if rank == root else None
+    r_all = [torch.empty_like(r_pad) for _ in range(world)] if rank == root else None
+    dist.gather(c_pad, c_all, dst=root, group=group)
+    dist.gather(r_pad, r_all, dst=root, group=group)
+    if rank != root:
+        return None
+    cs = [c_all[r][: int(all_sizes[r][0])].numpy() for r in range(world)]
+    rs = [r_all[r][: int(all_sizes[r][1])].numpy() for r in range(world)]
+    return np.concatenate(cs), np.concatenate(rs)
+
+
+def gather_boxes_via_shm(counts, rows, root=0, group=None, tag="msb200"):
+    """gather_boxes_to_root for the ranks of ONE box, through POSIX shared memory instead of sockets: every rank writes
+    its counts and rows into its own /dev/shm segment, the root maps them and concatenates (memcpy speed; the process
+    group only carries the sizes and two barriers).  Falls back to gather_boxes_to_root when /dev/shm is unusable."""
+    import os
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    counts = np.ascontiguousarray(counts, dtype=np.int32).reshape(-1)
+    rows = np.ascontiguousarray(rows, dtype=np.float32).reshape(-1, 9)
+    if not (dist.is_available() and dist.is_initialized()):
+        return counts, rows
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    base = f"/dev/shm/{tag}_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
+    ok = os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK)
+    flag = torch.tensor([1 if ok else 0], dtype=torch.int64)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+    if int(flag[0]) == 0:
+        return gather_boxes_to_root(counts, rows, root, group)
+    sizes = torch.tensor([len(counts), len(rows)], dtype=torch.int64)
+    all_sizes = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    dist.all_gather(all_sizes, sizes, group=group)
+    path = f"{base}_{rank}"
+    nbytes = counts.nbytes + rows.nbytes
+    if rank != root and nbytes:
+        mm = np.memmap(path, dtype=np.uint8, mode="w+", shape=(nbytes,))
+        mm[: counts.nbytes] = counts.view(np.uint8)
+        mm[counts.nbytes:] = rows.reshape(-1).view(np.uint8)
+        mm.flush()
+        del mm
+    dist.barrier(group=group)
+    out = None
+    if rank == root:
+        cs, rs = [], []
+        for r in range(world):
+            n_c, n_r = int(all_sizes[r][0]), int(all_sizes[r][1])
+            if r == root:
+                cs.append(counts)
+                rs.append(rows)
+            elif n_c or n_r:
+                mm = np.memmap(f"{base}_{r}", dtype=np.uint8, mode="r", shape=(n_c * 4 + n_r * 36,))
+                cs.append(np.array(mm[: n_c * 4]).view(np.int32))
+                rs.append(np.array(mm[n_c * 4:]).view(np.float32).reshape(-1, 9))
+                del mm
+        out = (np.concatenate(cs), np.concatenate(rs))
+    dist.barrier(group=group)
+    if rank != root and nbytes:
+        try:
+            os.unlink(path)
+        except OSError:
+            pass
+    return out
+
+
 def prefer_numa_node_of_gpu(device_index):
     """Ask the kernel to place this process's future allocations (the pinned host buffers) on the NUMA node the GPU hangs
     off, even when the CPU set cannot be narrowed (a container whose cpuset shows one socket): set_mempolicy(
@@ -108,5 +197,5 @@ def bind_to_gpu_cpus(device_index):
         return None
 
 
-__all__ = ["shard_pages", "gather_page_results", "gather_to_root", "run_sharded", "bind_to_gpu_cpus",
+__all__ = ["shard_pages", "gather_page_results", "gather_to_root", "gather_boxes_to_root", "gather_boxes_via_shm", "run_sharded", "bind_to_gpu_cpus",
            "prefer_numa_node_of_gpu"]

@@ -107,6 +107,15 @@ MS_API int ms_decode_quads_host(ms_ctx *ctx, const float *score, const float *ge
                          float score_thresh, double scale, int quantization, float *quads_out,
                          int64_t cap, int64_t *n_out);
 
+/* north_star's RBOX geometry decode -- NOT a reference behaviour (the reference's head is QUAD only: detectors/_east/
+ * east.py:99-100, utils.py:368-376), "parity unpinned".  Same thresholding, quantisation and row order as
+ * ms_decode_quads_host; geo5 (5,map_h,map_w) f32 = distances to the top, right, bottom, left edge of the rotated word
+ * rectangle (map units) and its angle (radians); rows are the rectangle's corners TL,TR,BR,BL + score, by the closed
+ * form of the public EAST implementations (restore_rectangle_rbox) in float64. */
+MS_API int ms_decode_rbox_host(ms_ctx *ctx, const float *score, const float *geo5, int map_h, int map_w,
+                        float score_thresh, double scale, int quantization, float *quads_out, int64_t cap,
+                        int64_t *n_out);
+
 /* replaces locality_aware_nms, detectors/_east/lanms.py:156 (called infer.py:332).
  * boxes (n,9) f32 -> out (<=n,9) f32 in descending-score order. */
 MS_API int ms_lanms_host(ms_ctx *ctx, const float *boxes, int64_t n, double iou_threshold, float *out,
@@ -185,6 +194,11 @@ MS_API int ms_decode_quads(ms_ctx *ctx, const float *score, const float *geo, in
                     float score_thresh, double scale, int quantization, float *quads_out,
                     int cap_per_page, int32_t *counts, int32_t *flags, void *stream);
 
+/* ms_decode_rbox_host for n_pages maps on the device: geo5 (n_pages,5,map_h,map_w). */
+MS_API int ms_decode_rbox(ms_ctx *ctx, const float *score, const float *geo5, int n_pages, int map_h, int map_w,
+                   float score_thresh, double scale, int quantization, float *quads_out, int cap_per_page,
+                   int32_t *counts, int32_t *flags, void *stream);
+
 /* lanms.py:156 for n_pages candidate lists (page-strided in, page-strided out). */
 MS_API int ms_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
              double iou_threshold, float *quads_out, int32_t *counts_out, int32_t *flags, void *stream);
@@ -228,6 +242,17 @@ MS_API int ms_quad_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_page
                             const float *quads, int quad_stride, const int32_t *page_of, int64_t n,
                             int min_text_size, int border_mode, int border_value, int out_h, int out_w,
                             float *batch_f32, uint8_t *canvas_u8, int32_t *sizes_out, void *stream);
+
+/* north_star's "TPS rectification grid_sample" -- NOT a reference behaviour (the reference's TRBAModel has no
+ * transformation stage, recognizers/_trba/model/model.py:338-393), "parity unpinned"; specified as the
+ * TPS-STN of the TRBA literature and checked against torch.nn.functional.grid_sample.  All pointers on the device:
+ * input (batch,chans,in_h,in_w) f32, c_prime (batch,n_fid,2) f32 predicted fiducial points in [-1,1],
+ * inv_delta_c (n_fid+3,n_fid+3) f32 and p_hat_t (n_fid+3, out_h*out_w) f32 (the TRANSPOSED P_hat) as
+ * manuscript_b200.tps.TPSGrid computes them; out (batch,chans,out_h,out_w) f32 =
+ * grid_sample(input, P_hat @ inv_delta_c @ [c_prime; 0], bilinear, padding_mode="border", align_corners=True). */
+MS_API int ms_tps_rectify(ms_ctx *ctx, const float *input, const float *c_prime, const float *inv_delta_c,
+                   const float *p_hat_t, int batch, int n_fid, int chans, int in_h, int in_w, int out_h, int out_w,
+                   float *out, void *stream);
 
 /* decode -> LANMS -> expand/filters -> word rects -> crop batch in one call (device buffers).
  * boxes_out (n_pages*cap_boxes,9), box_counts (n_pages); crops_out/n_crops/batch as above. */

@@ -293,6 +293,23 @@ extern "C" int ms_decode_quads(ms_ctx *ctx, const float *score, const float *geo
                       cap_per_page, counts, flags, bump, (cudaStream_t)stream);
 }
 
+extern "C" int ms_decode_rbox(ms_ctx *ctx, const float *score, const float *geo5, int n_pages, int map_h, int map_w,
+                              float score_thresh, double scale, int quantization, float *quads_out, int cap_per_page,
+                              int32_t *counts, int32_t *flags, void *stream)
+{
+    MS_CTX(ctx);
+    if (n_pages <= 0) return MS_OK;
+    if (!score || !geo5 || !quads_out || !counts || !flags) {
+        ms_set_error("ms_decode_rbox: NULL pointer");
+        return MS_ERR_INVALID;
+    }
+    if (quantization < 1) quantization = 1;
+    MS_TRY(ms_arena_reserve(ctx, msk_decode_scratch(n_pages, map_h, map_w, quantization)));
+    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    return msk_decode(ctx, score, geo5, n_pages, map_h, map_w, score_thresh, scale, quantization, quads_out, cap_per_page,
+                      counts, flags, bump, (cudaStream_t)stream, 0, 1);
+}
+
 extern "C" int ms_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                         double iou_threshold, float *quads_out, int32_t *counts_out, int32_t *flags, void *stream)
 {
@@ -421,6 +438,15 @@ extern "C" int ms_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, in
 {
     MS_CTX(ctx);
     return msk_detector_input(ctx, page, img_h, img_w, target_h, target_w, out_f32, out_u8, (cudaStream_t)stream);
+}
+
+extern "C" int ms_tps_rectify(ms_ctx *ctx, const float *input, const float *c_prime, const float *inv_delta_c,
+                              const float *p_hat_t, int batch, int n_fid, int chans, int in_h, int in_w, int out_h,
+                              int out_w, float *out, void *stream)
+{
+    MS_CTX(ctx);
+    return msk_tps_rectify(ctx, input, c_prime, inv_delta_c, p_hat_t, batch, n_fid, chans, in_h, in_w, out_h, out_w, out,
+                           (cudaStream_t)stream);
 }
 
 // candidate capacity per page that can never overflow: one row per quantisation cell (utils.py:347-356)
@@ -623,11 +649,28 @@ extern "C" int ms_page_batch(ms_ctx *ctx, const float *score, const float *geo, 
 // =========================================================================================================
 // host entry points (one page; copy in, run, copy out, synchronise)
 // =========================================================================================================
+static int decode_host_impl(ms_ctx *ctx, const float *score, const float *geo, int map_h, int map_w, float score_thresh,
+                            double scale, int quantization, float *quads_out, int64_t cap, int64_t *n_out, int rbox);
+
 extern "C" int ms_decode_quads_host(ms_ctx *ctx, const float *score, const float *geo, int map_h, int map_w,
                                     float score_thresh, double scale, int quantization, float *quads_out, int64_t cap,
                                     int64_t *n_out)
 {
+    return decode_host_impl(ctx, score, geo, map_h, map_w, score_thresh, scale, quantization, quads_out, cap, n_out, 0);
+}
+
+extern "C" int ms_decode_rbox_host(ms_ctx *ctx, const float *score, const float *geo5, int map_h, int map_w,
+                                   float score_thresh, double scale, int quantization, float *quads_out, int64_t cap,
+                                   int64_t *n_out)
+{
+    return decode_host_impl(ctx, score, geo5, map_h, map_w, score_thresh, scale, quantization, quads_out, cap, n_out, 1);
+}
+
+static int decode_host_impl(ms_ctx *ctx, const float *score, const float *geo, int map_h, int map_w, float score_thresh,
+                            double scale, int quantization, float *quads_out, int64_t cap, int64_t *n_out, int rbox)
+{
     MS_CTX(ctx);
+    const int planes = rbox ? 5 : 8;
     if (!score || !geo || !n_out || map_h <= 0 || map_w <= 0 || cap < 0 || (cap > 0 && !quads_out)) {
         ms_set_error("ms_decode_quads_host: bad arguments");
         return MS_ERR_INVALID;
@@ -638,12 +681,12 @@ extern "C" int ms_decode_quads_host(ms_ctx *ctx, const float *score, const float
     int capd = cand_cap(map_h, map_w, quantization);
     if (cap < capd) capd = (int)cap;
     if (capd < 1) capd = 1;
-    size_t need = al256(plane * 4) + al256(plane * 32) + al256((size_t)capd * 36) + 1024;
+    size_t need = al256(plane * 4) + al256(plane * 4 * planes) + al256((size_t)capd * 36) + 1024;
     MS_TRY(ms_stage_reserve(ctx, need));
     MS_TRY(ms_arena_reserve(ctx, msk_decode_scratch(1, map_h, map_w, quantization)));
     ms_bump sb{ctx->stage, 0, ctx->stage_bytes};
     float *d_score = sb.take<float>(plane);
-    float *d_geo = sb.take<float>(plane * 8);
+    float *d_geo = sb.take<float>(plane * planes);
     float *d_out = sb.take<float>((size_t)capd * 9);
     int32_t *d_cnt = sb.take<int32_t>(2);
     if (!d_cnt) {
@@ -652,11 +695,11 @@ extern "C" int ms_decode_quads_host(ms_ctx *ctx, const float *score, const float
     }
     cudaStream_t st = ctx->own_stream;
     MS_CUDA(cudaMemcpyAsync(d_score, score, plane * 4, cudaMemcpyHostToDevice, st));
-    MS_CUDA(cudaMemcpyAsync(d_geo, geo, plane * 32, cudaMemcpyHostToDevice, st));
+    MS_CUDA(cudaMemcpyAsync(d_geo, geo, plane * 4 * planes, cudaMemcpyHostToDevice, st));
     MS_CUDA(cudaMemsetAsync(d_cnt, 0, 2 * sizeof(int32_t), st));
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     MS_TRY(msk_decode(ctx, d_score, d_geo, 1, map_h, map_w, score_thresh, scale, quantization, d_out, capd, d_cnt,
-                      d_cnt + 1, bump, st));
+                      d_cnt + 1, bump, st, 0, rbox));
     int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
     MS_CUDA(cudaMemcpyAsync(h, d_cnt, 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));

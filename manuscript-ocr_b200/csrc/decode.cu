@@ -152,7 +152,42 @@ __global__ void __launch_bounds__(256) decode_scan_kernel(const int32_t *__restr
     }
 }
 
+// RBOX geometry (EAST, Zhou et al. 2017: four distances to the edges of the rotated word rectangle -- top, right,
+// bottom, left -- and its angle) -> the rectangle's corners TL, TR, BR, BL.  NOT a reference behaviour (the reference's
+// head is QUAD only); the closed form is the one of the public EAST implementations (restore_rectangle_rbox):
+// lay the rectangle out with the pixel at (d_left, -d_bottom) from its bottom-left corner (angle >= 0) or at
+// (-d_right, -d_bottom) from its bottom-right corner (angle < 0), rotate by the angle, translate the pixel back onto
+// (x, y).  float64 throughout; distances are map units times `scale`.
+__device__ __forceinline__ void rbox_to_quad(double ox, double oy, double dt, double dr, double db, double dl, double ang,
+                                             float *r)
+{
+    double px[4], py[4], qx, qy, c, s;
+    if (ang >= 0.0) {
+        px[0] = 0.0, py[0] = -dt - db;
+        px[1] = dr + dl, py[1] = -dt - db;
+        px[2] = dr + dl, py[2] = 0.0;
+        px[3] = 0.0, py[3] = 0.0;
+        qx = dl, qy = -db;
+        c = cos(ang), s = sin(ang);
+    } else {
+        px[0] = -dr - dl, py[0] = -dt - db;
+        px[1] = 0.0, py[1] = -dt - db;
+        px[2] = 0.0, py[2] = 0.0;
+        px[3] = -dr - dl, py[3] = 0.0;
+        qx = -dr, qy = -db;
+        c = cos(-ang), s = -sin(-ang);
+    }
+    // rotated point = (c * x + s * y, -s * x + c * y)
+    const double tx = ox - (c * qx + s * qy), ty = oy - (-s * qx + c * qy);
+#pragma unroll
+    for (int v = 0; v < 4; v++) {
+        r[2 * v] = (float)(c * px[v] + s * py[v] + tx);
+        r[2 * v + 1] = (float)(-s * px[v] + c * py[v] + ty);
+    }
+}
+
 // emit: rank candidates inside the tile, gather geometry at the cell centre, write rows in order
+template <bool kRbox>
 __global__ void __launch_bounds__(kThreads) decode_emit_kernel(const float *__restrict__ score,
                                                                const float *__restrict__ geo, DecodeGeom g,
                                                                double scale, const uint32_t *__restrict__ masks,
@@ -168,7 +203,7 @@ __global__ void __launch_bounds__(kThreads) decode_emit_kernel(const float *__re
     // (P, 8, H / q, W) -- what ms_page_batch_host uploads
     const size_t gplane = geo_compact ? (size_t)(g.H / g.q) * g.W : plane;
     const float *sc = score + (size_t)page * plane;
-    const float *ge = geo + (size_t)page * 8 * gplane;
+    const float *ge = geo + (size_t)page * (kRbox ? 5 : 8) * gplane;
     const uint32_t *mk = masks + (size_t)page * g.words;
 
     // exclusive prefix over the tile's 64 mask-word popcounts (two warps worth of data)
@@ -221,6 +256,12 @@ __global__ void __launch_bounds__(kThreads) decode_emit_kernel(const float *__re
             double xs = __dmul_rn((double)x, scale);
             double ys = __dmul_rn((double)y, scale);
             float *r = stage + rank * 9;
+            if (kRbox) {
+                double d[5];
+#pragma unroll
+                for (int v = 0; v < 5; v++) d[v] = (double)__ldg(ge + (size_t)v * gplane + gpix);
+                rbox_to_quad(xs, ys, d[0] * scale, d[1] * scale, d[2] * scale, d[3] * scale, d[4], r);
+            } else
 #pragma unroll
             for (int v = 0; v < 4; v++) {
                 float dx = __ldg(ge + (size_t)(2 * v) * gplane + gpix);
@@ -250,7 +291,7 @@ size_t msk_decode_scratch(int n_pages, int H, int W, int q)
 
 int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int H, int W, float thr,
                double scale, int q, float *quads_out, int cap_per_page, int32_t *counts, int32_t *flags,
-               ms_bump bump, cudaStream_t st, int geo_compact)
+               ms_bump bump, cudaStream_t st, int geo_compact, int rbox)
 {
     if (n_pages <= 0) return MS_OK;
     if (geo_compact && (q < 2 || H % q != 0)) {
@@ -274,8 +315,12 @@ int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, i
     MS_LAUNCH_CHECK(ctx);
     decode_scan_kernel<<<n_pages, 256, 0, st>>>(tile_counts, g.tiles, cap_per_page, tile_base, counts, flags);
     MS_LAUNCH_CHECK(ctx);
-    decode_emit_kernel<<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page, quads_out,
-                                                  geo_compact);
+    if (rbox)
+        decode_emit_kernel<true><<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page,
+                                                            quads_out, geo_compact);
+    else
+        decode_emit_kernel<false><<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page,
+                                                             quads_out, geo_compact);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

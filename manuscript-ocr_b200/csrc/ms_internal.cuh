@@ -98,7 +98,7 @@ int ms_stage_reserve(ms_ctx *ctx, size_t bytes);
 // decode.cu
 int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int H, int W, float thr,
                double scale, int q, float *quads_out, int cap_per_page, int32_t *counts, int32_t *flags,
-               ms_bump bump, cudaStream_t st, int geo_compact = 0);
+               ms_bump bump, cudaStream_t st, int geo_compact = 0, int rbox = 0);  // rbox: geo is (P,5,H,W)
 size_t msk_decode_scratch(int n_pages, int H, int W, int q);
 // sort.cu : stable LSD radix sort, per-page segments [page_off[p], page_off[p+1]) of (u32 key, u32 value), 4 passes
 int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_tmp, uint32_t *vals_tmp,
@@ -138,6 +138,9 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
              const int32_t *n_crops, const int32_t *range, int64_t crops_cap, int out_h, int out_w, float *batch_f32,
              uint8_t *canvas_u8, ms_bump bump, cudaStream_t st, const uint8_t *const *page_ptrs = nullptr,
              const int32_t *page_hw = nullptr);  // page_ptrs / page_hw (device): pages of their own sizes
+// tps.cu
+int msk_tps_rectify(ms_ctx *ctx, const float *input, const float *c_prime, const float *inv_delta_c, const float *p_hat_t,
+                    int batch, int n_fid, int chans, int in_h, int in_w, int out_h, int out_w, float *out, cudaStream_t st);
 int msk_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, int target_h, int target_w,
                        float *out_f32, uint8_t *out_u8, cudaStream_t st);
 size_t msk_crop_scratch(int64_t crops_cap, int n_pages);

@@ -16,6 +16,7 @@ from ._cabi import (  # noqa: F401
 from .ops import (  # noqa: F401
     crop_resize_pad,
     decode_quads_from_maps,
+    decode_rbox_from_maps,
     east_postprocess,
     expand_boxes,
     locality_aware_nms,
@@ -36,6 +37,7 @@ from .reading_order import (  # noqa: F401
     sort_boxes_reading_order,
     sort_boxes_reading_order_with_resolutions,
 )
+from .tps import TPSGrid, build_tps_constants  # noqa: F401
 from .trba import TRBA  # noqa: F401
 from .types import Block, Page, Word  # noqa: F401
 

@@ -78,6 +78,8 @@ SIGNATURES = {
     "ms_stage_timing": (_i, [_vp, _i]),
     "ms_stage_times": (_i, [_vp, C.POINTER(_d)]),
     "ms_decode_quads_host": (_i, [_vp, _vp, _vp, _i, _i, _f, _d, _i, _vp, _i64, C.POINTER(_i64)]),
+    "ms_decode_rbox_host": (_i, [_vp, _vp, _vp, _i, _i, _f, _d, _i, _vp, _i64, C.POINTER(_i64)]),
+    "ms_decode_rbox": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _vp, _i, _vp, _vp, _vp]),
     "ms_lanms_host": (_i, [_vp, _vp, _i64, _d, _vp, C.POINTER(_i64)]),
     "ms_standard_nms_host": (_i, [_vp, _vp, _vp, _i64, _d, _vp, C.POINTER(_i64)]),
     "ms_polygon_iou_host": (_i, [_vp, _vp, _vp, _i64, _vp]),
@@ -93,6 +95,7 @@ SIGNATURES = {
     "ms_quad_crop_resize_pad": (_i, [_vp, _vp, _i, _i, _i, _vp, _i, _vp, _i64, _i, _i, _i, _i, _i, _vp, _vp, _vp,
                                      _vp]),
     "ms_detector_input": (_i, [_vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "ms_tps_rectify": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
     "ms_decode_quads": (_i, [_vp, _vp, _vp, _i, _i, _i, _f, _d, _i, _vp, _i, _vp, _vp, _vp]),
     "ms_lanms": (_i, [_vp, _vp, _vp, _i, _i, _d, _vp, _vp, _vp, _vp]),
     "ms_east_boxes": (_i, [_vp, _vp, _vp, _i, _i, C.POINTER(EastParams), _vp, _vp, _vp, _vp]),

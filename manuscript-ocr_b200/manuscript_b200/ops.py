@@ -49,6 +49,32 @@ def decode_quads_from_maps(score_map, geo_map, score_thresh, scale, quantization
     return out[: n.value].copy()
 
 
+def decode_rbox_from_maps(score_map, geo_map, score_thresh, scale, quantization=1, ctx=None):
+    """RBOX variant of decode_quads_from_maps -- north_star names it, the reference has no such head (QUAD only), so
+    this is an extension with no reference behaviour to match.  geo_map (H,W,5) or (5,H,W): distances to the top,
+    right, bottom, left edge of the rotated word rectangle (map units) and its angle; returns (N,9) rows TL,TR,BR,BL +
+    score with the thresholding, quantisation and (y,x) order of the QUAD decode."""
+    s = np.asarray(score_map)
+    if s.ndim == 3 and s.shape[0] == 1:
+        s = s[0]
+    H, W = s.shape
+    g = np.asarray(geo_map)
+    if g.shape == (H, W, 5):
+        g = g.transpose(2, 0, 1)
+    elif g.shape != (5, H, W):
+        raise ValueError(f"geo_map must be (H,W,5) or (5,H,W) matching the score map, got {g.shape}")
+    s = np.ascontiguousarray(s, dtype=np.float32)
+    g = np.ascontiguousarray(g, dtype=np.float32)
+    q = max(int(quantization), 1)
+    cap = ((H + q - 1) // q) * ((W + q - 1) // q)
+    out = np.empty((max(cap, 1), 9), np.float32)
+    n = C.c_int64(0)
+    cx = _ctx(ctx)
+    check(cx.lib.ms_decode_rbox_host(cx.handle, _ptr(s), _ptr(g), H, W, float(np.float32(score_thresh)), float(scale), q,
+                                     _ptr(out), cap, C.byref(n)))
+    return out[: n.value].copy()
+
+
 # ---- detectors/_east/lanms.py:156-207 -----------------------------------------------------------------------
 def locality_aware_nms(boxes, iou_threshold, ctx=None):
     if boxes is None or len(boxes) == 0:

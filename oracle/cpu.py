@@ -51,6 +51,8 @@ def lib():
         L.orc_decode_quads.restype = C.c_int64
         L.orc_decode_quads.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int,
                                        _f32p, C.c_int64]
+        L.orc_decode_rbox.restype = C.c_int64
+        L.orc_decode_rbox.argtypes = [_f32p, _f32p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, _f32p, C.c_int64]
         L.orc_expand_boxes.restype = None
         L.orc_expand_boxes.argtypes = [_f32p, C.c_int64, C.c_double, C.c_double, _f32p]
         L.orc_scale_boxes.restype = None
@@ -189,6 +191,23 @@ def decode_quads_from_maps(score_map, geo_planar, score_thresh, scale, quantizat
     n = lib().orc_decode_quads(s, g, H, W, float(score_thresh), float(scale), q, out, cap)
     if n == -2:
         raise IndexError("quantised pixel index outside the map (utils.py:370 geo_map[y, x])")
+    assert n >= 0
+    return out[:n].copy()
+
+
+def decode_rbox_from_maps(score_map, geo5_planar, score_thresh, scale, quantization=1):
+    """RBOX decode (NOT a reference behaviour, parity unpinned -- see oracle.c): geo5 (5,H,W) = top / right / bottom /
+    left distances + angle; rows = rectangle corners TL,TR,BR,BL + score, thresholding / order as decode_quads."""
+    s = np.ascontiguousarray(score_map, dtype=np.float32)
+    g = np.ascontiguousarray(geo5_planar, dtype=np.float32)
+    H, W = s.shape
+    assert g.shape == (5, H, W)
+    q = max(int(quantization), 1)
+    cap = ((H + q - 1) // q) * ((W + q - 1) // q)
+    out = np.empty((max(cap, 1), 9), np.float32)
+    n = lib().orc_decode_rbox(s, g, H, W, float(score_thresh), float(scale), q, out, cap)
+    if n == -2:
+        raise IndexError("quantised pixel index outside the map")
     assert n >= 0
     return out[:n].copy()
 

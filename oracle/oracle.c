@@ -252,6 +252,67 @@ int64_t orc_standard_nms(const double *polys, const double *scores, int64_t n, d
 }
 
 /* ------------------------------------------------------------------------- */
+/* RBOX geometry decode -- NOT a reference behaviour ("parity unpinned"): the reference's geometry head is QUAD only
+ * (detectors/_east/east.py:99-100, utils.py:368-376).  BASELINE.json's north_star names it, so the closed
+ * form of the EAST paper (Zhou et al. 2017) is stated here as the public implementations do (restore_rectangle_rbox):
+ * geo5 = distances from the pixel to the top, right, bottom, left edge of the rotated rectangle and its angle.
+ * Thresholding / quantisation / row order exactly as orc_decode_quads (utils.py:340-356).  float64 arithmetic. */
+void orc_rbox_to_quad(double ox, double oy, double dt, double dr, double db, double dl, double ang, float *r)
+{
+    double px[4], py[4], qx, qy, c, s;
+    if (ang >= 0.0) {
+        px[0] = 0.0; py[0] = -dt - db;
+        px[1] = dr + dl; py[1] = -dt - db;
+        px[2] = dr + dl; py[2] = 0.0;
+        px[3] = 0.0; py[3] = 0.0;
+        qx = dl; qy = -db;
+        c = cos(ang); s = sin(ang);
+    } else {
+        px[0] = -dr - dl; py[0] = -dt - db;
+        px[1] = 0.0; py[1] = -dt - db;
+        px[2] = 0.0; py[2] = 0.0;
+        px[3] = -dr - dl; py[3] = 0.0;
+        qx = -dr; qy = -db;
+        c = cos(-ang); s = -sin(-ang);
+    }
+    double tx = ox - (c * qx + s * qy), ty = oy - (-s * qx + c * qy);
+    for (int v = 0; v < 4; v++) {
+        r[2 * v] = (float)(c * px[v] + s * py[v] + tx);
+        r[2 * v + 1] = (float)(-s * px[v] + c * py[v] + ty);
+    }
+}
+
+int64_t orc_decode_rbox(const float *score, const float *geo5, int H, int W, double thr, double scale, int q,
+                        float *out, int64_t cap)
+{
+    if (q < 1) q = 1;
+    int CH = (H + q - 1) / q, CW = (W + q - 1) / q;
+    float thr32 = (float)thr;
+    int64_t n = 0;
+    size_t plane = (size_t)H * W;
+    for (int cy = 0; cy < CH; cy++)
+        for (int cx = 0; cx < CW; cx++) {
+            int hit = 0;
+            for (int dy = 0; dy < q && !hit; dy++)
+                for (int dx = 0; dx < q && !hit; dx++) {
+                    int y = cy * q + dy, x = cx * q + dx;
+                    if (y < H && x < W && score[(size_t)y * W + x] > thr32) hit = 1;
+                }
+            if (!hit) continue;
+            int y = q > 1 ? cy * q + q / 2 : cy, x = q > 1 ? cx * q + q / 2 : cx;
+            if (y >= H || x >= W) return -2;
+            if (n >= cap) return -3;
+            size_t pix = (size_t)y * W + x;
+            orc_rbox_to_quad(x * scale, y * scale, geo5[pix] * scale, geo5[plane + pix] * scale,
+                             geo5[2 * plane + pix] * scale, geo5[3 * plane + pix] * scale, geo5[4 * plane + pix],
+                             out + 9 * n);
+            out[9 * n + 8] = score[pix];
+            n++;
+        }
+    return n;
+}
+
+/* ------------------------------------------------------------------------- */
 /* lanms.py:156-207  sort by x0, sequential weighted merge, then NMS          */
 /* boxes: (n,9) f32.  out: (cap,9) f32.  Optional debug outputs (may be NULL): */
 /*   cl_polys (n*8 f64), cl_scores (n f64), n_clusters, keep_cluster (n i64)   */

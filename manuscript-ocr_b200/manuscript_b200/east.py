@@ -87,12 +87,12 @@ class EAST:
         ~/.manuscript/east/east_quad_23_05.pth (downloaded there by the reference; this package has no network code)
         inside the reference's own network module.  FileNotFoundError when the weights are missing -- what the
         reference's torch.load raises offline -- and ImportError when the reference package that defines the network
-        (manuscript.detectors._east.east.EASTModel) is not installed next to this one."""
+        (manuscript.detectors._east.east.EAST) is not installed next to this one."""
         path = Path(weights_path) if weights_path is not None else DEFAULT_WEIGHTS
         if not path.exists():
             raise FileNotFoundError(f"EAST weights not found: {path} (the reference downloads them on first use; "
                                     "pass EAST(model=...) or weights_path=...)")
-        from manuscript.detectors._east.east import EASTModel  # the network is outside this package
+        from manuscript.detectors._east.east import EAST as EASTModel  # the network is outside this package (infer.py:15)
 
         det = cls(model=None, **kwargs)
         det.model = EASTModel(pretrained_backbone=False, pretrained_model_path=str(path)).to(det.device).eval()

@@ -530,3 +530,46 @@ def test_reading_order_beyond_device_capacity(mb, golden_dir):
     polys = _boxes_to_polys(bx)
     got = mb.word_reading_order(polys)
     assert list(got) == _host_order(mb, bx)
+
+
+# ---- BASELINE configs[0]: the plumbing run on the reference's example image, random-init reference network -----------------
+def test_configs0_example_image_random_init_network(mb, golden_dir):
+    """tests/golden/make_golden_cfg0.py ran the reference's OWN network module (detectors/_east/east.py, random init,
+    seed 0, CPU) on example/ocr_example_image.jpg prepared as EAST.predict prepares it, and the reference's
+    post-processing on the maps it produced (score_thresh = the map's median: random init never reaches 0.6).  Here
+    the maps are replayed through mb.EAST and mb.Pipeline: the network input made on the device is bit-identical to the
+    reference's, and candidates / kept rows / final boxes equal the reference's outputs."""
+    import hashlib
+
+    import torch
+
+    g = np.load(os.path.join(golden_dir, "cfg0_example.npz"))
+    target, thr = int(g["target"]), float(g["score_thresh"])
+    score, geo, resized = g["score"], g["geo"], g["resized"]
+    seen = {}
+
+    class Net:  # stands in for the reference's network: checks its input, replays the maps the real one produced
+        def __call__(self, x):
+            seen["sha"] = hashlib.sha256(x[0].cpu().numpy().tobytes()).hexdigest()
+            return {"score": torch.from_numpy(score)[None, None].cuda(), "geometry": torch.from_numpy(geo)[None].cuda()}
+
+    det = mb.EAST(model=Net(), target_size=target, score_thresh=thr, cap_boxes=8192)
+    quads = mb.decode_quads_from_maps(score, geo, thr, 4.0, 2)
+    assert len(quads) == int(g["n_candidates"])
+    assert hashlib.sha256(quads.tobytes()).hexdigest() == str(g["quads_sha"])
+    np.testing.assert_array_equal(mb.locality_aware_nms(quads, 0.2), g["lanms"])
+    orig_hw = tuple(int(v) for v in g["orig_hw"])
+    np.testing.assert_array_equal(det.boxes_from_maps(score, geo, orig_hw), g["final"])
+    # EAST.predict / Pipeline.predict on the (already resized) example image: same network input as the reference made
+    out = det.predict(resized, return_maps=True)
+    assert seen["sha"] == str(g["input_sha"])
+    np.testing.assert_array_equal(out["score_map"], score)
+    want = cpu.east_postprocess(g["lanms"], (target, target), target_size=target)
+    got = np.array([[v for pt in w.polygon for v in pt] + [w.detection_confidence] for w in out["page"].blocks[0].words],
+                   np.float32)
+    np.testing.assert_array_equal(got, want)
+    rec = mb.TRBA(model=lambda b: [("", 0.0)] * len(b), img_h=64, img_w=256)  # the reference's default canvas
+    pipe = mb.Pipeline(detector=det, recognizer=rec)
+    page = pipe.predict(resized)
+    assert pipe.last_route in ("fused", "fused+host_order")
+    assert len(page.blocks[0].words) == len(want)

@@ -234,14 +234,45 @@ int ms_stage_reserve(ms_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->stage, 
 
 static inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
 
+// Entry guard: a context is single-threaded by contract (one scratch arena); the guard turns a violation into an error.
+// Re-entrant on the same thread (the *_host entry points call themselves again after growing a capacity).
+struct ms_ctx_guard {
+    ms_ctx *c = nullptr;
+    bool owner = false;
+    static thread_local ms_ctx *t_inside;
+    int enter(ms_ctx *ctx, const char *fn)
+    {
+        if (t_inside == ctx) return MS_OK;  // nested call of this thread
+        if (__atomic_exchange_n(&ctx->busy, 1, __ATOMIC_ACQUIRE) != 0) {
+            ms_set_error("%s: this ms_ctx is in use by another thread (one context per thread)", fn);
+            return MS_ERR_INVALID;
+        }
+        c = ctx;
+        owner = true;
+        t_inside = ctx;
+        return MS_OK;
+    }
+    ~ms_ctx_guard()
+    {
+        if (owner) {
+            t_inside = nullptr;
+            __atomic_store_n(&c->busy, 0, __ATOMIC_RELEASE);
+        }
+    }
+};
+thread_local ms_ctx *ms_ctx_guard::t_inside = nullptr;
+
 #define MS_CTX(ctx)                                          \
-    do {                                                     \
-        if (!(ctx)) {                                        \
-            ms_set_error("%s: ctx is NULL", __func__);       \
-            return MS_ERR_INVALID;                           \
-        }                                                    \
-        MS_CUDA(cudaSetDevice((ctx)->device));               \
-    } while (0)
+    if (!(ctx)) {                                            \
+        ms_set_error("%s: ctx is NULL", __func__);           \
+        return MS_ERR_INVALID;                               \
+    }                                                        \
+    ms_ctx_guard _ms_guard;                                  \
+    {                                                        \
+        int _grc = _ms_guard.enter((ctx), __func__);         \
+        if (_grc != MS_OK) return _grc;                      \
+    }                                                        \
+    MS_CUDA(cudaSetDevice((ctx)->device))
 
 #define MS_TRY(expr)                 \
     do {                             \

@@ -34,16 +34,33 @@
 
 namespace {
 
-constexpr int kThreads = 224;   // copy warp + table/padding warp + 5 consumer warps; 4 CTAs per SM
+// CTA shape of the persistent kernel.  MS_CROP_PAD_WARP = 0: copy warp + table/padding warp + 5 consumer warps, 4 CTAs
+// per SM (224 threads, 72 registers).  MS_CROP_PAD_WARP = 1: copy warp + table warp + PADDING warp + 7 consumer warps,
+// 3 CTAs per SM (320 threads, 64 registers): the padding no longer serialises behind the tables in one warp.
+#ifndef MS_CROP_PAD_WARP
+#define MS_CROP_PAD_WARP 0
+#endif
+#if MS_CROP_PAD_WARP
+constexpr int kThreads = 320;
+constexpr int kCtasPerSm = 3;
+constexpr int kSlots = 4;       // crops in flight per CTA (ring slots: metadata + tables per slot, bytes from the ring)
+#else
+constexpr int kThreads = 224;
 constexpr int kCtasPerSm = 4;
+constexpr int kSlots = 3;
+#endif
+constexpr bool kPadWarp = MS_CROP_PAD_WARP != 0;
 constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
 constexpr int kSrcBuf = 40 * 1024;  // largest staged crop (bytes); the staging ring of a CTA holds at least one
-constexpr int kSlots = 3;       // crops in flight per CTA (ring slots: metadata + tables per slot, bytes from the ring)
 constexpr int kBandsY = 64, kCellsX = 8;
 #ifndef MS_COPY_PAD_CHANNELS
 #define MS_COPY_PAD_CHANNELS 0
 #endif
-constexpr int kCopyPadChannels = MS_COPY_PAD_CHANNELS;  // float32 padding channels written by the copy warp
+constexpr int kCopyPadChannels = MS_COPY_PAD_CHANNELS;
+#ifndef MS_PAD_LAG
+#define MS_PAD_LAG 0
+#endif
+constexpr int kPadLag = MS_PAD_LAG;  // crops between building a crop's tables and writing its padding  // float32 padding channels written by the copy warp
 #ifndef MS_CROP_WAIT_NS
 #define MS_CROP_WAIT_NS 100u
 #endif  // work-list buckets per page: (row band, x cell)
@@ -298,7 +315,7 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // Each consumer thread resamples a column strip (one destination column, G consecutive destination rows): with a
 // shrink factor near 2 neighbouring destination rows share their boundary source row, so a strip needs ~(2G + 1)
 // horizontal row sums instead of 3G; per-pixel arithmetic and its order are unchanged.
-constexpr int kProducerWarps = 2;
+constexpr int kProducerWarps = kPadWarp ? 3 : 2;
 constexpr int kConsumerWarps = kThreads / 32 - kProducerWarps;
 
 template <bool kWriteF32, bool kWriteU8>
@@ -309,13 +326,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                            uint8_t *__restrict__ redo)
 {
     extern __shared__ __align__(128) unsigned char smem[];  // [ring_bytes] staging ring, then kSlots table sets
-    const int tab_n = iw + ih;
-    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + ring_bytes);  // [kSlots][kTabWords][iw + ih]
+    const int tab_n = area_tab_words(ih, iw);  // words of one slot's table set
+    uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + ring_bytes);  // [kSlots][tab_n]
     __shared__ __align__(8) uint64_t s_full[kSlots], s_empty[kSlots], s_tick[kSlots];
     // per slot: the crop (index, -1 = no more crops) and what the consumers need of its plan, so that they never touch
     // the plan array in global memory
     __shared__ int s_next[kSlots];    // copy warp -> table warp: crop index of the slot
     __shared__ int s_off[kSlots];     // copy warp -> consumers: ring offset of the crop's first row
+    __shared__ int s_pad[kSlots][2];  // copy warp -> padding warp: nw | nh << 16, y0
     __shared__ long long s_ci[kSlots];
     __shared__ int s_meta[kSlots][8];  // nw, nh, y0, pitch, misalignment of row 0, its change per row, <= 3 x taps, strip height
 
@@ -326,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 #pragma unroll
         for (int i = 0; i < kSlots; i++) {
             mbar_init(&s_full[i], 2);  // the copy warp (with the byte count) and the table warp
-            mbar_init(&s_empty[i], kConsumerWarps);
+            mbar_init(&s_empty[i], kConsumerWarps + (kPadWarp ? 1 : 0));  // + the padding warp (it read the slot's descriptor)
             mbar_init(&s_tick[i], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -413,6 +431,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             if (lane == 0) {
                 s_next[s] = cur.ci;
                 s_off[s] = off;
+                s_pad[s][0] = cur.nwh;
+                s_pad[s][1] = cur.y0;
                 mbar_arrive(&s_tick[s]);  // release: the table warp and (through full) the consumers see both
             }
             uint32_t bytes = 0;
@@ -446,6 +466,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
     }
     if (warp == 1) {
         // ---------------- table warp: OpenCV's axis tables, then all of the padding ----------------
+        // kPadLag > 0: the padding of a crop is written kPadLag crops later, i.e. about when the consumers write its
+        // pixels, so that a canvas reaches DRAM in one visit instead of two
+        int lag_ci[kPadLag + 1], lag_nwh[kPadLag + 1], lag_y0[kPadLag + 1];
+#pragma unroll
+        for (int i = 0; i <= kPadLag; i++) lag_ci[i] = -1, lag_nwh[i] = 0, lag_y0[i] = 0;
+        auto pad_one = [&](int pci, int nwh, int py0) {
+            if (pci >= 0)
+                write_padding<kWriteF32, kWriteU8>(nwh & 0xffff, (int)((uint32_t)nwh >> 16), py0, ih, iw,
+                                                   kWriteF32 ? batch + (size_t)pci * 3 * plane : nullptr,
+                                                   kWriteU8 ? canvas_out + (size_t)pci * 3 * plane : nullptr, vec_ok, lane,
+                                                   32, 0, kWriteF32 ? 3 - kCopyPadChannels : 3);
+        };
         for (int k = 0;; k++) {
             const int s = k % kSlots;
             mbar_wait(&s_tick[s], (uint32_t)((k / kSlots) & 1));
@@ -455,11 +487,15 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                     s_ci[s] = -1;
                     mbar_arrive(&s_full[s]);
                 }
+#if !defined(MS_EXP_NO_PAD)
+#pragma unroll
+                for (int i = 0; i < kPadLag; i++) pad_one(lag_ci[i], lag_nwh[i], lag_y0[i]);
+#endif
                 break;
             }
             const Plan p = plans[ci];
             const bool two = p.interp == 2;  // exact 2 x 2 ratio: no tables
-            const bool x3 = two || __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)s * kTabWords * tab_n, tab_n, iw, lane));
+            const bool x3 = two || __all_sync(0xffffffffu, build_tables(p, tabs + (size_t)s * tab_n, tab_n, iw, lane));
             if (lane == 0) {
                 s_ci[s] = ci;
                 s_meta[s][0] = p.nw;
@@ -474,9 +510,30 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
             __syncwarp();  // every lane's table stores are ordered before lane 0's releasing arrive
             if (lane == 0) mbar_arrive(&s_full[s]);
 #if !defined(MS_EXP_NO_PAD)
-            write_padding<kWriteF32, kWriteU8>(p, ih, iw, kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
-                                              kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0,
-                                              kWriteF32 ? 3 - kCopyPadChannels : 3);
+            if (kPadWarp) continue;
+            lag_ci[kPadLag] = ci, lag_nwh[kPadLag] = p.nw | (p.nh << 16), lag_y0[kPadLag] = p.y0;
+            pad_one(lag_ci[0], lag_nwh[0], lag_y0[0]);
+#pragma unroll
+            for (int i = 0; i < kPadLag; i++) lag_ci[i] = lag_ci[i + 1], lag_nwh[i] = lag_nwh[i + 1], lag_y0[i] = lag_y0[i + 1];
+#endif
+        }
+        return;
+    }
+
+    if (kPadWarp && warp == 2) {
+        // ---------------- padding warp: the 255-padding of every crop, as soon as the copy warp has drawn it ----------------
+        for (int k = 0;; k++) {
+            const int s = k % kSlots;
+            mbar_wait(&s_tick[s], (uint32_t)((k / kSlots) & 1));
+            const int ci = s_next[s];
+            if (ci < 0) break;
+            const int nwh = s_pad[s][0], py0 = s_pad[s][1];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&s_empty[s]);  // the slot's descriptor has been read
+#if !defined(MS_EXP_NO_PAD)
+            write_padding<kWriteF32, kWriteU8>(nwh & 0xffff, (int)((uint32_t)nwh >> 16), py0, ih, iw,
+                                               kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr,
+                                               kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr, vec_ok, lane, 32, 0, 3);
 #endif
         }
         return;
@@ -496,7 +553,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
         const uint32_t stage_off = (uint32_t)s_off[s];
         float *dstf = kWriteF32 ? batch + (size_t)ci * 3 * plane : nullptr;
         uint8_t *dstu = kWriteU8 ? canvas_out + (size_t)ci * 3 * plane : nullptr;
-        const uint32_t *tab = tabs + (size_t)s * kTabWords * tab_n;
+        const uint32_t *tab = tabs + (size_t)s * tab_n;
         // three x taps at most (shrink factor below 2, most word boxes): a quarter of the horizontal work less; a page
         // stride that is a multiple of 16 bytes (sstep == 0): no per-row misalignment arithmetic
         bool bad = false;
@@ -688,7 +745,7 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     }
     // shared memory of the persistent kernel: kSlots table sets + the staging ring, which gets what is left of an SM's
     // 227 KB split over the CTAs per SM (1 KB per CTA is reserved by the system, ~0.5 KB is static)
-    const size_t tab_bytes = (size_t)kSlots * (size_t)(out_h + out_w) * kTabWords * sizeof(uint32_t);
+    const size_t tab_bytes = (size_t)kSlots * (size_t)area_tab_words(out_h, out_w) * sizeof(uint32_t);
     const size_t min_ring = (size_t)kSrcBuf + 128;
     int per_sm = kCtasPerSm;
     while (per_sm > 1 && (227 * 1024) / per_sm < (int)(tab_bytes + min_ring + 1024 + 512)) per_sm--;

@@ -431,6 +431,15 @@ __device__ __forceinline__ void hrow_area4(const unsigned char *smem_base, uint3
     }
 }
 
+// words of one crop's table set: x entries as five arrays of iw words, y entries as ih records of 8 words
+__host__ __device__ inline int area_tab_ybase(int iw) { return (5 * iw + 3) & ~3; }  // 16-byte aligned records
+__host__ __device__ inline int area_tab_words(int ih, int iw) { return area_tab_ybase(iw) + 8 * ih; }
+
+// The INTER_AREA coefficient tables of one crop for the 4-tap path.  x entries, structure of arrays (a warp's lanes read
+// consecutive columns): tab[0][i] = s0 | n << 16, tab[1..4][i] = tap weights (0 beyond n), i in [0, iw).  y entries,
+// array of 8-word records after them (a thread walks down the rows: one 16-byte load for the four weights):
+// ytab[d] = {s0 | n << 16, -, -, -, w0, w1, w2, w3} at word area_tab_ybase(iw) + 8 * d (weights 16-byte aligned).
+// (older description follows)
 // The INTER_AREA coefficient tables of one crop for the 4-tap path, structure of arrays:
 // tab[0][i] = s0 | n << 16, tab[1..4][i] = tap weights (0 beyond n); x entries occupy [0, iw), y entries
 // [iw, iw + ih) of every array.  Plan::fast guarantees n <= 4; an entry that violates it is stored with n = 0xffff
@@ -446,12 +455,19 @@ __device__ __forceinline__ bool build_tables(const Plan &p, uint32_t *tab, int t
         const bool isx = t < p.nw;
         const int d = isx ? t : t - p.nw;
         const AxisEnt e = isx ? area_entry(d, p.scale_x, p.w, inv_x) : area_entry(d, p.scale_y, p.h, inv_y);
-        const int at = isx ? d : iw + d;
         const bool fits = e.n <= 4 && e.s0 >= 0 && e.s0 < 65536;
         x3 = x3 && !(isx && e.n > 3);
-        tab[at] = fits ? ((uint32_t)e.s0 | ((uint32_t)e.n << 16)) : 0xffff0000u;
+        const uint32_t packed = fits ? ((uint32_t)e.s0 | ((uint32_t)e.n << 16)) : 0xffff0000u;
+        if (isx) {
+            tab[d] = packed;
 #pragma unroll
-        for (int k = 0; k < 4; k++) tw[(size_t)(1 + k) * tab_n + at] = k < e.n ? area_weight(e, k) : 0.f;
+            for (int k = 0; k < 4; k++) tw[(size_t)(1 + k) * iw + d] = k < e.n ? area_weight(e, k) : 0.f;
+        } else {
+            uint32_t *rec = tab + area_tab_ybase(iw) + 8 * d;
+            rec[0] = packed;
+#pragma unroll
+            for (int k = 0; k < 4; k++) reinterpret_cast<float *>(rec)[4 + k] = k < e.n ? area_weight(e, k) : 0.f;
+        }
     }
     return x3;
 }
@@ -534,17 +550,19 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
         const int grp = nw == 1 ? t : (int)__umulhi((uint32_t)t, magic), dx = t - grp * nw;
         const uint32_t px = tab[dx];
         bad = bad || (px >> 16) > 4u;
-        const float4 wx = make_float4(tw[tab_n + dx], tw[2 * tab_n + dx], tw[3 * tab_n + dx], tw[4 * tab_n + dx]);
+        const float4 wx = make_float4(tw[iw + dx], tw[2 * iw + dx], tw[3 * iw + dx], tw[4 * iw + dx]);
         const uint32_t xoff = stage_off + (px & 0xffffu) * 3u;
         int last_r = -1;
         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
         const int dy_end = min(nh, grp * G + G);
+        float *orow = kWriteF32 ? dstf + (size_t)(y0 + grp * G) * iw + dx : nullptr;  // walks down the strip's rows
         for (int dy = grp * G; dy < dy_end; dy++) {
-            const uint32_t py = tab[iw + dy];
+            const uint32_t *yrec = tab + area_tab_ybase(iw) + 8 * dy;
+            const uint32_t py = yrec[0];
             bad = bad || (py >> 16) > 4u;
             const int ys0 = (int)(py & 0xffffu), yn = min((int)(py >> 16), 4);
-            const float wyv[4] = {tw[tab_n + iw + dy], tw[2 * tab_n + iw + dy], tw[3 * tab_n + iw + dy],
-                                  tw[4 * tab_n + iw + dy]};
+            const float4 wy4 = *reinterpret_cast<const float4 *>(yrec + 4);
+            const float wyv[4] = {wy4.x, wy4.y, wy4.z, wy4.w};
             // row 0 is the previous destination row's last source row when the two share it (uniform branch);
             // the other rows are independent horizontal passes
             const uint32_t rbase = xoff + (uint32_t)ys0 * pitch;
@@ -569,9 +587,10 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
             const float f0 = rintf(sum0), f1 = rintf(sum1), f2 = rintf(sum2);
             const int at = (y0 + dy) * iw + dx;
             if (kWriteF32) {
-                ms_store(dstf + at, (f0 - 127.5f) * inv);
-                ms_store(dstf + plane + at, (f1 - 127.5f) * inv);
-                ms_store(dstf + 2 * plane + at, (f2 - 127.5f) * inv);
+                ms_store(orow, (f0 - 127.5f) * inv);
+                ms_store(orow + plane, (f1 - 127.5f) * inv);
+                ms_store(orow + 2 * plane, (f2 - 127.5f) * inv);
+                orow += iw;
             }
             if (kWriteU8) {
                 dstu[(size_t)at * 3] = sat_u8((int)f0);

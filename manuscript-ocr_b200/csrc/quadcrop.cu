@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(kQcThreads, 4) quad_crop_kernel(const uint8_t 
     AxisEnt *s_tab = reinterpret_cast<AxisEnt *>(qc_smem + kQcPatchBytes + 16);
     uint32_t *soa = reinterpret_cast<uint32_t *>(s_tab);
     __shared__ QuadPlan s_qp;
-    const int plane = ih * iw, tab_n = iw + ih;
-    const bool soa_fits = (size_t)tab_n * 5 * sizeof(uint32_t) <= (size_t)kQcMaxTab * sizeof(AxisEnt);
+    const int plane = ih * iw, tab_n = area_tab_words(ih, iw);
+    const bool soa_fits = (size_t)tab_n * sizeof(uint32_t) <= (size_t)kQcMaxTab * sizeof(AxisEnt);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int64_t ci = blockIdx.x; ci < n; ci += gridDim.x) {
         __syncthreads();  // the previous quad's plan, patch and tables are no longer read

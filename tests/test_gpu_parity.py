@@ -497,3 +497,50 @@ def test_containment_predicate_on_the_device(ops, thr):
         total += len(a)
         proved_total += int(proved.sum())
     assert total >= 1_000_000 and (proved_total > 100_000 or thr >= 0.5)
+
+
+def test_context_is_guarded_against_a_second_thread(ops):
+    """An ms_ctx owns one scratch arena and is single-threaded by contract; a second thread that enters while a call is
+    in flight gets MS_ERR_INVALID ("in use by another thread") instead of corrupting the arena, and the first call's
+    result is untouched.  Each thread's own default context is unaffected."""
+    import threading
+
+    from manuscript_b200._cabi import Context, last_error
+
+    ctx = Context(0)
+    score, geo, _ = synthdata.make_maps(11, 2048, 2000)
+    quads = ops.decode_quads_from_maps(score, geo, 0.6, 4.0, 2, ctx=ctx)
+    want = cpu.locality_aware_nms(quads, 0.2)
+    seen = {"busy": 0, "ok": 0, "other": []}
+    stop = threading.Event()
+
+    def intruder():
+        a = np.zeros((4, 4, 2), np.float64)
+        out = np.zeros(4, np.float64)
+        while not stop.is_set():
+            rc = ctx.lib.ms_polygon_iou_host(ctx.handle, a.ctypes.data, a.ctypes.data, 4, out.ctypes.data)
+            if rc == 0:
+                seen["ok"] += 1
+            elif rc == -1 and "another thread" in last_error():
+                seen["busy"] += 1
+            else:
+                seen["other"].append((rc, last_error()))
+
+    t = threading.Thread(target=intruder)
+    t.start()
+    done = turned_away = 0
+    try:
+        while done < 20:
+            try:
+                got = ops.locality_aware_nms(quads, 0.2, ctx=ctx)
+            except ops.CABIError as e:  # the intruder was inside its (short) call: this thread is the second one
+                assert e.code == -1 and "another thread" in str(e)
+                turned_away += 1
+                continue
+            np.testing.assert_array_equal(got, want)  # a call that was let in is never disturbed
+            done += 1
+    finally:
+        stop.set()
+        t.join()
+    assert not seen["other"], seen["other"][:3]
+    assert seen["busy"] + turned_away > 0  # the two threads did collide, and the second one was turned away each time

@@ -35,7 +35,7 @@ namespace {
 
 // neighbour-pair capacity per candidate is LanmsBuffers::ef (ms_ctx::edge_factor; overflow -> MS_FLAG_EDGE_OVERFLOW,
 // the host entry points then retry with a larger factor)
-constexpr int kGrid = 32;        // uniform grid per page for the neighbour search
+constexpr int kGrid = 64;  // uniform grid per page for the neighbour search (cells about one word box high)
 constexpr int kCells = kGrid * kGrid;
 // neighbour pair word: lo in bits 0..29, hi (higher NMS priority) in bits 30..59
 constexpr uint64_t kPairTrue = 1ull << 62;  // IoU already evaluated and > thr
@@ -695,15 +695,27 @@ __global__ void __launch_bounds__(256) nms_bin_count_kernel(const int32_t *__res
     }
 }
 
-__global__ void __launch_bounds__(kCells) nms_bin_scan_kernel(LanmsBuffers B)
+__global__ void __launch_bounds__(1024) nms_bin_scan_kernel(LanmsBuffers B)
 {
+    // exclusive scan of the page's kCells cell counts: a thread owns kCells / 1024 consecutive cells
+    static_assert(kCells % 1024 == 0, "cells per thread");
+    constexpr int kPer = kCells / 1024;
     const int page = blockIdx.x;
     __shared__ int s_warp[33];
-    const int v = B.cell_cnt[(size_t)page * kCells + threadIdx.x];
+    int v[kPer], sum = 0;
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        v[i] = B.cell_cnt[(size_t)page * kCells + threadIdx.x * kPer + i];
+        sum += v[i];
+    }
     int total;
-    const int off = block_excl_scan_1024(v, s_warp, total);
-    B.cell_off[(size_t)page * (kCells + 1) + threadIdx.x] = off;
-    B.cell_cur[(size_t)page * kCells + threadIdx.x] = off;
+    int off = block_excl_scan_1024(sum, s_warp, total);
+#pragma unroll
+    for (int i = 0; i < kPer; i++) {
+        B.cell_off[(size_t)page * (kCells + 1) + threadIdx.x * kPer + i] = off;
+        B.cell_cur[(size_t)page * kCells + threadIdx.x * kPer + i] = off;
+        off += v[i];
+    }
     if (threadIdx.x == 0) B.cell_off[(size_t)page * (kCells + 1) + kCells] = total;
 }
 
@@ -1455,7 +1467,7 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         if (g > sms * 8) g = sms * 8;
         nms_bin_count_kernel<<<g, 256, 0, st>>>(B.page_off, B.n_total, B);
         MS_LAUNCH_CHECK(ctx);
-        nms_bin_scan_kernel<<<n_pages, kCells, 0, st>>>(B);
+        nms_bin_scan_kernel<<<n_pages, 1024, 0, st>>>(B);
         MS_LAUNCH_CHECK(ctx);
         nms_bin_scatter_kernel<<<g, 256, 0, st>>>(B.page_off, B.n_total, B);
         MS_LAUNCH_CHECK(ctx);

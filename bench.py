@@ -683,7 +683,15 @@ def run_variants(a, mb, torch, dev, local, ctx, res, counts, d_score, d_geo, d_p
                                "note": "BASELINE configs[3]: 8 pages of 4096x4096 (2 distinct, repeated), ~10 000 quads and "
                                        "~63 000 candidates per page; parity of this shape: tests/test_gpu_batch.py::"
                                        "test_stress_4096_page against the committed oracle digests"}
-    del big, d4, r4, s4, g4, i4
+    # the same with the reading-order sort (10 000 boxes per page: the global-memory reading-order kernel)
+    del big
+    big_ro = mb.PageBatch(device=local, params=mb.EastParams.default(target_size=4096, sort_reading_order=1),
+                          cap_boxes=16384, crops_cap=8 * 12000, out_hw=(OUT_H, OUT_W))
+    r4o = big_ro.run(*d4, sync=True)
+    assert int(r4o.n_crops.item()) == int(r4.n_crops.item())
+    ms4o = timed(lambda: big_ro.run(*d4), reps=5)
+    variants["stress_4096"]["with_reading_order_ms_per_step"] = ms4o
+    del big_ro, r4o, d4, r4, s4, g4, i4
     # a denser candidate load (SURVEY 8d expected ~24k candidates per 2048^2 page): the score regions shrunk by 0.2 instead
     # of 0.3 of the shorter side, 16 pages
     sd, gd, _ = synthdata.make_batch(list(range(500, 516)), S, a.words, with_images=False, shrink=0.2)

@@ -48,8 +48,8 @@ extern "C" {
 #define MS_FLAG_CAND_OVERFLOW 1 /* more candidates than cap_per_page            */
 #define MS_FLAG_INDEX_ERROR 2   /* utils.py:370 would raise IndexError          */
 #define MS_FLAG_EDGE_OVERFLOW 4 /* NMS suppression-edge buffer exceeded         */
-#define MS_FLAG_ORDER_OVERFLOW 8 /* reading order not computed on the device for this page (more than 4096 boxes or
-                                    28672 intersecting box pairs): its boxes and crops are in detection order */
+#define MS_FLAG_ORDER_OVERFLOW 8 /* reading order not computed on the device for this page (more than
+                                    max(65536, 16 cap) intersecting box pairs): its boxes and crops are in detection order */
 
 typedef struct ms_ctx ms_ctx;
 
@@ -155,7 +155,8 @@ MS_API int ms_word_rects_host(ms_ctx *ctx, const float *polys8, int64_t n, int i
 /* replaces sort_boxes_reading_order_with_resolutions, detectors/_east/utils.py:610-644 (default y_tol_ratio /
  * x_gap_ratio), and the word re-matching of Pipeline.predict, _pipeline.py:105-123 (== infer.py:365-385):
  * polys (n,8) f32 -> order (n) int32, order[r] = index of the word at reading position r (the reference's quirks
- * with duplicate boxes included).  At most 4096 boxes and 28672 intersecting pairs per page: beyond that the call
+ * with duplicate boxes included).  Pages of up to 4096 boxes and 28672 intersecting pairs run in one shared-memory kernel, larger ones in
+ * a global-memory kernel; beyond max(65536, 16 n) intersecting pairs (or 2^20 boxes) the call
  * returns MS_ERR_CAPACITY (the Python host side then runs its exact restatement of the reference's host logic). */
 MS_API int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n, int32_t *order);
 
@@ -210,8 +211,8 @@ MS_API int ms_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts,
                   void *stream);
 
 /* utils.py:610-644 + _pipeline.py:105-123 for n_pages box lists (page-strided): order (n_pages*cap_per_page) int32 and,
- * if quads_out != NULL (must not alias quads), the rows in reading order.  A page beyond the device capacity (4096 boxes,
- * 28672 intersecting pairs) keeps its detection order and gets MS_FLAG_ORDER_OVERFLOW in `flags`. */
+ * if quads_out != NULL (must not alias quads), the rows in reading order.  A page beyond the device capacity (more than
+ * max(65536, 16 cap_per_page) intersecting pairs) keeps its detection order and gets MS_FLAG_ORDER_OVERFLOW in `flags`. */
 MS_API int ms_reading_order(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_pages, int cap_per_page,
                      int32_t *order, float *quads_out, int32_t *flags, void *stream);
 

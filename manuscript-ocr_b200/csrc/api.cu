@@ -97,6 +97,7 @@ extern "C" int ms_create(int device, ms_ctx **out)
     c->num_sms = prop.multiProcessorCount > 0 ? prop.multiProcessorCount : MS_NUM_SMS_B200;
     c->edge_factor = 16;
     c->graphs_enabled = getenv("MS_B200_NO_GRAPHS") ? 0 : 1;
+    c->ro_force_large = getenv("MS_B200_RO_FORCE_LARGE") ? 1 : 0;
     int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (int i = 0; i < 2 && rc == MS_OK; i++)
@@ -297,8 +298,8 @@ static int flags_to_rc(int32_t f, const char *where)
         return MS_ERR_CAPACITY;
     }
     if (f & MS_FLAG_ORDER_OVERFLOW) {
-        ms_set_error("%s: a page exceeds the device reading-order capacity (4096 boxes / 28672 intersecting pairs); run "
-                     "with sort_reading_order = 0 and order the boxes on the host", where);
+        ms_set_error("%s: a page exceeds the device reading-order capacity (max(65536, 16 cap_boxes) intersecting box "
+                     "pairs); run with sort_reading_order = 0 and order the boxes on the host", where);
         return MS_ERR_CAPACITY;
     }
     return MS_OK;
@@ -395,8 +396,8 @@ extern "C" int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n
         return MS_ERR_INVALID;
     }
     if (n == 0) return MS_OK;
-    if (n > 4096) {
-        ms_set_error("ms_reading_order_host: more than 4096 boxes on the page (got %lld)", (long long)n);
+    if (n > (1 << 20)) {
+        ms_set_error("ms_reading_order_host: more than 2^20 boxes on the page (got %lld)", (long long)n);
         return MS_ERR_CAPACITY;
     }
     const int cap = (int)n;
@@ -422,7 +423,8 @@ extern "C" int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n
     MS_CUDA(cudaMemcpyAsync(h + 4, d_i + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
     MS_CUDA(cudaStreamSynchronize(st));
     if (h[4] & MS_FLAG_ORDER_OVERFLOW) {
-        ms_set_error("ms_reading_order_host: more than 28672 intersecting box pairs on the page");
+        ms_set_error("ms_reading_order_host: more intersecting box pairs on the page than the device kernels hold "
+                     "(max(65536, 16 n))");
         return MS_ERR_CAPACITY;
     }
     return MS_OK;

@@ -52,6 +52,7 @@ struct ms_ctx {
     int graphs_enabled;           // 0 with MS_B200_NO_GRAPHS=1 in the environment
     int graph_clock;
     ms_graph_entry graphs[MS_GRAPH_SLOTS];
+    int ro_force_large;           // MS_B200_RO_FORCE_LARGE=1: every page takes the large-page reading-order kernel (tests)
     int busy;                     // 1 while a thread is inside an entry point (atomic test-and-set): a context owns ONE
                                   // scratch arena, so a second thread entering gets MS_ERR_INVALID instead of corrupting it
 };

@@ -105,7 +105,9 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
                                                                    const int32_t *__restrict__ counts, int cap,
                                                                    int4 *__restrict__ obox_g, int32_t *__restrict__ order,
                                                                    float *__restrict__ reordered, int32_t *__restrict__ flags,
-                                                                   uint16_t *__restrict__ gpairs16, int32_t *__restrict__ gbox32)
+                                                                   uint16_t *__restrict__ gpairs16, int32_t *__restrict__ gbox32,
+                                                                   int32_t *__restrict__ need_large,
+                                                                   int32_t *__restrict__ ticket, int force_large)
 {
     extern __shared__ __align__(16) unsigned char ro_smem[];
     int4 *box = reinterpret_cast<int4 *>(ro_smem);                                   // kRoMaxBoxes
@@ -134,16 +136,26 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     const int page = blockIdx.x;
     const int K = counts[page];
     const size_t pb = (size_t)page * cap;
-    // beyond the capacity of this kernel the page keeps its detection order and is flagged (the host side orders it)
+    if (threadIdx.x == 0 && need_large) {
+        need_large[page] = 0;
+        if (page == 0) *ticket = 0;  // the large-page kernel's work counter (it is launched after this kernel)
+    }
+    // beyond the capacity of this kernel the page is written in detection order and handed to reading_order_large_kernel
+    // (or, without one, flagged: the host side orders it)
     auto keep_detection_order = [&]() {
-        if (threadIdx.x == 0) atomicOr(flags + page, MS_FLAG_ORDER_OVERFLOW);
+        if (threadIdx.x == 0) {
+            if (need_large)
+                need_large[page] = 1;
+            else
+                atomicOr(flags + page, MS_FLAG_ORDER_OVERFLOW);
+        }
         for (int k = threadIdx.x; k < K; k += kRoThreads) {
             order[pb + k] = k;
             if (reordered)
                 for (int c = 0; c < row_stride; c++) reordered[(pb + k) * row_stride + c] = boxes8[(pb + k) * row_stride + c];
         }
     };
-    if (K > kRoMaxBoxes) {
+    if (K > kRoMaxBoxes || force_large) {
         keep_detection_order();
         return;
     }
@@ -749,12 +761,707 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     }
 }
 
+
+// =====================================================================================================================
+// Pages beyond the shared-memory kernel's capacity (more than 4096 boxes, or more than 28 672 initially intersecting
+// pairs): the same phases with every per-box / per-pair array in global scratch (L2-resident: a 10 000-box page needs
+// ~3 MB) and 32-bit indices.  One CTA per such page, at most kRlSlots pages in flight (one scratch slot each); the CTAs
+// draw the marked pages from a ticket counter.  Limits: kRlPairFactor * cap intersecting pairs per page (beyond that the
+// page keeps its detection order and is flagged, as before) and 4095 dependency levels for the parallel sweeps (deeper
+// chains are swept by one thread).  ~2 ms for a 10 000-box page instead of ~100 ms of host Python.
+// =====================================================================================================================
+constexpr int kRlCells = 64;        // pair-generation grid: cells per axis
+constexpr int kRlMaxLevels = 4095;  // dependency levels bucketed in shared memory
+constexpr int kRlSlots = 8;
+constexpr int kRlPairFactor = 16;
+constexpr uint32_t kRlNone = 0xffffffffu;
+
+__host__ __device__ inline int rl_pair_cap(int cap) { return cap * kRlPairFactor < 65536 ? 65536 : cap * kRlPairFactor; }
+__host__ __device__ inline int rl_grid_cap(int cap) { return 8 * cap + 4096; }
+__host__ __device__ inline int rl_pow2(int n)
+{
+    int p = 1;
+    while (p < n) p <<= 1;
+    return p;
+}
+
+// byte offsets of one slot's arrays (the same function sizes the scratch on the host and carves it in the kernel)
+struct RlLayout {
+    size_t box, pairs, lv, T, prevJ, bcnt, bstart, lastJ, row_cnt, row_start, centry, keys, keys2, line_sum, line_cy, line_cnt,
+        line_rank, line_of, seq_of, inv_seq, htab, obox, total;
+};
+__host__ __device__ inline RlLayout rl_layout(int cap)
+{
+    RlLayout L;
+    size_t o = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = o;
+        o = (o + bytes + 255) & ~size_t(255);
+        return at;
+    };
+    const size_t pc = (size_t)rl_pair_cap(cap), n2 = (size_t)rl_pow2(cap), c1 = (size_t)cap + 1;
+    L.box = take(c1 * 16);
+    L.obox = take(c1 * 16);
+    L.pairs = take(pc * 8);
+    L.lv = take(pc * 2);
+    L.T = take(pc * 4);       // transposed pair list, then the pairs bucketed by level
+    L.prevJ = take(pc * 4);
+    L.bcnt = take(c1 * 4);
+    L.bstart = take(c1 * 4);
+    L.lastJ = take(c1 * 4);
+    L.row_cnt = take(c1 * 4);
+    L.row_start = take(c1 * 4);
+    L.centry = take((size_t)rl_grid_cap(cap) * 4);
+    L.keys = take(n2 * 8);
+    L.keys2 = take(n2 * 4);
+    L.line_sum = take(c1 * 8);
+    L.line_cy = take(c1 * 8);
+    L.line_cnt = take(c1 * 4);
+    L.line_rank = take(c1 * 4);
+    L.line_of = take(c1 * 4);
+    L.seq_of = take(c1 * 4);
+    L.inv_seq = take(c1 * 4);
+    L.htab = take(n2 * 2 * 4);
+    L.total = o;
+    return L;
+}
+
+// exclusive scan of arr[0..n) in place (shared or global memory), n a multiple of kRoThreads or not; returns the total
+__device__ __forceinline__ int rl_scan_inplace(int *arr, int n, int *s_warp)
+{
+    int run = 0;
+    for (int base = 0; base < n; base += kRoThreads) {
+        const int i = base + threadIdx.x;
+        const int c = i < n ? arr[i] : 0;
+        int total;
+        const int off = run + ro_block_scan(c, s_warp, total);
+        if (i < n) arr[i] = off;
+        run += total;
+    }
+    __syncthreads();
+    return run;
+}
+
+// bitonic sort of (k1, k2) tuples, ascending
+__device__ __forceinline__ void rl_bitonic2(uint64_t *k1, uint32_t *k2, int n)
+{
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n; i += kRoThreads) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const uint64_t a1 = k1[i], b1 = k1[ixj];
+                    const uint32_t a2 = k2[i], b2 = k2[ixj];
+                    const bool gt = a1 > b1 || (a1 == b1 && a2 > b2);
+                    if (gt == ((i & k) == 0)) {
+                        k1[i] = b1;
+                        k1[ixj] = a1;
+                        k2[i] = b2;
+                        k2[ixj] = a2;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+struct RlShared {
+    int warp[33];
+    int g[4];
+    int np, lines, avg_pos, changed, maxl, dup, small, big, page;
+    long long hsum;
+    double ytol;
+    // phase B: cell counters / cell starts; phase C: level starts / fill cursors
+    int a[kRlCells * kRlCells + 2];
+    int b[kRlCells * kRlCells + 2];
+};
+
+// returns false when the page exceeds this kernel's pair capacity (the caller flags it)
+__device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int row_stride, int K, size_t pb, int cap,
+                              int32_t *__restrict__ order, float *__restrict__ reordered, unsigned char *slot)
+{
+    const RlLayout Lo = rl_layout(cap);
+    int4 *box = reinterpret_cast<int4 *>(slot + Lo.box);
+    int4 *obox = reinterpret_cast<int4 *>(slot + Lo.obox);
+    uint2 *pairs = reinterpret_cast<uint2 *>(slot + Lo.pairs);
+    uint16_t *lv = reinterpret_cast<uint16_t *>(slot + Lo.lv);
+    uint32_t *T = reinterpret_cast<uint32_t *>(slot + Lo.T);
+    uint32_t *prevJ = reinterpret_cast<uint32_t *>(slot + Lo.prevJ);
+    int *bcnt = reinterpret_cast<int *>(slot + Lo.bcnt);
+    int *bstart = reinterpret_cast<int *>(slot + Lo.bstart);
+    uint32_t *lastJ = reinterpret_cast<uint32_t *>(slot + Lo.lastJ);
+    int *row_cnt = reinterpret_cast<int *>(slot + Lo.row_cnt);
+    int *row_start = reinterpret_cast<int *>(slot + Lo.row_start);
+    uint32_t *centry = reinterpret_cast<uint32_t *>(slot + Lo.centry);
+    uint64_t *keys = reinterpret_cast<uint64_t *>(slot + Lo.keys);
+    uint32_t *keys2 = reinterpret_cast<uint32_t *>(slot + Lo.keys2);
+    long long *line_sum = reinterpret_cast<long long *>(slot + Lo.line_sum);
+    double *line_cy = reinterpret_cast<double *>(slot + Lo.line_cy);
+    int *line_cnt = reinterpret_cast<int *>(slot + Lo.line_cnt);
+    uint32_t *line_rank = reinterpret_cast<uint32_t *>(slot + Lo.line_rank);
+    uint32_t *line_of = reinterpret_cast<uint32_t *>(slot + Lo.line_of);
+    uint32_t *seq_of = reinterpret_cast<uint32_t *>(slot + Lo.seq_of);
+    int *inv_seq = reinterpret_cast<int *>(slot + Lo.inv_seq);
+    uint32_t *htab = reinterpret_cast<uint32_t *>(slot + Lo.htab);
+    const int pair_cap = rl_pair_cap(cap), grid_cap = rl_grid_cap(cap);
+    constexpr int NC = kRlCells * kRlCells;
+
+    // A. integer boxes (_pipeline.py:105-109)
+    for (int k = threadIdx.x; k < K; k += kRoThreads) {
+        const float *q = boxes8 + (pb + k) * row_stride;
+        int xmin, xmax, ymin, ymax;
+        xmin = xmax = ro_trunc(q[0]);
+        ymin = ymax = ro_trunc(q[1]);
+#pragma unroll
+        for (int v = 1; v < 4; v++) {
+            const int x = ro_trunc(q[2 * v]), y = ro_trunc(q[2 * v + 1]);
+            xmin = min(xmin, x);
+            xmax = max(xmax, x);
+            ymin = min(ymin, y);
+            ymax = max(ymax, y);
+        }
+        const int4 b = make_int4(xmin, ymin, xmax, ymax);
+        box[k] = b;
+        obox[k] = b;
+    }
+    if (threadIdx.x == 0) {
+        S.g[0] = S.g[1] = INT_MAX;
+        S.g[2] = S.g[3] = INT_MIN;
+        S.big = 0;
+    }
+    for (int t = threadIdx.x; t < NC + 2; t += kRoThreads) S.a[t] = 0;
+    __syncthreads();
+
+    // B. initially intersecting pairs (i < j) in (i, j) order through a 64 x 64 grid over the boxes' hull (see the
+    //    shared-memory kernel); all pairs when a box covers more than 64 cells or the registrations exceed the table
+    int *ccnt = S.a, *cstart = S.b;
+    {
+        int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
+        for (int i = threadIdx.x; i < K; i += kRoThreads) {
+            const int4 b = box[i];
+            mnx = min(mnx, min(b.x, b.z));
+            mxx = max(mxx, max(b.x, b.z));
+            mny = min(mny, min(b.y, b.w));
+            mxy = max(mxy, max(b.y, b.w));
+        }
+        mnx = __reduce_min_sync(0xffffffffu, mnx);
+        mny = __reduce_min_sync(0xffffffffu, mny);
+        mxx = __reduce_max_sync(0xffffffffu, mxx);
+        mxy = __reduce_max_sync(0xffffffffu, mxy);
+        if ((threadIdx.x & 31) == 0) {
+            atomicMin(&S.g[0], mnx);
+            atomicMin(&S.g[1], mny);
+            atomicMax(&S.g[2], mxx);
+            atomicMax(&S.g[3], mxy);
+        }
+    }
+    __syncthreads();
+    const int gx0 = S.g[0], gy0 = S.g[1];
+    int shx = 0, shy = 0;
+    {
+        const uint32_t ex = (uint32_t)S.g[2] - (uint32_t)gx0, ey = (uint32_t)S.g[3] - (uint32_t)gy0;
+        while ((ex >> shx) >= (uint32_t)kRlCells) shx++;
+        while ((ey >> shy) >= (uint32_t)kRlCells) shy++;
+    }
+    auto cell_x = [&](int x) { return (int)(((uint32_t)x - (uint32_t)gx0) >> shx); };
+    auto cell_y = [&](int y) { return (int)(((uint32_t)y - (uint32_t)gy0) >> shy); };
+    {
+        int mine = 0, big = 0;
+        for (int i = threadIdx.x; i < K; i += kRoThreads) {
+            const int4 b = box[i];
+            const int cx0 = cell_x(min(b.x, b.z)), cx1 = cell_x(max(b.x, b.z));
+            const int cy0 = cell_y(min(b.y, b.w)), cy1 = cell_y(max(b.y, b.w));
+            const int nc = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
+            if (nc <= 64) {
+                mine += nc;
+                for (int cy = cy0; cy <= cy1; cy++)
+                    for (int cx = cx0; cx <= cx1; cx++) atomicAdd(&ccnt[cy * kRlCells + cx], 1);
+            } else {
+                big = 1;  // a box over more than 64 cells: not worth a grid
+            }
+        }
+        int total_e;
+        ro_block_scan(mine, S.warp, total_e);
+        if (big) S.big = 1;
+        __syncthreads();
+        if (total_e > grid_cap && threadIdx.x == 0) S.big = 1;
+        __syncthreads();
+    }
+    const bool grid = S.big == 0;
+    if (grid) {
+        for (int t = threadIdx.x; t < NC; t += kRoThreads) cstart[t] = ccnt[t];
+        __syncthreads();
+        const int total_c = rl_scan_inplace(cstart, NC, S.warp);
+        if (threadIdx.x == 0) cstart[NC] = total_c;
+        for (int t = threadIdx.x; t < NC; t += kRoThreads) ccnt[t] = 0;
+        __syncthreads();
+        for (int i = threadIdx.x; i < K; i += kRoThreads) {
+            const int4 b = box[i];
+            const int cx0 = cell_x(min(b.x, b.z)), cx1 = cell_x(max(b.x, b.z));
+            const int cy0 = cell_y(min(b.y, b.w)), cy1 = cell_y(max(b.y, b.w));
+            for (int cy = cy0; cy <= cy1; cy++)
+                for (int cx = cx0; cx <= cx1; cx++) {
+                    const int c = cy * kRlCells + cx;
+                    centry[cstart[c] + atomicAdd(&ccnt[c], 1)] = (uint32_t)i;
+                }
+        }
+        __syncthreads();
+    }
+    auto row_pass = [&](int i, int off, bool write) -> int {
+        const int4 bi = box[i];
+        int cnt = 0;
+        if (grid) {
+            const int cx0 = cell_x(min(bi.x, bi.z)), cx1 = cell_x(max(bi.x, bi.z));
+            const int cy0 = cell_y(min(bi.y, bi.w)), cy1 = cell_y(max(bi.y, bi.w));
+            for (int cy = cy0; cy <= cy1; cy++)
+                for (int cx = cx0; cx <= cx1; cx++) {
+                    const int c = cy * kRlCells + cx;
+                    const int e1 = cstart[c + 1];
+                    for (int e = cstart[c]; e < e1; e++) {
+                        const int j = (int)centry[e];
+                        if (j <= i) continue;
+                        const int4 bj = box[j];
+                        if (!ro_intersect(bi, bj)) continue;
+                        if (cell_y(max(bi.y, bj.y)) * kRlCells + cell_x(max(bi.x, bj.x)) != c) continue;  // another cell's
+                        if (write && off + cnt < pair_cap) pairs[off + cnt] = make_uint2((uint32_t)i, (uint32_t)j);
+                        cnt++;
+                    }
+                }
+        } else {
+            for (int j = i + 1; j < K; j++) {
+                if (!ro_intersect(bi, box[j])) continue;
+                if (write && off + cnt < pair_cap) pairs[off + cnt] = make_uint2((uint32_t)i, (uint32_t)j);
+                cnt++;
+            }
+        }
+        return cnt;
+    };
+    const int half = (K + 1) / 2;
+    for (int t = threadIdx.x; t < half; t += kRoThreads) {
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const int i = side == 0 ? t : K - 1 - t;
+            if (side == 1 && i == t) break;
+            row_cnt[i] = min(row_pass(i, 0, false), pair_cap + 1);
+        }
+    }
+    __syncthreads();
+    long long run_ll = 0;
+    for (int base = 0; base < K; base += kRoThreads) {
+        const int i = base + threadIdx.x;
+        const int cnt = i < K ? row_cnt[i] : 0;
+        int total;
+        const int off = ro_block_scan(cnt, S.warp, total);  // < 1024 * (pair_cap + 1): fits 32 bits for cap <= 2^16
+        if (i < K) row_start[i] = (int)min(run_ll + off, (long long)pair_cap);
+        run_ll += total;
+    }
+    if (run_ll > pair_cap) return false;  // uniform over the CTA
+    const int np = (int)run_ll;
+    __syncthreads();
+    for (int t = threadIdx.x; t < half; t += kRoThreads) {
+#pragma unroll 1
+        for (int side = 0; side < 2; side++) {
+            const int i = side == 0 ? t : K - 1 - t;
+            if (side == 1 && i == t) break;
+            if (row_cnt[i] == 0) continue;
+            const int s0 = row_start[i];
+            row_pass(i, s0, true);
+            if (grid) {  // cell order -> ascending j (insertion sort of a short row)
+                const int e0 = s0 + row_cnt[i];
+                for (int a = s0 + 1; a < e0; a++) {
+                    const uint2 v = pairs[a];
+                    int bpos = a - 1;
+                    while (bpos >= s0 && pairs[bpos].y > v.y) {
+                        pairs[bpos + 1] = pairs[bpos];
+                        bpos--;
+                    }
+                    pairs[bpos + 1] = v;
+                }
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        S.np = np;
+        row_start[K] = np;
+        S.maxl = 0;
+    }
+    __syncthreads();
+
+    // C. dependency levels of the pairs (see the shared-memory kernel), then the shrink sweeps (utils.py:521-545)
+    {
+        for (int k = threadIdx.x; k <= K; k += kRoThreads) bcnt[k] = 0;
+        __syncthreads();
+        for (int p = threadIdx.x; p < np; p += kRoThreads) atomicAdd(&bcnt[pairs[p].y], 1);
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += kRoThreads) bstart[k] = bcnt[k];
+        __syncthreads();
+        const int run2 = rl_scan_inplace(bstart, K, S.warp);
+        for (int k = threadIdx.x; k < K; k += kRoThreads) bcnt[k] = 0;
+        if (threadIdx.x == 0) bstart[K] = run2;
+        __syncthreads();
+        for (int p = threadIdx.x; p < np; p += kRoThreads) {
+            const int j = (int)pairs[p].y;
+            T[bstart[j] + atomicAdd(&bcnt[j], 1)] = (uint32_t)p;
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < K; j += kRoThreads) {
+            const int s0 = bstart[j], e0 = bstart[j + 1];
+            for (int a = s0 + 1; a < e0; a++) {  // insertion sort of a short bucket
+                const uint32_t v = T[a];
+                int b = a - 1;
+                while (b >= s0 && T[b] > v) {
+                    T[b + 1] = T[b];
+                    b--;
+                }
+                T[b + 1] = v;
+            }
+            for (int a = s0; a < e0; a++) prevJ[T[a]] = a > s0 ? T[a - 1] : kRlNone;
+            lastJ[j] = e0 > s0 ? T[e0 - 1] : kRlNone;
+        }
+        for (int p = threadIdx.x; p < np; p += kRoThreads) lv[p] = 1;
+        __syncthreads();
+        for (int pass = 0; pass < kRlMaxLevels + 2; pass++) {
+            int changed = 0;
+            for (int p = threadIdx.x; p < np; p += kRoThreads) {
+                const int i = (int)pairs[p].x;
+                const uint32_t pi = p > row_start[i] ? (uint32_t)(p - 1) : lastJ[i];
+                const uint32_t pj = prevJ[p];
+                const int a = pi == kRlNone ? 0 : (int)lv[pi], b = pj == kRlNone ? 0 : (int)lv[pj];
+                const int l = 1 + max(a, b);
+                if (l > kRlMaxLevels) {
+                    S.maxl = -1;  // too deep for the level buckets: sequential sweeps below
+                } else if (l != (int)lv[p]) {
+                    lv[p] = (uint16_t)l;
+                    changed = 1;
+                }
+            }
+            if (!__syncthreads_or(changed) || S.maxl < 0) break;
+        }
+        if (S.maxl >= 0) {
+            int m = 0;
+            for (int p = threadIdx.x; p < np; p += kRoThreads) m = max(m, (int)lv[p]);
+            m = __reduce_max_sync(0xffffffffu, m);
+            if ((threadIdx.x & 31) == 0) atomicMax(&S.maxl, m);
+        }
+    }
+    __syncthreads();
+    if (S.maxl >= 0) {
+        const int maxl = S.maxl;
+        int *lstart = S.a, *lfill = S.b;  // the grid tables are dead
+        uint32_t *byl = T;                // so is the transposed list
+        for (int t = threadIdx.x; t <= kRlMaxLevels + 1; t += kRoThreads) lstart[t] = 0;
+        __syncthreads();
+        for (int p = threadIdx.x; p < np; p += kRoThreads) atomicAdd(&lstart[lv[p]], 1);
+        __syncthreads();
+        rl_scan_inplace(lstart, kRlMaxLevels + 2, S.warp);
+        for (int t = threadIdx.x; t <= kRlMaxLevels + 1; t += kRoThreads) lfill[t] = lstart[t];
+        __syncthreads();
+        for (int p = threadIdx.x; p < np; p += kRoThreads) byl[atomicAdd(&lfill[lv[p]], 1)] = (uint32_t)p;
+        __syncthreads();
+        for (int sweep = 0; sweep < 50; sweep++) {
+            if (threadIdx.x == 0) S.changed = 0;
+            __syncthreads();
+            for (int l = 1; l <= maxl; l++) {
+                const int e0 = lfill[l];  // == start of level l + 1
+                for (int t = lstart[l] + threadIdx.x; t < e0; t += kRoThreads) {
+                    const int p = (int)byl[t];
+                    if (lv[p] == 0) continue;
+                    const uint2 pr = pairs[p];
+                    int4 a = box[pr.x], c = box[pr.y];
+                    if (ro_intersect(a, c)) {
+                        a.z = ro_shrink(a.x, a.z);
+                        a.w = ro_shrink(a.y, a.w);
+                        c.z = ro_shrink(c.x, c.z);
+                        c.w = ro_shrink(c.y, c.w);
+                        box[pr.x] = a;
+                        box[pr.y] = c;
+                        S.changed = 1;
+                    } else {
+                        lv[p] = 0;
+                    }
+                }
+                __syncthreads();
+            }
+            const int changed = S.changed;
+            __syncthreads();
+            if (!changed) break;
+        }
+    } else if (threadIdx.x == 0) {
+        int n = np;
+        for (int sweep = 0; sweep < 50; sweep++) {
+            bool changed = false;
+            int w = 0;
+            for (int p = 0; p < n; p++) {
+                const uint2 pr = pairs[p];
+                int4 a = box[pr.x], c = box[pr.y];
+                if (ro_intersect(a, c)) {
+                    a.z = ro_shrink(a.x, a.z);
+                    a.w = ro_shrink(a.y, a.w);
+                    c.z = ro_shrink(c.x, c.z);
+                    c.w = ro_shrink(c.y, c.w);
+                    box[pr.x] = a;
+                    box[pr.y] = c;
+                    changed = true;
+                    pairs[w++] = pr;
+                }
+            }
+            n = w;
+            if (!changed) break;
+        }
+    }
+    __syncthreads();
+
+    // D1. avg_h (utils.py:581) and the vertical tolerance
+    {
+        long long hs = 0;
+        for (int k = threadIdx.x; k < K; k += kRoThreads) hs += (long long)box[k].w - (long long)box[k].y;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, off);
+        if (threadIdx.x == 0) S.hsum = 0;
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&S.hsum), (unsigned long long)hs);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const double avg = K > 0 ? (double)S.hsum / (double)K : 0.0;
+            S.ytol = avg * 0.6;
+            S.avg_pos = avg > 0.0 ? 1 : 0;
+            S.lines = 0;
+        }
+    }
+    __syncthreads();
+
+    // D2. stable order by centre y (utils.py:584): key = y0 + y1, ties by index (20 bits)
+    const int n2 = rl_pow2(K);
+    for (int i = threadIdx.x; i < n2; i += kRoThreads) {
+        uint64_t key = ~0ull;
+        if (i < K) {
+            const long long s2 = (long long)box[i].y + (long long)box[i].w;
+            key = ((uint64_t)(s2 + (1ll << 33)) << 20) | (uint64_t)i;
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    ro_bitonic(keys, n2);
+
+    // D3. line assignment by warp 0 (utils.py:584-603; the argument why only the newest line can match, and the exact
+    //     integer test, are in the shared-memory kernel)
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
+        const double ytol = S.ytol;
+        const bool tol_int = ytol >= 0.0 && ytol < 1.0e6;
+        const long long tolq = tol_int ? __double2ll_rn(2.0 * ytol * 65536.0) : 0;
+        const bool xgap_ok = S.avg_pos != 0;
+        auto line_ok = [&](long long s2, long long sum, long long cnt) -> bool {
+            const long long N = s2 * cnt - sum;
+            const long long aN = N < 0 ? -N : N, asum = sum < 0 ? -sum : sum;
+            const long long lhs = aN << 16, rhs = cnt * tolq;
+            const long long slack = cnt + ((asum + aN) >> 13) + 2;
+            if (tol_int && lhs <= rhs - slack) return true;
+            if (tol_int && lhs >= rhs + slack) return false;
+            const double d = (double)s2 / 2.0 - ((double)sum * 0.5) / (double)cnt;
+            return fabs(d) <= ytol;
+        };
+        int L = 0;
+        long long cur_sum = 0;
+        int cur_cnt = 0;
+        if (!xgap_ok) {
+            for (int r = lane; r < K; r += 32) {
+                const int k = (int)(keys[r] & 0xfffffu);
+                line_sum[r] = (long long)box[k].y + (long long)box[k].w;
+                line_cnt[r] = 1;
+                line_of[k] = (uint32_t)r;
+                seq_of[k] = (uint32_t)r;
+            }
+            L = K;
+        }
+        for (int r = xgap_ok ? 0 : K; r < K;) {
+            const int n = min(32, K - r);
+            int k = 0;
+            long long s2 = 0;
+            if (lane < n) {
+                k = (int)(keys[r + lane] & 0xfffffu);
+                const int4 b = box[k];
+                s2 = (long long)b.y + (long long)b.w;
+            }
+            long long pre = s2;
+#pragma unroll
+            for (int off = 1; off < 32; off <<= 1) {
+                const long long t = __shfl_up_sync(0xffffffffu, pre, off);
+                if (lane >= off) pre += t;
+            }
+            bool ok = false;
+            if (lane < n && xgap_ok && L > 0) ok = line_ok(s2, cur_sum + pre - s2, (long long)cur_cnt + lane);
+            const uint32_t fail = __ballot_sync(0xffffffffu, !ok);
+            const int f = __ffs(fail) - 1;
+            const int joined = f < 0 ? 32 : f;
+            if (lane < joined) {
+                line_of[k] = (uint32_t)(L - 1);
+                seq_of[k] = (uint32_t)(r + lane);
+            }
+            if (joined > 0) {
+                cur_sum += __shfl_sync(0xffffffffu, pre, joined - 1);
+                cur_cnt += joined;
+            }
+            if (joined < n) {
+                if (lane == 0 && L > 0) {
+                    line_sum[L - 1] = cur_sum;
+                    line_cnt[L - 1] = cur_cnt;
+                }
+                cur_sum = __shfl_sync(0xffffffffu, s2, joined);
+                cur_cnt = 1;
+                if (lane == joined) {
+                    line_of[k] = (uint32_t)L;
+                    seq_of[k] = (uint32_t)(r + lane);
+                }
+                L++;
+                r += joined + 1;
+            } else {
+                r += joined;
+            }
+        }
+        if (lane == 0) {
+            if (L > 0 && xgap_ok) {
+                line_sum[L - 1] = cur_sum;
+                line_cnt[L - 1] = cur_cnt;
+            }
+            S.lines = L;
+        }
+    }
+    __syncthreads();
+    const int L = S.lines;
+    for (int l = threadIdx.x; l < L; l += kRoThreads) line_cy[l] = ((double)line_sum[l] * 0.5) / (double)line_cnt[l];
+    __syncthreads();
+
+    // D4. lines ordered by mean centre (utils.py:605, stable)
+    for (int l = threadIdx.x; l < L; l += kRoThreads) {
+        const uint64_t key = ro_orderable(line_cy[l]);
+        int rank = 0;
+        for (int m = 0; m < L; m++) {
+            const uint64_t km = ro_orderable(line_cy[m]);
+            rank += (km < key || (km == key && m < l)) ? 1 : 0;
+        }
+        line_rank[l] = (uint32_t)rank;
+    }
+    __syncthreads();
+
+    // D5. boxes by (line, x0, insertion order) (utils.py:606-609): a (u64, u32) key
+    for (int i = threadIdx.x; i < n2; i += kRoThreads) {
+        uint64_t k1 = ~0ull;
+        uint32_t k2 = ~0u;
+        if (i < K) {
+            k1 = ((uint64_t)line_rank[line_of[i]] << 32) | (uint64_t)(uint32_t)((long long)box[i].x + (1ll << 31));
+            k2 = seq_of[i];
+        }
+        keys[i] = k1;
+        keys2[i] = k2;
+    }
+    for (int k = threadIdx.x; k < K; k += kRoThreads) inv_seq[seq_of[k]] = k;
+    __syncthreads();
+    rl_bitonic2(keys, keys2, n2);
+
+    // E. utils.py:639 (the LAST box with equal compressed coordinates wins) and _pipeline.py:113-123 (the FIRST word
+    //    with the same integer box), behind a hash-table check that two boxes coincide at all
+    if (threadIdx.x == 0) S.dup = 0;
+    const uint32_t hmask = (uint32_t)(2 * n2 - 1);
+    for (int pass = 0; pass < 2; pass++) {
+        const int4 *arr = pass == 0 ? box : obox;
+        for (uint32_t t = threadIdx.x; t <= hmask; t += kRoThreads) htab[t] = kRlNone;
+        __syncthreads();
+        for (int k = threadIdx.x; k < K; k += kRoThreads) {
+            const int4 v = arr[k];
+            uint32_t h = (uint32_t)v.x * 0x9E3779B1u ^ (uint32_t)v.y * 0x85EBCA77u ^ (uint32_t)v.z * 0xC2B2AE3Du ^
+                         (uint32_t)v.w * 0x27D4EB2Fu;
+            h ^= h >> 15;
+            for (uint32_t s = h & hmask;; s = (s + 1) & hmask) {  // K <= n2 < 2 n2 slots: a free slot exists
+                const uint32_t old = atomicCAS(&htab[s], kRlNone, (uint32_t)k);
+                if (old == kRlNone) break;
+                const int4 o = arr[old];
+                if (o.x == v.x && o.y == v.y && o.z == v.z && o.w == v.w) {
+                    S.dup = 1;
+                    break;
+                }
+            }
+        }
+        __syncthreads();
+    }
+    const bool any_dup = S.dup != 0;
+    for (int r = threadIdx.x; r < K; r += kRoThreads) {
+        const int k = inv_seq[keys2[r]];
+        int first = k;
+        if (any_dup) {
+            const int4 ck = box[k];
+            int last = k;
+            for (int m = K - 1; m > k; m--) {
+                const int4 cm = box[m];
+                if (cm.x == ck.x && cm.y == ck.y && cm.z == ck.z && cm.w == ck.w) {
+                    last = m;
+                    break;
+                }
+            }
+            const int4 ob = obox[last];
+            first = last;
+            for (int w = 0; w < last; w++) {
+                const int4 ow = obox[w];
+                if (ow.x == ob.x && ow.y == ob.y && ow.z == ob.z && ow.w == ob.w) {
+                    first = w;
+                    break;
+                }
+            }
+        }
+        order[pb + r] = first;
+        if (reordered) {
+            const float *src = boxes8 + (pb + first) * row_stride;
+            float *dst = reordered + (pb + r) * row_stride;
+            for (int c = 0; c < row_stride; c++) dst[c] = src[c];
+        }
+    }
+    return true;
+}
+
+__global__ void __launch_bounds__(kRoThreads) reading_order_large_kernel(const float *__restrict__ boxes8, int row_stride,
+                                                                         const int32_t *__restrict__ counts, int cap,
+                                                                         int n_pages, int32_t *__restrict__ order,
+                                                                         float *__restrict__ reordered,
+                                                                         int32_t *__restrict__ flags,
+                                                                         const int32_t *__restrict__ need_large,
+                                                                         int32_t *__restrict__ ticket,
+                                                                         unsigned char *__restrict__ slots,
+                                                                         size_t slot_bytes)
+{
+    __shared__ RlShared S;
+    for (;;) {
+        __syncthreads();  // the previous page's shared state is no longer read
+        if (threadIdx.x == 0) {
+            int p;
+            do {
+                p = atomicAdd(ticket, 1);
+            } while (p < n_pages && need_large[p] == 0);
+            S.page = p;
+        }
+        __syncthreads();
+        const int page = S.page;
+        if (page >= n_pages) return;
+        const bool ok = rl_order_page(S, boxes8, row_stride, counts[page], (size_t)page * cap, cap, order, reordered,
+                                      slots + (size_t)blockIdx.x * slot_bytes);
+        // beyond this kernel's capacity too: the page keeps the detection order the first kernel wrote, and is flagged
+        if (!ok && threadIdx.x == 0) atomicOr(flags + page, MS_FLAG_ORDER_OVERFLOW);
+    }
+}
+
 }  // namespace
+
+static int rl_slots(int n_pages, int cap_per_page)
+{
+    if (cap_per_page > (1 << 20)) return 0;  // 20-bit box indices in the sort keys
+    return n_pages < kRlSlots ? n_pages : kRlSlots;
+}
 
 size_t msk_reading_order_scratch(int n_pages, int cap_per_page)
 {
     return (size_t)n_pages * cap_per_page * sizeof(int4) + (size_t)n_pages * 2 * kRoMaxPairs * sizeof(uint16_t) +
-           (size_t)n_pages * 2 * (kRoMaxBoxes + 1) * sizeof(int32_t) + 4096;
+           (size_t)n_pages * 2 * (kRoMaxBoxes + 1) * sizeof(int32_t) + (size_t)(n_pages + 1) * sizeof(int32_t) +
+           (size_t)rl_slots(n_pages, cap_per_page) * rl_layout(cap_per_page).total + 8192;
 }
 
 // order (n_pages*cap) int32: order[p*cap + r] = index of the word at reading position r; `reordered` (may be NULL)
@@ -766,7 +1473,11 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
     int4 *obox = bump.take<int4>((size_t)n_pages * cap_per_page);
     uint16_t *gpairs16 = bump.take<uint16_t>((size_t)n_pages * 2 * kRoMaxPairs);
     int32_t *gbox32 = bump.take<int32_t>((size_t)n_pages * 2 * (kRoMaxBoxes + 1));
-    if (!obox || !gpairs16 || !gbox32) {
+    const int slots = rl_slots(n_pages, cap_per_page);
+    const size_t slot_bytes = rl_layout(cap_per_page).total;
+    int32_t *need_large = slots ? bump.take<int32_t>((size_t)n_pages + 1) : nullptr;  // [n_pages]: ticket counter
+    unsigned char *slot_mem = slots ? bump.take<unsigned char>((size_t)slots * slot_bytes) : nullptr;
+    if (!obox || !gpairs16 || !gbox32 || (slots && (!need_large || !slot_mem))) {
         ms_set_error("reading_order: scratch too small");
         return MS_ERR_CAPACITY;
     }
@@ -779,7 +1490,15 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
         ctx->smem_attr[3] = (int)smem;
     }
     reading_order_kernel<<<n_pages, kRoThreads, smem, st>>>(boxes8, row_stride, counts, cap_per_page, obox, order,
-                                                           reordered, flags, gpairs16, gbox32);
+                                                           reordered, flags, gpairs16, gbox32, need_large,
+                                                           need_large ? need_large + n_pages : nullptr,
+                                                           slots ? ctx->ro_force_large : 0);
     MS_LAUNCH_CHECK(ctx);
+    if (slots) {  // pages the first kernel could not hold (none, usually: the CTAs find no ticket and leave)
+        reading_order_large_kernel<<<slots, kRoThreads, 0, st>>>(boxes8, row_stride, counts, cap_per_page, n_pages, order,
+                                                                reordered, flags, need_large, need_large + n_pages,
+                                                                slot_mem, slot_bytes);
+        MS_LAUNCH_CHECK(ctx);
+    }
     return MS_OK;
 }

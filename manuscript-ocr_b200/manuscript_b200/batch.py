@@ -78,7 +78,7 @@ def _raise_for_flags(flags, allow_order_overflow=False):
     if f & MS_FLAG_EDGE_OVERFLOW:
         raise CABIError(-3, "NMS suppression-edge buffer exceeded")
     if f & MS_FLAG_ORDER_OVERFLOW:
-        raise ReadingOrderCapacity(-3, "a page exceeds the device reading-order capacity (4096 boxes / 28672 intersecting "
+        raise ReadingOrderCapacity(-3, "a page exceeds the device reading-order capacity (max(65536, 16 cap_boxes) intersecting "
                                        "pairs): its boxes and crops are in detection order")
 
 

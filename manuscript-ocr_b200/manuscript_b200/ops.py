@@ -178,16 +178,17 @@ def word_rects(polys, img_h, img_w, min_text_size=5, ctx=None):
 def word_reading_order(polys, ctx=None):
     """polys (n,4,2) or (n,>=8) float -> (n,) int32: index of the word at each reading position, exactly what
     Pipeline.predict's sort + re-match loop produces (duplicates resolved the way the reference's dict / first-match
-    loops do).  Up to 4096 boxes and 28672 intersecting pairs on the device, the exact host restatement beyond."""
+    loops do).  On the device: up to 4096 boxes and 28672 intersecting pairs in one shared-memory kernel, larger pages
+    in the global-memory kernel (up to max(65536, 16 n) intersecting pairs); the exact host restatement beyond that."""
     n = len(polys)
     order = np.zeros(n, np.int32)
     if n == 0:
         return order
     p = np.ascontiguousarray(np.asarray(polys, dtype=np.float32).reshape(n, -1)[:, :8])
     cx = _ctx(ctx)
-    rc = cx.lib.ms_reading_order_host(cx.handle, _ptr(p), n, _ptr(order)) if n <= 4096 else _cabi.MS_ERR_CAPACITY
+    rc = cx.lib.ms_reading_order_host(cx.handle, _ptr(p), n, _ptr(order)) if n <= (1 << 20) else _cabi.MS_ERR_CAPACITY
     if rc == _cabi.MS_ERR_CAPACITY:
-        # beyond the device kernel's capacity (4096 boxes / 28672 intersecting pairs): the exact host restatement of the
+        # beyond the device kernels' capacity (more than max(65536, 16 n) intersecting pairs): the exact host restatement of the
         # reference's own host logic (this step runs on the host in the reference too; it is not a CPU path of a kernel)
         from .reading_order import host_word_order
 

@@ -477,15 +477,19 @@ def test_pipeline_fused_route_is_device_resident_and_exact(mb):
     assert [w.polygon for w in again.blocks[0].words] == [w.polygon for w in got_words]
 
 
-# ---- reading order beyond the device kernel's capacity: flagged, never wrong, ordered by the host restatement ----------
-def test_reading_order_beyond_device_capacity(mb, golden_dir):
-    """BASELINE configs[3] (10 000 boxes > 4096) and a page of 3000 boxes with > 28 672 intersecting pairs: the device
-    stage leaves the page in detection order and flags it (MS_FLAG_ORDER_OVERFLOW); word_reading_order / reorder_words /
-    Pipeline.predict then use the exact host restatement.  The 10 000-box order is the REAL reference's (committed by
-    tests/golden/make_golden_large.py)."""
+# ---- reading order of pages beyond the shared-memory kernel: the global-memory kernel, then the flag + host restatement ---
+def test_reading_order_large_pages(mb, golden_dir):
+    """BASELINE configs[3] (10 000 boxes > 4096) and a page of 3000 boxes with > 28 672 intersecting pairs run in the
+    global-memory kernel (reading_order_large_kernel): no flag, device order == the REAL reference's (committed by
+    tests/golden/make_golden_large.py).  A page with more intersecting pairs than that kernel holds keeps its
+    detection order and is flagged (MS_FLAG_ORDER_OVERFLOW); word_reading_order / reorder_words / Pipeline.predict
+    then use the exact host restatement."""
+    import ctypes as C
+
     import torch
 
     from manuscript_b200._cabi import MS_FLAG_ORDER_OVERFLOW
+    from manuscript_b200.reading_order import host_word_order
 
     g = np.load(os.path.join(golden_dir, "large_pages.npz"))
     page, words = 4096, 10000
@@ -495,20 +499,22 @@ def test_reading_order_beyond_device_capacity(mb, golden_dir):
     final = plain.run(torch.from_numpy(score[None]).cuda(), torch.from_numpy(geo[None]).cuda(), None,
                       sync=True).page_boxes(0).cpu().numpy()
     assert len(final) == int(g["cfg3_n_final"])
-    order = mb.word_reading_order(final[:, :8])            # 10 000 boxes: host restatement
+    order = mb.word_reading_order(final[:, :8])            # 10 000 boxes: the global-memory kernel
     np.testing.assert_array_equal(order, g["cfg3_order"])  # == the reference's order
+    np.testing.assert_array_equal(host_word_order(final[:, :8]), g["cfg3_order"])  # the last-resort host restatement too
     ro = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page, sort_reading_order=1), cap_boxes=16384,
                       crops_cap=12000)
     res = ro.run(torch.from_numpy(score[None]).cuda(), torch.from_numpy(geo[None]).cuda(),
                  torch.from_numpy(img[None]).cuda(), sync=False)
     torch.cuda.synchronize()
-    assert int(res.flags.cpu()[0]) == MS_FLAG_ORDER_OVERFLOW and list(res.order_overflow_pages()) == [0]
-    np.testing.assert_array_equal(res.page_boxes(0).cpu().numpy(), final)  # detection order, every row intact
-    with pytest.raises(mb.CABIError):
-        res.raise_for_flags()
-    res.raise_for_flags(allow_order_overflow=True)
+    assert int(res.flags.cpu()[0]) == 0 and list(res.order_overflow_pages()) == []
+    np.testing.assert_array_equal(res.page_boxes(0).cpu().numpy(), final[g["cfg3_order"]])
+    res.raise_for_flags()
+    rects, valid = cpu.word_rects(final[g["cfg3_order"]], page, page, 5)
+    nc = int(res.n_crops.cpu()[0])
+    np.testing.assert_array_equal(res.crops[:nc].cpu().numpy()[:, 1:], rects[valid])  # the crops follow the reading order
 
-    # the whole thing through Pipeline.predict: fused route, host order, crops cut from the one uploaded page
+    # the whole thing through Pipeline.predict: fused route, everything on the device
     class Net:
         def __call__(self, x):
             return {"score": torch.from_numpy(score)[None, None].cuda(), "geometry": torch.from_numpy(geo)[None].cuda()}
@@ -517,19 +523,117 @@ def test_reading_order_beyond_device_capacity(mb, golden_dir):
     rec = mb.TRBA(model=lambda b: (seen.append(len(b)), [("t", 0.5)] * len(b))[1], img_h=32, img_w=128, batch_size=512)
     pipe = mb.Pipeline(detector=mb.EAST(model=Net(), target_size=page, cap_boxes=16384), recognizer=rec)
     pg = pipe.predict(img)
-    assert pipe.last_route == "fused+host_order"
+    assert pipe.last_route == "fused"
     got = np.array([[v for pt in w.polygon for v in pt] for w in pg.blocks[0].words], np.float32)
     np.testing.assert_array_equal(got, final[g["cfg3_order"], :8])
     assert sum(seen) == sum(1 for w in pg.blocks[0].words if w.text == "t") == 10000
 
-    # <= 4096 boxes but far too many intersecting pairs
+    # <= 4096 boxes but more intersecting pairs than the shared-memory kernel holds: the global-memory kernel again
     rng = np.random.default_rng(7)
     n = 3000
+    x0, y0 = rng.integers(0, 800, n), rng.integers(0, 800, n)
+    bx = np.stack([x0, y0, x0 + rng.integers(20, 80, n), y0 + rng.integers(10, 40, n)], axis=1)
+    b64 = bx.astype(np.int64)
+    inter = ~((b64[:, None, 2] <= b64[None, :, 0]) | (b64[None, :, 2] <= b64[:, None, 0]) |
+              (b64[:, None, 3] <= b64[None, :, 1]) | (b64[None, :, 3] <= b64[:, None, 1]))
+    n_pairs = (int(inter.sum()) - n) // 2
+    assert 28672 < n_pairs < 65536, n_pairs
+    assert list(mb.word_reading_order(_boxes_to_polys(bx))) == _host_order(mb, bx)
+
+    # far too many intersecting pairs for either kernel: flagged on the device, ordered by the host restatement
     x0, y0 = rng.integers(0, 300, n), rng.integers(0, 300, n)
     bx = np.stack([x0, y0, x0 + rng.integers(20, 80, n), y0 + rng.integers(10, 40, n)], axis=1)
     polys = _boxes_to_polys(bx)
-    got = mb.word_reading_order(polys)
-    assert list(got) == _host_order(mb, bx)
+    assert list(mb.word_reading_order(polys)) == _host_order(mb, bx)
+    ctx = mb.ops.default_context()
+    rows = np.zeros((n, 9), np.float32)
+    rows[:, :8] = np.asarray(polys, np.float32).reshape(n, 8)
+    rows[:, 8] = np.arange(n)
+    d_rows = torch.from_numpy(rows).cuda()
+    d_cnt = torch.tensor([n], dtype=torch.int32, device="cuda")
+    d_ord = torch.full((n,), -1, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros_like(d_rows)
+    d_flags = torch.zeros((1,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    mb._cabi.check(ctx.lib.ms_reading_order(ctx.handle, d_rows.data_ptr(), d_cnt.data_ptr(), 1, n, d_ord.data_ptr(),
+                                            d_out.data_ptr(), d_flags.data_ptr(), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert int(d_flags.cpu()[0]) == MS_FLAG_ORDER_OVERFLOW
+    np.testing.assert_array_equal(d_ord.cpu().numpy(), np.arange(n))   # detection order, every row intact
+    np.testing.assert_array_equal(d_out.cpu().numpy(), rows)
+    with pytest.raises(mb.CABIError):
+        mb.batch._raise_for_flags(d_flags.cpu().numpy())
+    mb.batch._raise_for_flags(d_flags.cpu().numpy(), allow_order_overflow=True)
+
+
+def test_reading_order_large_kernel_on_every_golden(golden_dir):
+    """MS_B200_RO_FORCE_LARGE=1 (read when a context is created) sends every page through the global-memory kernel:
+    the reference's 30 golden cases, detector output with fractional coordinates, duplicated boxes (the dict / first-match
+    quirks), boxes of zero height (avg_h <= 0: every box its own line) and a batch of pages of different sizes."""
+    import ctypes as C
+
+    import torch
+
+    import manuscript_b200 as mb
+
+    os.environ["MS_B200_RO_FORCE_LARGE"] = "1"
+    try:
+        ctx = mb._cabi.Context(0)
+    finally:
+        del os.environ["MS_B200_RO_FORCE_LARGE"]
+    g = np.load(os.path.join(golden_dir, "reading_order.npz"))
+    for i in range(int(g["n_cases"])):
+        boxes = g[f"boxes_{i}"]
+        got = mb.word_reading_order(_boxes_to_polys(boxes), ctx=ctx)
+        np.testing.assert_array_equal(boxes[got].reshape(-1, 4), g[f"sorted_res_{i}"], err_msg=f"case {i}")
+        assert list(got) == _host_order(mb, boxes), f"case {i}"
+    rng = np.random.default_rng(11)
+    cases = []
+    for n, side in ((1, 50), (2, 50), (700, 900), (2500, 2000), (5000, 3000)):
+        x0, y0 = rng.integers(0, side, n), rng.integers(0, side, n)
+        cases.append(np.stack([x0, y0, x0 + rng.integers(1, 90, n), y0 + rng.integers(1, 40, n)], axis=1))
+    dup = cases[2].copy()
+    dup[100:200] = dup[300:400]          # exact duplicates
+    dup[400:450, 2:] = dup[500:550, 2:]  # boxes that share a corner with another one
+    dup[:, 2] = np.maximum(dup[:, 2], dup[:, 0] + 1)  # (the Pipeline's integer boxes are min / max hulls: x0 <= x1)
+    dup[:, 3] = np.maximum(dup[:, 3], dup[:, 1] + 1)
+    cases.append(dup)
+    flat = cases[2].copy()
+    flat[:, 3] = flat[:, 1]              # zero height: avg_h == 0
+    cases.append(flat)
+    page_wide = cases[2].copy()
+    page_wide[5] = (0, 0, 900, 900)      # one box over more than 64 grid cells: all-pairs search
+    cases.append(page_wide)
+    for ci, bx in enumerate(cases):
+        assert list(mb.word_reading_order(_boxes_to_polys(bx), ctx=ctx)) == _host_order(mb, bx), f"random case {ci}"
+    # a batch of pages (more pages than scratch slots) through the device entry point
+    P, cap = 11, 3000
+    rows = np.zeros((P, cap, 9), np.float32)
+    cnts = np.zeros(P, np.int32)
+    per_page = []
+    for pg in range(P):
+        n = int(rng.integers(0, 2500)) if pg != 4 else 0
+        x0, y0 = rng.integers(0, 1500, n), rng.integers(0, 1500, n)
+        bx = np.stack([x0, y0, x0 + rng.integers(1, 90, n), y0 + rng.integers(1, 40, n)], axis=1).reshape(n, 4)
+        per_page.append(bx)
+        cnts[pg] = n
+        if n:
+            rows[pg, :n, :8] = np.asarray(_boxes_to_polys(bx), np.float32).reshape(n, 8)
+            rows[pg, :n, 8] = np.arange(n)
+    d_rows, d_cnt = torch.from_numpy(rows).cuda(), torch.from_numpy(cnts).cuda()
+    d_ord = torch.full((P, cap), -1, dtype=torch.int32, device="cuda")
+    d_out = torch.zeros_like(d_rows)
+    d_flags = torch.zeros((P,), dtype=torch.int32, device="cuda")
+    torch.cuda.synchronize()
+    mb._cabi.check(ctx.lib.ms_reading_order(ctx.handle, d_rows.data_ptr(), d_cnt.data_ptr(), P, cap, d_ord.data_ptr(),
+                                            d_out.data_ptr(), d_flags.data_ptr(), C.c_void_p(0)))
+    torch.cuda.synchronize()
+    assert not d_flags.cpu().numpy().any()
+    for pg in range(P):
+        want = _host_order(mb, per_page[pg])
+        assert d_ord[pg, : cnts[pg]].cpu().tolist() == want, f"page {pg}"
+        np.testing.assert_array_equal(d_out[pg, : cnts[pg]].cpu().numpy(), rows[pg, want] if len(want) else rows[pg, :0])
+    ctx.close()
 
 
 # ---- BASELINE configs[0]: the plumbing run on the reference's example image, random-init reference network -----------------

@@ -167,6 +167,11 @@ MS_API int ms_reading_order_host(ms_ctx *ctx, const float *polys8, int64_t n, in
 MS_API int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const int32_t *rects,
                             int64_t n, int out_h, int out_w, float *batch_f32, uint8_t *canvas_u8);
 
+/* DIAGNOSTIC (tests, bench): how the quads of this context's LAST ms_quad_crop_resize_pad* call were served --
+ * counts[0] quads taken by the staged (TMA window) kernel, counts[1] quads served by the generic kernel (not
+ * stageable, or handed back by the staged kernel).  Waits for the call's stream work. */
+MS_API int ms_quad_crop_last_counts(ms_ctx *ctx, int32_t *counts);
+
 /* ms_quad_crop_resize_pad for one page with HOST buffers: quads (n,8) f32, sizes_out (n,2) int32 or NULL. */
 MS_API int ms_quad_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quads,
                                  int64_t n, int min_text_size, int border_mode, int border_value, int out_h,

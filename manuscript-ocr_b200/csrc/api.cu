@@ -98,6 +98,7 @@ extern "C" int ms_create(int device, ms_ctx **out)
     c->edge_factor = 16;
     c->graphs_enabled = getenv("MS_B200_NO_GRAPHS") ? 0 : 1;
     c->ro_force_large = getenv("MS_B200_RO_FORCE_LARGE") ? 1 : 0;
+    c->quad_no_stage = getenv("MS_B200_QUAD_NO_STAGE") ? 1 : 0;
     int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     for (int i = 0; i < 2 && rc == MS_OK; i++)
@@ -230,7 +231,11 @@ static int grow(ms_ctx *ctx, char **buf, size_t *have, size_t want, const char *
     return MS_OK;
 }
 
-int ms_arena_reserve(ms_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->arena, &ctx->arena_bytes, bytes, "arena"); }
+int ms_arena_reserve(ms_ctx *ctx, size_t bytes)
+{
+    if (bytes > ctx->arena_bytes) ctx->quad_cnt = nullptr;  // the counters of the last rotated-crop call go with the old arena
+    return grow(ctx, &ctx->arena, &ctx->arena_bytes, bytes, "arena");
+}
 int ms_stage_reserve(ms_ctx *ctx, size_t bytes) { return grow(ctx, &ctx->stage, &ctx->stage_bytes, bytes, "stage"); }
 
 static inline size_t al256(size_t b) { return (b + 255) & ~size_t(255); }
@@ -1231,6 +1236,21 @@ extern "C" int ms_quad_crop_resize_pad(ms_ctx *ctx, const uint8_t *pages, int n_
     ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
     return msk_quad_crop(ctx, pages, n_pages, img_h, img_w, quads, quad_stride, page_of, n, min_text_size, border_mode,
                          border_value, out_h, out_w, batch_f32, canvas_u8, sizes_out, bump, (cudaStream_t)stream);
+}
+
+extern "C" int ms_quad_crop_last_counts(ms_ctx *ctx, int32_t *counts)
+{
+    MS_CTX(ctx);
+    if (!counts || !ctx->quad_cnt) {
+        ms_set_error("ms_quad_crop_last_counts: no rotated-crop call on this context yet");
+        return MS_ERR_INVALID;
+    }
+    int32_t *h = reinterpret_cast<int32_t *>(ctx->pinned);
+    MS_CUDA(cudaMemcpyAsync(h, ctx->quad_cnt, 4 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->quad_stream));
+    MS_CUDA(cudaStreamSynchronize(ctx->quad_stream));
+    counts[0] = h[0];
+    counts[1] = h[2];
+    return MS_OK;
 }
 
 extern "C" int ms_quad_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const float *quads,

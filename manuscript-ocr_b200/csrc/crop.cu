@@ -61,9 +61,7 @@ constexpr int kCopyPadChannels = MS_COPY_PAD_CHANNELS;
 #define MS_PAD_LAG 0
 #endif
 constexpr int kPadLag = MS_PAD_LAG;  // crops between building a crop's tables and writing its padding  // float32 padding channels written by the copy warp
-#ifndef MS_CROP_WAIT_NS
-#define MS_CROP_WAIT_NS 100u
-#endif  // work-list buckets per page: (row band, x cell)
+  // work-list buckets per page: (row band, x cell)
 
 // Pages are either one (n_pages, img_h, img_w, 3) tensor, or -- page_ptrs != NULL -- separate images of their own
 // sizes: page_ptrs[p] -> (page_hw[2p], page_hw[2p+1], 3) bytes.
@@ -115,44 +113,6 @@ __device__ __forceinline__ void make_plan(const int32_t *cr, int n_pages, int im
     p.fast = p.staged && p.w < 65536 && p.h < 65536 &&
              ((p.interp == 3 && p.scale_x < 2.999 && p.scale_y < 2.999) || (p.interp == 2 && p.isx == 2 && p.isy == 2));
 }
-
-// ---- mbarrier + TMA bulk copy (sm_90+ PTX; SASS: SYNCS / UBLKCP) ----------------------------------------------
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
-{
-    // A failed try sleeps before the next one: a waiting warp that retries every few tens of cycles takes issue slots
-    // from the warps that do the arithmetic (r2c capture: a quarter of all executed instructions were retries).
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "WAIT_%=:\n"
-        "nanosleep.u32 %2;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@!p bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity), "r"(MS_CROP_WAIT_NS)
-        : "memory");
-}
-__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     smem_u32(dst_smem)),
-                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
-                 : "memory");
-}
-
 
 // plans for all crops (thread per crop): the float64 sizing arithmetic of transforms.py:91-98 runs here, off the
 // critical path of the persistent resampling kernel.  Fast crops are also counted into their work-list bucket
@@ -293,12 +253,6 @@ __global__ void __launch_bounds__(256) crop_bucket_scatter_kernel(const Plan *__
         }
     }
 }
-
-__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
-{
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-
 
 // Warp-specialised persistent kernel for the crops with Plan::fast.  Two producer warps run ahead of the consumers:
 // warp 0 (copy warp) takes the next crop of the work list (a global ticket counter: a CTA that drew narrow words simply

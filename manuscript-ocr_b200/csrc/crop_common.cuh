@@ -21,6 +21,50 @@ __device__ __forceinline__ void ms_store(T *p, const T &v)
 #endif
 }
 
+#ifndef MS_CROP_WAIT_NS
+#define MS_CROP_WAIT_NS 100u
+#endif
+// ---- mbarrier + TMA bulk copy (sm_90+ PTX; SASS: SYNCS / UBLKCP) ----------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, int count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    // A failed try sleeps before the next one: a waiting warp that retries every few tens of cycles takes issue slots
+    // from the warps that do the arithmetic (r2c capture: a quarter of all executed instructions were retries).
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "WAIT_%=:\n"
+        "nanosleep.u32 %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity), "r"(MS_CROP_WAIT_NS)
+        : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 struct Plan {
     int page, x1, y1, w, h;
     int nw, nh, y0;
@@ -537,12 +581,16 @@ __device__ __forceinline__ void area2x2_pixels(const unsigned char *smem, uint32
 template <bool kWriteF32, bool kWriteU8, int kCT, int kTaps, bool kAligned = false>
 __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t stage_off, uint32_t pitch, uint32_t a0,
                                              uint32_t sstep, const uint32_t *tab, int tab_n, int ih, int iw, int nw,
-                                             int nh, int y0, float *dstf, uint8_t *dstu, int ct, int G_in = 0)
+                                             int nh, int y0, float *dstf, uint8_t *dstu, int ct, int G_in = 0,
+                                             int dy_lo = 0, int dy_hi = -1)
 {
+    // [dy_lo, dy_hi): the destination rows to produce (default: all nh of them); the staged rows are addressed by
+    // their absolute source row either way
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
     const int G = G_in > 0 ? G_in : strip_height<kCT>(nw, nh);
-    const int nitems = ((nh + G - 1) / G) * nw;
+    if (dy_hi < 0) dy_hi = nh;
+    const int nitems = ((dy_hi - dy_lo + G - 1) / G) * nw;
     const uint32_t magic = 0xFFFFFFFFu / (uint32_t)nw + 1u;  // t / nw for t < 2^32 / nw
     const float *tw = reinterpret_cast<const float *>(tab);
     bool bad = false;
@@ -554,9 +602,9 @@ __device__ __forceinline__ bool area4_strips(const unsigned char *smem, uint32_t
         const uint32_t xoff = stage_off + (px & 0xffffu) * 3u;
         int last_r = -1;
         float b0 = 0.f, b1 = 0.f, b2 = 0.f;
-        const int dy_end = min(nh, grp * G + G);
-        float *orow = kWriteF32 ? dstf + (size_t)(y0 + grp * G) * iw + dx : nullptr;  // walks down the strip's rows
-        for (int dy = grp * G; dy < dy_end; dy++) {
+        const int dy_first = dy_lo + grp * G, dy_end = min(dy_hi, dy_first + G);
+        float *orow = kWriteF32 ? dstf + (size_t)(y0 + dy_first) * iw + dx : nullptr;  // walks down the strip's rows
+        for (int dy = dy_first; dy < dy_end; dy++) {
             const uint32_t *yrec = tab + area_tab_ybase(iw) + 8 * dy;
             const uint32_t py = yrec[0];
             bad = bad || (py >> 16) > 4u;

@@ -52,6 +52,10 @@ struct ms_ctx {
     int graphs_enabled;           // 0 with MS_B200_NO_GRAPHS=1 in the environment
     int graph_clock;
     ms_graph_entry graphs[MS_GRAPH_SLOTS];
+    int smem_attr_quad_staged[3]; // ... and to the staged quad-crop kernel f32 / u8 / both
+    const int32_t *quad_cnt;      // device counters of the last rotated-crop call (ms_quad_crop_last_counts)
+    cudaStream_t quad_stream;
+    int quad_no_stage;            // MS_B200_QUAD_NO_STAGE=1: rotated crops by the generic kernel only (A/B runs, tests)
     int ro_force_large;           // MS_B200_RO_FORCE_LARGE=1: every page takes the large-page reading-order kernel (tests)
     int busy;                     // 1 while a thread is inside an entry point (atomic test-and-set): a context owns ONE
                                   // scratch arena, so a second thread entering gets MS_ERR_INVALID instead of corrupting it

@@ -291,7 +291,7 @@ def test_quad_crop_device_entry(mb):
                                              d_po.data_ptr(), n, 5, 1, 0, 32, 128, batch.data_ptr(), None,
                                              sizes.data_ptr(), C.c_void_p(stream.cuda_stream))
         assert rc == 0, mb._cabi.last_error()
-        assert ctx.launches - before == 2
+        assert ctx.launches - before == 3  # plan, fallback list, generic kernel (1500-byte rows are not 16-byte aligned: no staged kernel)
     stream.synchronize()
     got, sz = batch.cpu().numpy(), sizes.cpu().numpy()
     for i in range(n):

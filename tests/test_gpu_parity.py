@@ -411,6 +411,71 @@ def test_quad_crop_vs_oracle(ops, out_hw):
     np.testing.assert_array_equal(ops.warp_quad(page, big, "replicate"), cpu.warp_quad(page, big, "replicate"))
 
 
+def _quad_counts(ctx):
+    import ctypes as C
+
+    c = (C.c_int32 * 2)()
+    from manuscript_b200 import _cabi
+
+    _cabi.check(ctx.lib.ms_quad_crop_last_counts(ctx.handle, c))
+    return int(c[0]), int(c[1])
+
+
+def test_quad_crop_staged_kernel(ops):
+    """The staged rotated-crop kernel (TMA window + per-warp bands + dp4a blend) takes a quad when its window lies
+    inside a page whose rows are 16-byte aligned.  Checked (a) against the oracle chain (cv2-pinned) quad by quad, float32
+    batch + uint8 canvas, (b) against the generic kernel (MS_B200_QUAD_NO_STAGE=1) on thousands of quads -- turned word
+    boxes, strong perspective, tall / narrow / tiny quads, quads over the page border (generic kernel), non-convex
+    quads (handed back) -- bit for bit, both output variants."""
+    import manuscript_b200 as mb
+
+    rng = np.random.default_rng(123)
+    H, W = 416, 704  # 704 * 3 bytes per row: a multiple of 16
+    page = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    quads = np.concatenate([
+        _random_quads(rng, 120, H, W, 200, 60),   # word-sized, turned by up to +-0.7 rad
+        _random_quads(rng, 30, H, W, 30, 12),     # small
+        _random_quads(rng, 10, H, W, 380, 90),    # wide
+        np.array([[100, 100, 220, 90, 200, 160, 90, 150],     # perspective
+                  [300, 200, 420, 200, 420, 240, 300, 240],   # axis aligned
+                  [300, 100, 400, 100, 320, 130, 300, 160],   # concave: taps leave the hull -> handed back
+                  [50, 300, 150, 300.5, 150, 340, 50, 340.5]], np.float32),
+    ])
+    ctx = mb.ops.default_context()
+    batch, canvas, valid = ops.quad_crop_resize_pad(page, quads, 32, 128, 5, "constant", 7, want_canvas=True)
+    n_staged, n_generic = _quad_counts(ctx)
+    assert n_staged >= 25 and n_generic >= 20, (n_staged, n_generic)
+    for i, q in enumerate(quads):
+        want_canvas, want_chw = cpu.quad_crop_resize_pad(page, q, 32, 128, 5, "constant", 7)
+        if want_canvas is None:
+            assert not valid[i] and (canvas[i] == 255).all()
+            continue
+        np.testing.assert_array_equal(canvas[i], want_canvas, err_msg=f"quad {i}")
+        np.testing.assert_array_equal(batch[i], want_chw, err_msg=f"quad {i}")
+    only_f32, _ = ops.quad_crop_resize_pad(page, quads, 32, 128, 5, "constant", 7)
+    np.testing.assert_array_equal(only_f32, batch)
+    # a larger population against the generic kernel
+    os.environ["MS_B200_QUAD_NO_STAGE"] = "1"
+    try:
+        gctx = mb._cabi.Context(0)
+    finally:
+        del os.environ["MS_B200_QUAD_NO_STAGE"]
+    H2, W2 = 1024, 1024
+    page2 = synthdata.make_page_image(5, H2)
+    many = np.concatenate([_random_quads(rng, 3000, H2, W2, 160, 70), _random_quads(rng, 500, H2, W2, 60, 25)])
+    many[::7] += rng.uniform(-6, 6, many[::7].shape).astype(np.float32)  # stronger perspective
+    for border in ("constant", "replicate"):
+        a_f, a_u, a_v = ops.quad_crop_resize_pad(page2, many, 32, 128, 5, border, 0, want_canvas=True)
+        ns, ng = _quad_counts(ctx)
+        b_f, b_u, b_v = ops.quad_crop_resize_pad(page2, many, 32, 128, 5, border, 0, want_canvas=True, ctx=gctx)
+        assert _quad_counts(gctx)[0] == 0
+        assert ns > 1000, (ns, ng)
+        np.testing.assert_array_equal(a_v, b_v)
+        np.testing.assert_array_equal(a_u, b_u)
+        np.testing.assert_array_equal(a_f, b_f)
+    gctx.close()
+
+
 # ---- the NMS shortcut predicates themselves (test-only C-ABI entry ms_test_iou_proved_host) ---------------------
 def _rot(q, th, ctr=None):
     ctr = q.mean(1, keepdims=True) if ctr is None else ctr

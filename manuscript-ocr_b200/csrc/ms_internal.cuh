@@ -41,7 +41,7 @@ struct ms_ctx {
     // ms_stage_timing: ring of per-batch event sets
     int edge_factor;              // NMS neighbour-pair capacity per candidate (grown by the host entry points)
     int smem_attr[8];             // largest dynamic shared-memory size already granted to: crop f32 / u8 / both, reading
-                                  // order, quad crop f32 / u8 / both
+                                  // order, quad crop f32 / u8 / both, large-page reading order
     cudaStream_t copy_stream;     // H2D stream of the pipelined host entry point
     cudaEvent_t chunk_ev[2];
     int timing;

@@ -775,6 +775,8 @@ constexpr int kRlMaxLevels = 4095;  // dependency levels bucketed in shared memo
 constexpr int kRlSlots = 8;
 constexpr int kRlPairFactor = 16;
 constexpr uint32_t kRlNone = 0xffffffffu;
+constexpr int kRlSmemKeys = 16384;     // sort keys held in dynamic shared memory (8 + 4 bytes each)
+constexpr int kRlSmemBytes = kRlSmemKeys * 12;
 
 __host__ __device__ inline int rl_pair_cap(int cap) { return cap * kRlPairFactor < 65536 ? 65536 : cap * kRlPairFactor; }
 __host__ __device__ inline int rl_grid_cap(int cap) { return 8 * cap + 4096; }
@@ -907,6 +909,13 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
     const int pair_cap = rl_pair_cap(cap), grid_cap = rl_grid_cap(cap);
     constexpr int NC = kRlCells * kRlCells;
 
+    // The 192 KB of dynamic shared memory serve three phases in turn: a copy of the boxes while the pairs are generated
+    // (B: every candidate test is a random box read), the pairs' levels during the relaxation and the sweeps (C: random
+    // level reads), the sort keys (D).  A page too large for one of them uses the global array for that phase.
+    extern __shared__ __align__(16) unsigned char rl_dyn[];
+    const int4 *bxs_c;
+    int4 *bxs = K <= kRlSmemBytes / 16 ? reinterpret_cast<int4 *>(rl_dyn) : box;
+    bxs_c = bxs;
     // A. integer boxes (_pipeline.py:105-109)
     for (int k = threadIdx.x; k < K; k += kRoThreads) {
         const float *q = boxes8 + (pb + k) * row_stride;
@@ -924,6 +933,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
         const int4 b = make_int4(xmin, ymin, xmax, ymax);
         box[k] = b;
         obox[k] = b;
+        if (bxs != box) bxs[k] = b;
     }
     if (threadIdx.x == 0) {
         S.g[0] = S.g[1] = INT_MAX;
@@ -939,7 +949,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
     {
         int mnx = INT_MAX, mny = INT_MAX, mxx = INT_MIN, mxy = INT_MIN;
         for (int i = threadIdx.x; i < K; i += kRoThreads) {
-            const int4 b = box[i];
+            const int4 b = bxs_c[i];
             mnx = min(mnx, min(b.x, b.z));
             mxx = max(mxx, max(b.x, b.z));
             mny = min(mny, min(b.y, b.w));
@@ -969,7 +979,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
     {
         int mine = 0, big = 0;
         for (int i = threadIdx.x; i < K; i += kRoThreads) {
-            const int4 b = box[i];
+            const int4 b = bxs_c[i];
             const int cx0 = cell_x(min(b.x, b.z)), cx1 = cell_x(max(b.x, b.z));
             const int cy0 = cell_y(min(b.y, b.w)), cy1 = cell_y(max(b.y, b.w));
             const int nc = (cx1 - cx0 + 1) * (cy1 - cy0 + 1);
@@ -997,7 +1007,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
         for (int t = threadIdx.x; t < NC; t += kRoThreads) ccnt[t] = 0;
         __syncthreads();
         for (int i = threadIdx.x; i < K; i += kRoThreads) {
-            const int4 b = box[i];
+            const int4 b = bxs_c[i];
             const int cx0 = cell_x(min(b.x, b.z)), cx1 = cell_x(max(b.x, b.z));
             const int cy0 = cell_y(min(b.y, b.w)), cy1 = cell_y(max(b.y, b.w));
             for (int cy = cy0; cy <= cy1; cy++)
@@ -1009,7 +1019,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
         __syncthreads();
     }
     auto row_pass = [&](int i, int off, bool write) -> int {
-        const int4 bi = box[i];
+        const int4 bi = bxs_c[i];
         int cnt = 0;
         if (grid) {
             const int cx0 = cell_x(min(bi.x, bi.z)), cx1 = cell_x(max(bi.x, bi.z));
@@ -1021,7 +1031,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
                     for (int e = cstart[c]; e < e1; e++) {
                         const int j = (int)centry[e];
                         if (j <= i) continue;
-                        const int4 bj = box[j];
+                        const int4 bj = bxs_c[j];
                         if (!ro_intersect(bi, bj)) continue;
                         if (cell_y(max(bi.y, bj.y)) * kRlCells + cell_x(max(bi.x, bj.x)) != c) continue;  // another cell's
                         if (write && off + cnt < pair_cap) pairs[off + cnt] = make_uint2((uint32_t)i, (uint32_t)j);
@@ -1030,7 +1040,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
                 }
         } else {
             for (int j = i + 1; j < K; j++) {
-                if (!ro_intersect(bi, box[j])) continue;
+                if (!ro_intersect(bi, bxs_c[j])) continue;
                 if (write && off + cnt < pair_cap) pairs[off + cnt] = make_uint2((uint32_t)i, (uint32_t)j);
                 cnt++;
             }
@@ -1089,6 +1099,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
     __syncthreads();
 
     // C. dependency levels of the pairs (see the shared-memory kernel), then the shrink sweeps (utils.py:521-545)
+    uint16_t *lvp = np <= kRlSmemBytes / 2 ? reinterpret_cast<uint16_t *>(rl_dyn) : lv;  // (the box copy is dead)
     {
         for (int k = threadIdx.x; k <= K; k += kRoThreads) bcnt[k] = 0;
         __syncthreads();
@@ -1119,28 +1130,56 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
             for (int a = s0; a < e0; a++) prevJ[T[a]] = a > s0 ? T[a - 1] : kRlNone;
             lastJ[j] = e0 > s0 ? T[e0 - 1] : kRlNone;
         }
-        for (int p = threadIdx.x; p < np; p += kRoThreads) lv[p] = 1;
+        __syncthreads();  // the buckets in T have been read: T now holds every pair's predecessor on its first box
+        uint32_t *prevI = T;
+        for (int p = threadIdx.x; p < np; p += kRoThreads) {
+            const int i = (int)pairs[p].x;
+            prevI[p] = p > row_start[i] ? (uint32_t)(p - 1) : lastJ[i];
+            lvp[p] = 1;
+        }
         __syncthreads();
+        // a pass walks the pairs four per thread with all index loads, then all level loads, in flight together: the
+        // arrays live in L2 and a pass is bound by the latency of those dependent loads
         for (int pass = 0; pass < kRlMaxLevels + 2; pass++) {
             int changed = 0;
-            for (int p = threadIdx.x; p < np; p += kRoThreads) {
-                const int i = (int)pairs[p].x;
-                const uint32_t pi = p > row_start[i] ? (uint32_t)(p - 1) : lastJ[i];
-                const uint32_t pj = prevJ[p];
-                const int a = pi == kRlNone ? 0 : (int)lv[pi], b = pj == kRlNone ? 0 : (int)lv[pj];
-                const int l = 1 + max(a, b);
-                if (l > kRlMaxLevels) {
-                    S.maxl = -1;  // too deep for the level buckets: sequential sweeps below
-                } else if (l != (int)lv[p]) {
-                    lv[p] = (uint16_t)l;
-                    changed = 1;
+            for (int base = 0; base < np; base += 4 * kRoThreads) {
+                uint32_t pi[4], pj[4];
+                int cur[4], a[4], b[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int p = base + u * kRoThreads + (int)threadIdx.x;
+                    pi[u] = pj[u] = kRlNone;
+                    cur[u] = 0;
+                    if (p < np) {
+                        pi[u] = prevI[p];
+                        pj[u] = prevJ[p];
+                        cur[u] = (int)lvp[p];
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    a[u] = pi[u] == kRlNone ? 0 : (int)lvp[pi[u]];
+                    b[u] = pj[u] == kRlNone ? 0 : (int)lvp[pj[u]];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    const int p = base + u * kRoThreads + (int)threadIdx.x;
+                    if (p < np) {
+                        const int l = 1 + max(a[u], b[u]);
+                        if (l > kRlMaxLevels) {
+                            S.maxl = -1;  // too deep for the level buckets: sequential sweeps below
+                        } else if (l != cur[u]) {
+                            lvp[p] = (uint16_t)l;
+                            changed = 1;
+                        }
+                    }
                 }
             }
             if (!__syncthreads_or(changed) || S.maxl < 0) break;
         }
         if (S.maxl >= 0) {
             int m = 0;
-            for (int p = threadIdx.x; p < np; p += kRoThreads) m = max(m, (int)lv[p]);
+            for (int p = threadIdx.x; p < np; p += kRoThreads) m = max(m, (int)lvp[p]);
             m = __reduce_max_sync(0xffffffffu, m);
             if ((threadIdx.x & 31) == 0) atomicMax(&S.maxl, m);
         }
@@ -1152,12 +1191,12 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
         uint32_t *byl = T;                // so is the transposed list
         for (int t = threadIdx.x; t <= kRlMaxLevels + 1; t += kRoThreads) lstart[t] = 0;
         __syncthreads();
-        for (int p = threadIdx.x; p < np; p += kRoThreads) atomicAdd(&lstart[lv[p]], 1);
+        for (int p = threadIdx.x; p < np; p += kRoThreads) atomicAdd(&lstart[lvp[p]], 1);
         __syncthreads();
         rl_scan_inplace(lstart, kRlMaxLevels + 2, S.warp);
         for (int t = threadIdx.x; t <= kRlMaxLevels + 1; t += kRoThreads) lfill[t] = lstart[t];
         __syncthreads();
-        for (int p = threadIdx.x; p < np; p += kRoThreads) byl[atomicAdd(&lfill[lv[p]], 1)] = (uint32_t)p;
+        for (int p = threadIdx.x; p < np; p += kRoThreads) byl[atomicAdd(&lfill[lvp[p]], 1)] = (uint32_t)p;
         __syncthreads();
         for (int sweep = 0; sweep < 50; sweep++) {
             if (threadIdx.x == 0) S.changed = 0;
@@ -1166,7 +1205,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
                 const int e0 = lfill[l];  // == start of level l + 1
                 for (int t = lstart[l] + threadIdx.x; t < e0; t += kRoThreads) {
                     const int p = (int)byl[t];
-                    if (lv[p] == 0) continue;
+                    if (lvp[p] == 0) continue;
                     const uint2 pr = pairs[p];
                     int4 a = box[pr.x], c = box[pr.y];
                     if (ro_intersect(a, c)) {
@@ -1178,7 +1217,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
                         box[pr.y] = c;
                         S.changed = 1;
                     } else {
-                        lv[p] = 0;
+                        lvp[p] = 0;
                     }
                 }
                 __syncthreads();
@@ -1233,16 +1272,19 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
 
     // D2. stable order by centre y (utils.py:584): key = y0 + y1, ties by index (20 bits)
     const int n2 = rl_pow2(K);
+    // the two sorts run in shared memory when the page has at most 16 384 boxes (192 KB of keys), else in the slot
+    uint64_t *K1 = n2 <= kRlSmemKeys ? reinterpret_cast<uint64_t *>(rl_dyn) : keys;
+    uint32_t *K2 = n2 <= kRlSmemKeys ? reinterpret_cast<uint32_t *>(rl_dyn + (size_t)kRlSmemKeys * 8) : keys2;
     for (int i = threadIdx.x; i < n2; i += kRoThreads) {
         uint64_t key = ~0ull;
         if (i < K) {
             const long long s2 = (long long)box[i].y + (long long)box[i].w;
             key = ((uint64_t)(s2 + (1ll << 33)) << 20) | (uint64_t)i;
         }
-        keys[i] = key;
+        K1[i] = key;
     }
     __syncthreads();
-    ro_bitonic(keys, n2);
+    ro_bitonic(K1, n2);
 
     // D3. line assignment by warp 0 (utils.py:584-603; the argument why only the newest line can match, and the exact
     //     integer test, are in the shared-memory kernel)
@@ -1267,7 +1309,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
         int cur_cnt = 0;
         if (!xgap_ok) {
             for (int r = lane; r < K; r += 32) {
-                const int k = (int)(keys[r] & 0xfffffu);
+                const int k = (int)(K1[r] & 0xfffffu);
                 line_sum[r] = (long long)box[k].y + (long long)box[k].w;
                 line_cnt[r] = 1;
                 line_of[k] = (uint32_t)r;
@@ -1280,7 +1322,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
             int k = 0;
             long long s2 = 0;
             if (lane < n) {
-                k = (int)(keys[r + lane] & 0xfffffu);
+                k = (int)(K1[r + lane] & 0xfffffu);
                 const int4 b = box[k];
                 s2 = (long long)b.y + (long long)b.w;
             }
@@ -1353,12 +1395,12 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
             k1 = ((uint64_t)line_rank[line_of[i]] << 32) | (uint64_t)(uint32_t)((long long)box[i].x + (1ll << 31));
             k2 = seq_of[i];
         }
-        keys[i] = k1;
-        keys2[i] = k2;
+        K1[i] = k1;
+        K2[i] = k2;
     }
     for (int k = threadIdx.x; k < K; k += kRoThreads) inv_seq[seq_of[k]] = k;
     __syncthreads();
-    rl_bitonic2(keys, keys2, n2);
+    rl_bitonic2(K1, K2, n2);
 
     // E. utils.py:639 (the LAST box with equal compressed coordinates wins) and _pipeline.py:113-123 (the FIRST word
     //    with the same integer box), behind a hash-table check that two boxes coincide at all
@@ -1387,7 +1429,7 @@ __device__ bool rl_order_page(RlShared &S, const float *__restrict__ boxes8, int
     }
     const bool any_dup = S.dup != 0;
     for (int r = threadIdx.x; r < K; r += kRoThreads) {
-        const int k = inv_seq[keys2[r]];
+        const int k = inv_seq[K2[r]];
         int first = k;
         if (any_dup) {
             const int4 ck = box[k];
@@ -1495,7 +1537,12 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
                                                            slots ? ctx->ro_force_large : 0);
     MS_LAUNCH_CHECK(ctx);
     if (slots) {  // pages the first kernel could not hold (none, usually: the CTAs find no ticket and leave)
-        reading_order_large_kernel<<<slots, kRoThreads, 0, st>>>(boxes8, row_stride, counts, cap_per_page, n_pages, order,
+        const int smem_l = kRlSmemKeys * 12;
+        if (smem_l > ctx->smem_attr[7]) {
+            MS_CUDA(cudaFuncSetAttribute(reading_order_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));
+            ctx->smem_attr[7] = smem_l;
+        }
+        reading_order_large_kernel<<<slots, kRoThreads, smem_l, st>>>(boxes8, row_stride, counts, cap_per_page, n_pages, order,
                                                                 reordered, flags, need_large, need_large + n_pages,
                                                                 slot_mem, slot_bytes);
         MS_LAUNCH_CHECK(ctx);

@@ -338,7 +338,8 @@ def run_b200(a):
     # parity of THIS step's results with the oracle, before anything is timed
     parity = None
     if rank == 0 and not a.no_parity:
-        parity = parity_check(a, score_np, geo_np, imgs_np, res)
+        # the first and the last page: one from each of the two concurrent halves of the batch's front stages
+        parity = parity_check(a, score_np, geo_np, imgs_np, res, pages=(0, P - 1) if P > 1 else (0,))
 
     # per-page work counts for the algorithmic-byte model (outside the timed region)
     counts = res.box_counts.cpu().numpy().astype(np.int64)

@@ -98,9 +98,13 @@ extern "C" int ms_create(int device, ms_ctx **out)
     c->edge_factor = 16;
     c->graphs_enabled = getenv("MS_B200_NO_GRAPHS") ? 0 : 1;
     c->ro_force_large = getenv("MS_B200_RO_FORCE_LARGE") ? 1 : 0;
+    c->split_front = getenv("MS_B200_NO_SPLIT") ? 0 : 1;
     c->quad_no_stage = getenv("MS_B200_QUAD_NO_STAGE") ? 1 : 0;
     int rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking), "cudaStreamCreate");
     if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    if (rc == MS_OK) rc = ms_check_cuda(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking), "cudaStreamCreate");
+    for (int i = 0; i < 2 && rc == MS_OK; i++)
+        rc = ms_check_cuda(cudaEventCreateWithFlags(&c->split_ev[i], cudaEventDisableTiming), "cudaEventCreate");
     for (int i = 0; i < 2 && rc == MS_OK; i++)
         rc = ms_check_cuda(cudaEventCreateWithFlags(&c->chunk_ev[i], cudaEventDisableTiming), "cudaEventCreate");
     if (rc == MS_OK) {
@@ -123,6 +127,12 @@ extern "C" void ms_destroy(ms_ctx *ctx)
         cudaStreamSynchronize(ctx->own_stream);
         cudaStreamDestroy(ctx->own_stream);
     }
+    if (ctx->aux_stream) {
+        cudaStreamSynchronize(ctx->aux_stream);
+        cudaStreamDestroy(ctx->aux_stream);
+    }
+    for (int i = 0; i < 2; i++)
+        if (ctx->split_ev[i]) cudaEventDestroy(ctx->split_ev[i]);
     if (ctx->copy_stream) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
@@ -495,8 +505,9 @@ static int cand_cap(int map_h, int map_w, int q)
     return (int)(c > 0x7fffffffLL ? 0x7fffffff : c);
 }
 
-static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int64_t crops_cap, int ef,
-                                 int cap_boxes, int total_pages)
+// Scratch of the front stages (decode -> LANMS -> box filters -> reading order) for n_pages pages: the candidate / NMS
+// buffers that live through all of them + the largest stage scratch.
+static size_t front_scratch(int n_pages, int map_h, int map_w, int q, int cap_c, int ef, int cap_boxes)
 {
     size_t fixed = 2 * al256((size_t)n_pages * cap_c * 9 * sizeof(float)) + 2 * al256((size_t)n_pages * sizeof(int32_t));
     size_t stage = msk_decode_scratch(n_pages, map_h, map_w, q);
@@ -504,54 +515,46 @@ static size_t page_batch_scratch(int n_pages, int map_h, int map_w, int q, int c
     if (s2 > stage) stage = s2;
     s2 = msk_east_boxes_scratch(n_pages, cap_c);
     if (s2 > stage) stage = s2;
-    s2 = word_rects_scratch_full(n_pages, cap_c);
-    if (s2 > stage) stage = s2;
     s2 = msk_reading_order_scratch(n_pages, cap_boxes);
-    if (s2 > stage) stage = s2;
-    s2 = msk_crop_scratch(crops_cap, total_pages);
     if (s2 > stage) stage = s2;
     // reading order keeps the unsorted boxes and the order next to the candidates for the rest of the call
     fixed += al256((size_t)n_pages * cap_boxes * 36) + al256((size_t)n_pages * cap_boxes * 4) + 512;
-    return fixed + stage + 4096;
+    return al256(fixed + stage + 4096);
 }
 
-// One chunk of pages through the whole path.  `pages_all` / `total_pages` describe the page-image tensor the crop
-// rows index into; this call handles pages [page_base, page_base + n_pages) of it, whose maps start at score / geo
-// and whose boxes go to boxes_out / box_counts / flags (already offset by the caller).  append != 0 adds this
-// chunk's crops after the *n_crops rows already listed.
-static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages_all, int total_pages,
-                           int page_base, int n_pages, int map_h, int map_w, int img_h, int img_w,
-                           const ms_east_params *p, int min_text_size, int out_h, int out_w, int cap_boxes,
-                           float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
-                           int32_t *n_crops, int append, float *batch_f32, uint8_t *canvas_u8, int32_t *flags,
-                           cudaStream_t st, int geo_compact = 0, const uint8_t *const *page_ptrs = nullptr,
-                           const int32_t *page_hw = nullptr)
+// ... and of the tail (crop rectangles, crops), which runs after the front stages and may reuse their bytes
+static size_t tail_scratch(int n_pages, int cap_c, int64_t crops_cap, int total_pages)
 {
-    // page_ptrs / page_hw (device, indexed by the global page number): page images of their own sizes
-    const bool ragged = page_ptrs != nullptr && page_hw != nullptr;
-    const int32_t *hw_here = ragged ? page_hw + 2 * (size_t)page_base : nullptr;  // this chunk's pages
-    const bool want_crops = (pages_all != nullptr || ragged) && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
-    const int q = p->quantization < 1 ? 1 : p->quantization;
-    const int cap_c = cand_cap(map_h, map_w, q);
-    MS_TRY(ms_arena_reserve(ctx, page_batch_scratch(n_pages, map_h, map_w, q, cap_c, want_crops ? crops_cap : 0, ctx->edge_factor, cap_boxes, total_pages)));
-    ms_bump bump{ctx->arena, 0, ctx->arena_bytes};
+    size_t stage = word_rects_scratch_full(n_pages, cap_c);
+    const size_t s2 = msk_crop_scratch(crops_cap, total_pages);
+    if (s2 > stage) stage = s2;
+    return al256(stage + 4096);
+}
+
+// Pages below this count run their front stages as one sequence; from it on as two concurrent halves (see below).
+#define MS_SPLIT_MIN_PAGES 16
+
+// decode -> LANMS -> expand + EAST filters (-> reading order) of n_pages pages on stream st; boxes into boxes_out /
+// box_counts.  marks: record the stage-timing events (the half that runs on the caller's stream does).
+static int front_half(ms_ctx *ctx, const float *score, const float *geo, int n_pages, int map_h, int map_w, int img_h,
+                      int img_w, const ms_east_params *p, int q, int cap_c, int cap_boxes, const int32_t *hw_here,
+                      float *boxes_out, int32_t *box_counts, int32_t *flags, ms_bump bump, cudaStream_t st,
+                      int geo_compact, bool marks)
+{
     float *qa = bump.take<float>((size_t)n_pages * cap_c * 9);  // candidates
     float *qb = bump.take<float>((size_t)n_pages * cap_c * 9);  // NMS output
     int32_t *ca = bump.take<int32_t>(n_pages);
     int32_t *cb = bump.take<int32_t>(n_pages);
-    int32_t *range = bump.take<int32_t>(2);
-    if (!range) {
+    if (!cb) {
         ms_set_error("ms_page_batch: arena too small");
         return MS_ERR_CAPACITY;
     }
-    MS_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_pages * sizeof(int32_t), st));
-    MS_TRY(timing_mark(ctx, 0, st));
     MS_TRY(msk_decode(ctx, score, geo, n_pages, map_h, map_w, p->score_thresh, p->scale, q, qa, cap_c, ca, flags, bump,
                       st, geo_compact));
-    MS_TRY(timing_mark(ctx, 1, st));
+    if (marks) MS_TRY(timing_mark(ctx, 1, st));
     MS_TRY(msk_lanms(ctx, qa, ca, n_pages, cap_c, p->iou_threshold, qb, cb, flags, bump, st));
     // expand + EAST filters; boxes are scaled to the page images' size (infer.py:134-147: the original image), or target_size
-    MS_TRY(timing_mark(ctx, 2, st));
+    if (marks) MS_TRY(timing_mark(ctx, 2, st));
     if (p->sort_reading_order) {
         // filtered boxes -> scratch, then into boxes_out in reading order (the order the crops are produced in)
         float *tmp = bump.take<float>((size_t)n_pages * cap_boxes * 9);
@@ -567,14 +570,81 @@ static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, co
         MS_TRY(msk_east_boxes(ctx, qb, cb, n_pages, cap_c, p, hw_here, boxes_out, cap_boxes, box_counts, flags, bump,
                               st, img_h, img_w));
     }
+    return MS_OK;
+}
+
+// One chunk of pages through the whole path.  `pages_all` / `total_pages` describe the page-image tensor the crop
+// rows index into; this call handles pages [page_base, page_base + n_pages) of it, whose maps start at score / geo
+// and whose boxes go to boxes_out / box_counts / flags (already offset by the caller).  append != 0 adds this
+// chunk's crops after the *n_crops rows already listed.
+//
+// The front stages of a batch of MS_SPLIT_MIN_PAGES pages or more run as TWO CONCURRENT HALVES (pages are independent):
+// the first on the caller's stream, the second on the context's auxiliary stream, forked and joined with events (under
+// stream capture they become two parallel branches of the graph).  Most front kernels are bound by latency -- one CTA
+// (or one cluster) per page walking a serial recurrence, or lanes waiting on dependent loads -- and leave most of the
+// SMs' issue slots free; the other half's kernels fill them.  The crop rectangles and the crop kernel then run once
+// over all pages.  MS_B200_NO_SPLIT=1 keeps one sequence.
+static int page_batch_impl(ms_ctx *ctx, const float *score, const float *geo, const uint8_t *pages_all, int total_pages,
+                           int page_base, int n_pages, int map_h, int map_w, int img_h, int img_w,
+                           const ms_east_params *p, int min_text_size, int out_h, int out_w, int cap_boxes,
+                           float *boxes_out, int32_t *box_counts, int32_t *crops_out, int64_t crops_cap,
+                           int32_t *n_crops, int append, float *batch_f32, uint8_t *canvas_u8, int32_t *flags,
+                           cudaStream_t st, int geo_compact = 0, const uint8_t *const *page_ptrs = nullptr,
+                           const int32_t *page_hw = nullptr)
+{
+    // page_ptrs / page_hw (device, indexed by the global page number): page images of their own sizes
+    const bool ragged = page_ptrs != nullptr && page_hw != nullptr;
+    const int32_t *hw_here = ragged ? page_hw + 2 * (size_t)page_base : nullptr;  // this chunk's pages
+    const bool want_crops = (pages_all != nullptr || ragged) && crops_out != nullptr && n_crops != nullptr && crops_cap > 0;
+    const int q = p->quantization < 1 ? 1 : p->quantization;
+    const int cap_c = cand_cap(map_h, map_w, q);
+    const bool split = ctx->split_front && n_pages >= MS_SPLIT_MIN_PAGES && st != ctx->aux_stream;
+    const int nA = split ? n_pages / 2 : n_pages, nB = n_pages - nA;
+    const size_t szA = front_scratch(nA, map_h, map_w, q, cap_c, ctx->edge_factor, cap_boxes);
+    const size_t szB = split ? front_scratch(nB, map_h, map_w, q, cap_c, ctx->edge_factor, cap_boxes) : 0;
+    const size_t szT = tail_scratch(n_pages, cap_c, want_crops ? crops_cap : 0, total_pages);
+    // (one sequence: the tail reuses the front stages' scratch; two halves: A | B | tail side by side)
+    MS_TRY(ms_arena_reserve(ctx, split ? szA + szB + szT + 1024 : (szA > szT ? szA : szT) + 1024));
+    ms_bump bumpA{ctx->arena, 0, split ? szA : ctx->arena_bytes};
+    ms_bump bumpT{split ? ctx->arena + szA + szB : ctx->arena, 0, split ? ctx->arena_bytes - szA - szB : ctx->arena_bytes};
+    MS_CUDA(cudaMemsetAsync(flags, 0, (size_t)n_pages * sizeof(int32_t), st));
+    MS_TRY(timing_mark(ctx, 0, st));
+    if (split) {
+        const size_t plane = (size_t)map_h * map_w;
+        const size_t gplane = geo_compact ? (size_t)(map_h / q) * map_w : plane;
+        ms_bump bumpB{ctx->arena + szA, 0, szB};
+        MS_CUDA(cudaEventRecord(ctx->split_ev[0], st));
+        MS_CUDA(cudaStreamWaitEvent(ctx->aux_stream, ctx->split_ev[0], 0));
+        int rc = front_half(ctx, score, geo, nA, map_h, map_w, img_h, img_w, p, q, cap_c, cap_boxes, hw_here, boxes_out,
+                            box_counts, flags, bumpA, st, geo_compact, true);
+        if (rc == MS_OK)
+            rc = front_half(ctx, score + (size_t)nA * plane, geo + (size_t)nA * 8 * gplane, nB, map_h, map_w, img_h, img_w,
+                            p, q, cap_c, cap_boxes, hw_here ? hw_here + 2 * (size_t)nA : nullptr,
+                            boxes_out + (size_t)nA * cap_boxes * 9, box_counts + nA, flags + nA, bumpB, ctx->aux_stream,
+                            geo_compact, false);
+        // always join (a capture must not end with the auxiliary stream still forked)
+        const int rj = ms_check_cuda(cudaEventRecord(ctx->split_ev[1], ctx->aux_stream), "cudaEventRecord");
+        const int rw = ms_check_cuda(cudaStreamWaitEvent(st, ctx->split_ev[1], 0), "cudaStreamWaitEvent");
+        if (rc != MS_OK) return rc;
+        if (rj != MS_OK) return rj;
+        if (rw != MS_OK) return rw;
+    } else {
+        MS_TRY(front_half(ctx, score, geo, n_pages, map_h, map_w, img_h, img_w, p, q, cap_c, cap_boxes, hw_here, boxes_out,
+                          box_counts, flags, bumpA, st, geo_compact, true));
+    }
     MS_TRY(timing_mark(ctx, 3, st));
+    int32_t *range = bumpT.take<int32_t>(2);
+    if (!range) {
+        ms_set_error("ms_page_batch: arena too small");
+        return MS_ERR_CAPACITY;
+    }
     if (want_crops) {
         MS_TRY(msk_word_rects(ctx, boxes_out, box_counts, n_pages, cap_boxes, hw_here, img_h, img_w, min_text_size,
-                              crops_out, crops_cap, n_crops, page_base, append, range, bump, st));
+                              crops_out, crops_cap, n_crops, page_base, append, range, bumpT, st));
         MS_TRY(timing_mark(ctx, 4, st));
         if (batch_f32 || canvas_u8)
             MS_TRY(msk_crop(ctx, pages_all, total_pages, img_h, img_w, crops_out, n_crops, range, crops_cap, out_h,
-                            out_w, batch_f32, canvas_u8, bump, st, page_ptrs, page_hw));
+                            out_w, batch_f32, canvas_u8, bumpT, st, page_ptrs, page_hw));
     } else {
         MS_TRY(timing_mark(ctx, 4, st));
     }

@@ -44,6 +44,9 @@ struct ms_ctx {
                                   // order, quad crop f32 / u8 / both, large-page reading order
     cudaStream_t copy_stream;     // H2D stream of the pipelined host entry point
     cudaEvent_t chunk_ev[2];
+    cudaStream_t aux_stream;      // second half of a batch's front stages (page_batch_impl)
+    cudaEvent_t split_ev[2];      // fork / join of that half
+    int split_front;              // 0 with MS_B200_NO_SPLIT=1
     int timing;
     int timing_n;                 // batches recorded since the last read (<= MS_TIMING_RING)
     cudaEvent_t *timing_ev;       // MS_TIMING_RING * (MS_N_STAGES + 1) events, created lazily

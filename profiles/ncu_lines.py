@@ -1,7 +1,7 @@
 """Stall samples and executed instructions per CUDA source line of one kernel of an `ncu --set full --import-source on`
 capture (the library is built with -lineinfo):
 
-    python profiles/ncu_lines.py X.ncu-rep [top]
+    python profiles/ncu_lines.py X.ncu-rep [top] [kernel-name regex]
 """
 import collections
 import csv
@@ -13,8 +13,10 @@ import sys
 def main():
     rep = sys.argv[1]
     top = int(sys.argv[2]) if len(sys.argv) > 2 else 40
-    out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"],
-                         capture_output=True, text=True).stdout
+    cmd = ["ncu", "-i", rep, "--page", "source", "--print-source", "cuda,sass", "--csv"]
+    if len(sys.argv) > 3:
+        cmd += ["--kernel-name", "regex:" + sys.argv[3]]
+    out = subprocess.run(cmd, capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     hdr = next(r for r in rows if r and r[0] == "Line No")
     i_s, i_i = hdr.index("# Samples"), hdr.index("Instructions Executed")

@@ -414,3 +414,47 @@ def test_repeated_batches_replay_a_cuda_graph(torch_cuda):
     assert not np.array_equal(first[0], fourth[0])
     _, _, want_boxes, _ = oracle_page(score2[1], geo2[1], imgs2[1], page)
     np.testing.assert_array_equal(fourth[1][1, : fourth[0][1]], want_boxes)
+
+
+def test_front_stages_as_two_concurrent_halves(torch_cuda):
+    """A batch of 16 pages or more runs its front stages (decode -> LANMS -> filters -> reading order) as two halves on
+    two streams.  Same bits as one sequence (MS_B200_NO_SPLIT=1), as a graph replay too; pages of both halves against
+    the oracle; an odd page count, an empty page and the reading-order stage included."""
+    import os
+
+    torch = torch_cuda
+    import manuscript_b200 as mb
+
+    page, words, n_pages = 512, 80, 19
+    score, geo, imgs = synthdata.make_batch(list(range(300, 300 + n_pages)), page, words)
+    score[11] = 0.0
+    d = [torch.from_numpy(x).cuda() for x in (score, geo, imgs)]
+    for ro in (0, 1):
+        params = mb.EastParams.default(target_size=page, sort_reading_order=ro)
+        split = mb.PageBatch(device=0, params=params, cap_boxes=512)
+        os.environ["MS_B200_NO_SPLIT"] = "1"
+        try:
+            plain = mb.PageBatch(device=0, params=params, cap_boxes=512)  # its context is created here
+        finally:
+            del os.environ["MS_B200_NO_SPLIT"]
+        want = plain.run(*d)
+        torch.cuda.synchronize()
+        wb, wc, wf = want.boxes.cpu().numpy().copy(), want.box_counts.cpu().numpy().copy(), want.flags.cpu().numpy().copy()
+        wn = int(want.n_crops.cpu()[0])
+        wcr, wba = want.crops.cpu().numpy()[:wn].copy(), want.batch[:wn].cpu().numpy().copy()
+        for rep in range(3):  # direct launches, graph capture, graph replay
+            got = split.run(*d)
+            torch.cuda.synchronize()
+            np.testing.assert_array_equal(got.box_counts.cpu().numpy(), wc)
+            np.testing.assert_array_equal(got.flags.cpu().numpy(), wf)
+            for pg in range(n_pages):
+                np.testing.assert_array_equal(got.boxes[pg, : wc[pg]].cpu().numpy(), wb[pg, : wc[pg]])
+            assert int(got.n_crops.cpu()[0]) == wn
+            np.testing.assert_array_equal(got.crops.cpu().numpy()[:wn], wcr)
+            np.testing.assert_array_equal(got.batch[:wn].cpu().numpy(), wba)
+        assert int(wf.max()) == 0 and wc[11] == 0
+        if ro == 0:
+            for pg in (0, 8, 9, 18):  # both halves (9 + 10 pages)
+                _, _, want_boxes, want_rects = oracle_page(score[pg], geo[pg], imgs[pg], page)
+                np.testing.assert_array_equal(wb[pg, : wc[pg]], want_boxes)
+                np.testing.assert_array_equal(wcr[wcr[:, 0] == pg][:, 1:], want_rects)

@@ -439,7 +439,11 @@ def test_quad_crop_staged_kernel(ops):
         np.array([[100, 100, 220, 90, 200, 160, 90, 150],     # perspective
                   [300, 200, 420, 200, 420, 240, 300, 240],   # axis aligned
                   [300, 100, 400, 100, 320, 130, 300, 160],   # concave: taps leave the hull -> handed back
-                  [50, 300, 150, 300.5, 150, 340, 50, 340.5]], np.float32),
+                  [50, 300, 150, 300.5, 150, 340, 50, 340.5],
+                  [np.nan, 0, 50, 0, 50, 20, 0, 20], [0, 0, 3e38, 0, 3e38, 20, 0, 20],     # no patch
+                  [5, 5, 5.2, 5, 5.2, 5.2, 5, 5.2], [10, 20, 13, 20, 13, 60, 10, 60],     # degenerate / below min_text_size
+                  [100, 100, 200, 100, 100, 100.001, 200, 100.001],                       # nearly collinear
+                  [-20, -10, 90, -12, 92, 30, -18, 28], [650, 380, 720, 384, 718, 420, 648, 416]], np.float32),  # over the border
     ])
     ctx = mb.ops.default_context()
     batch, canvas, valid = ops.quad_crop_resize_pad(page, quads, 32, 128, 5, "constant", 7, want_canvas=True)

@@ -21,6 +21,53 @@ __global__ void __launch_bounds__(224, 4) store_kernel(float4 *out, size_t n4, i
     }
 }
 
+// mode 2: the crop kernel's real write pattern.  A CTA takes canvases (96 rows of 512 bytes: 3 channels x 32 rows x 128
+// floats) in turn; warp 0 writes the last 288 bytes of every row as 16-byte stores (the padding warp), warps 1..5 write
+// the first 224 bytes as 4-byte stores, 32 consecutive floats per warp instruction (the consumers).  No synchronisation.
+template <int kPix>  // floats of a row written by the pixel warps (a multiple of 4); the padding warp writes the rest
+__global__ void __launch_bounds__(224, 4) split_kernel(float *out, size_t canvases)
+{
+    constexpr int kTail4 = (128 - kPix) / 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp > 5) return;
+    for (size_t c = blockIdx.x; c < canvases; c += gridDim.x) {
+        float *cv = out + c * 96 * 128;
+        if (warp == 0) {
+            const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+            for (int i = lane; i < 96 * kTail4; i += 32)
+                __stcs(reinterpret_cast<float4 *>(cv + (i / kTail4) * 128 + kPix) + i % kTail4, one);
+        } else {
+            for (int i = (warp - 1) * 32 + lane; i < 96 * kPix; i += 160) __stcs(cv + (i / kPix) * 128 + i % kPix, 0.5f);
+        }
+    }
+}
+
+// modes 3 / 4: whole canvases (or quarter canvases) as TMA bulk stores out of shared memory, one elected thread per CTA,
+// `depth` stores in flight
+__global__ void __launch_bounds__(224, 4) bulk_kernel(float *out, size_t canvases, int piece_bytes, int depth)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    for (int i = threadIdx.x; i < piece_bytes / 4; i += blockDim.x) reinterpret_cast<float *>(sm)[i] = 1.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const int pieces = 96 * 512 / piece_bytes;
+    const unsigned src = (unsigned)__cvta_generic_to_shared(sm);
+    for (size_t c = blockIdx.x; c < canvases; c += gridDim.x)
+        for (int p = 0; p < pieces; p++) {
+            char *dst = reinterpret_cast<char *>(out) + c * 96 * 512 + (size_t)p * piece_bytes;
+            asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src), "r"(piece_bytes) : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+            if (depth == 1)
+                asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+            else if (depth == 2)
+                asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+            else
+                asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
+        }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 int main()
 {
     const size_t bytes = (size_t)6 << 30;
@@ -48,6 +95,48 @@ int main()
             const double written = mode == 0 ? (double)bytes : (double)bytes * 18 / 32;
             printf("mode %d warps/CTA %d: %.3f ms  %.0f GB/s written\n", mode, w, best, written / best / 1e6);
         }
+    {
+        const size_t canvases = bytes / (96 * 512);
+        float best = 1e9f;
+        for (int pix : {56, 64, 48, 32, 96, 60}) {
+            best = 1e9f;
+            for (int rep = 0; rep < 4; rep++) {
+                cudaEventRecord(e0);
+                float *o = reinterpret_cast<float *>(buf);
+                switch (pix) {
+                case 56: split_kernel<56><<<592, 224>>>(o, canvases); break;
+                case 64: split_kernel<64><<<592, 224>>>(o, canvases); break;
+                case 48: split_kernel<48><<<592, 224>>>(o, canvases); break;
+                case 32: split_kernel<32><<<592, 224>>>(o, canvases); break;
+                case 96: split_kernel<96><<<592, 224>>>(o, canvases); break;
+                default: split_kernel<60><<<592, 224>>>(o, canvases); break;
+                }
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            printf("split pattern, %d pixel floats + %d padding floats per row (padding warp + 5 pixel warps): %.3f ms  %.0f GB/s written\n",
+                   pix, 128 - pix, best, (double)canvases * 96 * 512 / best / 1e6);
+        }
+        cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 512);
+        for (int piece : {96 * 512, 24 * 512, 8 * 512})
+            for (int depth : {1, 2, 4}) {
+                best = 1e9f;
+                for (int rep = 0; rep < 4; rep++) {
+                    cudaEventRecord(e0);
+                    bulk_kernel<<<592, 224, piece>>>(reinterpret_cast<float *>(buf), canvases, piece, depth);
+                    cudaEventRecord(e1);
+                    cudaEventSynchronize(e1);
+                    float ms;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (ms < best) best = ms;
+                }
+                printf("TMA bulk stores of %d bytes, %d in flight per CTA: %.3f ms  %.0f GB/s written\n", piece, depth, best,
+                       (double)canvases * 96 * 512 / best / 1e6);
+            }
+    }
     float best = 1e9f;
     for (int rep = 0; rep < 4; rep++) {
         cudaEventRecord(e0);

@@ -2,7 +2,43 @@
 // Answers whether ONE padding warp per CTA of crop_resize_pad_kernel can be write-bandwidth bound by itself.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o store_bw store_bw.cu && ./store_bw
 #include <cstdio>
+#include <cuda.h>
+#include <cudaTypedefs.h>
 #include <cuda_runtime.h>
+
+// modes 5: what a crop kernel with its canvas rows assembled in shared memory would write -- per canvas ONE TMA tensor
+// store of the pixel box (kPix floats x 96 rows out of a dense tile) + 12 tensor stores of the padding tails ((128 - kPix)
+// floats x 8 rows out of a block of 1.0f); one thread per CTA issues, `depth` canvases in flight.
+struct Maps2 {
+    CUtensorMap pix, tail;
+};
+__global__ void __launch_bounds__(224, 4) tensor_kernel(const __grid_constant__ Maps2 maps, size_t canvases, int pix, int depth)
+{
+    extern __shared__ __align__(128) unsigned char sm[];  // [96][pix] tile, then [8][128 - pix] ones
+    float *tile = reinterpret_cast<float *>(sm), *ones = tile + 96 * pix;
+    for (int i = threadIdx.x; i < 96 * pix + 8 * (128 - pix); i += blockDim.x) tile[i] = 1.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    const unsigned stile = (unsigned)__cvta_generic_to_shared(tile), sones = (unsigned)__cvta_generic_to_shared(ones);
+    for (size_t c = blockIdx.x; c < canvases; c += gridDim.x) {
+        const int row0 = (int)(c * 96);
+        asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&maps.pix), "r"(0),
+                     "r"(row0), "r"(stile)
+                     : "memory");
+        if (pix < 128)
+            for (int b = 0; b < 12; b++)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&maps.tail),
+                             "r"(pix), "r"(row0 + 8 * b), "r"(sones)
+                             : "memory");
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        if (depth == 1)
+            asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+        else
+            asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+    }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
 
 template <int kMode>  // 0: contiguous per warp-iteration (512 B), 1: rows of 288 B inside 512 B rows (the padding pattern)
 __global__ void __launch_bounds__(224, 4) store_kernel(float4 *out, size_t n4, int warps_active)
@@ -135,6 +171,45 @@ int main()
                 }
                 printf("TMA bulk stores of %d bytes, %d in flight per CTA: %.3f ms  %.0f GB/s written\n", piece, depth, best,
                        (double)canvases * 96 * 512 / best / 1e6);
+            }
+    }
+    {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q);
+        PFN_cuTensorMapEncodeTiled encode = reinterpret_cast<PFN_cuTensorMapEncodeTiled>(fn);
+        const size_t canvases = bytes / (96 * 512);
+        cudaFuncSetAttribute(tensor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 56 * 1024);
+        for (int pix : {40, 64, 128, 32, 96})
+            for (int depth : {1, 2}) {
+                Maps2 maps;
+                const cuuint64_t gdim[2] = {128, (cuuint64_t)canvases * 96};
+                const cuuint64_t gstride[1] = {512};
+                const cuuint32_t estride[2] = {1, 1};
+                const cuuint32_t bp[2] = {(cuuint32_t)pix, 96}, bt[2] = {(cuuint32_t)(pix < 128 ? 128 - pix : 4), 8};
+                CUresult r1 = encode(&maps.pix, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, buf, gdim, gstride, bp, estride,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                CUresult r2 = encode(&maps.tail, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, buf, gdim, gstride, bt, estride,
+                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS) {
+                    printf("encode failed %d %d\n", (int)r1, (int)r2);
+                    continue;
+                }
+                const size_t smem = (size_t)(96 * pix + 8 * (128 - pix)) * 4;
+                float best = 1e9f;
+                for (int rep = 0; rep < 4; rep++) {
+                    cudaEventRecord(e0);
+                    tensor_kernel<<<592, 224, smem>>>(maps, canvases, pix, depth);
+                    cudaEventRecord(e1);
+                    cudaEventSynchronize(e1);
+                    float ms;
+                    cudaEventElapsedTime(&ms, e0, e1);
+                    if (ms < best) best = ms;
+                }
+                printf("TMA tensor stores: pixel box %d x 96 + 12 tail boxes %d x 8 per canvas, %d in flight: %.3f ms  %.0f GB/s written (%s)\n",
+                       pix, 128 - pix, depth, best, (double)canvases * 96 * 512 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
             }
     }
     float best = 1e9f;

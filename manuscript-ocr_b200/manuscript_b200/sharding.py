@@ -91,13 +91,12 @@ def gather_boxes_via_shm(counts, rows, root=0, group=None, tag="msb200"):
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     base = f"/dev/shm/{tag}_{os.environ.get('MASTER_PORT', '0')}_{os.getppid() if world > 1 else os.getpid()}"
     ok = os.path.isdir("/dev/shm") and os.access("/dev/shm", os.W_OK)
-    flag = torch.tensor([1 if ok else 0], dtype=torch.int64)
-    dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-    if int(flag[0]) == 0:
-        return gather_boxes_to_root(counts, rows, root, group)
-    sizes = torch.tensor([len(counts), len(rows)], dtype=torch.int64)
-    all_sizes = [torch.zeros(2, dtype=torch.int64) for _ in range(world)]
+    # one collective carries both the sizes and whether every rank can write /dev/shm
+    sizes = torch.tensor([len(counts), len(rows), 1 if ok else 0], dtype=torch.int64)
+    all_sizes = [torch.zeros(3, dtype=torch.int64) for _ in range(world)]
     dist.all_gather(all_sizes, sizes, group=group)
+    if any(int(sz[2]) == 0 for sz in all_sizes):
+        return gather_boxes_to_root(counts, rows, root, group)
     path = f"{base}_{rank}"
     nbytes = counts.nbytes + rows.nbytes
     if rank != root and nbytes:
@@ -109,18 +108,24 @@ def gather_boxes_via_shm(counts, rows, root=0, group=None, tag="msb200"):
     dist.barrier(group=group)
     out = None
     if rank == root:
-        cs, rs = [], []
+        # every rank's segment is copied ONCE, straight into its place in the result (no per-rank temporaries)
+        tot_c = sum(int(sz[0]) for sz in all_sizes)
+        tot_r = sum(int(sz[1]) for sz in all_sizes)
+        out_c, out_r = np.empty(tot_c, np.int32), np.empty((tot_r, 9), np.float32)
+        at_c = at_r = 0
         for r in range(world):
             n_c, n_r = int(all_sizes[r][0]), int(all_sizes[r][1])
             if r == root:
-                cs.append(counts)
-                rs.append(rows)
+                out_c[at_c:at_c + n_c] = counts
+                out_r[at_r:at_r + n_r] = rows
             elif n_c or n_r:
                 mm = np.memmap(f"{base}_{r}", dtype=np.uint8, mode="r", shape=(n_c * 4 + n_r * 36,))
-                cs.append(np.array(mm[: n_c * 4]).view(np.int32))
-                rs.append(np.array(mm[n_c * 4:]).view(np.float32).reshape(-1, 9))
+                out_c[at_c:at_c + n_c].view(np.uint8)[:] = mm[: n_c * 4]
+                out_r[at_r:at_r + n_r].reshape(-1).view(np.uint8)[:] = mm[n_c * 4:]
                 del mm
-        out = (np.concatenate(cs), np.concatenate(rs))
+            at_c += n_c
+            at_r += n_r
+        out = (out_c, out_r)
     dist.barrier(group=group)
     if rank != root and nbytes:
         try:

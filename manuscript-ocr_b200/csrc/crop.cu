@@ -47,21 +47,22 @@ constexpr int kSlots = 4;       // crops in flight per CTA (ring slots: metadata
 #else
 constexpr int kThreads = 224;
 constexpr int kCtasPerSm = 4;
-constexpr int kSlots = 3;
+#ifndef MS_CROP_SLOTS
+#define MS_CROP_SLOTS 3
+#endif
+constexpr int kSlots = MS_CROP_SLOTS;  // (4 slots: 3.5 KB less ring per CTA -- measured r2p, see profiles/README.md)
 #endif
 constexpr bool kPadWarp = MS_CROP_PAD_WARP != 0;
-constexpr int kTabWords = 5;    // per axis entry: packed (s0 | n << 16) and 4 tap weights, one array each (SoA)
 constexpr int kSrcBuf = 40 * 1024;  // largest staged crop (bytes); the staging ring of a CTA holds at least one
-constexpr int kBandsY = 64, kCellsX = 8;
+constexpr int kBandsY = 64, kCellsX = 8;  // work-list buckets per page: (row band, x cell)
 #ifndef MS_COPY_PAD_CHANNELS
 #define MS_COPY_PAD_CHANNELS 0
 #endif
-constexpr int kCopyPadChannels = MS_COPY_PAD_CHANNELS;
+constexpr int kCopyPadChannels = MS_COPY_PAD_CHANNELS;  // float32 padding channels written by the copy warp (A/B switch)
 #ifndef MS_PAD_LAG
 #define MS_PAD_LAG 0
 #endif
-constexpr int kPadLag = MS_PAD_LAG;  // crops between building a crop's tables and writing its padding  // float32 padding channels written by the copy warp
-  // work-list buckets per page: (row band, x cell)
+constexpr int kPadLag = MS_PAD_LAG;  // crops between building a crop's tables and writing its padding (A/B switch)
 
 // Pages are either one (n_pages, img_h, img_w, 3) tensor, or -- page_ptrs != NULL -- separate images of their own
 // sizes: page_ptrs[p] -> (page_hw[2p], page_hw[2p+1], 3) bytes.

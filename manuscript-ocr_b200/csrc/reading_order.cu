@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     __shared__ int s_warp[33];
     __shared__ int s_g[4];  // hull of all boxes
     __shared__ int s_lstart[257], s_lfill[257];  // pairs bucketed by level: segment starts / fill cursors (= ends)
-    __shared__ int s_np, s_lines, s_avg_pos, s_changed, s_maxl, s_dup, s_small;
+    __shared__ int s_np, s_lines, s_avg_pos, s_changed, s_maxl, s_dup;
     __shared__ long long s_hsum;
     __shared__ double s_ytol;
 
@@ -522,17 +522,14 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
     // D1. avg_h (utils.py:581) and the vertical tolerance
     {
         long long hs = 0;
-        int small = 1;  // every |y| below 2^15: the line assignment can run on 32-bit integers
         for (int k = threadIdx.x; k < K; k += kRoThreads) {
             const int y0 = box[k].y, y1 = box[k].w;
             hs += (long long)y1 - (long long)y0;
-            small &= (y0 > -32768 && y0 < 32768 && y1 > -32768 && y1 < 32768) ? 1 : 0;
         }
 #pragma unroll
         for (int off = 16; off > 0; off >>= 1) hs += __shfl_xor_sync(0xffffffffu, hs, off);
         if (threadIdx.x == 0) s_hsum = 0;
-        small = __syncthreads_and(small);
-        if (threadIdx.x == 0) s_small = small;
+        __syncthreads();
         if ((threadIdx.x & 31) == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&s_hsum), (unsigned long long)hs);
         __syncthreads();
         if (threadIdx.x == 0) {

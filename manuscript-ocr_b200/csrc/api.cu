@@ -1083,6 +1083,7 @@ extern "C" int ms_word_rects_host(ms_ctx *ctx, const float *polys8, int64_t n, i
 __global__ void ms_rects_to_crops_kernel(const int32_t *__restrict__ rects, int64_t n, int32_t *__restrict__ crops,
                                          int32_t *__restrict__ n_crops)
 {
+    ms_pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         crops[i * 5] = 0;
 #pragma unroll
@@ -1128,7 +1129,7 @@ extern "C" int ms_crop_resize_pad_host(ms_ctx *ctx, const uint8_t *page, int img
     {
         int grid = (int)((n + 255) / 256);
         if (grid > ctx->num_sms * 4) grid = ctx->num_sms * 4;
-        ms_rects_to_crops_kernel<<<grid, 256, 0, st>>>(d_rects, n, d_crops, d_n);
+        ms_launch(ms_rects_to_crops_kernel, grid, 256, 0, st, d_rects, n, d_crops, d_n);
         MS_LAUNCH_CHECK(ctx);
     }
     MS_TRY(ms_arena_reserve(ctx, msk_crop_scratch(n, 1)));

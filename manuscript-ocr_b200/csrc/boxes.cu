@@ -51,6 +51,7 @@ __device__ __forceinline__ void expand_quad(const float *p, float sx, float sy, 
 
 __global__ void expand_kernel(const float *__restrict__ quads, int64_t n, double ew, double eh, float *__restrict__ out)
 {
+    ms_pdl_wait();
     const bool ident = (ew == 0 && eh == 0);  // utils.py:388 returns the input unchanged
     const float sx = (float)(1.0 + ew) - 1.0f, sy = (float)(1.0 + eh) - 1.0f;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(256) east_prep_kernel(const float *__restrict_
                                                         ms_east_params P, const int32_t *__restrict__ orig_hw,
                                                         int orig_h, int orig_w, EastScratch S)
 {
+    ms_pdl_wait();
     const bool ident = (P.expand_ratio_w == 0 && P.expand_ratio_h == 0);
     const float ex = (float)(1.0 + P.expand_ratio_w) - 1.0f, ey = (float)(1.0 + P.expand_ratio_h) - 1.0f;
     const int page = blockIdx.y;
@@ -323,6 +325,7 @@ __global__ void __launch_bounds__(256) east_prep_kernel(const float *__restrict_
 // 1b) page extents + grid geometry (one CTA per page); pages with a non-finite box use the all-pairs kernel
 __global__ void __launch_bounds__(256) east_ext_kernel(const int32_t *__restrict__ counts, int cap, EastScratch S)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     const int K = counts[page];
     const size_t pb = (size_t)page * cap;
@@ -388,6 +391,7 @@ __global__ void __launch_bounds__(256) east_ext_kernel(const int32_t *__restrict
 
 __global__ void __launch_bounds__(256) east_bin_count_kernel(const int32_t *__restrict__ counts, int cap, EastScratch S)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (S.dense[page]) return;
     const int K = counts[page];
@@ -403,6 +407,7 @@ __global__ void __launch_bounds__(256) east_bin_count_kernel(const int32_t *__re
 
 __global__ void __launch_bounds__(kECells) east_bin_scan_kernel(EastScratch S)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     __shared__ int s_warp[33];
     const int v = S.cell_cnt[(size_t)page * kECells + threadIdx.x];
@@ -415,6 +420,7 @@ __global__ void __launch_bounds__(kECells) east_bin_scan_kernel(EastScratch S)
 
 __global__ void __launch_bounds__(256) east_bin_scatter_kernel(const int32_t *__restrict__ counts, int cap, EastScratch S)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (S.dense[page]) return;
     const int K = counts[page];
@@ -432,6 +438,7 @@ __global__ void __launch_bounds__(256) east_bin_scatter_kernel(const int32_t *__
 __global__ void __launch_bounds__(256) east_contain_binned_kernel(const int32_t *__restrict__ counts, int cap,
                                                                   EastScratch S)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (S.dense[page]) return;
     const int K = counts[page];
@@ -486,6 +493,7 @@ constexpr int kContainThreads = 256;
 __global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int32_t *__restrict__ counts, int cap,
                                                                        EastScratch S)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (!S.dense[page]) return;  // the grid search handled this page
     const int K = counts[page];
@@ -556,6 +564,7 @@ __global__ void __launch_bounds__(512) east_finish_kernel(const int32_t *__restr
                                                           int out_cap, int32_t *__restrict__ counts_out,
                                                           int32_t *__restrict__ flags)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     const int K = counts[page];
     const size_t pb = (size_t)page * cap;
@@ -769,6 +778,7 @@ __device__ __forceinline__ bool word_rect(const float *q, int img_h, int img_w, 
 __global__ void word_rects_flat_kernel(const float *__restrict__ polys8, int64_t n, int img_h, int img_w, int min_text,
                                        int32_t *__restrict__ rects, uint8_t *__restrict__ valid)
 {
+    ms_pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         float q[8];
 #pragma unroll
@@ -788,6 +798,7 @@ __global__ void __launch_bounds__(256) word_rects_page_kernel(const float *__res
                                                               int min_text, int32_t *__restrict__ tmp,
                                                               int32_t *__restrict__ page_n)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     const int K = counts[page];
     const size_t pb = (size_t)page * cap;
@@ -823,6 +834,7 @@ __global__ void __launch_bounds__(256) word_rects_page_kernel(const float *__res
 __global__ void word_rects_offsets_kernel(const int32_t *__restrict__ page_n, int n_pages, int32_t *page_off,
                                           int64_t crops_cap, int32_t *n_crops, int append, int32_t *range)
 {
+    ms_pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         long long run = append ? *n_crops : 0;
         const long long begin = run > crops_cap ? crops_cap : run;
@@ -844,6 +856,7 @@ __global__ void word_rects_pack_kernel(const int32_t *__restrict__ tmp, const in
                                        const int32_t *__restrict__ page_off, int n_pages, int cap, int64_t crops_cap,
                                        int page_base, int32_t *__restrict__ crops)
 {
+    ms_pdl_wait();
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p = (int)(g / cap), i = (int)(g % cap);
     if (p >= n_pages || i >= page_n[p]) return;
@@ -887,7 +900,7 @@ int msk_expand(ms_ctx *ctx, const float *quads, int64_t n, double ew, double eh,
     if (n <= 0) return MS_OK;
     int grid = (int)((n + 127) / 128);
     if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
-    expand_kernel<<<grid, 128, 0, st>>>(quads, n, ew, eh, out);
+    ms_launch(expand_kernel, grid, 128, 0, st, quads, n, ew, eh, out);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }
@@ -920,24 +933,24 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
     // counts live on the device: grids are sized for a few thousand boxes per page and stride beyond that
     int gx = (cap_per_page + 255) / 256;
     if (gx > 16) gx = 16;
-    east_prep_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(quads, counts, n_pages, cap_per_page, *p, orig_hw, orig_h, orig_w, S);
+    ms_launch(east_prep_kernel, dim3(gx, n_pages), 256, 0, st, quads, counts, n_pages, cap_per_page, *p, orig_hw, orig_h, orig_w, S);
     MS_LAUNCH_CHECK(ctx);
-    east_ext_kernel<<<n_pages, 256, 0, st>>>(counts, cap_per_page, S);
+    ms_launch(east_ext_kernel, n_pages, 256, 0, st, counts, cap_per_page, S);
     MS_LAUNCH_CHECK(ctx);
-    east_bin_count_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(counts, cap_per_page, S);
+    ms_launch(east_bin_count_kernel, dim3(gx, n_pages), 256, 0, st, counts, cap_per_page, S);
     MS_LAUNCH_CHECK(ctx);
-    east_bin_scan_kernel<<<n_pages, kECells, 0, st>>>(S);
+    ms_launch(east_bin_scan_kernel, n_pages, kECells, 0, st, S);
     MS_LAUNCH_CHECK(ctx);
-    east_bin_scatter_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(counts, cap_per_page, S);
+    ms_launch(east_bin_scatter_kernel, dim3(gx, n_pages), 256, 0, st, counts, cap_per_page, S);
     MS_LAUNCH_CHECK(ctx);
-    east_contain_binned_kernel<<<dim3(gx * 2, n_pages), 256, 0, st>>>(counts, cap_per_page, S);
+    ms_launch(east_contain_binned_kernel, dim3(gx * 2, n_pages), 256, 0, st, counts, cap_per_page, S);
     MS_LAUNCH_CHECK(ctx);
     gx = (cap_per_page + kContainThreads - 1) / kContainThreads;
     if (gx > 32) gx = 32;
-    east_contain_kernel<<<dim3(gx, n_pages), kContainThreads, 0, st>>>(counts, cap_per_page, S);  // dense pages only
+    ms_launch(east_contain_kernel, dim3(gx, n_pages), kContainThreads, 0, st, counts, cap_per_page, S);  // dense pages only
     MS_LAUNCH_CHECK(ctx);
     // device recursion in np_pairwise_f32: depth <= log2(cap/128) + 1 frames of a few dozen bytes
-    east_finish_kernel<<<n_pages, 512, 0, st>>>(counts, cap_per_page, *p, S, quads_out, out_cap, counts_out, flags);
+    ms_launch(east_finish_kernel, n_pages, 512, 0, st, counts, cap_per_page, *p, S, quads_out, out_cap, counts_out, flags);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }
@@ -958,13 +971,13 @@ int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
         ms_set_error("word_rects: scratch too small");
         return MS_ERR_CAPACITY;
     }
-    word_rects_page_kernel<<<n_pages, 256, 0, st>>>(quads, counts, cap_per_page, img_hw, img_h, img_w, min_text_size,
+    ms_launch(word_rects_page_kernel, n_pages, 256, 0, st, quads, counts, cap_per_page, img_hw, img_h, img_w, min_text_size,
                                                     tmp, page_n);
     MS_LAUNCH_CHECK(ctx);
-    word_rects_offsets_kernel<<<1, 32, 0, st>>>(page_n, n_pages, page_off, crops_cap, n_crops, append, range);
+    ms_launch(word_rects_offsets_kernel, 1, 32, 0, st, page_n, n_pages, page_off, crops_cap, n_crops, append, range);
     MS_LAUNCH_CHECK(ctx);
     size_t threads = (size_t)n_pages * cap_per_page;
-    word_rects_pack_kernel<<<(int)((threads + 255) / 256), 256, 0, st>>>(tmp, page_n, page_off, n_pages, cap_per_page,
+    ms_launch(word_rects_pack_kernel, (int)((threads + 255) / 256), 256, 0, st, tmp, page_n, page_off, n_pages, cap_per_page,
                                                                          crops_cap, page_base, crops_out);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
@@ -976,7 +989,7 @@ int msk_word_rects_flat(ms_ctx *ctx, const float *polys8, int64_t n, int img_h, 
     if (n <= 0) return MS_OK;
     int grid = (int)((n + 127) / 128);
     if (grid > ctx->num_sms * 8) grid = ctx->num_sms * 8;
-    word_rects_flat_kernel<<<grid, 128, 0, st>>>(polys8, n, img_h, img_w, min_text_size, rects, valid);
+    ms_launch(word_rects_flat_kernel, grid, 128, 0, st, polys8, n, img_h, img_w, min_text_size, rects, valid);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

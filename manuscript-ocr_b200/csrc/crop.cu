@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
                                                         const int32_t *__restrict__ range, int64_t crops_cap, int ih,
                                                         int iw, Plan *__restrict__ plans, int32_t *__restrict__ hist)
 {
+    ms_pdl_wait();
     int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
@@ -153,6 +154,7 @@ __global__ void __launch_bounds__(256) crop_plan_kernel(const uint8_t *__restric
 __global__ void __launch_bounds__(1024) crop_bucket_scan_kernel(int32_t *__restrict__ hist, int n_buckets,
                                                                 int32_t *__restrict__ n_work)
 {
+    ms_pdl_wait();
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -235,6 +237,7 @@ __global__ void __launch_bounds__(256) crop_bucket_scatter_kernel(const Plan *__
                                                                   const int32_t *__restrict__ range, int64_t crops_cap,
                                                                   int32_t *__restrict__ cursors, CopyDesc *__restrict__ work)
 {
+    ms_pdl_wait();
     int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
@@ -280,6 +283,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
                            int iw, float *__restrict__ batch, uint8_t *__restrict__ canvas_out, int vec_ok,
                            uint8_t *__restrict__ redo)
 {
+    ms_pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];  // [ring_bytes] staging ring, then kSlots table sets
     const int tab_n = area_tab_words(ih, iw);  // words of one slot's table set
     uint32_t *tabs = reinterpret_cast<uint32_t *>(smem + ring_bytes);  // [kSlots][tab_n]
@@ -544,6 +548,7 @@ __global__ void __launch_bounds__(256) crop_generic_list_kernel(const Plan *__re
                                                                 const uint8_t *__restrict__ redo,
                                                                 int32_t *__restrict__ list, int32_t *__restrict__ list_n)
 {
+    ms_pdl_wait();
     const int64_t begin = range ? range[0] : 0;
     int64_t n_crops = range ? range[1] : *n_crops_dev;
     if (n_crops > crops_cap) n_crops = crops_cap;
@@ -563,6 +568,7 @@ __global__ void __launch_bounds__(256) crop_generic_kernel(const Plan *__restric
                                                            float *__restrict__ batch,
                                                            uint8_t *__restrict__ canvas_out, int vec_ok)
 {
+    ms_pdl_wait();
     __shared__ AxisEnt s_tab[kGenericMaxTab];
     const int plane = ih * iw;
     const float inv = 1.0f / 127.5f;
@@ -625,6 +631,7 @@ __global__ void __launch_bounds__(256) detector_input_kernel(const uint8_t *__re
                                                              int tw, float *__restrict__ out_f32,
                                                              uint8_t *__restrict__ out_u8)
 {
+    ms_pdl_wait();
     const double scale_x = 1.0 / ((double)tw / (double)W), scale_y = 1.0 / ((double)th / (double)H);
     const bool same = (th == H && tw == W);  // cv2.resize returns a copy
     const size_t plane = (size_t)th * tw;
@@ -666,7 +673,7 @@ int msk_detector_input(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, i
     const size_t n = (size_t)target_h * target_w;
     size_t grid = (n + 255) / 256;
     if (grid > (size_t)ctx->num_sms * 16) grid = (size_t)ctx->num_sms * 16;
-    detector_input_kernel<<<(int)grid, 256, 0, st>>>(page, img_h, img_w, target_h, target_w, out_f32, out_u8);
+    ms_launch(detector_input_kernel, (int)grid, 256, 0, st, page, img_h, img_w, target_h, target_w, out_f32, out_u8);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }
@@ -728,12 +735,12 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
     MS_CUDA(cudaMemsetAsync(cnt, 0, 4 * sizeof(int32_t), st));
     int64_t lgrid = (crops_cap + 255) / 256;
     if (lgrid > (int64_t)ctx->num_sms * 8) lgrid = (int64_t)ctx->num_sms * 8;
-    crop_plan_kernel<<<(int)lgrid, 256, 0, st>>>(pages, ragged ? page_ptrs : nullptr, page_hw, n_pages, img_h, img_w, crops,
+    ms_launch(crop_plan_kernel, (int)lgrid, 256, 0, st, pages, ragged ? page_ptrs : nullptr, page_hw, n_pages, img_h, img_w, crops,
                                                  n_crops, range, crops_cap, out_h, out_w, plans, hist);
     MS_LAUNCH_CHECK(ctx);
-    crop_bucket_scan_kernel<<<1, 1024, 0, st>>>(hist, n_buckets, n_work);
+    ms_launch(crop_bucket_scan_kernel, 1, 1024, 0, st, hist, n_buckets, n_work);
     MS_LAUNCH_CHECK(ctx);
-    crop_bucket_scatter_kernel<<<(int)lgrid, 256, 0, st>>>(plans, ragged ? page_hw : nullptr, n_pages, img_h, img_w, n_crops,
+    ms_launch(crop_bucket_scatter_kernel, (int)lgrid, 256, 0, st, plans, ragged ? page_hw : nullptr, n_pages, img_h, img_w, n_crops,
                                                            range, crops_cap, hist, work);
     MS_LAUNCH_CHECK(ctx);
     int64_t grid = (int64_t)ctx->num_sms * per_sm;
@@ -751,12 +758,12 @@ int msk_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int img_
             MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));                \
             granted = (int)smem;                                                                                       \
         }                                                                                                              \
-        kfn<<<(int)grid, kThreads, smem, st>>>(plans, work, n_work, ticket, (int)ring, out_h, out_w, batch_f32,      \
+        ms_launch(kfn, (int)grid, kThreads, smem, st, plans, work, n_work, ticket, (int)ring, out_h, out_w, batch_f32,      \
                                               canvas_u8, vec_ok, redo);                                               \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
-        crop_generic_list_kernel<<<(int)lgrid, 256, 0, st>>>(plans, n_crops, range, crops_cap, redo, glist, glist_n);  \
+        ms_launch(crop_generic_list_kernel, (int)lgrid, 256, 0, st, plans, n_crops, range, crops_cap, redo, glist, glist_n);  \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
-        crop_generic_kernel<F32, U8><<<(int)ggrid, 256, 0, st>>>(plans, glist, glist_n, out_h,                        \
+        ms_launch(crop_generic_kernel<F32, U8>, (int)ggrid, 256, 0, st, plans, glist, glist_n, out_h,                        \
                                                                  out_w, batch_f32, canvas_u8, vec_ok);                \
     } while (0)
     if (batch_f32 && canvas_u8)

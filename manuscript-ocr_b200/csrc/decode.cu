@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(kThreads) decode_mark_kernel(const float *__re
                                                                int32_t *__restrict__ tile_counts,
                                                                int32_t *__restrict__ flags)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y, tile = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const float *sc = score + (size_t)page * g.H * g.W;
@@ -119,6 +120,7 @@ __global__ void __launch_bounds__(256) decode_scan_kernel(const int32_t *__restr
                                                           int cap, int32_t *__restrict__ tile_base,
                                                           int32_t *__restrict__ counts, int32_t *__restrict__ flags)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     __shared__ int s_part[256];
     __shared__ int s_run;
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(kThreads) decode_emit_kernel(const float *__re
                                                                const int32_t *__restrict__ tile_base, int cap,
                                                                float *__restrict__ out, int geo_compact)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y, tile = blockIdx.x;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     __shared__ int s_word_base[kTileWords];
@@ -311,15 +314,15 @@ int msk_decode(ms_ctx *ctx, const float *score, const float *geo, int n_pages, i
         return MS_ERR_CAPACITY;
     }
     dim3 grid(g.tiles, n_pages);
-    decode_mark_kernel<<<grid, kThreads, 0, st>>>(score, g, thr, masks, tile_counts, flags);
+    ms_launch(decode_mark_kernel, grid, kThreads, 0, st, score, g, thr, masks, tile_counts, flags);
     MS_LAUNCH_CHECK(ctx);
-    decode_scan_kernel<<<n_pages, 256, 0, st>>>(tile_counts, g.tiles, cap_per_page, tile_base, counts, flags);
+    ms_launch(decode_scan_kernel, n_pages, 256, 0, st, tile_counts, g.tiles, cap_per_page, tile_base, counts, flags);
     MS_LAUNCH_CHECK(ctx);
     if (rbox)
-        decode_emit_kernel<true><<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page,
+        ms_launch(decode_emit_kernel<true>, grid, kThreads, 0, st, score, geo, g, scale, masks, tile_base, cap_per_page,
                                                             quads_out, geo_compact);
     else
-        decode_emit_kernel<false><<<grid, kThreads, 0, st>>>(score, geo, g, scale, masks, tile_base, cap_per_page,
+        ms_launch(decode_emit_kernel<false>, grid, kThreads, 0, st, score, geo, g, scale, masks, tile_base, cap_per_page,
                                                              quads_out, geo_compact);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;

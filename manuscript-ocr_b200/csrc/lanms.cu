@@ -155,6 +155,7 @@ __global__ void lanms_offsets_kernel(const int32_t *__restrict__ counts, int n_p
                                      int32_t *n_total, int32_t *hot_count, int32_t *edge_count, int32_t *irr_count,
                                      int32_t *page_redo)
 {
+    ms_pdl_wait();
     // one thread: n_pages is small (<= a few thousand)
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         int run = 0;
@@ -177,6 +178,7 @@ __global__ void lanms_keys_kernel(const float *__restrict__ quads, const int32_t
                                   uint32_t *__restrict__ keys, uint32_t *__restrict__ vals,
                                   int32_t *__restrict__ pos_page)
 {
+    ms_pdl_wait();
     size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     int p = (int)(g / cap), i = (int)(g % cap);
     if (p >= n_pages || i >= counts[p]) return;
@@ -194,6 +196,7 @@ __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__re
                                                                const int32_t *__restrict__ n_total, double thr,
                                                                LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int n = *n_total;
     double buf[4 * MS_MAXV];
     __shared__ int s_q[128 / 32][64];  // per warp: positions whose IoU with the predecessor has to be evaluated
@@ -269,6 +272,7 @@ __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__re
 __global__ void __launch_bounds__(128) lanms_runs_kernel(const int32_t *__restrict__ page_off, double thr,
                                                          LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int nh = *B.hot_count;
     double buf[4 * MS_MAXV];
     for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nh; j += gridDim.x * blockDim.x) {
@@ -340,6 +344,7 @@ constexpr int kAcceptBatch = 2048;  // hot positions walked per round out of sha
 
 __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     const int p0 = page_off[page], p1 = page_off[page + 1];
     __shared__ int s_warp[33];
@@ -459,6 +464,7 @@ constexpr int kBuildRuns = 1024;  // accepted runs searched out of shared memory
 __global__ void __launch_bounds__(kBuildThreads) lanms_build_clusters_kernel(const int32_t *__restrict__ page_off,
                                                                              int all_irregular, LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     const int p0 = page_off[page], p1 = page_off[page + 1];
     __shared__ int s_h[kBuildRuns], s_e[kBuildRuns], s_pm[kBuildRuns];
@@ -629,6 +635,7 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
                                                                    const int32_t *__restrict__ n_total, double thr,
                                                                    LanmsBuffers B, int32_t *flags, int irregular_only)
 {
+    ms_pdl_wait();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int n = *n_total;
     __shared__ int2 s_q[kPairWarps][kQueue];
@@ -682,6 +689,7 @@ __global__ void __launch_bounds__(kPairThreads) lanms_pairs_kernel(const int32_t
 __global__ void __launch_bounds__(256) nms_bin_count_kernel(const int32_t *__restrict__ page_off,
                                                             const int32_t *__restrict__ n_total, LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int n = *n_total;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
         const int page = B.pos_page[slot];
@@ -697,6 +705,7 @@ __global__ void __launch_bounds__(256) nms_bin_count_kernel(const int32_t *__res
 
 __global__ void __launch_bounds__(1024) nms_bin_scan_kernel(LanmsBuffers B)
 {
+    ms_pdl_wait();
     // exclusive scan of the page's kCells cell counts: a thread owns kCells / 1024 consecutive cells
     static_assert(kCells % 1024 == 0, "cells per thread");
     constexpr int kPer = kCells / 1024;
@@ -722,6 +731,7 @@ __global__ void __launch_bounds__(1024) nms_bin_scan_kernel(LanmsBuffers B)
 __global__ void __launch_bounds__(256) nms_bin_scatter_kernel(const int32_t *__restrict__ page_off,
                                                               const int32_t *__restrict__ n_total, LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int n = *n_total;
     for (int slot = blockIdx.x * blockDim.x + threadIdx.x; slot < n; slot += gridDim.x * blockDim.x) {
         const int page = B.pos_page[slot];
@@ -747,6 +757,7 @@ constexpr int kMaxHits = 32;  // higher-index neighbours one cluster may have (o
 __global__ void __launch_bounds__(kBinThreads) nms_pairs_binned_kernel(const int32_t *__restrict__ page_off,
                                                                        LanmsBuffers B, int32_t *flags)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     const int p0 = page_off[page];
     const int C = B.cl_count[page];
@@ -842,6 +853,7 @@ __device__ __forceinline__ void walk_neighbours(const LanmsBuffers &B, int p0, i
 
 __global__ void __launch_bounds__(kBinThreads) nms_redo_count_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (!B.page_redo[page]) return;
     const int p0 = page_off[page];
@@ -856,6 +868,7 @@ __global__ void __launch_bounds__(kBinThreads) nms_redo_count_kernel(const int32
 __global__ void __launch_bounds__(1024) nms_redo_scan_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B,
                                                              int32_t *flags)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     if (!B.page_redo[page]) return;
     const int p0 = page_off[page];
@@ -879,6 +892,7 @@ __global__ void __launch_bounds__(1024) nms_redo_scan_kernel(const int32_t *__re
 
 __global__ void __launch_bounds__(kBinThreads) nms_redo_fill_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (!B.page_redo[page]) return;
     const int p0 = page_off[page];
@@ -958,6 +972,7 @@ __device__ __forceinline__ void cluster_sync_all()
 __global__ void __launch_bounds__(1024) lanms_resolve_kernel(const int32_t *__restrict__ page_off, double thr,
                                                              LanmsBuffers B, int32_t *__restrict__ und_flags)
 {
+    ms_pdl_wait();
     uint32_t crank, csize;
     asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(crank));
     asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(csize));
@@ -1103,13 +1118,15 @@ static int launch_resolve(ms_ctx *ctx, int n_pages, const int32_t *page_off, dou
     cfg.blockDim = dim3(1024, 1, 1);
     cfg.dynamicSmemBytes = 0;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = (unsigned)cs;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = ms_pdl_enabled() ? 2 : 1;
     MS_CUDA(cudaLaunchKernelEx(&cfg, lanms_resolve_kernel, page_off, thr, B, und_flags));
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
@@ -1129,6 +1146,7 @@ __device__ __forceinline__ uint64_t desc_score_key(double sc)
 __global__ void __launch_bounds__(1024) lanms_kept_kernel(const int32_t *__restrict__ page_off, LanmsBuffers B,
                                                           int32_t *__restrict__ counts_out, int f32_scores)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     const int p0 = page_off[page];
     const int C = B.cl_count[page];
@@ -1172,6 +1190,7 @@ __global__ void __launch_bounds__(1024) lanms_sort_emit_kernel(const int32_t *__
                                                                LanmsBuffers B, float *__restrict__ out,
                                                                const int32_t *__restrict__ counts_out)
 {
+    ms_pdl_wait();
     const int page = blockIdx.x;
     const int p0 = page_off[page];
     const int K = counts_out[page];
@@ -1226,6 +1245,7 @@ __global__ void __launch_bounds__(256) lanms_emit_sorted_kernel(const int32_t *_
                                                                 LanmsBuffers B, float *__restrict__ out,
                                                                 const int32_t *__restrict__ counts_out)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     const int K = counts_out[page];
     const int p0 = page_off[page];
@@ -1248,6 +1268,7 @@ __global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t 
                                                                   int32_t *__restrict__ keep_idx_out,
                                                                   const int32_t *__restrict__ rank_needed)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     if (rank_needed && !rank_needed[page]) return;
     const int p0 = page_off[page];
@@ -1299,6 +1320,7 @@ __global__ void __launch_bounds__(kRankThreads) lanms_emit_kernel(const int32_t 
 __global__ void iou_pairs_kernel(const double *__restrict__ subj, const double *__restrict__ clip, int64_t n,
                                  double *__restrict__ iou)
 {
+    ms_pdl_wait();
     double buf[4 * MS_MAXV];
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double a[8], b[8];
@@ -1314,6 +1336,7 @@ __global__ void iou_pairs_kernel(const double *__restrict__ subj, const double *
 __global__ void iou_proved_kernel(const double *__restrict__ subj, const double *__restrict__ clip, int64_t n,
                                   double thr, uint8_t *__restrict__ out)
 {
+    ms_pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         double a[8], b[8];
         load_quad(subj + i * 8, a);
@@ -1328,6 +1351,7 @@ __global__ void iou_proved_kernel(const double *__restrict__ subj, const double 
 __global__ void nms_prepare_kernel(const double *__restrict__ polys, const double *__restrict__ scores, int n,
                                    LanmsBuffers B)
 {
+    ms_pdl_wait();
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         B.page_off[0] = 0;
         B.page_off[1] = n;
@@ -1433,24 +1457,24 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         return MS_ERR_CAPACITY;
     }
     const int sms = ctx->num_sms;
-    lanms_offsets_kernel<<<1, 32, 0, st>>>(counts, n_pages, B.page_off, B.n_total, B.hot_count, B.edge_count,
+    ms_launch(lanms_offsets_kernel, 1, 32, 0, st, counts, n_pages, B.page_off, B.n_total, B.hot_count, B.edge_count,
                                            B.irr_count, B.page_redo);
     MS_LAUNCH_CHECK(ctx);
     {
         size_t threads = n_max;
         int grid = (int)((threads + 255) / 256);
-        lanms_keys_kernel<<<grid, 256, 0, st>>>(quads, counts, B.page_off, n_pages, cap_per_page, B.keys, B.vals,
+        ms_launch(lanms_keys_kernel, grid, 256, 0, st, quads, counts, B.page_off, n_pages, cap_per_page, B.keys, B.vals,
                                                 B.pos_page);
         MS_LAUNCH_CHECK(ctx);
     }
     int rc = msk_sort_pages(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.page_off, nullptr, -1, n_pages, cap_per_page,
                             bump, st);
     if (rc != MS_OK) return rc;
-    lanms_gather_hot_kernel<<<sms * 8, 128, 0, st>>>(quads, B.vals, B.page_off, B.n_total, thr, B);
+    ms_launch(lanms_gather_hot_kernel, sms * 8, 128, 0, st, quads, B.vals, B.page_off, B.n_total, thr, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_runs_kernel<<<sms * 4, 128, 0, st>>>(B.page_off, thr, B);
+    ms_launch(lanms_runs_kernel, sms * 4, 128, 0, st, B.page_off, thr, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_accept_kernel<<<n_pages, kResolveThreads, 0, st>>>(B.page_off, B);
+    ms_launch(lanms_accept_kernel, n_pages, kResolveThreads, 0, st, B.page_off, B);
     MS_LAUNCH_CHECK(ctx);
     {
         // a few CTAs per page, each striding over the page's positions (the counts live on the device)
@@ -1458,49 +1482,48 @@ int msk_lanms(ms_ctx *ctx, const float *quads, const int32_t *counts, int n_page
         const int want = (sms * 8 + n_pages - 1) / n_pages;
         if (gx > want) gx = want;
         if (gx < 1) gx = 1;
-        lanms_build_clusters_kernel<<<dim3((unsigned)gx, (unsigned)n_pages), kBuildThreads, 0, st>>>(
-            B.page_off, thr < 0 ? 1 : 0, B);
+        ms_launch(lanms_build_clusters_kernel, dim3((unsigned)gx, (unsigned)n_pages), kBuildThreads, 0, st, B.page_off, thr < 0 ? 1 : 0, B);
     }
     MS_LAUNCH_CHECK(ctx);
     {
         int g = (int)((n_max + 255) / 256);
         if (g > sms * 8) g = sms * 8;
-        nms_bin_count_kernel<<<g, 256, 0, st>>>(B.page_off, B.n_total, B);
+        ms_launch(nms_bin_count_kernel, g, 256, 0, st, B.page_off, B.n_total, B);
         MS_LAUNCH_CHECK(ctx);
-        nms_bin_scan_kernel<<<n_pages, 1024, 0, st>>>(B);
+        ms_launch(nms_bin_scan_kernel, n_pages, 1024, 0, st, B);
         MS_LAUNCH_CHECK(ctx);
-        nms_bin_scatter_kernel<<<g, 256, 0, st>>>(B.page_off, B.n_total, B);
+        ms_launch(nms_bin_scatter_kernel, g, 256, 0, st, B.page_off, B.n_total, B);
         MS_LAUNCH_CHECK(ctx);
         int gx = (cap_per_page + kBinThreads - 1) / kBinThreads;
         if (gx > 64) gx = 64;
-        nms_pairs_binned_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B, flags);
+        ms_launch(nms_pairs_binned_kernel, dim3(gx, n_pages), kBinThreads, 0, st, B.page_off, B, flags);
         MS_LAUNCH_CHECK(ctx);
-        nms_redo_count_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B);
+        ms_launch(nms_redo_count_kernel, dim3(gx, n_pages), kBinThreads, 0, st, B.page_off, B);
         MS_LAUNCH_CHECK(ctx);
-        nms_redo_scan_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, flags);
+        ms_launch(nms_redo_scan_kernel, n_pages, 1024, 0, st, B.page_off, B, flags);
         MS_LAUNCH_CHECK(ctx);
-        nms_redo_fill_kernel<<<dim3(gx, n_pages), kBinThreads, 0, st>>>(B.page_off, B);
+        ms_launch(nms_redo_fill_kernel, dim3(gx, n_pages), kBinThreads, 0, st, B.page_off, B);
         MS_LAUNCH_CHECK(ctx);
     }
-    lanms_pairs_kernel<<<sms * 4, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 1);
+    ms_launch(lanms_pairs_kernel, sms * 4, kPairThreads, 0, st, B.page_off, B.n_total, thr, B, flags, 1);
     MS_LAUNCH_CHECK(ctx);
     {
         int rc2 = launch_resolve(ctx, n_pages, B.page_off, thr, B, B.und_flags, st);
         if (rc2 != MS_OK) return rc2;
     }
-    lanms_kept_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, B, counts_out, 1);
+    ms_launch(lanms_kept_kernel, n_pages, 1024, 0, st, B.page_off, B, counts_out, 1);
     MS_LAUNCH_CHECK(ctx);
     {
         int gx = (cap_per_page + kRankThreads - 1) / kRankThreads;
         if (gx > 32) gx = 32;
-        lanms_sort_emit_kernel<<<n_pages, 1024, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out);
+        ms_launch(lanms_sort_emit_kernel, n_pages, 1024, 0, st, B.page_off, cap_per_page, B, quads_out, counts_out);
         MS_LAUNCH_CHECK(ctx);
         // pages with more kept boxes than the shared-memory sort holds: stable radix sort of (descending score key,
         // cluster index) -- the kernels return at once for the other pages
         int rc2 = msk_sort_pages(ctx, B.keys, B.vals, B.keys_tmp, B.vals_tmp, B.page_off, counts_out, kSortMax, n_pages,
                                  cap_per_page, bump, st);
         if (rc2 != MS_OK) return rc2;
-        lanms_emit_sorted_kernel<<<dim3(gx, n_pages), 256, 0, st>>>(B.page_off, cap_per_page, B, quads_out, counts_out);
+        ms_launch(lanms_emit_sorted_kernel, dim3(gx, n_pages), 256, 0, st, B.page_off, cap_per_page, B, quads_out, counts_out);
         MS_LAUNCH_CHECK(ctx);
     }
     return MS_OK;
@@ -1517,20 +1540,20 @@ int msk_standard_nms(ms_ctx *ctx, const double *polys, const double *scores, int
         return MS_ERR_CAPACITY;
     }
     const int sms = ctx->num_sms;
-    nms_prepare_kernel<<<sms, 256, 0, st>>>(polys, scores, n, B);
+    ms_launch(nms_prepare_kernel, sms, 256, 0, st, polys, scores, n, B);
     MS_LAUNCH_CHECK(ctx);
-    lanms_pairs_kernel<<<sms * 8, kPairThreads, 0, st>>>(B.page_off, B.n_total, thr, B, flags, 0);
+    ms_launch(lanms_pairs_kernel, sms * 8, kPairThreads, 0, st, B.page_off, B.n_total, thr, B, flags, 0);
     MS_LAUNCH_CHECK(ctx);
     {
         int rc2 = launch_resolve(ctx, 1, B.page_off, thr, B, B.und_flags, st);
         if (rc2 != MS_OK) return rc2;
     }
-    lanms_kept_kernel<<<1, 1024, 0, st>>>(B.page_off, B, k_out, 0);
+    ms_launch(lanms_kept_kernel, 1, 1024, 0, st, B.page_off, B, k_out, 0);
     MS_LAUNCH_CHECK(ctx);
     {
         int gx = (n + kRankThreads - 1) / kRankThreads;
         if (gx > 148) gx = 148;
-        lanms_emit_kernel<<<dim3(gx, 1), kRankThreads, 0, st>>>(B.page_off, n, B, nullptr, k_out, keep_idx, nullptr);
+        ms_launch(lanms_emit_kernel, dim3(gx, 1), kRankThreads, 0, st, B.page_off, n, B, nullptr, k_out, keep_idx, nullptr);
         MS_LAUNCH_CHECK(ctx);
     }
     return MS_OK;
@@ -1542,7 +1565,7 @@ int msk_iou_proved(ms_ctx *ctx, const double *subj, const double *clip, int64_t 
     if (n <= 0) return MS_OK;
     int grid = (int)((n + 127) / 128);
     if (grid > ctx->num_sms * 16) grid = ctx->num_sms * 16;
-    iou_proved_kernel<<<grid, 128, 0, st>>>(subj, clip, n, thr, out);
+    ms_launch(iou_proved_kernel, grid, 128, 0, st, subj, clip, n, thr, out);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }
@@ -1552,7 +1575,7 @@ int msk_polygon_iou(ms_ctx *ctx, const double *subj, const double *clip, int64_t
     if (n <= 0) return MS_OK;
     int grid = (int)((n + 127) / 128);
     if (grid > ctx->num_sms * 16) grid = ctx->num_sms * 16;
-    iou_pairs_kernel<<<grid, 128, 0, st>>>(subj, clip, n, iou);
+    ms_launch(iou_pairs_kernel, grid, 128, 0, st, subj, clip, n, iou);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

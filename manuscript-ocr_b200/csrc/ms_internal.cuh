@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "../../include/manuscript_b200.h"
 
@@ -94,6 +95,39 @@ int ms_stage_reserve(ms_ctx *ctx, size_t bytes);
         int _rc = ms_check_cuda((call), #call);                        \
         if (_rc != MS_OK) return _rc;                                  \
     } while (0)
+
+// ---- programmatic dependent launch --------------------------------------------------------------------------------
+// The front stages are ~50 short kernels, each depending on the one before it: the gap between two of them (the next
+// kernel's CTAs are only scheduled after the previous grid has completed and flushed) is a few microseconds per edge,
+// direct or as a graph.  Kernels launched through ms_launch carry cudaLaunchAttributeProgrammaticStreamSerialization, so
+// their CTAs are scheduled while the previous kernel's last CTAs drain; EVERY such kernel executes ms_pdl_wait()
+// (griddepcontrol.wait: returns when the preceding grid has completed and its writes are visible) before it touches
+// memory, which makes the chain transitive and the results those of plain stream order.  MS_B200_NO_PDL=1: plain launches.
+#if defined(__CUDACC__)
+__device__ __forceinline__ void ms_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+inline bool ms_pdl_enabled()
+{
+    static const bool on = getenv("MS_B200_NO_PDL") == nullptr;
+    return on;
+}
+
+template <typename... KArgs, typename... Args>
+inline void ms_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = ms_pdl_enabled() ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);  // errors surface through MS_LAUNCH_CHECK (cudaGetLastError)
+}
+#endif
 
 #define MS_LAUNCH_CHECK(ctx)                                           \
     do {                                                               \

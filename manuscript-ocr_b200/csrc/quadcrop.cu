@@ -137,6 +137,7 @@ __global__ void __launch_bounds__(128) quad_plan_kernel(const float *__restrict_
                                                         int stage_ok, QuadDesc *__restrict__ work,
                                                         int32_t *__restrict__ n_work)
 {
+    ms_pdl_wait();
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         const float *q = quads + i * quad_stride;
         QuadPlan qp;
@@ -400,6 +401,7 @@ __global__ void __launch_bounds__(kQcThreads, 4) quad_crop_kernel(const uint8_t 
                                                                   const int32_t *__restrict__ list,
                                                                   const int32_t *__restrict__ list_n)
 {
+    ms_pdl_wait();
     // `list` != NULL: only the quads it names (those the staged kernel did not take, or handed back)
     // [patch stage kQcPatchBytes + 16][tables: AxisEnt[kQcMaxTab] for resample_px, or the SoA tables of area4_strips]
     extern __shared__ __align__(16) unsigned char qc_smem[];
@@ -497,6 +499,7 @@ __global__ void __launch_bounds__(kQsThreads, 2)
                             int32_t *__restrict__ ticket, int ih, int iw, float *__restrict__ batch,
                             uint8_t *__restrict__ canvas_out, int vec_ok, uint8_t *__restrict__ redo)
 {
+    ms_pdl_wait();
     extern __shared__ __align__(128) unsigned char smem[];  // [kQsRing + 64][kQsCW band buffers][kQsSlots table sets]
     const int tab_n = area_tab_words(ih, iw);
     unsigned char *bands = smem + kQsRing + 64;
@@ -749,6 +752,7 @@ __global__ void __launch_bounds__(256) quad_fallback_list_kernel(const QuadPlan 
                                                                  const uint8_t *__restrict__ redo,
                                                                  int32_t *__restrict__ list, int32_t *__restrict__ list_n)
 {
+    ms_pdl_wait();
     for (int64_t ci = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += (int64_t)gridDim.x * blockDim.x)
         if (!qplans[ci].staged || redo[ci]) list[atomicAdd(list_n, 1)] = (int32_t)ci;
 }
@@ -758,6 +762,7 @@ __global__ void __launch_bounds__(256) quad_warp_kernel(const uint8_t *__restric
                                                         const QuadPlan *__restrict__ qplan, int replicate, int bval,
                                                         uint8_t *__restrict__ patch)
 {
+    ms_pdl_wait();
     __shared__ QuadPlan s_qp;
     if (threadIdx.x == 0) s_qp = *qplan;
     __syncthreads();
@@ -837,7 +842,7 @@ int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int
     MS_CUDA(cudaMemsetAsync(redo, 0, (size_t)n, st));
     int64_t pg = (n + 127) / 128;
     if (pg > (int64_t)ctx->num_sms * 16) pg = (int64_t)ctx->num_sms * 16;
-    quad_plan_kernel<<<(int)pg, 128, 0, st>>>(quads, quad_stride, page_of, n, n_pages, min_text_size, out_h, out_w,
+    ms_launch(quad_plan_kernel, (int)pg, 128, 0, st, quads, quad_stride, page_of, n, n_pages, min_text_size, out_h, out_w,
                                              qplans, plans, sizes_out, pages, img_h, img_w, stage_ok, work, cnt);
     MS_LAUNCH_CHECK(ctx);
     const int vec_ok = ((out_w & 3) == 0 && (reinterpret_cast<uintptr_t>(batch_f32) & 15) == 0) ? 1 : 0;
@@ -855,11 +860,11 @@ int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int
                 MS_CUDA(cudaFuncSetAttribute(sfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_s));              \
                 sgranted = smem_s;                                                                                     \
             }                                                                                                          \
-            sfn<<<ctx->num_sms * 2, kQsThreads, smem_s, st>>>(qplans, plans, work, cnt, cnt + 1, out_h, out_w,        \
+            ms_launch(sfn, ctx->num_sms * 2, kQsThreads, smem_s, st, qplans, plans, work, cnt, cnt + 1, out_h, out_w,        \
                                                                batch_f32, canvas_u8, vec_ok, redo);                    \
             MS_LAUNCH_CHECK(ctx);                                                                                      \
         }                                                                                                              \
-        quad_fallback_list_kernel<<<(int)pg, 256, 0, st>>>(qplans, n, redo, list, cnt + 2);                            \
+        ms_launch(quad_fallback_list_kernel, (int)pg, 256, 0, st, qplans, n, redo, list, cnt + 2);                            \
         MS_LAUNCH_CHECK(ctx);                                                                                          \
         auto kfn = quad_crop_kernel<F32, U8>;                                                                          \
         int &granted = ctx->smem_attr[4 + (F32 ? 1 : 0) + (U8 ? 2 : 0) - 1];                                           \
@@ -867,7 +872,7 @@ int msk_quad_crop(ms_ctx *ctx, const uint8_t *pages, int n_pages, int img_h, int
             MS_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));                     \
             granted = smem;                                                                                            \
         }                                                                                                              \
-        kfn<<<(int)grid, kQcThreads, smem, st>>>(pages, img_h, img_w, qplans, plans, n, border_mode, border_value,     \
+        ms_launch(kfn, (int)grid, kQcThreads, smem, st, pages, img_h, img_w, qplans, plans, n, border_mode, border_value,     \
                                                  out_h, out_w, batch_f32, canvas_u8, vec_ok, list, cnt + 2);          \
     } while (0)
     if (batch_f32 && canvas_u8)
@@ -894,7 +899,7 @@ int msk_quad_warp(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const 
         ms_set_error("quad_warp: scratch too small");
         return MS_ERR_CAPACITY;
     }
-    quad_plan_kernel<<<1, 128, 0, st>>>(quad_dev, 8, nullptr, 1, 1, 0, 32, 128, qplan, plan, size, nullptr, img_h, img_w, 0,
+    ms_launch(quad_plan_kernel, 1, 128, 0, st, quad_dev, 8, nullptr, 1, 1, 0, 32, 128, qplan, plan, size, nullptr, img_h, img_w, 0,
                                         nullptr, nullptr);
     MS_LAUNCH_CHECK(ctx);
     int32_t hs[2] = {0, 0};
@@ -910,7 +915,7 @@ int msk_quad_warp(ms_ctx *ctx, const uint8_t *page, int img_h, int img_w, const 
     }
     int64_t grid = ((int64_t)hs[0] * hs[1] + 255) / 256;
     if (grid > (int64_t)ctx->num_sms * 8) grid = (int64_t)ctx->num_sms * 8;
-    quad_warp_kernel<<<(int)grid, 256, 0, st>>>(page, img_h, img_w, qplan, border_mode, border_value, patch_dev);
+    ms_launch(quad_warp_kernel, (int)grid, 256, 0, st, page, img_h, img_w, qplan, border_mode, border_value, patch_dev);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }

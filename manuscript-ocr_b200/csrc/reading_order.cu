@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_kernel(const float *
                                                                    int32_t *__restrict__ need_large,
                                                                    int32_t *__restrict__ ticket, int force_large)
 {
+    ms_pdl_wait();
     extern __shared__ __align__(16) unsigned char ro_smem[];
     int4 *box = reinterpret_cast<int4 *>(ro_smem);                                   // kRoMaxBoxes
     uint32_t *pairs = reinterpret_cast<uint32_t *>(ro_smem + kRoMaxBoxes * 16);      // kRoMaxPairs
@@ -1468,6 +1469,7 @@ __global__ void __launch_bounds__(kRoThreads) reading_order_large_kernel(const f
                                                                          unsigned char *__restrict__ slots,
                                                                          size_t slot_bytes)
 {
+    ms_pdl_wait();
     __shared__ RlShared S;
     for (;;) {
         __syncthreads();  // the previous page's shared state is no longer read
@@ -1528,7 +1530,7 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
         MS_CUDA(cudaFuncSetAttribute(reading_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ctx->smem_attr[3] = (int)smem;
     }
-    reading_order_kernel<<<n_pages, kRoThreads, smem, st>>>(boxes8, row_stride, counts, cap_per_page, obox, order,
+    ms_launch(reading_order_kernel, n_pages, kRoThreads, smem, st, boxes8, row_stride, counts, cap_per_page, obox, order,
                                                            reordered, flags, gpairs16, gbox32, need_large,
                                                            need_large ? need_large + n_pages : nullptr,
                                                            slots ? ctx->ro_force_large : 0);
@@ -1539,7 +1541,7 @@ int msk_reading_order(ms_ctx *ctx, const float *boxes8, int row_stride, const in
             MS_CUDA(cudaFuncSetAttribute(reading_order_large_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_l));
             ctx->smem_attr[7] = smem_l;
         }
-        reading_order_large_kernel<<<slots, kRoThreads, smem_l, st>>>(boxes8, row_stride, counts, cap_per_page, n_pages, order,
+        ms_launch(reading_order_large_kernel, slots, kRoThreads, smem_l, st, boxes8, row_stride, counts, cap_per_page, n_pages, order,
                                                                 reordered, flags, need_large, need_large + n_pages,
                                                                 slot_mem, slot_bytes);
         MS_LAUNCH_CHECK(ctx);

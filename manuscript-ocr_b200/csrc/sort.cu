@@ -25,6 +25,7 @@ __global__ void __launch_bounds__(kThreads) seg_hist_kernel(const uint32_t *__re
                                                             const int32_t *__restrict__ seg_len, int skip_le,
                                                             int tiles_max, int shift, int32_t *__restrict__ hist)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     const int p0 = page_off[page], n = seg_len ? seg_len[page] : page_off[page + 1] - p0;
     if (n <= skip_le) return;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(kThreads) seg_scatter_kernel(const uint32_t *_
                                                                uint32_t *__restrict__ keys_out,
                                                                uint32_t *__restrict__ vals_out)
 {
+    ms_pdl_wait();
     const int page = blockIdx.y;
     const int p0 = page_off[page], n = seg_len ? seg_len[page] : page_off[page + 1] - p0;
     if (n <= skip_le) return;
@@ -177,9 +179,9 @@ int msk_sort_pages(ms_ctx *ctx, uint32_t *keys, uint32_t *vals, uint32_t *keys_t
     if (gx < 1) gx = 1;
     const dim3 grid(gx, n_pages);
     for (int pass = 0; pass < 4; pass++) {
-        seg_hist_kernel<<<grid, kThreads, 0, st>>>(kin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist);
+        ms_launch(seg_hist_kernel, grid, kThreads, 0, st, kin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist);
         MS_LAUNCH_CHECK(ctx);
-        seg_scatter_kernel<<<grid, kThreads, 0, st>>>(kin, vin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist, kout,
+        ms_launch(seg_scatter_kernel, grid, kThreads, 0, st, kin, vin, page_off, seg_len, skip_le, tiles_max, 8 * pass, hist, kout,
                                                       vout);
         MS_LAUNCH_CHECK(ctx);
         uint32_t *t = kin;

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(kTpsThreads) tps_rectify_kernel(const float *_
                                                                    int in_h, int in_w, int out_h, int out_w,
                                                                    float *__restrict__ out)
 {
+    ms_pdl_wait();
     __shared__ double s_t[kTpsMaxK][2];
     const int b = blockIdx.y, K = n_fid + 3, n = out_h * out_w;
     // T = inv_delta_C[:, :F] @ C'   (the three appended rows of zeros contribute nothing)
@@ -83,7 +84,7 @@ int msk_tps_rectify(ms_ctx *ctx, const float *input, const float *c_prime, const
     }
     const int n = out_h * out_w;
     dim3 grid((n + kTpsThreads - 1) / kTpsThreads, batch);
-    tps_rectify_kernel<<<grid, kTpsThreads, 0, st>>>(input, c_prime, inv_delta_c, p_hat_t, n_fid, chans, in_h, in_w, out_h,
+    ms_launch(tps_rectify_kernel, grid, kTpsThreads, 0, st, input, c_prime, inv_delta_c, p_hat_t, n_fid, chans, in_h, in_w, out_h,
                                                     out_w, out);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;

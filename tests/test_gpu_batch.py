@@ -458,3 +458,50 @@ def test_front_stages_as_two_concurrent_halves(torch_cuda):
                 _, _, want_boxes, want_rects = oracle_page(score[pg], geo[pg], imgs[pg], page)
                 np.testing.assert_array_equal(wb[pg, : wc[pg]], want_boxes)
                 np.testing.assert_array_equal(wcr[wcr[:, 0] == pg][:, 1:], want_rects)
+
+
+_PDL_CHILD = r"""
+import hashlib, os, sys
+sys.path[:0] = [ROOT, os.path.join(ROOT, "manuscript-ocr_b200")]
+import numpy as np, torch
+import manuscript_b200 as mb, synthdata
+page, n_pages = 512, 18
+score, geo, imgs = synthdata.make_batch(list(range(700, 700 + n_pages)), page, 70)
+d = [torch.from_numpy(x).cuda() for x in (score, geo, imgs)]
+h = hashlib.sha256()
+for ro in (0, 1):
+    runner = mb.PageBatch(device=0, params=mb.EastParams.default(target_size=page, sort_reading_order=ro), cap_boxes=512)
+    for rep in range(3):  # direct launches, graph capture, graph replay
+        r = runner.run(*d)
+        torch.cuda.synchronize()
+        n = int(r.n_crops.cpu()[0])
+        cnt = r.box_counts.cpu().numpy()
+        h.update(cnt.tobytes()); h.update(r.flags.cpu().numpy().tobytes())
+        for pg in range(n_pages):
+            h.update(r.boxes[pg, : cnt[pg]].cpu().numpy().tobytes())
+        h.update(r.crops[:n].cpu().numpy().tobytes()); h.update(r.batch[:n].cpu().numpy().tobytes())
+print("DIGEST", h.hexdigest(), int(cnt.sum()), n)
+"""
+
+
+def test_programmatic_dependent_launch_changes_nothing(torch_cuda):
+    """Every kernel is launched as a programmatic dependent launch and waits (griddepcontrol.wait) before it touches
+    memory.  The switch is read once per process, so the same batch -- two concurrent halves, with and without the
+    reading-order stage, direct launches and graph replay -- runs in two child processes, with MS_B200_NO_PDL=1 and
+    without, and must give the same bits."""
+    import os
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = {}
+    for tag, extra in (("pdl", {}), ("plain", {"MS_B200_NO_PDL": "1"})):
+        env = dict(os.environ, **extra)
+        env.pop("MS_B200_NO_PDL", None) if not extra else None
+        p = subprocess.run([sys.executable, "-c", f"ROOT = {root!r}\n" + _PDL_CHILD], env=env, capture_output=True,
+                           text=True, timeout=600)
+        assert p.returncode == 0, p.stderr[-2000:]
+        line = [ln for ln in p.stdout.splitlines() if ln.startswith("DIGEST")][-1].split()
+        out[tag] = line[1:]
+    assert out["pdl"] == out["plain"], out
+    assert int(out["pdl"][1]) > 500 and int(out["pdl"][2]) > 500

@@ -78,6 +78,32 @@ __global__ void __launch_bounds__(224, 4) split_kernel(float *out, size_t canvas
     }
 }
 
+// the same split with the pixel part written kVec floats per lane (8- or 16-byte stores): what a consumer mapping with 2 or
+// 4 adjacent columns per thread would issue
+template <int kPix, int kVec>
+__global__ void __launch_bounds__(224, 4) split_vec_kernel(float *out, size_t canvases)
+{
+    constexpr int kTail4 = (128 - kPix) / 4, kPv = kPix / kVec;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp > 5) return;
+    for (size_t c = blockIdx.x; c < canvases; c += gridDim.x) {
+        float *cv = out + c * 96 * 128;
+        if (warp == 0) {
+            const float4 one = make_float4(1.f, 1.f, 1.f, 1.f);
+            for (int i = lane; i < 96 * kTail4; i += 32)
+                __stcs(reinterpret_cast<float4 *>(cv + (i / kTail4) * 128 + kPix) + i % kTail4, one);
+        } else {
+            for (int i = (warp - 1) * 32 + lane; i < 96 * kPv; i += 160) {
+                float *at = cv + (i / kPv) * 128 + (i % kPv) * kVec;
+                if (kVec == 2)
+                    __stcs(reinterpret_cast<float2 *>(at), make_float2(0.5f, 0.5f));
+                else
+                    __stcs(reinterpret_cast<float4 *>(at), make_float4(0.5f, 0.5f, 0.5f, 0.5f));
+            }
+        }
+    }
+}
+
 // modes 3 / 4: whole canvases (or quarter canvases) as TMA bulk stores out of shared memory, one elected thread per CTA,
 // `depth` stores in flight
 __global__ void __launch_bounds__(224, 4) bulk_kernel(float *out, size_t canvases, int piece_bytes, int depth)
@@ -101,6 +127,33 @@ __global__ void __launch_bounds__(224, 4) bulk_kernel(float *out, size_t canvase
             else
                 asm volatile("cp.async.bulk.wait_group.read 3;" ::: "memory");
         }
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+// mode 6: pixel part of every canvas row by five warps with 4-byte stores (as the crop kernel's consumers write it), the
+// padding tails of the SAME canvas at the same time as TMA tensor stores issued by one more thread
+__global__ void __launch_bounds__(224, 4) mixed_kernel(const __grid_constant__ Maps2 maps, float *out, size_t canvases, int pix)
+{
+    extern __shared__ __align__(128) unsigned char sm[];
+    float *ones = reinterpret_cast<float *>(sm);
+    for (int i = threadIdx.x; i < 8 * (128 - pix); i += blockDim.x) ones[i] = 1.f;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (warp > 5) return;
+    const unsigned sones = (unsigned)__cvta_generic_to_shared(ones);
+    for (size_t c = blockIdx.x; c < canvases; c += gridDim.x) {
+        float *cv = out + c * 96 * 128;
+        if (warp == 0) {
+            if (lane < 12)
+                asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(&maps.tail),
+                             "r"(pix), "r"((int)(c * 96) + 8 * lane), "r"(sones)
+                             : "memory");
+            asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        } else {
+            for (int i = (warp - 1) * 32 + lane; i < 96 * pix; i += 160) __stcs(cv + (i / pix) * 128 + i % pix, 0.5f);
+        }
+    }
     asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
@@ -156,6 +209,37 @@ int main()
             printf("split pattern, %d pixel floats + %d padding floats per row (padding warp + 5 pixel warps): %.3f ms  %.0f GB/s written\n",
                    pix, 128 - pix, best, (double)canvases * 96 * 512 / best / 1e6);
         }
+        for (int vec : {2, 4}) {
+            best = 1e9f;
+            for (int rep = 0; rep < 4; rep++) {
+                cudaEventRecord(e0);
+                if (vec == 2)
+                    split_vec_kernel<40, 2><<<592, 224>>>(reinterpret_cast<float *>(buf), canvases);
+                else
+                    split_vec_kernel<40, 4><<<592, 224>>>(reinterpret_cast<float *>(buf), canvases);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            printf("split pattern, 40 pixel floats written %d per lane (%d-byte stores) + 88 padding floats: %.3f ms  %.0f GB/s written\n",
+                   vec, 4 * vec, best, (double)canvases * 96 * 512 / best / 1e6);
+        }
+        {
+            best = 1e9f;
+            for (int rep = 0; rep < 4; rep++) {
+                cudaEventRecord(e0);
+                split_kernel<40><<<592, 224>>>(reinterpret_cast<float *>(buf), canvases);
+                cudaEventRecord(e1);
+                cudaEventSynchronize(e1);
+                float ms;
+                cudaEventElapsedTime(&ms, e0, e1);
+                if (ms < best) best = ms;
+            }
+            printf("split pattern, 40 pixel floats written 1 per lane (4-byte stores) + 88 padding floats: %.3f ms  %.0f GB/s written\n",
+                   best, (double)canvases * 96 * 512 / best / 1e6);
+        }
         cudaFuncSetAttribute(bulk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 512);
         for (int piece : {96 * 512, 24 * 512, 8 * 512})
             for (int depth : {1, 2, 4}) {
@@ -210,6 +294,20 @@ int main()
                 }
                 printf("TMA tensor stores: pixel box %d x 96 + 12 tail boxes %d x 8 per canvas, %d in flight: %.3f ms  %.0f GB/s written (%s)\n",
                        pix, 128 - pix, depth, best, (double)canvases * 96 * 512 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+                if (depth == 1 && pix < 128) {
+                    best = 1e9f;
+                    for (int rep = 0; rep < 4; rep++) {
+                        cudaEventRecord(e0);
+                        mixed_kernel<<<592, 224, 8 * (128 - pix) * 4>>>(maps, reinterpret_cast<float *>(buf), canvases, pix);
+                        cudaEventRecord(e1);
+                        cudaEventSynchronize(e1);
+                        float ms;
+                        cudaEventElapsedTime(&ms, e0, e1);
+                        if (ms < best) best = ms;
+                    }
+                    printf("mixed: %d pixel floats per row by 4-byte stores of five warps + the tails as TMA tensor stores, same canvas: %.3f ms  %.0f GB/s written (%s)\n",
+                           pix, best, (double)canvases * 96 * 512 / best / 1e6, cudaGetErrorString(cudaGetLastError()));
+                }
             }
     }
     float best = 1e9f;

@@ -10,6 +10,7 @@ For every kernel: instruction count and the opcodes that show which hardware pat
   FADD2/FMUL2/FFMA2 packed float32 pairs (FFMA2 must be 0: a fused multiply-add would break bit-exactness)
   FFMA              fused float32 multiply-add (only inside division / sqrt sequences; the library is built --fmad=false)
   HMMA/UTC*MMA      tensor cores (none: no stage of this path is a dense contraction)
+  ACQBULK           griddepcontrol.wait: every kernel is a programmatic dependent launch and waits for its predecessor
 """
 import collections
 import os
@@ -20,7 +21,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "manuscript-ocr_b200", "manuscript_b200", "libmanuscript_b200.so")
 WATCH = ["UBLKCP", "UTMALDG", "SYNCS", "UCGABAR", "NANOSLEEP", "ATOMG", "RED", "ATOMS", "DADD", "DMUL", "DFMA", "FADD2",
-         "FMUL2", "FFMA2", "FFMA", "FADD", "FMUL", "LDS", "STS", "LDG", "STG", "PRMT", "SHFL", "VOTE", "BAR", "HMMA", "UTC"]
+         "FMUL2", "FFMA2", "FFMA", "FADD", "FMUL", "LDS", "STS", "LDG", "STG", "PRMT", "SHFL", "VOTE", "BAR", "HMMA", "UTC", "ACQBULK"]
 
 
 def demangle(names):

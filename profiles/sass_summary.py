@@ -48,7 +48,7 @@ def main():
     names = demangle(list(kernels))
     print(f"# {os.path.relpath(so, ROOT)}: {len(kernels)} kernels, sm_100a SASS (cuobjdump -sass), opcode counts per kernel")
     cols = ["UBLKCP", "SYNCS", "UCGABAR", "NANOSLEEP", "ATOMG", "DFMA", "DMUL", "DADD", "FADD2", "FMUL2", "FFMA2", "FFMA",
-            "FADD", "FMUL", "PRMT", "LDS", "SHFL", "HMMA", "UTC"]
+            "FADD", "FMUL", "PRMT", "LDS", "SHFL", "HMMA", "UTC", "ACQBULK"]
     print(f"{'kernel':58s} {'instr':>6s} " + " ".join(f"{c:>6s}" for c in cols))
     tot = collections.Counter()
     for (mangled, cnt), name in sorted(zip(kernels.items(), names), key=lambda t: t[1]):
@@ -56,7 +56,8 @@ def main():
         tot.update(cnt)
     print(f"{'TOTAL':58s} {tot['_total']:6d} " + " ".join(f"{tot[c]:6d}" for c in cols))
     print("\nUTMALDG (tensor-map TMA):", tot["UTMALDG"], "| tensor-core opcodes (HMMA / UTC*MMA):", tot["HMMA"] + tot["UTC"],
-          "| FFMA2 (must be 0):", tot["FFMA2"])
+          "| FFMA2 (must be 0):", tot["FFMA2"], "| kernels without griddepcontrol.wait (ACQBULK):",
+          sum(1 for c in kernels.values() if c["ACQBULK"] == 0))
 
 
 if __name__ == "__main__":

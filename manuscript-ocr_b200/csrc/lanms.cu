@@ -338,7 +338,7 @@ __device__ __forceinline__ int block_excl_scan_1024(int v, int *s_warp, int &tot
 }
 
 // 4a. one CTA per page: the page's hot positions in order, the accepted runs among them (a run is accepted iff its
-//     head lies beyond the end of the last accepted run -- a sequential walk, done by one thread over shared memory),
+//     head lies beyond the end of the last accepted run -- a greedy chain, marked by pointer doubling in shared memory),
 //     and for every accepted run the number of merged positions before it.  Clusters = positions outside the runs.
 constexpr int kAcceptBatch = 2048;  // hot positions walked per round out of shared memory
 
@@ -348,8 +348,9 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
     const int page = blockIdx.x;
     const int p0 = page_off[page], p1 = page_off[page + 1];
     __shared__ int s_warp[33];
-    __shared__ int s_h[kAcceptBatch], s_e[kAcceptBatch], s_sel[kAcceptBatch];
-    __shared__ int s_klast, s_nacc, s_merged, s_nv;
+    __shared__ int s_h[kAcceptBatch], s_e[kAcceptBatch], s_sel[kAcceptBatch], s_ptr[kAcceptBatch];
+    __shared__ unsigned char s_mark[kAcceptBatch];
+    __shared__ int s_klast, s_nacc, s_merged, s_nv, s_root;
     int32_t *hot_sorted = B.cl_cell + p0;  // scratch until the neighbour grid is built
     int32_t *acc_h = B.kept_list + p0, *acc_e = B.nb_cnt + p0, *acc_pm = B.sb_id + p0;
     if (threadIdx.x == 0) {
@@ -390,29 +391,80 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
             s_e[j] = B.run_end[h];
         }
         __syncthreads();
+        // Which runs are accepted is a greedy chain: run j is accepted iff its head lies beyond the end of the last
+        // accepted run, i.e. the accepted runs are root, next(root), next(next(root)), ... with
+        // next(j) = first j' with h[j'] > e[j] (the heads are ascending: a binary search), root = first j with
+        // h[j] > klast.  A one-thread walk of that chain was 50 us per launch (one dependent step per hot position);
+        // here every position finds its successor at once and the chain is marked by pointer doubling: in round r
+        // every marked position marks its 2^r-th successor, then the successor table is squared.  ceil(log2(nb))
+        // rounds, each a few shared-memory accesses per thread.  (Marks only ever go from 0 to 1 and the marked set is
+        // closed under next, so a position marked in the middle of a round may take part in it at once.)
+        for (int j = threadIdx.x; j < nb; j += kResolveThreads) {
+            const int key = s_e[j];  // first j' with s_h[j'] > key; j' > j because e >= h
+            int lo = j + 1, hi = nb;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_h[mid] > key)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            s_ptr[j] = lo;
+            s_mark[j] = 0;
+        }
         if (threadIdx.x == 0) {
-            // The walk is one dependent chain and a lone warp issues an instruction every 5-6 cycles: it keeps to a
-            // compare, a select and one predicated store per position (which positions are accepted); everything
-            // else about an accepted run is computed by the whole CTA afterwards.  Positions are read four ahead.
-            int klast = s_klast, nv = 0;
-            for (int j = 0; j < nb; j += 4) {
-                int h[4], e[4];
+            const int klast = s_klast;
+            int lo = 0, hi = nb;
+            while (lo < hi) {
+                const int mid = (lo + hi) >> 1;
+                if (s_h[mid] > klast)
+                    hi = mid;
+                else
+                    lo = mid + 1;
+            }
+            s_root = lo;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0 && s_root < nb) s_mark[s_root] = 1;
+        __syncthreads();
+        for (int span = 1; span < nb; span <<= 1) {
+            int nxt[kAcceptBatch / kResolveThreads];
 #pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    const bool in = j + u < nb;
-                    h[u] = in ? s_h[j + u] : INT_MIN;  // never beyond klast
-                    e[u] = in ? s_e[j + u] : 0;
-                }
-#pragma unroll
-                for (int u = 0; u < 4; u++) {
-                    if (h[u] > klast) {
-                        klast = e[u];
-                        s_sel[nv++] = j + u;
+            for (int u = 0; u < kAcceptBatch / kResolveThreads; u++) {
+                const int j = threadIdx.x + u * kResolveThreads;
+                nxt[u] = nb;
+                if (j < nb) {
+                    const int p = s_ptr[j];
+                    if (p < nb) {
+                        if (s_mark[j]) s_mark[p] = 1;
+                        nxt[u] = s_ptr[p];
                     }
                 }
             }
-            s_klast = klast;
-            s_nv = nv;
+            __syncthreads();  // every s_ptr[p] of this round has been read
+#pragma unroll
+            for (int u = 0; u < kAcceptBatch / kResolveThreads; u++) {
+                const int j = threadIdx.x + u * kResolveThreads;
+                if (j < nb) s_ptr[j] = nxt[u];
+            }
+            __syncthreads();
+        }
+        // the marked positions in order -> s_sel; the last one's end is where the next batch continues
+        {
+            int nv_run = 0;
+            for (int t0 = 0; t0 < nb; t0 += kResolveThreads) {
+                const int j = t0 + threadIdx.x;
+                const int m = (j < nb && s_mark[j]) ? 1 : 0;
+                int total;
+                const int pos = block_excl_scan_1024(m, s_warp, total);
+                if (m) s_sel[nv_run + pos] = j;
+                nv_run += total;
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                s_nv = nv_run;
+                if (nv_run > 0) s_klast = s_e[s_sel[nv_run - 1]];
+            }
         }
         __syncthreads();
         const int nv = s_nv;

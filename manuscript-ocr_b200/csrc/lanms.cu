@@ -275,16 +275,31 @@ __global__ void __launch_bounds__(128) lanms_runs_kernel(const int32_t *__restri
     ms_pdl_wait();
     const int nh = *B.hot_count;
     double buf[4 * MS_MAXV];
-    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < nh; j += gridDim.x * blockDim.x) {
-        const int h = B.hot_list[j];
-        const int page_end = page_off[B.pos_page[h] + 1];
-        double L[8], nb[8], al[8];
-        load_quad(B.sq + (size_t)(h - 1) * 8, L);
-        double wsum = (double)B.ss[h - 1];
-        double score = wsum;
-        int i = h;
-        load_quad(B.sq + (size_t)i * 8, nb);
-        while (true) {
+    // Runs differ in length (most end at their first IoU test, a few swallow a whole word) and one step of a run is a
+    // float64 polygon clip: with a run per loop trip the lanes of a warp waited for its longest run (8 of 32 lanes active
+    // on average).  Here a lane that finishes its run takes the next one of its own strided list at once, so the lanes
+    // of a warp are at different steps of different runs and the clip runs nearly full; the steps of a run and their
+    // order are unchanged.
+    const int stride = gridDim.x * blockDim.x;
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    bool active = false;
+    int h = 0, i = 0, page_end = 0;
+    double L[8], nb[8], al[8];
+    double wsum = 0.0, score = 0.0;
+    while (true) {
+        if (!active && j < nh) {
+            h = B.hot_list[j];
+            j += stride;
+            page_end = page_off[B.pos_page[h] + 1];
+            load_quad(B.sq + (size_t)(h - 1) * 8, L);
+            wsum = (double)B.ss[h - 1];
+            score = wsum;
+            i = h;
+            load_quad(B.sq + (size_t)i * 8, nb);
+            active = true;
+        }
+        if (!__any_sync(0xffffffffu, active)) break;
+        if (active) {
             // merge box i into the running cluster (lanms.py:181-188)
             double sc = (double)B.ss[i];
             ms_align_vertices(L, nb, al);
@@ -294,15 +309,20 @@ __global__ void __launch_bounds__(128) lanms_runs_kernel(const int32_t *__restri
             wsum = tw;
             score = (sc > score) ? sc : score;  // python max(old, new)
             i++;
-            if (i >= page_end) break;
-            load_quad(B.sq + (size_t)i * 8, nb);
-            if (!(ms_quad_iou(nb, L, buf) > thr)) break;
-        }
-        B.run_end[h] = i;
-        double2 *dst = reinterpret_cast<double2 *>(B.run_poly + (size_t)h * 8);
+            bool fin = i >= page_end;
+            if (!fin) {
+                load_quad(B.sq + (size_t)i * 8, nb);
+                fin = !(ms_quad_iou(nb, L, buf) > thr);
+            }
+            if (fin) {
+                B.run_end[h] = i;
+                double2 *dst = reinterpret_cast<double2 *>(B.run_poly + (size_t)h * 8);
 #pragma unroll
-        for (int k = 0; k < 4; k++) dst[k] = make_double2(L[2 * k], L[2 * k + 1]);
-        B.run_score[h] = score;
+                for (int k = 0; k < 4; k++) dst[k] = make_double2(L[2 * k], L[2 * k + 1]);
+                B.run_score[h] = score;
+                active = false;
+            }
+        }
     }
 }
 

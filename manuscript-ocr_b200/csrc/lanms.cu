@@ -417,8 +417,8 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
         // h[j] > klast.  A one-thread walk of that chain was 50 us per launch (one dependent step per hot position);
         // here every position finds its successor at once and the chain is marked by pointer doubling: in round r
         // every marked position marks its 2^r-th successor, then the successor table is squared.  ceil(log2(nb))
-        // rounds, each a few shared-memory accesses per thread.  (Marks only ever go from 0 to 1 and the marked set is
-        // closed under next, so a position marked in the middle of a round may take part in it at once.)
+        // rounds, each a few shared-memory accesses per thread.  (Before round r every position within 2^r steps of the
+        // root is marked; round r marks those within 2^(r+1).)
         for (int j = threadIdx.x; j < nb; j += kResolveThreads) {
             const int key = s_e[j];  // first j' with s_h[j'] > key; j' > j because e >= h
             int lo = j + 1, hi = nb;
@@ -448,23 +448,27 @@ __global__ void __launch_bounds__(kResolveThreads) lanms_accept_kernel(const int
         if (threadIdx.x == 0 && s_root < nb) s_mark[s_root] = 1;
         __syncthreads();
         for (int span = 1; span < nb; span <<= 1) {
-            int nxt[kAcceptBatch / kResolveThreads];
+            // read phase (marks and successors as they stand), barrier, write phase: no location is read and written
+            // in the same phase; several threads may store the same 1 into a mark
+            int nxt[kAcceptBatch / kResolveThreads], tgt[kAcceptBatch / kResolveThreads];
 #pragma unroll
             for (int u = 0; u < kAcceptBatch / kResolveThreads; u++) {
                 const int j = threadIdx.x + u * kResolveThreads;
                 nxt[u] = nb;
+                tgt[u] = -1;
                 if (j < nb) {
                     const int p = s_ptr[j];
                     if (p < nb) {
-                        if (s_mark[j]) s_mark[p] = 1;
+                        if (s_mark[j]) tgt[u] = p;
                         nxt[u] = s_ptr[p];
                     }
                 }
             }
-            __syncthreads();  // every s_ptr[p] of this round has been read
+            __syncthreads();
 #pragma unroll
             for (int u = 0; u < kAcceptBatch / kResolveThreads; u++) {
                 const int j = threadIdx.x + u * kResolveThreads;
+                if (tgt[u] >= 0) s_mark[tgt[u]] = 1;
                 if (j < nb) s_ptr[j] = nxt[u];
             }
             __syncthreads();

@@ -559,7 +559,7 @@ __global__ void __launch_bounds__(kContainThreads) east_contain_kernel(const int
 }
 
 // 3) one CTA per page: the rare sequential leftovers, then anomaly removal -> axis align -> write.
-__global__ void __launch_bounds__(512) east_finish_kernel(const int32_t *__restrict__ counts, int cap,
+__global__ void __launch_bounds__(1024) east_finish_kernel(const int32_t *__restrict__ counts, int cap,
                                                           ms_east_params P, EastScratch S, float *__restrict__ out,
                                                           int out_cap, int32_t *__restrict__ counts_out,
                                                           int32_t *__restrict__ flags)
@@ -792,7 +792,7 @@ __global__ void word_rects_flat_kernel(const float *__restrict__ polys8, int64_t
 }
 
 // one CTA per page: ordered compaction of valid crops into a page-strided temp list
-__global__ void __launch_bounds__(256) word_rects_page_kernel(const float *__restrict__ quads,
+__global__ void __launch_bounds__(1024) word_rects_page_kernel(const float *__restrict__ quads,
                                                               const int32_t *__restrict__ counts, int cap,
                                                               const int32_t *__restrict__ img_hw, int img_h, int img_w,
                                                               int min_text, int32_t *__restrict__ tmp,
@@ -950,7 +950,7 @@ int msk_east_boxes(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
     ms_launch(east_contain_kernel, dim3(gx, n_pages), kContainThreads, 0, st, counts, cap_per_page, S);  // dense pages only
     MS_LAUNCH_CHECK(ctx);
     // device recursion in np_pairwise_f32: depth <= log2(cap/128) + 1 frames of a few dozen bytes
-    ms_launch(east_finish_kernel, n_pages, 512, 0, st, counts, cap_per_page, *p, S, quads_out, out_cap, counts_out, flags);
+    ms_launch(east_finish_kernel, n_pages, 1024, 0, st, counts, cap_per_page, *p, S, quads_out, out_cap, counts_out, flags);
     MS_LAUNCH_CHECK(ctx);
     return MS_OK;
 }
@@ -971,7 +971,7 @@ int msk_word_rects(ms_ctx *ctx, const float *quads, const int32_t *counts, int n
         ms_set_error("word_rects: scratch too small");
         return MS_ERR_CAPACITY;
     }
-    ms_launch(word_rects_page_kernel, n_pages, 256, 0, st, quads, counts, cap_per_page, img_hw, img_h, img_w, min_text_size,
+    ms_launch(word_rects_page_kernel, n_pages, 1024, 0, st, quads, counts, cap_per_page, img_hw, img_h, img_w, min_text_size,
                                                     tmp, page_n);
     MS_LAUNCH_CHECK(ctx);
     ms_launch(word_rects_offsets_kernel, 1, 32, 0, st, page_n, n_pages, page_off, crops_cap, n_crops, append, range);

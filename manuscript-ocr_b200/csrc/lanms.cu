@@ -225,22 +225,32 @@ __global__ void __launch_bounds__(128) lanms_gather_hot_kernel(const float *__re
     for (int s0 = blockIdx.x * blockDim.x; s0 < n; s0 += stride) {  // warp-uniform trip count
         const int s = s0 + threadIdx.x;
         bool need = false;
+        // the row of position s, and its predecessor's from the lane below (lane 0 reads it itself)
+        float r[8], pr[8];
+        const float *row = quads + (size_t)(s < n ? vals[s] : 0) * 9;
+#pragma unroll
+        for (int k = 0; k < 8; k++) r[k] = s < n ? row[k] : 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; k++) pr[k] = __shfl_up_sync(0xffffffffu, r[k], 1);
+        if (lane == 0 && s > 0 && s < n) {
+            const float *prow = quads + (size_t)vals[s - 1] * 9;
+#pragma unroll
+            for (int k = 0; k < 8; k++) pr[k] = prow[k];
+        }
         if (s < n) {
             const int page = B.pos_page[s];
-            const float *row = quads + (size_t)vals[s] * 9;
             double me[8];
 #pragma unroll
-            for (int k = 0; k < 8; k++) me[k] = (double)row[k];
+            for (int k = 0; k < 8; k++) me[k] = (double)r[k];
             double2 *dst = reinterpret_cast<double2 *>(B.sq + (size_t)s * 8);
 #pragma unroll
             for (int k = 0; k < 4; k++) dst[k] = make_double2(me[2 * k], me[2 * k + 1]);
             B.ss[s] = row[8];
             B.hot[s] = 0;
             if (s > page_off[page]) {
-                const float *prow = quads + (size_t)vals[s - 1] * 9;
                 double pv[8];
 #pragma unroll
-                for (int k = 0; k < 8; k++) pv[k] = (double)prow[k];
+                for (int k = 0; k < 8; k++) pv[k] = (double)pr[k];
                 bool disjoint = false;
                 float4 pb;
                 if (thr >= 0.0 && quad_regular_bbox(pv, pb)) {
